@@ -1,0 +1,127 @@
+// Shared infrastructure of libb200lbfgs.so: status/error plumbing, the context object
+// (device, stream, NCCL communicator), launch accounting and warp/block reductions.
+#pragma once
+
+#include "../../include/b200_lbfgs.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<long> g_launches;
+
+#define B200_CUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));  \
+      return B200_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+#define B200_TRY(call)            \
+  do {                            \
+    int _s = (call);              \
+    if (_s != B200_OK) return _s; \
+  } while (0)
+
+#define B200_REQUIRE(cond, msg)                                        \
+  do {                                                                 \
+    if (!(cond)) {                                                     \
+      ::b200::set_error("%s:%d: %s", __FILE__, __LINE__, msg);        \
+      return B200_ERR_INVALID;                                         \
+    }                                                                  \
+  } while (0)
+
+// every kernel launch in the library goes through this so b200_launch_count() is exact
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
+    ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
+    B200_CUDA(cudaGetLastError());                                              \
+  } while (0)
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---- NCCL, loaded lazily with dlopen so the single-GPU path has no NCCL dependency -------------
+struct NcclApi;
+NcclApi *nccl_api(); // nullptr (and error set) if libnccl cannot be loaded
+
+} // namespace b200
+
+// ---- context ---------------------------------------------------------------------------------------
+struct b200_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // multi-GPU (one process per GPU)
+  void *comm = nullptr; // ncclComm_t
+  int rank = 0, world = 1;
+  // small pinned host mailbox for scalar read-backs
+  double *h_scalars = nullptr; // 64 doubles, pinned
+  double *d_scalars = nullptr; // 64 doubles, device
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+};
+
+namespace b200 {
+
+int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev); // grad (float) + 1 double
+int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n);
+
+// ---- device helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in thread 0. `red` must hold >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (w == 0) {
+    v = (lane < nw) ? red[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+__device__ __forceinline__ float act_apply(int act, float v) {
+  switch (act) {
+  case B200_ACT_TANH: return tanhf(v);
+  case B200_ACT_RELU: return v > 0.0f ? v : 0.0f;
+  case B200_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+  default: return v;
+  }
+}
+// derivative from the POST-activation value, as the reference CUDA backend does
+// (src/cuda/kernels.cuh:109-133); equal to the CPU backend's prime(z) for all four activations.
+__device__ __forceinline__ float act_deriv_from_output(int act, float a) {
+  switch (act) {
+  case B200_ACT_TANH: return 1.0f - a * a;
+  case B200_ACT_RELU: return a > 0.0f ? 1.0f : 0.0f;
+  case B200_ACT_SIGMOID: return a * (1.0f - a);
+  default: return 1.0f;
+  }
+}
+
+} // namespace b200

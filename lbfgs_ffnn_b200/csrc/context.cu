@@ -1,0 +1,260 @@
+// Context, error plumbing, raw device memory and the NCCL bridge of libb200lbfgs.so.
+//
+// b200_ctx replaces cuda_mlp::CublasHandle (src/cuda/cublas_handle.cuh:22-39): where the reference
+// carries a cuBLAS handle on the legacy default stream, this carries a non-blocking stream, a pinned
+// scalar mailbox and (multi-GPU) an NCCL communicator. No cuBLAS is linked.
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h> // types only; the functions are resolved with dlopen (no link-time NCCL dependency)
+
+#include <cstring>
+#include <mutex>
+
+namespace b200 {
+
+static thread_local std::string t_error;
+std::atomic<long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_error = buf;
+}
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                                cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  static bool ok = false;
+  std::call_once(once, [] {
+    // if the host process (torch.distributed) already mapped an NCCL, the SONAME lookup returns that one
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+#define B200_SYM(field, sym)                                              \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym)); \
+  if (!api.field) return;
+    B200_SYM(GetUniqueId, "ncclGetUniqueId")
+    B200_SYM(CommInitRank, "ncclCommInitRank")
+    B200_SYM(CommDestroy, "ncclCommDestroy")
+    B200_SYM(AllReduce, "ncclAllReduce")
+    B200_SYM(ReduceScatter, "ncclReduceScatter")
+    B200_SYM(AllGather, "ncclAllGather")
+    B200_SYM(GroupStart, "ncclGroupStart")
+    B200_SYM(GroupEnd, "ncclGroupEnd")
+    B200_SYM(GetErrorString, "ncclGetErrorString")
+#undef B200_SYM
+    ok = true;
+  });
+  if (!ok) {
+    set_error("NCCL could not be loaded (dlopen libnccl.so.2): %s", dlerror() ? dlerror() : "missing symbol");
+    return nullptr;
+  }
+  return &api;
+}
+
+#define B200_NCCL(api, call)                                                                   \
+  do {                                                                                         \
+    ncclResult_t _r = (call);                                                                  \
+    if (_r != ncclSuccess) {                                                                   \
+      ::b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, (api)->GetErrorString(_r)); \
+      return B200_ERR_COMM;                                                                    \
+    }                                                                                          \
+  } while (0)
+
+// sum-allreduce of the flat gradient and (optionally) the double loss scalar as ONE grouped NCCL launch
+int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev) {
+  if (ctx->world <= 1) return B200_OK;
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  B200_NCCL(api, api->GroupStart());
+  if (grad && n) B200_NCCL(api, api->AllReduce(grad, grad, n, ncclFloat, ncclSum, comm, ctx->stream));
+  if (loss_dev) B200_NCCL(api, api->AllReduce(loss_dev, loss_dev, 1, ncclDouble, ncclSum, comm, ctx->stream));
+  B200_NCCL(api, api->GroupEnd());
+  return B200_OK;
+}
+
+int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n) {
+  if (ctx->world <= 1) return B200_OK;
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  B200_NCCL(api, api->AllReduce(v, v, n, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  return B200_OK;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char *b200_last_error(void) { return t_error.c_str(); }
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200_ctx_create(int device, b200_ctx **out) {
+  B200_REQUIRE(out, "null out pointer");
+  int count = 0;
+  B200_CUDA(cudaGetDeviceCount(&count));
+  B200_REQUIRE(device >= 0 && device < count, "no such CUDA device (this library has no CPU fallback)");
+  B200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libb200lbfgs.so is built for sm_100a only", device, prop.major, prop.minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  b200_ctx *ctx = new b200_ctx;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  B200_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  B200_CUDA(cudaMallocHost(&ctx->h_scalars, sizeof(double) * 64));
+  B200_CUDA(cudaMalloc(&ctx->d_scalars, sizeof(double) * 64));
+  B200_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
+  B200_CUDA(cudaEventCreate(&ctx->ev_a));
+  B200_CUDA(cudaEventCreate(&ctx->ev_b));
+  *out = ctx;
+  return B200_OK;
+}
+
+int b200_ctx_destroy(b200_ctx *ctx) {
+  if (!ctx) return B200_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) {
+    if (NcclApi *api = nccl_api()) api->CommDestroy((ncclComm_t)ctx->comm);
+  }
+  cudaEventDestroy(ctx->ev_a);
+  cudaEventDestroy(ctx->ev_b);
+  cudaFreeHost(ctx->h_scalars);
+  cudaFree(ctx->d_scalars);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return B200_OK;
+}
+
+int b200_ctx_synchronize(b200_ctx *ctx) {
+  B200_REQUIRE(ctx, "null ctx");
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream) {
+  B200_REQUIRE(ctx, "null ctx");
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return B200_OK;
+}
+void *b200_ctx_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int b200_ctx_device(b200_ctx *ctx) { return ctx ? ctx->device : -1; }
+int b200_ctx_rank(b200_ctx *ctx) { return ctx ? ctx->rank : 0; }
+int b200_ctx_world(b200_ctx *ctx) { return ctx ? ctx->world : 1; }
+
+int b200_comm_unique_id(void *out_128_bytes) {
+  B200_REQUIRE(out_128_bytes, "null out pointer");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  ncclUniqueId id;
+  B200_NCCL(api, api->GetUniqueId(&id));
+  memcpy(out_128_bytes, &id, sizeof(id));
+  return B200_OK;
+}
+
+int b200_ctx_init_comm(b200_ctx *ctx, const void *unique_id_128_bytes, int rank, int world) {
+  B200_REQUIRE(ctx && unique_id_128_bytes, "null argument");
+  B200_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  B200_REQUIRE(!ctx->comm, "communicator already initialised");
+  if (world == 1) return B200_OK;
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  B200_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id_128_bytes, sizeof(id));
+  ncclComm_t comm;
+  B200_NCCL(api, api->CommInitRank(&comm, world, id, rank));
+  ctx->comm = comm;
+  ctx->rank = rank;
+  ctx->world = world;
+  return B200_OK;
+}
+
+int b200_ctx_allreduce_f32(b200_ctx *ctx, float *dev, size_t n) {
+  B200_REQUIRE(ctx && dev, "null argument");
+  return ctx_allreduce(ctx, dev, n, nullptr);
+}
+
+// ---- raw device memory (DeviceBuffer<T>, src/cuda/device_buffer.cuh:7-96) ------------------------
+int b200_malloc(void **dev, size_t bytes) {
+  B200_REQUIRE(dev, "null out pointer");
+  *dev = nullptr;
+  if (bytes == 0) return B200_OK;
+  B200_CUDA(cudaMalloc(dev, bytes));
+  return B200_OK;
+}
+int b200_free(void *dev) {
+  if (dev) B200_CUDA(cudaFree(dev));
+  return B200_OK;
+}
+int b200_memcpy_h2d(void *dev, const void *host, size_t bytes) {
+  if (bytes) {
+    B200_CUDA(cudaDeviceSynchronize()); // library work runs on a non-blocking stream the legacy stream does not order with
+    B200_CUDA(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+  }
+  return B200_OK;
+}
+int b200_memcpy_d2h(void *host, const void *dev, size_t bytes) {
+  if (bytes) {
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+  }
+  return B200_OK;
+}
+int b200_memcpy_d2d(void *dst, const void *src, size_t bytes) {
+  if (bytes) {
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    B200_CUDA(cudaDeviceSynchronize());
+  }
+  return B200_OK;
+}
+int b200_memset(void *dev, int value, size_t bytes) {
+  if (bytes) {
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemset(dev, value, bytes));
+    B200_CUDA(cudaDeviceSynchronize());
+  }
+  return B200_OK;
+}
+int b200_host_alloc_pinned(void **host, size_t bytes) {
+  B200_REQUIRE(host, "null out pointer");
+  B200_CUDA(cudaMallocHost(host, bytes ? bytes : 1));
+  return B200_OK;
+}
+int b200_host_free_pinned(void *host) {
+  if (host) B200_CUDA(cudaFreeHost(host));
+  return B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,507 @@
+// Kernels of the compact-form L-BFGS direction and the fused line-search vector operations.
+// See lbfgs_kernels.cuh for the algebra and the reference lines each kernel replaces.
+#include "lbfgs_kernels.cuh"
+
+#include <algorithm>
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ int ring_phys(int head, int count, int mod, int logical) {
+  int start = (head - count) % mod; // src/cuda/lbfgs.cuh:225-230
+  if (start < 0) start += mod;
+  return (start + logical) % mod;
+}
+
+__device__ __forceinline__ float4 ld4(const float *p, size_t i, size_t n, bool vec) {
+  if (vec && i + 3 < n) return __ldg(reinterpret_cast<const float4 *>(p + i));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i + 0 < n) v.x = __ldg(p + i + 0);
+  if (i + 1 < n) v.y = __ldg(p + i + 1);
+  if (i + 2 < n) v.z = __ldg(p + i + 2);
+  if (i + 3 < n) v.w = __ldg(p + i + 3);
+  return v;
+}
+__device__ __forceinline__ void st4(float *p, size_t i, size_t n, bool vec, float4 v) {
+  if (vec && i + 3 < n) {
+    *reinterpret_cast<float4 *>(p + i) = v;
+    return;
+  }
+  if (i + 0 < n) p[i + 0] = v.x;
+  if (i + 1 < n) p[i + 1] = v.y;
+  if (i + 2 < n) p[i + 2] = v.z;
+  if (i + 3 < n) p[i + 3] = v.w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1) batched GEMV over the ring. Each CTA streams tiles of kDotsTile elements: the tile of
+// g / s_new / y_new is staged once in shared memory (as doubles), then every warp owns the ring rows
+// r = warp, warp + 8, ... and accumulates its 5 dot products per row in fp64 registers across ALL tiles
+// of the CTA, so the shuffle reduction happens once per kernel, not once per tile.
+// RPW = rows per warp (compile-time so the accumulators stay in registers).
+// ------------------------------------------------------------------------------------------------
+template <int RPW, bool PAIR>
+__global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs a) {
+  __shared__ __align__(16) double sh_g[kDotsTile];
+  __shared__ __align__(16) double sh_s[PAIR ? kDotsTile : 2];
+  __shared__ __align__(16) double sh_y[PAIR ? kDotsTile : 2];
+  __shared__ int sh_rows[kMaxSlots];
+  __shared__ int sh_nrows, sh_w;
+  __shared__ double sh_red[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mp = a.st.h->mp, mod = a.st.h->mod;
+  if (tid == 0) {
+    int head = a.st.h->head, count = a.st.h->count;
+    if (a.reset_first) head = count = 0;
+    const int w = head;
+    int nr = 0;
+    for (int p = 0; p < mod; ++p) {
+      int rel = (p - (head - count)) % mod;
+      if (rel < 0) rel += mod;
+      const bool valid = rel < count;
+      if (valid || (PAIR && p == w)) sh_rows[nr++] = p;
+    }
+    sh_nrows = nr;
+    sh_w = w;
+  }
+  __syncthreads();
+  const int nrows = sh_nrows, w = sh_w;
+
+  const bool vec = ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.S) |
+                     reinterpret_cast<uintptr_t>(a.Y) | reinterpret_cast<uintptr_t>(a.x) |
+                     reinterpret_cast<uintptr_t>(a.x_prev) | reinterpret_cast<uintptr_t>(a.g_prev)) & 15u) == 0 &&
+                   (a.ld % 4 == 0);
+
+  double acc[RPW][kDotsCols];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int c = 0; c < kDotsCols; ++c) acc[r][c] = 0.0;
+  double gg = 0.0;
+
+  const size_t ntiles = (a.n + kDotsTile - 1) / kDotsTile;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t base = tile * kDotsTile;
+    __syncthreads(); // previous tile fully consumed
+    { // stage: one float4 per thread
+      const size_t i = base + (size_t)tid * 4;
+      const float4 g4 = ld4(a.g, i, a.n, vec);
+      if (a.row_begin == 0) gg += (double)g4.x * g4.x + (double)g4.y * g4.y + (double)g4.z * g4.z + (double)g4.w * g4.w;
+      sh_g[tid * 4 + 0] = g4.x; sh_g[tid * 4 + 1] = g4.y; sh_g[tid * 4 + 2] = g4.z; sh_g[tid * 4 + 3] = g4.w;
+      if constexpr (PAIR) {
+        float4 s4, y4;
+        if (a.mode == DOTS_FORM_PAIR && a.row_begin > 0) { // already formed and stored by the first launch
+          s4 = ld4(a.S + (size_t)w * a.ld, i, a.n, vec);
+          y4 = ld4(a.Y + (size_t)w * a.ld, i, a.n, vec);
+        } else if (a.mode == DOTS_FORM_PAIR) {
+          const float4 x4 = ld4(a.x, i, a.n, vec), xp4 = ld4(a.x_prev, i, a.n, vec), gp4 = ld4(a.g_prev, i, a.n, vec);
+          s4 = make_float4(x4.x - xp4.x, x4.y - xp4.y, x4.z - xp4.z, x4.w - xp4.w);
+          y4 = make_float4(g4.x - gp4.x, g4.y - gp4.y, g4.z - gp4.z, g4.w - gp4.w);
+          st4(a.S + (size_t)w * a.ld, i, a.n, vec, s4);
+          st4(a.Y + (size_t)w * a.ld, i, a.n, vec, y4);
+        } else {
+          s4 = ld4(a.S + (size_t)w * a.ld, i, a.n, vec);
+          y4 = ld4(a.Y + (size_t)w * a.ld, i, a.n, vec);
+        }
+        sh_s[tid * 4 + 0] = s4.x; sh_s[tid * 4 + 1] = s4.y; sh_s[tid * 4 + 2] = s4.z; sh_s[tid * 4 + 3] = s4.w;
+        sh_y[tid * 4 + 0] = y4.x; sh_y[tid * 4 + 1] = y4.y; sh_y[tid * 4 + 2] = y4.z; sh_y[tid * 4 + 3] = y4.w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int ri = a.row_begin + warp + r * kDotsWarps;
+      if (ri >= nrows) break;
+      const int p = sh_rows[ri];
+      const float *Sp = a.S + (size_t)p * a.ld, *Yp = a.Y + (size_t)p * a.ld;
+      const bool self = PAIR && (p == w) && (a.mode == DOTS_FORM_PAIR); // row being written this pass: use smem copy
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 sv[4], yv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = (half * 4 + j) * 128 + lane * 4;
+          if (self) {
+            sv[j] = make_float4((float)sh_s[e], (float)sh_s[e + 1], (float)sh_s[e + 2], (float)sh_s[e + 3]);
+            yv[j] = make_float4((float)sh_y[e], (float)sh_y[e + 1], (float)sh_y[e + 2], (float)sh_y[e + 3]);
+          } else {
+            sv[j] = ld4(Sp, base + e, a.n, vec);
+            yv[j] = ld4(Yp, base + e, a.n, vec);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = (half * 4 + j) * 128 + lane * 4;
+          const double s_[4] = {sv[j].x, sv[j].y, sv[j].z, sv[j].w};
+          const double y_[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double gq = sh_g[e + q];
+            acc[r][0] = fma(s_[q], gq, acc[r][0]);
+            acc[r][2] = fma(y_[q], gq, acc[r][2]);
+            if constexpr (PAIR) {
+              const double sn = sh_s[e + q], yn = sh_y[e + q];
+              acc[r][1] = fma(s_[q], yn, acc[r][1]);
+              acc[r][3] = fma(y_[q], sn, acc[r][3]);
+              acc[r][4] = fma(y_[q], yn, acc[r][4]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // one reduction per kernel
+  const int ncols = kDotsCols * mp + 1;
+  double *out = a.partials + (size_t)blockIdx.x * ncols;
+  if (a.row_begin == 0)
+    for (int c = tid; c < ncols; c += blockDim.x) out[c] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int ri = a.row_begin + warp + r * kDotsWarps;
+#pragma unroll
+    for (int c = 0; c < kDotsCols; ++c) {
+      const double v = warp_sum(acc[r][c]);
+      if (lane == 0 && ri < nrows) out[sh_rows[ri] * kDotsCols + c] = v;
+    }
+  }
+  gg = block_sum(gg, sh_red);
+  if (tid == 0 && a.row_begin == 0) out[kDotsCols * mp] = gg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2) one CTA: reduce the per-CTA partials (fixed order => deterministic), update the Gram blocks for
+// the slot written by (1), curvature test + ring advance, then the two-loop recurrences in fp64.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
+  extern __shared__ double sh[]; // tot[ncols] | alpha[mp] | beta[mp]
+  LbfgsHeader *h = a.st.h;
+  const int mp = h->mp, mod = h->mod;
+  const int ncols = kDotsCols * mp + 1;
+  double *tot = sh, *alpha = sh + ncols, *dlt = alpha + mp;
+  __shared__ int s_head, s_count, s_w;
+
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < a.nblocks; ++b) s += a.partials[(size_t)b * ncols + c];
+    tot[c] = s;
+  }
+  if (threadIdx.x == 0) {
+    int head = h->head, count = h->count;
+    if (a.reset_first) head = count = 0;
+    s_head = head; s_count = count; s_w = head;
+  }
+  __syncthreads();
+  const int w = s_w;
+  const bool pair = a.mode != DOTS_NONE;
+
+  // Gram update for every row the dots kernel visited (valid rows + w)
+  for (int p = threadIdx.x; p < mod; p += blockDim.x) {
+    int rel = (p - (s_head - s_count)) % mod;
+    if (rel < 0) rel += mod;
+    const bool valid = rel < s_count;
+    if (!(valid || (pair && p == w))) continue;
+    a.st.sg[p] = tot[p * kDotsCols + 0];
+    a.st.yg[p] = tot[p * kDotsCols + 2];
+    if (pair) {
+      a.st.SY[p * mp + w] = tot[p * kDotsCols + 1]; // s_p . y_w
+      a.st.SY[w * mp + p] = tot[p * kDotsCols + 3]; // s_w . y_p
+      a.st.YY[p * mp + w] = tot[p * kDotsCols + 4];
+      a.st.YY[w * mp + p] = tot[p * kDotsCols + 4];
+    }
+  }
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    int head = s_head, count = s_count, flags = 0;
+    if (pair) {
+      const double ys = a.st.SY[w * mp + w];
+      h->ys_new = ys;
+      h->yy_new = a.st.YY[w * mp + w];
+      // curvature filter y^T s > 1e-10 (src/cuda/lbfgs.cuh:161-169, src/minimizer/lbfgs.hpp:77-84)
+      // S-LBFGS: |y^T s| > 1e-10 (src/minimizer/s_lbfgs.hpp:253-258)
+      const bool accept = a.force_accept ? true : (a.policy == POLICY_SLBFGS ? fabs(ys) > 1e-10 : ys > 1e-10);
+      if (accept) {
+        a.st.rho[w] = a.force_accept ? a.ext_rho : 1.0 / ys;
+        head = (head + 1) % mod;
+        count = min(count + 1, h->m);
+        flags |= FLAG_PAIR_ACCEPTED;
+      }
+    }
+    h->head = head; h->count = count; h->flags = flags;
+    h->gnorm2 = tot[kDotsCols * mp];
+    s_head = head; s_count = count;
+  }
+  __syncthreads();
+
+  // two-loop recurrences on the Gram blocks: warp 0, lanes parallel over the inner sums
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int head = s_head, k = s_count;
+    const double gg = tot[kDotsCols * mp];
+    for (int i = lane; i < k; i += 32) a.st.phys[i] = ring_phys(head, k, mod, i);
+    __syncwarp();
+    double gamma = 1.0, cg = -1.0, gdotp = -gg;
+    if (k > 0) {
+      for (int i = k - 1; i >= 0; --i) {
+        const int pi = a.st.phys[i];
+        double s = 0.0;
+        for (int j = i + 1 + lane; j < k; j += 32) s += alpha[j] * a.st.SY[pi * mp + a.st.phys[j]];
+        s = warp_sum(s);
+        if (lane == 0) alpha[i] = a.st.rho[pi] * (a.st.sg[pi] - s);
+        __syncwarp();
+      }
+      const int pl = a.st.phys[k - 1];
+      const double ys = a.st.SY[pl * mp + pl], yy = a.st.YY[pl * mp + pl];
+      if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
+      else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
+      else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
+        gamma = (fabs(yy) < 1e-12) ? 1.0 : ys / yy;
+        gamma = fmin(fmax(gamma, 1e-6), 1e6);
+      }
+      for (int i = 0; i < k; ++i) {
+        const int pi = a.st.phys[i];
+        double s1 = 0.0, s2 = 0.0;
+        for (int j = lane; j < k; j += 32) s1 += alpha[j] * a.st.YY[pi * mp + a.st.phys[j]];
+        for (int j = lane; j < i; j += 32) s2 += dlt[j] * a.st.SY[a.st.phys[j] * mp + pi];
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+          const double beta = a.st.rho[pi] * (gamma * (a.st.yg[pi] - s1) + s2);
+          dlt[i] = alpha[i] - beta;
+        }
+        __syncwarp();
+      }
+      cg = -gamma;
+      double gp = 0.0;
+      for (int j = lane; j < k; j += 32) {
+        const double csj = -dlt[j], cyj = gamma * alpha[j];
+        a.st.cs[j] = csj;
+        a.st.cy[j] = cyj;
+        gp += csj * a.st.sg[a.st.phys[j]] + cyj * a.st.yg[a.st.phys[j]];
+      }
+      gp = warp_sum(gp);
+      gdotp = cg * gg + gp;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int kk = k;
+      // non-descent direction: steepest descent + history reset (src/cuda/lbfgs.cuh:97-104).
+      // The CPU backend has no such check (src/minimizer/lbfgs.hpp:56-65).
+      if (a.policy == POLICY_ARMIJO && kk > 0 && !(gdotp < 0.0)) {
+        kk = 0; cg = -1.0; gdotp = -gg; gamma = 1.0;
+        h->head = 0; h->count = 0; h->flags |= FLAG_SD_FALLBACK;
+      }
+      h->k = kk; h->cg = cg; h->gdotp = gdotp; h->gamma = gamma;
+      const double gn = sqrt(gg);
+      h->alpha0 = a.first_iter ? fmin(1.0, 1.0 / gn) : 1.0; // lbfgs.cuh:108, lbfgs.hpp:60-61
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (3) p = cg g + sum_j cs_j s_j + cy_j y_j  (fp64 accumulate, one rounding); x_prev = x; x += alpha0 p
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
+  __shared__ double s_cs[kMaxSlots], s_cy[kMaxSlots];
+  __shared__ int s_ph[kMaxSlots];
+  const LbfgsHeader *h = a.st.h;
+  const int k = h->k;
+  if (threadIdx.x < k) {
+    s_cs[threadIdx.x] = a.st.cs[threadIdx.x] * a.sign;
+    s_cy[threadIdx.x] = a.st.cy[threadIdx.x] * a.sign;
+    s_ph[threadIdx.x] = a.st.phys[threadIdx.x];
+  }
+  __syncthreads();
+  const double cg = h->cg * a.sign;
+  const float alpha0 = (a.step != 0.0f) ? a.step : (float)h->alpha0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.S) |
+                     reinterpret_cast<uintptr_t>(a.Y) | reinterpret_cast<uintptr_t>(a.p) |
+                     reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.x_prev) |
+                     reinterpret_cast<uintptr_t>(a.x_copy)) & 15u) == 0 &&
+                   (a.ld % 4 == 0);
+  const size_t nv = (a.n + 3) / 4;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = v * 4;
+    const float4 g4 = ld4(a.g, i, a.n, vec);
+    double r0 = cg * g4.x, r1 = cg * g4.y, r2 = cg * g4.z, r3 = cg * g4.w;
+    for (int j = 0; j < k; ++j) {
+      const float4 s4 = ld4(a.S + (size_t)s_ph[j] * a.ld, i, a.n, vec);
+      const float4 y4 = ld4(a.Y + (size_t)s_ph[j] * a.ld, i, a.n, vec);
+      const double cs = s_cs[j], cy = s_cy[j];
+      r0 = fma(cs, (double)s4.x, r0); r1 = fma(cs, (double)s4.y, r1);
+      r2 = fma(cs, (double)s4.z, r2); r3 = fma(cs, (double)s4.w, r3);
+      r0 = fma(cy, (double)y4.x, r0); r1 = fma(cy, (double)y4.y, r1);
+      r2 = fma(cy, (double)y4.z, r2); r3 = fma(cy, (double)y4.w, r3);
+    }
+    const float4 p4 = make_float4((float)r0, (float)r1, (float)r2, (float)r3);
+    st4(a.p, i, a.n, vec, p4);
+    if (a.x) {
+      const float4 x4 = ld4(a.x, i, a.n, vec);
+      if (a.x_prev) st4(a.x_prev, i, a.n, vec, x4);
+      // one rounding per element like the reference's copy + axpy (lbfgs.cuh:116-117, cuBLAS axpy is an FMA)
+      const float4 xn = make_float4(fmaf(alpha0, p4.x, x4.x), fmaf(alpha0, p4.y, x4.y), fmaf(alpha0, p4.z, x4.z),
+                                    fmaf(alpha0, p4.w, x4.w));
+      st4(a.x, i, a.n, vec, xn);
+      if (a.x_copy) st4(a.x_copy, i, a.n, vec, xn);
+    }
+  }
+}
+
+__global__ void lbfgs_init_kernel(LbfgsView v, int m, int mod) {
+  const int mp = m + 1;
+  for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { v.SY[i] = 0.0; v.YY[i] = 0.0; }
+  for (int i = threadIdx.x; i < mp; i += blockDim.x) {
+    v.rho[i] = 0.0; v.sg[i] = 0.0; v.yg[i] = 0.0; v.cs[i] = 0.0; v.cy[i] = 0.0; v.phys[i] = 0;
+  }
+  if (threadIdx.x == 0) {
+    LbfgsHeader h{};
+    h.m = m; h.mp = mp; h.mod = mod; h.cg = -1.0; h.alpha0 = 1.0; h.gamma = 1.0;
+    *v.h = h;
+  }
+}
+
+// copy an explicit (s, y) pair into slot `head` (the Gram update happens in the following dots/solve)
+__global__ void __launch_bounds__(256) store_pair_kernel(float *S, float *Y, size_t n, size_t ld, LbfgsView st,
+                                                         const float *s, const float *y) {
+  const int w = st.h->head;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    S[(size_t)w * ld + i] = s[i];
+    Y[(size_t)w * ld + i] = y[i];
+  }
+}
+
+// ---- BLAS-1 replacements -----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trial_point_kernel(size_t n, const float *__restrict__ x0, float alpha,
+                                                          const float *__restrict__ p, float *__restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, p[i], x0[i]);
+}
+__global__ void __launch_bounds__(256) axpy_kernel(size_t n, float alpha, const float *__restrict__ x, float *y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, x[i], y[i]);
+}
+__global__ void __launch_bounds__(256) scal_kernel(size_t n, float alpha, float *x) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] *= alpha;
+}
+__global__ void __launch_bounds__(256) momentum_step_kernel(size_t n, float mu, float lr, const float *__restrict__ g,
+                                                            float *v, float *x) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // v = mu*v; v += -lr*g; x += v  (src/cuda/gd.cuh:77-81: scal, axpy, axpy)
+    const float vv = fmaf(-lr, g[i], mu * v[i]);
+    v[i] = vv;
+    x[i] += vv;
+  }
+}
+__global__ void __launch_bounds__(256) f64_to_f32_kernel(size_t n, const double *__restrict__ s, float *__restrict__ d) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = (float)s[i];
+}
+__global__ void __launch_bounds__(256) dot_part_kernel(const float *__restrict__ x, const float *__restrict__ y, size_t n,
+                                                       double *part) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s = fma((double)x[i], (double)y[i], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) dot_final_kernel(const double *part, int nparts, double *out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s;
+}
+
+inline int vec_blocks(size_t n, int cap) { return (int)std::max<size_t>(1, std::min<size_t>((size_t)cap, (n + 255) / 256)); }
+
+} // namespace
+
+int lbfgs_dots_blocks(b200_ctx *ctx, size_t n) {
+  const size_t tiles = (n + kDotsTile - 1) / kDotsTile;
+  return (int)std::max<size_t>(1, std::min<size_t>((size_t)2 * ctx->num_sms, tiles));
+}
+int dot_blocks(b200_ctx *ctx, size_t n) { return vec_blocks(n, 2 * ctx->num_sms); }
+
+int launch_lbfgs_dots(const DotsArgs &a0, int mp, int nblocks, cudaStream_t st) {
+  B200_REQUIRE(mp <= kMaxSlots, "history size above 256 is not supported");
+  const bool pair = a0.mode != DOTS_NONE;
+  // the row count is device state (<= mp); launches beyond the live rows exit after the staging loop
+  for (int row_begin = 0; row_begin < mp; row_begin += kRowsPerLaunch) {
+    DotsArgs a = a0;
+    a.row_begin = row_begin;
+    const int rpw = ceil_div(std::min(mp - row_begin, kRowsPerLaunch), kDotsWarps);
+#define B200_DOTS_CASE(R)                                                                            \
+  case R:                                                                                            \
+    if (pair) B200_LAUNCH((lbfgs_dots_kernel<R, true>), nblocks, kDotsThreads, 0, st, a);            \
+    else B200_LAUNCH((lbfgs_dots_kernel<R, false>), nblocks, kDotsThreads, 0, st, a);                \
+    break;
+    switch (rpw) {
+      B200_DOTS_CASE(1)
+      B200_DOTS_CASE(2)
+      B200_DOTS_CASE(3)
+      B200_DOTS_CASE(4)
+    default:
+      set_error("unsupported rows per warp %d", rpw);
+      return B200_ERR_INVALID;
+    }
+#undef B200_DOTS_CASE
+  }
+  return B200_OK;
+}
+
+int launch_lbfgs_solve(const SolveArgs &a, int mp, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (kDotsCols * mp + 1 + 2 * mp);
+  B200_LAUNCH(lbfgs_solve_kernel, 1, 256, smem, st, a);
+  return B200_OK;
+}
+
+int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st) {
+  B200_LAUNCH(lbfgs_apply_kernel, nblocks, 256, 0, st, a);
+  return B200_OK;
+}
+
+int lbfgs_init_state(LbfgsView v, int m, int mod, cudaStream_t st) {
+  B200_LAUNCH(lbfgs_init_kernel, 1, 256, 0, st, v, m, mod);
+  return B200_OK;
+}
+
+int launch_lbfgs_store_pair(float *S, float *Y, size_t n, size_t ld, LbfgsView stv, const float *s, const float *y,
+                            cudaStream_t stream) {
+  B200_LAUNCH(store_pair_kernel, vec_blocks(n, 1184), 256, 0, stream, S, Y, n, ld, stv, s, y);
+  return B200_OK;
+}
+
+int launch_trial_point(size_t n, const float *x0, float alpha, const float *p, float *y, cudaStream_t st) {
+  B200_LAUNCH(trial_point_kernel, vec_blocks(n, 1184), 256, 0, st, n, x0, alpha, p, y);
+  return B200_OK;
+}
+int launch_axpy(size_t n, float alpha, const float *x, float *y, cudaStream_t st) {
+  B200_LAUNCH(axpy_kernel, vec_blocks(n, 1184), 256, 0, st, n, alpha, x, y);
+  return B200_OK;
+}
+int launch_scal(size_t n, float alpha, float *x, cudaStream_t st) {
+  B200_LAUNCH(scal_kernel, vec_blocks(n, 1184), 256, 0, st, n, alpha, x);
+  return B200_OK;
+}
+int launch_momentum_step(size_t n, float mu, float lr, const float *g, float *v, float *x, cudaStream_t st) {
+  B200_LAUNCH(momentum_step_kernel, vec_blocks(n, 1184), 256, 0, st, n, mu, lr, g, v, x);
+  return B200_OK;
+}
+int launch_f64_to_f32(size_t n, const double *src, float *dst, cudaStream_t st) {
+  B200_LAUNCH(f64_to_f32_kernel, vec_blocks(n, 1184), 256, 0, st, n, src, dst);
+  return B200_OK;
+}
+int launch_dot(b200_ctx *ctx, const float *x, const float *y, size_t n, double *part, double *out) {
+  const int nb = dot_blocks(ctx, n);
+  B200_LAUNCH(dot_part_kernel, nb, 256, 0, ctx->stream, x, y, n, part);
+  B200_LAUNCH(dot_final_kernel, 1, 256, 0, ctx->stream, part, nb, out);
+  return B200_OK;
+}
+
+} // namespace b200

@@ -1,0 +1,481 @@
+// The MLP objective: forward, loss, backward — replaces cuda_mlp::CudaNetwork / CudaDenseLayer
+// (src/cuda/network.cuh:16-156, src/cuda/layer.cuh:13-117). Per evaluation the reference issues
+// 5 SGEMMs + 11 small kernels/memsets/memcpys + one blocking dot for a 2-layer net; here it is
+// L forward GEMMs (bias+activation, and loss/delta on the last one, in the epilogue), L-1 dX GEMMs
+// (activation derivative in the epilogue), L split-K dW GEMMs (bias gradient as an extra ones-row)
+// and one finalize pass that reduces the split-K partials straight into the caller's gradient buffer.
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "network.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+namespace b200 {
+
+namespace {
+
+constexpr int kMaxLayers = 16;
+
+struct FinLayer {
+  unsigned long long off, size, part_off;
+  int splits;
+};
+struct FinParams {
+  FinLayer L[kMaxLayers];
+  int nl;
+  unsigned long long n;
+  const float *partials;
+  const float *w;
+  float lam;
+  float *grad;
+  double *fin_part; // [gridDim.x][2] = {sum g^2, sum w^2}
+};
+
+// grad[j] = sum_s partial_l[s][j - off_l] (+ lam * w[j]); per-CTA partials of ||g||^2, ||w||^2.
+// Deterministic: fixed split order, fixed CTA -> element mapping.
+__global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
+  __shared__ double red[32];
+  double g2 = 0.0, w2 = 0.0;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < p.n;
+       j += (unsigned long long)gridDim.x * blockDim.x) {
+    int l = 0;
+#pragma unroll 1
+    while (l + 1 < p.nl && j >= p.L[l + 1].off) ++l;
+    const FinLayer &L = p.L[l];
+    const float *src = p.partials + L.part_off + (j - L.off);
+    double acc = 0.0; // fp64 combine of the fp32 split-K partials: one rounding into the gradient
+    for (int sp = 0; sp < L.splits; ++sp) acc += (double)__ldg(src + (unsigned long long)sp * L.size);
+    if (p.lam != 0.0f) {
+      const float wv = __ldg(p.w + j);
+      acc = fma((double)p.lam, (double)wv, acc);
+      w2 += (double)wv * (double)wv;
+    }
+    const float s = (float)acc;
+    p.grad[j] = s;
+    g2 += (double)s * (double)s;
+  }
+  const double a = block_sum(g2, red);
+  const double b = block_sum(w2, red);
+  if (threadIdx.x == 0) {
+    p.fin_part[2 * blockIdx.x + 0] = a;
+    p.fin_part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// loss = 0.5 * inv_batch * sum(loss_part) + 0.5 * lam * sum(w^2 parts); gnorm2 = sum(g^2 parts)
+__global__ void __launch_bounds__(256) eval_scalars_kernel(const double *loss_part, int n_loss, const double *fin_part,
+                                                           int n_fin, double inv_batch, double lam, int want_gnorm,
+                                                           EvalOut *out) {
+  __shared__ double red[32];
+  double l = 0.0, g2 = 0.0, w2 = 0.0;
+  for (int i = threadIdx.x; i < n_loss; i += blockDim.x) l += loss_part[i];
+  for (int i = threadIdx.x; i < n_fin; i += blockDim.x) {
+    g2 += fin_part[2 * i];
+    w2 += fin_part[2 * i + 1];
+  }
+  l = block_sum(l, red);
+  g2 = block_sum(g2, red);
+  w2 = block_sum(w2, red);
+  if (threadIdx.x == 0) {
+    out->loss = 0.5 * inv_batch * l + 0.5 * lam * w2;
+    if (want_gnorm) out->gnorm2 = g2;
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_part_kernel(const float *x, unsigned long long n, double *part) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (unsigned long long)gridDim.x * blockDim.x) {
+    const float v = x[j];
+    s += (double)v * (double)v;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[2 * blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) gnorm_from_parts_kernel(const double *part, int nparts, EvalOut *out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[2 * i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out->gnorm2 = s;
+}
+
+// UnifiedLauncher<CudaBackend>::evaluate (src/unified_launcher.hpp:154-199) on the device:
+// per sample arg-max of prediction vs target (first maximum wins, strict >), squared error sum.
+__global__ void __launch_bounds__(256) evaluate_kernel(const float *out, const float *tgt, long batch, int od,
+                                                       double *part) {
+  __shared__ double red[32];
+  double se = 0.0, correct = 0.0;
+  for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < batch; b += (long)gridDim.x * blockDim.x) {
+    int pi = 0, ti = 0;
+    double pm = -1e20, tm = -1e20;
+    for (int r = 0; r < od; ++r) {
+      const double v = out[b * od + r], tv = tgt[b * od + r];
+      se += (v - tv) * (v - tv);
+      if (v > pm) { pm = v; pi = r; }
+      if (tv > tm) { tm = tv; ti = r; }
+    }
+    if (pi == ti) correct += 1.0;
+  }
+  se = block_sum(se, red);
+  correct = block_sum(correct, red);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = se;
+    part[2 * blockIdx.x + 1] = correct;
+  }
+}
+
+int free_batch_buffers(b200_net *net) {
+  for (float *p : net->act) if (p) cudaFree(p);
+  for (float *p : net->delta) if (p) cudaFree(p);
+  net->act.assign(net->nlayers(), nullptr);
+  net->delta.assign(net->nlayers(), nullptr);
+  if (net->loss_part) { cudaFree(net->loss_part); net->loss_part = nullptr; }
+  net->cap = 0;
+  return B200_OK;
+}
+
+} // namespace
+
+// Per-batch buffers. Unlike the reference (re-cudaMalloc on every batch-size change,
+// src/cuda/network.cuh:133-147) capacity only grows, so SGD mini-batches alternating with
+// full-batch recorder evaluations do not churn the allocator.
+int net_ensure(b200_net *net, long batch) {
+  B200_REQUIRE(batch > 0, "batch must be positive");
+  const int L = net->nlayers();
+  if (batch > net->cap) {
+    free_batch_buffers(net);
+    for (int l = 0; l < L; ++l) {
+      B200_CUDA(cudaMalloc(&net->act[l], sizeof(float) * (size_t)net->dims[l + 1] * batch));
+      B200_CUDA(cudaMalloc(&net->delta[l], sizeof(float) * (size_t)net->dims[l + 1] * batch));
+    }
+    net->loss_part_cap = ceil_div(batch, kBM) * ceil_div(net->dims[L], 16);
+    B200_CUDA(cudaMalloc(&net->loss_part, sizeof(double) * net->loss_part_cap));
+    net->cap = batch;
+  }
+  if (batch != net->partials_batch) {
+    // split-K plan: enough CTAs to fill the machine ~2x, each split a multiple of 16 samples
+    const int target = 2 * net->ctx->num_sms;
+    size_t total = 0;
+    for (int l = 0; l < L; ++l) {
+      const int M = net->dims[l] + 1, N = net->dims[l + 1];
+      const int tn = (N > 64) ? 8 : (N > 32 ? 4 : (N > 16 ? 2 : 1));
+      const int tiles = ceil_div(M, kBM) * ceil_div(N, 16 * tn);
+      int s = std::max(1, std::min(ceil_div(target, tiles), ceil_div(batch, 64)));
+      int kc = ceil_div(ceil_div(batch, s), kBK) * kBK;
+      s = ceil_div(batch, kc);
+      net->splits[l] = s;
+      net->k_chunk[l] = kc;
+      net->part_off[l] = total;
+      total += (size_t)s * M * N;
+    }
+    if (total > net->partials_cap) {
+      if (net->partials) cudaFree(net->partials);
+      B200_CUDA(cudaMalloc(&net->partials, sizeof(float) * total));
+      net->partials_cap = total;
+    }
+    net->partials_batch = batch;
+  }
+  return B200_OK;
+}
+
+static int launch_fwd_layer(b200_net *net, int l, const float *params, const float *in, long batch, bool last,
+                            const float *t, float inv_batch) {
+  const int K = net->dims[l], N = net->dims[l + 1];
+  const float *W = params + net->offs[l];
+  GemmParams p{};
+  p.A = in; p.lda = K;
+  p.B = W; p.ldb = N;
+  p.M = (int)batch; p.N = N; p.K = K;
+  p.vecA = aligned16(in) && (K % 4 == 0);
+  p.vecB = aligned16(W) && (N % 4 == 0);
+  p.a_ones_row = -1;
+  p.k_chunk = K;
+  p.bias = W + (size_t)K * N;
+  p.act = net->acts[l];
+  p.out = net->act[l]; p.ldo = N;
+  if (last) {
+    p.aux = t;
+    p.delta = net->delta[l];
+    p.inv_batch = inv_batch;
+    p.loss_part = net->loss_part;
+    const int tn = (N > 64) ? 8 : (N > 32 ? 4 : (N > 16 ? 2 : 1));
+    net->loss_part_n = ceil_div(batch, kBM) * ceil_div(N, 16 * tn);
+    return launch_gemm_simt<true, false, EPI_FWD_LAST>(p, 1, net->ctx->stream);
+  }
+  return launch_gemm_simt<true, false, EPI_FWD>(p, 1, net->ctx->stream);
+}
+
+int net_forward(b200_net *net, const float *params, const float *x, long batch) {
+  B200_TRY(net_ensure(net, batch));
+  const float *cur = x;
+  for (int l = 0; l < net->nlayers(); ++l) {
+    bool done = false;
+    if (net->prec != B200_PREC_FP32) B200_TRY(tc_forward_layer(net, l, params, cur, batch, &done));
+    if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, false, nullptr, 0.f));
+    cur = net->act[l];
+  }
+  net->last_batch = batch;
+  return B200_OK;
+}
+
+int net_eval(b200_net *net, const float *params, const float *x, const float *t, long batch, long batch_global,
+             float *grad_out, EvalOut *out) {
+  B200_REQUIRE(net && params && x && t && grad_out && out, "null argument");
+  B200_TRY(net_ensure(net, batch));
+  b200_ctx *ctx = net->ctx;
+  cudaStream_t st = ctx->stream;
+  const int L = net->nlayers();
+  if (batch_global <= 0) batch_global = net->batch_global > 0 ? net->batch_global : batch * ctx->world;
+  const float inv_batch = 1.0f / (float)batch_global;
+
+  // forward sweep
+  const float *cur = x;
+  for (int l = 0; l < L; ++l) {
+    const bool last = (l == L - 1);
+    bool done = false;
+    if (!last && net->prec != B200_PREC_FP32) B200_TRY(tc_forward_layer(net, l, params, cur, batch, &done));
+    if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, last, t, inv_batch));
+    cur = net->act[l];
+  }
+  net->last_batch = batch;
+
+  // backward sweep
+  for (int l = L - 1; l >= 0; --l) {
+    const int K = net->dims[l], N = net->dims[l + 1];
+    const float *W = params + net->offs[l];
+    const float *in = (l == 0) ? x : net->act[l - 1];
+    if (l > 0) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
+      GemmParams p{};
+      p.A = net->delta[l]; p.lda = N;
+      p.B = W; p.ldb = N;
+      p.M = (int)batch; p.N = K; p.K = N;
+      p.vecA = aligned16(p.A) && (N % 4 == 0);
+      p.vecB = aligned16(W) && (N % 4 == 0);
+      p.a_ones_row = -1;
+      p.k_chunk = N;
+      p.act = net->acts[l - 1];
+      p.out = net->delta[l - 1]; p.ldo = K;
+      p.aux = net->act[l - 1];
+      B200_TRY((launch_gemm_simt<true, true, EPI_DX>(p, 1, st)));
+    }
+    { // [dW; db] partials = [A_{l-1} | 1]^T delta_l over batch slices
+      bool done = false;
+      if (net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
+      if (!done) {
+        GemmParams p{};
+        p.A = in; p.lda = K;
+        p.B = net->delta[l]; p.ldb = N;
+        p.M = K + 1; p.N = N; p.K = (int)batch;
+        p.vecA = aligned16(in) && (K % 4 == 0);
+        p.vecB = aligned16(p.B) && (N % 4 == 0);
+        p.a_ones_row = K;
+        p.k_chunk = net->k_chunk[l];
+        p.out = net->partials + net->part_off[l];
+        B200_TRY((launch_gemm_simt<false, false, EPI_DW>(p, net->splits[l], st)));
+      }
+    }
+  }
+
+  // split-K reduction straight into the caller's gradient buffer (+ L2 term, + ||g||^2 partials)
+  FinParams fp{};
+  fp.nl = L;
+  for (int l = 0; l < L; ++l) {
+    fp.L[l].off = net->offs[l];
+    fp.L[l].size = (unsigned long long)(net->dims[l] + 1) * net->dims[l + 1];
+    fp.L[l].part_off = net->part_off[l];
+    fp.L[l].splits = net->splits[l];
+  }
+  fp.n = net->n;
+  fp.partials = net->partials;
+  fp.w = params;
+  fp.lam = net->l2 / (float)ctx->world; // each rank adds its share; the all-reduce sums them
+  fp.grad = grad_out;
+  fp.fin_part = net->fin_part;
+  B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);
+  const bool multi = ctx->world > 1;
+  B200_LAUNCH(eval_scalars_kernel, 1, 256, 0, st, net->loss_part, net->loss_part_n, net->fin_part, net->fin_blocks,
+              (double)inv_batch, (double)fp.lam, multi ? 0 : 1, out);
+  if (multi) {
+    B200_TRY(ctx_allreduce(ctx, grad_out, net->n, &out->loss));
+    B200_LAUNCH(sumsq_part_kernel, net->fin_blocks, 256, 0, st, grad_out, (unsigned long long)net->n, net->fin_part);
+    B200_LAUNCH(gnorm_from_parts_kernel, 1, 256, 0, st, net->fin_part, net->fin_blocks, out);
+  }
+  return B200_OK;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+// =====================================================================================================
+// C ABI: network
+// =====================================================================================================
+extern "C" {
+
+int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts, b200_net **out) {
+  B200_REQUIRE(ctx && dims && acts && out, "null argument");
+  B200_REQUIRE(nlayers >= 1 && nlayers <= kMaxLayers, "1..16 layers supported");
+  for (int l = 0; l <= nlayers; ++l) B200_REQUIRE(dims[l] > 0, "layer dimensions must be positive");
+  for (int l = 0; l < nlayers; ++l) B200_REQUIRE(acts[l] >= 0 && acts[l] <= 3, "unknown activation");
+  b200_net *net = new b200_net;
+  net->ctx = ctx;
+  net->dims.assign(dims, dims + nlayers + 1);
+  net->acts.assign(acts, acts + nlayers);
+  net->offs.resize(nlayers);
+  size_t off = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    net->offs[l] = off;
+    off += (size_t)dims[l + 1] * dims[l] + dims[l + 1];
+  }
+  net->n = off;
+  net->act.assign(nlayers, nullptr);
+  net->delta.assign(nlayers, nullptr);
+  net->splits.assign(nlayers, 1);
+  net->k_chunk.assign(nlayers, 16);
+  net->part_off.assign(nlayers, 0);
+  net->fin_blocks = std::max(1, std::min(2 * ctx->num_sms, ceil_div((long)net->n, 256)));
+  cudaSetDevice(ctx->device);
+  B200_CUDA(cudaMalloc(&net->fin_part, sizeof(double) * 2 * net->fin_blocks));
+  B200_CUDA(cudaMalloc(&net->eval_out, sizeof(EvalOut)));
+  *out = net;
+  return B200_OK;
+}
+
+int b200_net_destroy(b200_net *net) {
+  if (!net) return B200_OK;
+  cudaSetDevice(net->ctx->device);
+  cudaStreamSynchronize(net->ctx->stream);
+  free_batch_buffers(net);
+  tc_release(net);
+  if (net->partials) cudaFree(net->partials);
+  if (net->fin_part) cudaFree(net->fin_part);
+  if (net->eval_out) cudaFree(net->eval_out);
+  if (net->params) cudaFree(net->params);
+  if (net->grads) cudaFree(net->grads);
+  delete net;
+  return B200_OK;
+}
+
+size_t b200_net_params_size(b200_net *net) { return net ? net->n : 0; }
+int b200_net_output_size(b200_net *net) { return net ? net->dims.back() : 0; }
+
+static float activation_scale(int act) { // src/cuda/kernels.cuh:61-71
+  return act == B200_ACT_RELU ? 1.41421356f : 1.0f;
+}
+
+int b200_net_bind_params(b200_net *net, unsigned seed) {
+  B200_REQUIRE(net, "null net");
+  cudaSetDevice(net->ctx->device);
+  if (!net->params) B200_CUDA(cudaMalloc(&net->params, sizeof(float) * net->n));
+  if (!net->grads) B200_CUDA(cudaMalloc(&net->grads, sizeof(float) * net->n));
+  // host-side init, same RNG consumption as CudaNetwork::bindParams (src/cuda/network.cuh:37-59)
+  std::vector<float> host(net->n);
+  std::mt19937 gen(seed);
+  size_t off = 0;
+  for (int l = 0; l < net->nlayers(); ++l) {
+    const size_t wc = (size_t)net->dims[l + 1] * net->dims[l], bc = net->dims[l + 1];
+    const float sd = activation_scale(net->acts[l]) * std::sqrt(1.0f / (float)net->dims[l]);
+    std::normal_distribution<float> dist(0.0f, sd);
+    for (size_t i = 0; i < wc; ++i) host[off + i] = dist(gen);
+    for (size_t i = 0; i < bc; ++i) host[off + wc + i] = 0.0f;
+    off += wc + bc;
+  }
+  B200_CUDA(cudaMemcpyAsync(net->params, host.data(), sizeof(float) * net->n, cudaMemcpyHostToDevice, net->ctx->stream));
+  B200_CUDA(cudaMemsetAsync(net->grads, 0, sizeof(float) * net->n, net->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  return B200_OK;
+}
+
+float *b200_net_params_data(b200_net *net) { return net ? net->params : nullptr; }
+float *b200_net_grads_data(b200_net *net) { return net ? net->grads : nullptr; }
+
+int b200_net_zero_grads(b200_net *net) {
+  B200_REQUIRE(net && net->grads, "params not bound");
+  B200_CUDA(cudaMemsetAsync(net->grads, 0, sizeof(float) * net->n, net->ctx->stream));
+  return B200_OK;
+}
+
+int b200_net_set_precision(b200_net *net, int prec) {
+  B200_REQUIRE(net, "null net");
+  B200_REQUIRE(prec >= B200_PREC_FP32 && prec <= B200_PREC_TF32, "unknown precision mode");
+  net->prec = prec;
+  return B200_OK;
+}
+int b200_net_get_precision(b200_net *net) { return net ? net->prec : -1; }
+
+int b200_net_set_l2(b200_net *net, float lambda) {
+  B200_REQUIRE(net, "null net");
+  net->l2 = lambda;
+  return B200_OK;
+}
+
+int b200_net_set_global_batch(b200_net *net, long batch_global) {
+  B200_REQUIRE(net && batch_global >= 0, "bad argument");
+  net->batch_global = batch_global;
+  return B200_OK;
+}
+
+int b200_net_forward(b200_net *net, const float *x_dev, long batch) {
+  B200_REQUIRE(net && net->params && x_dev, "null argument / params not bound");
+  cudaSetDevice(net->ctx->device);
+  return net_forward(net, net->params, x_dev, batch);
+}
+
+int b200_net_loss_grad_async(b200_net *net, const float *params_dev, const float *x_dev, const float *t_dev, long batch,
+                             float *grad_dev, double *loss_dev) {
+  B200_REQUIRE(net && x_dev && t_dev, "null argument");
+  const float *pp = params_dev ? params_dev : net->params;
+  float *gg = grad_dev ? grad_dev : net->grads;
+  B200_REQUIRE(pp && gg, "params not bound");
+  cudaSetDevice(net->ctx->device);
+  B200_TRY(net_eval(net, pp, x_dev, t_dev, batch, 0, gg, (EvalOut *)net->eval_out));
+  if (loss_dev)
+    B200_CUDA(cudaMemcpyAsync(loss_dev, net->eval_out, sizeof(double), cudaMemcpyDeviceToDevice, net->ctx->stream));
+  return B200_OK;
+}
+
+int b200_net_loss_grad(b200_net *net, const float *x_dev, const float *t_dev, long batch, float *loss_host) {
+  B200_REQUIRE(net && net->params, "params not bound");
+  B200_TRY(b200_net_loss_grad_async(net, nullptr, x_dev, t_dev, batch, nullptr, nullptr));
+  b200_ctx *ctx = net->ctx;
+  B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (loss_host) *loss_host = (float)ctx->h_scalars[0];
+  return B200_OK;
+}
+
+int b200_net_copy_output_to_host(b200_net *net, float *host, size_t n) {
+  B200_REQUIRE(net && host, "null argument");
+  if (net->act.empty() || !net->act.back() || net->last_batch == 0) return B200_OK; // network.cuh:122-124
+  B200_REQUIRE(n <= (size_t)net->dims.back() * net->last_batch, "more elements requested than the last batch produced");
+  B200_CUDA(cudaMemcpyAsync(host, net->act.back(), sizeof(float) * n, cudaMemcpyDeviceToHost, net->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  return B200_OK;
+}
+
+int b200_net_last_batch(b200_net *net) { return net ? (int)net->last_batch : 0; }
+
+int b200_net_evaluate(b200_net *net, const float *x_dev, const float *t_dev, long batch, double *mse, double *accuracy) {
+  B200_REQUIRE(net && net->params && x_dev && t_dev, "null argument / params not bound");
+  cudaSetDevice(net->ctx->device);
+  B200_TRY(net_forward(net, net->params, x_dev, batch));
+  const int od = net->dims.back();
+  const int blocks = std::max(1, std::min(net->fin_blocks, ceil_div(batch, 256)));
+  B200_LAUNCH(evaluate_kernel, blocks, 256, 0, net->ctx->stream, net->act.back(), t_dev, batch, od, net->fin_part);
+  std::vector<double> part(2 * blocks);
+  B200_CUDA(cudaMemcpyAsync(part.data(), net->fin_part, sizeof(double) * 2 * blocks, cudaMemcpyDeviceToHost,
+                            net->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  double se = 0.0, correct = 0.0;
+  for (int i = 0; i < blocks; ++i) { se += part[2 * i]; correct += part[2 * i + 1]; }
+  if (mse) *mse = se / ((double)batch * od);               // unified_launcher.hpp:196
+  if (accuracy) *accuracy = correct / (double)batch * 100.0; // :197
+  return B200_OK;
+}
+
+} // extern "C"

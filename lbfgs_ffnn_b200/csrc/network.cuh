@@ -1,0 +1,58 @@
+// b200_net: the MLP objective (replaces cuda_mlp::CudaNetwork, src/cuda/network.cuh).
+#pragma once
+
+#include "common.cuh"
+
+#include <vector>
+
+struct b200_net {
+  b200_ctx *ctx = nullptr;
+  std::vector<int> dims; // nlayers + 1
+  std::vector<int> acts; // nlayers
+  std::vector<size_t> offs;
+  size_t n = 0;
+  int prec = B200_PREC_FP32;
+  float l2 = 0.0f;
+  long batch_global = 0; // 0: shard batch x world
+
+  // flat parameter / gradient buffers (owned after bind_params)
+  float *params = nullptr, *grads = nullptr;
+
+  // per-batch state
+  long cap = 0;        // sample capacity of act/delta
+  long last_batch = 0;
+  std::vector<float *> act, delta;
+
+  // split-K partials of [dW; db] per layer and their layout
+  std::vector<int> splits, k_chunk;
+  std::vector<size_t> part_off;
+  float *partials = nullptr;
+  size_t partials_cap = 0;
+  long partials_batch = -1;
+
+  double *loss_part = nullptr; // per-CTA partials of sum diff^2
+  int loss_part_cap = 0, loss_part_n = 0;
+  double *fin_part = nullptr;  // per-CTA partials of ||g||^2 and ||w||^2 (2 per CTA)
+  int fin_blocks = 0;
+  double *eval_out = nullptr;  // device {loss, gnorm2}
+
+  int nlayers() const { return (int)acts.size(); }
+};
+
+namespace b200 {
+
+struct EvalOut { // device-resident result of one evaluation
+  double loss;
+  double gnorm2;
+};
+
+// Evaluate loss and gradient at `params` (device, flat layout) on the shard (x, t, batch).
+// grad_out (device, n floats) receives the gradient (all-reduced when a communicator exists);
+// out (device EvalOut) receives loss and ||grad||^2. Asynchronous on ctx->stream.
+// batch_global is the 1/B denominator (sum of shard sizes over ranks).
+int net_eval(b200_net *net, const float *params, const float *x, const float *t, long batch, long batch_global,
+             float *grad_out, EvalOut *out);
+int net_forward(b200_net *net, const float *params, const float *x, long batch);
+int net_ensure(b200_net *net, long batch);
+
+} // namespace b200

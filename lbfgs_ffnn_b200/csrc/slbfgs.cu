@@ -1,0 +1,342 @@
+// Stochastic L-BFGS (Moritz et al. 2016) on the GPU — SLBFGS::stochastic_solve
+// (src/minimizer/s_lbfgs.hpp:165-290) with the objective closures of UnifiedSLBFGS_CPU::optimize
+// (src/unified_optimization.hpp:314-407: mean-squared loss / batch + 0.5*lambda*||w||^2).
+//
+// New functionality: the reference static_asserts on UnifiedSLBFGS<CudaBackend>
+// (src/unified_optimization.hpp:639-641). The control flow and the RNG consumption order
+// (mini-batch draws, H-batch draws, anchor pick from ONE std::mt19937(seed)) are the reference's;
+// all index streams of an epoch are drawn on the host up front (they do not depend on device results)
+// and uploaded once, so an epoch runs without a single host synchronisation:
+//   per inner step: gather -> eval(w_t) -> eval(w~) -> v = g_t - g_k + mu -> dots -> solve -> apply
+//   every L steps : iterate mean u, s = u - u_prev, w+- = u +- eps*s, 2 evaluations on the H-batch,
+//                   y = (g+ - g-)/(2 eps), ring push with the |y.s| > 1e-10 filter decided on the device.
+#include "lbfgs_kernels.cuh"
+#include "network.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <random>
+#include <vector>
+
+namespace b200 {
+
+namespace {
+
+// Partial Fisher-Yates over the identity permutation, one uniform_int_distribution<size_t>(i, N-1) draw
+// per element (s_lbfgs.hpp:141-161). The reference rebuilds iota(N) for every batch; undoing the swaps
+// gives the same result in O(b).
+struct Sampler {
+  std::mt19937 rng;
+  std::vector<size_t> idx;
+  std::vector<std::pair<size_t, size_t>> undo;
+  explicit Sampler(unsigned seed, size_t N) : rng(seed), idx(N) { std::iota(idx.begin(), idx.end(), 0); }
+  void draw(size_t N, size_t b, uint32_t *out) {
+    if (b >= N) {
+      for (size_t i = 0; i < N; ++i) out[i] = (uint32_t)i;
+      return;
+    }
+    undo.clear();
+    for (size_t i = 0; i < b; ++i) {
+      std::uniform_int_distribution<size_t> dist(i, N - 1);
+      const size_t j = dist(rng);
+      std::swap(idx[i], idx[j]);
+      undo.emplace_back(i, j);
+    }
+    for (size_t i = 0; i < b; ++i) out[i] = (uint32_t)idx[i];
+    for (size_t q = undo.size(); q-- > 0;) std::swap(idx[undo[q].first], idx[undo[q].second]);
+  }
+  size_t pick(size_t hi_inclusive) {
+    std::uniform_int_distribution<size_t> d(0, hi_inclusive);
+    return d(rng);
+  }
+};
+
+// rows of X / T selected by idx into contiguous batch buffers (one warp per sample row)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ X, const float *__restrict__ T,
+                                                          const uint32_t *__restrict__ idx, int count, int in_dim,
+                                                          int out_dim, float *__restrict__ Xb, float *__restrict__ Tb) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < count; i += warps) {
+    const size_t src = idx[i];
+    const float *xs = X + src * in_dim;
+    float *xd = Xb + (size_t)i * in_dim;
+    if ((in_dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xb)) & 15u) == 0) {
+      for (int c = lane; c < in_dim / 4; c += 32)
+        reinterpret_cast<float4 *>(xd)[c] = __ldg(reinterpret_cast<const float4 *>(xs) + c);
+    } else {
+      for (int c = lane; c < in_dim; c += 32) xd[c] = __ldg(xs + c);
+    }
+    for (int c = lane; c < out_dim; c += 32) Tb[(size_t)i * out_dim + c] = __ldg(T + src * out_dim + c);
+  }
+}
+
+// v = g_t - g_k + mu   (s_lbfgs.hpp:225-228)
+__global__ void __launch_bounds__(256) vr_combine_kernel(size_t n, const float *__restrict__ gt, const float *__restrict__ gk,
+                                                         const float *__restrict__ mu, float *__restrict__ v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    v[i] = (gt[i] - gk[i]) + mu[i];
+}
+
+// u = mean of `count` ring slots (s_lbfgs.hpp:238-242); s = u - u_prev; w+- = u +- eps*s (:92-93)
+__global__ void __launch_bounds__(256) hvp_points_kernel(size_t n, size_t ld, const float *__restrict__ W, int count,
+                                                         float *__restrict__ u, const float *__restrict__ u_prev,
+                                                         int have_prev, float eps, float *__restrict__ s,
+                                                         float *__restrict__ wp, float *__restrict__ wm) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.0f;
+    for (int r = 0; r < count; ++r) acc += W[(size_t)r * ld + i]; // slot order == logical order only up to rotation: a sum
+    const float uu = acc / (float)count;
+    u[i] = uu;
+    if (have_prev) {
+      const float ss = uu - u_prev[i];
+      s[i] = ss;
+      wp[i] = fmaf(eps, ss, uu);
+      wm[i] = fmaf(-eps, ss, uu);
+    }
+  }
+}
+
+// y = (g+ - g-) / (2 eps)   (s_lbfgs.hpp:100)
+__global__ void __launch_bounds__(256) hvp_diff_kernel(size_t n, const float *__restrict__ gp, const float *__restrict__ gm,
+                                                       float inv_2eps, float *__restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = (gp[i] - gm[i]) * inv_2eps;
+}
+
+inline int vblocks(size_t n) { return (int)std::max<size_t>(1, std::min<size_t>(1184, (n + 255) / 256)); }
+
+} // namespace
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void b200_slbfgs_default_opts(b200_slbfgs_opts *o) {
+  if (!o) return;
+  o->max_iters = 100; o->tol = 1e-4f; o->step_size = 0.01f; o->batch_size = 128; // UnifiedConfig defaults, unified_optimization.hpp:26-48
+  o->memory = 10; o->L = 10; o->b_H = 0; o->lambda = 1e-4f; o->epsilon = 1e-4f; o->seed = 123; o->record = 1;
+}
+
+int b200_slbfgs_sample_stream(unsigned seed, long N, long b, int count, uint32_t *out_host) {
+  B200_REQUIRE(out_host && N > 0 && b > 0 && count >= 0, "bad argument");
+  Sampler s(seed, (size_t)N);
+  const size_t per = (size_t)std::min(b, N);
+  for (int c = 0; c < count; ++c) s.draw((size_t)N, (size_t)b, out_host + (size_t)c * per);
+  return B200_OK;
+}
+
+int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const float *input, const float *target,
+                      int total_samples, const b200_slbfgs_opts *opts, b200_history *hist) {
+  B200_REQUIRE(ctx && net, "null argument");
+  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  if (n <= 0 || params == nullptr) return B200_OK;
+  B200_REQUIRE((size_t)n == net->n && input && target && total_samples > 0, "bad argument");
+  b200_slbfgs_opts o;
+  if (opts) o = *opts; else b200_slbfgs_default_opts(&o);
+  B200_REQUIRE(o.batch_size > 0 && o.L > 0 && o.memory >= 0 && o.memory <= kMaxSlots - 1, "bad S-LBFGS options");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long launches0 = b200_launch_count();
+
+  const int N = total_samples, W = ctx->world, R = ctx->rank;
+  const int b = std::min(o.batch_size, N);
+  int b_H = o.b_H > 0 ? o.b_H : o.batch_size / 2; // unified_optimization.hpp:325
+  b_H = std::max(1, std::min(b_H, N));
+  int m_inner = N / o.batch_size;                 // :326-327
+  if (m_inner == 0) m_inner = 1;
+  const int M = o.memory, L = o.L, mp = M + 1, mod = M + 1;
+  const int in_dim = net->dims.front(), out_dim = net->dims.back();
+  const size_t Nn = (size_t)n, ld = (Nn + 3) & ~size_t(3);
+  // multi-GPU: every rank holds the full data set; each batch's index list is split into W contiguous chunks
+  B200_REQUIRE(b % W == 0 && b_H % W == 0 && N % W == 0, "batch sizes must be divisible by the number of ranks");
+
+  const float old_l2 = net->l2;
+  net->l2 = o.lambda;
+  struct RestoreL2 { b200_net *n; float v; ~RestoreL2() { n->l2 = v; } } restore{net, old_l2};
+
+  // ---- workspace ---------------------------------------------------------------------------------
+  const int nblk = lbfgs_dots_blocks(ctx, Nn);
+  const int ncols = kDotsCols * mp + 1;
+  const size_t state_bytes = lbfgs_state_bytes(M);
+  const size_t part_bytes = (sizeof(double) * (size_t)nblk * ncols + 255) & ~size_t(255);
+  const size_t vec = sizeof(float) * ld;
+  const int nvec = 13 + (L + 1) + 2 * mp; // wt mu gt gk v d u uprev s y wp wm gfull | w_history | S Y
+  const int maxb = std::max(b, b_H) / W;
+  const size_t xb_bytes = (sizeof(float) * (size_t)maxb * in_dim + 255) & ~size_t(255);
+  const size_t tb_bytes = (sizeof(float) * (size_t)maxb * out_dim + 255) & ~size_t(255);
+  // index streams of one epoch: m_inner mini-batches + at most m_inner/L H-batches
+  const size_t idx_cap = (size_t)m_inner * (b / W) + (size_t)(m_inner / L + 1) * (b_H / W);
+  const size_t idx_bytes = (sizeof(uint32_t) * idx_cap + 255) & ~size_t(255);
+  char *ws = nullptr;
+  const size_t total = state_bytes + part_bytes + vec * nvec + xb_bytes + tb_bytes + idx_bytes + 2 * sizeof(EvalOut) + 256;
+  B200_CUDA(cudaMalloc(&ws, total));
+  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
+  B200_CUDA(cudaMemsetAsync(ws, 0, total, st));
+  size_t off = 0;
+  LbfgsView view = lbfgs_view(ws + off, M); off += state_bytes;
+  double *partials = (double *)(ws + off); off += part_bytes;
+  auto take = [&](size_t bytes) { char *p = ws + off; off += bytes; return p; };
+  float *wt = (float *)take(vec), *mu = (float *)take(vec), *gt = (float *)take(vec), *gk = (float *)take(vec);
+  float *v = (float *)take(vec), *d = (float *)take(vec), *u = (float *)take(vec), *u_prev = (float *)take(vec);
+  float *s = (float *)take(vec), *y = (float *)take(vec), *wp = (float *)take(vec), *wm = (float *)take(vec);
+  float *gfull = (float *)take(vec);
+  float *Wh = (float *)take(vec * (L + 1));
+  float *S = (float *)take(vec * mp), *Y = (float *)take(vec * mp);
+  float *Xb = (float *)take(xb_bytes), *Tb = (float *)take(tb_bytes);
+  uint32_t *d_idx = (uint32_t *)take(idx_bytes);
+  EvalOut *ev_scratch = (EvalOut *)take(sizeof(EvalOut));
+  B200_TRY(lbfgs_init_state(view, M, mod, st));
+  uint32_t *h_idx = nullptr;
+  B200_CUDA(cudaMallocHost(&h_idx, sizeof(uint32_t) * idx_cap));
+  struct FreeHost { uint32_t *p; ~FreeHost() { cudaFreeHost(p); } } free_h{h_idx};
+
+  Sampler sampler(o.seed, (size_t)N);
+  std::vector<uint32_t> draw_buf((size_t)std::max(b, b_H));
+  double *h_mail = ctx->h_scalars;
+  long evals = 0;
+  const int apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (ld / 4 + 255) / 256));
+  const int shard_N = N / W;
+  const float *x_shard = input + (size_t)R * shard_N * in_dim, *t_shard = target + (size_t)R * shard_N * out_dim;
+
+  auto full_eval = [&](const float *w, float *g) -> int { // batch_g on the full index set + norm (:204-210)
+    ++evals;
+    B200_TRY(net_eval(net, w, x_shard, t_shard, shard_N, N, g, (EvalOut *)net->eval_out));
+    B200_CUDA(cudaMemcpyAsync(h_mail, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+  };
+
+  bool have_u_prev = false;   // !u_list.empty()
+  bool mu_valid = false;      // gfull holds the full gradient at `params` (from the recorder evaluation)
+  int iters = 0;
+  cudaEvent_t ev0 = ctx->ev_a, ev1 = ctx->ev_b;
+  float elapsed = 0.f;
+  while (iters < o.max_iters) {
+    if (hist) B200_CUDA(cudaEventRecord(ev0, st));
+    // 1. full gradient at the anchor (:204-206)
+    if (mu_valid) {
+      B200_CUDA(cudaMemcpyAsync(mu, gfull, vec, cudaMemcpyDeviceToDevice, st));
+    } else {
+      B200_TRY(full_eval(params, mu));
+    }
+    const double mu_norm = std::sqrt(h_mail[1]);
+    if (mu_norm < (double)o.tol) break; // :208-211
+    B200_CUDA(cudaMemcpyAsync(wt, params, sizeof(float) * Nn, cudaMemcpyDeviceToDevice, st));
+    // w_history.clear(); push_back(wt)  — physical slot = push count % (L+1)
+    int wh_pushes = 0;
+    B200_CUDA(cudaMemcpyAsync(Wh, params, sizeof(float) * Nn, cudaMemcpyDeviceToDevice, st));
+    wh_pushes = 1;
+
+    // ---- draw every index stream of this epoch in the reference's order (:220, :248) ---------------
+    size_t idx_used = 0;
+    std::vector<size_t> mb_off(m_inner), hb_off(m_inner, (size_t)-1);
+    bool u_nonempty = have_u_prev;
+    for (int t = 0; t < m_inner; ++t) {
+      sampler.draw((size_t)N, (size_t)b, draw_buf.data());
+      mb_off[t] = idx_used;
+      std::copy(draw_buf.begin() + (size_t)R * (b / W), draw_buf.begin() + (size_t)(R + 1) * (b / W), h_idx + idx_used);
+      idx_used += b / W;
+      if (t > 0 && t % L == 0) {
+        if (u_nonempty) {
+          sampler.draw((size_t)N, (size_t)b_H, draw_buf.data());
+          hb_off[t] = idx_used;
+          std::copy(draw_buf.begin() + (size_t)R * (b_H / W), draw_buf.begin() + (size_t)(R + 1) * (b_H / W),
+                    h_idx + idx_used);
+          idx_used += b_H / W;
+        }
+        u_nonempty = true;
+      }
+    }
+    B200_CUDA(cudaMemcpyAsync(d_idx, h_idx, sizeof(uint32_t) * idx_used, cudaMemcpyHostToDevice, st));
+
+    // 2. inner loop (:216-262)
+    for (int t = 0; t < m_inner; ++t) {
+      const int bl = b / W;
+      B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(bl, 8)), 256, 0, st, input, target, d_idx + mb_off[t], bl,
+                  in_dim, out_dim, Xb, Tb);
+      evals += 2;
+      B200_TRY(net_eval(net, wt, Xb, Tb, bl, b, gt, ev_scratch));
+      B200_TRY(net_eval(net, params, Xb, Tb, bl, b, gk, ev_scratch));
+      B200_LAUNCH(vr_combine_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, mu, v);
+      // direction = H v (two-loop on the current ring), w_t -= eta * direction, history push (:230-233)
+      DotsArgs da{S, Y, Nn, ld, view, v, nullptr, nullptr, nullptr, DOTS_NONE, 0, 0, partials};
+      B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
+      SolveArgs sa{view, partials, nblk, DOTS_NONE, 0, POLICY_SLBFGS, 0, 0, 0.0, 0};
+      B200_TRY(launch_lbfgs_solve(sa, mp, st));
+      float *wh_slot = Wh + (size_t)(wh_pushes % (L + 1)) * ld;
+      ApplyArgs aa{S, Y, Nn, ld, view, v, d, wt, nullptr, -1.0, -o.step_size, wh_slot};
+      B200_TRY(launch_lbfgs_apply(aa, apply_blocks, st));
+      ++wh_pushes;
+
+      // 3. curvature pair every L steps (:236-261)
+      if (t > 0 && t % L == 0) {
+        const int cnt = std::min(wh_pushes, L + 1);
+        B200_LAUNCH(hvp_points_kernel, vblocks(Nn), 256, 0, st, Nn, ld, Wh, cnt, u, u_prev, have_u_prev ? 1 : 0,
+                    o.epsilon, s, wp, wm);
+        if (have_u_prev) {
+          const int hl = b_H / W;
+          B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(hl, 8)), 256, 0, st, input, target, d_idx + hb_off[t],
+                      hl, in_dim, out_dim, Xb, Tb);
+          evals += 2;
+          B200_TRY(net_eval(net, wp, Xb, Tb, hl, b_H, gt, ev_scratch));
+          B200_TRY(net_eval(net, wm, Xb, Tb, hl, b_H, gk, ev_scratch));
+          B200_LAUNCH(hvp_diff_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, 1.0f / (2.0f * o.epsilon), y);
+          if (M > 0) {
+            B200_TRY(launch_lbfgs_store_pair(S, Y, Nn, ld, view, s, y, st));
+            DotsArgs dp{S, Y, Nn, ld, view, v, nullptr, nullptr, nullptr, DOTS_PAIR_IN_SLOT, 0, 0, partials};
+            B200_TRY(launch_lbfgs_dots(dp, mp, nblk, st));
+            SolveArgs sp{view, partials, nblk, DOTS_PAIR_IN_SLOT, 0, POLICY_SLBFGS, 0, 0, 0.0, 0};
+            B200_TRY(launch_lbfgs_solve(sp, mp, st));
+          }
+        }
+        B200_CUDA(cudaMemcpyAsync(u_prev, u, sizeof(float) * Nn, cudaMemcpyDeviceToDevice, st)); // u_list.push_back(u)
+        have_u_prev = true;
+      }
+    }
+
+    // anchor reset to a random earlier iterate (:265-270)
+    const int wsize = std::min(wh_pushes, L + 1);
+    if (wsize >= 2) {
+      const size_t pick = sampler.pick((size_t)wsize - 2);
+      const int head = (wh_pushes > L + 1) ? (wh_pushes % (L + 1)) : 0; // RingBuffer _head after wrap
+      const int phys = (int)((head + pick) % (size_t)(L + 1));
+      B200_CUDA(cudaMemcpyAsync(params, Wh + (size_t)phys * ld, sizeof(float) * Nn, cudaMemcpyDeviceToDevice, st));
+    } else {
+      B200_CUDA(cudaMemcpyAsync(params, wt, sizeof(float) * Nn, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // recorder: full loss and full gradient norm at the new anchor (:274-284); the gradient doubles as the
+    // next epoch's mu (same point), saving the reference's redundant evaluation
+    if (hist && o.record) {
+      B200_TRY(full_eval(params, gfull));
+      mu_valid = true;
+      B200_CUDA(cudaEventRecord(ev1, st));
+      B200_CUDA(cudaEventSynchronize(ev1));
+      float ms = 0.f;
+      B200_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+      elapsed += ms;
+      if (iters < hist->capacity) {
+        if (hist->loss) hist->loss[iters] = (float)h_mail[0];
+        if (hist->grad_norm) hist->grad_norm[iters] = (float)std::sqrt(h_mail[1]);
+        if (hist->time_ms) hist->time_ms[iters] = elapsed;
+        hist->size = iters + 1;
+      }
+    } else {
+      mu_valid = false;
+    }
+    ++iters;
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (hist) {
+    hist->iterations = iters;
+    hist->evaluations = evals;
+    hist->launches = b200_launch_count() - launches0;
+  }
+  return B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,530 @@
+// Minimizer strategies: CudaLBFGS / CudaGD / CudaSGD (src/cuda/lbfgs.cuh, gd.cuh, sgd.cuh) behind the C ABI.
+//
+// The control flow of each solve() follows the reference line by line (cited inline); what changes is
+// where the arithmetic happens. Per L-BFGS iteration the reference issues ~2k+6 blocking cuBLAS
+// reductions and ~2k+10 BLAS-1 / memcpy launches; here an iteration is
+//     dots -> solve -> apply(+ trial point) -> evaluation          (3 + evaluation kernels)
+// with ONE host synchronisation per line-search trial (the Armijo / Wolfe test itself, which the
+// reference also performs on the host).
+#include "lbfgs_kernels.cuh"
+#include "network.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+namespace b200 {
+
+namespace {
+
+struct HostMail { // pinned mailbox layout (ctx->h_scalars, 64 doubles)
+  double loss, gnorm2; // EvalOut
+  double gnew_dot_p;   // WOLFE
+  double pad;
+  LbfgsHeader hdr;     // copy of the device header after lbfgs_solve_kernel
+};
+static_assert(sizeof(HostMail) <= 64 * sizeof(double), "mailbox overflow");
+
+// Objective seen by the minimizers: either the library's own network (asynchronous, result on the
+// device) or a caller-supplied LossGradFun (synchronous, loss returned on the host).
+struct Objective {
+  b200_ctx *ctx;
+  b200_net *net;
+  b200_loss_grad_fn fn;
+  void *user;
+  const float *input, *target;
+  int batch;
+  long batch_global;
+  long evals = 0;
+  double *d_part = nullptr; // dot partials (callback path)
+  size_t n = 0;
+
+  // launches the evaluation of x into grad; the result lands in mail->loss / mail->gnorm2 after sync()
+  int eval_async(const float *x, float *grad, HostMail *mail, double *host_loss_cb) {
+    ++evals;
+    if (net) {
+      B200_TRY(net_eval(net, x, input, target, batch, batch_global, grad, (EvalOut *)net->eval_out));
+      B200_CUDA(cudaMemcpyAsync(&mail->loss, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
+      return B200_OK;
+    }
+    // reference calling convention (src/cuda/minimizer_base.cuh:15-16): blocking, loss on the host
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    *host_loss_cb = (double)fn(user, x, grad, input, target, batch);
+    B200_CUDA(cudaDeviceSynchronize()); // the callback may have used any stream
+    B200_TRY(launch_dot(ctx, grad, grad, n, d_part, ctx->d_scalars));
+    B200_CUDA(cudaMemcpyAsync(&mail->gnorm2, ctx->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return B200_OK;
+  }
+};
+
+struct Timer { // per-iteration CUDA-event timing exactly as src/cuda/lbfgs.cuh:80-91,176-182
+  b200_ctx *ctx;
+  bool on;
+  float elapsed = 0.f;
+  int start() {
+    if (on) B200_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    return B200_OK;
+  }
+  int stop() {
+    if (!on) return B200_OK;
+    B200_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    B200_CUDA(cudaEventSynchronize(ctx->ev_b));
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    elapsed += ms;
+    return B200_OK;
+  }
+};
+
+void record(b200_history *h, int idx, double loss, double gnorm, float ms) {
+  if (!h || idx >= h->capacity) return;
+  if (h->loss) h->loss[idx] = (float)loss;
+  if (h->grad_norm) h->grad_norm[idx] = (float)gnorm;
+  if (h->time_ms) h->time_ms[idx] = ms;
+  h->size = std::max(h->size, idx + 1);
+}
+
+long batch_global_of(b200_ctx *, long) {
+  // sample-sharded multi-GPU: the 1/B of the loss is the global batch; 0 lets net_eval resolve it
+  // (b200_net_set_global_batch, else shard batch x ranks)
+  return 0;
+}
+
+} // namespace
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void b200_lbfgs_default_opts(b200_lbfgs_opts *o) {
+  if (!o) return;
+  o->max_iters = 200; o->tol = 1e-6f; o->memory = 16; o->max_line_iters = 20; // minimizer_base.cuh:61-65, lbfgs.cuh:263
+  o->c1 = 1e-4f; o->rho = 0.5f; o->c2 = 0.9f;
+  o->linesearch = B200_LS_ARMIJO; o->record_timing = 1;
+}
+void b200_gd_default_opts(b200_gd_opts *o) {
+  if (!o) return;
+  o->max_iters = 200; o->tol = 1e-6f; o->lr = 0.01f; o->momentum = 0.9f; o->record_timing = 1;
+}
+void b200_sgd_default_opts(b200_sgd_opts *o) {
+  if (!o) return;
+  o->max_iters = 200; o->tol = 1e-6f; o->lr = 0.01f; o->momentum = 0.9f; o->decay_rate = 1.0f; o->decay_step = 0;
+  o->batch_size = 64; o->input_dim = 0; o->output_dim = 0; o->record_timing = 1;
+}
+
+// ===================================================================================================
+// CudaLBFGS::solve (src/cuda/lbfgs.cuh:39-194) / cpu_mlp::LBFGS::solve (src/minimizer/lbfgs.hpp:38-100)
+// ===================================================================================================
+int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
+                     const float *input, const float *target, int batch, const b200_lbfgs_opts *opts,
+                     b200_history *hist) {
+  B200_REQUIRE(ctx, "null ctx");
+  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  if (n <= 0 || params == nullptr) return B200_OK; // lbfgs.cuh:45-48: silent return, iterations() == 0
+  B200_REQUIRE(net || fn, "either a network or a loss_grad callback is required");
+  B200_REQUIRE(!net || (size_t)n == net->n, "n does not match the network's parameter count");
+  b200_lbfgs_opts o;
+  if (opts) o = *opts; else b200_lbfgs_default_opts(&o);
+  B200_REQUIRE(o.memory >= 0 && o.memory <= kMaxSlots - 1, "memory must be in [0, 256]");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long launches0 = b200_launch_count();
+
+  const int m = o.memory;
+  const bool wolfe = (o.linesearch == B200_LS_WOLFE);
+  const int policy = wolfe ? POLICY_WOLFE : POLICY_ARMIJO;
+  const int mod = wolfe ? m + 1 : std::max(m, 1);
+  const int mp = m + 1;
+  const size_t N = (size_t)n, ld = (N + 3) & ~size_t(3);
+
+  // one allocation for all work vectors (the reference allocates 6 + 2m DeviceBuffers per solve, lbfgs.cuh:53-71)
+  const int nblk = lbfgs_dots_blocks(ctx, N);
+  const int ncols = kDotsCols * mp + 1;
+  const size_t state_bytes = lbfgs_state_bytes(m);
+  const size_t part_bytes = sizeof(double) * (size_t)nblk * ncols;
+  const size_t dotp_bytes = sizeof(double) * (size_t)dot_blocks(ctx, N);
+  const size_t vec_bytes = sizeof(float) * ld;
+  char *ws = nullptr;
+  const size_t total = state_bytes + part_bytes + dotp_bytes + 256 + vec_bytes * (4 + 2 * (size_t)mp);
+  B200_CUDA(cudaMalloc(&ws, total));
+  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
+  B200_CUDA(cudaMemsetAsync(ws, 0, total, st));
+  size_t off = 0;
+  LbfgsView view = lbfgs_view(ws + off, m); off += state_bytes;
+  double *partials = (double *)(ws + off); off += part_bytes;
+  double *dot_part = (double *)(ws + off); off += dotp_bytes;
+  off = (off + 255) & ~size_t(255);
+  float *gbuf[2] = {(float *)(ws + off), (float *)(ws + off + vec_bytes)}; off += 2 * vec_bytes;
+  float *p = (float *)(ws + off); off += vec_bytes;
+  float *x_prev = (float *)(ws + off); off += vec_bytes;
+  float *S = (float *)(ws + off); off += vec_bytes * mp;
+  float *Y = (float *)(ws + off);
+  B200_TRY(lbfgs_init_state(view, m, mod, st));
+
+  HostMail *mail = (HostMail *)ctx->h_scalars;
+  Objective obj{ctx, net, fn, user, input, target, batch, batch_global_of(ctx, batch)};
+  obj.d_part = dot_part;
+  obj.n = N;
+  Timer timer{ctx, hist != nullptr && o.record_timing != 0};
+  const int apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (ld / 4 + 255) / 256));
+
+  double cb_loss = 0.0;
+  // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
+  B200_TRY(obj.eval_async(params, gbuf[0], mail, &cb_loss));
+  B200_CUDA(cudaStreamSynchronize(st));
+  double loss = net ? mail->loss : cb_loss;
+  double gnorm = std::sqrt(mail->gnorm2);
+
+  int cur = 0, iterations_done = 0, reset_next = 0;
+  const int max_ls = o.max_line_iters;
+  for (int iter = 0; iter < o.max_iters; ++iter) {
+    B200_TRY(timer.start());
+    if (gnorm < (double)o.tol) break; // lbfgs.cuh:92-93 / lbfgs.hpp:53-55
+    float *g = gbuf[cur], *g_new = gbuf[cur ^ 1];
+
+    // ---- direction: pair formation of the previous step + two-loop + first trial point, 3 launches ----
+    const int mode = (iter > 0 && m > 0) ? DOTS_FORM_PAIR : DOTS_NONE;
+    DotsArgs da{S, Y, N, ld, view, g, params, x_prev, gbuf[cur ^ 1], mode, reset_next, 0, partials};
+    B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
+    SolveArgs sa{view, partials, nblk, mode, reset_next, policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
+    B200_TRY(launch_lbfgs_solve(sa, mp, st));
+    ApplyArgs aa{S, Y, N, ld, view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
+    B200_TRY(launch_lbfgs_apply(aa, apply_blocks, st));
+    B200_CUDA(cudaMemcpyAsync(&mail->hdr, view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+    reset_next = 0;
+
+    // ---- line search ------------------------------------------------------------------------------
+    double loss_new = 0.0, gnorm2_new = 0.0, alpha = 1.0;
+    if (!wolfe) {
+      // Armijo backtracking with safeguarded quadratic interpolation (lbfgs.cuh:106-147)
+      bool armijo_ok = false, evaluated = false;
+      double gdotp = 0.0;
+      for (int ls = 0; ls < max_ls; ++ls) {
+        if (ls > 0) B200_TRY(launch_trial_point(N, x_prev, (float)alpha, p, params, st)); // lbfgs.cuh:116-117
+        B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
+        B200_CUDA(cudaStreamSynchronize(st));
+        if (ls == 0) { alpha = (double)(float)mail->hdr.alpha0; gdotp = mail->hdr.gdotp; }
+        loss_new = net ? mail->loss : cb_loss;
+        gnorm2_new = mail->gnorm2;
+        evaluated = true;
+        if (loss_new <= loss + (double)o.c1 * alpha * gdotp) { armijo_ok = true; break; }
+        const double denom = 2.0 * (loss_new - loss - gdotp * alpha);
+        bool fallback = true;
+        if (std::fabs(denom) > 1e-20) {
+          const double na = -(gdotp * alpha * alpha) / denom;
+          if (na >= 0.1 * alpha && na <= 0.9 * alpha) { alpha = na; fallback = false; }
+        }
+        if (fallback) alpha *= (double)o.rho;
+      }
+      if (!evaluated) { // max_line_iters == 0 (lbfgs.cuh:142-145): the fused first trial point stands
+        B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
+        B200_CUDA(cudaStreamSynchronize(st));
+        loss_new = net ? mail->loss : cb_loss;
+        gnorm2_new = mail->gnorm2;
+        armijo_ok = true;
+      }
+      if (!armijo_ok) reset_next = 1; // lbfgs.cuh:147 — the step is still accepted
+    } else {
+      // weak-Wolfe bisection / expansion (full_batch_minimizer.hpp:126-157); iteration 0 takes
+      // alpha = min(1, 1/||g||) without a line search (lbfgs.hpp:60-63)
+      B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
+      if (iter > 0) {
+        B200_TRY(launch_dot(ctx, g_new, p, N, dot_part, ctx->d_scalars + 1));
+        B200_CUDA(cudaMemcpyAsync(&mail->gnew_dot_p, ctx->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
+      B200_CUDA(cudaStreamSynchronize(st));
+      loss_new = net ? mail->loss : cb_loss;
+      gnorm2_new = mail->gnorm2;
+      alpha = (double)(float)mail->hdr.alpha0;
+      if (iter > 0) {
+        const double f_old = loss, gfo = mail->hdr.gdotp, inf = std::numeric_limits<double>::infinity();
+        double a_min = 0.0, a_max = inf;
+        bool at_alpha = true; // at_alpha: params/g_new currently hold the point for `alpha`
+        const int trials = o.max_line_iters > 0 ? o.max_line_iters : 50;
+        for (int i = 0; i < trials; ++i) {
+          if (!at_alpha) {
+            B200_TRY(launch_trial_point(N, x_prev, (float)alpha, p, params, st));
+            B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
+            B200_TRY(launch_dot(ctx, g_new, p, N, dot_part, ctx->d_scalars + 1));
+            B200_CUDA(cudaMemcpyAsync(&mail->gnew_dot_p, ctx->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            loss_new = net ? mail->loss : cb_loss;
+            gnorm2_new = mail->gnorm2;
+            at_alpha = true;
+          }
+          if (loss_new > f_old + (double)o.c1 * alpha * gfo) {
+            a_max = alpha;
+            alpha = (double)o.rho * (a_min + a_max);
+            at_alpha = false;
+            continue;
+          }
+          if (mail->gnew_dot_p < (double)o.c2 * gfo) {
+            a_min = alpha;
+            alpha = (a_max == inf) ? alpha * 2.0 : (double)o.rho * (a_min + a_max);
+            at_alpha = false;
+            continue;
+          }
+          break;
+        }
+        if (!at_alpha) { // trials exhausted: the reference steps with the last (unevaluated) alpha (:156, lbfgs.hpp:67-70)
+          B200_TRY(launch_trial_point(N, x_prev, (float)alpha, p, params, st));
+          B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
+          B200_CUDA(cudaStreamSynchronize(st));
+          loss_new = net ? mail->loss : cb_loss;
+          gnorm2_new = mail->gnorm2;
+        }
+      }
+    }
+
+    // accept: g <- g_new, loss <- loss_new (lbfgs.cuh:171-175); s, y are formed by the next dots pass
+    cur ^= 1;
+    loss = loss_new;
+    gnorm = std::sqrt(gnorm2_new);
+    B200_TRY(timer.stop());
+    record(hist, iterations_done, loss, gnorm, timer.elapsed);
+    ++iterations_done;
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (hist) {
+    hist->iterations = iterations_done;
+    hist->evaluations = obj.evals;
+    hist->launches = b200_launch_count() - launches0;
+  }
+  return B200_OK;
+}
+
+// ===================================================================================================
+// CudaGD::solve (src/cuda/gd.cuh:38-106)
+// ===================================================================================================
+int b200_gd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
+                  const float *input, const float *target, int batch, const b200_gd_opts *opts, b200_history *hist) {
+  B200_REQUIRE(ctx, "null ctx");
+  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  if (n <= 0 || params == nullptr) return B200_OK;
+  B200_REQUIRE(net || fn, "either a network or a loss_grad callback is required");
+  B200_REQUIRE(!net || (size_t)n == net->n, "n does not match the network's parameter count");
+  b200_gd_opts o;
+  if (opts) o = *opts; else b200_gd_default_opts(&o);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long launches0 = b200_launch_count();
+  const size_t N = (size_t)n;
+  char *ws = nullptr;
+  const size_t dotp_bytes = (sizeof(double) * (size_t)dot_blocks(ctx, N) + 255) & ~size_t(255);
+  B200_CUDA(cudaMalloc(&ws, dotp_bytes + 2 * sizeof(float) * N));
+  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
+  double *dot_part = (double *)ws;
+  float *grad = (float *)(ws + dotp_bytes), *vel = grad + N;
+  if (o.momentum > 0.0f) B200_CUDA(cudaMemsetAsync(vel, 0, sizeof(float) * N, st)); // gd.cuh:54-56
+
+  HostMail *mail = (HostMail *)ctx->h_scalars;
+  Objective obj{ctx, net, fn, user, input, target, batch, batch_global_of(ctx, batch)};
+  obj.d_part = dot_part;
+  obj.n = N;
+  Timer timer{ctx, hist != nullptr && o.record_timing != 0};
+  double cb_loss = 0.0;
+  B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
+  B200_CUDA(cudaStreamSynchronize(st));
+  double loss = net ? mail->loss : cb_loss;
+  double gnorm = std::sqrt(mail->gnorm2);
+  int iterations_done = 0;
+  for (int iter = 0; iter < o.max_iters; ++iter) {
+    B200_TRY(timer.start());
+    if (gnorm < (double)o.tol) break; // gd.cuh:70-71
+    if (o.momentum > 0.0f) B200_TRY(launch_momentum_step(N, o.momentum, o.lr, grad, vel, params, st)); // :73-81
+    else B200_TRY(launch_axpy(N, -o.lr, grad, params, st));                                             // :83-84
+    B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
+    B200_CUDA(cudaStreamSynchronize(st));
+    loss = net ? mail->loss : cb_loss;
+    gnorm = std::sqrt(mail->gnorm2);
+    B200_TRY(timer.stop());
+    record(hist, iterations_done, loss, gnorm, timer.elapsed);
+    ++iterations_done;
+  }
+  if (hist) {
+    hist->iterations = iterations_done;
+    hist->evaluations = obj.evals;
+    hist->launches = b200_launch_count() - launches0;
+  }
+  return B200_OK;
+}
+
+// ===================================================================================================
+// CudaSGD::solve (src/cuda/sgd.cuh:50-153): sequential, unshuffled mini-batches by pointer offset
+// ===================================================================================================
+int b200_sgd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
+                   const float *input, const float *target, int total_samples, const b200_sgd_opts *opts,
+                   b200_history *hist) {
+  B200_REQUIRE(ctx, "null ctx");
+  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  if (n <= 0 || params == nullptr) return B200_OK;
+  B200_REQUIRE(net || fn, "either a network or a loss_grad callback is required");
+  B200_REQUIRE(!net || (size_t)n == net->n, "n does not match the network's parameter count");
+  b200_sgd_opts o;
+  if (opts) o = *opts; else b200_sgd_default_opts(&o);
+  if (o.input_dim == 0 || o.output_dim == 0) { // sgd.cuh:61-65
+    fprintf(stderr, "Error: Dimensions not set for SGD\n");
+    return B200_OK;
+  }
+  B200_REQUIRE(o.batch_size > 0, "batch_size must be positive");
+  B200_REQUIRE(ctx->world == 1, "CudaSGD is single-GPU (sequential mini-batches)");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long launches0 = b200_launch_count();
+  const size_t N = (size_t)n;
+  char *ws = nullptr;
+  const size_t dotp_bytes = (sizeof(double) * (size_t)dot_blocks(ctx, N) + 255) & ~size_t(255);
+  B200_CUDA(cudaMalloc(&ws, dotp_bytes + 2 * sizeof(float) * N));
+  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
+  double *dot_part = (double *)ws;
+  float *grad = (float *)(ws + dotp_bytes), *vel = grad + N;
+  if (o.momentum > 0.0f) B200_CUDA(cudaMemsetAsync(vel, 0, sizeof(float) * N, st));
+
+  HostMail *mail = (HostMail *)ctx->h_scalars;
+  Objective full{ctx, net, fn, user, input, target, total_samples, (long)total_samples};
+  full.d_part = dot_part;
+  full.n = N;
+  Timer timer{ctx, hist != nullptr && o.record_timing != 0};
+  long evals = 0;
+  double cb_loss = 0.0;
+  float current_lr = o.lr;
+  const int num_batches = (total_samples + o.batch_size - 1) / o.batch_size;
+  float prev_epoch_loss_avg = std::numeric_limits<float>::infinity();
+  int iterations_done = 0;
+  if (hist) { // sgd.cuh:89-94: initial full-batch record at index 0
+    B200_TRY(full.eval_async(params, grad, mail, &cb_loss));
+    B200_CUDA(cudaStreamSynchronize(st));
+    record(hist, iterations_done, net ? mail->loss : cb_loss, std::sqrt(mail->gnorm2), 0.f);
+    ++iterations_done;
+  }
+  for (int iter = 0; iter < o.max_iters; ++iter) {
+    B200_TRY(timer.start());
+    if (o.decay_step > 0 && iter > 0 && iter % o.decay_step == 0) current_lr *= o.decay_rate; // :97-99
+    float epoch_loss_sum = 0.0f;
+    for (int b = 0; b < num_batches; ++b) {
+      const int start_idx = b * o.batch_size;
+      const int cbs = std::min(o.batch_size, total_samples - start_idx);
+      Objective mb{ctx, net, fn, user, input + (size_t)start_idx * o.input_dim, target + (size_t)start_idx * o.output_dim,
+                   cbs, (long)cbs};
+      mb.d_part = dot_part;
+      mb.n = N;
+      B200_TRY(mb.eval_async(params, grad, mail, &cb_loss));
+      ++evals;
+      if (o.momentum > 0.0f) B200_TRY(launch_momentum_step(N, o.momentum, current_lr, grad, vel, params, st));
+      else B200_TRY(launch_axpy(N, -current_lr, grad, params, st));
+      // the epoch-average needs every mini-batch loss on the host (sgd.cuh:124); the copy was queued by
+      // eval_async, so this sync also covers the parameter update
+      B200_CUDA(cudaStreamSynchronize(st));
+      const float bl = (float)(net ? mail->loss : cb_loss);
+      epoch_loss_sum += bl * (float)cbs;
+    }
+    const float epoch_loss_avg = epoch_loss_sum / (float)total_samples;
+    if (o.tol > 0.0f && std::isfinite(prev_epoch_loss_avg)) { // :128-133
+      const float denom = std::max(1.0f, std::fabs(prev_epoch_loss_avg));
+      const float rel = std::fabs(prev_epoch_loss_avg - epoch_loss_avg) / denom;
+      if (rel < o.tol) break;
+    }
+    prev_epoch_loss_avg = epoch_loss_avg;
+    if (hist) { // :136-147
+      B200_TRY(full.eval_async(params, grad, mail, &cb_loss));
+      B200_CUDA(cudaStreamSynchronize(st));
+      B200_TRY(timer.stop());
+      record(hist, iterations_done, net ? mail->loss : cb_loss, std::sqrt(mail->gnorm2), timer.elapsed);
+    }
+    ++iterations_done;
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (hist) {
+    hist->iterations = iterations_done;
+    hist->evaluations = evals + full.evals;
+    hist->launches = b200_launch_count() - launches0;
+  }
+  return B200_OK;
+}
+
+// ===================================================================================================
+// building blocks
+// ===================================================================================================
+int b200_lbfgs_direction(b200_ctx *ctx, size_t n, int k, const float *S_dev, const float *Y_dev, const float *rho_host,
+                         const float *g_dev, int policy, float *p_dev, double *g_dot_p_host) {
+  B200_REQUIRE(ctx && g_dev && p_dev, "null argument");
+  B200_REQUIRE(k >= 0 && k <= kMaxSlots - 1, "k must be in [0, 256]");
+  B200_REQUIRE(k == 0 || (S_dev && Y_dev && rho_host), "history arrays required");
+  B200_REQUIRE(policy >= 0 && policy <= 2, "unknown policy");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int m = std::max(k, 1), mp = m + 1;
+  const int nblk = lbfgs_dots_blocks(ctx, n);
+  const int ncols = kDotsCols * mp + 1;
+  const size_t state_bytes = lbfgs_state_bytes(m);
+  char *ws = nullptr;
+  B200_CUDA(cudaMalloc(&ws, state_bytes + sizeof(double) * (size_t)nblk * ncols));
+  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
+  LbfgsView view = lbfgs_view(ws, m);
+  double *partials = (double *)(ws + state_bytes);
+  B200_TRY(lbfgs_init_state(view, m, mp, st));
+  // caller's arrays are k x n row-major in logical order: slot i = row i, ring modulus m+1 never wraps
+  float *S = const_cast<float *>(S_dev), *Y = const_cast<float *>(Y_dev);
+  if (k == 0) {
+    DotsArgs da{S, Y, n, n, view, g_dev, nullptr, nullptr, nullptr, DOTS_NONE, 0, 0, partials};
+    B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
+    SolveArgs sa{view, partials, nblk, DOTS_NONE, 0, policy, 0, 0, 0.0, 0};
+    B200_TRY(launch_lbfgs_solve(sa, mp, st));
+  }
+  for (int w = 0; w < k; ++w) { // build the Gram blocks one slot at a time (head == w before each pass)
+    DotsArgs da{S, Y, n, n, view, g_dev, nullptr, nullptr, nullptr, DOTS_PAIR_IN_SLOT, 0, 0, partials};
+    B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
+    SolveArgs sa{view, partials, nblk, DOTS_PAIR_IN_SLOT, 0, policy, 0, 1, (double)rho_host[w], 0};
+    B200_TRY(launch_lbfgs_solve(sa, mp, st));
+  }
+  const int apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (n / 4 + 255) / 256));
+  ApplyArgs aa{S, Y, n, n, view, g_dev, p_dev, nullptr, nullptr, policy == POLICY_SLBFGS ? -1.0 : 1.0, 0.0f, nullptr};
+  B200_TRY(launch_lbfgs_apply(aa, apply_blocks, st));
+  HostMail *mail = (HostMail *)ctx->h_scalars;
+  B200_CUDA(cudaMemcpyAsync(&mail->hdr, view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (g_dot_p_host) *g_dot_p_host = mail->hdr.gdotp * (policy == POLICY_SLBFGS ? -1.0 : 1.0);
+  return B200_OK;
+}
+
+int b200_vec_dot(b200_ctx *ctx, const float *x, const float *y, size_t n, double *out_host) {
+  B200_REQUIRE(ctx && x && y && out_host, "null argument");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  double *part = nullptr;
+  B200_CUDA(cudaMalloc(&part, sizeof(double) * (size_t)dot_blocks(ctx, n)));
+  struct Free { double *p; ~Free() { cudaFree(p); } } f{part};
+  B200_TRY(launch_dot(ctx, x, y, n, part, ctx->d_scalars));
+  B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out_host = ctx->h_scalars[0];
+  return B200_OK;
+}
+int b200_vec_nrm2(b200_ctx *ctx, const float *x, size_t n, double *out_host) {
+  B200_TRY(b200_vec_dot(ctx, x, x, n, out_host));
+  *out_host = std::sqrt(*out_host);
+  return B200_OK;
+}
+int b200_vec_axpy(b200_ctx *ctx, size_t n, float alpha, const float *x, float *y) {
+  B200_REQUIRE(ctx && x && y, "null argument");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return launch_axpy(n, alpha, x, y, ctx->stream);
+}
+int b200_vec_scal(b200_ctx *ctx, size_t n, float alpha, float *x) {
+  B200_REQUIRE(ctx && x, "null argument");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return launch_scal(n, alpha, x, ctx->stream);
+}
+int b200_vec_trial_point(b200_ctx *ctx, size_t n, const float *x0, float alpha, const float *p, float *y) {
+  B200_REQUIRE(ctx && x0 && p && y, "null argument");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return launch_trial_point(n, x0, alpha, p, y, ctx->stream);
+}
+int b200_convert_f64_to_f32(b200_ctx *ctx, const double *src_dev, float *dst_dev, size_t n) {
+  B200_REQUIRE(ctx && src_dev && dst_dev, "null argument");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return launch_f64_to_f32(n, src_dev, dst_dev, ctx->stream);
+}
+
+} // extern "C"
