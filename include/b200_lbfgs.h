@@ -50,6 +50,10 @@ void *b200_ctx_stream(b200_ctx *ctx); /* cudaStream_t the library launches on */
 /* adopt a caller-owned stream (e.g. the host framework's current stream); NULL restores the library's own */
 int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
 int b200_ctx_device(b200_ctx *ctx);
+/* per-launch CUDA-event profiling of the library's own kernels (bench.py's roofline figures): enable, run,
+ * then report writes a JSON object {"kernel-class": [launches, total_ms], ...} into json_out. */
+int b200_ctx_profile(b200_ctx *ctx, int enable);
+int b200_ctx_profile_report(b200_ctx *ctx, char *json_out, size_t capacity);
 /* multi-GPU: one process per GPU. Rank 0 calls b200_comm_unique_id and ships the 128 bytes to the
  * other ranks (torch.distributed / MPI / file); every rank then calls b200_ctx_init_comm. */
 int b200_comm_unique_id(void *out_128_bytes);
@@ -143,6 +147,15 @@ void b200_lbfgs_default_opts(b200_lbfgs_opts *o);
 int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
                      const float *input, const float *target, int batch, const b200_lbfgs_opts *opts,
                      b200_history *hist);
+/* The same solve as a resumable object: create allocates the work vectors the reference allocates per solve()
+ * (lbfgs.cuh:53-71); each run continues the SAME minimisation for up to `iters` more iterations (the first run
+ * performs the initial evaluation, lbfgs.cuh:78). b200_lbfgs_solve == create + run(max_iters) + destroy.
+ * hist (may be NULL) is filled from index 0 on every run. */
+typedef struct b200_lbfgs b200_lbfgs;
+int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lbfgs **out);
+int b200_lbfgs_run(b200_lbfgs *solver, b200_net *net, b200_loss_grad_fn fn, void *user, float *params,
+                   const float *input, const float *target, int batch, int iters, b200_history *hist);
+int b200_lbfgs_destroy(b200_lbfgs *solver);
 
 typedef struct b200_gd_opts { /* src/cuda/gd.cuh:108-110 */
   int max_iters;              /* 200 */

@@ -58,6 +58,8 @@ SYMBOLS = {
     "b200_ctx_stream": (_vp, [_vp]),
     "b200_ctx_set_stream": (_i, [_vp, _vp]),
     "b200_ctx_device": (_i, [_vp]),
+    "b200_ctx_profile": (_i, [_vp, _i]),
+    "b200_ctx_profile_report": (_i, [_vp, C.c_char_p, _sz]),
     "b200_comm_unique_id": (_i, [_vp]),
     "b200_ctx_init_comm": (_i, [_vp, _vp, _i, _i]),
     "b200_ctx_rank": (_i, [_vp]),
@@ -92,6 +94,9 @@ SYMBOLS = {
     "b200_lbfgs_default_opts": (None, [C.POINTER(LbfgsOpts)]),
     "b200_lbfgs_solve": (_i, [_vp, _vp, LOSS_GRAD_FN, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(LbfgsOpts),
                               C.POINTER(History)]),
+    "b200_lbfgs_create": (_i, [_vp, _i, C.POINTER(LbfgsOpts), C.POINTER(_vp)]),
+    "b200_lbfgs_run": (_i, [_vp, _vp, LOSS_GRAD_FN, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(History)]),
+    "b200_lbfgs_destroy": (_i, [_vp]),
     "b200_gd_default_opts": (None, [C.POINTER(GdOpts)]),
     "b200_gd_solve": (_i, [_vp, _vp, LOSS_GRAD_FN, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(GdOpts), C.POINTER(History)]),
     "b200_sgd_default_opts": (None, [C.POINTER(SgdOpts)]),

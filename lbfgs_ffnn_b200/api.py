@@ -66,6 +66,16 @@ class CublasHandle:
     def set_stream(self, cuda_stream):
         check(lib().b200_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def profile(self, enable=True):
+        check(lib().b200_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_report(self):
+        """{kernel class: (launches, total_ms)} measured with CUDA events around each launch"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().b200_ctx_profile_report(self._h, buf, len(buf)))
+        return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}
+
     @staticmethod
     def unique_id():
         buf = (C.c_char * 128)()
@@ -377,15 +387,38 @@ class CudaLBFGS(CudaMinimizerBase):
         """'armijo' = reference CUDA backend; 'wolfe' = reference CPU backend"""
         self.linesearch_, self.c2_ = policy, float(c2)
 
-    def solve(self, n, params, input_dev, target_dev, batch, loss_grad):
-        """loss_grad: a CudaNetwork (fast path, the network's own objective) or a Python callable
-        f(params_ptr, grad_ptr, input_ptr, target_ptr, batch) -> float (the reference's LossGradFun)."""
+    def _opts(self):
         o = _lib.LbfgsOpts()
         lib().b200_lbfgs_default_opts(C.byref(o))
         o.max_iters, o.tol, o.memory = self.max_iters_, self.tol_, self.m_
         o.max_line_iters, o.c1, o.rho, o.c2 = self.max_line_iters_, self.c1_, self.rho_, self.c2_
         o.linesearch = LS[self.linesearch_]
         o.record_timing = 1
+        return o
+
+    # resumable form (b200_lbfgs_create / run / destroy): the same minimisation continued in slices
+    def begin(self, n):
+        self.end()
+        self._solver = C.c_void_p()
+        o = self._opts()
+        check(lib().b200_lbfgs_create(self.handle._h, int(n), C.byref(o), C.byref(self._solver)))
+
+    def run(self, params, input_dev, target_dev, batch, iters, loss_grad):
+        cb, net_h = self._callback(loss_grad)
+        h = self._history()
+        check(lib().b200_lbfgs_run(self._solver, net_h, cb, None, C.c_void_p(_ptr(params)), C.c_void_p(_ptr(input_dev)),
+                                   C.c_void_p(_ptr(target_dev)), int(batch), int(iters), C.byref(h)))
+        self._finish(h)
+
+    def end(self):
+        if getattr(self, "_solver", None):
+            lib().b200_lbfgs_destroy(self._solver)
+        self._solver = None
+
+    def solve(self, n, params, input_dev, target_dev, batch, loss_grad):
+        """loss_grad: a CudaNetwork (fast path, the network's own objective) or a Python callable
+        f(params_ptr, grad_ptr, input_ptr, target_ptr, batch) -> float (the reference's LossGradFun)."""
+        o = self._opts()
         cb, net_h = self._callback(loss_grad)
         h = self._history()
         check(lib().b200_lbfgs_solve(self.handle._h, net_h, cb, None, int(n), C.c_void_p(_ptr(params) or 0),

@@ -58,8 +58,35 @@ NcclApi *nccl_api(); // nullptr (and error set) if libnccl cannot be loaded
 
 } // namespace b200
 
+// ---- per-launch profiling (CUDA events on the launching stream; no sync until the report) ---------
+namespace b200 {
+struct Profiler {
+  bool on = false;
+  std::vector<std::string> names;
+  struct Entry { int id; cudaEvent_t a, b; };
+  std::vector<Entry> entries;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      if (pool.size() >= (1u << 17)) return nullptr;
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  int id_of(const char *name) {
+    for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) return (int)i;
+    names.emplace_back(name);
+    return (int)names.size() - 1;
+  }
+};
+} // namespace b200
+
 // ---- context ---------------------------------------------------------------------------------------
 struct b200_ctx {
+  b200::Profiler prof;
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -74,6 +101,23 @@ struct b200_ctx {
 };
 
 namespace b200 {
+
+// brackets the launches issued during its lifetime with two events when profiling is enabled
+struct ProfScope {
+  b200_ctx *ctx;
+  cudaEvent_t b = nullptr;
+  ProfScope(b200_ctx *c, const char *name) : ctx(c) {
+    if (!c->prof.on) return;
+    cudaEvent_t a = c->prof.get();
+    b = c->prof.get();
+    if (!a || !b) { b = nullptr; return; }
+    c->prof.entries.push_back({c->prof.id_of(name), a, b});
+    cudaEventRecord(a, c->stream);
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, ctx->stream);
+  }
+};
 
 int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev); // grad (float) + 1 double
 int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n);

@@ -146,12 +146,47 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   if (ctx->comm) {
     if (NcclApi *api = nccl_api()) api->CommDestroy((ncclComm_t)ctx->comm);
   }
+  for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_a);
   cudaEventDestroy(ctx->ev_b);
   cudaFreeHost(ctx->h_scalars);
   cudaFree(ctx->d_scalars);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
+  return B200_OK;
+}
+
+int b200_ctx_profile(b200_ctx *ctx, int enable) {
+  B200_REQUIRE(ctx, "null ctx");
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->prof.on = enable != 0;
+  ctx->prof.entries.clear();
+  ctx->prof.used = 0;
+  return B200_OK;
+}
+
+int b200_ctx_profile_report(b200_ctx *ctx, char *json_out, size_t capacity) {
+  B200_REQUIRE(ctx && json_out && capacity > 2, "bad argument");
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<double> ms(ctx->prof.names.size(), 0.0);
+  std::vector<long> calls(ctx->prof.names.size(), 0);
+  for (const auto &e : ctx->prof.entries) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) {
+      ms[e.id] += t;
+      calls[e.id] += 1;
+    }
+  }
+  std::string out = "{";
+  for (size_t i = 0; i < ms.size(); ++i) {
+    if (!calls[i]) continue;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": [%ld, %.6f]", out.size() > 1 ? ", " : "", ctx->prof.names[i].c_str(), calls[i], ms[i]);
+    out += buf;
+  }
+  out += "}";
+  B200_REQUIRE(out.size() + 1 <= capacity, "report buffer too small");
+  memcpy(json_out, out.c_str(), out.size() + 1);
   return B200_OK;
 }
 

@@ -238,8 +238,13 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
     bool done = false;
-    if (!last && net->prec != B200_PREC_FP32) B200_TRY(tc_forward_layer(net, l, params, cur, batch, &done));
-    if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, last, t, inv_batch));
+    {
+      char nm[16];
+      snprintf(nm, sizeof(nm), "fwd%d", l);
+      ProfScope ps(ctx, nm);
+      if (!last && net->prec != B200_PREC_FP32) B200_TRY(tc_forward_layer(net, l, params, cur, batch, &done));
+      if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, last, t, inv_batch));
+    }
     cur = net->act[l];
   }
   net->last_batch = batch;
@@ -250,6 +255,9 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     const float *W = params + net->offs[l];
     const float *in = (l == 0) ? x : net->act[l - 1];
     if (l > 0) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
+      char nm[16];
+      snprintf(nm, sizeof(nm), "dx%d", l);
+      ProfScope ps(ctx, nm);
       GemmParams p{};
       p.A = net->delta[l]; p.lda = N;
       p.B = W; p.ldb = N;
@@ -264,6 +272,9 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       B200_TRY((launch_gemm_simt<true, true, EPI_DX>(p, 1, st)));
     }
     { // [dW; db] partials = [A_{l-1} | 1]^T delta_l over batch slices
+      char nm[16];
+      snprintf(nm, sizeof(nm), "dw%d", l);
+      ProfScope ps(ctx, nm);
       bool done = false;
       if (net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
       if (!done) {
@@ -296,11 +307,15 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   fp.lam = net->l2 / (float)ctx->world; // each rank adds its share; the all-reduce sums them
   fp.grad = grad_out;
   fp.fin_part = net->fin_part;
-  B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);
   const bool multi = ctx->world > 1;
-  B200_LAUNCH(eval_scalars_kernel, 1, 256, 0, st, net->loss_part, net->loss_part_n, net->fin_part, net->fin_blocks,
-              (double)inv_batch, (double)fp.lam, multi ? 0 : 1, out);
+  {
+    ProfScope ps(ctx, "finalize");
+    B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);
+    B200_LAUNCH(eval_scalars_kernel, 1, 256, 0, st, net->loss_part, net->loss_part_n, net->fin_part, net->fin_blocks,
+                (double)inv_batch, (double)fp.lam, multi ? 0 : 1, out);
+  }
   if (multi) {
+    ProfScope ps(ctx, "allreduce");
     B200_TRY(ctx_allreduce(ctx, grad_out, net->n, &out->loss));
     B200_LAUNCH(sumsq_part_kernel, net->fin_blocks, 256, 0, st, grad_out, (unsigned long long)net->n, net->fin_part);
     B200_LAUNCH(gnorm_from_parts_kernel, 1, 256, 0, st, net->fin_part, net->fin_blocks, out);

@@ -117,83 +117,144 @@ void b200_sgd_default_opts(b200_sgd_opts *o) {
 // ===================================================================================================
 // CudaLBFGS::solve (src/cuda/lbfgs.cuh:39-194) / cpu_mlp::LBFGS::solve (src/minimizer/lbfgs.hpp:38-100)
 // ===================================================================================================
-int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
-                     const float *input, const float *target, int batch, const b200_lbfgs_opts *opts,
-                     b200_history *hist) {
-  B200_REQUIRE(ctx, "null ctx");
-  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
-  if (n <= 0 || params == nullptr) return B200_OK; // lbfgs.cuh:45-48: silent return, iterations() == 0
-  B200_REQUIRE(net || fn, "either a network or a loss_grad callback is required");
-  B200_REQUIRE(!net || (size_t)n == net->n, "n does not match the network's parameter count");
+} // extern "C"
+
+struct b200_lbfgs {
+  b200_ctx *ctx = nullptr;
+  b200_lbfgs_opts o{};
+  size_t N = 0, ld = 0;
+  int m = 0, mp = 1, mod = 1, policy = POLICY_ARMIJO;
+  int nblk = 1, apply_blocks = 1;
+  char *ws = nullptr;
+  LbfgsView view{};
+  double *partials = nullptr, *dot_part = nullptr;
+  float *gbuf[2] = {nullptr, nullptr}, *p = nullptr, *x_prev = nullptr, *S = nullptr, *Y = nullptr;
+  // minimisation state carried across runs
+  bool started = false;
+  int cur = 0, iter = 0, reset_next = 0;
+  double loss = 0.0, gnorm = 0.0;
+};
+
+extern "C" {
+
+int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lbfgs **out) {
+  B200_REQUIRE(ctx && out && n > 0, "bad argument");
   b200_lbfgs_opts o;
   if (opts) o = *opts; else b200_lbfgs_default_opts(&o);
   B200_REQUIRE(o.memory >= 0 && o.memory <= kMaxSlots - 1, "memory must be in [0, 256]");
   B200_CUDA(cudaSetDevice(ctx->device));
+  b200_lbfgs *s = new b200_lbfgs;
+  s->ctx = ctx;
+  s->o = o;
+  s->m = o.memory;
+  const bool wolfe = (o.linesearch == B200_LS_WOLFE);
+  s->policy = wolfe ? POLICY_WOLFE : POLICY_ARMIJO;
+  s->mod = wolfe ? s->m + 1 : std::max(s->m, 1);
+  s->mp = s->m + 1;
+  s->N = (size_t)n;
+  s->ld = (s->N + 3) & ~size_t(3);
+  // one allocation for all work vectors (the reference allocates 6 + 2m DeviceBuffers per solve, lbfgs.cuh:53-71)
+  s->nblk = lbfgs_dots_blocks(ctx, s->N);
+  const int ncols = kDotsCols * s->mp + 1;
+  const size_t state_bytes = lbfgs_state_bytes(s->m);
+  const size_t part_bytes = sizeof(double) * (size_t)s->nblk * ncols;
+  const size_t dotp_bytes = sizeof(double) * (size_t)dot_blocks(ctx, s->N);
+  const size_t vec_bytes = sizeof(float) * s->ld;
+  const size_t total = state_bytes + part_bytes + dotp_bytes + 256 + vec_bytes * (4 + 2 * (size_t)s->mp);
+  if (cudaMalloc(&s->ws, total) != cudaSuccess) {
+    delete s;
+    set_error("cudaMalloc of %zu bytes of L-BFGS work space failed", total);
+    return B200_ERR_CUDA;
+  }
+  cudaStream_t st = ctx->stream;
+  B200_CUDA(cudaMemsetAsync(s->ws, 0, total, st));
+  size_t off = 0;
+  s->view = lbfgs_view(s->ws + off, s->m); off += state_bytes;
+  s->partials = (double *)(s->ws + off); off += part_bytes;
+  s->dot_part = (double *)(s->ws + off); off += dotp_bytes;
+  off = (off + 255) & ~size_t(255);
+  s->gbuf[0] = (float *)(s->ws + off); s->gbuf[1] = (float *)(s->ws + off + vec_bytes); off += 2 * vec_bytes;
+  s->p = (float *)(s->ws + off); off += vec_bytes;
+  s->x_prev = (float *)(s->ws + off); off += vec_bytes;
+  s->S = (float *)(s->ws + off); off += vec_bytes * s->mp;
+  s->Y = (float *)(s->ws + off);
+  B200_TRY(lbfgs_init_state(s->view, s->m, s->mod, st));
+  s->apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (s->ld / 4 + 255) / 256));
+  *out = s;
+  return B200_OK;
+}
+
+int b200_lbfgs_destroy(b200_lbfgs *s) {
+  if (!s) return B200_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->ws);
+  delete s;
+  return B200_OK;
+}
+
+int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *user, float *params, const float *input,
+                   const float *target, int batch, int iters, b200_history *hist) {
+  B200_REQUIRE(s && params, "null argument");
+  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  B200_REQUIRE(net || fn, "either a network or a loss_grad callback is required");
+  B200_REQUIRE(!net || s->N == net->n, "n does not match the network's parameter count");
+  b200_ctx *ctx = s->ctx;
+  const b200_lbfgs_opts &o = s->o;
+  B200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const long launches0 = b200_launch_count();
-
-  const int m = o.memory;
-  const bool wolfe = (o.linesearch == B200_LS_WOLFE);
-  const int policy = wolfe ? POLICY_WOLFE : POLICY_ARMIJO;
-  const int mod = wolfe ? m + 1 : std::max(m, 1);
-  const int mp = m + 1;
-  const size_t N = (size_t)n, ld = (N + 3) & ~size_t(3);
-
-  // one allocation for all work vectors (the reference allocates 6 + 2m DeviceBuffers per solve, lbfgs.cuh:53-71)
-  const int nblk = lbfgs_dots_blocks(ctx, N);
-  const int ncols = kDotsCols * mp + 1;
-  const size_t state_bytes = lbfgs_state_bytes(m);
-  const size_t part_bytes = sizeof(double) * (size_t)nblk * ncols;
-  const size_t dotp_bytes = sizeof(double) * (size_t)dot_blocks(ctx, N);
-  const size_t vec_bytes = sizeof(float) * ld;
-  char *ws = nullptr;
-  const size_t total = state_bytes + part_bytes + dotp_bytes + 256 + vec_bytes * (4 + 2 * (size_t)mp);
-  B200_CUDA(cudaMalloc(&ws, total));
-  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
-  B200_CUDA(cudaMemsetAsync(ws, 0, total, st));
-  size_t off = 0;
-  LbfgsView view = lbfgs_view(ws + off, m); off += state_bytes;
-  double *partials = (double *)(ws + off); off += part_bytes;
-  double *dot_part = (double *)(ws + off); off += dotp_bytes;
-  off = (off + 255) & ~size_t(255);
-  float *gbuf[2] = {(float *)(ws + off), (float *)(ws + off + vec_bytes)}; off += 2 * vec_bytes;
-  float *p = (float *)(ws + off); off += vec_bytes;
-  float *x_prev = (float *)(ws + off); off += vec_bytes;
-  float *S = (float *)(ws + off); off += vec_bytes * mp;
-  float *Y = (float *)(ws + off);
-  B200_TRY(lbfgs_init_state(view, m, mod, st));
+  const size_t N = s->N, ld = s->ld;
+  const int m = s->m, mp = s->mp;
+  const bool wolfe = (s->policy == POLICY_WOLFE);
+  float *p = s->p, *x_prev = s->x_prev, *S = s->S, *Y = s->Y;
+  double *dot_part = s->dot_part;
 
   HostMail *mail = (HostMail *)ctx->h_scalars;
   Objective obj{ctx, net, fn, user, input, target, batch, batch_global_of(ctx, batch)};
   obj.d_part = dot_part;
   obj.n = N;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
-  const int apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (ld / 4 + 255) / 256));
 
   double cb_loss = 0.0;
-  // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
-  B200_TRY(obj.eval_async(params, gbuf[0], mail, &cb_loss));
-  B200_CUDA(cudaStreamSynchronize(st));
-  double loss = net ? mail->loss : cb_loss;
-  double gnorm = std::sqrt(mail->gnorm2);
+  if (!s->started) {
+    // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
+    B200_TRY(obj.eval_async(params, s->gbuf[0], mail, &cb_loss));
+    B200_CUDA(cudaStreamSynchronize(st));
+    s->loss = net ? mail->loss : cb_loss;
+    s->gnorm = std::sqrt(mail->gnorm2);
+    s->started = true;
+    s->cur = 0; s->iter = 0; s->reset_next = 0;
+  }
 
-  int cur = 0, iterations_done = 0, reset_next = 0;
+  int iterations_done = 0;
   const int max_ls = o.max_line_iters;
-  for (int iter = 0; iter < o.max_iters; ++iter) {
+  for (int it = 0; it < iters; ++it) {
+    const int iter = s->iter;
     B200_TRY(timer.start());
-    if (gnorm < (double)o.tol) break; // lbfgs.cuh:92-93 / lbfgs.hpp:53-55
-    float *g = gbuf[cur], *g_new = gbuf[cur ^ 1];
+    if (s->gnorm < (double)o.tol) break; // lbfgs.cuh:92-93 / lbfgs.hpp:53-55
+    float *g = s->gbuf[s->cur], *g_new = s->gbuf[s->cur ^ 1];
+    const double loss = s->loss;
 
     // ---- direction: pair formation of the previous step + two-loop + first trial point, 3 launches ----
     const int mode = (iter > 0 && m > 0) ? DOTS_FORM_PAIR : DOTS_NONE;
-    DotsArgs da{S, Y, N, ld, view, g, params, x_prev, gbuf[cur ^ 1], mode, reset_next, 0, partials};
-    B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
-    SolveArgs sa{view, partials, nblk, mode, reset_next, policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
-    B200_TRY(launch_lbfgs_solve(sa, mp, st));
-    ApplyArgs aa{S, Y, N, ld, view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
-    B200_TRY(launch_lbfgs_apply(aa, apply_blocks, st));
-    B200_CUDA(cudaMemcpyAsync(&mail->hdr, view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
-    reset_next = 0;
+    {
+      ProfScope ps(ctx, "lbfgs_dots");
+      DotsArgs da{S, Y, N, ld, s->view, g, params, x_prev, g_new, mode, s->reset_next, 0, s->partials};
+      B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
+    }
+    {
+      ProfScope ps(ctx, "lbfgs_solve");
+      SolveArgs sa{s->view, s->partials, s->nblk, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
+      B200_TRY(launch_lbfgs_solve(sa, mp, st));
+    }
+    {
+      ProfScope ps(ctx, "lbfgs_apply");
+      ApplyArgs aa{S, Y, N, ld, s->view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
+      B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
+    }
+    B200_CUDA(cudaMemcpyAsync(&mail->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+    s->reset_next = 0;
 
     // ---- line search ------------------------------------------------------------------------------
     double loss_new = 0.0, gnorm2_new = 0.0, alpha = 1.0;
@@ -225,7 +286,7 @@ int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *u
         gnorm2_new = mail->gnorm2;
         armijo_ok = true;
       }
-      if (!armijo_ok) reset_next = 1; // lbfgs.cuh:147 — the step is still accepted
+      if (!armijo_ok) s->reset_next = 1; // lbfgs.cuh:147 — the step is still accepted
     } else {
       // weak-Wolfe bisection / expansion (full_batch_minimizer.hpp:126-157); iteration 0 takes
       // alpha = min(1, 1/||g||) without a line search (lbfgs.hpp:60-63)
@@ -241,7 +302,7 @@ int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *u
       if (iter > 0) {
         const double f_old = loss, gfo = mail->hdr.gdotp, inf = std::numeric_limits<double>::infinity();
         double a_min = 0.0, a_max = inf;
-        bool at_alpha = true; // at_alpha: params/g_new currently hold the point for `alpha`
+        bool at_alpha = true; // params / g_new currently hold the point for `alpha`
         const int trials = o.max_line_iters > 0 ? o.max_line_iters : 50;
         for (int i = 0; i < trials; ++i) {
           if (!at_alpha) {
@@ -279,11 +340,12 @@ int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *u
     }
 
     // accept: g <- g_new, loss <- loss_new (lbfgs.cuh:171-175); s, y are formed by the next dots pass
-    cur ^= 1;
-    loss = loss_new;
-    gnorm = std::sqrt(gnorm2_new);
+    s->cur ^= 1;
+    s->loss = loss_new;
+    s->gnorm = std::sqrt(gnorm2_new);
+    s->iter = iter + 1;
     B200_TRY(timer.stop());
-    record(hist, iterations_done, loss, gnorm, timer.elapsed);
+    record(hist, iterations_done, s->loss, s->gnorm, timer.elapsed);
     ++iterations_done;
   }
   B200_CUDA(cudaStreamSynchronize(st));
@@ -293,6 +355,19 @@ int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *u
     hist->launches = b200_launch_count() - launches0;
   }
   return B200_OK;
+}
+
+int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
+                     const float *input, const float *target, int batch, const b200_lbfgs_opts *opts,
+                     b200_history *hist) {
+  B200_REQUIRE(ctx, "null ctx");
+  if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  if (n <= 0 || params == nullptr) return B200_OK; // lbfgs.cuh:45-48: silent return, iterations() == 0
+  b200_lbfgs *s = nullptr;
+  B200_TRY(b200_lbfgs_create(ctx, n, opts, &s));
+  const int status = b200_lbfgs_run(s, net, fn, user, params, input, target, batch, s->o.max_iters, hist);
+  b200_lbfgs_destroy(s);
+  return status;
 }
 
 // ===================================================================================================
