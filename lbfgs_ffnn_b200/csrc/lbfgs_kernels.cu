@@ -184,10 +184,17 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
   double *tot = sh, *alpha = sh + ncols, *dlt = alpha + mp;
   __shared__ int s_head, s_count, s_w;
 
-  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+  // fixed-order (deterministic) reduction of the per-CTA partials: 8 threads per column, each a strided
+  // slice of the blocks, combined by shuffles — ~nblocks/8 dependent loads instead of nblocks
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     double s = 0.0;
-    for (int b = 0; b < a.nblocks; ++b) s += a.partials[(size_t)b * ncols + c];
-    tot[c] = s;
+    if (c < ncols)
+      for (int b = sub; b < a.nblocks; b += 8) s += a.partials[(size_t)b * ncols + c];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (c < ncols && sub == 0) tot[c] = s;
   }
   if (threadIdx.x == 0) {
     int head = h->head, count = h->count;

@@ -248,7 +248,7 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
                     h_idx + idx_used);
           idx_used += b_H / W;
         }
-        u_nonempty = true;
+        u_nonempty = (M > 0); // u_list has capacity M+1, or 0 when M == 0 (push_back is then a no-op, :176)
       }
     }
     B200_CUDA(cudaMemcpyAsync(d_idx, h_idx, sizeof(uint32_t) * idx_used, cudaMemcpyHostToDevice, st));
@@ -294,7 +294,7 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
           }
         }
         B200_CUDA(cudaMemcpyAsync(u_prev, u, sizeof(float) * Nn, cudaMemcpyDeviceToDevice, st)); // u_list.push_back(u)
-        have_u_prev = true;
+        have_u_prev = (M > 0);
       }
     }
 

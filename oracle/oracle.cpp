@@ -836,7 +836,7 @@ long oracle_net_params_size(void *h) { return (long)((Net *)h)->nparams; }
 
 // Network::bindParams (src/network.hpp:45-70): ONE mt19937(seed), per layer a fresh
 // normal_distribution<double>(0, scale*sqrt(1/in)) drawn for ALL entries incl. biases.
-void oracle_init_params_cpu_rule(void *h, unsigned seed, double *out) {
+__attribute__((optimize("fp-contract=off"))) void oracle_init_params_cpu_rule(void *h, unsigned seed, double *out) {
   Net &n = *(Net *)h;
   std::mt19937 gen(seed);
   double *p = out;
@@ -850,7 +850,7 @@ void oracle_init_params_cpu_rule(void *h, unsigned seed, double *out) {
 }
 // CudaNetwork::bindParams (src/cuda/network.cuh:37-59): normal_distribution<float> for the
 // weights only, biases = 0.
-void oracle_init_params_cuda_rule(void *h, unsigned seed, float *out) {
+__attribute__((optimize("fp-contract=off"))) void oracle_init_params_cuda_rule(void *h, unsigned seed, float *out) {
   Net &n = *(Net *)h;
   std::mt19937 gen(seed);
   size_t off = 0;
