@@ -144,7 +144,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+                    help="tf32x3 (default): fp32-accurate hi/lo split on the tensor cores; fp32: FFMA; tf32: single pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -311,7 +312,8 @@ def main():
         value = args.steps / (ms_total / 1e3)
         line = {"metric": "lbfgs_iters_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split products, fp32 accumulate)", "tf32": "tf32"}[args.precision],
+                "data": "synthetic",
                 "config": {"workload": WORKLOAD, "memory": MEMORY, "line_search": "armijo (reference CUDA backend)",
                            "precision": args.precision, "samples_per_gpu": shard, "params": n,
                            "l2": "inputs (188 MB fp32 X) larger than the 126 MB L2; no flush needed",

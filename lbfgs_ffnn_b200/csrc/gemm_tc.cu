@@ -1,15 +1,723 @@
+// tcgen05 / TMEM / TMA GEMMs of the MLP objective (precision modes B200_PREC_TF32 and B200_PREC_TF32X3).
+//
+// One warp-specialised kernel template covers the three GEMM roles of a dense layer
+// (src/cuda/layer.cuh:48-58 forward, :81-86 dW + db, :89-103 dX) with the reference's separate
+// element-wise kernels (kernels.cuh:74-153) folded into the epilogue:
+//
+//   role  D rows (M=128/CTA)  D cols (N)   K        A operand (smem)            B operand (smem)
+//   FWD   samples             out          in       act_{l-1} [B][in]  K-major   W_l [in][out]      MN-major
+//   DX    samples             in           out      delta_l   [B][out] K-major   W_l (n=in, k=out)  K-major
+//   DW    out                 in           samples  delta_l   [B][out] MN-major  act_{l-1} [B][in]  MN-major
+//
+// Data path: TMA (cp.async.bulk.tensor, SWIZZLE_128B, OOB zero fill handles every ragged edge) -> shared
+// memory ring (3 stages) -> tcgen05.mma.kind::tf32 issued by one thread, fp32 accumulator in TMEM ->
+// tcgen05.ld -> fused epilogue. All tiles are 32 floats (one 128-byte swizzle row) deep in K.
+// 3xTF32 (fp32-accurate mode): four otherwise idle warps split every landed tile in place into
+// hi = rna_tf32(a) and lo = a - hi (exact), and the issuer runs hi*hi + hi*lo + lo*hi into the same
+// accumulator, i.e. fp32-level products at one third of the TF32 rate with no extra HBM traffic.
+// DW is split-K over the batch with per-split partial tiles (deterministic, combined in fp64 by
+// finalize_grad_kernel); the bias gradient is one extra N=16 MMA per K step against a tile of ones.
 #include "gemm_tc.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace b200 {
 
-int tc_forward_layer(b200_net *, int, const float *, const float *, long, bool *done) {
-  *done = false;
+namespace {
+
+constexpr int BM = 128;           // UMMA M (cta_group::1)
+constexpr int BK = 32;            // floats per K block = one 128-byte swizzle row
+constexpr int kATileBytes = BM * BK * 4;
+constexpr int kTcThreads = 256;   // warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-7 epilogue / splitter
+constexpr int kOnesBytes = 2048;  // 16 rows x 128 B of 1.0f (bias-gradient B operand; layout-agnostic)
+constexpr int kLastCols = 12;                          // fused last layer: out <= 12, rows padded to 12 floats
+constexpr int kLastBytes = (128 + 1) * kLastCols * 4;  // [W_last | b_last] staged in shared memory
+
+enum { MAJOR_K = 0, MAJOR_MN = 1 };
+enum { TC_FWD = 0, TC_DX = 1, TC_DW = 2 };
+
+struct TcParams {
+  int rows_valid;   // FWD/DX: batch, DW: out
+  int cols_valid;   // FWD: out, DX: in, DW: in
+  int k_blocks;     // total K blocks of 32
+  int kb_per_split; // DW: K blocks per split (others: k_blocks)
+  int act;          // FWD: this layer's activation, DX: previous layer's
+  const float *bias;
+  float *out;       // FWD: activations, DX: delta_prev ; row-major [rows][ld_out]
+  long ld_out;
+  const float *aux; // DX: act_{l-1}
+  float *partial;   // DW: [split][(in+1)*out]
+  unsigned long long partial_stride;
+  int out_dim, in_dim; // DW
+  // FWD of the penultimate layer with the (skinny, out <= 16) last layer fused into the epilogue
+  int fuse_last, last_out, last_act;
+  const float *w_last;   // [cols_valid][last_out] followed by the last_out biases
+  const float *targets;  // [rows][last_out]
+  float *out_last, *delta_last, *delta_prev;
+  float inv_batch;
+  double *loss_part;     // [gridDim.x * 4]
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, descriptor version 1 (Blackwell).
+// K-major  (layout 2, SWIZZLE_128B: 16 B chunks XOR row%8): rows of 128 B (32 floats of K) at 128 B pitch,
+//           8-row groups at SBO = 1024 B; LBO unused (1). TMA: CU_TENSOR_MAP_SWIZZLE_128B.
+// MN-major (layout 1, SWIZZLE_128B_BASE32B: 32 B chunks XOR row%4 — the only MN-major layout for 32-bit
+//           operands): atoms of [4 K-rows][32 MN floats] (512 B); next 4-row K group at SBO = 512 B, next
+//           MN atom (32 floats further along M/N) at LBO. TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46; // version
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t saddr) { return make_desc(saddr, 16, 1024, 2); }
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr) { return make_desc(saddr, 4096, 512, 1); }
+// instruction descriptor: fp32 accumulate, tf32 x tf32, given majors and N (M = 128)
+__host__ __device__ constexpr uint32_t make_idesc(int a_major, int b_major, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// packed fp32 FMA (Blackwell FFMA2): (d0, d1) += (a0, a1) * (b0, b1) in ONE issue slot
+__device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// Store a 32(row) x 32(col) fp32 block held one row per lane as 32 fully coalesced 128-byte row segments
+// (a per-thread row store would touch 32 different lines per instruction, 8x the L2 write transactions).
+// scratch: this warp's private 32 x 33 floats of shared memory.
+__device__ __forceinline__ void store_block_coalesced(const float (&r)[32], float *scratch, float *gbase, long ld,
+                                                      int rows_ok, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = r[j];
+  __syncwarp();
+#pragma unroll 8
+  for (int rr = 0; rr < 32; ++rr)
+    if (rr < rows_ok) gbase[(long)rr * ld + lane] = scratch[rr * 33 + lane];
+  __syncwarp();
+}
+
+template <int BN, bool X3>
+struct SmemPlan {
+  static constexpr int kBTileBytes = BN * BK * 4;
+  static constexpr int kStageBytes = (kATileBytes + kBTileBytes) * (X3 ? 2 : 1);
+  static constexpr int kStages = (kStageBytes * 3 <= 200 * 1024) ? 3 : 2;
+  static constexpr int kBarOffset = kStages * kStageBytes + kOnesBytes + ((kLastBytes + 127) / 128) * 128;
+  static constexpr int kTotal = kBarOffset + 128 + 1024; // barriers + tmem slot + alignment slack
+};
+
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Plan = SmemPlan<BN, X3>;
+  constexpr int kBTileBytes = Plan::kBTileBytes;
+  constexpr int kStages = Plan::kStages;
+  constexpr bool kBias = (ROLE == TC_DW);
+  // 3xTF32 accumulator plan. The tensor core's fp32 accumulate truncates (measured: a ~3e-8 relative bias per
+  // accumulating MMA on same-signed sums), so the fp32-accurate mode (a) rotates the hi*hi products of successive
+  // K blocks over kMain accumulators and (b) keeps the 2^-12-sized hi*lo + lo*hi corrections in their own
+  // accumulator; the epilogue adds them in round-to-nearest fp32. DW keeps one (its sums are sign-mixed).
+  constexpr bool kSplitAcc = X3 && ROLE != TC_DW;
+  constexpr int kMain = kSplitAcc ? (BN <= 128 ? 3 : 1) : 1;
+  constexpr int kColsNeeded = kMain * BN + (kSplitAcc ? BN : 0) + (kBias ? 32 : 0);
+  constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
+                          : kColsNeeded <= 256 ? 256 : 512;
+  static_assert(kColsNeeded <= 512, "TMEM has 512 columns");
+  constexpr int kSmallCol = kMain * BN;                          // hi*lo + lo*hi accumulator (kSplitAcc)
+  constexpr int kBiasCol = kMain * BN + (kSplitAcc ? BN : 0);    // bias-gradient accumulator (DW)
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  auto a_tile = [&](int s, int lo) { return base + s * Plan::kStageBytes + lo * (kATileBytes + kBTileBytes); };
+  auto b_tile = [&](int s, int lo) { return a_tile(s, lo) + kATileBytes; };
+  const uint32_t ones = base + kStages * Plan::kStageBytes;
+  const uint32_t bars = base + Plan::kBarOffset;
+  auto bar_full = [&](int s) { return bars + 8 * s; };
+  auto bar_empty = [&](int s) { return bars + 8 * (kStages + s); };
+  auto bar_split = [&](int s) { return bars + 8 * (2 * kStages + s); };
+  const uint32_t bar_accum = bars + 8 * (3 * kStages);
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(base_ptr + Plan::kBarOffset + 8 * (3 * kStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  int kb_begin = 0, kb_end = p.k_blocks;
+  if (ROLE == TC_DW) {
+    kb_begin = blockIdx.z * p.kb_per_split;
+    kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+  }
+  const int nkb = max(0, kb_end - kb_begin);
+  // UMMA N of this CTA: the valid columns rounded up to a whole 32-float swizzle atom
+  const int n_valid = min(BN, p.cols_valid - n0);
+  const int umma_n = (n_valid + 31) & ~31;
+  const bool do_bias = kBias && (blockIdx.y == gridDim.y - 1);
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_split(s), 128);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (kBias && warp == 3) { // tile of ones for the bias-gradient MMA
+    float4 *o4 = reinterpret_cast<float4 *>(base_ptr + kStages * Plan::kStageBytes);
+    for (int i = lane; i < kOnesBytes / 16; i += 32) o4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  float *wl = reinterpret_cast<float *>(base_ptr + kStages * Plan::kStageBytes + kOnesBytes); // fused last layer
+  const bool fuse = (ROLE == TC_FWD) && p.fuse_last;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer ========================================================================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(bar_empty(s), ph ^ 1);
+        mbar_expect_tx(bar_full(s), kATileBytes + kBTileBytes);
+        const int k0 = kb * BK;
+        if (A_MAJOR == MAJOR_K) {
+          tma_load_2d(a_tile(s, 0), &tmA, bar_full(s), k0, m0); // box {32 K, 128 rows}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BM / 32; ++g) tma_load_2d(a_tile(s, 0) + g * 4096, &tmA, bar_full(s), m0 + 32 * g, k0);
+        }
+        if (B_MAJOR == MAJOR_K) {
+          tma_load_2d(b_tile(s, 0), &tmB, bar_full(s), k0, n0); // box {32 K, BN rows}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g) tma_load_2d(b_tile(s, 0) + g * 4096, &tmB, bar_full(s), n0 + 32 * g, k0);
+        }
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer ==========================================================================
+      const uint32_t idesc = make_idesc(A_MAJOR, B_MAJOR, umma_n);
+      const uint32_t idesc_bias = make_idesc(A_MAJOR, MAJOR_K, 16);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(X3 ? bar_split(s) : bar_full(s), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t acc = (kb > kb_begin || ks > 0) ? 1u : 0u;
+          uint64_t da[2], db[2];
+#pragma unroll
+          for (int lo = 0; lo < (X3 ? 2 : 1); ++lo) {
+            da[lo] = (A_MAJOR == MAJOR_K) ? desc_k_major(a_tile(s, lo) + ks * 32) : desc_mn_major(a_tile(s, lo) + ks * 1024);
+            db[lo] = (B_MAJOR == MAJOR_K) ? desc_k_major(b_tile(s, lo) + ks * 32) : desc_mn_major(b_tile(s, lo) + ks * 1024);
+          }
+          const int rel = kb - kb_begin;
+          const uint32_t d_main = tmem_base + (uint32_t)((rel % kMain) * BN);
+          const uint32_t acc_main = (rel >= kMain || ks > 0) ? 1u : 0u; // first touch of this accumulator overwrites
+          umma_tf32(d_main, da[0], db[0], idesc, acc_main);
+          if (X3) {
+            const uint32_t d_small = kSplitAcc ? tmem_base + kSmallCol : d_main;
+            umma_tf32(d_small, da[0], db[1], idesc, kSplitAcc ? acc : 1u); // hi * lo
+            umma_tf32(d_small, da[1], db[0], idesc, 1u);                   // lo * hi
+          }
+          if (do_bias) {
+            const uint64_t dones = desc_k_major(ones);
+            umma_tf32(tmem_base + kBiasCol, da[0], dones, idesc_bias, acc);
+            if (X3) umma_tf32(tmem_base + kBiasCol, da[1], dones, idesc_bias, 1u);
+          }
+        }
+        umma_commit(bar_empty(s)); // smem slot reusable once these MMAs have read it
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(bar_accum); // accumulator complete
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    if (fuse) { // stage [W_last | b_last], rows zero-padded to kLastCols floats (row cols_valid = the bias)
+      const int OL = p.last_out;
+      for (int i = threadIdx.x - 64; i < (p.cols_valid + 1) * kLastCols; i += 64) {
+        const int k = i / kLastCols, j = i - k * kLastCols;
+        wl[i] = (j < OL) ? __ldg(p.w_last + (size_t)k * OL + j) : 0.0f;
+      }
+    }
+  } else if (X3) {
+    // ===== 3xTF32 splitter: hi = rna_tf32(a) in place, lo = a - hi (exact) ========================
+    const int et = threadIdx.x - 128; // 0..127
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(bar_full(s), ph);
+      // A and B tiles are contiguous: [A hi | B hi] then [A lo | B lo]; element-wise, layout-agnostic
+      float4 *hi = reinterpret_cast<float4 *>(base_ptr + s * Plan::kStageBytes);
+      float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * Plan::kStageBytes + kATileBytes + kBTileBytes);
+      constexpr int kVec = (kATileBytes + kBTileBytes) / 16;
+#pragma unroll 4
+      for (int i = et; i < kVec; i += 128) {
+        const float4 a = hi[i];
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.x)); h.x = __uint_as_float(t); l.x = a.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.y)); h.y = __uint_as_float(t); l.y = a.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.z)); h.z = __uint_as_float(t); l.z = a.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.w)); h.w = __uint_as_float(t); l.w = a.w - h.w;
+        hi[i] = h;
+        lo[i] = l;
+      }
+      fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_split(s));
+      if (++s == kStages) { s = 0; ph ^= 1; }
+    }
+  }
+
+  // ===== epilogue: all 8 warps. Warps w and w+4 own TMEM lanes (= D rows) 32*(w%4).., and split the 32-column
+  // chunks of the accumulator between them (even chunks: warps 0-3, odd chunks: warps 4-7) ===================
+  __syncthreads(); // roles done issuing; wl staged
+  if (nkb > 0) {
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+  }
+  {
+    const int half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane; // TMEM lane == D row
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const long grow = (long)m0 + row;
+    const bool row_ok = grow < p.rows_valid;
+    // the pipeline stages are idle once the accumulator is complete: they double as store-transpose scratch
+    // (8 x 32x33 floats) and as the exchange buffer of the fused last layer
+    float *scratch = reinterpret_cast<float *>(base_ptr) + warp * (32 * 33);
+    float *zbuf = reinterpret_cast<float *>(base_ptr) + 8 * (32 * 33); // [2][128][kLastCols]
+    const long wrow0 = (long)m0 + (warp & 3) * 32;                          // first row of this warp
+    const int rows_ok = (int)max(0L, min(32L, (long)p.rows_valid - wrow0)); // valid rows of this warp
+    // accumulator chunk c0..c0+31 of this thread's row: (main_0 + main_1 + main_2) + small in RN fp32
+    auto load_chunk = [&](int c0, uint32_t (&v)[32]) {
+      if (nkb > 0) {
+        tmem_ld32(lane_addr + c0, v);
+        if (kSplitAcc) {
+          uint32_t w[32];
+#pragma unroll
+          for (int a = 1; a < kMain; ++a) {
+            if (a < nkb) {
+              tmem_ld32(lane_addr + a * BN + c0, w);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            }
+          }
+          tmem_ld32(lane_addr + kSmallCol + c0, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+    };
+    float z[kLastCols]; // fused last layer: this half's share of the pre-activations of this thread's sample
+#pragma unroll
+    for (int j = 0; j < kLastCols; ++j) z[j] = 0.0f;
+    for (int c0 = half * 32; c0 < umma_n; c0 += 64) {
+      uint32_t v[32];
+      load_chunk(c0, v);
+      const int gcol0 = n0 + c0;
+      if (ROLE == TC_FWD || ROLE == TC_DX) {
+        if (gcol0 + 32 <= p.cols_valid) {
+          float r[32];
+          const float *aux = (ROLE == TC_DX && row_ok) ? p.aux + grow * p.ld_out + gcol0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (ROLE == TC_FWD) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + gcol0) + q);
+              r[4 * q + 0] = act_apply(p.act, __uint_as_float(v[4 * q + 0]) + b4.x);
+              r[4 * q + 1] = act_apply(p.act, __uint_as_float(v[4 * q + 1]) + b4.y);
+              r[4 * q + 2] = act_apply(p.act, __uint_as_float(v[4 * q + 2]) + b4.z);
+              r[4 * q + 3] = act_apply(p.act, __uint_as_float(v[4 * q + 3]) + b4.w);
+              if (fuse) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = r[4 * q + e];
+                  const float4 *wr = reinterpret_cast<const float4 *>(wl + (size_t)(gcol0 + 4 * q + e) * kLastCols);
+                  const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2];
+                  ffma2(z[0], z[1], a, a, w0.x, w0.y); ffma2(z[2], z[3], a, a, w0.z, w0.w);
+                  ffma2(z[4], z[5], a, a, w1.x, w1.y); ffma2(z[6], z[7], a, a, w1.z, w1.w);
+                  ffma2(z[8], z[9], a, a, w2.x, w2.y); ffma2(z[10], z[11], a, a, w2.z, w2.w);
+                }
+              }
+            } else {
+              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row_ok) a4 = __ldg(reinterpret_cast<const float4 *>(aux) + q);
+              r[4 * q + 0] = __uint_as_float(v[4 * q + 0]) * act_deriv_from_output(p.act, a4.x);
+              r[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * act_deriv_from_output(p.act, a4.y);
+              r[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * act_deriv_from_output(p.act, a4.z);
+              r[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * act_deriv_from_output(p.act, a4.w);
+            }
+          }
+          store_block_coalesced(r, scratch, p.out + wrow0 * p.ld_out + gcol0, p.ld_out, rows_ok, lane);
+        } else if (row_ok) {
+          float *dst = p.out + grow * p.ld_out + gcol0;
+          const float *aux = (ROLE == TC_DX) ? p.aux + grow * p.ld_out + gcol0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (gcol0 + j < p.cols_valid) {
+              const float acc = __uint_as_float(v[j]);
+              dst[j] = (ROLE == TC_FWD) ? act_apply(p.act, acc + __ldg(p.bias + gcol0 + j))
+                                        : acc * act_deriv_from_output(p.act, __ldg(aux + j));
+            }
+          }
+        }
+      } else { // TC_DW: D[o][i] -> partial[split][i*out + o]; lanes are consecutive o => coalesced per column
+        if (row_ok) {
+          float *dst = p.partial + (unsigned long long)blockIdx.z * p.partial_stride + grow;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gcol0 + j < p.cols_valid) dst[(long)(gcol0 + j) * p.out_dim] = __uint_as_float(v[j]);
+        }
+      }
+    }
+    if (fuse) {
+      // last layer forward, loss, delta_L (src/cuda/network.cuh:100-107) and delta_{L-1} (layer.cuh:89-103 +
+      // kernels.cuh:109-133) for this thread's sample. The two warps of a row exchange their half sums of z.
+#pragma unroll
+      for (int j = 0; j < kLastCols; ++j) zbuf[(half * 128 + row) * kLastCols + j] = z[j];
+      __syncthreads();
+      const int OL = p.last_out;
+      float dl[kLastCols];
+      double lsum = 0.0;
+      const float *brow = wl + (size_t)p.cols_valid * kLastCols;
+      const float *zo = zbuf + ((half ^ 1) * 128 + row) * kLastCols;
+#pragma unroll
+      for (int j = 0; j < kLastCols; ++j) {
+        dl[j] = 0.0f;
+        if (j < OL && row_ok) {
+          const float zz = (half == 0) ? (z[j] + zo[j]) : (zo[j] + z[j]); // same operand order in both warps
+          const float o = act_apply(p.last_act, zz + brow[j]);
+          const float d = o - __ldg(p.targets + grow * OL + j);
+          dl[j] = d * p.inv_batch * act_deriv_from_output(p.last_act, o);
+          if (half == 0) {
+            p.out_last[grow * OL + j] = o;
+            p.delta_last[grow * OL + j] = dl[j];
+            lsum += (double)d * (double)d;
+          }
+        }
+      }
+      if (half == 0) {
+        lsum = warp_sum(lsum);
+        if (lane == 0) p.loss_part[blockIdx.x * 4 + (warp & 3)] = lsum;
+      }
+      for (int c0 = half * 32; c0 < umma_n; c0 += 64) {
+        uint32_t v[32];
+        load_chunk(c0, v);
+        float r[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + c0) + q);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = act_apply(p.act, __uint_as_float(v[4 * q + e]) + bb[e]);
+            const float4 *wr = reinterpret_cast<const float4 *>(wl + (size_t)(c0 + 4 * q + e) * kLastCols);
+            const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2];
+            float g0 = 0.0f, g1 = 0.0f;
+            ffma2(g0, g1, w0.x, w0.y, dl[0], dl[1]); ffma2(g0, g1, w0.z, w0.w, dl[2], dl[3]);
+            ffma2(g0, g1, w1.x, w1.y, dl[4], dl[5]); ffma2(g0, g1, w1.z, w1.w, dl[6], dl[7]);
+            ffma2(g0, g1, w2.x, w2.y, dl[8], dl[9]); ffma2(g0, g1, w2.z, w2.w, dl[10], dl[11]);
+            r[4 * q + e] = (g0 + g1) * act_deriv_from_output(p.act, a);
+          }
+        }
+        store_block_coalesced(r, scratch, p.delta_prev + wrow0 * p.ld_out + c0, p.ld_out, rows_ok, lane);
+      }
+    }
+    if (do_bias && half == 0) { // db[o] = sum_b delta[b][o]: first column of the bias accumulator
+      uint32_t v[32];
+      if (nkb > 0) {
+        tmem_ld32(lane_addr + kBiasCol, v);
+      } else {
+        v[0] = 0u;
+      }
+      if (row_ok)
+        p.partial[(unsigned long long)blockIdx.z * p.partial_stride + (unsigned long long)p.in_dim * p.out_dim + grow] =
+            __uint_as_float(v[0]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 (contiguous) x dim1 with row stride ld floats; box {32, box1}; SWIZZLE_128B; OOB -> 0
+int make_map(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long ld,
+             unsigned box1, int major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box1};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        major == MAJOR_K ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu box1 %u ptr %p", (int)r, dim0, dim1, ld, box1, ptr);
+    return B200_ERR_CUDA;
+  }
   return B200_OK;
 }
-int tc_dw_layer(b200_net *, int, const float *, long, bool *done) {
-  *done = false;
+
+bool tma_ok(const float *ptr, long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (ld % 4) == 0; }
+
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3>
+int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<A_MAJOR, B_MAJOR, ROLE, BN, X3>;
+  constexpr int smem = SmemPlan<BN, X3>::kTotal;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid, kTcThreads, smem, st>>>(ta, tb, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
+
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN>
+int launch_tc_prec(bool x3, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, dim3 grid, cudaStream_t st) {
+  return x3 ? launch_tc<A_MAJOR, B_MAJOR, ROLE, BN, true>(ta, tb, p, grid, st)
+            : launch_tc<A_MAJOR, B_MAJOR, ROLE, BN, false>(ta, tb, p, grid, st);
+}
+
+int tc_mask() { // debugging aid: B200_TC_MASK bit0 = FWD, bit1 = DX, bit2 = DW (default all); read per call
+  const char *e = std::getenv("B200_TC_MASK");
+  return e ? std::atoi(e) : 7;
+}
+
+} // namespace
+
+// A_l = act(A_{l-1} W_l + b_l) for hidden layers. With `fuse` (l is the penultimate layer and the last layer has
+// out <= 16) the epilogue also runs the last layer, the loss partials, delta_L and delta_{L-1}.
+int tc_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch, const TcFuseLast *fuse,
+                     bool *done, bool *fused) {
+  *done = false;
+  if (fused) *fused = false;
+  if (!(tc_mask() & 1)) return B200_OK;
+  const int K = net->dims[l], N = net->dims[l + 1];
+  const float *W = params + net->offs[l];
+  if (!tma_ok(in, K) || !tma_ok(W, N) || !tma_ok(net->act[l], N) || N % 32 != 0) return B200_OK;
+  const bool x3 = net->prec == B200_PREC_TF32X3;
+  CUtensorMap ta, tb;
+  B200_TRY(make_map(&ta, in, K, batch, K, BM, MAJOR_K)); // A: {K, rows}, box {32, 128}
+  B200_TRY(make_map(&tb, W, N, K, N, 32, MAJOR_MN));  // B: {N, K}, box {32, 32}
+  TcParams p{};
+  p.rows_valid = (int)batch; p.cols_valid = N;
+  p.k_blocks = ceil_div(K, BK); p.kb_per_split = p.k_blocks;
+  p.act = net->acts[l]; p.bias = W + (size_t)K * N;
+  p.out = net->act[l]; p.ld_out = N;
+  const int L = net->nlayers();
+  if (fuse && (tc_mask() & 8) == 0 && l == L - 2 && N <= 128 && net->dims[L] <= kLastCols && tma_ok(net->delta[l], N)) {
+    p.fuse_last = 1;
+    p.last_out = net->dims[L];
+    p.last_act = net->acts[L - 1];
+    p.w_last = params + net->offs[L - 1];
+    p.targets = fuse->targets;
+    p.out_last = net->act[L - 1];
+    p.delta_last = net->delta[L - 1];
+    p.delta_prev = net->delta[l];
+    p.inv_batch = fuse->inv_batch;
+    p.loss_part = net->loss_part;
+    net->loss_part_n = ceil_div(batch, BM) * 4;
+    if (fused) *fused = true;
+  }
+  cudaStream_t st = net->ctx->stream;
+  if (N <= 64) {
+    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(N, 64)), st)));
+  } else {
+    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 128>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(N, 128)), st)));
+  }
+  *done = true;
+  return B200_OK;
+}
+
+// delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
+int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *done) {
+  *done = false;
+  if (!(tc_mask() & 2)) return B200_OK;
+  const int Kin = net->dims[l], Nout = net->dims[l + 1]; // contraction over out, result width in
+  const float *W = params + net->offs[l];
+  if (!tma_ok(net->delta[l], Nout) || !tma_ok(W, Nout) || !tma_ok(net->delta[l - 1], Kin) || !tma_ok(net->act[l - 1], Kin) ||
+      Kin % 32 != 0)
+    return B200_OK;
+  const bool x3 = net->prec == B200_PREC_TF32X3;
+  CUtensorMap ta, tb;
+  B200_TRY(make_map(&ta, net->delta[l], Nout, batch, Nout, BM, MAJOR_K)); // A: {K = out, rows}, box {32, 128}
+  TcParams p{};
+  p.rows_valid = (int)batch; p.cols_valid = Kin;
+  p.k_blocks = ceil_div(Nout, BK); p.kb_per_split = p.k_blocks;
+  p.act = net->acts[l - 1];
+  p.out = net->delta[l - 1]; p.ld_out = Kin; p.aux = net->act[l - 1];
+  cudaStream_t st = net->ctx->stream;
+  if (Kin <= 64) {
+    B200_TRY(make_map(&tb, W, Nout, Kin, Nout, 64, MAJOR_K)); // B: {K = out, N = in}, box {32, BN}
+    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 64>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 64)), st)));
+  } else {
+    B200_TRY(make_map(&tb, W, Nout, Kin, Nout, 128, MAJOR_K));
+    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 128>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 128)), st)));
+  }
+  *done = true;
+  return B200_OK;
+}
+
+// [dW_l ; db_l] split-K partials = [A_{l-1} | 1]^T delta_l
+int tc_dw_plan(b200_net *net, int l, long batch, int *splits) {
+  const int Kin = net->dims[l], Nout = net->dims[l + 1];
+  const int tiles = ceil_div(Nout, BM) * ceil_div(Kin, 256);
+  const int kblocks = ceil_div(batch, BK);
+  int s = std::max(1, std::min(ceil_div(net->ctx->num_sms, tiles), kblocks));
+  const int per = ceil_div(kblocks, s);
+  *splits = ceil_div(kblocks, per);
+  return per;
+}
+
+int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
+  *done = false;
+  if (!(tc_mask() & 4)) return B200_OK;
+  const int Kin = net->dims[l], Nout = net->dims[l + 1];
+  if (!tma_ok(net->delta[l], Nout) || !tma_ok(in, Kin)) return B200_OK;
+  const bool x3 = net->prec == B200_PREC_TF32X3;
+  CUtensorMap ta, tb;
+  B200_TRY(make_map(&ta, net->delta[l], Nout, batch, Nout, 32, MAJOR_MN)); // A: {M = out, K = batch}, box {32, 32}
+  B200_TRY(make_map(&tb, in, Kin, batch, Kin, 32, MAJOR_MN));              // B: {N = in, K = batch}, box {32, 32}
+  int splits = 1;
+  const int per = tc_dw_plan(net, l, batch, &splits);
+  TcParams p{};
+  p.rows_valid = Nout; p.cols_valid = Kin;
+  p.k_blocks = ceil_div(batch, BK); p.kb_per_split = per;
+  p.partial = net->partials + net->part_off[l];
+  p.partial_stride = (unsigned long long)(Kin + 1) * Nout;
+  p.out_dim = Nout; p.in_dim = Kin;
+  B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256>(x3, ta, tb, p, dim3(ceil_div(Nout, BM), ceil_div(Kin, 256), splits),
+                                                           net->ctx->stream)));
+  net->splits_used[l] = splits; // finalize_grad_kernel combines exactly the splits this launch wrote
+  *done = true;
+  return B200_OK;
+}
+
 void tc_release(b200_net *) {}
 
 } // namespace b200

@@ -6,8 +6,16 @@
 
 namespace b200 {
 
-int tc_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch, bool *done);
+struct TcFuseLast { // request to fuse the last layer + loss + deltas into the penultimate layer's forward epilogue
+  const float *targets;
+  float inv_batch;
+};
+int tc_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch, const TcFuseLast *fuse,
+                     bool *done, bool *fused);
+int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *done);
 int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done);
+// split-K plan of the tensor-core dW kernel: returns K blocks per split, *splits = number of splits
+int tc_dw_plan(b200_net *net, int l, long batch, int *splits);
 void tc_release(b200_net *net);
 
 } // namespace b200

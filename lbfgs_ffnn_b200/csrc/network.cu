@@ -35,27 +35,49 @@ struct FinParams {
 };
 
 // grad[j] = sum_s partial_l[s][j - off_l] (+ lam * w[j]); per-CTA partials of ||g||^2, ||w||^2.
-// Deterministic: fixed split order, fixed CTA -> element mapping.
+// A CTA takes 32 consecutive gradient elements at a time; its 8 warps take the splits round-robin (every
+// load is one coalesced 128-byte row segment, up to 8 in flight per thread), accumulate in fp64 and are
+// combined in a fixed warp order, so the result is deterministic and rounded once.
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
+  __shared__ double sh[8][32];
   __shared__ double red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double g2 = 0.0, w2 = 0.0;
-  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < p.n;
-       j += (unsigned long long)gridDim.x * blockDim.x) {
-    int l = 0;
+  const unsigned long long ngroups = (p.n + 31) / 32;
+  for (unsigned long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const unsigned long long j = grp * 32 + lane;
+    double acc = 0.0;
+    if (j < p.n) {
+      int l = 0;
 #pragma unroll 1
-    while (l + 1 < p.nl && j >= p.L[l + 1].off) ++l;
-    const FinLayer &L = p.L[l];
-    const float *src = p.partials + L.part_off + (j - L.off);
-    double acc = 0.0; // fp64 combine of the fp32 split-K partials: one rounding into the gradient
-    for (int sp = 0; sp < L.splits; ++sp) acc += (double)__ldg(src + (unsigned long long)sp * L.size);
-    if (p.lam != 0.0f) {
-      const float wv = __ldg(p.w + j);
-      acc = fma((double)p.lam, (double)wv, acc);
-      w2 += (double)wv * (double)wv;
+      while (l + 1 < p.nl && j >= p.L[l + 1].off) ++l;
+      const FinLayer &L = p.L[l];
+      const float *src = p.partials + L.part_off + (j - L.off);
+      int sp = warp;
+      for (; sp + 56 < L.splits; sp += 64) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldg(src + (unsigned long long)(sp + 8 * u) * L.size);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += (double)t[u];
+      }
+      for (; sp < L.splits; sp += 8) acc += (double)__ldg(src + (unsigned long long)sp * L.size);
     }
-    const float s = (float)acc;
-    p.grad[j] = s;
-    g2 += (double)s * (double)s;
+    __syncthreads();
+    sh[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && j < p.n) {
+      double tot = ((sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane])) +
+                   ((sh[4][lane] + sh[5][lane]) + (sh[6][lane] + sh[7][lane]));
+      if (p.lam != 0.0f) {
+        const float wv = __ldg(p.w + j);
+        tot = fma((double)p.lam, (double)wv, tot);
+        w2 += (double)wv * (double)wv;
+      }
+      const float s = (float)tot;
+      p.grad[j] = s;
+      g2 += (double)s * (double)s;
+    }
   }
   const double a = block_sum(g2, red);
   const double b = block_sum(w2, red);
@@ -129,6 +151,70 @@ __global__ void __launch_bounds__(256) evaluate_kernel(const float *out, const f
   }
 }
 
+// [dW; db] split-K partials of a skinny layer (out <= 16). Each CTA takes a slice of the batch; its 8 warps
+// take samples round-robin, a lane owns the input features lane, lane+32, ... (feature `in` is the bias row,
+// reading as 1), so every A_prev row is one coalesced 4*in-byte read and the 16 delta values are smem broadcasts.
+// The per-warp accumulators are combined in a fixed warp order (deterministic). Replaces a 128x16-tile GEMM
+// that would idle 15/16 of its lanes (and the reference's serial sum_rows_kernel, src/cuda/kernels.cuh:144-153).
+constexpr int kSkinnyTile = 64;
+template <int FPL>
+__global__ void __launch_bounds__(256) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int in,
+                                                        int out, long batch, int chunk, float *__restrict__ partial,
+                                                        unsigned long long pstride) {
+  __shared__ __align__(16) float sd[kSkinnyTile][16];
+  __shared__ float red[32 * FPL * 16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long b0 = (long)blockIdx.x * chunk, b1 = min(batch, b0 + (long)chunk);
+  float acc[FPL][16];
+#pragma unroll
+  for (int c = 0; c < FPL; ++c)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[c][j] = 0.0f;
+  for (long bt = b0; bt < b1; bt += kSkinnyTile) {
+    const int nb = (int)min((long)kSkinnyTile, b1 - bt);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kSkinnyTile * 16; e += blockDim.x) {
+      const int r = e >> 4, j = e & 15;
+      sd[r][j] = (r < nb && j < out) ? __ldg(D + (bt + r) * out + j) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = warp; r < nb; r += 8) {
+      float a[FPL];
+#pragma unroll
+      for (int c = 0; c < FPL; ++c) {
+        const int i = lane + 32 * c;
+        a[c] = (i < in) ? __ldg(A + (bt + r) * in + i) : (i == in ? 1.0f : 0.0f);
+      }
+      const float4 d0 = *reinterpret_cast<const float4 *>(&sd[r][0]), d1 = *reinterpret_cast<const float4 *>(&sd[r][4]);
+      const float4 d2 = *reinterpret_cast<const float4 *>(&sd[r][8]), d3 = *reinterpret_cast<const float4 *>(&sd[r][12]);
+      const float d[16] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
+#pragma unroll
+      for (int c = 0; c < FPL; ++c)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c][j] = fmaf(a[c], d[j], acc[c][j]);
+    }
+  }
+  for (int w = 0; w < 8; ++w) { // fixed-order cross-warp combine
+    __syncthreads();
+    if (warp == w) {
+#pragma unroll
+      for (int c = 0; c < FPL; ++c)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float *slot = &red[((lane + 32 * c) * 16) + j];
+          *slot = (w == 0) ? acc[c][j] : *slot + acc[c][j];
+        }
+    }
+  }
+  __syncthreads();
+  float *dst = partial + (unsigned long long)blockIdx.x * pstride;
+  for (int e = threadIdx.x; e < (in + 1) * out; e += blockDim.x) {
+    const int i = e / out, j = e - i * out;
+    dst[e] = red[i * 16 + j];
+  }
+}
+
 int free_batch_buffers(b200_net *net) {
   for (float *p : net->act) if (p) cudaFree(p);
   for (float *p : net->delta) if (p) cudaFree(p);
@@ -153,7 +239,7 @@ int net_ensure(b200_net *net, long batch) {
       B200_CUDA(cudaMalloc(&net->act[l], sizeof(float) * (size_t)net->dims[l + 1] * batch));
       B200_CUDA(cudaMalloc(&net->delta[l], sizeof(float) * (size_t)net->dims[l + 1] * batch));
     }
-    net->loss_part_cap = ceil_div(batch, kBM) * ceil_div(net->dims[L], 16);
+    net->loss_part_cap = 4 * ceil_div(batch, kBM) * ceil_div(net->dims[L], 16);
     B200_CUDA(cudaMalloc(&net->loss_part, sizeof(double) * net->loss_part_cap));
     net->cap = batch;
   }
@@ -171,7 +257,10 @@ int net_ensure(b200_net *net, long batch) {
       net->splits[l] = s;
       net->k_chunk[l] = kc;
       net->part_off[l] = total;
-      total += (size_t)s * M * N;
+      int s_tc = 1;
+      tc_dw_plan(net, l, batch, &s_tc); // room for whichever path runs
+      net->skinny_splits[l] = 2 * net->ctx->num_sms;
+      total += (size_t)std::max(std::max(s, s_tc), net->skinny_splits[l]) * M * N;
     }
     if (total > net->partials_cap) {
       if (net->partials) cudaFree(net->partials);
@@ -215,7 +304,8 @@ int net_forward(b200_net *net, const float *params, const float *x, long batch) 
   const float *cur = x;
   for (int l = 0; l < net->nlayers(); ++l) {
     bool done = false;
-    if (net->prec != B200_PREC_FP32) B200_TRY(tc_forward_layer(net, l, params, cur, batch, &done));
+    if (net->prec != B200_PREC_FP32 && l + 1 < net->nlayers())
+      B200_TRY(tc_forward_layer(net, l, params, cur, batch, nullptr, &done, nullptr));
     if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, false, nullptr, 0.f));
     cur = net->act[l];
   }
@@ -235,14 +325,19 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
 
   // forward sweep
   const float *cur = x;
+  bool fused_last = false; // last layer, loss, delta_L and delta_{L-1} produced by the penultimate layer's epilogue
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
+    if (last && fused_last) break;
     bool done = false;
     {
       char nm[16];
       snprintf(nm, sizeof(nm), "fwd%d", l);
       ProfScope ps(ctx, nm);
-      if (!last && net->prec != B200_PREC_FP32) B200_TRY(tc_forward_layer(net, l, params, cur, batch, &done));
+      if (!last && net->prec != B200_PREC_FP32) {
+        const TcFuseLast fuse{t, inv_batch};
+        B200_TRY(tc_forward_layer(net, l, params, cur, batch, &fuse, &done, &fused_last));
+      }
       if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, last, t, inv_batch));
     }
     cur = net->act[l];
@@ -254,22 +349,26 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     const int K = net->dims[l], N = net->dims[l + 1];
     const float *W = params + net->offs[l];
     const float *in = (l == 0) ? x : net->act[l - 1];
-    if (l > 0) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
+    if (l > 0 && !(l == L - 1 && fused_last)) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
       char nm[16];
       snprintf(nm, sizeof(nm), "dx%d", l);
       ProfScope ps(ctx, nm);
-      GemmParams p{};
-      p.A = net->delta[l]; p.lda = N;
-      p.B = W; p.ldb = N;
-      p.M = (int)batch; p.N = K; p.K = N;
-      p.vecA = aligned16(p.A) && (N % 4 == 0);
-      p.vecB = aligned16(W) && (N % 4 == 0);
-      p.a_ones_row = -1;
-      p.k_chunk = N;
-      p.act = net->acts[l - 1];
-      p.out = net->delta[l - 1]; p.ldo = K;
-      p.aux = net->act[l - 1];
-      B200_TRY((launch_gemm_simt<true, true, EPI_DX>(p, 1, st)));
+      bool done = false;
+      if (net->prec != B200_PREC_FP32) B200_TRY(tc_dx_layer(net, l, params, batch, &done));
+      if (!done) {
+        GemmParams p{};
+        p.A = net->delta[l]; p.lda = N;
+        p.B = W; p.ldb = N;
+        p.M = (int)batch; p.N = K; p.K = N;
+        p.vecA = aligned16(p.A) && (N % 4 == 0);
+        p.vecB = aligned16(W) && (N % 4 == 0);
+        p.a_ones_row = -1;
+        p.k_chunk = N;
+        p.act = net->acts[l - 1];
+        p.out = net->delta[l - 1]; p.ldo = K;
+        p.aux = net->act[l - 1];
+        B200_TRY((launch_gemm_simt<true, true, EPI_DX>(p, 1, st)));
+      }
     }
     { // [dW; db] partials = [A_{l-1} | 1]^T delta_l over batch slices
       char nm[16];
@@ -277,6 +376,17 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       ProfScope ps(ctx, nm);
       bool done = false;
       if (net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
+      if (!done && N <= 16 && K + 1 <= 160 && net->prec != B200_PREC_FP32) {
+        const int splits = std::max(1, std::min(net->skinny_splits[l], ceil_div(batch, kSkinnyTile)));
+        const int chunk = ceil_div(ceil_div(batch, splits), kSkinnyTile) * kSkinnyTile;
+        const int s_used = ceil_div(batch, chunk);
+        float *part = net->partials + net->part_off[l];
+        const unsigned long long ps = (unsigned long long)(K + 1) * N;
+        if (K + 1 <= 96) B200_LAUNCH(skinny_dw_kernel<3>, s_used, 256, 0, st, in, net->delta[l], K, N, batch, chunk, part, ps);
+        else B200_LAUNCH(skinny_dw_kernel<5>, s_used, 256, 0, st, in, net->delta[l], K, N, batch, chunk, part, ps);
+        net->splits_used[l] = s_used;
+        done = true;
+      }
       if (!done) {
         GemmParams p{};
         p.A = in; p.lda = K;
@@ -288,6 +398,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         p.k_chunk = net->k_chunk[l];
         p.out = net->partials + net->part_off[l];
         B200_TRY((launch_gemm_simt<false, false, EPI_DW>(p, net->splits[l], st)));
+        net->splits_used[l] = net->splits[l];
       }
     }
   }
@@ -299,7 +410,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     fp.L[l].off = net->offs[l];
     fp.L[l].size = (unsigned long long)(net->dims[l] + 1) * net->dims[l + 1];
     fp.L[l].part_off = net->part_off[l];
-    fp.L[l].splits = net->splits[l];
+    fp.L[l].splits = net->splits_used[l];
   }
   fp.n = net->n;
   fp.partials = net->partials;
@@ -351,9 +462,11 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   net->act.assign(nlayers, nullptr);
   net->delta.assign(nlayers, nullptr);
   net->splits.assign(nlayers, 1);
+  net->splits_used.assign(nlayers, 1);
+  net->skinny_splits.assign(nlayers, 1);
   net->k_chunk.assign(nlayers, 16);
   net->part_off.assign(nlayers, 0);
-  net->fin_blocks = std::max(1, std::min(2 * ctx->num_sms, ceil_div((long)net->n, 256)));
+  net->fin_blocks = std::max(1, std::min(32 * ctx->num_sms, ceil_div((long)net->n, 32)));
   cudaSetDevice(ctx->device);
   B200_CUDA(cudaMalloc(&net->fin_part, sizeof(double) * 2 * net->fin_blocks));
   B200_CUDA(cudaMalloc(&net->eval_out, sizeof(EvalOut)));

@@ -24,7 +24,9 @@ struct b200_net {
   std::vector<float *> act, delta;
 
   // split-K partials of [dW; db] per layer and their layout
-  std::vector<int> splits, k_chunk;
+  std::vector<int> splits, k_chunk; // FFMA split-K plan
+  std::vector<int> skinny_splits;   // split plan of the skinny (out <= 16) dW kernel
+  std::vector<int> splits_used;     // splits written by the last evaluation (either path)
   std::vector<size_t> part_off;
   float *partials = nullptr;
   size_t partials_cap = 0;
