@@ -1,0 +1,3 @@
+// forwarding header: the reference includes "cuda/sgd.cuh"; everything lives in cuda_mlp.hpp + unified.hpp
+#pragma once
+#include "../unified/unified.hpp"
