@@ -43,7 +43,8 @@ if rank == 0:
     loss_single, w_single = run(h1, X, T, B, B)
     d = float(np.max(np.abs(loss_multi - loss_single) / np.abs(loss_single)))
     pr = float(np.linalg.norm(w_multi - w_single) / np.linalg.norm(w_single))
-    print(json.dumps({"world": world, "iters": iters, "max_rel_loss_diff": d, "params_rel_l2": pr,
+    d5 = float(np.max(np.abs(loss_multi[:5] - loss_single[:5]) / np.abs(loss_single[:5])))
+    print(json.dumps({"world": world, "iters": iters, "max_rel_loss_diff": d, "max_rel_loss_diff_first5": d5, "params_rel_l2": pr,
                       "loss_multi_last": float(loss_multi[-1]), "loss_single_last": float(loss_single[-1])}))
 dist.barrier()
 dist.destroy_process_group()
