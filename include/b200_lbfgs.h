@@ -92,6 +92,14 @@ int b200_net_get_precision(b200_net *net);
 int b200_net_set_l2(b200_net *net, float lambda);
 /* sample-sharded multi-GPU: the B of the 1/B scaling. 0 (default) = shard batch x number of ranks. */
 int b200_net_set_global_batch(b200_net *net, long batch_global);
+/* Input cache for 8-bit image data. If EVERY element of x_dev[batch][in] is exactly float(u)/255.0f, u in 0..255
+ * (what the reference's loader produces, tests/mnist/mnist_loader.hpp:59) a uint8 copy is kept and the tensor-core
+ * modes read it instead of the fp32 array in the two input-bound GEMMs of layer 0 (4x fewer HBM bytes; u is exact in
+ * TF32, results agree with the fp32 path to ~1e-7). Otherwise nothing happens (*quantized = 0). The solvers call it
+ * themselves at the start of a solve (x is constant during a solve) and clear it at the end; callers of the one-shot
+ * entry points may call it explicitly and MUST call b200_net_clear_input_cache before modifying x in place. */
+int b200_net_quantize_input(b200_net *net, const float *x_dev, long batch, int *quantized);
+int b200_net_clear_input_cache(b200_net *net);
 /* forward_only (network.cuh:79-88): X device (in x batch). Output stays on device. */
 int b200_net_forward(b200_net *net, const float *x_dev, long batch);
 /* compute_loss_and_grad (network.cuh:97-119): evaluates at the network's bound params, writes the gradient

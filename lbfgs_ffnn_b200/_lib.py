@@ -85,6 +85,8 @@ SYMBOLS = {
     "b200_net_get_precision": (_i, [_vp]),
     "b200_net_set_l2": (_i, [_vp, _f]),
     "b200_net_set_global_batch": (_i, [_vp, _l]),
+    "b200_net_quantize_input": (_i, [_vp, _vp, _l, C.POINTER(_i)]),
+    "b200_net_clear_input_cache": (_i, [_vp]),
     "b200_net_forward": (_i, [_vp, _vp, _l]),
     "b200_net_loss_grad": (_i, [_vp, _vp, _vp, _l, _pf]),
     "b200_net_loss_grad_async": (_i, [_vp, _vp, _vp, _vp, _l, _vp, _vp]),

@@ -255,6 +255,15 @@ class CudaNetwork:
     def set_global_batch(self, batch_global):
         check(lib().b200_net_set_global_batch(self._h, int(batch_global)))
 
+    def quantize_input(self, input_dev, batch):
+        """cache a uint8 copy of an input that is exactly u/255 (see include/b200_lbfgs.h); returns True if used"""
+        ok = C.c_int(0)
+        check(lib().b200_net_quantize_input(self._h, C.c_void_p(_ptr(input_dev)), int(batch), C.byref(ok)))
+        return bool(ok.value)
+
+    def clear_input_cache(self):
+        check(lib().b200_net_clear_input_cache(self._h))
+
     def set_params(self, host):
         """inject an explicit parameter vector (the two reference backends initialise differently)"""
         a = np.asarray(host)

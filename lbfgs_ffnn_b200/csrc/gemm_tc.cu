@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 namespace b200 {
 
@@ -31,6 +32,7 @@ namespace {
 constexpr int BM = 128;           // UMMA M (cta_group::1)
 constexpr int BK = 32;            // floats per K block = one 128-byte swizzle row
 constexpr int kATileBytes = BM * BK * 4;
+constexpr int kSplitThreads = 192; // warps 2-7 prepare operands (3xTF32 split / uint8 conversion) during the main loop
 constexpr int kTcThreads = 256;   // warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-7 epilogue / splitter
 constexpr int kOnesBytes = 2048;  // 16 rows x 128 B of 1.0f (bias-gradient B operand; layout-agnostic)
 constexpr int kLastCols = 12;                          // fused last layer: out <= 12, rows padded to 12 floats
@@ -52,6 +54,7 @@ struct TcParams {
   float *partial;   // DW: [split][(in+1)*out]
   unsigned long long partial_stride;
   int out_dim, in_dim; // DW
+  float acc_scale;     // uint8 operand variants: 1/255 (accumulator holds 255 * result)
   // FWD of the penultimate layer with the (skinny, out <= 16) last layer fused into the epilogue
   int fuse_last, last_out, last_act;
   const float *w_last;   // [cols_valid][last_out] followed by the last_out biases
@@ -59,6 +62,7 @@ struct TcParams {
   float *out_last, *delta_last, *delta_prev;
   float inv_batch;
   double *loss_part;     // [gridDim.x * 4]
+  long long *dbg;        // B200_TC_TIMING=1: per-CTA {main loop, epilogue} clock64 durations
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -161,6 +165,20 @@ __device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, 
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+// activation with a compile-time tag when ACT >= 0 (the ReLU fast path), else the runtime switch. A per-element
+// runtime switch puts a uniform branch between every pair of independent FMAs and serialises the epilogue.
+template <int ACT> __device__ __forceinline__ float act_apply_c(int act, float v) {
+  if constexpr (ACT == B200_ACT_RELU) return fmaxf(v, 0.0f);
+  else if constexpr (ACT == B200_ACT_LINEAR) return v;
+  else return act_apply(act, v);
+}
+template <int ACT> __device__ __forceinline__ float act_deriv_c(int act, float a) {
+  if constexpr (ACT == B200_ACT_RELU) return a > 0.0f ? 1.0f : 0.0f;
+  else if constexpr (ACT == B200_ACT_LINEAR) return 1.0f;
+  else return act_deriv_from_output(act, a);
+}
+template <int V> struct IntTag { static constexpr int value = V; };
+
 // Store a 32(row) x 32(col) fp32 block held one row per lane as 32 fully coalesced 128-byte row segments
 // (a per-thread row store would touch 32 different lines per instruction, 8x the L2 write transactions).
 // scratch: this warp's private 32 x 33 floats of shared memory.
@@ -175,19 +193,43 @@ __device__ __forceinline__ void store_block_coalesced(const float (&r)[32], floa
   __syncwarp();
 }
 
-template <int BN, bool X3>
+// U8: 0 = both operands fp32 in HBM; 1 = the A operand (FWD: the input X) is stored as uint8 = 255*x;
+//     2 = the B operand (DW: X) is. A uint8 operand is converted to fp32 in shared memory by the splitter warps;
+//     it is exact in TF32, so it needs no lo tile and contributes no lo*hi product.
+template <int BN, bool X3, int U8>
 struct SmemPlan {
   static constexpr int kBTileBytes = BN * BK * 4;
-  static constexpr int kStageBytes = (kATileBytes + kBTileBytes) * (X3 ? 2 : 1);
-  static constexpr int kStages = (kStageBytes * 3 <= 200 * 1024) ? 3 : 2;
-  static constexpr int kBarOffset = kStages * kStageBytes + kOnesBytes + ((kLastBytes + 127) / 128) * 128;
+  static constexpr bool kSplitA = X3 && U8 != 1, kSplitB = X3 && U8 != 2;
+  static constexpr int kOffBHi = kATileBytes;
+  static constexpr int kOffALo = kATileBytes + kBTileBytes;
+  static constexpr int kOffBLo = kOffALo + (kSplitA ? kATileBytes : 0);
+  static constexpr int kOffU8 = kOffBLo + (kSplitB ? kBTileBytes : 0);
+  static constexpr int kU8Bytes = U8 == 1 ? BM * BK : (U8 == 2 ? BN * BK : 0);
+  static constexpr int kStageBytes = ((kOffU8 + kU8Bytes + 1023) / 1024) * 1024;
+  // 3 stages when that leaves room for two CTAs per SM (epilogue of one overlaps the main loop of the other),
+  // otherwise as deep as one CTA's 200 KB allows: HBM latency under load is ~4 us, so bytes in flight are what
+  // bound the streaming GEMMs (Little's law), not the tensor pipe
+  static constexpr int kFit = (200 * 1024) / kStageBytes;
+  // uint8-A forward kernel: HBM-light (4 KB per K block), epilogue-heavy -> 2 stages so that TWO CTAs fit an SM and one's
+  // epilogue overlaps the other's main loop
+  static constexpr int kStages = (U8 == 1 && kStageBytes * 2 <= 104 * 1024) ? 2
+                               : (kStageBytes * 3 <= 100 * 1024) ? 3 : (kFit > 6 ? 6 : (kFit < 2 ? 2 : kFit));
+  static constexpr int kTxBytes = (U8 == 1 ? BM * BK : kATileBytes) + (U8 == 2 ? BN * BK : kBTileBytes);
+  static constexpr int kOnes = (U8 == 1) ? 0 : kOnesBytes; // the ones tile is a dW-only operand; the uint8-A kernel is forward-only
+  static constexpr int kBarOffset = kStages * kStageBytes + kOnes + ((kLastBytes + 127) / 128) * 128;
   static constexpr int kTotal = kBarOffset + 128 + 1024; // barriers + tmem slot + alignment slack
 };
 
-template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3>
-__global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Plan = SmemPlan<BN, X3>;
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8>
+__global__ void __launch_bounds__(kTcThreads, ((SmemPlan<BN, X3, U8>::kTotal + 1024) * 2 <= 227 * 1024) ? 2 : 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  using Plan = SmemPlan<BN, X3, U8>;
+  constexpr bool kSplitA = Plan::kSplitA, kSplitB = Plan::kSplitB;
+  // FWD / DX: the B operand is the weight matrix, the same for every CTA: its hi / lo parts are split ONCE per
+  // evaluation into two global arrays (split_params_kernel) and arrive as two TMA loads; only A is split in-kernel
+  constexpr bool kPresplitB = kSplitB && ROLE != TC_DW;
+  constexpr bool kUseSplit = X3 || U8 != 0; // the issuer waits for the splitter / converter warps
   constexpr int kBTileBytes = Plan::kBTileBytes;
   constexpr int kStages = Plan::kStages;
   constexpr bool kBias = (ROLE == TC_DW);
@@ -196,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // K blocks over kMain accumulators and (b) keeps the 2^-12-sized hi*lo + lo*hi corrections in their own
   // accumulator; the epilogue adds them in round-to-nearest fp32. DW keeps one (its sums are sign-mixed).
   constexpr bool kSplitAcc = X3 && ROLE != TC_DW;
-  constexpr int kMain = kSplitAcc ? (BN <= 128 ? 3 : 1) : 1;
+  constexpr int kMain = kSplitAcc ? ((BN <= 128 && U8 != 1) ? 3 : 1) : 1; // uint8-A: 256 TMEM columns per CTA, two CTAs per SM
   constexpr int kColsNeeded = kMain * BN + (kSplitAcc ? BN : 0) + (kBias ? 32 : 0);
   constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                           : kColsNeeded <= 256 ? 256 : 512;
@@ -207,8 +249,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  auto a_tile = [&](int s, int lo) { return base + s * Plan::kStageBytes + lo * (kATileBytes + kBTileBytes); };
-  auto b_tile = [&](int s, int lo) { return a_tile(s, lo) + kATileBytes; };
+  auto a_tile = [&](int s, int lo) { return base + s * Plan::kStageBytes + (lo ? Plan::kOffALo : 0); };
+  auto b_tile = [&](int s, int lo) { return base + s * Plan::kStageBytes + (lo ? Plan::kOffBLo : Plan::kOffBHi); };
+  auto u8_tile = [&](int s) { return base + s * Plan::kStageBytes + Plan::kOffU8; };
   const uint32_t ones = base + kStages * Plan::kStageBytes;
   const uint32_t bars = base + Plan::kBarOffset;
   auto bar_full = [&](int s) { return bars + 8 * s; };
@@ -218,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(base_ptr + Plan::kBarOffset + 8 * (3 * kStages + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = p.dbg ? clock64() : 0;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   int kb_begin = 0, kb_end = p.k_blocks;
   if (ROLE == TC_DW) {
@@ -239,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
-      mbar_init(bar_split(s), 128);
+      mbar_init(bar_split(s), kSplitThreads);
     }
     mbar_init(bar_accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -260,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  float *wl = reinterpret_cast<float *>(base_ptr + kStages * Plan::kStageBytes + kOnesBytes); // fused last layer
+  float *wl = reinterpret_cast<float *>(base_ptr + kStages * Plan::kStageBytes + Plan::kOnes); // fused last layer
   const bool fuse = (ROLE == TC_FWD) && p.fuse_last;
 
   if (warp == 0) {
@@ -270,19 +314,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_expect_tx(bar_full(s), kATileBytes + kBTileBytes);
+        mbar_expect_tx(bar_full(s), Plan::kTxBytes + (kPresplitB ? kBTileBytes : 0));
         const int k0 = kb * BK;
-        if (A_MAJOR == MAJOR_K) {
+        if (U8 == 1) {
+          tma_load_2d(u8_tile(s), &tmA, bar_full(s), k0, m0);   // uint8 box {32 K bytes, 128 rows}, no swizzle
+        } else if (A_MAJOR == MAJOR_K) {
           tma_load_2d(a_tile(s, 0), &tmA, bar_full(s), k0, m0); // box {32 K, 128 rows}
         } else {
 #pragma unroll
           for (int g = 0; g < BM / 32; ++g) tma_load_2d(a_tile(s, 0) + g * 4096, &tmA, bar_full(s), m0 + 32 * g, k0);
         }
-        if (B_MAJOR == MAJOR_K) {
+        if (U8 == 2) {
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g) tma_load_2d(u8_tile(s) + g * 1024, &tmB, bar_full(s), n0 + 32 * g, k0); // uint8 {32 N, 32 K}
+        } else if (B_MAJOR == MAJOR_K) {
           tma_load_2d(b_tile(s, 0), &tmB, bar_full(s), k0, n0); // box {32 K, BN rows}
+          if (kPresplitB) tma_load_2d(b_tile(s, 1), &tmBlo, bar_full(s), k0, n0);
         } else {
 #pragma unroll
           for (int g = 0; g < BN / 32; ++g) tma_load_2d(b_tile(s, 0) + g * 4096, &tmB, bar_full(s), n0 + 32 * g, k0);
+          if (kPresplitB) {
+#pragma unroll
+            for (int g = 0; g < BN / 32; ++g) tma_load_2d(b_tile(s, 1) + g * 4096, &tmBlo, bar_full(s), n0 + 32 * g, k0);
+          }
         }
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
@@ -296,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(X3 ? bar_split(s) : bar_full(s), ph);
+        mbar_wait(kUseSplit ? bar_split(s) : bar_full(s), ph);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
@@ -313,13 +367,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_tf32(d_main, da[0], db[0], idesc, acc_main);
           if (X3) {
             const uint32_t d_small = kSplitAcc ? tmem_base + kSmallCol : d_main;
-            umma_tf32(d_small, da[0], db[1], idesc, kSplitAcc ? acc : 1u); // hi * lo
-            umma_tf32(d_small, da[1], db[0], idesc, 1u);                   // lo * hi
+            uint32_t acc_small = kSplitAcc ? acc : 1u;
+            if (kSplitB) { umma_tf32(d_small, da[0], db[1], idesc, acc_small); acc_small = 1u; } // hi * lo
+            if (kSplitA) { umma_tf32(d_small, da[1], db[0], idesc, acc_small); }                 // lo * hi
           }
           if (do_bias) {
             const uint64_t dones = desc_k_major(ones);
             umma_tf32(tmem_base + kBiasCol, da[0], dones, idesc_bias, acc);
-            if (X3) umma_tf32(tmem_base + kBiasCol, da[1], dones, idesc_bias, 1u);
+            if (kSplitA) umma_tf32(tmem_base + kBiasCol, da[1], dones, idesc_bias, 1u);
           }
         }
         umma_commit(bar_empty(s)); // smem slot reusable once these MMAs have read it
@@ -328,36 +383,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(bar_accum); // accumulator complete
     }
     __syncwarp();
-  } else if (warp < 4) {
-    if (fuse) { // stage [W_last | b_last], rows zero-padded to kLastCols floats (row cols_valid = the bias)
-      const int OL = p.last_out;
-      for (int i = threadIdx.x - 64; i < (p.cols_valid + 1) * kLastCols; i += 64) {
-        const int k = i / kLastCols, j = i - k * kLastCols;
-        wl[i] = (j < OL) ? __ldg(p.w_last + (size_t)k * OL + j) : 0.0f;
-      }
+  }
+  if (warp >= 2 && warp < 4 && fuse) { // stage [W_last | b_last], rows zero-padded to kLastCols floats (row cols_valid = the bias)
+    const int OL = p.last_out;
+    for (int i = threadIdx.x - 64; i < (p.cols_valid + 1) * kLastCols; i += 64) {
+      const int k = i / kLastCols, j = i - k * kLastCols;
+      wl[i] = (j < OL) ? __ldg(p.w_last + (size_t)k * OL + j) : 0.0f;
     }
-  } else if (X3) {
-    // ===== 3xTF32 splitter: hi = rna_tf32(a) in place, lo = a - hi (exact) ========================
-    const int et = threadIdx.x - 128; // 0..127
+  }
+  if (warp < 2) {
+  } else if (kUseSplit) {
+    // ===== operand preparation warps (4-7) =======================================================
+    // 3xTF32: hi = rna_tf32(a) in place, lo = a - hi (exact), element-wise hence layout-agnostic.
+    // uint8 operand: u -> float(u) written straight into the UMMA canonical layout (exact in TF32, no lo tile).
+    const int et = threadIdx.x - 64; // 0..191
+    auto split_tile = [&](uint8_t *hi_p, uint8_t *lo_p, int bytes) {
+      float4 *hi = reinterpret_cast<float4 *>(hi_p);
+      float4 *lo = reinterpret_cast<float4 *>(lo_p);
+#pragma unroll 4
+      for (int i = et; i < bytes / 16; i += kSplitThreads) {
+        // hi = a rounded to the nearest TF32 (ties away): add half an ulp of the 10-bit mantissa, clear the low 13
+        // bits. cvt.rna.tf32.f32 is emulated with ~12 integer instructions on sm_100; this is 2 (finite inputs).
+        const float4 a = hi[i];
+        float4 h, l;
+        h.x = __uint_as_float((__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u); l.x = a.x - h.x;
+        h.y = __uint_as_float((__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u); l.y = a.y - h.y;
+        h.z = __uint_as_float((__float_as_uint(a.z) + 0x1000u) & 0xFFFFE000u); l.z = a.z - h.z;
+        h.w = __uint_as_float((__float_as_uint(a.w) + 0x1000u) & 0xFFFFE000u); l.w = a.w - h.w;
+        hi[i] = h;
+        lo[i] = l;
+      }
+    };
+    auto u8x4_to_f4 = [](uint32_t w) { // float(u) = as_float(0x4B000000 | u) - 2^23, exact
+      return make_float4(__uint_as_float(0x4B000000u | (w & 0xFFu)) - 8388608.0f,
+                         __uint_as_float(0x4B000000u | ((w >> 8) & 0xFFu)) - 8388608.0f,
+                         __uint_as_float(0x4B000000u | ((w >> 16) & 0xFFu)) - 8388608.0f,
+                         __uint_as_float(0x4B000000u | (w >> 24)) - 8388608.0f);
+    };
     int s = 0;
     uint32_t ph = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(bar_full(s), ph);
-      // A and B tiles are contiguous: [A hi | B hi] then [A lo | B lo]; element-wise, layout-agnostic
-      float4 *hi = reinterpret_cast<float4 *>(base_ptr + s * Plan::kStageBytes);
-      float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * Plan::kStageBytes + kATileBytes + kBTileBytes);
-      constexpr int kVec = (kATileBytes + kBTileBytes) / 16;
+      uint8_t *st = base_ptr + s * Plan::kStageBytes;
+      if (U8 == 1) {
+        // raw [128 rows][32 B] -> K-major SWIZZLE_128B tile: row r at r*128, 16-byte chunk c at (c ^ (r & 7))*16
+        const uint32_t *raw = reinterpret_cast<const uint32_t *>(st + Plan::kOffU8);
+#pragma unroll 2
+        for (int idx = et; idx < BM * BK / 4; idx += kSplitThreads) {
+          const int r = idx >> 3, c = idx & 7;
+          *reinterpret_cast<float4 *>(st + r * 128 + ((c ^ (r & 7)) << 4)) = u8x4_to_f4(raw[idx]);
+        }
+      } else if (kSplitA) {
+        split_tile(st, st + Plan::kOffALo, kATileBytes);
+      }
+      if (U8 == 2) {
+        // raw [BN/32 groups][32 K rows][32 B] -> MN-major SWIZZLE_128B_BASE32B: group g at g*4096, row r at r*128,
+        // 32-byte chunk q/2 at ((q/2) ^ (r & 3))*32, half (q & 1)*16
+        const uint32_t *raw = reinterpret_cast<const uint32_t *>(st + Plan::kOffU8);
 #pragma unroll 4
-      for (int i = et; i < kVec; i += 128) {
-        const float4 a = hi[i];
-        float4 h, l;
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.x)); h.x = __uint_as_float(t); l.x = a.x - h.x;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.y)); h.y = __uint_as_float(t); l.y = a.y - h.y;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.z)); h.z = __uint_as_float(t); l.z = a.z - h.z;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a.w)); h.w = __uint_as_float(t); l.w = a.w - h.w;
-        hi[i] = h;
-        lo[i] = l;
+        for (int idx = et; idx < BN * BK / 4; idx += kSplitThreads) {
+          const int g = idx >> 8, r = (idx >> 3) & 31, q = idx & 7;
+          *reinterpret_cast<float4 *>(st + Plan::kOffBHi + g * 4096 + r * 128 + ((((q >> 1) ^ (r & 3)) << 5) | ((q & 1) << 4))) =
+              u8x4_to_f4(raw[idx]);
+        }
+      } else if (kSplitB && !kPresplitB) {
+        split_tile(st + Plan::kOffBHi, st + Plan::kOffBLo, kBTileBytes);
       }
       fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(bar_split(s));
@@ -372,7 +462,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(bar_accum, 0);
     tc_fence_after();
   }
-  {
+  const long long t_acc = p.dbg ? clock64() : 0;
+  auto epilogue = [&](auto act_tag) {
+    constexpr int ACT = decltype(act_tag)::value;
     const int half = warp >> 2;
     const int row = (warp & 3) * 32 + lane; // TMEM lane == D row
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -410,9 +502,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float z[kLastCols]; // fused last layer: this half's share of the pre-activations of this thread's sample
 #pragma unroll
     for (int j = 0; j < kLastCols; ++j) z[j] = 0.0f;
+    uint32_t relu_mask[(BN + 63) / 64]; // ReLU fast path: act'(a) of this thread's elements, one bit each
+#pragma unroll
+    for (int j = 0; j < (BN + 63) / 64; ++j) relu_mask[j] = 0u;
     for (int c0 = half * 32; c0 < umma_n; c0 += 64) {
       uint32_t v[32];
       load_chunk(c0, v);
+      if (U8 != 0) { // uint8 operand = 255 * x: undo the scale once per accumulator element
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.acc_scale);
+      }
       const int gcol0 = n0 + c0;
       if (ROLE == TC_FWD || ROLE == TC_DX) {
         if (gcol0 + 32 <= p.cols_valid) {
@@ -422,14 +521,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int q = 0; q < 8; ++q) {
             if (ROLE == TC_FWD) {
               const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + gcol0) + q);
-              r[4 * q + 0] = act_apply(p.act, __uint_as_float(v[4 * q + 0]) + b4.x);
-              r[4 * q + 1] = act_apply(p.act, __uint_as_float(v[4 * q + 1]) + b4.y);
-              r[4 * q + 2] = act_apply(p.act, __uint_as_float(v[4 * q + 2]) + b4.z);
-              r[4 * q + 3] = act_apply(p.act, __uint_as_float(v[4 * q + 3]) + b4.w);
+              r[4 * q + 0] = act_apply_c<ACT>(p.act, __uint_as_float(v[4 * q + 0]) + b4.x);
+              r[4 * q + 1] = act_apply_c<ACT>(p.act, __uint_as_float(v[4 * q + 1]) + b4.y);
+              r[4 * q + 2] = act_apply_c<ACT>(p.act, __uint_as_float(v[4 * q + 2]) + b4.z);
+              r[4 * q + 3] = act_apply_c<ACT>(p.act, __uint_as_float(v[4 * q + 3]) + b4.w);
               if (fuse) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float a = r[4 * q + e];
+                  if (ACT == B200_ACT_RELU && a > 0.0f) relu_mask[c0 / 64] |= 1u << (4 * q + e);
                   const float4 *wr = reinterpret_cast<const float4 *>(wl + (size_t)(gcol0 + 4 * q + e) * kLastCols);
                   const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2];
                   ffma2(z[0], z[1], a, a, w0.x, w0.y); ffma2(z[2], z[3], a, a, w0.z, w0.w);
@@ -440,10 +540,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (row_ok) a4 = __ldg(reinterpret_cast<const float4 *>(aux) + q);
-              r[4 * q + 0] = __uint_as_float(v[4 * q + 0]) * act_deriv_from_output(p.act, a4.x);
-              r[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * act_deriv_from_output(p.act, a4.y);
-              r[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * act_deriv_from_output(p.act, a4.z);
-              r[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * act_deriv_from_output(p.act, a4.w);
+              r[4 * q + 0] = __uint_as_float(v[4 * q + 0]) * act_deriv_c<ACT>(p.act, a4.x);
+              r[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * act_deriv_c<ACT>(p.act, a4.y);
+              r[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * act_deriv_c<ACT>(p.act, a4.z);
+              r[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * act_deriv_c<ACT>(p.act, a4.w);
             }
           }
           store_block_coalesced(r, scratch, p.out + wrow0 * p.ld_out + gcol0, p.ld_out, rows_ok, lane);
@@ -454,8 +554,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) {
             if (gcol0 + j < p.cols_valid) {
               const float acc = __uint_as_float(v[j]);
-              dst[j] = (ROLE == TC_FWD) ? act_apply(p.act, acc + __ldg(p.bias + gcol0 + j))
-                                        : acc * act_deriv_from_output(p.act, __ldg(aux + j));
+              dst[j] = (ROLE == TC_FWD) ? act_apply_c<ACT>(p.act, acc + __ldg(p.bias + gcol0 + j))
+                                        : acc * act_deriv_c<ACT>(p.act, __ldg(aux + j));
             }
           }
         }
@@ -500,22 +600,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int c0 = half * 32; c0 < umma_n; c0 += 64) {
         uint32_t v[32];
-        load_chunk(c0, v);
+        if (ACT != B200_ACT_RELU) { // generic activations need the activation value again for act'(a)
+          load_chunk(c0, v);
+          if (U8 != 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.acc_scale);
+          }
+        }
         float r[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + c0) + q);
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          float bb[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ACT != B200_ACT_RELU) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + c0) + q);
+            bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = act_apply(p.act, __uint_as_float(v[4 * q + e]) + bb[e]);
             const float4 *wr = reinterpret_cast<const float4 *>(wl + (size_t)(c0 + 4 * q + e) * kLastCols);
             const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2];
             float g0 = 0.0f, g1 = 0.0f;
             ffma2(g0, g1, w0.x, w0.y, dl[0], dl[1]); ffma2(g0, g1, w0.z, w0.w, dl[2], dl[3]);
             ffma2(g0, g1, w1.x, w1.y, dl[4], dl[5]); ffma2(g0, g1, w1.z, w1.w, dl[6], dl[7]);
             ffma2(g0, g1, w2.x, w2.y, dl[8], dl[9]); ffma2(g0, g1, w2.z, w2.w, dl[10], dl[11]);
-            r[4 * q + e] = (g0 + g1) * act_deriv_from_output(p.act, a);
+            if (ACT == B200_ACT_RELU) {
+              r[4 * q + e] = ((relu_mask[c0 / 64] >> (4 * q + e)) & 1u) ? (g0 + g1) : 0.0f;
+            } else {
+              const float a = act_apply_c<ACT>(p.act, __uint_as_float(v[4 * q + e]) + bb[e]);
+              r[4 * q + e] = (g0 + g1) * act_deriv_c<ACT>(p.act, a);
+            }
           }
         }
         store_block_coalesced(r, scratch, p.delta_prev + wrow0 * p.ld_out + c0, p.ld_out, rows_ok, lane);
@@ -533,8 +646,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __uint_as_float(v[0]);
     }
     tc_fence_before();
-  }
+  };
+  if (p.act == B200_ACT_RELU) epilogue(IntTag<B200_ACT_RELU>{});
+  else if (p.act == B200_ACT_LINEAR) epilogue(IntTag<B200_ACT_LINEAR>{});
+  else epilogue(IntTag<-1>{});
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    const long long t_end = clock64();
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (cta < 4096) { p.dbg[2 * cta] = t_acc - t_start; p.dbg[2 * cta + 1] = t_end - t_acc; }
+  }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
@@ -580,27 +701,78 @@ int make_map(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigne
   return B200_OK;
 }
 
+// 2-D uint8 tensor map (the quantised input): dim0 bytes contiguous, box {32, box1}, no swizzle, OOB -> 0
+int make_map_u8(CUtensorMap *tm, const uint8_t *ptr, unsigned long long dim0, unsigned long long dim1, unsigned box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {dim0};
+  cuuint32_t box[2] = {32, box1};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(uint8) failed (%d): dims %llu x %llu box1 %u ptr %p", (int)r, dim0, dim1, box1, ptr);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
 bool tma_ok(const float *ptr, long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (ld % 4) == 0; }
 
-template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3>
-int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<A_MAJOR, B_MAJOR, ROLE, BN, X3>;
-  constexpr int smem = SmemPlan<BN, X3>::kTotal;
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8>
+int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tblo, const TcParams &p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<A_MAJOR, B_MAJOR, ROLE, BN, X3, U8>;
+  constexpr int smem = SmemPlan<BN, X3, U8>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  kern<<<grid, kTcThreads, smem, st>>>(ta, tb, p);
+  static long long *dbg = nullptr;
+  static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
+  TcParams pp = p;
+  if (timing) {
+    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 2 * 4096));
+    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 2 * 4096, st));
+    pp.dbg = dbg;
+  }
+  kern<<<grid, kTcThreads, smem, st>>>(ta, tb, tblo, pp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
+  if (timing) { // debugging aid: average main-loop and epilogue duration per CTA, in SM clocks
+    std::vector<long long> h(2 * 4096);
+    B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    const size_t n = std::min<size_t>(4096, (size_t)grid.x * grid.y * grid.z);
+    double m = 0, e = 0;
+    for (size_t i = 0; i < n; ++i) { m += h[2 * i]; e += h[2 * i + 1]; }
+    fprintf(stderr, "[tc timing] role %d BN %d x3 %d u8 %d grid %ux%ux%u: main loop %.0f clk, epilogue %.0f clk per CTA\n", ROLE, BN,
+            (int)X3, U8, grid.x, grid.y, grid.z, m / n, e / n);
+  }
   return B200_OK;
 }
 
-template <int A_MAJOR, int B_MAJOR, int ROLE, int BN>
-int launch_tc_prec(bool x3, const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, dim3 grid, cudaStream_t st) {
-  return x3 ? launch_tc<A_MAJOR, B_MAJOR, ROLE, BN, true>(ta, tb, p, grid, st)
-            : launch_tc<A_MAJOR, B_MAJOR, ROLE, BN, false>(ta, tb, p, grid, st);
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, int U8 = 0>
+int launch_tc_prec(bool x3, const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tblo, const TcParams &p, dim3 grid,
+                   cudaStream_t st) {
+  return x3 ? launch_tc<A_MAJOR, B_MAJOR, ROLE, BN, true, U8>(ta, tb, tblo, p, grid, st)
+            : launch_tc<A_MAJOR, B_MAJOR, ROLE, BN, false, U8>(ta, tb, tblo, p, grid, st);
+}
+
+__global__ void __launch_bounds__(256) split_params_kernel(const float *__restrict__ w, unsigned long long n, float *__restrict__ hi,
+                                                         float *__restrict__ lo) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float a = w[i];
+    const float h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = a - h;
+  }
 }
 
 int tc_mask() { // debugging aid: B200_TC_MASK bit0 = FWD, bit1 = DX, bit2 = DW (default all); read per call
@@ -621,10 +793,18 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   const float *W = params + net->offs[l];
   if (!tma_ok(in, K) || !tma_ok(W, N) || !tma_ok(net->act[l], N) || N % 32 != 0) return B200_OK;
   const bool x3 = net->prec == B200_PREC_TF32X3;
+  // layer 0 with an input that is exactly u/255: read the 4x smaller uint8 copy (net_quantize_input)
+  const uint8_t *xq = (l == 0 && (tc_mask() & 16) == 0) ? net_xq_lookup(net, in, batch) : nullptr;
   CUtensorMap ta, tb;
-  B200_TRY(make_map(&ta, in, K, batch, K, BM, MAJOR_K)); // A: {K, rows}, box {32, 128}
-  B200_TRY(make_map(&tb, W, N, K, N, 32, MAJOR_MN));  // B: {N, K}, box {32, 32}
+  if (xq) B200_TRY(make_map_u8(&ta, xq, K, batch, BM));        // A: uint8 {K bytes, rows}, box {32, 128}
+  else B200_TRY(make_map(&ta, in, K, batch, K, BM, MAJOR_K)); // A: {K, rows}, box {32, 128}
+  // 3xTF32: B = the pre-split weights (net_split_params); otherwise the raw weights (tblo unused)
+  const float *Whi = x3 ? net->w_hi + net->offs[l] : W, *Wlo = x3 ? net->w_lo + net->offs[l] : W;
+  CUtensorMap tblo;
+  B200_TRY(make_map(&tb, Whi, N, K, N, 32, MAJOR_MN));        // B: {N, K}, box {32, 32}
+  B200_TRY(make_map(&tblo, Wlo, N, K, N, 32, MAJOR_MN));
   TcParams p{};
+  p.acc_scale = xq ? 1.0f / 255.0f : 1.0f;
   p.rows_valid = (int)batch; p.cols_valid = N;
   p.k_blocks = ceil_div(K, BK); p.kb_per_split = p.k_blocks;
   p.act = net->acts[l]; p.bias = W + (size_t)K * N;
@@ -645,10 +825,13 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
     if (fused) *fused = true;
   }
   cudaStream_t st = net->ctx->stream;
-  if (N <= 64) {
-    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(N, 64)), st)));
+  const dim3 g64(ceil_div(batch, BM), ceil_div(N, 64)), g128(ceil_div(batch, BM), ceil_div(N, 128));
+  if (xq) {
+    if (N <= 64) B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64, 1>(x3, ta, tb, tblo, p, g64, st)));
+    else B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 128, 1>(x3, ta, tb, tblo, p, g128, st)));
   } else {
-    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 128>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(N, 128)), st)));
+    if (N <= 64) B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64>(x3, ta, tb, tblo, p, g64, st)));
+    else B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 128>(x3, ta, tb, tblo, p, g128, st)));
   }
   *done = true;
   return B200_OK;
@@ -670,14 +853,19 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
   p.rows_valid = (int)batch; p.cols_valid = Kin;
   p.k_blocks = ceil_div(Nout, BK); p.kb_per_split = p.k_blocks;
   p.act = net->acts[l - 1];
+  p.acc_scale = 1.0f;
   p.out = net->delta[l - 1]; p.ld_out = Kin; p.aux = net->act[l - 1];
   cudaStream_t st = net->ctx->stream;
+  const float *Whi = x3 ? net->w_hi + net->offs[l] : W, *Wlo = x3 ? net->w_lo + net->offs[l] : W;
+  CUtensorMap tblo;
   if (Kin <= 64) {
-    B200_TRY(make_map(&tb, W, Nout, Kin, Nout, 64, MAJOR_K)); // B: {K = out, N = in}, box {32, BN}
-    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 64>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 64)), st)));
+    B200_TRY(make_map(&tb, Whi, Nout, Kin, Nout, 64, MAJOR_K)); // B: {K = out, N = in}, box {32, BN}
+    B200_TRY(make_map(&tblo, Wlo, Nout, Kin, Nout, 64, MAJOR_K));
+    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 64>(x3, ta, tb, tblo, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 64)), st)));
   } else {
-    B200_TRY(make_map(&tb, W, Nout, Kin, Nout, 128, MAJOR_K));
-    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 128>(x3, ta, tb, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 128)), st)));
+    B200_TRY(make_map(&tb, Whi, Nout, Kin, Nout, 128, MAJOR_K));
+    B200_TRY(make_map(&tblo, Wlo, Nout, Kin, Nout, 128, MAJOR_K));
+    B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 128>(x3, ta, tb, tblo, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 128)), st)));
   }
   *done = true;
   return B200_OK;
@@ -700,24 +888,44 @@ int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
   const int Kin = net->dims[l], Nout = net->dims[l + 1];
   if (!tma_ok(net->delta[l], Nout) || !tma_ok(in, Kin)) return B200_OK;
   const bool x3 = net->prec == B200_PREC_TF32X3;
+  const uint8_t *xq = (l == 0 && (tc_mask() & 16) == 0) ? net_xq_lookup(net, in, batch) : nullptr;
   CUtensorMap ta, tb;
   B200_TRY(make_map(&ta, net->delta[l], Nout, batch, Nout, 32, MAJOR_MN)); // A: {M = out, K = batch}, box {32, 32}
-  B200_TRY(make_map(&tb, in, Kin, batch, Kin, 32, MAJOR_MN));              // B: {N = in, K = batch}, box {32, 32}
+  if (xq) B200_TRY(make_map_u8(&tb, xq, Kin, batch, 32));                  // B: uint8 {N = in bytes, K = batch}, box {32, 32}
+  else B200_TRY(make_map(&tb, in, Kin, batch, Kin, 32, MAJOR_MN));         // B: {N = in, K = batch}, box {32, 32}
   int splits = 1;
   const int per = tc_dw_plan(net, l, batch, &splits);
   TcParams p{};
+  p.acc_scale = xq ? 1.0f / 255.0f : 1.0f;
   p.rows_valid = Nout; p.cols_valid = Kin;
   p.k_blocks = ceil_div(batch, BK); p.kb_per_split = per;
   p.partial = net->partials + net->part_off[l];
   p.partial_stride = (unsigned long long)(Kin + 1) * Nout;
   p.out_dim = Nout; p.in_dim = Kin;
-  B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256>(x3, ta, tb, p, dim3(ceil_div(Nout, BM), ceil_div(Kin, 256), splits),
-                                                           net->ctx->stream)));
+  const dim3 grid(ceil_div(Nout, BM), ceil_div(Kin, 256), splits);
+  if (xq) B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256, 2>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
+  else B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
   net->splits_used[l] = splits; // finalize_grad_kernel combines exactly the splits this launch wrote
   *done = true;
   return B200_OK;
 }
 
-void tc_release(b200_net *) {}
+// 3xTF32: hi / lo parts of the whole parameter vector, once per evaluation (read by the FWD and DX kernels)
+int tc_split_params(b200_net *net, const float *params) {
+  if (net->prec != B200_PREC_TF32X3) return B200_OK;
+  if (!net->w_hi) {
+    B200_CUDA(cudaMalloc(&net->w_hi, sizeof(float) * net->n));
+    B200_CUDA(cudaMalloc(&net->w_lo, sizeof(float) * net->n));
+  }
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * net->ctx->num_sms, (net->n + 255) / 256));
+  B200_LAUNCH(split_params_kernel, blocks, 256, 0, net->ctx->stream, params, (unsigned long long)net->n, net->w_hi, net->w_lo);
+  return B200_OK;
+}
+
+void tc_release(b200_net *net) {
+  if (net->w_hi) cudaFree(net->w_hi);
+  if (net->w_lo) cudaFree(net->w_lo);
+  net->w_hi = net->w_lo = nullptr;
+}
 
 } // namespace b200

@@ -16,6 +16,7 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
 int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done);
 // split-K plan of the tensor-core dW kernel: returns K blocks per split, *splits = number of splits
 int tc_dw_plan(b200_net *net, int l, long batch, int *splits);
+int tc_split_params(b200_net *net, const float *params);
 void tc_release(b200_net *net);
 
 } // namespace b200

@@ -215,6 +215,29 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float *__restrict_
   }
 }
 
+// x -> u = round(255 x) as uint8; *flag &= (every x is exactly float(u)/255.0f with 0 <= u <= 255)
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n,
+                                                          uint8_t *__restrict__ q, int *flag) {
+  int ok = 1;
+  const unsigned long long nv = n / 4;
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv;
+       v += (unsigned long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(x) + v);
+    const float f[4] = {a.x, a.y, a.z, a.w};
+    unsigned packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int u = __float2int_rn(f[e] * 255.0f);
+      ok &= (u >= 0 && u <= 255 && __fdiv_rn((float)u, 255.0f) == f[e]) ? 1 : 0;
+      packed |= (unsigned)(u & 255) << (8 * e);
+    }
+    reinterpret_cast<unsigned *>(q)[v] = packed;
+  }
+  if (!__all_sync(0xffffffffu, ok)) {
+    if ((threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+  }
+}
+
 int free_batch_buffers(b200_net *net) {
   for (float *p : net->act) if (p) cudaFree(p);
   for (float *p : net->delta) if (p) cudaFree(p);
@@ -272,6 +295,52 @@ int net_ensure(b200_net *net, long batch) {
   return B200_OK;
 }
 
+void net_xq_clear(b200_net *net) {
+  net->xq.valid = false;
+  net->xq.src = nullptr;
+  net->xq.rows = 0;
+}
+
+int net_quantize_input(b200_net *net, const float *x, long batch) {
+  const int in = net->dims[0];
+  if (net->xq.valid && net->xq.src == x && net->xq.rows == batch) return B200_OK;
+  net_xq_clear(net);
+  // TMA needs 16-byte row strides on the uint8 copy; float4 reads need an aligned source
+  if (in % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0 || batch <= 0) return B200_OK;
+  const size_t bytes = (size_t)batch * in;
+  cudaStream_t st = net->ctx->stream;
+  if (bytes > net->xq.cap) {
+    if (net->xq.data) cudaFree(net->xq.data);
+    net->xq.data = nullptr;
+    net->xq.cap = 0;
+    B200_CUDA(cudaMalloc(&net->xq.data, bytes));
+    net->xq.cap = bytes;
+  }
+  if (!net->xq.flag) B200_CUDA(cudaMalloc(&net->xq.flag, sizeof(int)));
+  const int one = 1;
+  B200_CUDA(cudaMemcpyAsync(net->xq.flag, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  B200_LAUNCH(quantize_u8_kernel, 8 * net->ctx->num_sms, 256, 0, st, x, (unsigned long long)bytes, net->xq.data, net->xq.flag);
+  int ok = 0;
+  B200_CUDA(cudaMemcpyAsync(&ok, net->xq.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (ok) {
+    net->xq.valid = true;
+    net->xq.src = x;
+    net->xq.rows = batch;
+  }
+  return B200_OK;
+}
+
+const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch) {
+  if (!net->xq.valid || x < net->xq.src) return nullptr;
+  const size_t off = (size_t)(x - net->xq.src);
+  const int in = net->dims[0];
+  if (off % in != 0) return nullptr;
+  const long row0 = (long)(off / in);
+  if (row0 + batch > net->xq.rows) return nullptr;
+  return net->xq.data + (size_t)row0 * in;
+}
+
 static int launch_fwd_layer(b200_net *net, int l, const float *params, const float *in, long batch, bool last,
                             const float *t, float inv_batch) {
   const int K = net->dims[l], N = net->dims[l + 1];
@@ -301,9 +370,13 @@ static int launch_fwd_layer(b200_net *net, int l, const float *params, const flo
 
 int net_forward(b200_net *net, const float *params, const float *x, long batch) {
   B200_TRY(net_ensure(net, batch));
+  B200_TRY(tc_split_params(net, params));
   const float *cur = x;
   for (int l = 0; l < net->nlayers(); ++l) {
     bool done = false;
+    char nm[16];
+    snprintf(nm, sizeof(nm), "fwdonly%d", l);
+    ProfScope ps(net->ctx, nm);
     if (net->prec != B200_PREC_FP32 && l + 1 < net->nlayers())
       B200_TRY(tc_forward_layer(net, l, params, cur, batch, nullptr, &done, nullptr));
     if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, false, nullptr, 0.f));
@@ -323,6 +396,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   if (batch_global <= 0) batch_global = net->batch_global > 0 ? net->batch_global : batch * ctx->world;
   const float inv_batch = 1.0f / (float)batch_global;
 
+  B200_TRY(tc_split_params(net, params));
   // forward sweep
   const float *cur = x;
   bool fused_last = false; // last layer, loss, delta_L and delta_{L-1} produced by the penultimate layer's epilogue
@@ -480,6 +554,8 @@ int b200_net_destroy(b200_net *net) {
   cudaStreamSynchronize(net->ctx->stream);
   free_batch_buffers(net);
   tc_release(net);
+  if (net->xq.data) cudaFree(net->xq.data);
+  if (net->xq.flag) cudaFree(net->xq.flag);
   if (net->partials) cudaFree(net->partials);
   if (net->fin_part) cudaFree(net->fin_part);
   if (net->eval_out) cudaFree(net->eval_out);
@@ -545,6 +621,19 @@ int b200_net_set_l2(b200_net *net, float lambda) {
 int b200_net_set_global_batch(b200_net *net, long batch_global) {
   B200_REQUIRE(net && batch_global >= 0, "bad argument");
   net->batch_global = batch_global;
+  return B200_OK;
+}
+
+int b200_net_quantize_input(b200_net *net, const float *x_dev, long batch, int *quantized) {
+  B200_REQUIRE(net && x_dev, "null argument");
+  cudaSetDevice(net->ctx->device);
+  B200_TRY(net_quantize_input(net, x_dev, batch));
+  if (quantized) *quantized = net->xq.valid ? 1 : 0;
+  return B200_OK;
+}
+int b200_net_clear_input_cache(b200_net *net) {
+  B200_REQUIRE(net, "null net");
+  net_xq_clear(net);
   return B200_OK;
 }
 

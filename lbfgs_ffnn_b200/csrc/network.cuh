@@ -32,6 +32,19 @@ struct b200_net {
   size_t partials_cap = 0;
   long partials_batch = -1;
 
+  // uint8 copy of an input that is exactly u/255 (MNIST-style pixels, tests/mnist/mnist_loader.hpp:59): the two
+  // X-bound GEMMs of layer 0 then read 4x fewer bytes and need no hi/lo split for X (u is exact in TF32)
+  struct InputQ {
+    const float *src = nullptr;
+    long rows = 0;
+    uint8_t *data = nullptr;
+    size_t cap = 0;
+    bool valid = false;
+    int *flag = nullptr; // device
+  } xq;
+
+  float *w_hi = nullptr, *w_lo = nullptr; // 3xTF32: hi / lo split of the parameter vector of the current evaluation
+
   double *loss_part = nullptr; // per-CTA partials of sum diff^2
   int loss_part_cap = 0, loss_part_n = 0;
   double *fin_part = nullptr;  // per-CTA partials of ||g||^2 and ||w||^2 (2 per CTA)
@@ -56,5 +69,10 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
              float *grad_out, EvalOut *out);
 int net_forward(b200_net *net, const float *params, const float *x, long batch);
 int net_ensure(b200_net *net, long batch);
+// build (or reuse) the uint8 copy of x[batch][in]; no-op unless every element is exactly float(u)/255.0f
+int net_quantize_input(b200_net *net, const float *x, long batch);
+void net_xq_clear(b200_net *net);
+// the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
+const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
 
 } // namespace b200

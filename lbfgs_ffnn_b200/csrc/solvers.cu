@@ -217,6 +217,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
 
   double cb_loss = 0.0;
+  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch)); // no-op unless x == u/255
   if (!s->started) {
     // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
     B200_TRY(obj.eval_async(params, s->gbuf[0], mail, &cb_loss));
@@ -367,6 +368,7 @@ int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *u
   B200_TRY(b200_lbfgs_create(ctx, n, opts, &s));
   const int status = b200_lbfgs_run(s, net, fn, user, params, input, target, batch, s->o.max_iters, hist);
   b200_lbfgs_destroy(s);
+  if (net) net_xq_clear(net); // the caller may change x after the solve
   return status;
 }
 
@@ -400,6 +402,8 @@ int b200_gd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user
   obj.n = N;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   double cb_loss = 0.0;
+  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch));
+  struct ClearQ { b200_net *n; ~ClearQ() { if (n) net_xq_clear(n); } } clear_q{net};
   B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
   B200_CUDA(cudaStreamSynchronize(st));
   double loss = net ? mail->loss : cb_loss;
@@ -464,6 +468,8 @@ int b200_sgd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *use
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   long evals = 0;
   double cb_loss = 0.0;
+  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, total_samples));
+  struct ClearQ { b200_net *n; ~ClearQ() { if (n) net_xq_clear(n); } } clear_q{net};
   float current_lr = o.lr;
   const int num_batches = (total_samples + o.batch_size - 1) / o.batch_size;
   float prev_epoch_loss_avg = std::numeric_limits<float>::infinity();

@@ -86,3 +86,59 @@ def test_tc_lbfgs_trajectory(handle, oracle):
     loss, _, _ = rec.copy_to_host()
     for k in range(iters):
         assert abs(loss[k] - ref["loss"][k]) <= 4e-5 * (1.6 ** min(k, 20)) * abs(ref["loss"][k]), (k, loss[k], ref["loss"][k])
+
+
+@pytest.mark.parametrize("prec", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("dims,acts", NETS[:2])
+@pytest.mark.parametrize("batch", [37, 1000, 60000])
+def test_u8_input_path(handle, oracle, dims, acts, batch, prec):
+    """8-bit image inputs (x == float(u)/255.0f exactly): the layer-0 GEMMs read a uint8 copy (b200_net_quantize_input)"""
+    onet, w, X, T = make_problem(oracle, dims, acts, batch)
+    loss_o, g_o = onet.loss_grad(w, X, T)
+    net = make_gpu_net(handle, dims, acts, w, precision=prec)
+    dx, dt = upload(X), upload(T)
+    assert net.quantize_input(dx, batch) is True
+    loss = net.compute_loss_and_grad(dx, dt, batch)
+    g = net.get_grads()
+    tol_l = TOL[prec] if prec == "tf32x3" else 2e-3
+    tol_g = max(TOL[prec], 5e-5) if batch >= 60000 else TOL[prec]
+    if prec == "tf32" and batch < 100:
+        tol_g = 1.0
+    assert abs(loss - loss_o) <= tol_l * abs(loss_o), (loss, loss_o)
+    assert rel_l2(g, g_o) <= tol_g, rel_l2(g, g_o)
+    # the fp32-array path on the same network gives the same answer to rounding
+    net.clear_input_cache()
+    loss_f = net.compute_loss_and_grad(dx, dt, batch)
+    g_f = net.get_grads()
+    if prec == "tf32x3":
+        assert abs(loss - loss_f) <= 5e-6 * abs(loss_f)
+        assert rel_l2(g, g_f) <= tol_g
+
+
+def test_u8_input_rejected_when_not_quantised(handle, oracle):
+    dims, acts, batch = NETS[0][0], NETS[0][1], 500
+    onet, w, X, T = make_problem(oracle, dims, acts, batch)
+    Xn = (X + np.float32(1e-3) * np.random.RandomState(0).rand(*X.shape).astype(np.float32)).astype(np.float32)
+    net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
+    dx, dt = upload(Xn), upload(T)
+    assert net.quantize_input(dx, batch) is False
+    loss_o, g_o = onet.loss_grad(w, Xn, T)
+    loss = net.compute_loss_and_grad(dx, dt, batch)
+    assert abs(loss - loss_o) <= 2e-5 * abs(loss_o) and rel_l2(net.get_grads(), g_o) <= 2e-5
+
+
+def test_sgd_tensorcore_subranges(handle, oracle):
+    """CudaSGD slices the input by pointer offset (src/cuda/sgd.cuh:104-107): the uint8 cache must follow the slices"""
+    dims, acts, B = [784, 128, 10], ["relu", "linear"], 1000
+    onet, w, X, T = make_problem(oracle, dims, acts, B)
+    ref = onet.sgd_cuda_policy(w, X, T, batch_size=96, lr=0.02, momentum=0.9, decay_rate=0.5, decay_step=2, max_iters=3,
+                               tol=0.0, record=True)
+    net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
+    s = P.CudaSGD(handle)
+    s.setLearningRate(0.02); s.setMomentum(0.9); s.setBatchSize(96); s.setLearningRateDecay(0.5, 2)
+    s.setMaxIterations(3); s.setTolerance(0.0); s.setDimensions(784, 10)
+    rec = P.IterationRecorder(); rec.init(4); s.setRecorder(rec)
+    s.solve(net.params_size(), net.params_data(), upload(X), upload(T), B, net)
+    loss, _, _ = rec.copy_to_host()
+    assert np.allclose(loss, ref["loss"], rtol=3e-4)
+    assert rel_l2(net.get_params(), ref["params"]) <= 3e-4
