@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
 }
 
 // loss = 0.5 * inv_batch * sum(loss_part) + 0.5 * lam * sum(w^2 parts); gnorm2 = sum(g^2 parts)
-__global__ void __launch_bounds__(256) eval_scalars_kernel(const double *loss_part, int n_loss, const double *fin_part,
+__global__ void __launch_bounds__(1024) eval_scalars_kernel(const double *loss_part, int n_loss, const double *fin_part,
                                                            int n_fin, double inv_batch, double lam, int want_gnorm,
                                                            EvalOut *out) {
   __shared__ double red[32];
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) evaluate_kernel(const float *out, const f
 // that would idle 15/16 of its lanes (and the reference's serial sum_rows_kernel, src/cuda/kernels.cuh:144-153).
 constexpr int kSkinnyTile = 64;
 template <int FPL>
-__global__ void __launch_bounds__(256) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int in,
+__global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int in,
                                                         int out, long batch, int chunk, float *__restrict__ partial,
                                                         unsigned long long pstride) {
   __shared__ __align__(16) float sd[kSkinnyTile][16];
@@ -496,7 +496,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   {
     ProfScope ps(ctx, "finalize");
     B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);
-    B200_LAUNCH(eval_scalars_kernel, 1, 256, 0, st, net->loss_part, net->loss_part_n, net->fin_part, net->fin_blocks,
+    B200_LAUNCH(eval_scalars_kernel, 1, 1024, 0, st, net->loss_part, net->loss_part_n, net->fin_part, net->fin_blocks,
                 (double)inv_batch, (double)fp.lam, multi ? 0 : 1, out);
   }
   if (multi) {
@@ -540,7 +540,7 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   net->skinny_splits.assign(nlayers, 1);
   net->k_chunk.assign(nlayers, 16);
   net->part_off.assign(nlayers, 0);
-  net->fin_blocks = std::max(1, std::min(32 * ctx->num_sms, ceil_div((long)net->n, 32)));
+  net->fin_blocks = std::max(1, std::min(8 * ctx->num_sms, ceil_div((long)net->n, 32)));
   cudaSetDevice(ctx->device);
   B200_CUDA(cudaMalloc(&net->fin_part, sizeof(double) * 2 * net->fin_blocks));
   B200_CUDA(cudaMalloc(&net->eval_out, sizeof(EvalOut)));

@@ -11,6 +11,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
 
 namespace b200 {
@@ -129,6 +131,12 @@ struct b200_lbfgs {
   LbfgsView view{};
   double *partials = nullptr, *dot_part = nullptr;
   float *gbuf[2] = {nullptr, nullptr}, *p = nullptr, *x_prev = nullptr, *S = nullptr, *Y = nullptr;
+  // one CUDA graph per (gradient-buffer parity, history-reset flag): direction kernels + first trial evaluation +
+  // the two scalar read-backs of a steady-state iteration are ONE launch instead of ~10
+  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  long graph_launches[2][2] = {{0, 0}, {0, 0}};
+  const void *gkey[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // net, params, input, target, batch
+  bool graphs_ok = true;
   // minimisation state carried across runs
   bool started = false;
   int cur = 0, iter = 0, reset_next = 0;
@@ -184,10 +192,19 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
   return B200_OK;
 }
 
+static void lbfgs_drop_graphs(b200_lbfgs *s) {
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      if (s->graph[a][b]) cudaGraphExecDestroy(s->graph[a][b]);
+      s->graph[a][b] = nullptr;
+    }
+}
+
 int b200_lbfgs_destroy(b200_lbfgs *s) {
   if (!s) return B200_OK;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
+  lbfgs_drop_graphs(s);
   cudaFree(s->ws);
   delete s;
   return B200_OK;
@@ -239,22 +256,63 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
 
     // ---- direction: pair formation of the previous step + two-loop + first trial point, 3 launches ----
     const int mode = (iter > 0 && m > 0) ? DOTS_FORM_PAIR : DOTS_NONE;
-    {
-      ProfScope ps(ctx, "lbfgs_dots");
-      DotsArgs da{S, Y, N, ld, s->view, g, params, x_prev, g_new, mode, s->reset_next, 0, s->partials};
-      B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
+    auto issue_direction = [&]() -> int {
+      {
+        ProfScope ps(ctx, "lbfgs_dots");
+        DotsArgs da{S, Y, N, ld, s->view, g, params, x_prev, g_new, mode, s->reset_next, 0, s->partials};
+        B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
+      }
+      {
+        ProfScope ps(ctx, "lbfgs_solve");
+        SolveArgs sa{s->view, s->partials, s->nblk, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
+        B200_TRY(launch_lbfgs_solve(sa, mp, st));
+      }
+      {
+        ProfScope ps(ctx, "lbfgs_apply");
+        ApplyArgs aa{S, Y, N, ld, s->view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
+        B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
+      }
+      B200_CUDA(cudaMemcpyAsync(&mail->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+      return B200_OK;
+    };
+    // Steady-state iterations of the network objective replay a captured graph: direction + first trial evaluation.
+    bool first_eval_issued = false;
+    const bool graphable = net && !wolfe && s->graphs_ok && mode == DOTS_FORM_PAIR && ctx->world == 1 && !ctx->prof.on &&
+                           max_ls > 0 && std::getenv("B200_NO_GRAPH") == nullptr && std::getenv("B200_TC_TIMING") == nullptr;
+    if (graphable) {
+      const void *key[5] = {net, params, input, target, (const void *)(intptr_t)batch};
+      if (memcmp(key, s->gkey, sizeof(key)) != 0) {
+        lbfgs_drop_graphs(s);
+        memcpy(s->gkey, key, sizeof(key));
+      }
+      cudaGraphExec_t &ge = s->graph[s->cur][s->reset_next];
+      if (!ge) {
+        const long l0 = b200_launch_count();
+        cudaGraph_t gr = nullptr;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          ok = issue_direction() == B200_OK && obj.eval_async(params, g_new, mail, &cb_loss) == B200_OK;
+          --obj.evals; // counted when the graph is replayed
+          ok = (cudaStreamEndCapture(st, &gr) == cudaSuccess) && ok && gr != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&ge, gr, 0) == cudaSuccess;
+        if (gr) cudaGraphDestroy(gr);
+        s->graph_launches[s->cur][s->reset_next] = b200_launch_count() - l0;
+        g_launches.fetch_add(-(b200_launch_count() - l0), std::memory_order_relaxed); // captured, not executed
+        if (!ok) {
+          cudaGetLastError();
+          ge = nullptr;
+          s->graphs_ok = false; // fall back to plain launches for the rest of this solver's life
+        }
+      }
+      if (ge) {
+        B200_CUDA(cudaGraphLaunch(ge, st));
+        g_launches.fetch_add(s->graph_launches[s->cur][s->reset_next], std::memory_order_relaxed);
+        ++obj.evals;
+        first_eval_issued = true;
+      }
     }
-    {
-      ProfScope ps(ctx, "lbfgs_solve");
-      SolveArgs sa{s->view, s->partials, s->nblk, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
-      B200_TRY(launch_lbfgs_solve(sa, mp, st));
-    }
-    {
-      ProfScope ps(ctx, "lbfgs_apply");
-      ApplyArgs aa{S, Y, N, ld, s->view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
-      B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
-    }
-    B200_CUDA(cudaMemcpyAsync(&mail->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+    if (!first_eval_issued) B200_TRY(issue_direction());
     s->reset_next = 0;
 
     // ---- line search ------------------------------------------------------------------------------
@@ -265,7 +323,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
       double gdotp = 0.0;
       for (int ls = 0; ls < max_ls; ++ls) {
         if (ls > 0) B200_TRY(launch_trial_point(N, x_prev, (float)alpha, p, params, st)); // lbfgs.cuh:116-117
-        B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
+        if (!(ls == 0 && first_eval_issued)) B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
         B200_CUDA(cudaStreamSynchronize(st));
         if (ls == 0) { alpha = (double)(float)mail->hdr.alpha0; gdotp = mail->hdr.gdotp; }
         loss_new = net ? mail->loss : cb_loss;
