@@ -40,7 +40,9 @@ struct GemmParams {
   float *out;         // FWD: activations [M][N]; DX: delta_prev [M][N]; DW: partials [split][M*N]
   long ldo;
   const float *aux;   // FWD_LAST: targets [M][N]; DX: A_prev [M][N]
-  float *delta;       // FWD_LAST: delta out [M][N]
+  long ld_aux;        // row stride of aux (DX: act_{l-1} is [M][N] while delta_{l-1} = out is [M][ldo])
+  float *delta;       // FWD_LAST: delta out [M][ldd]
+  long ldd;
   float inv_batch;    // FWD_LAST: 1/B_global
   double *loss_part;  // FWD_LAST: one partial per CTA
 };
@@ -214,12 +216,12 @@ __global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const GemmParams p)
         const float a = act_apply(p.act, v + __ldg(p.bias + n));
         p.out[(long)m * p.ldo + n] = a;
         if constexpr (EPI == EPI_FWD_LAST) {
-          const float d = a - __ldg(p.aux + (long)m * p.ldo + n);
+          const float d = a - __ldg(p.aux + (long)m * p.ld_aux + n);
           loss_local += (double)d * (double)d;
-          p.delta[(long)m * p.ldo + n] = d * p.inv_batch * act_deriv_from_output(p.act, a);
+          p.delta[(long)m * p.ldd + n] = d * p.inv_batch * act_deriv_from_output(p.act, a);
         }
       } else if constexpr (EPI == EPI_DX) {
-        const float ap = __ldg(p.aux + (long)m * p.ldo + n);
+        const float ap = __ldg(p.aux + (long)m * p.ld_aux + n);
         p.out[(long)m * p.ldo + n] = v * act_deriv_from_output(p.act, ap);
       } else { // EPI_DW: partial of the flat [ (in+1) x out ] gradient block of this layer
         p.out[(long)blockIdx.z * ((long)p.M * p.N) + (long)m * p.N + n] = v;

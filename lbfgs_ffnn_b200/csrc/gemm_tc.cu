@@ -60,6 +60,7 @@ struct TcParams {
   const float *w_last;   // [cols_valid][last_out] followed by the last_out biases
   const float *targets;  // [rows][last_out]
   float *out_last, *delta_last, *delta_prev;
+  int ld_delta_last;     // row stride of delta_last (out rounded up to 4)
   float inv_batch;
   double *loss_part;     // [gridDim.x * 4]
   long long *dbg;        // B200_TC_TIMING=1: per-CTA {main loop, epilogue} clock64 durations
@@ -589,7 +590,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           dl[j] = d * p.inv_batch * act_deriv_from_output(p.last_act, o);
           if (half == 0) {
             p.out_last[grow * OL + j] = o;
-            p.delta_last[grow * OL + j] = dl[j];
+            p.delta_last[grow * p.ld_delta_last + j] = dl[j];
             lsum += (double)d * (double)d;
           }
         }
@@ -810,7 +811,7 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   p.act = net->acts[l]; p.bias = W + (size_t)K * N;
   p.out = net->act[l]; p.ld_out = N;
   const int L = net->nlayers();
-  if (fuse && (tc_mask() & 8) == 0 && l == L - 2 && N <= 128 && net->dims[L] <= kLastCols && tma_ok(net->delta[l], N)) {
+  if (fuse && (tc_mask() & 8) == 0 && l == L - 2 && N <= 128 && net->dims[L] <= kLastCols && tma_ok(net->delta[l], net->ldd[l]) && net->ldd[l] == N) {
     p.fuse_last = 1;
     p.last_out = net->dims[L];
     p.last_act = net->acts[L - 1];
@@ -818,6 +819,7 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
     p.targets = fuse->targets;
     p.out_last = net->act[L - 1];
     p.delta_last = net->delta[L - 1];
+    p.ld_delta_last = net->ldd[L - 1];
     p.delta_prev = net->delta[l];
     p.inv_batch = fuse->inv_batch;
     p.loss_part = net->loss_part;
@@ -843,12 +845,13 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
   if (!(tc_mask() & 2)) return B200_OK;
   const int Kin = net->dims[l], Nout = net->dims[l + 1]; // contraction over out, result width in
   const float *W = params + net->offs[l];
-  if (!tma_ok(net->delta[l], Nout) || !tma_ok(W, Nout) || !tma_ok(net->delta[l - 1], Kin) || !tma_ok(net->act[l - 1], Kin) ||
+  if (!tma_ok(net->delta[l], net->ldd[l]) || !tma_ok(W, Nout) || !tma_ok(net->delta[l - 1], Kin) || net->ldd[l - 1] != Kin ||
+      !tma_ok(net->act[l - 1], Kin) ||
       Kin % 32 != 0)
     return B200_OK;
   const bool x3 = net->prec == B200_PREC_TF32X3;
   CUtensorMap ta, tb;
-  B200_TRY(make_map(&ta, net->delta[l], Nout, batch, Nout, BM, MAJOR_K)); // A: {K = out, rows}, box {32, 128}
+  B200_TRY(make_map(&ta, net->delta[l], Nout, batch, net->ldd[l], BM, MAJOR_K)); // A: {K = out, rows}, box {32, 128}
   TcParams p{};
   p.rows_valid = (int)batch; p.cols_valid = Kin;
   p.k_blocks = ceil_div(Nout, BK); p.kb_per_split = p.k_blocks;
@@ -886,11 +889,11 @@ int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
   *done = false;
   if (!(tc_mask() & 4)) return B200_OK;
   const int Kin = net->dims[l], Nout = net->dims[l + 1];
-  if (!tma_ok(net->delta[l], Nout) || !tma_ok(in, Kin)) return B200_OK;
+  if (!tma_ok(net->delta[l], net->ldd[l]) || !tma_ok(in, Kin)) return B200_OK;
   const bool x3 = net->prec == B200_PREC_TF32X3;
   const uint8_t *xq = (l == 0 && (tc_mask() & 16) == 0) ? net_xq_lookup(net, in, batch) : nullptr;
   CUtensorMap ta, tb;
-  B200_TRY(make_map(&ta, net->delta[l], Nout, batch, Nout, 32, MAJOR_MN)); // A: {M = out, K = batch}, box {32, 32}
+  B200_TRY(make_map(&ta, net->delta[l], Nout, batch, net->ldd[l], 32, MAJOR_MN)); // A: {M = out, K = batch}, box {32, 32}
   if (xq) B200_TRY(make_map_u8(&tb, xq, Kin, batch, 32));                  // B: uint8 {N = in bytes, K = batch}, box {32, 32}
   else B200_TRY(make_map(&tb, in, Kin, batch, Kin, 32, MAJOR_MN));         // B: {N = in, K = batch}, box {32, 32}
   int splits = 1;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) evaluate_kernel(const float *out, const f
 // that would idle 15/16 of its lanes (and the reference's serial sum_rows_kernel, src/cuda/kernels.cuh:144-153).
 constexpr int kSkinnyTile = 64;
 template <int FPL>
-__global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int in,
+__global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int ldd, int in,
                                                         int out, long batch, int chunk, float *__restrict__ partial,
                                                         unsigned long long pstride) {
   __shared__ __align__(16) float sd[kSkinnyTile][16];
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restri
     __syncthreads();
     for (int e = threadIdx.x; e < kSkinnyTile * 16; e += blockDim.x) {
       const int r = e >> 4, j = e & 15;
-      sd[r][j] = (r < nb && j < out) ? __ldg(D + (bt + r) * out + j) : 0.0f;
+      sd[r][j] = (r < nb && j < out) ? __ldg(D + (bt + r) * ldd + j) : 0.0f;
     }
     __syncthreads();
 #pragma unroll 2
@@ -260,7 +260,8 @@ int net_ensure(b200_net *net, long batch) {
     free_batch_buffers(net);
     for (int l = 0; l < L; ++l) {
       B200_CUDA(cudaMalloc(&net->act[l], sizeof(float) * (size_t)net->dims[l + 1] * batch));
-      B200_CUDA(cudaMalloc(&net->delta[l], sizeof(float) * (size_t)net->dims[l + 1] * batch));
+      B200_CUDA(cudaMalloc(&net->delta[l], sizeof(float) * (size_t)net->ldd[l] * batch));
+      B200_CUDA(cudaMemsetAsync(net->delta[l], 0, sizeof(float) * (size_t)net->ldd[l] * batch, net->ctx->stream)); // padding columns stay 0
     }
     net->loss_part_cap = 4 * ceil_div(batch, kBM) * ceil_div(net->dims[L], 16);
     B200_CUDA(cudaMalloc(&net->loss_part, sizeof(double) * net->loss_part_cap));
@@ -357,8 +358,9 @@ static int launch_fwd_layer(b200_net *net, int l, const float *params, const flo
   p.act = net->acts[l];
   p.out = net->act[l]; p.ldo = N;
   if (last) {
-    p.aux = t;
+    p.aux = t; p.ld_aux = N;
     p.delta = net->delta[l];
+    p.ldd = net->ldd[l];
     p.inv_batch = inv_batch;
     p.loss_part = net->loss_part;
     const int tn = (N > 64) ? 8 : (N > 32 ? 4 : (N > 16 ? 2 : 1));
@@ -431,16 +433,16 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       if (net->prec != B200_PREC_FP32) B200_TRY(tc_dx_layer(net, l, params, batch, &done));
       if (!done) {
         GemmParams p{};
-        p.A = net->delta[l]; p.lda = N;
+        p.A = net->delta[l]; p.lda = net->ldd[l];
         p.B = W; p.ldb = N;
         p.M = (int)batch; p.N = K; p.K = N;
-        p.vecA = aligned16(p.A) && (N % 4 == 0);
+        p.vecA = aligned16(p.A) && (N % 4 == 0) && (net->ldd[l] % 4 == 0);
         p.vecB = aligned16(W) && (N % 4 == 0);
         p.a_ones_row = -1;
         p.k_chunk = N;
         p.act = net->acts[l - 1];
-        p.out = net->delta[l - 1]; p.ldo = K;
-        p.aux = net->act[l - 1];
+        p.out = net->delta[l - 1]; p.ldo = net->ldd[l - 1];
+        p.aux = net->act[l - 1]; p.ld_aux = K;
         B200_TRY((launch_gemm_simt<true, true, EPI_DX>(p, 1, st)));
       }
     }
@@ -456,15 +458,15 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         const int s_used = ceil_div(batch, chunk);
         float *part = net->partials + net->part_off[l];
         const unsigned long long ps = (unsigned long long)(K + 1) * N;
-        if (K + 1 <= 96) B200_LAUNCH(skinny_dw_kernel<3>, s_used, 256, 0, st, in, net->delta[l], K, N, batch, chunk, part, ps);
-        else B200_LAUNCH(skinny_dw_kernel<5>, s_used, 256, 0, st, in, net->delta[l], K, N, batch, chunk, part, ps);
+        if (K + 1 <= 96) B200_LAUNCH(skinny_dw_kernel<3>, s_used, 256, 0, st, in, net->delta[l], net->ldd[l], K, N, batch, chunk, part, ps);
+        else B200_LAUNCH(skinny_dw_kernel<5>, s_used, 256, 0, st, in, net->delta[l], net->ldd[l], K, N, batch, chunk, part, ps);
         net->splits_used[l] = s_used;
         done = true;
       }
       if (!done) {
         GemmParams p{};
         p.A = in; p.lda = K;
-        p.B = net->delta[l]; p.ldb = N;
+        p.B = net->delta[l]; p.ldb = net->ldd[l];
         p.M = K + 1; p.N = N; p.K = (int)batch;
         p.vecA = aligned16(in) && (K % 4 == 0);
         p.vecB = aligned16(p.B) && (N % 4 == 0);
@@ -535,6 +537,8 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   net->n = off;
   net->act.assign(nlayers, nullptr);
   net->delta.assign(nlayers, nullptr);
+  net->ldd.resize(nlayers);
+  for (int l = 0; l < nlayers; ++l) net->ldd[l] = (dims[l + 1] + 3) & ~3;
   net->splits.assign(nlayers, 1);
   net->splits_used.assign(nlayers, 1);
   net->skinny_splits.assign(nlayers, 1);

@@ -22,6 +22,7 @@ struct b200_net {
   long cap = 0;        // sample capacity of act/delta
   long last_batch = 0;
   std::vector<float *> act, delta;
+  std::vector<int> ldd; // row stride of delta[l]: out rounded up to 4 floats so that TMA (16-byte strides) can address it
 
   // split-K partials of [dW; db] per layer and their layout
   std::vector<int> splits, k_chunk; // FFMA split-K plan
