@@ -143,6 +143,10 @@ typedef struct b200_lbfgs_opts { /* defaults: minimizer_base.cuh:63-64, lbfgs.cu
   float c2;                      /* 0.9 (WOLFE only) */
   int linesearch;                /* B200_LS_ARMIJO */
   int record_timing;             /* 1: per-iteration CUDA-event timing when a history is attached */
+  int shard_history;             /* multi-GPU: 0 = history replicated on every rank (gradient all-reduce);
+                                  * 1 = x, g, S, Y sharded by parameter index: gradient reduce-scatter, only the
+                                  *     5(m+1)+1 partial dot products all-reduced, parameters all-gathered;
+                                  * -1 (default) = sharded when n >= 4M parameters and more than one rank */
 } b200_lbfgs_opts;
 void b200_lbfgs_default_opts(b200_lbfgs_opts *o);
 

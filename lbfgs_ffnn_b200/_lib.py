@@ -26,7 +26,7 @@ class History(C.Structure):
 class LbfgsOpts(C.Structure):
     _fields_ = [("max_iters", C.c_int), ("tol", C.c_float), ("memory", C.c_int), ("max_line_iters", C.c_int),
                 ("c1", C.c_float), ("rho", C.c_float), ("c2", C.c_float), ("linesearch", C.c_int),
-                ("record_timing", C.c_int)]
+                ("record_timing", C.c_int), ("shard_history", C.c_int)]
 
 
 class GdOpts(C.Structure):

@@ -392,6 +392,10 @@ class CudaLBFGS(CudaMinimizerBase):
     def setMemory(self, m):
         self.m_ = int(m)
 
+    def setShardHistory(self, mode):
+        """multi-GPU: 0 replicated, 1 sharded by parameter index, -1 auto (see include/b200_lbfgs.h)"""
+        self.shard_history_ = int(mode)
+
     def setLineSearchPolicy(self, policy, c2=0.9):
         """'armijo' = reference CUDA backend; 'wolfe' = reference CPU backend"""
         self.linesearch_, self.c2_ = policy, float(c2)
@@ -403,6 +407,7 @@ class CudaLBFGS(CudaMinimizerBase):
         o.max_line_iters, o.c1, o.rho, o.c2 = self.max_line_iters_, self.c1_, self.rho_, self.c2_
         o.linesearch = LS[self.linesearch_]
         o.record_timing = 1
+        o.shard_history = getattr(self, "shard_history_", -1)
         return o
 
     # resumable form (b200_lbfgs_create / run / destroy): the same minimisation continued in slices

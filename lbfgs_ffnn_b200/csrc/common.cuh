@@ -121,6 +121,8 @@ struct ProfScope {
 
 int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev); // grad (float) + 1 double
 int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n);
+int ctx_reduce_shards(b200_ctx *ctx, const float *full, float *shard_out, size_t n, size_t chunk);
+int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk);
 
 // ---- device helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h> // types only; the functions are resolved with dlopen (no link-time NCCL dependency)
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -34,6 +35,8 @@ struct NcclApi {
   ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                                 cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -60,6 +63,8 @@ NcclApi *nccl_api() {
     B200_SYM(AllReduce, "ncclAllReduce")
     B200_SYM(ReduceScatter, "ncclReduceScatter")
     B200_SYM(AllGather, "ncclAllGather")
+    B200_SYM(Reduce, "ncclReduce")
+    B200_SYM(Broadcast, "ncclBroadcast")
     B200_SYM(GroupStart, "ncclGroupStart")
     B200_SYM(GroupEnd, "ncclGroupEnd")
     B200_SYM(GetErrorString, "ncclGetErrorString")
@@ -91,6 +96,37 @@ int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev) {
   B200_NCCL(api, api->GroupStart());
   if (grad && n) B200_NCCL(api, api->AllReduce(grad, grad, n, ncclFloat, ncclSum, comm, ctx->stream));
   if (loss_dev) B200_NCCL(api, api->AllReduce(loss_dev, loss_dev, 1, ncclDouble, ncclSum, comm, ctx->stream));
+  B200_NCCL(api, api->GroupEnd());
+  return B200_OK;
+}
+
+// reduce-scatter with exact (possibly uneven) shards: rank i receives sum over ranks of full[i*chunk .. min(n, (i+1)*chunk))
+// in shard_out; one grouped launch of W ncclReduce calls
+int ctx_reduce_shards(b200_ctx *ctx, const float *full, float *shard_out, size_t n, size_t chunk) {
+  if (ctx->world <= 1) return B200_OK;
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  B200_NCCL(api, api->GroupStart());
+  for (int i = 0; i < ctx->world; ++i) {
+    const size_t lo = std::min(n, (size_t)i * chunk), len = std::min(chunk, n - lo);
+    if (len) B200_NCCL(api, api->Reduce(full + lo, shard_out, len, ncclFloat, ncclSum, i, comm, ctx->stream));
+  }
+  B200_NCCL(api, api->GroupEnd());
+  return B200_OK;
+}
+
+// all-gather with the same shard layout, in place on `full` (rank i is the root of its own shard)
+int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk) {
+  if (ctx->world <= 1) return B200_OK;
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  B200_NCCL(api, api->GroupStart());
+  for (int i = 0; i < ctx->world; ++i) {
+    const size_t lo = std::min(n, (size_t)i * chunk), len = std::min(chunk, n - lo);
+    if (len) B200_NCCL(api, api->Broadcast(full + lo, full + lo, len, ncclFloat, i, comm, ctx->stream));
+  }
   B200_NCCL(api, api->GroupEnd());
   return B200_OK;
 }

@@ -358,6 +358,21 @@ __global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
   }
 }
 
+// totals[c] = sum_b partials[b][c] in a fixed order (sharded history: the totals are then all-reduced over ranks)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nblocks, int ncols,
+                                                             double *__restrict__ totals) {
+  for (int c0 = blockIdx.x * 32; c0 < ncols; c0 += gridDim.x * 32) {
+    const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+    double s = 0.0;
+    if (c < ncols)
+      for (int b = sub; b < nblocks; b += 8) s += partials[(size_t)b * ncols + c];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (c < ncols && sub == 0) totals[c] = s;
+  }
+}
+
 __global__ void lbfgs_init_kernel(LbfgsView v, int m, int mod) {
   const int mp = m + 1;
   for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { v.SY[i] = 0.0; v.YY[i] = 0.0; }
@@ -470,6 +485,11 @@ int launch_lbfgs_solve(const SolveArgs &a, int mp, cudaStream_t st) {
 
 int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st) {
   B200_LAUNCH(lbfgs_apply_kernel, nblocks, 256, 0, st, a);
+  return B200_OK;
+}
+
+int launch_reduce_partials(const double *partials, int nblocks, int ncols, double *totals, cudaStream_t st) {
+  B200_LAUNCH(reduce_partials_kernel, std::max(1, std::min(8, (ncols + 31) / 32)), 256, 0, st, partials, nblocks, ncols, totals);
   return B200_OK;
 }
 

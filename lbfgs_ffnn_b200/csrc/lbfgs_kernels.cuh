@@ -127,6 +127,7 @@ int launch_lbfgs_solve(const SolveArgs &a, int mp, cudaStream_t st);
 int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st);
 int lbfgs_dots_blocks(b200_ctx *ctx, size_t n);
 int lbfgs_init_state(LbfgsView v, int m, int mod, cudaStream_t st);
+int launch_reduce_partials(const double *partials, int nblocks, int ncols, double *totals, cudaStream_t st);
 // ring push of an explicit pair (S-LBFGS curvature pairs): s, y device vectors copied into slot head
 int launch_lbfgs_store_pair(float *S, float *Y, size_t n, size_t ld, LbfgsView st, const float *s, const float *y,
                             cudaStream_t stream);

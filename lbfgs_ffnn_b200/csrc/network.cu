@@ -494,7 +494,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   fp.lam = net->l2 / (float)ctx->world; // each rank adds its share; the all-reduce sums them
   fp.grad = grad_out;
   fp.fin_part = net->fin_part;
-  const bool multi = ctx->world > 1;
+  const bool multi = ctx->world > 1 && !net->defer_reduce;
   {
     ProfScope ps(ctx, "finalize");
     B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);

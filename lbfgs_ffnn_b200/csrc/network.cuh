@@ -14,6 +14,7 @@ struct b200_net {
   int prec = B200_PREC_FP32;
   float l2 = 0.0f;
   long batch_global = 0; // 0: shard batch x world
+  bool defer_reduce = false; // multi-GPU: leave the gradient / loss as this rank's partial (the caller reduce-scatters)
 
   // flat parameter / gradient buffers (owned after bind_params)
   float *params = nullptr, *grads = nullptr;

@@ -104,7 +104,7 @@ void b200_lbfgs_default_opts(b200_lbfgs_opts *o) {
   if (!o) return;
   o->max_iters = 200; o->tol = 1e-6f; o->memory = 16; o->max_line_iters = 20; // minimizer_base.cuh:61-65, lbfgs.cuh:263
   o->c1 = 1e-4f; o->rho = 0.5f; o->c2 = 0.9f;
-  o->linesearch = B200_LS_ARMIJO; o->record_timing = 1;
+  o->linesearch = B200_LS_ARMIJO; o->record_timing = 1; o->shard_history = -1;
 }
 void b200_gd_default_opts(b200_gd_opts *o) {
   if (!o) return;
@@ -125,6 +125,11 @@ struct b200_lbfgs {
   b200_ctx *ctx = nullptr;
   b200_lbfgs_opts o{};
   size_t N = 0, ld = 0;
+  // sharded history (multi-GPU): this rank owns parameter indices [lo, lo + len); chunk = shard size of every rank but the last
+  bool sharded = false;
+  size_t lo = 0, len = 0, chunk = 0;
+  float *gfull = nullptr; // sharded: this rank's un-reduced full-length gradient
+  double *totals = nullptr;
   int m = 0, mp = 1, mod = 1, policy = POLICY_ARMIJO;
   int nblk = 1, apply_blocks = 1;
   char *ws = nullptr;
@@ -160,15 +165,21 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
   s->mod = wolfe ? s->m + 1 : std::max(s->m, 1);
   s->mp = s->m + 1;
   s->N = (size_t)n;
-  s->ld = (s->N + 3) & ~size_t(3);
+  s->sharded = ctx->world > 1 && !wolfe && (o.shard_history == 1 || (o.shard_history < 0 && s->N >= (size_t(4) << 20)));
+  s->chunk = s->sharded ? ((((s->N + ctx->world - 1) / ctx->world) + 3) & ~size_t(3)) : s->N;
+  s->lo = s->sharded ? std::min(s->N, (size_t)ctx->rank * s->chunk) : 0;
+  s->len = s->sharded ? std::min(s->chunk, s->N - s->lo) : s->N;
+  s->ld = (std::max<size_t>(s->len, 4) + 3) & ~size_t(3);
   // one allocation for all work vectors (the reference allocates 6 + 2m DeviceBuffers per solve, lbfgs.cuh:53-71)
-  s->nblk = lbfgs_dots_blocks(ctx, s->N);
+  s->nblk = lbfgs_dots_blocks(ctx, std::max<size_t>(s->len, 1));
   const int ncols = kDotsCols * s->mp + 1;
   const size_t state_bytes = lbfgs_state_bytes(s->m);
   const size_t part_bytes = sizeof(double) * (size_t)s->nblk * ncols;
   const size_t dotp_bytes = sizeof(double) * (size_t)dot_blocks(ctx, s->N);
   const size_t vec_bytes = sizeof(float) * s->ld;
-  const size_t total = state_bytes + part_bytes + dotp_bytes + 256 + vec_bytes * (4 + 2 * (size_t)s->mp);
+  const size_t gfull_bytes = s->sharded ? ((sizeof(float) * s->N + 255) & ~size_t(255)) : 0;
+  const size_t totals_bytes = (sizeof(double) * ncols + 255) & ~size_t(255);
+  const size_t total = state_bytes + part_bytes + dotp_bytes + 512 + vec_bytes * (4 + 2 * (size_t)s->mp) + gfull_bytes + totals_bytes;
   if (cudaMalloc(&s->ws, total) != cudaSuccess) {
     delete s;
     set_error("cudaMalloc of %zu bytes of L-BFGS work space failed", total);
@@ -185,7 +196,10 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
   s->p = (float *)(s->ws + off); off += vec_bytes;
   s->x_prev = (float *)(s->ws + off); off += vec_bytes;
   s->S = (float *)(s->ws + off); off += vec_bytes * s->mp;
-  s->Y = (float *)(s->ws + off);
+  s->Y = (float *)(s->ws + off); off += vec_bytes * s->mp;
+  off = (off + 255) & ~size_t(255);
+  s->totals = (double *)(s->ws + off); off += totals_bytes;
+  if (s->sharded) s->gfull = (float *)(s->ws + off);
   B200_TRY(lbfgs_init_state(s->view, s->m, s->mod, st));
   s->apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (s->ld / 4 + 255) / 256));
   *out = s;
@@ -210,10 +224,17 @@ int b200_lbfgs_destroy(b200_lbfgs *s) {
   return B200_OK;
 }
 
+static int lbfgs_run_sharded(b200_lbfgs *s, b200_net *net, float *params, const float *input, const float *target, int batch,
+                             int iters, b200_history *hist);
+
 int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *user, float *params, const float *input,
                    const float *target, int batch, int iters, b200_history *hist) {
   B200_REQUIRE(s && params, "null argument");
   if (hist) { hist->size = 0; hist->iterations = 0; hist->evaluations = 0; hist->launches = 0; }
+  if (s->sharded) {
+    B200_REQUIRE(net, "the sharded-history mode needs the library's network objective");
+    return lbfgs_run_sharded(s, net, params, input, target, batch, iters, hist);
+  }
   B200_REQUIRE(net || fn, "either a network or a loss_grad callback is required");
   B200_REQUIRE(!net || s->N == net->n, "n does not match the network's parameter count");
   b200_ctx *ctx = s->ctx;
@@ -411,6 +432,125 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   if (hist) {
     hist->iterations = iterations_done;
     hist->evaluations = obj.evals;
+    hist->launches = b200_launch_count() - launches0;
+  }
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sharded-history L-BFGS (multi-GPU, large n — BASELINE configs[4]): rank r owns the parameter slice
+// [lo, lo+len) of x, g, p and of every history vector. Per evaluation: local full-length gradient ->
+// reduce-scatter to the owners; per direction: ONE all-reduce of the 5(m+1)+1 partial dot products;
+// per trial point: all-gather of the parameters. Same control flow as the replicated Armijo path.
+// ---------------------------------------------------------------------------------------------------
+static int lbfgs_run_sharded(b200_lbfgs *s, b200_net *net, float *params, const float *input, const float *target, int batch,
+                             int iters, b200_history *hist) {
+  b200_ctx *ctx = s->ctx;
+  const b200_lbfgs_opts &o = s->o;
+  B200_REQUIRE(s->N == net->n, "n does not match the network's parameter count");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long launches0 = b200_launch_count();
+  const size_t N = s->N, len = s->len, lo = s->lo, ld = s->ld;
+  const int m = s->m, mp = s->mp, ncols = kDotsCols * mp + 1;
+  float *x = params + lo; // this rank's slice of the caller's parameter buffer
+  HostMail *mail = (HostMail *)ctx->h_scalars;
+  Timer timer{ctx, hist != nullptr && o.record_timing != 0};
+  long evals = 0;
+  if (net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch));
+  struct Defer { b200_net *n; ~Defer() { n->defer_reduce = false; } } defer{net};
+  net->defer_reduce = true;
+
+  // evaluation at the (replicated) full parameter vector; the owner's gradient slice lands in g_shard
+  auto eval = [&](float *g_shard) -> int {
+    ++evals;
+    EvalOut *eo = (EvalOut *)net->eval_out;
+    B200_TRY(net_eval(net, params, input, target, batch, 0, s->gfull, eo)); // partial loss, un-reduced gradient
+    {
+      ProfScope ps(ctx, "reduce_scatter");
+      B200_TRY(ctx_reduce_shards(ctx, s->gfull, g_shard, N, s->chunk));
+    }
+    B200_TRY(launch_dot(ctx, g_shard, g_shard, len, s->dot_part, &eo->gnorm2)); // ||g_shard||^2 next to the partial loss
+    B200_TRY(ctx_allreduce_f64(ctx, (double *)eo, 2));
+    B200_CUDA(cudaMemcpyAsync(&mail->loss, eo, sizeof(EvalOut), cudaMemcpyDeviceToHost, st));
+    return B200_OK;
+  };
+
+  if (!s->started) {
+    B200_TRY(eval(s->gbuf[0]));
+    B200_CUDA(cudaStreamSynchronize(st));
+    s->loss = mail->loss;
+    s->gnorm = std::sqrt(mail->gnorm2);
+    s->started = true;
+    s->cur = 0; s->iter = 0; s->reset_next = 0;
+  }
+  int iterations_done = 0;
+  for (int it = 0; it < iters; ++it) {
+    const int iter = s->iter;
+    B200_TRY(timer.start());
+    if (s->gnorm < (double)o.tol) break;
+    float *g = s->gbuf[s->cur], *g_new = s->gbuf[s->cur ^ 1];
+    const double loss = s->loss;
+    const int mode = (iter > 0 && m > 0) ? DOTS_FORM_PAIR : DOTS_NONE;
+    {
+      ProfScope ps(ctx, "lbfgs_dots");
+      DotsArgs da{s->S, s->Y, len, ld, s->view, g, x, s->x_prev, g_new, mode, s->reset_next, 0, s->partials};
+      B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
+      B200_TRY(launch_reduce_partials(s->partials, s->nblk, ncols, s->totals, st));
+    }
+    {
+      ProfScope ps(ctx, "dots_allreduce");
+      B200_TRY(ctx_allreduce_f64(ctx, s->totals, (size_t)ncols)); // the only exchange of the direction: 5(m+1)+1 doubles
+    }
+    {
+      ProfScope ps(ctx, "lbfgs_solve");
+      SolveArgs sa{s->view, s->totals, 1, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
+      B200_TRY(launch_lbfgs_solve(sa, mp, st));
+    }
+    {
+      ProfScope ps(ctx, "lbfgs_apply");
+      ApplyArgs aa{s->S, s->Y, len, ld, s->view, g, s->p, x, s->x_prev, 1.0, 0.0f, nullptr};
+      B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
+    }
+    B200_CUDA(cudaMemcpyAsync(&mail->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+    s->reset_next = 0;
+
+    double loss_new = 0.0, gnorm2_new = 0.0, alpha = 1.0, gdotp = 0.0;
+    bool armijo_ok = false;
+    const int max_ls = std::max(1, o.max_line_iters);
+    for (int ls = 0; ls < max_ls; ++ls) {
+      if (ls > 0) B200_TRY(launch_trial_point(len, s->x_prev, (float)alpha, s->p, x, st));
+      {
+        ProfScope ps(ctx, "allgather");
+        B200_TRY(ctx_allgather_shards(ctx, params, N, s->chunk));
+      }
+      B200_TRY(eval(g_new));
+      B200_CUDA(cudaStreamSynchronize(st));
+      if (ls == 0) { alpha = (double)(float)mail->hdr.alpha0; gdotp = mail->hdr.gdotp; }
+      loss_new = mail->loss;
+      gnorm2_new = mail->gnorm2;
+      if (loss_new <= loss + (double)o.c1 * alpha * gdotp) { armijo_ok = true; break; }
+      const double denom = 2.0 * (loss_new - loss - gdotp * alpha);
+      bool fallback = true;
+      if (std::fabs(denom) > 1e-20) {
+        const double na = -(gdotp * alpha * alpha) / denom;
+        if (na >= 0.1 * alpha && na <= 0.9 * alpha) { alpha = na; fallback = false; }
+      }
+      if (fallback) alpha *= (double)o.rho;
+    }
+    if (!armijo_ok) s->reset_next = 1;
+    s->cur ^= 1;
+    s->loss = loss_new;
+    s->gnorm = std::sqrt(gnorm2_new);
+    s->iter = iter + 1;
+    B200_TRY(timer.stop());
+    record(hist, iterations_done, s->loss, s->gnorm, timer.elapsed);
+    ++iterations_done;
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (hist) {
+    hist->iterations = iterations_done;
+    hist->evaluations = evals;
     hist->launches = b200_launch_count() - launches0;
   }
   return B200_OK;

@@ -32,3 +32,7 @@ def test_two_rank_lbfgs_matches_single():
     assert r["max_rel_loss_diff_first5"] <= 2e-5, r
     assert r["max_rel_loss_diff"] <= 3e-3, r
     assert r["params_rel_l2"] <= 5e-3, r
+    # history sharded by parameter index (reduce-scatter + all-reduce of the 5(m+1)+1 partial dots + all-gather)
+    assert r["sharded_max_rel_loss_diff_first5"] <= 2e-5, r
+    assert r["sharded_max_rel_loss_diff"] <= 3e-3, r
+    assert r["sharded_params_rel_l2"] <= 5e-3, r

@@ -142,3 +142,14 @@ def test_sgd_tensorcore_subranges(handle, oracle):
     loss, _, _ = rec.copy_to_host()
     assert np.allclose(loss, ref["loss"], rtol=3e-4)
     assert rel_l2(net.get_params(), ref["params"]) <= 3e-4
+
+
+@pytest.mark.parametrize("prec", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("dims,acts,batch", [([784, 512, 256, 10], ["relu", "tanh", "linear"], 777),
+                                             ([784, 1024, 1024, 10], ["relu", "relu", "linear"], 1500),
+                                             ([256, 384, 96, 32, 8], ["sigmoid", "relu", "relu", "linear"], 300)])
+def test_tc_multi_tile_shapes(handle, oracle, dims, acts, batch, prec):
+    """hidden widths above one 128-wide tile: several N tiles in FWD/DX, several M tiles and N tiles in DW
+    (the shape class of BASELINE configs[4], 784-4096-4096-10, at test size)"""
+    el, eg, eo = _check(handle, oracle, dims, acts, batch, prec)
+    assert el <= TOL[prec] and eg <= TOL[prec] and eo <= TOL[prec], (el, eg, eo)
