@@ -459,6 +459,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // ===== epilogue: all 8 warps. Warps w and w+4 own TMEM lanes (= D rows) 32*(w%4).., and split the 32-column
   // chunks of the accumulator between them (even chunks: warps 0-3, odd chunks: warps 4-7) ===================
   __syncthreads(); // roles done issuing; wl staged
+  // fused last layer: fetch this row's targets now; the ~4 us loaded HBM latency hides behind the rest of the main loop
+  float tgt[kLastCols];
+#pragma unroll
+  for (int j = 0; j < kLastCols; ++j) tgt[j] = 0.0f;
+  if (fuse) {
+    const long trow = (long)m0 + (warp & 3) * 32 + lane;
+    if (trow < p.rows_valid) {
+#pragma unroll
+      for (int j = 0; j < kLastCols; ++j)
+        if (j < p.last_out) tgt[j] = __ldg(p.targets + trow * p.last_out + j);
+    }
+  }
   if (nkb > 0) {
     mbar_wait(bar_accum, 0);
     tc_fence_after();
@@ -569,6 +581,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    const long long t_p1 = p.dbg ? clock64() : 0;
+    if (p.dbg && threadIdx.x == 0 && blockIdx.x < 1024) p.dbg[8192 + 4 * blockIdx.x + 0] = t_p1 - t_acc;
     if (fuse) {
       // last layer forward, loss, delta_L (src/cuda/network.cuh:100-107) and delta_{L-1} (layer.cuh:89-103 +
       // kernels.cuh:109-133) for this thread's sample. The two warps of a row exchange their half sums of z.
@@ -586,7 +600,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (j < OL && row_ok) {
           const float zz = (half == 0) ? (z[j] + zo[j]) : (zo[j] + z[j]); // same operand order in both warps
           const float o = act_apply(p.last_act, zz + brow[j]);
-          const float d = o - __ldg(p.targets + grow * OL + j);
+          const float d = o - tgt[j];
           dl[j] = d * p.inv_batch * act_deriv_from_output(p.last_act, o);
           if (half == 0) {
             p.out_last[grow * OL + j] = o;
@@ -599,6 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         lsum = warp_sum(lsum);
         if (lane == 0) p.loss_part[blockIdx.x * 4 + (warp & 3)] = lsum;
       }
+      if (p.dbg && threadIdx.x == 0 && blockIdx.x < 1024) p.dbg[8192 + 4 * blockIdx.x + 1] = clock64() - t_p1;
       for (int c0 = half * 32; c0 < umma_n; c0 += 64) {
         uint32_t v[32];
         if (ACT != B200_ACT_RELU) { // generic activations need the activation value again for act'(a)
@@ -738,22 +753,25 @@ int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &t
   static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
   TcParams pp = p;
   if (timing) {
-    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 2 * 4096));
-    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 2 * 4096, st));
+    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 4 * 4096));
+    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 4 * 4096, st));
     pp.dbg = dbg;
   }
   kern<<<grid, kTcThreads, smem, st>>>(ta, tb, tblo, pp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) { // debugging aid: average main-loop and epilogue duration per CTA, in SM clocks
-    std::vector<long long> h(2 * 4096);
+    std::vector<long long> h(4 * 4096);
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     const size_t n = std::min<size_t>(4096, (size_t)grid.x * grid.y * grid.z);
     double m = 0, e = 0;
     for (size_t i = 0; i < n; ++i) { m += h[2 * i]; e += h[2 * i + 1]; }
-    fprintf(stderr, "[tc timing] role %d BN %d x3 %d u8 %d grid %ux%ux%u: main loop %.0f clk, epilogue %.0f clk per CTA\n", ROLE, BN,
-            (int)X3, U8, grid.x, grid.y, grid.z, m / n, e / n);
+    double p1 = 0, mid = 0;
+    const size_t n2 = std::min<size_t>(1024, n);
+    for (size_t i = 0; i < n2; ++i) { p1 += h[8192 + 4 * i]; mid += h[8192 + 4 * i + 1]; }
+    fprintf(stderr, "[tc timing] role %d BN %d x3 %d u8 %d grid %ux%ux%u: main loop %.0f clk, epilogue %.0f clk per CTA (pass1 %.0f, last layer %.0f)\n",
+            ROLE, BN, (int)X3, U8, grid.x, grid.y, grid.z, m / n, e / n, p1 / n2, mid / n2);
   }
   return B200_OK;
 }
