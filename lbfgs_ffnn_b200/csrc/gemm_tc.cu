@@ -893,11 +893,20 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
 }
 
 // [dW_l ; db_l] split-K partials = [A_{l-1} | 1]^T delta_l
+// N tile of the dW kernel: 256 columns (fewer re-reads of delta) except in 3xTF32, where a 256-wide stage is 72-96 KB and
+// only two fit — the TMA -> split/convert -> MMA chain then runs latency-bound; 128-wide stages pipeline three deep
+static int tc_dw_bn(const b200_net *net) {
+  const char *e = std::getenv("B200_DW_BN");
+  if (e) return std::atoi(e) == 128 ? 128 : 256;
+  return net->prec == B200_PREC_TF32X3 ? 128 : 256;
+}
+
 int tc_dw_plan(b200_net *net, int l, long batch, int *splits) {
   const int Kin = net->dims[l], Nout = net->dims[l + 1];
-  const int tiles = ceil_div(Nout, BM) * ceil_div(Kin, 256);
+  const int tiles = ceil_div(Nout, BM) * ceil_div(Kin, tc_dw_bn(net));
   const int kblocks = ceil_div(batch, BK);
-  int s = std::max(1, std::min(ceil_div(net->ctx->num_sms, tiles), kblocks));
+  // one CTA per SM (the stages take most of the shared memory): never more CTAs than SMs, or a second wave doubles the time
+  int s = std::max(1, std::min(net->ctx->num_sms / tiles, kblocks));
   const int per = ceil_div(kblocks, s);
   *splits = ceil_div(kblocks, per);
   return per;
@@ -923,9 +932,15 @@ int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
   p.partial = net->partials + net->part_off[l];
   p.partial_stride = (unsigned long long)(Kin + 1) * Nout;
   p.out_dim = Nout; p.in_dim = Kin;
-  const dim3 grid(ceil_div(Nout, BM), ceil_div(Kin, 256), splits);
-  if (xq) B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256, 2>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
-  else B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
+  const int bn = tc_dw_bn(net);
+  const dim3 grid(ceil_div(Nout, BM), ceil_div(Kin, bn), splits);
+  if (bn == 128) {
+    if (xq) B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 128, 2>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
+    else B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 128>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
+  } else {
+    if (xq) B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256, 2>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
+    else B200_TRY((launch_tc_prec<MAJOR_MN, MAJOR_MN, TC_DW, 256>(x3, ta, tb, tb, p, grid, net->ctx->stream)));
+  }
   net->splits_used[l] = splits; // finalize_grad_kernel combines exactly the splits this launch wrote
   *done = true;
   return B200_OK;
