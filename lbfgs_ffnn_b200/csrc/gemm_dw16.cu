@@ -1,0 +1,383 @@
+// [dW_0 ; db_0] split-K partials of layer 0 on the fp16 tensor cores, for an input that is exactly u/255 (uint8-resident X).
+//
+// Replaces CudaDenseLayer::backward's dW SGEMM (K = batch) and the serial sum_rows_kernel (src/cuda/layer.cuh:81-86,
+// src/cuda/kernels.cuh:144-153) for the first layer:
+//     D[f][o] = sum_s X[s][f] * delta[s][o]          f = input feature (M, tiles of 128), o = output neuron, s = sample (K)
+// Operands: A = X^T, converted uint8 -> fp16 (exact) by four warps straight into the UMMA MN-major SWIZZLE_128B layout;
+// B = [delta_hi | delta_lo], the scaled fp16 split of delta written by tail_bwd_kernel (22 mantissa bits), loaded by TMA in
+// MN-major layout. One kind::f16 MMA of N = 2 * out per 16 samples yields D = [hi | lo] in adjacent TMEM columns; the
+// epilogue adds them and undoes the scales (1/255 of X, 1/S of delta). The bias gradient is the row f = in of the same
+// product: the converter plants a row of ones there (sum_s 1 * delta[s][o]), exactly the [W | b] layout of the flat gradient.
+// tcgen05.mma issues at one instruction per ~140-160 clk regardless of N (tools/probe/mma_probe.cu), so the N = 256,
+// K = 16 shape is what makes this 4x faster than the TF32 N = 128, K = 8 kernel it replaces.
+#include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+namespace b200 {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int kDM = 128;                  // input features per M tile = UMMA M
+constexpr int kDMT = 2;                   // M tiles per CTA: every delta tile read from L2 feeds two MMAs (the L2 -> SM path,
+                                          // ~43 B/clk per SM, is what bounds a one-tile CTA), accumulators fill the 512 TMEM columns
+constexpr int kDK = 32;                   // samples per stage
+constexpr int kDRawTile = kDK * kDM;      // uint8 [32 samples][128 features]
+constexpr int kDRawBytes = kDMT * kDRawTile;
+constexpr int kDConvTile = kDK * kDM * 2; // fp16: two feature atoms of [32 K-rows][128 B]
+constexpr int kDConvBytes = kDMT * kDConvTile;
+constexpr int kDAtom = kDK * 128;         // one MN atom column of a stage: [32 K-rows][64 elements]
+constexpr int kDNR = 8, kDNS = 4;         // raw ring; converted-A and B rings share one stage index (one commit frees both)
+constexpr int kDThreads = 384;            // warp 0 raw TMA, 1 MMA issue, 2 TMEM alloc, 3 delta TMA, 4-11 converters (4-7 then run the epilogue)
+constexpr int kDConvThreads = 256;
+
+struct Dw16Params {
+  int in_dim, out_dim;    // layer 0: in (784), out (<= 128)
+  int k_blocks, kb_per_split;
+  float *partial;         // [split][(in+1)*out]
+  unsigned long long partial_stride;
+  const float *scale_inv; // device scalar 1 / S of the fp16 delta
+  long long *dbg;
+};
+
+template <int NB> struct DPlan { // NB = 2 * out rounded up to 128 / 256: width of [delta_hi | delta_lo]
+  static constexpr int kBStage = NB * kDK * 2;
+  static constexpr int kOffConv = 0;
+  static constexpr int kOffB = kDNS * kDConvBytes;
+  static constexpr int kOffRaw = kOffB + kDNS * kBStage;
+  static constexpr int kOffBar = kOffRaw + kDNR * kDRawBytes;
+  static constexpr int kTotal = kOffBar + 256 + 1024;
+};
+
+__device__ __forceinline__ void umma_f16_d(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// fp32 accumulate, fp16 x fp16, both operands MN-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kDM >> 4) << 24);
+}
+// MN-major SWIZZLE_128B, 16-bit: atoms of [8 K-rows][64 MN elements] (1024 B); next 8-row K group at SBO = 1024 B, next MN atom
+// (64 elements further along M / N) at LBO = one [32 K-rows][128 B] box = 4096 B
+__device__ __forceinline__ uint64_t desc_mn16(uint32_t saddr) { return make_desc(saddr, kDAtom, 1024, 2); }
+
+__device__ __forceinline__ void u8x4_to_h4_d(uint32_t w, uint32_t &lo, uint32_t &hi) {
+  const uint32_t a = __byte_perm(w, 0x64646464u, 0x5140), b = __byte_perm(w, 0x64646464u, 0x7362);
+  const __half2 k = __halves2half2(__ushort_as_half((unsigned short)0x6400), __ushort_as_half((unsigned short)0x6400));
+  const __half2 ra = __hsub2(*reinterpret_cast<const __half2 *>(&a), k), rb = __hsub2(*reinterpret_cast<const __half2 *>(&b), k);
+  lo = *reinterpret_cast<const uint32_t *>(&ra);
+  hi = *reinterpret_cast<const uint32_t *>(&rb);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kDThreads, 1)
+dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const Dw16Params p) {
+  using Plan = DPlan<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
+  auto conv_a = [&](int s) { return base + Plan::kOffConv + s * kDConvBytes; };
+  auto b_a = [&](int s) { return base + Plan::kOffB + s * Plan::kBStage; };
+  auto raw_a = [&](int s) { return base + Plan::kOffRaw + s * kDRawBytes; };
+  const uint32_t bars = base + Plan::kOffBar;
+  auto raw_full = [&](int s) { return bars + 8 * s; };
+  auto raw_empty = [&](int s) { return bars + 8 * (kDNR + s); };
+  auto conv_full = [&](int s) { return bars + 8 * (2 * kDNR + s); };
+  auto b_full = [&](int s) { return bars + 8 * (2 * kDNR + kDNS + s); };
+  auto st_empty = [&](int s) { return bars + 8 * (2 * kDNR + 2 * kDNS + s); }; // MMAs of the stage done: A and B tiles reusable
+  const uint32_t acc_full = bars + 8 * (2 * kDNR + 3 * kDNS);
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kDNR + 3 * kDNS + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = p.dbg ? clock64() : 0;
+  const int m0 = blockIdx.x * (kDMT * kDM);
+  const int nmt = min(kDMT, (p.in_dim + 1 - m0 + kDM - 1) / kDM); // M tiles of this CTA that hold features (the last group may hold one)
+  const int kb_begin = blockIdx.y * p.kb_per_split, kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < kDNR; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), kDConvThreads / 64); }
+    for (int s = 0; s < kDNS; ++s) { mbar_init(conv_full(s), kDConvThreads / 64); mbar_init(b_full(s), 1); mbar_init(st_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                 "r"((uint32_t)(kDMT * NB))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) { // ===== raw uint8 producer: box {128 features, 64 samples} ===================================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(raw_empty(s), ph ^ 1);
+        mbar_expect_tx(raw_full(s), nmt * kDRawTile);
+        for (int t = 0; t < nmt; ++t) tma_load_2d(raw_a(s) + t * kDRawTile, &tmX, raw_full(s), m0 + t * kDM, kb * kDK);
+        if (++s == kDNR) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    if (lane == 0) { // ===== delta producer: NB / 64 boxes {64 halves, 64 samples}, MN-major SWIZZLE_128B ==========
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(st_empty(s), ph ^ 1);
+        mbar_expect_tx(b_full(s), Plan::kBStage);
+#pragma unroll
+        for (int j = 0; j < NB / 64; ++j) tma_load_2d(b_a(s) + j * kDAtom, &tmD, b_full(s), 64 * j, kb * kDK);
+        if (++s == kDNS) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) { // ===== MMA issuer ======================================================================
+      const uint32_t idesc = make_idesc_f16_mn(NB);
+      const uint64_t dA0 = desc_mn16(conv_a(0)), dB0 = desc_mn16(b_a(0));
+      int s = 0;
+      uint32_t ph = 0;
+      long long waited = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const long long t0 = p.dbg ? clock64() : 0;
+        mbar_wait(conv_full(s), ph);
+        mbar_wait(b_full(s), ph);
+        if (p.dbg) waited += clock64() - t0;
+        tc_fence_after();
+        const uint64_t da = dA0 + (uint64_t)(s * (kDConvBytes >> 4)), db = dB0 + (uint64_t)(s * (Plan::kBStage >> 4));
+#pragma unroll
+        for (int t = 0; t < kDMT; ++t) {
+          if (t < nmt) {
+#pragma unroll
+            for (int ks = 0; ks < kDK / 16; ++ks) // 16 samples = two 8-row K groups = 2048 B further into every atom
+              umma_f16_d(tmem_base + t * NB, da + t * (kDConvTile >> 4) + 128 * ks, db + 128 * ks, idesc,
+                         (kb > kb_begin || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(st_empty(s));
+        if (++s == kDNS) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_full);
+      if (p.dbg) p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = waited;
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===== converters: raw [64 samples][128 B] -> fp16 MN-major: feature atom j = f / 64 at j * 8192, sample row r at r * 128,
+    // 16-byte chunk c (8 features) at (c ^ (r & 7)) * 16. Eight consecutive lanes take one sample's 128 bytes.
+    // Two groups of four warps take alternate K blocks (two wait -> convert -> proxy fence -> arrive chains in flight).
+    const int tt = threadIdx.x - 128, grp = tt >> 7, t = tt & 127, q = t & 7, rb = t >> 3; // rb = sample rows rb, rb + 16
+    int n = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb, ++n) {
+      if ((n & 1) != grp) continue;
+      const int rs = n % kDNR, cs = n % kDNS;
+      const uint32_t rph = (uint32_t)(n / kDNR) & 1u, cph = (uint32_t)(n / kDNS) & 1u;
+      mbar_wait(raw_full(rs), rph);
+      mbar_wait(st_empty(cs), cph ^ 1);
+      const uint8_t *raw = bp + Plan::kOffRaw + rs * kDRawBytes;
+      uint8_t *conv = bp + Plan::kOffConv + cs * kDConvBytes;
+      uint4 w[2 * kDMT];
+#pragma unroll
+      for (int i = 0; i < 2 * kDMT; ++i)
+        if ((i >> 1) < nmt) w[i] = *reinterpret_cast<const uint4 *>(raw + (i >> 1) * kDRawTile + (rb + 16 * (i & 1)) * kDM + q * 16);
+#pragma unroll
+      for (int i = 0; i < 2 * kDMT; ++i) {
+        if ((i >> 1) < nmt) {
+          const int r = rb + 16 * (i & 1);
+          uint32_t o[8];
+          u8x4_to_h4_d(w[i].x, o[0], o[1]);
+          u8x4_to_h4_d(w[i].y, o[2], o[3]);
+          u8x4_to_h4_d(w[i].z, o[4], o[5]);
+          u8x4_to_h4_d(w[i].w, o[6], o[7]);
+          const int fl = p.in_dim - (m0 + (i >> 1) * kDM); // local row of the bias (ones) feature, if it falls into this tile
+          if (fl >= 0 && fl < kDM && (fl >> 4) == q) { // feature `in` reads as 1 for every sample: D row `in` = sum_s delta[s][:]
+            const int e = fl & 15;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k == (e >> 1)) o[k] = (e & 1) ? ((o[k] & 0x0000FFFFu) | 0x3C000000u) : ((o[k] & 0xFFFF0000u) | 0x00003C00u);
+          }
+          uint8_t *dst = conv + (i >> 1) * kDConvTile + (q >> 2) * kDAtom;
+          const int c0 = 2 * (q & 3);
+          *reinterpret_cast<uint4 *>(dst + r * 128 + ((c0 ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4 *>(dst + r * 128 + (((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { // one arrival per warp
+        mbar_arrive(conv_full(cs));
+        mbar_arrive(raw_empty(rs));
+      }
+    }
+    // ===== epilogue (same warps: warp w owns TMEM lanes 32 * (w % 4) ..): partial[split][f * out + o] = (hi + lo) * scale ====
+    const int OUT = p.out_dim;
+    if (warp < 8) {
+    if (nkb > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const float sinv = __ldg(p.scale_inv);
+    for (int t2 = 0; t2 < nmt; ++t2) {
+      const int row = (warp & 3) * 32 + lane, f = m0 + t2 * kDM + row;
+      const float scale = (f < p.in_dim) ? sinv * (1.0f / 255.0f) : sinv;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t2 * NB);
+      float *dstrow = p.partial + (unsigned long long)blockIdx.y * p.partial_stride + (unsigned long long)f * OUT;
+      for (int c0 = 0; c0 < OUT; c0 += 32) {
+        uint32_t v[32], w[32];
+        if (nkb > 0) {
+          tmem_ld32(lane_addr + c0, v);
+          tmem_ld32(lane_addr + NB / 2 + c0, w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = 0u; w[j] = 0u; }
+        }
+        if (f <= p.in_dim) {
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) {
+            float4 r;
+            r.x = (__uint_as_float(v[4 * qq + 0]) + __uint_as_float(w[4 * qq + 0])) * scale;
+            r.y = (__uint_as_float(v[4 * qq + 1]) + __uint_as_float(w[4 * qq + 1])) * scale;
+            r.z = (__uint_as_float(v[4 * qq + 2]) + __uint_as_float(w[4 * qq + 2])) * scale;
+            r.w = (__uint_as_float(v[4 * qq + 3]) + __uint_as_float(w[4 * qq + 3])) * scale;
+            if (c0 + 4 * qq + 3 < OUT) *reinterpret_cast<float4 *>(dstrow + c0 + 4 * qq) = r;
+          }
+        }
+      }
+    }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x)] = clock64() - t_start;
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kDMT * NB)) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_2d_d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsigned long long dim0, unsigned long long dim1,
+                  unsigned long long stride_bytes, unsigned box0, unsigned box1, CUtensorMapSwizzle sw) {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {stride_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu stride %llu box %u x %u ptr %p", (int)r, dim0, dim1,
+              stride_bytes, box0, box1, ptr);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+template <int NB> int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const Dw16Params &p, dim3 grid, cudaStream_t st) {
+  auto kern = dw16_kernel<NB>;
+  constexpr int smem = DPlan<NB>::kTotal;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  static long long *dbg = nullptr;
+  static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
+  Dw16Params pp = p;
+  if (timing) {
+    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 4 * 1024));
+    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 4 * 1024, st));
+    pp.dbg = dbg;
+  }
+  kern<<<grid, kDThreads, smem, st>>>(tx, td, pp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  B200_CUDA(cudaGetLastError());
+  if (timing) {
+    std::vector<long long> h(4 * 1024);
+    B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    const int n = std::min(1024, (int)(grid.x * grid.y));
+    double tot = 0, iw = 0;
+    for (int i = 0; i < n; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; }
+    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting %.0f\n", NB, grid.x, grid.y,
+            p.kb_per_split, tot / n, iw / n);
+  }
+  return B200_OK;
+}
+
+} // namespace
+
+bool dw16_applicable(const b200_net *net) {
+  const char *env = std::getenv("B200_DW16"); // debugging aid, read per call: 0 = generic tcgen05 kernel
+  if (env && std::atoi(env) == 0) return false;
+  const int K0 = net->dims[0], N0 = net->dims[1];
+  return net->nlayers() == 2 && net->prec != B200_PREC_FP32 && K0 % 16 == 0 && (N0 == 64 || N0 == 128) && tail_applicable(net);
+}
+
+// split plan: one CTA per (feature tile, split); never more CTAs than SMs
+int dw16_plan(const b200_net *net, long batch, int *splits) {
+  const int tiles = ceil_div(net->dims[0] + 1, kDMT * kDM);
+  const int kblocks = ceil_div(batch, kDK);
+  const int s = std::max(1, std::min(net->ctx->num_sms / tiles, kblocks));
+  const int per = ceil_div(kblocks, s);
+  *splits = ceil_div(kblocks, per);
+  return per;
+}
+
+// layer 0 [dW; db] partials from the uint8 input copy and the fp16 {hi | lo} delta written by tail_layer(want16)
+int dw16_layer(b200_net *net, const uint8_t *xq, long batch, bool *done) {
+  *done = false;
+  if (!xq || !net->delta16) return B200_OK;
+  const int K0 = net->dims[0], N0 = net->dims[1];
+  CUtensorMap tx, td;
+  B200_TRY(make_map_2d_d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K0, batch, K0, kDM, kDK, CU_TENSOR_MAP_SWIZZLE_NONE));
+  B200_TRY(make_map_2d_d(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->delta16, 2 * N0, batch, (unsigned long long)2 * N0 * 2, 64, kDK,
+                         CU_TENSOR_MAP_SWIZZLE_128B));
+  int splits = 1;
+  const int per = dw16_plan(net, batch, &splits);
+  Dw16Params p{};
+  p.in_dim = K0; p.out_dim = N0;
+  p.k_blocks = ceil_div(batch, kDK); p.kb_per_split = per;
+  p.partial = net->partials + net->part_off[0];
+  p.partial_stride = (unsigned long long)(K0 + 1) * N0;
+  p.scale_inv = net->scale16_inv;
+  const dim3 grid(ceil_div(K0 + 1, kDMT * kDM), splits);
+  if (N0 == 128) B200_TRY(launch_dw16<256>(tx, td, p, grid, net->ctx->stream));
+  else B200_TRY(launch_dw16<128>(tx, td, p, grid, net->ctx->stream));
+  net->splits_used[0] = splits;
+  *done = true;
+  return B200_OK;
+}
+
+} // namespace b200

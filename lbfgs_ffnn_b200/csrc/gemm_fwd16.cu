@@ -1,0 +1,518 @@
+// Persistent forward kernel of layer 0 for an input that is exactly u/255 (uint8-resident X), fp16 tensor-core operands.
+//
+// Replaces, for the first dense layer, CudaDenseLayer::forward (src/cuda/layer.cuh:48-58: SGEMM + add_bias_kernel +
+// activation_kernel).
+//
+// Why fp16: u in [0, 255] is exact in fp16, so X needs no hi/lo split; each weight is split ONCE per evaluation into
+// hi = fp16(s_o * w), lo = fp16(s_o * w - hi) with a per-output-neuron power-of-two scale s_o (split_w16_kernel), i.e. 22
+// mantissa bits, and the accumulator is rescaled by 1/(255 s_o) in the epilogue. Two kind::f16 MMAs per K step give
+// fp32-level products at the fp16 rate (4x the 3xTF32 rate) with half the shared memory per K element.
+//
+// Structure (one CTA per SM, 512 threads, tiles of 128 samples taken round-robin):
+//   warp 0      TMA producer of the raw uint8 ring   (kNR stages x [128 rows][64 B], straight from HBM)
+//   warp 3      TMA producer of the weight ring      (kNW stages x {hi, lo} [BN rows][64 fp16], L2-resident)
+//   warps 12-15 converters: raw uint8 -> fp16 in the UMMA K-major SWIZZLE_128B layout (kNC stages)
+//   warp 1      tcgen05.mma.kind::f16 issuer; accumulators {hi, lo} DOUBLE-BUFFERED in TMEM (2 x 2 x BN columns)
+//   warps 4-11  epilogue of tile i while the main loop of tile i+1 runs
+// The rings are decoupled on purpose: the old single ring made TMA -> convert -> MMA one latency chain per stage.
+#include "gemm_tc.cuh"
+#include "tc_epilogue.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+namespace b200 {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int kFM = 128;                   // samples per tile = UMMA M
+constexpr int kFK = 64;                    // K elements per stage (64 uint8 -> 64 fp16 = one 128-byte swizzle row)
+constexpr int kRawBytes = kFM * kFK;       // 8 KB
+constexpr int kConvBytes = kFM * kFK * 2;  // 16 KB
+constexpr int kNR = 4, kNC = 4, kNW = 4; // converted-X and weight rings share one stage index, so ONE tcgen05.commit frees both
+constexpr int kFThreads = 640;
+constexpr int kEpiWarp0 = 4, kEpiThreads = 256, kConvWarp0 = 12, kConvThreads = 256; // 8 converter warps: 4 were the bottleneck
+
+struct F16Params {
+  int rows_valid, cols_valid, k_total, k_blocks, tiles;
+  int act;
+  const float *bias;     // [N]
+  const float *colscale; // [N]: 1 / (255 s_o)
+  float *out;            // activations [rows][ld_out]
+  long ld_out;
+  long long *dbg;        // B200_TC_TIMING: per CTA {total, epilogue busy, epilogue waiting for the accumulator, issuer waiting}
+};
+
+static_assert(kNC == kNW, "the converted-X and weight rings share their empty barriers");
+template <int BN, bool X2> struct FPlan {
+  static constexpr int kWStage = BN * 128 * (X2 ? 2 : 1);
+  static constexpr int kOffConv = 0;
+  static constexpr int kOffW = kNC * kConvBytes;
+  static constexpr int kOffRaw = kOffW + kNW * kWStage;
+  static constexpr int kOffCol = kOffRaw + kNR * kRawBytes; // colscale[128], bias[128]
+  static constexpr int kOffBar = kOffCol + 1024;
+  static constexpr int kTotal = kOffBar + 256 + 1024;
+  static constexpr int kTmemCols = (4 * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// fp32 accumulate, fp16 x fp16, both operands K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 4 uint8 -> 4 fp16, exact: bytes are planted in the mantissa of 1024.0h (0x6400, ulp 1) and 1024 is subtracted
+__device__ __forceinline__ void u8x4_to_h4(uint32_t w, uint32_t &lo, uint32_t &hi) {
+  const uint32_t a = __byte_perm(w, 0x64646464u, 0x5140), b = __byte_perm(w, 0x64646464u, 0x7362);
+  const __half2 k = __halves2half2(__ushort_as_half((unsigned short)0x6400), __ushort_as_half((unsigned short)0x6400));
+  const __half2 ra = __hsub2(*reinterpret_cast<const __half2 *>(&a), k), rb = __hsub2(*reinterpret_cast<const __half2 *>(&b), k);
+  lo = *reinterpret_cast<const uint32_t *>(&ra);
+  hi = *reinterpret_cast<const uint32_t *>(&rb);
+}
+
+template <int BN, bool X2>
+__global__ void __launch_bounds__(kFThreads, 1)
+fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
+             const __grid_constant__ CUtensorMap tmWl, const F16Params p) {
+  using Plan = FPlan<BN, X2>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
+  auto conv_a = [&](int s) { return base + Plan::kOffConv + s * kConvBytes; };
+  auto w_a = [&](int s, int lo) { return base + Plan::kOffW + s * Plan::kWStage + lo * (BN * 128); };
+  auto raw_a = [&](int s) { return base + Plan::kOffRaw + s * kRawBytes; };
+  const uint32_t bars = base + Plan::kOffBar;
+  auto raw_full = [&](int s) { return bars + 8 * s; };
+  auto raw_empty = [&](int s) { return bars + 8 * (kNR + s); };
+  auto conv_full = [&](int s) { return bars + 8 * (2 * kNR + s); };
+  auto conv_empty = [&](int s) { return bars + 8 * (2 * kNR + kNC + s); };
+  auto w_full = [&](int s) { return bars + 8 * (2 * kNR + 2 * kNC + s); };
+  auto w_empty = [&](int s) { return conv_empty(s); }; // shared: the MMA warp's single commit per K block releases both tiles
+  auto tm_full = [&](int b) { return bars + 8 * (2 * kNR + 2 * kNC + 2 * kNW + b); };
+  auto tm_empty = [&](int b) { return bars + 8 * (2 * kNR + 2 * kNC + 2 * kNW + 2 + b); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kNR + 2 * kNC + 2 * kNW + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = p.dbg ? clock64() : 0;
+
+  // ---- one-time setup -----------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWh);
+    if (X2) tma_prefetch_desc(&tmWl);
+    for (int s = 0; s < kNR; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), kConvThreads / 64); }
+    for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), kConvThreads / 64); mbar_init(conv_empty(s), 1); }
+    for (int s = 0; s < kNW; ++s) mbar_init(w_full(s), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), kEpiThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                 "r"((uint32_t)Plan::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  float *colsc = reinterpret_cast<float *>(bp + Plan::kOffCol), *biass = colsc + 128;
+  for (int i = threadIdx.x; i < 128; i += kFThreads) {
+    colsc[i] = (i < p.cols_valid) ? __ldg(p.colscale + i) : 0.0f;
+    biass[i] = (i < p.cols_valid) ? __ldg(p.bias + i) : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int umma_n = min(BN, (p.cols_valid + 31) & ~31);
+
+  if (warp == 0) {
+    if (lane == 0) { // ===== raw uint8 producer ==========================================================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(raw_empty(s), ph ^ 1);
+          mbar_expect_tx(raw_full(s), kRawBytes);
+          tma_load_2d(raw_a(s), &tmX, raw_full(s), kb * kFK, tile * kFM);
+          if (++s == kNR) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    if (lane == 0) { // ===== weight producer ===========================================================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(w_empty(s), ph ^ 1);
+          mbar_expect_tx(w_full(s), Plan::kWStage);
+          tma_load_2d(w_a(s, 0), &tmWh, w_full(s), kb * kFK, 0);
+          if (X2) tma_load_2d(w_a(s, 1), &tmWl, w_full(s), kb * kFK, 0);
+          if (++s == kNW) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) { // ===== MMA issuer ================================================================
+      // One MMA per K step: with the lo tile stored right behind the hi tile, B = [W_hi; W_lo] is a single 2*BN-row K-major
+      // operand and D = [hi | lo] lands in adjacent TMEM columns. Descriptors are built once; per stage / K step only the
+      // 14-bit start-address field moves (the issuing thread is otherwise bound by descriptor arithmetic, not by the tensor pipe).
+      const uint32_t idesc = make_idesc_f16(X2 ? 2 * BN : umma_n);
+      const uint64_t dA0 = desc_k_major(conv_a(0)), dB0 = desc_k_major(w_a(0, 0));
+      int cs = 0, ws = 0, it = 0;
+      uint32_t cph = 0, wph = 0;
+      long long waited = 0, waited_w = 0, waited_tm = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t d_acc = tmem_base + (uint32_t)(buf * 2 * BN);
+        const long long tt0 = p.dbg ? clock64() : 0;
+        mbar_wait(tm_empty(buf), ((it >> 1) & 1) ^ 1);
+        if (p.dbg) waited_tm += clock64() - tt0;
+        tc_fence_after();
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          const long long t0 = p.dbg ? clock64() : 0;
+          mbar_wait(conv_full(cs), cph);
+          const long long t0b = p.dbg ? clock64() : 0;
+          mbar_wait(w_full(ws), wph);
+          if (p.dbg) { waited += t0b - t0; waited_w += clock64() - t0b; }
+          tc_fence_after();
+          const int nks = min(kFK / 16, (p.k_total - kb * kFK + 15) / 16);
+          const uint64_t da = dA0 + (uint64_t)(cs * (kConvBytes >> 4)), db = dB0 + (uint64_t)(ws * (Plan::kWStage >> 4));
+#pragma unroll
+          for (int ks = 0; ks < kFK / 16; ++ks)
+            if (ks < nks) umma_f16(d_acc, da + 2 * ks, db + 2 * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(conv_empty(cs)); // == w_empty(ws): kNC == kNW and both rings advance together
+          if (++cs == kNC) { cs = 0; cph ^= 1; }
+          if (++ws == kNW) { ws = 0; wph ^= 1; }
+        }
+        umma_commit(tm_full(buf));
+      }
+      if (p.dbg) { p.dbg[8 * blockIdx.x + 3] = waited; p.dbg[8 * blockIdx.x + 4] = waited_w; p.dbg[8 * blockIdx.x + 5] = waited_tm; }
+    }
+    __syncwarp();
+  } else if (warp >= kConvWarp0) {
+    // ===== converters: raw [128][64 B] -> fp16 K-major SWIZZLE_128B tile (row r at r*128, 16-byte chunk c at (c ^ (r&7))*16).
+    // Four consecutive lanes take one row's four 16-byte pieces, so a quarter-warp reads 128 contiguous bytes.
+    // Two groups of four warps take alternate K blocks: one block's wait -> load -> convert -> proxy fence -> arrive chain is
+    // ~1 k clk however many threads share it, so two chains in flight are what doubles the converter's throughput.
+    const int tt = threadIdx.x - kConvWarp0 * 32, grp = tt >> 7, t = tt & 127, j = t & 3, rb = t >> 2;
+    long long cw_raw = 0, cw_empty = 0;
+    int n = 0; // running K-block index of this CTA (over all its tiles)
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.k_blocks; ++kb, ++n) {
+        if ((n & 1) != grp) continue;
+        const int rs = n % kNR, cs = n % kNC;
+        const uint32_t rph = (uint32_t)(n / kNR) & 1u, cph = (uint32_t)(n / kNC) & 1u;
+        const long long c0 = p.dbg ? clock64() : 0;
+        mbar_wait(raw_full(rs), rph);
+        const long long c1 = p.dbg ? clock64() : 0;
+        mbar_wait(conv_empty(cs), cph ^ 1);
+        if (p.dbg) { cw_raw += c1 - c0; cw_empty += clock64() - c1; }
+        const uint8_t *raw = bp + Plan::kOffRaw + rs * kRawBytes;
+        uint8_t *dst = bp + Plan::kOffConv + cs * kConvBytes;
+        uint4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4 *>(raw + (rb + 32 * i) * kFK + j * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rb + 32 * i;
+          uint4 o0, o1;
+          u8x4_to_h4(w[i].x, o0.x, o0.y);
+          u8x4_to_h4(w[i].y, o0.z, o0.w);
+          u8x4_to_h4(w[i].z, o1.x, o1.y);
+          u8x4_to_h4(w[i].w, o1.z, o1.w);
+          *reinterpret_cast<uint4 *>(dst + r * 128 + (((2 * j) ^ (r & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4 *>(dst + r * 128 + (((2 * j + 1) ^ (r & 7)) << 4)) = o1;
+        }
+        fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) { // one arrival per warp
+          mbar_arrive(conv_full(cs));
+          mbar_arrive(raw_empty(rs));
+        }
+      }
+    }
+    if (p.dbg && tt == 0) { p.dbg[8 * blockIdx.x + 6] = cw_raw; p.dbg[8 * blockIdx.x + 7] = cw_empty; }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue warps 4-11: warp w owns TMEM lanes (= samples) 32*(w%4).., the two warps of a lane quarter split the
+    // 32-column chunks. A thread owns one 128-byte line of the output row per chunk: eight 16-byte stores from registers
+    // (no shared-memory transpose; the line is completed in L2) ==================================================
+    auto epilogue = [&](auto act_tag) {
+      constexpr int ACT = decltype(act_tag)::value;
+      const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
+      const int row = q * 32 + lane;
+      const float4 *colsc4 = reinterpret_cast<const float4 *>(colsc), *bias4 = reinterpret_cast<const float4 *>(biass);
+      long long busy = 0, waiting = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const long grow = (long)tile * kFM + row;
+        const bool row_ok = grow < p.rows_valid;
+        const long long t0 = p.dbg ? clock64() : 0;
+        mbar_wait(tm_full(buf), (it >> 1) & 1);
+        tc_fence_after();
+        const long long t1 = p.dbg ? clock64() : 0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) { // 16 columns at a time keeps this warp role under the 96 registers 640 threads leave
+          const int c0 = half * 16 + 32 * i;
+          if (c0 < p.cols_valid) {
+            uint32_t v[16];
+            tmem_ld16_nowait(lane_addr + c0, v);
+            if (X2) { // hi + lo accumulators, added in RN fp32
+              uint32_t w[16];
+              tmem_ld16_nowait(lane_addr + BN + c0, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            } else {
+              tmem_ld_wait();
+            }
+            float4 *dst = reinterpret_cast<float4 *>(p.out + grow * p.ld_out + c0);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const float4 s4 = colsc4[c0 / 4 + qq], b4 = bias4[c0 / 4 + qq];
+              float4 r;
+              r.x = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 0]), s4.x, b4.x));
+              r.y = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 1]), s4.y, b4.y));
+              r.z = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 2]), s4.z, b4.z));
+              r.w = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 3]), s4.w, b4.w));
+              if (row_ok) dst[qq] = r;
+            }
+          }
+        }
+        tc_fence_before(); // accumulator consumed: the issuer may start tile it+2 in this buffer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tm_empty(buf));
+        if (p.dbg) { const long long t2 = clock64(); waiting += t1 - t0; busy += t2 - t1; }
+      }
+      if (p.dbg && threadIdx.x == kEpiWarp0 * 32) { p.dbg[8 * blockIdx.x + 1] = busy; p.dbg[8 * blockIdx.x + 2] = waiting; }
+    };
+    if (p.act == B200_ACT_RELU) epilogue(IntTag<B200_ACT_RELU>{});
+    else if (p.act == B200_ACT_LINEAR) epilogue(IntTag<B200_ACT_LINEAR>{});
+    else epilogue(IntTag<-1>{});
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbg && threadIdx.x == 0) p.dbg[8 * blockIdx.x] = clock64() - t_start;
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Plan::kTmemCols) : "memory");
+  }
+}
+
+// W_l [K][N] fp32 (N contiguous) -> wh, wl [N][ldk] fp16 (K contiguous) with a per-neuron power-of-two scale:
+// s_o * max_k |w| in [2^13, 2^14) (fp16 overflows at 65504); colscale[o] = pre / s_o. One CTA of 1024 threads per 8 neurons
+// (one 32-byte sector per weight row), 128 K-slices per neuron: every weight is loaded ONCE (<= 8 per thread, all in flight
+// together), kept in registers across the max reduction, split, and written out through a shared-memory transpose.
+constexpr int kSplitNeurons = 8, kSplitMaxK = 1024;
+__global__ void __launch_bounds__(1024) split_w16_kernel(const float *__restrict__ W, int K, int N, int ldk, float pre,
+                                                       __half *__restrict__ wh, __half *__restrict__ wlo,
+                                                       float *__restrict__ colscale) {
+  __shared__ float red[128][kSplitNeurons + 1];
+  __shared__ float sc[kSplitNeurons];
+  __shared__ __align__(16) __half th[kSplitNeurons][kSplitMaxK + 8], tl[kSplitNeurons][kSplitMaxK + 8];
+  const int o = threadIdx.x & (kSplitNeurons - 1), kq = threadIdx.x / kSplitNeurons, o0 = blockIdx.x * kSplitNeurons;
+  const bool ok = o0 + o < N;
+  float v[kSplitMaxK / 128];
+  float amax = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kSplitMaxK / 128; ++i) {
+    const int k = kq + 128 * i;
+    v[i] = (ok && k < K) ? __ldg(W + (size_t)k * N + o0 + o) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < kSplitMaxK / 128; ++i) amax = fmaxf(amax, fabsf(v[i]));
+  red[kq][o] = amax;
+  __syncthreads();
+  if (threadIdx.x < kSplitNeurons) {
+    float m = 0.0f;
+    for (int i = 0; i < 128; ++i) m = fmaxf(m, red[i][threadIdx.x]);
+    int e = 0;
+    if (m > 0.0f && m < 3.0e38f) frexpf(m, &e); // m = f * 2^e, f in [0.5, 1)
+    e = max(-100, min(100, e));
+    sc[threadIdx.x] = ldexpf(1.0f, 14 - e);      // s * m in [2^13, 2^14)
+    if (o0 + threadIdx.x < N) colscale[o0 + threadIdx.x] = pre * ldexpf(1.0f, e - 14);
+  }
+  __syncthreads();
+  const float s = sc[o];
+#pragma unroll
+  for (int i = 0; i < kSplitMaxK / 128; ++i) {
+    const int k = kq + 128 * i;
+    const float x = v[i] * s;
+    const __half h = __float2half_rn(x);
+    th[o][k] = h;
+    tl[o][k] = __float2half_rn(x - __half2float(h));
+  }
+  __syncthreads();
+  const int vec_per_row = ldk / 8; // ldk is a multiple of 8: 16-byte stores
+  for (int idx = threadIdx.x; idx < kSplitNeurons * vec_per_row; idx += 1024) {
+    const int oo = idx / vec_per_row, kv = idx - oo * vec_per_row;
+    if (o0 + oo < N) {
+      *reinterpret_cast<uint4 *>(wh + (size_t)(o0 + oo) * ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&th[oo][8 * kv]);
+      *reinterpret_cast<uint4 *>(wlo + (size_t)(o0 + oo) * ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&tl[oo][8 * kv]);
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsigned long long dim0, unsigned long long dim1,
+                unsigned long long stride_bytes, unsigned box0, unsigned box1, CUtensorMapSwizzle sw) {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {stride_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu stride %llu box %u x %u ptr %p", (int)r, dim0, dim1,
+              stride_bytes, box0, box1, ptr);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+template <int BN, bool X2>
+int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const F16Params &p, int grid, cudaStream_t st) {
+  auto kern = fwd16_kernel<BN, X2>;
+  constexpr int smem = FPlan<BN, X2>::kTotal;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  static long long *dbg = nullptr;
+  static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
+  F16Params pp = p;
+  if (timing) {
+    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 1024));
+    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * 1024, st));
+    pp.dbg = dbg;
+  }
+  kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, pp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  B200_CUDA(cudaGetLastError());
+  if (timing) {
+    std::vector<long long> h(8 * 1024);
+    B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < 8; ++j) a[j] += (double)h[8 * i + j] / grid;
+    fprintf(stderr, "[fwd16 timing] BN %d x2 %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: conv %.0f, "
+            "weights %.0f, tmem %.0f | converter waits: raw %.0f, conv slot %.0f\n",
+            BN, (int)X2, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+  }
+  return B200_OK;
+}
+
+} // namespace
+
+// Layer 0 forward on the uint8 copy of the input (xq). Sets *done when it ran.
+int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t *xq, long batch, bool *done) {
+  *done = false;
+  const char *env = std::getenv("B200_FWD16"); // debugging aid, read per call: 0 = use the generic tcgen05 kernel
+  const bool off = env && std::atoi(env) == 0;
+  if (off || l != 0 || !xq) return B200_OK;
+  const int K = net->dims[0], N = net->dims[1];
+  if (K % 16 != 0 || K > kSplitMaxK || N % 32 != 0 || N > 128 || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
+  const bool x2 = net->prec == B200_PREC_TF32X3;
+  const int ldk = (K + 7) & ~7;
+  cudaStream_t st = net->ctx->stream;
+  if (!net->w16h) {
+    B200_CUDA(cudaMalloc(&net->w16h, sizeof(__half) * (size_t)N * ldk));
+    B200_CUDA(cudaMalloc(&net->w16l, sizeof(__half) * (size_t)N * ldk));
+    B200_CUDA(cudaMalloc(&net->colscale, sizeof(float) * N));
+  }
+  const float *W = params + net->offs[0];
+  {
+    ProfScope ps(net->ctx, "split16");
+    B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, st, W, K, N, ldk, 1.0f / 255.0f, (__half *)net->w16h,
+                (__half *)net->w16l, net->colscale);
+  }
+  CUtensorMap tx, twh, twl;
+  B200_TRY(make_map_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K, batch, K, kFK, kFM, CU_TENSOR_MAP_SWIZZLE_NONE));
+  const unsigned bn = N > 64 ? 128 : 64;
+  B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16h, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
+                       CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16l, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
+                       CU_TENSOR_MAP_SWIZZLE_128B));
+  F16Params p{};
+  p.rows_valid = (int)batch; p.cols_valid = N; p.k_total = K;
+  p.k_blocks = ceil_div(K, kFK);
+  p.tiles = ceil_div(batch, kFM);
+  p.act = net->acts[0];
+  p.bias = W + (size_t)K * N;
+  p.colscale = net->colscale;
+  p.out = net->act[0]; p.ld_out = N;
+  const int grid = std::min(net->ctx->num_sms, p.tiles);
+  if (bn == 128) {
+    if (x2) B200_TRY((launch_fwd16<128, true>(tx, twh, twl, p, grid, st)));
+    else B200_TRY((launch_fwd16<128, false>(tx, twh, twl, p, grid, st)));
+  } else {
+    if (x2) B200_TRY((launch_fwd16<64, true>(tx, twh, twl, p, grid, st)));
+    else B200_TRY((launch_fwd16<64, false>(tx, twh, twl, p, grid, st)));
+  }
+  *done = true;
+  return B200_OK;
+}
+
+void fwd16_release(b200_net *net) {
+  if (net->w16h) cudaFree(net->w16h);
+  if (net->w16l) cudaFree(net->w16l);
+  if (net->colscale) cudaFree(net->colscale);
+  net->w16h = net->w16l = nullptr;
+  net->colscale = nullptr;
+}
+
+} // namespace b200

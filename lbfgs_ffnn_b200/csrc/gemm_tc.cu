@@ -18,6 +18,8 @@
 // DW is split-K over the batch with per-split partial tiles (deterministic, combined in fp64 by
 // finalize_grad_kernel); the bias gradient is one extra N=16 MMA per K step against a tile of ones.
 #include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
 
 #include <cuda.h>
 
@@ -66,133 +68,7 @@ struct TcParams {
   long long *dbg;        // B200_TC_TIMING=1: per-CTA {main loop, epilogue} clock64 durations
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, descriptor version 1 (Blackwell).
-// K-major  (layout 2, SWIZZLE_128B: 16 B chunks XOR row%8): rows of 128 B (32 floats of K) at 128 B pitch,
-//           8-row groups at SBO = 1024 B; LBO unused (1). TMA: CU_TENSOR_MAP_SWIZZLE_128B.
-// MN-major (layout 1, SWIZZLE_128B_BASE32B: 32 B chunks XOR row%4 — the only MN-major layout for 32-bit
-//           operands): atoms of [4 K-rows][32 MN floats] (512 B); next 4-row K group at SBO = 512 B, next
-//           MN atom (32 floats further along M/N) at LBO. TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46; // version
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-__device__ __forceinline__ uint64_t desc_k_major(uint32_t saddr) { return make_desc(saddr, 16, 1024, 2); }
-__device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr) { return make_desc(saddr, 4096, 512, 1); }
-// instruction descriptor: fp32 accumulate, tf32 x tf32, given majors and N (M = 128)
-__host__ __device__ constexpr uint32_t make_idesc(int a_major, int b_major, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-// packed fp32 FMA (Blackwell FFMA2): (d0, d1) += (a0, a1) * (b0, b1) in ONE issue slot
-__device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t"
-      "mov.b64 rb, {%4, %5};\n\t"
-      "mov.b64 rc, {%0, %1};\n\t"
-      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rc;\n\t}"
-      : "+f"(d0), "+f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-
-// activation with a compile-time tag when ACT >= 0 (the ReLU fast path), else the runtime switch. A per-element
-// runtime switch puts a uniform branch between every pair of independent FMAs and serialises the epilogue.
-template <int ACT> __device__ __forceinline__ float act_apply_c(int act, float v) {
-  if constexpr (ACT == B200_ACT_RELU) return fmaxf(v, 0.0f);
-  else if constexpr (ACT == B200_ACT_LINEAR) return v;
-  else return act_apply(act, v);
-}
-template <int ACT> __device__ __forceinline__ float act_deriv_c(int act, float a) {
-  if constexpr (ACT == B200_ACT_RELU) return a > 0.0f ? 1.0f : 0.0f;
-  else if constexpr (ACT == B200_ACT_LINEAR) return 1.0f;
-  else return act_deriv_from_output(act, a);
-}
-template <int V> struct IntTag { static constexpr int value = V; };
-
-// Store a 32(row) x 32(col) fp32 block held one row per lane as 32 fully coalesced 128-byte row segments
-// (a per-thread row store would touch 32 different lines per instruction, 8x the L2 write transactions).
-// scratch: this warp's private 32 x 33 floats of shared memory.
-__device__ __forceinline__ void store_block_coalesced(const float (&r)[32], float *scratch, float *gbase, long ld,
-                                                      int rows_ok, int lane) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = r[j];
-  __syncwarp();
-#pragma unroll 8
-  for (int rr = 0; rr < 32; ++rr)
-    if (rr < rows_ok) gbase[(long)rr * ld + lane] = scratch[rr * 33 + lane];
-  __syncwarp();
-}
+using namespace tcx;
 
 // U8: 0 = both operands fp32 in HBM; 1 = the A operand (FWD: the input X) is stored as uint8 = 255*x;
 //     2 = the B operand (DW: X) is. A uint8 operand is converted to fp32 in shared memory by the splitter warps;
@@ -801,6 +677,8 @@ int tc_mask() { // debugging aid: B200_TC_MASK bit0 = FWD, bit1 = DX, bit2 = DW 
 
 } // namespace
 
+static int tc_ensure_split(b200_net *net);
+
 // A_l = act(A_{l-1} W_l + b_l) for hidden layers. With `fuse` (l is the penultimate layer and the last layer has
 // out <= 16) the epilogue also runs the last layer, the loss partials, delta_L and delta_{L-1}.
 int tc_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch, const TcFuseLast *fuse,
@@ -814,6 +692,11 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   const bool x3 = net->prec == B200_PREC_TF32X3;
   // layer 0 with an input that is exactly u/255: read the 4x smaller uint8 copy (net_quantize_input)
   const uint8_t *xq = (l == 0 && (tc_mask() & 16) == 0) ? net_xq_lookup(net, in, batch) : nullptr;
+  if (xq && !fuse) { // persistent fp16 kernel (gemm_fwd16.cu); the last layer then runs in tail_layer.cu
+    B200_TRY(fwd16_forward_layer(net, l, params, xq, batch, done));
+    if (*done) return B200_OK;
+  }
+  B200_TRY(tc_ensure_split(net));
   CUtensorMap ta, tb;
   if (xq) B200_TRY(make_map_u8(&ta, xq, K, batch, BM));        // A: uint8 {K bytes, rows}, box {32, 128}
   else B200_TRY(make_map(&ta, in, K, batch, K, BM, MAJOR_K)); // A: {K, rows}, box {32, 128}
@@ -868,6 +751,7 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
       Kin % 32 != 0)
     return B200_OK;
   const bool x3 = net->prec == B200_PREC_TF32X3;
+  B200_TRY(tc_ensure_split(net));
   CUtensorMap ta, tb;
   B200_TRY(make_map(&ta, net->delta[l], Nout, batch, net->ldd[l], BM, MAJOR_K)); // A: {K = out, rows}, box {32, 128}
   TcParams p{};
@@ -948,7 +832,14 @@ int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
 
 // 3xTF32: hi / lo parts of the whole parameter vector, once per evaluation (read by the FWD and DX kernels)
 int tc_split_params(b200_net *net, const float *params) {
-  if (net->prec != B200_PREC_TF32X3) return B200_OK;
+  net->split_src = (net->prec == B200_PREC_TF32X3) ? params : nullptr; // launched by the first kernel that reads the split
+  return B200_OK;
+}
+
+static int tc_ensure_split(b200_net *net) {
+  const float *params = net->split_src;
+  if (!params) return B200_OK;
+  net->split_src = nullptr;
   if (!net->w_hi) {
     B200_CUDA(cudaMalloc(&net->w_hi, sizeof(float) * net->n));
     B200_CUDA(cudaMalloc(&net->w_lo, sizeof(float) * net->n));
@@ -962,6 +853,7 @@ void tc_release(b200_net *net) {
   if (net->w_hi) cudaFree(net->w_hi);
   if (net->w_lo) cudaFree(net->w_lo);
   net->w_hi = net->w_lo = nullptr;
+  fwd16_release(net);
 }
 
 } // namespace b200

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs
 // the slot written by (1), curvature test + ring advance, then the two-loop recurrences in fp64.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
-  extern __shared__ double sh[]; // tot[ncols] | alpha[mp] | beta[mp]
+  extern __shared__ double sh[]; // tot[ncols] | alpha[mp] | beta[mp] | SY[mp*mp] | YY[mp*mp] | rho, sg, yg [mp] | phys[mp] (int)
   LbfgsHeader *h = a.st.h;
   const int mp = h->mp, mod = h->mod;
   const int ncols = kDotsCols * mp + 1;
@@ -244,25 +244,38 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
   }
   __syncthreads();
 
-  // two-loop recurrences on the Gram blocks: warp 0, lanes parallel over the inner sums
+  // two-loop recurrences on the Gram blocks: warp 0, lanes parallel over the inner sums. Everything the 2k dependent
+  // steps touch is staged in shared memory first: with the Gram blocks in global memory every step paid an L2 round trip
+  // (~0.3 us), i.e. most of this kernel's time.
+  // (histories too long for the staging area, m > ~100, read the global copies as before)
+  const double *sSY = a.st.SY, *sYY = a.st.YY, *srho = a.st.rho, *ssg = a.st.sg, *syg = a.st.yg;
+  int *sphys = a.st.phys;
+  if (a.stage_gram) {
+    double *tSY = dlt + mp, *tYY = tSY + mp * mp, *trho = tYY + mp * mp, *tsg = trho + mp, *tyg = tsg + mp;
+    for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { tSY[i] = a.st.SY[i]; tYY[i] = a.st.YY[i]; }
+    for (int i = threadIdx.x; i < mp; i += blockDim.x) { trho[i] = a.st.rho[i]; tsg[i] = a.st.sg[i]; tyg[i] = a.st.yg[i]; }
+    sSY = tSY; sYY = tYY; srho = trho; ssg = tsg; syg = tyg;
+    sphys = reinterpret_cast<int *>(tyg + mp);
+  }
+  __syncthreads();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const int head = s_head, k = s_count;
     const double gg = tot[kDotsCols * mp];
-    for (int i = lane; i < k; i += 32) a.st.phys[i] = ring_phys(head, k, mod, i);
+    for (int i = lane; i < k; i += 32) { const int ph = ring_phys(head, k, mod, i); sphys[i] = ph; a.st.phys[i] = ph; }
     __syncwarp();
     double gamma = 1.0, cg = -1.0, gdotp = -gg;
     if (k > 0) {
       for (int i = k - 1; i >= 0; --i) {
-        const int pi = a.st.phys[i];
+        const int pi = sphys[i];
         double s = 0.0;
-        for (int j = i + 1 + lane; j < k; j += 32) s += alpha[j] * a.st.SY[pi * mp + a.st.phys[j]];
+        for (int j = i + 1 + lane; j < k; j += 32) s += alpha[j] * sSY[pi * mp + sphys[j]];
         s = warp_sum(s);
-        if (lane == 0) alpha[i] = a.st.rho[pi] * (a.st.sg[pi] - s);
+        if (lane == 0) alpha[i] = srho[pi] * (ssg[pi] - s);
         __syncwarp();
       }
-      const int pl = a.st.phys[k - 1];
-      const double ys = a.st.SY[pl * mp + pl], yy = a.st.YY[pl * mp + pl];
+      const int pl = sphys[k - 1];
+      const double ys = sSY[pl * mp + pl], yy = sYY[pl * mp + pl];
       if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
       else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
       else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
@@ -270,14 +283,14 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
         gamma = fmin(fmax(gamma, 1e-6), 1e6);
       }
       for (int i = 0; i < k; ++i) {
-        const int pi = a.st.phys[i];
+        const int pi = sphys[i];
         double s1 = 0.0, s2 = 0.0;
-        for (int j = lane; j < k; j += 32) s1 += alpha[j] * a.st.YY[pi * mp + a.st.phys[j]];
-        for (int j = lane; j < i; j += 32) s2 += dlt[j] * a.st.SY[a.st.phys[j] * mp + pi];
+        for (int j = lane; j < k; j += 32) s1 += alpha[j] * sYY[pi * mp + sphys[j]];
+        for (int j = lane; j < i; j += 32) s2 += dlt[j] * sSY[sphys[j] * mp + pi];
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
         if (lane == 0) {
-          const double beta = a.st.rho[pi] * (gamma * (a.st.yg[pi] - s1) + s2);
+          const double beta = srho[pi] * (gamma * (syg[pi] - s1) + s2);
           dlt[i] = alpha[i] - beta;
         }
         __syncwarp();
@@ -288,7 +301,7 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
         const double csj = -dlt[j], cyj = gamma * alpha[j];
         a.st.cs[j] = csj;
         a.st.cy[j] = cyj;
-        gp += csj * a.st.sg[a.st.phys[j]] + cyj * a.st.yg[a.st.phys[j]];
+        gp += csj * ssg[sphys[j]] + cyj * syg[sphys[j]];
       }
       gp = warp_sum(gp);
       gdotp = cg * gg + gp;
@@ -477,8 +490,19 @@ int launch_lbfgs_dots(const DotsArgs &a0, int mp, int nblocks, cudaStream_t st) 
   return B200_OK;
 }
 
-int launch_lbfgs_solve(const SolveArgs &a, int mp, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (kDotsCols * mp + 1 + 2 * mp);
+int launch_lbfgs_solve(const SolveArgs &a0, int mp, cudaStream_t st) {
+  SolveArgs a = a0;
+  const size_t base = sizeof(double) * (kDotsCols * mp + 1 + 2 * mp);
+  const size_t staged = base + sizeof(double) * (2 * (size_t)mp * mp + 3 * mp) + sizeof(int) * mp;
+  a.stage_gram = staged <= 200 * 1024;
+  const size_t smem = a.stage_gram ? staged : base;
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CUDA(cudaFuncSetAttribute(lbfgs_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+  }
   B200_LAUNCH(lbfgs_solve_kernel, 1, 256, smem, st, a);
   return B200_OK;
 }

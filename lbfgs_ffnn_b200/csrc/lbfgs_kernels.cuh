@@ -108,6 +108,7 @@ struct SolveArgs {
   int force_accept;      // direct API: accept the pair with the caller's rho
   double ext_rho;
   int allreduce_done;    // unused on one GPU (partials are already global)
+  int stage_gram;        // set by launch_lbfgs_solve: the Gram blocks fit the shared-memory staging area
 };
 
 struct ApplyArgs {

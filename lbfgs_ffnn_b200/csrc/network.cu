@@ -263,7 +263,7 @@ int net_ensure(b200_net *net, long batch) {
       B200_CUDA(cudaMalloc(&net->delta[l], sizeof(float) * (size_t)net->ldd[l] * batch));
       B200_CUDA(cudaMemsetAsync(net->delta[l], 0, sizeof(float) * (size_t)net->ldd[l] * batch, net->ctx->stream)); // padding columns stay 0
     }
-    net->loss_part_cap = 4 * ceil_div(batch, kBM) * ceil_div(net->dims[L], 16);
+    net->loss_part_cap = std::max(4 * ceil_div(batch, kBM) * ceil_div(net->dims[L], 16), 2 * net->ctx->num_sms);
     B200_CUDA(cudaMalloc(&net->loss_part, sizeof(double) * net->loss_part_cap));
     net->cap = batch;
   }
@@ -402,9 +402,18 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   // forward sweep
   const float *cur = x;
   bool fused_last = false; // last layer, loss, delta_L and delta_{L-1} produced by the penultimate layer's epilogue
+  bool tail_done = false;  // ... or by the one-pass last-layer kernel, which also produces the [dW_L; db_L] partials
+  const bool use_tail = tail_applicable(net);
+  const uint8_t *xq0 = (use_tail && net->prec != B200_PREC_FP32 && dw16_applicable(net)) ? net_xq_lookup(net, x, batch) : nullptr;
+  const bool use_dw16 = xq0 != nullptr; // layer-0 dW on the fp16 tensor cores: the tail writes delta_0 as scaled fp16 {hi | lo}
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
     if (last && fused_last) break;
+    if (last && use_tail) {
+      B200_TRY(tail_layer(net, params, t, batch, inv_batch, /*want32=*/!use_dw16, /*want16=*/use_dw16));
+      tail_done = true;
+      break;
+    }
     bool done = false;
     {
       char nm[16];
@@ -412,7 +421,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       ProfScope ps(ctx, nm);
       if (!last && net->prec != B200_PREC_FP32) {
         const TcFuseLast fuse{t, inv_batch};
-        B200_TRY(tc_forward_layer(net, l, params, cur, batch, &fuse, &done, &fused_last));
+        B200_TRY(tc_forward_layer(net, l, params, cur, batch, use_tail ? nullptr : &fuse, &done, &fused_last));
       }
       if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, last, t, inv_batch));
     }
@@ -425,7 +434,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     const int K = net->dims[l], N = net->dims[l + 1];
     const float *W = params + net->offs[l];
     const float *in = (l == 0) ? x : net->act[l - 1];
-    if (l > 0 && !(l == L - 1 && fused_last)) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
+    if (l > 0 && !(l == L - 1 && (fused_last || tail_done))) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
       char nm[16];
       snprintf(nm, sizeof(nm), "dx%d", l);
       ProfScope ps(ctx, nm);
@@ -446,12 +455,13 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         B200_TRY((launch_gemm_simt<true, true, EPI_DX>(p, 1, st)));
       }
     }
-    { // [dW; db] partials = [A_{l-1} | 1]^T delta_l over batch slices
+    if (!(l == L - 1 && tail_done)) { // [dW; db] partials = [A_{l-1} | 1]^T delta_l over batch slices
       char nm[16];
       snprintf(nm, sizeof(nm), "dw%d", l);
       ProfScope ps(ctx, nm);
       bool done = false;
-      if (net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
+      if (l == 0 && use_dw16) B200_TRY(dw16_layer(net, xq0, batch, &done));
+      if (!done && net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
       if (!done && N <= 16 && K + 1 <= 160 && net->prec != B200_PREC_FP32) {
         const int splits = std::max(1, std::min(net->skinny_splits[l], ceil_div(batch, kSkinnyTile)));
         const int chunk = ceil_div(ceil_div(batch, splits), kSkinnyTile) * kSkinnyTile;
@@ -558,6 +568,7 @@ int b200_net_destroy(b200_net *net) {
   cudaStreamSynchronize(net->ctx->stream);
   free_batch_buffers(net);
   tc_release(net);
+  tail_release(net);
   if (net->xq.data) cudaFree(net->xq.data);
   if (net->xq.flag) cudaFree(net->xq.flag);
   if (net->partials) cudaFree(net->partials);

@@ -46,6 +46,14 @@ struct b200_net {
   } xq;
 
   float *w_hi = nullptr, *w_lo = nullptr; // 3xTF32: hi / lo split of the parameter vector of the current evaluation
+  const float *split_src = nullptr;       // parameters of the current evaluation whose TF32 split has not been launched yet (lazy)
+  // fp16 forward of layer 0 on a uint8 input (gemm_fwd16.cu): per-neuron-scaled hi / lo fp16 weights [out][ldk], 1/(255 s_o)
+  void *w16h = nullptr, *w16l = nullptr;
+  float *colscale = nullptr;
+  // one-pass last layer (tail_layer.cu): per-CTA max |delta_L|, scaled fp16 {hi | lo} copy of delta_{L-1} and 1 / its scale
+  float *amax_part = nullptr, *scale16_inv = nullptr;
+  void *delta16 = nullptr;
+  long delta16_cap = 0;
 
   double *loss_part = nullptr; // per-CTA partials of sum diff^2
   int loss_part_cap = 0, loss_part_n = 0;
@@ -76,5 +84,9 @@ int net_quantize_input(b200_net *net, const float *x, long batch);
 void net_xq_clear(b200_net *net);
 // the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
+// the skinny last layer in one pass: forward, loss, both deltas and the [dW_L; db_L] partials (tail_layer.cu)
+bool tail_applicable(const b200_net *net);
+int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16);
+void tail_release(b200_net *net);
 
 } // namespace b200

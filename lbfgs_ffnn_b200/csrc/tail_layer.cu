@@ -1,0 +1,394 @@
+// The skinny last layer (out <= 12, in = 32 / 64 / 128) in ONE pass over the penultimate activations:
+//   forward  A_L = act(A_{L-1} W_L + b_L)                      (src/cuda/layer.cuh:48-58, kernels.cuh:74-106)
+//   loss     0.5 ||A_L - T||^2 / B, delta_L = (A_L - T)/B .* act'   (src/cuda/network.cuh:100-107, layer.cuh:69-79)
+//   dX       delta_{L-1} = (delta_L W_L^T) .* act'(A_{L-1})     (layer.cuh:89-103, kernels.cuh:109-133)
+//   dW, db   [A_{L-1} | 1]^T delta_L split-K partials           (layer.cuh:81-86, kernels.cuh:144-153)
+// i.e. 3 SGEMMs + 7 element-wise kernels + a blocking dot of the reference. A_{L-1} is read once (coalesced rows) and
+// delta_{L-1} written once; everything else stays in registers: a lane owns in/32 consecutive features and the matching
+// rows of W_L, a warp takes two samples at a time and reduces their 2 x 16 partial pre-activations with a 27-shuffle
+// transpose-reduce (lane v ends up with value v), so no shared memory is touched until the per-CTA dW combine.
+// HBM-bound by design (bytes: A_{L-1} + delta_{L-1}); fp32 FFMA throughout, so it serves every precision mode.
+#include "network.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace b200 {
+
+namespace {
+
+struct TailParams {
+  const float *A;      // [B][in] penultimate activations
+  const float *W;      // [in][out] then out biases
+  const float *T;      // [B][out]
+  float *out_last;     // [B][out]
+  float *delta_last;   // [B][ldd]
+  float *delta_prev;   // [B][in] fp32 (nullptr: not needed)
+  __half *d16;         // [B][2 in] fp16 {hi | lo} of S * delta_prev (nullptr: not needed)
+  float *scale16_inv;  // device scalar 1 / S
+  float *amax_part;    // [grid] per-CTA max |delta_L|
+  int n_amax;
+  float *partial;      // [grid][(in+1)*out]
+  double *loss_part;   // [grid]
+  long batch;
+  int chunk;           // samples per CTA (even)
+  int out, ldd, act_last, act_prev;
+  float inv_batch;
+};
+
+template <int FPL> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int FPL> __device__ __forceinline__ void load_row(const float *p, float (&a)[FPL]) {
+  using V = typename VecT<FPL>::type;
+  const V v = __ldg(reinterpret_cast<const V *>(p));
+  const float *f = reinterpret_cast<const float *>(&v);
+#pragma unroll
+  for (int c = 0; c < FPL; ++c) a[c] = f[c];
+}
+template <int FPL> __device__ __forceinline__ void store_row(float *p, const float (&a)[FPL]) {
+  using V = typename VecT<FPL>::type;
+  V v;
+  float *f = reinterpret_cast<float *>(&v);
+#pragma unroll
+  for (int c = 0; c < FPL; ++c) f[c] = a[c];
+  *reinterpret_cast<V *>(p) = v;
+}
+
+// transpose-reduce of 2 x 16 per-lane partials over the warp: lane v ends up with the warp total of value v
+// (v = 16 * sample + output); 27 shuffles for OLP <= 12 instead of 5 per value
+template <int OLP>
+__device__ __forceinline__ float transpose_reduce(const float (&p0)[OLP], const float (&p1)[OLP], int lane) {
+  float q[16];
+  const int half = lane >> 4;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < OLP) {
+      const float send = half ? p0[j] : p1[j], keep = half ? p1[j] : p0[j];
+      q[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    } else {
+      q[j] = 0.0f;
+    }
+  }
+  float r8[8], r4[4], r2[2];
+  {
+    const bool b = (lane >> 3) & 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float send = b ? q[j] : q[8 + j], keep = b ? q[8 + j] : q[j];
+      r8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool b = (lane >> 2) & 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = b ? r8[j] : r8[4 + j], keep = b ? r8[4 + j] : r8[j];
+      r4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool b = (lane >> 1) & 1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = b ? r4[j] : r4[2 + j], keep = b ? r4[2 + j] : r4[j];
+      r2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool b = lane & 1;
+  const float send = b ? r2[0] : r2[1], keep = b ? r2[1] : r2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// ---- pass 1: last-layer forward, loss, delta_L; per-CTA max |delta_L| (the scale of the fp16 delta_{L-1} needs it) ----
+// OLP: compile-time padded output count (10 = the MNIST fast path, 12 = anything up to 12 with zero-padded weights)
+template <int FPL, int OLP>
+__global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
+  constexpr int IN = 32 * FPL;
+  __shared__ double lred[32];
+  __shared__ float mred[8];
+  __shared__ float dbred[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OL = p.out;
+  float w[FPL][OLP];
+#pragma unroll
+  for (int c = 0; c < FPL; ++c)
+#pragma unroll
+    for (int j = 0; j < OLP; ++j) w[c][j] = (j < OL) ? __ldg(p.W + (size_t)(lane * FPL + c) * OL + j) : 0.0f;
+  const int myj = lane & 15, half = lane >> 4;
+  const float bj = (myj < OL) ? __ldg(p.W + (size_t)IN * OL + myj) : 0.0f;
+  double lsum = 0.0;
+  float amax = 0.0f, accd = 0.0f; // accd: this lane's (sample parity, output) share of db_L = sum_s delta_L[s][:]
+  const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
+  float a0[FPL], a1[FPL], n0[FPL], n1[FPL];
+  auto fetch = [&](long s, float (&x0)[FPL], float (&x1)[FPL]) {
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) { x0[c] = 0.0f; x1[c] = 0.0f; }
+    if (s < b1) load_row<FPL>(p.A + s * IN + lane * FPL, x0);
+    if (s + 1 < b1) load_row<FPL>(p.A + (s + 1) * IN + lane * FPL, x1);
+  };
+  long s = b0 + 2 * warp;
+  fetch(s, a0, a1);
+  for (; s < b1; s += 16) {
+    fetch(s + 16, n0, n1); // next pair of this warp: in flight while this pair is processed
+    const long smy = s + half;
+    float tj = 0.0f;
+    if (myj < OL && smy < b1) tj = __ldg(p.T + smy * OL + myj);
+    float p0[OLP], p1[OLP];
+#pragma unroll
+    for (int j = 0; j < OLP; ++j) { p0[j] = 0.0f; p1[j] = 0.0f; }
+#pragma unroll
+    for (int c = 0; c < FPL; ++c)
+#pragma unroll
+      for (int j = 0; j < OLP; ++j) { p0[j] = fmaf(a0[c], w[c][j], p0[j]); p1[j] = fmaf(a1[c], w[c][j], p1[j]); }
+    const float z = transpose_reduce<OLP>(p0, p1, lane); // pre-activation of (sample smy, output myj)
+    if (myj < OL && smy < b1) {
+      const float o = act_apply(p.act_last, z + bj);
+      const float d = o - tj;
+      const float dl = d * p.inv_batch * act_deriv_from_output(p.act_last, o);
+      p.out_last[smy * OL + myj] = o;
+      p.delta_last[smy * p.ldd + myj] = dl;
+      lsum += (double)d * (double)d;
+      amax = fmaxf(amax, fabsf(dl));
+      accd += dl;
+    }
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) { a0[c] = n0[c]; a1[c] = n1[c]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) mred[warp] = amax;
+  const float dbv = accd + __shfl_xor_sync(0xffffffffu, accd, 16); // lanes j and 16 + j hold the two sample parities
+  if (lane < 16) dbred[warp][lane] = dbv;
+  const double tot = block_sum(lsum, lred); // (contains the __syncthreads that publishes mred and dbred)
+  if (threadIdx.x < OL) { // bias row of this CTA's [dW_L; db_L] partial (tail_bwd_kernel writes the dW rows), fixed warp order
+    float v = dbred[0][threadIdx.x];
+    for (int i = 1; i < 8; ++i) v += dbred[i][threadIdx.x];
+    p.partial[(size_t)blockIdx.x * (size_t)(IN + 1) * OL + (size_t)IN * OL + threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) {
+    p.loss_part[blockIdx.x] = tot;
+    float m = mred[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, mred[i]);
+    p.amax_part[blockIdx.x] = m;
+  }
+}
+
+// ---- pass 2: delta_{L-1} (fp32 for a dX GEMM and / or scaled fp16 hi|lo for the fp16 dW GEMM) and the [dW_L; db_L] partials ----
+template <int FPL, int OLP>
+__global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
+  constexpr int IN = 32 * FPL;
+  __shared__ float red[(IN + 1) * OLP];
+  __shared__ float mred[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OL = p.out;
+  float w[FPL][OLP];
+#pragma unroll
+  for (int c = 0; c < FPL; ++c)
+#pragma unroll
+    for (int j = 0; j < OLP; ++j) w[c][j] = (j < OL) ? __ldg(p.W + (size_t)(lane * FPL + c) * OL + j) : 0.0f;
+  // power-of-two scale S of the fp16 copy: |delta_{L-1}| <= max_f ||W_L[f,:]||_1 * max |delta_L| =: bound; S * bound in [2^13, 2^14)
+  float S = 1.0f;
+  if (p.d16) {
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < p.n_amax; i += blockDim.x) m = fmaxf(m, __ldg(p.amax_part + i));
+    float cw = 0.0f;
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) {
+      float r = 0.0f;
+#pragma unroll
+      for (int j = 0; j < OLP; ++j) r += fabsf(w[c][j]);
+      cw = fmaxf(cw, r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      cw = fmaxf(cw, __shfl_xor_sync(0xffffffffu, cw, o));
+    }
+    if (lane == 0) mred[warp] = m;
+    __syncthreads();
+    m = mred[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, mred[i]);
+    const float bound = m * cw;
+    int e = 0;
+    if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &e);
+    e = max(-100, min(100, e));
+    S = ldexpf(1.0f, 14 - e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.scale16_inv = ldexpf(1.0f, e - 14);
+  }
+  float acc[FPL][OLP];
+#pragma unroll
+  for (int c = 0; c < FPL; ++c)
+#pragma unroll
+    for (int j = 0; j < OLP; ++j) acc[c][j] = 0.0f;
+
+  const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
+  // one sample per warp and step; the next sample's activations and delta_L (48 bytes, the same for every lane) are in
+  // flight while this one is processed
+  float a[FPL], an[FPL], an2[FPL];
+  float4 dv[3], dn[3];
+  auto fetch_a = [&](long s, float (&x)[FPL]) {
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) x[c] = 0.0f;
+    if (s < b1) load_row<FPL>(p.A + s * IN + lane * FPL, x);
+  };
+  auto fetch_d = [&](long s, float4 (&y)[3]) { // delta_L of one sample: 48 bytes, L2-resident (tail_fwd_kernel just wrote it)
+    y[0] = y[1] = y[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < b1) {
+      const float4 *dp = reinterpret_cast<const float4 *>(p.delta_last + s * p.ldd);
+      y[0] = __ldg(dp);
+      if (p.ldd > 4) y[1] = __ldg(dp + 1);
+      if (p.ldd > 8) y[2] = __ldg(dp + 2);
+    }
+  };
+  long s = b0 + warp;
+  fetch_a(s, a); fetch_d(s, dv);
+  fetch_a(s + 8, an);
+  for (; s < b1; s += 8) {
+    fetch_a(s + 16, an2); // activations two samples ahead (HBM latency), delta_L one ahead
+    fetch_d(s + 8, dn);
+    float d[OLP];
+    {
+      const float t[12] = {dv[0].x, dv[0].y, dv[0].z, dv[0].w, dv[1].x, dv[1].y, dv[1].z, dv[1].w, dv[2].x, dv[2].y, dv[2].z, dv[2].w};
+#pragma unroll
+      for (int j = 0; j < OLP; ++j) d[j] = (j < OL) ? t[j] : 0.0f;
+    }
+    float g[FPL];
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) {
+      float x = 0.0f;
+#pragma unroll
+      for (int j = 0; j < OLP; ++j) {
+        x = fmaf(w[c][j], d[j], x);
+        acc[c][j] = fmaf(a[c], d[j], acc[c][j]);
+      }
+      g[c] = x * act_deriv_from_output(p.act_prev, a[c]);
+    }
+    if (p.delta_prev) store_row<FPL>(p.delta_prev + s * IN + lane * FPL, g);
+    if (p.d16) { // [s][0..IN) = hi, [s][IN..2 IN) = lo of S * delta
+      __half hi[FPL], lo[FPL];
+#pragma unroll
+      for (int c = 0; c < FPL; ++c) {
+        const float x = g[c] * S;
+        hi[c] = __float2half_rn(x);
+        lo[c] = __float2half_rn(x - __half2float(hi[c]));
+      }
+      __half *row = p.d16 + s * (2 * IN) + lane * FPL;
+      if constexpr (FPL == 4) {
+        *reinterpret_cast<uint2 *>(row) = *reinterpret_cast<const uint2 *>(hi);
+        *reinterpret_cast<uint2 *>(row + IN) = *reinterpret_cast<const uint2 *>(lo);
+      } else if constexpr (FPL == 2) {
+        *reinterpret_cast<uint32_t *>(row) = *reinterpret_cast<const uint32_t *>(hi);
+        *reinterpret_cast<uint32_t *>(row + IN) = *reinterpret_cast<const uint32_t *>(lo);
+      } else {
+        row[0] = hi[0];
+        row[IN] = lo[0];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) { a[c] = an[c]; an[c] = an2[c]; }
+    dv[0] = dn[0]; dv[1] = dn[1]; dv[2] = dn[2];
+  }
+
+  // ---- per-CTA combine in a fixed warp order (deterministic), then one partial per CTA -------------------------
+  for (int wv = 0; wv < 8; ++wv) {
+    __syncthreads();
+    if (warp == wv) {
+#pragma unroll
+      for (int c = 0; c < FPL; ++c)
+#pragma unroll
+        for (int j = 0; j < OLP; ++j) {
+          float *slot = &red[(lane * FPL + c) * OLP + j];
+          *slot = (wv == 0) ? acc[c][j] : *slot + acc[c][j];
+        }
+    }
+  }
+  __syncthreads();
+  float *dst = p.partial + (size_t)blockIdx.x * (size_t)(IN + 1) * OL; // the bias row was written by tail_fwd_kernel
+  for (int e = threadIdx.x; e < IN * OL; e += blockDim.x) {
+    const int i = e / OL, j = e - i * OL;
+    dst[e] = red[i * OLP + j];
+  }
+}
+
+template <int FPL> int launch_tail(b200_ctx *ctx, const TailParams &p, int grid, cudaStream_t st) {
+  if (p.out == 10) {
+    { ProfScope ps(ctx, "tail_fwd"); B200_LAUNCH((tail_fwd_kernel<FPL, 10>), grid, 256, 0, st, p); }
+    { ProfScope ps(ctx, "tail_bwd"); B200_LAUNCH((tail_bwd_kernel<FPL, 10>), grid, 256, 0, st, p); }
+  } else {
+    { ProfScope ps(ctx, "tail_fwd"); B200_LAUNCH((tail_fwd_kernel<FPL, 12>), grid, 256, 0, st, p); }
+    { ProfScope ps(ctx, "tail_bwd"); B200_LAUNCH((tail_bwd_kernel<FPL, 12>), grid, 256, 0, st, p); }
+  }
+  return B200_OK;
+}
+
+} // namespace
+
+bool tail_applicable(const b200_net *net) {
+  const char *env = std::getenv("B200_TAIL"); // debugging aid, read per call: 0 = per-layer kernels
+  if (env && std::atoi(env) == 0) return false;
+  const int L = net->nlayers();
+  if (L < 2) return false;
+  const int in = net->dims[L - 1], out = net->dims[L];
+  return out <= 12 && (in == 32 || in == 64 || in == 128) && net->ldd[L - 2] == in;
+}
+
+// Runs the last layer forward, loss, delta_L, delta_{L-1} and the [dW_L; db_L] partials. Requires net_ensure(batch) and the
+// penultimate activations in net->act[L-2]. want16: also (or, with !want32, only) write delta_{L-1} as scaled fp16 {hi | lo}
+// into net->delta16 for the fp16 dW GEMM of layer L-2 (gemm_dw16.cu), with 1 / scale in net->scale16_inv.
+int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16) {
+  const int L = net->nlayers();
+  const int in = net->dims[L - 1], out = net->dims[L];
+  if (!net->amax_part) {
+    B200_CUDA(cudaMalloc(&net->amax_part, sizeof(float) * 2 * net->ctx->num_sms));
+    B200_CUDA(cudaMalloc(&net->scale16_inv, sizeof(float)));
+  }
+  if (want16 && net->delta16_cap < batch) {
+    if (net->delta16) cudaFree(net->delta16);
+    net->delta16 = nullptr;
+    B200_CUDA(cudaMalloc(&net->delta16, sizeof(__half) * 2 * (size_t)in * net->cap));
+    net->delta16_cap = net->cap;
+  }
+  TailParams p{};
+  p.A = net->act[L - 2];
+  p.W = params + net->offs[L - 1];
+  p.T = t;
+  p.out_last = net->act[L - 1];
+  p.delta_last = net->delta[L - 1];
+  p.delta_prev = want32 ? net->delta[L - 2] : nullptr;
+  p.d16 = want16 ? (__half *)net->delta16 : nullptr;
+  p.scale16_inv = net->scale16_inv;
+  p.amax_part = net->amax_part;
+  p.partial = net->partials + net->part_off[L - 1];
+  p.loss_part = net->loss_part;
+  p.batch = batch;
+  p.out = out; p.ldd = net->ldd[L - 1];
+  p.act_last = net->acts[L - 1]; p.act_prev = net->acts[L - 2];
+  p.inv_batch = inv_batch;
+  const int max_grid = std::min(std::min(net->skinny_splits[L - 1], net->loss_part_cap), 2 * net->ctx->num_sms);
+  int grid = std::max(1, std::min(max_grid, ceil_div(batch, 32)));
+  p.chunk = ceil_div(ceil_div(batch, grid), 16) * 16;
+  grid = ceil_div(batch, p.chunk);
+  p.n_amax = grid;
+  if (in == 128) B200_TRY(launch_tail<4>(net->ctx, p, grid, net->ctx->stream));
+  else if (in == 64) B200_TRY(launch_tail<2>(net->ctx, p, grid, net->ctx->stream));
+  else B200_TRY(launch_tail<1>(net->ctx, p, grid, net->ctx->stream));
+  net->splits_used[L - 1] = grid;
+  net->loss_part_n = grid;
+  return B200_OK;
+}
+
+void tail_release(b200_net *net) {
+  if (net->amax_part) cudaFree(net->amax_part);
+  if (net->scale16_inv) cudaFree(net->scale16_inv);
+  if (net->delta16) cudaFree(net->delta16);
+  net->amax_part = net->scale16_inv = nullptr;
+  net->delta16 = nullptr;
+  net->delta16_cap = 0;
+}
+
+} // namespace b200
