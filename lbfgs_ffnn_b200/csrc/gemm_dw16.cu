@@ -83,7 +83,8 @@ __device__ __forceinline__ void u8x4_to_h4_d(uint32_t w, uint32_t &lo, uint32_t 
 
 template <int NB>
 __global__ void __launch_bounds__(kDThreads, 1)
-dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const Dw16Params p) {
+dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmOut,
+            const Dw16Params p) {
   using Plan = DPlan<NB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -132,8 +133,8 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(raw_empty(s), ph ^ 1);
-        mbar_expect_tx(raw_full(s), nmt * kDRawTile);
-        for (int t = 0; t < nmt; ++t) tma_load_2d(raw_a(s) + t * kDRawTile, &tmX, raw_full(s), m0 + t * kDM, kb * kDK);
+        mbar_expect_tx(raw_full(s), kDRawBytes); // ONE box {256 feature bytes, 32 samples}: 256-byte contiguous DRAM segments
+        tma_load_2d(raw_a(s), &tmX, raw_full(s), m0, kb * kDK);
         if (++s == kDNR) { s = 0; ph ^= 1; }
       }
     }
@@ -157,12 +158,13 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       const uint64_t dA0 = desc_mn16(conv_a(0)), dB0 = desc_mn16(b_a(0));
       int s = 0;
       uint32_t ph = 0;
-      long long waited = 0;
+      long long waited = 0, waited_b = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(conv_full(s), ph);
+        const long long t1 = p.dbg ? clock64() : 0;
         mbar_wait(b_full(s), ph);
-        if (p.dbg) waited += clock64() - t0;
+        if (p.dbg) { waited += t1 - t0; waited_b += clock64() - t1; }
         tc_fence_after();
         const uint64_t da = dA0 + (uint64_t)(s * (kDConvBytes >> 4)), db = dB0 + (uint64_t)(s * (Plan::kBStage >> 4));
 #pragma unroll
@@ -178,7 +180,7 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         if (++s == kDNS) { s = 0; ph ^= 1; }
       }
       umma_commit(acc_full);
-      if (p.dbg) p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = waited;
+      if (p.dbg) { p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = waited; p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + 2] = waited_b; }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -198,7 +200,7 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       uint4 w[2 * kDMT];
 #pragma unroll
       for (int i = 0; i < 2 * kDMT; ++i)
-        if ((i >> 1) < nmt) w[i] = *reinterpret_cast<const uint4 *>(raw + (i >> 1) * kDRawTile + (rb + 16 * (i & 1)) * kDM + q * 16);
+        if ((i >> 1) < nmt) w[i] = *reinterpret_cast<const uint4 *>(raw + (rb + 16 * (i & 1)) * (kDMT * kDM) + (i >> 1) * kDM + q * 16);
 #pragma unroll
       for (int i = 0; i < 2 * kDMT; ++i) {
         if ((i >> 1) < nmt) {
@@ -236,11 +238,14 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       tc_fence_after();
     }
     const float sinv = __ldg(p.scale_inv);
+    // Each warp stages [32 feature rows][32 outputs] blocks in the (now idle) pipeline memory and one lane issues a 3-D TMA
+    // tile store {output, feature, split}: full lines, and rows past feature `in` are clipped by the tensor map.
+    const uint32_t stage_a = base + (warp - 4) * 4096;
+    uint8_t *stage_p = bp + (warp - 4) * 4096;
     for (int t2 = 0; t2 < nmt; ++t2) {
       const int row = (warp & 3) * 32 + lane, f = m0 + t2 * kDM + row;
       const float scale = (f < p.in_dim) ? sinv * (1.0f / 255.0f) : sinv;
       const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t2 * NB);
-      float *dstrow = p.partial + (unsigned long long)blockIdx.y * p.partial_stride + (unsigned long long)f * OUT;
       for (int c0 = 0; c0 < OUT; c0 += 32) {
         uint32_t v[32], w[32];
         if (nkb > 0) {
@@ -250,19 +255,26 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = 0u; w[j] = 0u; }
         }
-        if (f <= p.in_dim) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq) {
-            float4 r;
-            r.x = (__uint_as_float(v[4 * qq + 0]) + __uint_as_float(w[4 * qq + 0])) * scale;
-            r.y = (__uint_as_float(v[4 * qq + 1]) + __uint_as_float(w[4 * qq + 1])) * scale;
-            r.z = (__uint_as_float(v[4 * qq + 2]) + __uint_as_float(w[4 * qq + 2])) * scale;
-            r.w = (__uint_as_float(v[4 * qq + 3]) + __uint_as_float(w[4 * qq + 3])) * scale;
-            if (c0 + 4 * qq + 3 < OUT) *reinterpret_cast<float4 *>(dstrow + c0 + 4 * qq) = r;
-          }
+        for (int qq = 0; qq < 8; ++qq) {
+          float4 r;
+          r.x = (__uint_as_float(v[4 * qq + 0]) + __uint_as_float(w[4 * qq + 0])) * scale;
+          r.y = (__uint_as_float(v[4 * qq + 1]) + __uint_as_float(w[4 * qq + 1])) * scale;
+          r.z = (__uint_as_float(v[4 * qq + 2]) + __uint_as_float(w[4 * qq + 2])) * scale;
+          r.w = (__uint_as_float(v[4 * qq + 3]) + __uint_as_float(w[4 * qq + 3])) * scale;
+          *reinterpret_cast<float4 *>(stage_p + lane * 128 + ((qq ^ (lane & 7)) << 4)) = r;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmOut, stage_a, c0, m0 + t2 * kDM + (warp & 3) * 32, blockIdx.y);
+          tma_store_commit();
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();
     }
   }
   tc_fence_before();
@@ -277,6 +289,9 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map_3d_d(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
+                  unsigned box0, unsigned box1); // defined below
 
 int make_map_2d_d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsigned long long dim0, unsigned long long dim1,
                   unsigned long long stride_bytes, unsigned box0, unsigned box1, CUtensorMapSwizzle sw) {
@@ -304,7 +319,31 @@ int make_map_2d_d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsi
   return B200_OK;
 }
 
-template <int NB> int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const Dw16Params &p, dim3 grid, cudaStream_t st) {
+// fp32 {dim0 contiguous, dim1, dim2} with dense strides, box {box0, box1, 1}, SWIZZLE_128B (the split-K partial tensor)
+int make_map_3d_d(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
+                  unsigned box0, unsigned box1) {
+  void *f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {dim0 * 4, dim0 * dim1 * 4};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((EncodeTiledFn)f)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d): dims %llu x %llu x %llu ptr %p", (int)r, dim0, dim1, dim2, ptr);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+template <int NB>
+int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap &tout, const Dw16Params &p, dim3 grid, cudaStream_t st) {
   auto kern = dw16_kernel<NB>;
   constexpr int smem = DPlan<NB>::kTotal;
   static bool attr_set = false;
@@ -320,7 +359,7 @@ template <int NB> int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, 
     B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 4 * 1024, st));
     pp.dbg = dbg;
   }
-  kern<<<grid, kDThreads, smem, st>>>(tx, td, pp);
+  kern<<<grid, kDThreads, smem, st>>>(tx, td, tout, pp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) {
@@ -328,10 +367,10 @@ template <int NB> int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, 
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     const int n = std::min(1024, (int)(grid.x * grid.y));
-    double tot = 0, iw = 0;
-    for (int i = 0; i < n; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; }
-    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting %.0f\n", NB, grid.x, grid.y,
-            p.kb_per_split, tot / n, iw / n);
+    double tot = 0, iw = 0, ib = 0;
+    for (int i = 0; i < n; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2]; }
+    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting: converted X %.0f, delta %.0f\n", NB,
+            grid.x, grid.y, p.kb_per_split, tot / n, iw / n, ib / n);
   }
   return B200_OK;
 }
@@ -360,8 +399,8 @@ int dw16_layer(b200_net *net, const uint8_t *xq, long batch, bool *done) {
   *done = false;
   if (!xq || !net->delta16) return B200_OK;
   const int K0 = net->dims[0], N0 = net->dims[1];
-  CUtensorMap tx, td;
-  B200_TRY(make_map_2d_d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K0, batch, K0, kDM, kDK, CU_TENSOR_MAP_SWIZZLE_NONE));
+  CUtensorMap tx, td, tout;
+  B200_TRY(make_map_2d_d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K0, batch, K0, kDMT * kDM, kDK, CU_TENSOR_MAP_SWIZZLE_NONE));
   B200_TRY(make_map_2d_d(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->delta16, 2 * N0, batch, (unsigned long long)2 * N0 * 2, 64, kDK,
                          CU_TENSOR_MAP_SWIZZLE_128B));
   int splits = 1;
@@ -373,8 +412,9 @@ int dw16_layer(b200_net *net, const uint8_t *xq, long batch, bool *done) {
   p.partial_stride = (unsigned long long)(K0 + 1) * N0;
   p.scale_inv = net->scale16_inv;
   const dim3 grid(ceil_div(K0 + 1, kDMT * kDM), splits);
-  if (N0 == 128) B200_TRY(launch_dw16<256>(tx, td, p, grid, net->ctx->stream));
-  else B200_TRY(launch_dw16<128>(tx, td, p, grid, net->ctx->stream));
+  B200_TRY(make_map_3d_d(&tout, p.partial, N0, K0 + 1, splits, 32, 32));
+  if (N0 == 128) B200_TRY(launch_dw16<256>(tx, td, tout, p, grid, net->ctx->stream));
+  else B200_TRY(launch_dw16<128>(tx, td, tout, p, grid, net->ctx->stream));
   net->splits_used[0] = splits;
   *done = true;
   return B200_OK;

@@ -36,9 +36,11 @@ constexpr int kFM = 128;                   // samples per tile = UMMA M
 constexpr int kFK = 64;                    // K elements per stage (64 uint8 -> 64 fp16 = one 128-byte swizzle row)
 constexpr int kRawBytes = kFM * kFK;       // 8 KB
 constexpr int kConvBytes = kFM * kFK * 2;  // 16 KB
-constexpr int kNR = 4, kNC = 4, kNW = 4; // converted-X and weight rings share one stage index, so ONE tcgen05.commit frees both
-constexpr int kFThreads = 640;
-constexpr int kEpiWarp0 = 4, kEpiThreads = 256, kConvWarp0 = 12, kConvThreads = 256; // 8 converter warps: 4 were the bottleneck
+constexpr int kNR = 4, kNC = 3, kNW = 3; // converted-X and weight rings share one stage index, so ONE tcgen05.commit frees both
+constexpr int kFThreads = 512;
+constexpr int kEpiWarp0 = 4, kEpiThreads = 256, kConvWarp0 = 12, kConvThreads = 128;
+constexpr int kConvGroups = kConvThreads / 128; // groups of four warps taking alternate K blocks (one is enough: measured)
+constexpr int kStageOutBytes = 32 * 128;      // per epilogue warp: one [32 rows][32 floats] TMA-store box
 
 struct F16Params {
   int rows_valid, cols_valid, k_total, k_blocks, tiles;
@@ -47,6 +49,7 @@ struct F16Params {
   const float *colscale; // [N]: 1 / (255 s_o)
   float *out;            // activations [rows][ld_out]
   long ld_out;
+  int dry;               // B200_FWD16_DRY (timing experiments only): 1 = converters skip the conversion, 2 = epilogue skips its stores
   long long *dbg;        // B200_TC_TIMING: per CTA {total, epilogue busy, epilogue waiting for the accumulator, issuer waiting}
 };
 
@@ -56,7 +59,8 @@ template <int BN, bool X2> struct FPlan {
   static constexpr int kOffConv = 0;
   static constexpr int kOffW = kNC * kConvBytes;
   static constexpr int kOffRaw = kOffW + kNW * kWStage;
-  static constexpr int kOffCol = kOffRaw + kNR * kRawBytes; // colscale[128], bias[128]
+  static constexpr int kOffOut = kOffRaw + kNR * kRawBytes; // epilogue staging tiles (TMA store), 1024-byte aligned
+  static constexpr int kOffCol = kOffOut + 8 * kStageOutBytes; // colscale[128], bias[128]
   static constexpr int kOffBar = kOffCol + 1024;
   static constexpr int kTotal = kOffBar + 256 + 1024;
   static constexpr int kTmemCols = (4 * BN <= 256) ? 256 : 512;
@@ -110,7 +114,7 @@ __device__ __forceinline__ void u8x4_to_h4(uint32_t w, uint32_t &lo, uint32_t &h
 template <int BN, bool X2>
 __global__ void __launch_bounds__(kFThreads, 1)
 fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
-             const __grid_constant__ CUtensorMap tmWl, const F16Params p) {
+             const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmOut, const F16Params p) {
   using Plan = FPlan<BN, X2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,8 +141,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWh);
     if (X2) tma_prefetch_desc(&tmWl);
-    for (int s = 0; s < kNR; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), kConvThreads / 64); }
-    for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), kConvThreads / 64); mbar_init(conv_empty(s), 1); }
+    for (int s = 0; s < kNR; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 4); }
+    for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), 4); mbar_init(conv_empty(s), 1); }
     for (int s = 0; s < kNW; ++s) mbar_init(w_full(s), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), kEpiThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -233,11 +237,11 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     // Two groups of four warps take alternate K blocks: one block's wait -> load -> convert -> proxy fence -> arrive chain is
     // ~1 k clk however many threads share it, so two chains in flight are what doubles the converter's throughput.
     const int tt = threadIdx.x - kConvWarp0 * 32, grp = tt >> 7, t = tt & 127, j = t & 3, rb = t >> 2;
-    long long cw_raw = 0, cw_empty = 0;
+    long long cw_raw = 0, cw_empty = 0, cw_fence = 0, cw_work = 0;
     int n = 0; // running K-block index of this CTA (over all its tiles)
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.k_blocks; ++kb, ++n) {
-        if ((n & 1) != grp) continue;
+        if ((n % kConvGroups) != grp) continue;
         const int rs = n % kNR, cs = n % kNC;
         const uint32_t rph = (uint32_t)(n / kNR) & 1u, cph = (uint32_t)(n / kNC) & 1u;
         const long long c0 = p.dbg ? clock64() : 0;
@@ -248,6 +252,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const uint8_t *raw = bp + Plan::kOffRaw + rs * kRawBytes;
         uint8_t *dst = bp + Plan::kOffConv + cs * kConvBytes;
         uint4 w[4];
+        if (!(p.dry & 1)) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4 *>(raw + (rb + 32 * i) * kFK + j * 16);
 #pragma unroll
@@ -261,60 +266,72 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           *reinterpret_cast<uint4 *>(dst + r * 128 + (((2 * j) ^ (r & 7)) << 4)) = o0;
           *reinterpret_cast<uint4 *>(dst + r * 128 + (((2 * j + 1) ^ (r & 7)) << 4)) = o1;
         }
+        }
+        const long long f0 = p.dbg ? clock64() : 0;
         fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (p.dbg) cw_fence += clock64() - f0;
         __syncwarp();
         if (lane == 0) { // one arrival per warp
           mbar_arrive(conv_full(cs));
           mbar_arrive(raw_empty(rs));
         }
+        if (p.dbg) cw_work += clock64() - f0;
       }
     }
-    if (p.dbg && tt == 0) { p.dbg[8 * blockIdx.x + 6] = cw_raw; p.dbg[8 * blockIdx.x + 7] = cw_empty; }
+    if (p.dbg && tt == 0) { p.dbg[8 * blockIdx.x + 6] = cw_raw; p.dbg[8 * blockIdx.x + 7] = cw_empty; p.dbg[8 * 1024 + 2 * blockIdx.x] = cw_fence; p.dbg[8 * 1024 + 2 * blockIdx.x + 1] = cw_work; }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue warps 4-11: warp w owns TMEM lanes (= samples) 32*(w%4).., the two warps of a lane quarter split the
-    // 32-column chunks. A thread owns one 128-byte line of the output row per chunk: eight 16-byte stores from registers
-    // (no shared-memory transpose; the line is completed in L2) ==================================================
+    // 32-column chunks. Each warp stages its [32 rows][32 floats] block in shared memory (SWIZZLE_128B, conflict-free 16-byte
+    // stores) and ONE lane issues a TMA tile store: full 128-byte lines, asynchronous, rows past the batch clipped by the
+    // tensor map. (Per-thread row stores from registers hit 32 different lines per instruction and throttled the whole SM:
+    // 24 k of 50 k clk per CTA.) ===================================================================================
     auto epilogue = [&](auto act_tag) {
       constexpr int ACT = decltype(act_tag)::value;
       const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
-      const int row = q * 32 + lane;
       const float4 *colsc4 = reinterpret_cast<const float4 *>(colsc), *bias4 = reinterpret_cast<const float4 *>(biass);
+      const uint32_t stage_a = base + Plan::kOffOut + (warp - kEpiWarp0) * kStageOutBytes;
+      uint8_t *stage_p = bp + Plan::kOffOut + (warp - kEpiWarp0) * kStageOutBytes;
       long long busy = 0, waiting = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        const long grow = (long)tile * kFM + row;
-        const bool row_ok = grow < p.rows_valid;
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(tm_full(buf), (it >> 1) & 1);
         tc_fence_after();
         const long long t1 = p.dbg ? clock64() : 0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) { // 16 columns at a time keeps this warp role under the 96 registers 640 threads leave
-          const int c0 = half * 16 + 32 * i;
+        for (int i = 0; i < BN / 64; ++i) {
+          const int c0 = half * 32 + 64 * i;
           if (c0 < p.cols_valid) {
-            uint32_t v[16];
-            tmem_ld16_nowait(lane_addr + c0, v);
+            uint32_t v[32];
+            tmem_ld32_nowait(lane_addr + c0, v);
             if (X2) { // hi + lo accumulators, added in RN fp32
-              uint32_t w[16];
-              tmem_ld16_nowait(lane_addr + BN + c0, w);
+              uint32_t w[32];
+              tmem_ld32_nowait(lane_addr + BN + c0, w);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
             } else {
               tmem_ld_wait();
             }
-            float4 *dst = reinterpret_cast<float4 *>(p.out + grow * p.ld_out + c0);
+            if (lane == 0) tma_store_wait_read(); // the previous block of this warp has left the staging tile
+            __syncwarp();
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < 8; ++qq) {
               const float4 s4 = colsc4[c0 / 4 + qq], b4 = bias4[c0 / 4 + qq];
               float4 r;
               r.x = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 0]), s4.x, b4.x));
               r.y = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 1]), s4.y, b4.y));
               r.z = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 2]), s4.z, b4.z));
               r.w = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 3]), s4.w, b4.w));
-              if (row_ok) dst[qq] = r;
+              *reinterpret_cast<float4 *>(stage_p + lane * 128 + ((qq ^ (lane & 7)) << 4)) = r;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(p.dry & 2)) {
+              tma_store_2d(&tmOut, stage_a, c0, tile * kFM + q * 32);
+              tma_store_commit();
             }
           }
         }
@@ -323,6 +340,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(tm_empty(buf));
         if (p.dbg) { const long long t2 = clock64(); waiting += t1 - t0; busy += t2 - t1; }
       }
+      if (lane == 0) tma_store_wait_all();
       if (p.dbg && threadIdx.x == kEpiWarp0 * 32) { p.dbg[8 * blockIdx.x + 1] = busy; p.dbg[8 * blockIdx.x + 2] = waiting; }
     };
     if (p.act == B200_ACT_RELU) epilogue(IntTag<B200_ACT_RELU>{});
@@ -423,7 +441,8 @@ int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsign
 }
 
 template <int BN, bool X2>
-int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const F16Params &p, int grid, cudaStream_t st) {
+int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const CUtensorMap &tout, const F16Params &p, int grid,
+                 cudaStream_t st) {
   auto kern = fwd16_kernel<BN, X2>;
   constexpr int smem = FPlan<BN, X2>::kTotal;
   static bool attr_set = false;
@@ -434,24 +453,27 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
   static long long *dbg = nullptr;
   static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
   F16Params pp = p;
+  { const char *e = std::getenv("B200_FWD16_DRY"); pp.dry = e ? std::atoi(e) : 0; }
   if (timing) {
-    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 1024));
-    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * 1024, st));
+    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 10 * 1024));
+    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 10 * 1024, st));
     pp.dbg = dbg;
   }
-  kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, pp);
+  kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, tout, pp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) {
-    std::vector<long long> h(8 * 1024);
+    std::vector<long long> h(10 * 1024);
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < grid; ++i)
       for (int j = 0; j < 8; ++j) a[j] += (double)h[8 * i + j] / grid;
+    double cf = 0, cw = 0;
+    for (int i = 0; i < grid; ++i) { cf += (double)h[8 * 1024 + 2 * i] / grid; cw += (double)h[8 * 1024 + 2 * i + 1] / grid; }
     fprintf(stderr, "[fwd16 timing] BN %d x2 %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: conv %.0f, "
-            "weights %.0f, tmem %.0f | converter waits: raw %.0f, conv slot %.0f\n",
-            BN, (int)X2, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+            "weights %.0f, tmem %.0f | converter group 0 waits: raw %.0f, conv slot %.0f; proxy fence %.0f, fence..arrive %.0f\n",
+            BN, (int)X2, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], cf, cw);
   }
   return B200_OK;
 }
@@ -480,13 +502,15 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t
     B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, st, W, K, N, ldk, 1.0f / 255.0f, (__half *)net->w16h,
                 (__half *)net->w16l, net->colscale);
   }
-  CUtensorMap tx, twh, twl;
+  CUtensorMap tx, twh, twl, tout;
   B200_TRY(make_map_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K, batch, K, kFK, kFM, CU_TENSOR_MAP_SWIZZLE_NONE));
   const unsigned bn = N > 64 ? 128 : 64;
   B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16h, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
                        CU_TENSOR_MAP_SWIZZLE_128B));
   B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16l, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
                        CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, net->act[0], N, batch, (unsigned long long)N * 4, 32, 32,
+                       CU_TENSOR_MAP_SWIZZLE_128B)); // activations [batch][N], stored as [32 rows][32 floats] boxes
   F16Params p{};
   p.rows_valid = (int)batch; p.cols_valid = N; p.k_total = K;
   p.k_blocks = ceil_div(K, kFK);
@@ -497,11 +521,11 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t
   p.out = net->act[0]; p.ld_out = N;
   const int grid = std::min(net->ctx->num_sms, p.tiles);
   if (bn == 128) {
-    if (x2) B200_TRY((launch_fwd16<128, true>(tx, twh, twl, p, grid, st)));
-    else B200_TRY((launch_fwd16<128, false>(tx, twh, twl, p, grid, st)));
+    if (x2) B200_TRY((launch_fwd16<128, true>(tx, twh, twl, tout, p, grid, st)));
+    else B200_TRY((launch_fwd16<128, false>(tx, twh, twl, tout, p, grid, st)));
   } else {
-    if (x2) B200_TRY((launch_fwd16<64, true>(tx, twh, twl, p, grid, st)));
-    else B200_TRY((launch_fwd16<64, false>(tx, twh, twl, p, grid, st)));
+    if (x2) B200_TRY((launch_fwd16<64, true>(tx, twh, twl, tout, p, grid, st)));
+    else B200_TRY((launch_fwd16<64, false>(tx, twh, twl, tout, p, grid, st)));
   }
   *done = true;
   return B200_OK;

@@ -42,7 +42,7 @@ __device__ __forceinline__ void st4(float *p, size_t i, size_t n, bool vec, floa
 // RPW = rows per warp (compile-time so the accumulators stay in registers).
 // ------------------------------------------------------------------------------------------------
 template <int RPW, bool PAIR>
-__global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs a) {
+__device__ __forceinline__ void dots_body(const DotsArgs &a) {
   __shared__ __align__(16) double sh_g[kDotsTile];
   __shared__ __align__(16) double sh_s[PAIR ? kDotsTile : 2];
   __shared__ __align__(16) double sh_y[PAIR ? kDotsTile : 2];
@@ -171,18 +171,41 @@ __global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs
   gg = block_sum(gg, sh_red);
   if (tid == 0 && a.row_begin == 0) out[kDotsCols * mp] = gg;
 }
+template <int RPW, bool PAIR>
+__global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs a) {
+  dots_body<RPW, PAIR>(a);
+}
 
 // ------------------------------------------------------------------------------------------------
 // (2) one CTA: reduce the per-CTA partials (fixed order => deterministic), update the Gram blocks for
 // the slot written by (1), curvature test + ring advance, then the two-loop recurrences in fp64.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
-  extern __shared__ double sh[]; // tot[ncols] | alpha[mp] | beta[mp] | SY[mp*mp] | YY[mp*mp] | rho, sg, yg [mp] | phys[mp] (int)
+// Per-CTA results of the solve, kept in shared memory for a fused apply phase.
+struct SolveLocal {
+  int k;
+  double cg, alpha0;
+  double *cs, *cy; // [mp] (shared memory)
+  int *phys;       // [mp]
+};
+
+// `leader` CTAs write the device state; in the fused direction kernel every CTA runs this redundantly on the same inputs
+// (identical results) so that no second grid-wide barrier is needed, and only CTA 0 is the leader. head_in / count_in: the
+// ring header as it was BEFORE this direction (the leader overwrites it while other CTAs may still be reading).
+__device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool leader, int head_in, int count_in, SolveLocal *res) {
+  // sh: tot[ncols] | alpha[mp] | dlt[mp] | cs[mp] | cy[mp] | (staged) SY[mp*mp] | YY[mp*mp] | rho, sg, yg [mp] | phys[mp] (int)
   LbfgsHeader *h = a.st.h;
   const int mp = h->mp, mod = h->mod;
   const int ncols = kDotsCols * mp + 1;
-  double *tot = sh, *alpha = sh + ncols, *dlt = alpha + mp;
-  __shared__ int s_head, s_count, s_w;
+  double *tot = sh, *alpha = sh + ncols, *dlt = alpha + mp, *lcs = dlt + mp, *lcy = lcs + mp;
+  __shared__ int s_head, s_count, s_w, s_k;
+  __shared__ double s_cg, s_alpha0;
+  const bool stage = a.stage_gram != 0;
+  double *SYp = a.st.SY, *YYp = a.st.YY, *rhop = a.st.rho, *sgp = a.st.sg, *ygp = a.st.yg;
+  int *physp = a.st.phys;
+  if (stage) {
+    SYp = lcy + mp; YYp = SYp + mp * mp; rhop = YYp + mp * mp; sgp = rhop + mp; ygp = sgp + mp;
+    physp = reinterpret_cast<int *>(ygp + mp);
+  }
 
   // fixed-order (deterministic) reduction of the per-CTA partials: 8 threads per column, each a strided
   // slice of the blocks, combined by shuffles — ~nblocks/8 dependent loads instead of nblocks
@@ -190,20 +213,25 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
     const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     double s = 0.0;
     if (c < ncols)
-      for (int b = sub; b < a.nblocks; b += 8) s += a.partials[(size_t)b * ncols + c];
+      for (int b = sub; b < a.nblocks; b += 8) s += __ldcg(a.partials + (size_t)b * ncols + c);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     if (c < ncols && sub == 0) tot[c] = s;
   }
+  if (stage) { // everything the 2k dependent recurrence steps touch lives in shared memory (an L2 round trip per step otherwise)
+    for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { SYp[i] = a.st.SY[i]; YYp[i] = a.st.YY[i]; }
+    for (int i = threadIdx.x; i < mp; i += blockDim.x) { rhop[i] = a.st.rho[i]; sgp[i] = a.st.sg[i]; ygp[i] = a.st.yg[i]; }
+  }
   if (threadIdx.x == 0) {
-    int head = h->head, count = h->count;
+    int head = head_in, count = count_in;
     if (a.reset_first) head = count = 0;
     s_head = head; s_count = count; s_w = head;
   }
   __syncthreads();
   const int w = s_w;
   const bool pair = a.mode != DOTS_NONE;
+  const bool wr_global = leader && stage; // staged: mirror the updates into the device state; unstaged: the pointers ARE the state
 
   // Gram update for every row the dots kernel visited (valid rows + w)
   for (int p = threadIdx.x; p < mod; p += blockDim.x) {
@@ -211,71 +239,81 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
     if (rel < 0) rel += mod;
     const bool valid = rel < s_count;
     if (!(valid || (pair && p == w))) continue;
-    a.st.sg[p] = tot[p * kDotsCols + 0];
-    a.st.yg[p] = tot[p * kDotsCols + 2];
-    if (pair) {
-      a.st.SY[p * mp + w] = tot[p * kDotsCols + 1]; // s_p . y_w
-      a.st.SY[w * mp + p] = tot[p * kDotsCols + 3]; // s_w . y_p
-      a.st.YY[p * mp + w] = tot[p * kDotsCols + 4];
-      a.st.YY[w * mp + p] = tot[p * kDotsCols + 4];
+    const double v0 = tot[p * kDotsCols + 0], v1 = tot[p * kDotsCols + 1], v2 = tot[p * kDotsCols + 2],
+                 v3 = tot[p * kDotsCols + 3], v4 = tot[p * kDotsCols + 4];
+    if (stage || leader) {
+      sgp[p] = v0;
+      ygp[p] = v2;
+      if (pair) {
+        SYp[p * mp + w] = v1; // s_p . y_w
+        SYp[w * mp + p] = v3; // s_w . y_p
+        YYp[p * mp + w] = v4;
+        YYp[w * mp + p] = v4;
+      }
+    }
+    if (wr_global) {
+      a.st.sg[p] = v0;
+      a.st.yg[p] = v2;
+      if (pair) {
+        a.st.SY[p * mp + w] = v1;
+        a.st.SY[w * mp + p] = v3;
+        a.st.YY[p * mp + w] = v4;
+        a.st.YY[w * mp + p] = v4;
+      }
     }
   }
   __syncthreads();
 
   if (threadIdx.x == 0) {
     int head = s_head, count = s_count, flags = 0;
+    double ys = 0.0, yy = 0.0;
     if (pair) {
-      const double ys = a.st.SY[w * mp + w];
-      h->ys_new = ys;
-      h->yy_new = a.st.YY[w * mp + w];
+      ys = SYp[w * mp + w];
+      yy = YYp[w * mp + w];
       // curvature filter y^T s > 1e-10 (src/cuda/lbfgs.cuh:161-169, src/minimizer/lbfgs.hpp:77-84)
       // S-LBFGS: |y^T s| > 1e-10 (src/minimizer/s_lbfgs.hpp:253-258)
       const bool accept = a.force_accept ? true : (a.policy == POLICY_SLBFGS ? fabs(ys) > 1e-10 : ys > 1e-10);
       if (accept) {
-        a.st.rho[w] = a.force_accept ? a.ext_rho : 1.0 / ys;
+        const double r = a.force_accept ? a.ext_rho : 1.0 / ys;
+        if (stage || leader) rhop[w] = r;
+        if (wr_global) a.st.rho[w] = r;
         head = (head + 1) % mod;
         count = min(count + 1, h->m);
         flags |= FLAG_PAIR_ACCEPTED;
       }
     }
-    h->head = head; h->count = count; h->flags = flags;
-    h->gnorm2 = tot[kDotsCols * mp];
+    if (leader) {
+      if (pair) { h->ys_new = ys; h->yy_new = yy; }
+      h->head = head; h->count = count; h->flags = flags;
+      h->gnorm2 = tot[kDotsCols * mp];
+    }
     s_head = head; s_count = count;
   }
   __syncthreads();
 
-  // two-loop recurrences on the Gram blocks: warp 0, lanes parallel over the inner sums. Everything the 2k dependent
-  // steps touch is staged in shared memory first: with the Gram blocks in global memory every step paid an L2 round trip
-  // (~0.3 us), i.e. most of this kernel's time.
-  // (histories too long for the staging area, m > ~100, read the global copies as before)
-  const double *sSY = a.st.SY, *sYY = a.st.YY, *srho = a.st.rho, *ssg = a.st.sg, *syg = a.st.yg;
-  int *sphys = a.st.phys;
-  if (a.stage_gram) {
-    double *tSY = dlt + mp, *tYY = tSY + mp * mp, *trho = tYY + mp * mp, *tsg = trho + mp, *tyg = tsg + mp;
-    for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { tSY[i] = a.st.SY[i]; tYY[i] = a.st.YY[i]; }
-    for (int i = threadIdx.x; i < mp; i += blockDim.x) { trho[i] = a.st.rho[i]; tsg[i] = a.st.sg[i]; tyg[i] = a.st.yg[i]; }
-    sSY = tSY; sYY = tYY; srho = trho; ssg = tsg; syg = tyg;
-    sphys = reinterpret_cast<int *>(tyg + mp);
-  }
-  __syncthreads();
+  // two-loop recurrences on the Gram blocks: warp 0, lanes parallel over the inner sums
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const int head = s_head, k = s_count;
     const double gg = tot[kDotsCols * mp];
-    for (int i = lane; i < k; i += 32) { const int ph = ring_phys(head, k, mod, i); sphys[i] = ph; a.st.phys[i] = ph; }
+    for (int i = lane; i < k; i += 32) {
+      const int ph = ring_phys(head, k, mod, i);
+      physp[i] = ph;
+      if (wr_global) a.st.phys[i] = ph;
+    }
     __syncwarp();
     double gamma = 1.0, cg = -1.0, gdotp = -gg;
     if (k > 0) {
       for (int i = k - 1; i >= 0; --i) {
-        const int pi = sphys[i];
+        const int pi = physp[i];
         double s = 0.0;
-        for (int j = i + 1 + lane; j < k; j += 32) s += alpha[j] * sSY[pi * mp + sphys[j]];
+        for (int j = i + 1 + lane; j < k; j += 32) s += alpha[j] * SYp[pi * mp + physp[j]];
         s = warp_sum(s);
-        if (lane == 0) alpha[i] = srho[pi] * (ssg[pi] - s);
+        if (lane == 0) alpha[i] = rhop[pi] * (sgp[pi] - s);
         __syncwarp();
       }
-      const int pl = sphys[k - 1];
-      const double ys = sSY[pl * mp + pl], yy = sYY[pl * mp + pl];
+      const int pl = physp[k - 1];
+      const double ys = SYp[pl * mp + pl], yy = YYp[pl * mp + pl];
       if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
       else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
       else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
@@ -283,14 +321,14 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
         gamma = fmin(fmax(gamma, 1e-6), 1e6);
       }
       for (int i = 0; i < k; ++i) {
-        const int pi = sphys[i];
+        const int pi = physp[i];
         double s1 = 0.0, s2 = 0.0;
-        for (int j = lane; j < k; j += 32) s1 += alpha[j] * sYY[pi * mp + sphys[j]];
-        for (int j = lane; j < i; j += 32) s2 += dlt[j] * sSY[sphys[j] * mp + pi];
+        for (int j = lane; j < k; j += 32) s1 += alpha[j] * YYp[pi * mp + physp[j]];
+        for (int j = lane; j < i; j += 32) s2 += dlt[j] * SYp[physp[j] * mp + pi];
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
         if (lane == 0) {
-          const double beta = srho[pi] * (gamma * (syg[pi] - s1) + s2);
+          const double beta = rhop[pi] * (gamma * (ygp[pi] - s1) + s2);
           dlt[i] = alpha[i] - beta;
         }
         __syncwarp();
@@ -299,9 +337,10 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
       double gp = 0.0;
       for (int j = lane; j < k; j += 32) {
         const double csj = -dlt[j], cyj = gamma * alpha[j];
-        a.st.cs[j] = csj;
-        a.st.cy[j] = cyj;
-        gp += csj * ssg[sphys[j]] + cyj * syg[sphys[j]];
+        lcs[j] = csj;
+        lcy[j] = cyj;
+        if (leader) { a.st.cs[j] = csj; a.st.cy[j] = cyj; }
+        gp += csj * sgp[physp[j]] + cyj * ygp[physp[j]];
       }
       gp = warp_sum(gp);
       gdotp = cg * gg + gp;
@@ -311,33 +350,47 @@ __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
       int kk = k;
       // non-descent direction: steepest descent + history reset (src/cuda/lbfgs.cuh:97-104).
       // The CPU backend has no such check (src/minimizer/lbfgs.hpp:56-65).
-      if (a.policy == POLICY_ARMIJO && kk > 0 && !(gdotp < 0.0)) {
-        kk = 0; cg = -1.0; gdotp = -gg; gamma = 1.0;
-        h->head = 0; h->count = 0; h->flags |= FLAG_SD_FALLBACK;
-      }
-      h->k = kk; h->cg = cg; h->gdotp = gdotp; h->gamma = gamma;
+      const bool sd = a.policy == POLICY_ARMIJO && kk > 0 && !(gdotp < 0.0);
+      if (sd) { kk = 0; cg = -1.0; gdotp = -gg; gamma = 1.0; }
       const double gn = sqrt(gg);
-      h->alpha0 = a.first_iter ? fmin(1.0, 1.0 / gn) : 1.0; // lbfgs.cuh:108, lbfgs.hpp:60-61
+      const double alpha0 = a.first_iter ? fmin(1.0, 1.0 / gn) : 1.0; // lbfgs.cuh:108, lbfgs.hpp:60-61
+      if (leader) {
+        if (sd) { h->head = 0; h->count = 0; h->flags |= FLAG_SD_FALLBACK; }
+        h->k = kk; h->cg = cg; h->gdotp = gdotp; h->gamma = gamma;
+        h->alpha0 = alpha0;
+      }
+      s_k = kk; s_cg = cg; s_alpha0 = alpha0;
     }
   }
+  __syncthreads();
+  if (res) { res->k = s_k; res->cg = s_cg; res->alpha0 = s_alpha0; res->cs = lcs; res->cy = lcy; res->phys = physp; }
+}
+
+__global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
+  extern __shared__ double sh[];
+  solve_body(a, sh, true, a.st.h->head, a.st.h->count, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
 // (3) p = cg g + sum_j cs_j s_j + cy_j y_j  (fp64 accumulate, one rounding); x_prev = x; x += alpha0 p
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
-  __shared__ double s_cs[kMaxSlots], s_cy[kMaxSlots];
-  __shared__ int s_ph[kMaxSlots];
-  const LbfgsHeader *h = a.st.h;
-  const int k = h->k;
-  if (threadIdx.x < k) {
-    s_cs[threadIdx.x] = a.st.cs[threadIdx.x] * a.sign;
-    s_cy[threadIdx.x] = a.st.cy[threadIdx.x] * a.sign;
-    s_ph[threadIdx.x] = a.st.phys[threadIdx.x];
-  }
-  __syncthreads();
-  const double cg = h->cg * a.sign;
-  const float alpha0 = (a.step != 0.0f) ? a.step : (float)h->alpha0;
+// COHERENT: the history slot written earlier in the SAME kernel (fused direction) must not come through the read-only path
+template <bool COHERENT> __device__ __forceinline__ float4 ld4c(const float *p, size_t i, size_t n, bool vec) {
+  if constexpr (!COHERENT) return ld4(p, i, n, vec);
+  if (vec && i + 3 < n) return __ldcg(reinterpret_cast<const float4 *>(p + i));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i + 0 < n) v.x = __ldcg(p + i + 0);
+  if (i + 1 < n) v.y = __ldcg(p + i + 1);
+  if (i + 2 < n) v.z = __ldcg(p + i + 2);
+  if (i + 3 < n) v.w = __ldcg(p + i + 3);
+  return v;
+}
+
+template <bool COHERENT>
+__device__ __forceinline__ void apply_body(const ApplyArgs &a, int k, double cg_in, double alpha0_in, const double *s_cs,
+                                           const double *s_cy, const int *s_ph) {
+  const double cg = cg_in * a.sign;
+  const float alpha0 = (a.step != 0.0f) ? a.step : (float)alpha0_in;
   const bool vec = ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.S) |
                      reinterpret_cast<uintptr_t>(a.Y) | reinterpret_cast<uintptr_t>(a.p) |
                      reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.x_prev) |
@@ -346,12 +399,12 @@ __global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
   const size_t nv = (a.n + 3) / 4;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
     const size_t i = v * 4;
-    const float4 g4 = ld4(a.g, i, a.n, vec);
+    const float4 g4 = ld4c<COHERENT>(a.g, i, a.n, vec);
     double r0 = cg * g4.x, r1 = cg * g4.y, r2 = cg * g4.z, r3 = cg * g4.w;
     for (int j = 0; j < k; ++j) {
-      const float4 s4 = ld4(a.S + (size_t)s_ph[j] * a.ld, i, a.n, vec);
-      const float4 y4 = ld4(a.Y + (size_t)s_ph[j] * a.ld, i, a.n, vec);
-      const double cs = s_cs[j], cy = s_cy[j];
+      const float4 s4 = ld4c<COHERENT>(a.S + (size_t)s_ph[j] * a.ld, i, a.n, vec);
+      const float4 y4 = ld4c<COHERENT>(a.Y + (size_t)s_ph[j] * a.ld, i, a.n, vec);
+      const double cs = s_cs[j] * a.sign, cy = s_cy[j] * a.sign;
       r0 = fma(cs, (double)s4.x, r0); r1 = fma(cs, (double)s4.y, r1);
       r2 = fma(cs, (double)s4.z, r2); r3 = fma(cs, (double)s4.w, r3);
       r0 = fma(cy, (double)y4.x, r0); r1 = fma(cy, (double)y4.y, r1);
@@ -360,7 +413,7 @@ __global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
     const float4 p4 = make_float4((float)r0, (float)r1, (float)r2, (float)r3);
     st4(a.p, i, a.n, vec, p4);
     if (a.x) {
-      const float4 x4 = ld4(a.x, i, a.n, vec);
+      const float4 x4 = ld4c<COHERENT>(a.x, i, a.n, vec);
       if (a.x_prev) st4(a.x_prev, i, a.n, vec, x4);
       // one rounding per element like the reference's copy + axpy (lbfgs.cuh:116-117, cuBLAS axpy is an FMA)
       const float4 xn = make_float4(fmaf(alpha0, p4.x, x4.x), fmaf(alpha0, p4.y, x4.y), fmaf(alpha0, p4.z, x4.z),
@@ -369,6 +422,62 @@ __global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
       if (a.x_copy) st4(a.x_copy, i, a.n, vec, xn);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
+  __shared__ double s_cs[kMaxSlots], s_cy[kMaxSlots];
+  __shared__ int s_ph[kMaxSlots];
+  const LbfgsHeader *h = a.st.h;
+  const int k = h->k;
+  if (threadIdx.x < k) {
+    s_cs[threadIdx.x] = a.st.cs[threadIdx.x];
+    s_cy[threadIdx.x] = a.st.cy[threadIdx.x];
+    s_ph[threadIdx.x] = a.st.phys[threadIdx.x];
+  }
+  if (k > (int)blockDim.x)
+    for (int j = blockDim.x + threadIdx.x; j < k; j += blockDim.x) { s_cs[j] = a.st.cs[j]; s_cy[j] = a.st.cy[j]; s_ph[j] = a.st.phys[j]; }
+  __syncthreads();
+  apply_body<false>(a, k, h->cg, h->alpha0, s_cs, s_cy, s_ph);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1)+(2)+(3) in ONE launch (histories of <= 32 slots, one GPU): dots pass -> grid-wide barrier -> every CTA reduces the
+// partials and runs the O(k^2) solve redundantly (identical inputs, identical results; only CTA 0 writes the device state)
+// -> apply pass on the same tiles the CTA streamed in phase 1. Saves two launches and their dependency latency per direction;
+// needs all CTAs co-resident (checked on the host with the occupancy API).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) { // bar[0] arrivals, bar[1] generation
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned *gen = bar + 1;
+    const unsigned g = *gen; // read before arriving: it can only change after EVERY CTA has arrived
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      bar[0] = 0u; // ready for the next launch
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) __nanosleep(40);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int RPW, bool PAIR>
+__global__ void __launch_bounds__(kDotsThreads) lbfgs_direction_kernel(const DotsArgs da, const SolveArgs sa, const ApplyArgs aa,
+                                                                      unsigned *bar) {
+  extern __shared__ double sh[];
+  __shared__ int s_head0, s_count0;
+  if (threadIdx.x == 0) { s_head0 = da.st.h->head; s_count0 = da.st.h->count; } // before anyone can overwrite the header
+  dots_body<RPW, PAIR>(da); // (its barriers publish s_head0 / s_count0)
+  grid_barrier(bar, gridDim.x);
+  __shared__ SolveLocal res;
+  SolveLocal r;
+  solve_body(sa, sh, blockIdx.x == 0, s_head0, s_count0, &r);
+  if (threadIdx.x == 0) res = r;
+  __syncthreads();
+  apply_body<true>(aa, res.k, res.cg, res.alpha0, res.cs, res.cy, res.phys);
 }
 
 // totals[c] = sum_b partials[b][c] in a fixed order (sharded history: the totals are then all-reduced over ranks)
@@ -490,12 +599,16 @@ int launch_lbfgs_dots(const DotsArgs &a0, int mp, int nblocks, cudaStream_t st) 
   return B200_OK;
 }
 
+static size_t solve_smem_bytes(int mp, bool stage) {
+  size_t b = sizeof(double) * (kDotsCols * mp + 1 + 4 * (size_t)mp);
+  if (stage) b += sizeof(double) * (2 * (size_t)mp * mp + 3 * mp) + sizeof(int) * mp;
+  return b;
+}
+
 int launch_lbfgs_solve(const SolveArgs &a0, int mp, cudaStream_t st) {
   SolveArgs a = a0;
-  const size_t base = sizeof(double) * (kDotsCols * mp + 1 + 2 * mp);
-  const size_t staged = base + sizeof(double) * (2 * (size_t)mp * mp + 3 * mp) + sizeof(int) * mp;
-  a.stage_gram = staged <= 200 * 1024;
-  const size_t smem = a.stage_gram ? staged : base;
+  a.stage_gram = solve_smem_bytes(mp, true) <= 200 * 1024;
+  const size_t smem = solve_smem_bytes(mp, a.stage_gram != 0);
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -505,6 +618,43 @@ int launch_lbfgs_solve(const SolveArgs &a0, int mp, cudaStream_t st) {
   }
   B200_LAUNCH(lbfgs_solve_kernel, 1, 256, smem, st, a);
   return B200_OK;
+}
+
+// Fused direction: returns false in *done when the shape does not qualify (the caller then issues the three kernels).
+int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da0, const SolveArgs &sa0, const ApplyArgs &aa, int mp, int nblocks,
+                           unsigned *bar, cudaStream_t st, bool *done) {
+  *done = false;
+  const size_t smem = solve_smem_bytes(mp, true);
+  if (mp > kRowsPerLaunch || smem > 16 * 1024 || !bar) return B200_OK;
+  const bool pair = da0.mode != DOTS_NONE;
+  const int rpw = ceil_div(mp, kDotsWarps);
+  DotsArgs da = da0;
+  da.row_begin = 0;
+  SolveArgs sa = sa0;
+  sa.stage_gram = 1;
+  auto run = [&](auto kern) -> int {
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDotsThreads, smem));
+    if ((long)per_sm * ctx->num_sms < nblocks) return B200_OK; // the grid barrier needs every CTA resident
+    kern<<<nblocks, kDotsThreads, smem, st>>>(da, sa, aa, bar);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    B200_CUDA(cudaGetLastError());
+    *done = true;
+    return B200_OK;
+  };
+#define B200_DIR_CASE(R)                                                      \
+  case R:                                                                     \
+    if (pair) return run(lbfgs_direction_kernel<R, true>);                    \
+    return run(lbfgs_direction_kernel<R, false>);
+  switch (rpw) {
+    B200_DIR_CASE(1)
+    B200_DIR_CASE(2)
+    B200_DIR_CASE(3)
+    B200_DIR_CASE(4)
+  default:
+    return B200_OK;
+  }
+#undef B200_DIR_CASE
 }
 
 int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st) {

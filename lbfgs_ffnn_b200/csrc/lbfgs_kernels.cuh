@@ -126,6 +126,9 @@ struct ApplyArgs {
 int launch_lbfgs_dots(const DotsArgs &a, int mp, int nblocks, cudaStream_t st);
 int launch_lbfgs_solve(const SolveArgs &a, int mp, cudaStream_t st);
 int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st);
+// dots + solve + apply in one launch (grid-wide barrier); *done = false when the shape does not qualify
+int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da, const SolveArgs &sa, const ApplyArgs &aa, int mp, int nblocks,
+                           unsigned *bar, cudaStream_t st, bool *done);
 int lbfgs_dots_blocks(b200_ctx *ctx, size_t n);
 int lbfgs_init_state(LbfgsView v, int m, int mod, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int nblocks, int ncols, double *totals, cudaStream_t st);

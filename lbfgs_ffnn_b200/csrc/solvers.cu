@@ -135,6 +135,7 @@ struct b200_lbfgs {
   char *ws = nullptr;
   LbfgsView view{};
   double *partials = nullptr, *dot_part = nullptr;
+  unsigned *gridbar = nullptr; // {arrivals, generation} of the fused direction kernel's grid-wide barrier
   float *gbuf[2] = {nullptr, nullptr}, *p = nullptr, *x_prev = nullptr, *S = nullptr, *Y = nullptr;
   // one CUDA graph per (gradient-buffer parity, history-reset flag): direction kernels + first trial evaluation +
   // the two scalar read-backs of a steady-state iteration are ONE launch instead of ~10
@@ -200,6 +201,8 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
   off = (off + 255) & ~size_t(255);
   s->totals = (double *)(s->ws + off); off += totals_bytes;
   if (s->sharded) s->gfull = (float *)(s->ws + off);
+  B200_CUDA(cudaMalloc(&s->gridbar, 2 * sizeof(unsigned)));
+  B200_CUDA(cudaMemsetAsync(s->gridbar, 0, 2 * sizeof(unsigned), st));
   B200_TRY(lbfgs_init_state(s->view, s->m, s->mod, st));
   s->apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (s->ld / 4 + 255) / 256));
   *out = s;
@@ -220,6 +223,7 @@ int b200_lbfgs_destroy(b200_lbfgs *s) {
   cudaStreamSynchronize(s->ctx->stream);
   lbfgs_drop_graphs(s);
   cudaFree(s->ws);
+  if (s->gridbar) cudaFree(s->gridbar);
   delete s;
   return B200_OK;
 }
@@ -278,20 +282,27 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
     // ---- direction: pair formation of the previous step + two-loop + first trial point, 3 launches ----
     const int mode = (iter > 0 && m > 0) ? DOTS_FORM_PAIR : DOTS_NONE;
     auto issue_direction = [&]() -> int {
-      {
-        ProfScope ps(ctx, "lbfgs_dots");
-        DotsArgs da{S, Y, N, ld, s->view, g, params, x_prev, g_new, mode, s->reset_next, 0, s->partials};
-        B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
+      DotsArgs da{S, Y, N, ld, s->view, g, params, x_prev, g_new, mode, s->reset_next, 0, s->partials};
+      SolveArgs sa{s->view, s->partials, s->nblk, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0, 0};
+      ApplyArgs aa{S, Y, N, ld, s->view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
+      bool fused = false;
+      if (std::getenv("B200_NO_FUSED_DIRECTION") == nullptr) { // one launch: dots -> grid barrier -> solve (every CTA) -> apply
+        ProfScope ps(ctx, "lbfgs_direction");
+        B200_TRY(launch_lbfgs_direction(ctx, da, sa, aa, mp, s->nblk, s->gridbar, st, &fused));
       }
-      {
-        ProfScope ps(ctx, "lbfgs_solve");
-        SolveArgs sa{s->view, s->partials, s->nblk, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0};
-        B200_TRY(launch_lbfgs_solve(sa, mp, st));
-      }
-      {
-        ProfScope ps(ctx, "lbfgs_apply");
-        ApplyArgs aa{S, Y, N, ld, s->view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
-        B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
+      if (!fused) {
+        {
+          ProfScope ps(ctx, "lbfgs_dots");
+          B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
+        }
+        {
+          ProfScope ps(ctx, "lbfgs_solve");
+          B200_TRY(launch_lbfgs_solve(sa, mp, st));
+        }
+        {
+          ProfScope ps(ctx, "lbfgs_apply");
+          B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
+        }
       }
       B200_CUDA(cudaMemcpyAsync(&mail->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
       return B200_OK;
