@@ -10,7 +10,7 @@ MNIST-shaped samples, m = 10, fp32-accurate arithmetic. For N > 1 the 60 000 sam
 and the flat gradient (+ loss) is all-reduced with NCCL once per evaluation ("strong" scaling: total work fixed).
 
 value : iterations/s with X, T and the parameters already resident in HBM (CUDA events on the library's stream,
-        max over ranks). Inputs (188 MB) exceed L2 (126 MB), so no explicit flush is needed between iterations.
+        max over ranks). The per-iteration working set (142 MB: see config.l2) exceeds L2 (126 MB); no explicit flush.
 e2e   : the same K iterations through the public C-ABI solve call starting from PINNED HOST buffers: the timed
         region contains the H2D copy of X, T and the parameters, b200_lbfgs_solve (which returns every
         iteration's loss / gradient norm to the host), and the D2H copy of the final parameters.
@@ -281,26 +281,49 @@ def main():
     rep = prof["report"] or {}
     pk = peaks()
     roofline, kernels = None, {}
+    rooflines = {}
     if rep:
         total_prof = sum(v[1] for v in rep.values())
-        evals = max(1, prof["evals"])
-        flops_fwd_dw = 2.0 * shard * DIMS[0] * DIMS[1]  # layer-1 forward and dW1 GEMMs: 2*B*784*128 each
         for k, (calls, tot) in rep.items():
             kernels[k] = {"launches": calls, "avg_us": 1e3 * tot / calls, "share": tot / total_prof}
-        dom = max(rep, key=lambda k: rep[k][1])
-        calls, tot = rep[dom]
-        avg_s = tot / calls / 1e3
-        alg_flops = {"fwd0": flops_fwd_dw, "dw0": flops_fwd_dw + 2.0 * shard * DIMS[1]}.get(dom)
-        tf32_peak = pk["bf16_sustained"] / 2.0
-        if alg_flops:
-            ach = alg_flops / avg_s / 1e12
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": ach / tf32_peak, "traffic": None, "avg_launch_us": avg_s * 1e6,
-                        "share_of_step": tot / total_prof,
-                        "peak_note": f"dense TF32 = 1/2 of the {pk['source']} sustained bf16 figure ({pk['bf16_sustained']} TFLOP/s); "
-                                     f"precision mode {args.precision}"}
-        # the two-loop recursion (HBM-bound class): algorithmic bytes (4k+2)*n*4, k = 10
-        if "lbfgs_dots" in rep and "lbfgs_apply" in rep:
+        # Algorithmic work per launch of the kernels with a roof (shard = samples on this GPU, fp32-accurate mode):
+        #   fwd0  layer-0 forward: 2*B*784*128 flop; reads X (uint8 when the input is 8-bit pixels, else fp32) + writes A1
+        #   dw0   layer-0 [dW; db]: 2*B*785*128 flop; reads X + delta_0 (fp16 hi|lo = 4 B/element, or fp32) + writes the split-K partials
+        #   tail_fwd / tail_bwd  last layer in two passes: read A1 (+ write delta_0): HBM class
+        #   lbfgs_direction  two-loop recursion, (4k+2)*n*4 bytes
+        B, K0, N0 = shard, DIMS[0], DIMS[1]
+        u8 = args.precision != "fp32"
+        x_bytes = B * K0 * (1 if u8 else 4)
+        work = {
+            "fwd0": dict(flops=2.0 * B * K0 * N0, bytes=x_bytes + 4.0 * B * N0),
+            "dw0": dict(flops=2.0 * B * (K0 + 1) * N0, bytes=x_bytes + 4.0 * B * N0),
+            "tail_fwd": dict(flops=2.0 * B * N0 * DIMS[2], bytes=4.0 * B * (N0 + 3 * DIMS[2])),
+            "tail_bwd": dict(flops=4.0 * B * N0 * DIMS[2], bytes=4.0 * B * (2 * N0 + DIMS[2])),
+            "lbfgs_direction": dict(flops=0.0, bytes=(4.0 * MEMORY + 2) * n * 4),
+        }
+        tensor_peak = pk["bf16_sustained"]  # kind::f16 MMAs: the measured dense 16-bit figure (TF32 is half of it)
+        for k, w in work.items():
+            if k not in rep:
+                continue
+            calls, tot = rep[k]
+            avg_s = tot / calls / 1e3
+            t_hbm = w["bytes"] / (pk["hbm"] * 1e9)
+            t_tc = w["flops"] / (tensor_peak * 1e12)
+            if t_tc > t_hbm:
+                ach = w["flops"] / avg_s / 1e12
+                rooflines[k] = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak}
+            else:
+                ach = w["bytes"] / avg_s / 1e9
+                rooflines[k] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+            rooflines[k].update({"avg_launch_us": avg_s * 1e6, "share_of_step": tot / total_prof, "alg_flops": w["flops"],
+                                 "alg_bytes": w["bytes"], "tensor_TFLOPs": w["flops"] / avg_s / 1e12})
+        if rooflines:
+            dom = max(rooflines, key=lambda k: rooflines[k]["share_of_step"])
+            roofline = dict(kernel=dom, traffic=None, **rooflines[dom])
+            roofline["peak_note"] = (f"{pk['source']} peaks: HBM {pk['hbm']} GB/s, dense 16-bit tensor {tensor_peak} TFLOP/s sustained; the bound is "
+                                     f"the larger of bytes/HBM and flops/tensor for the kernel's ALGORITHMIC work; precision mode {args.precision}; "
+                                     "lbfgs_direction streams an L2-resident history at this size (latency-bound)")
+        if "lbfgs_dots" in rep and "lbfgs_apply" in rep:  # unfused direction (B200_NO_FUSED_DIRECTION)
             t_dir = (rep["lbfgs_dots"][1] / rep["lbfgs_dots"][0] + rep["lbfgs_solve"][1] / rep["lbfgs_solve"][0] +
                      rep["lbfgs_apply"][1] / rep["lbfgs_apply"][0]) / 1e3
             bytes_dir = (4 * MEMORY + 2) * n * 4
@@ -312,11 +335,11 @@ def main():
         value = args.steps / (ms_total / 1e3)
         line = {"metric": "lbfgs_iters_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split products, fp32 accumulate)", "tf32": "tf32"}[args.precision],
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (fp32-accurate split products on the tensor cores: fp16 hi+lo x exact uint8 pixels, fp32 accumulate)", "tf32": "tf32 / fp16 single-pass operands"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "memory": MEMORY, "line_search": "armijo (reference CUDA backend)",
                            "precision": args.precision, "samples_per_gpu": shard, "params": n,
-                           "l2": "inputs (188 MB fp32 X) larger than the 126 MB L2; no flush needed",
+                           "l2": "no flush: iterations run back to back inside one solver call; per-iteration working set at 60 000 samples = X 47 MB (uint8 copy; 188 MB as fp32) + A1 31 MB + delta 31 MB + split-K partials 16 MB + history 9 MB + T/outputs 8 MB = 142 MB > 126 MB L2",
                            "evals_per_iteration": res["evals"] / args.steps,
                            "parallelism": f"samples sharded x{world}, NCCL allreduce of grad+loss" if world > 1 else "1 GPU"},
                 "gpu_launches": res["launches"],
@@ -325,7 +348,7 @@ def main():
                 "e2e": {"value": e2e_iters / (e2e_ms / 1e3), "unit": "iterations/s", "h2d_bytes_per_step": h2d / max(1, e2e_iters),
                         "d2h_bytes_per_step": d2h / max(1, e2e_iters), "ms_total": e2e_ms, "iterations": e2e_iters,
                         "note": "H2D of X,T,params from pinned memory + b200_lbfgs_solve + D2H of params inside the timed region"},
-                "roofline": roofline, "kernels": kernels}
+                "roofline": roofline, "rooflines": rooflines, "kernels": kernels}
         if world == 1 and not args.no_cpu_baseline:
             k_cpu = max(3, min(args.steps, 20))
             rate, info = cpu_lbfgs_rate(k_cpu, 2, w0, Xh, Th)

@@ -480,28 +480,42 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
 
 } // namespace
 
-// Layer 0 forward on the uint8 copy of the input (xq). Sets *done when it ran.
-int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t *xq, long batch, bool *done) {
-  *done = false;
+static bool fwd16_shape_ok(const b200_net *net) {
   const char *env = std::getenv("B200_FWD16"); // debugging aid, read per call: 0 = use the generic tcgen05 kernel
-  const bool off = env && std::atoi(env) == 0;
-  if (off || l != 0 || !xq) return B200_OK;
+  if (env && std::atoi(env) == 0) return false;
   const int K = net->dims[0], N = net->dims[1];
-  if (K % 16 != 0 || K > kSplitMaxK || N % 32 != 0 || N > 128 || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
-  const bool x2 = net->prec == B200_PREC_TF32X3;
+  return net->nlayers() >= 2 && net->prec != B200_PREC_FP32 && K % 16 == 0 && K <= kSplitMaxK && N % 32 == 0 && N <= 128;
+}
+
+// Per evaluation, before the forward sweep: the scaled fp16 {hi, lo} split of W_0 (its own launch, so that it is timed and
+// profiled apart from the GEMM). No-op when the fp16 forward does not apply.
+int fwd16_prepare(b200_net *net, const float *params) {
+  net->w16_params = nullptr;
+  if (!fwd16_shape_ok(net)) return B200_OK;
+  const int K = net->dims[0], N = net->dims[1];
   const int ldk = (K + 7) & ~7;
-  cudaStream_t st = net->ctx->stream;
   if (!net->w16h) {
     B200_CUDA(cudaMalloc(&net->w16h, sizeof(__half) * (size_t)N * ldk));
     B200_CUDA(cudaMalloc(&net->w16l, sizeof(__half) * (size_t)N * ldk));
     B200_CUDA(cudaMalloc(&net->colscale, sizeof(float) * N));
   }
+  ProfScope ps(net->ctx, "split16");
+  B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, net->ctx->stream, params + net->offs[0], K, N, ldk, 1.0f / 255.0f,
+              (__half *)net->w16h, (__half *)net->w16l, net->colscale);
+  net->w16_params = params;
+  return B200_OK;
+}
+
+// Layer 0 forward on the uint8 copy of the input (xq). Sets *done when it ran.
+int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t *xq, long batch, bool *done) {
+  *done = false;
+  if (l != 0 || !xq || !fwd16_shape_ok(net) || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
+  if (net->w16_params != params) B200_TRY(fwd16_prepare(net, params)); // callers normally prepare before the sweep
+  const int K = net->dims[0], N = net->dims[1];
+  const bool x2 = net->prec == B200_PREC_TF32X3;
+  const int ldk = (K + 7) & ~7;
+  cudaStream_t st = net->ctx->stream;
   const float *W = params + net->offs[0];
-  {
-    ProfScope ps(net->ctx, "split16");
-    B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, st, W, K, N, ldk, 1.0f / 255.0f, (__half *)net->w16h,
-                (__half *)net->w16l, net->colscale);
-  }
   CUtensorMap tx, twh, twl, tout;
   B200_TRY(make_map_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K, batch, K, kFK, kFM, CU_TENSOR_MAP_SWIZZLE_NONE));
   const unsigned bn = N > 64 ? 128 : 64;

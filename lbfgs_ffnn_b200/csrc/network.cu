@@ -373,6 +373,8 @@ static int launch_fwd_layer(b200_net *net, int l, const float *params, const flo
 int net_forward(b200_net *net, const float *params, const float *x, long batch) {
   B200_TRY(net_ensure(net, batch));
   B200_TRY(tc_split_params(net, params));
+  net->w16_params = nullptr;
+  if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
   const float *cur = x;
   for (int l = 0; l < net->nlayers(); ++l) {
     bool done = false;
@@ -399,6 +401,8 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   const float inv_batch = 1.0f / (float)batch_global;
 
   B200_TRY(tc_split_params(net, params));
+  net->w16_params = nullptr;
+  if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
   // forward sweep
   const float *cur = x;
   bool fused_last = false; // last layer, loss, delta_L and delta_{L-1} produced by the penultimate layer's epilogue

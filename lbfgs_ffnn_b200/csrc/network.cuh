@@ -50,6 +50,7 @@ struct b200_net {
   // fp16 forward of layer 0 on a uint8 input (gemm_fwd16.cu): per-neuron-scaled hi / lo fp16 weights [out][ldk], 1/(255 s_o)
   void *w16h = nullptr, *w16l = nullptr;
   float *colscale = nullptr;
+  const float *w16_params = nullptr; // parameter vector the fp16 split currently holds (per evaluation)
   // one-pass last layer (tail_layer.cu): per-CTA max |delta_L|, scaled fp16 {hi | lo} copy of delta_{L-1} and 1 / its scale
   float *amax_part = nullptr, *scale16_inv = nullptr;
   void *delta16 = nullptr;
