@@ -98,6 +98,10 @@ struct b200_ctx {
   double *h_scalars = nullptr; // 64 doubles, pinned
   double *d_scalars = nullptr; // 64 doubles, device
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  // solver objects parked by b200_lbfgs_destroy for reuse (work space + instantiated CUDA graphs): a solve call from host
+  // buffers otherwise pays ~15 ms of cudaMalloc / cudaFree / graph instantiation per call (reference: 6 + 2m DeviceBuffers per solve)
+  std::vector<void *> lbfgs_pool;
+  void (*lbfgs_pool_free)(void *) = nullptr;
 };
 
 namespace b200 {

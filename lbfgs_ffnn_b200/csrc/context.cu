@@ -182,6 +182,9 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   if (ctx->comm) {
     if (NcclApi *api = nccl_api()) api->CommDestroy((ncclComm_t)ctx->comm);
   }
+  if (ctx->lbfgs_pool_free)
+    for (void *p : ctx->lbfgs_pool) ctx->lbfgs_pool_free(p);
+  ctx->lbfgs_pool.clear();
   for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_a);
   cudaEventDestroy(ctx->ev_b);

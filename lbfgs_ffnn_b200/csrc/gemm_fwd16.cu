@@ -498,6 +498,7 @@ int fwd16_prepare(b200_net *net, const float *params) {
     B200_CUDA(cudaMalloc(&net->w16h, sizeof(__half) * (size_t)N * ldk));
     B200_CUDA(cudaMalloc(&net->w16l, sizeof(__half) * (size_t)N * ldk));
     B200_CUDA(cudaMalloc(&net->colscale, sizeof(float) * N));
+    ++net->config_gen;
   }
   ProfScope ps(net->ctx, "split16");
   B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, net->ctx->stream, params + net->offs[0], K, N, ldk, 1.0f / 255.0f,

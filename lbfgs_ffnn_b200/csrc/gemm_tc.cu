@@ -843,6 +843,7 @@ static int tc_ensure_split(b200_net *net) {
   if (!net->w_hi) {
     B200_CUDA(cudaMalloc(&net->w_hi, sizeof(float) * net->n));
     B200_CUDA(cudaMalloc(&net->w_lo, sizeof(float) * net->n));
+    ++net->config_gen;
   }
   const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * net->ctx->num_sms, (net->n + 255) / 256));
   B200_LAUNCH(split_params_kernel, blocks, 256, 0, net->ctx->stream, params, (unsigned long long)net->n, net->w_hi, net->w_lo);

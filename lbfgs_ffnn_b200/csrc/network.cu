@@ -32,6 +32,13 @@ struct FinParams {
   float lam;
   float *grad;
   double *fin_part; // [gridDim.x][2] = {sum g^2, sum w^2}
+  // the LAST CTA to finish also reduces the scalars (what eval_scalars_kernel did in a launch of its own)
+  unsigned *done_count; // zero on entry, reset by the last CTA
+  const double *loss_part;
+  int n_loss;
+  double inv_batch, lam_d;
+  int want_gnorm;
+  EvalOut *out;
 };
 
 // grad[j] = sum_s partial_l[s][j - off_l] (+ lam * w[j]); per-CTA partials of ||g||^2, ||w||^2.
@@ -81,9 +88,30 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   }
   const double a = block_sum(g2, red);
   const double b = block_sum(w2, red);
+  __shared__ bool last;
   if (threadIdx.x == 0) {
     p.fin_part[2 * blockIdx.x + 0] = a;
     p.fin_part[2 * blockIdx.x + 1] = b;
+    __threadfence();
+    last = atomicAdd(p.done_count, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // loss = 0.5 * inv_batch * sum(loss_part) + 0.5 * lam * sum(w^2 parts); gnorm2 = sum(g^2 parts): fixed order (deterministic)
+  __threadfence();
+  double l = 0.0, sg = 0.0, sw = 0.0;
+  for (int i = threadIdx.x; i < p.n_loss; i += blockDim.x) l += __ldcg(p.loss_part + i);
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    sg += __ldcg(p.fin_part + 2 * i);
+    sw += __ldcg(p.fin_part + 2 * i + 1);
+  }
+  l = block_sum(l, red);
+  sg = block_sum(sg, red);
+  sw = block_sum(sw, red);
+  if (threadIdx.x == 0) {
+    p.out->loss = 0.5 * p.inv_batch * l + 0.5 * p.lam_d * sw;
+    if (p.want_gnorm) p.out->gnorm2 = sg;
+    *p.done_count = 0u;
   }
 }
 
@@ -265,6 +293,7 @@ int net_ensure(b200_net *net, long batch) {
     }
     net->loss_part_cap = std::max(4 * ceil_div(batch, kBM) * ceil_div(net->dims[L], 16), 2 * net->ctx->num_sms);
     B200_CUDA(cudaMalloc(&net->loss_part, sizeof(double) * net->loss_part_cap));
+    ++net->config_gen;
     net->cap = batch;
   }
   if (batch != net->partials_batch) {
@@ -289,6 +318,7 @@ int net_ensure(b200_net *net, long batch) {
     if (total > net->partials_cap) {
       if (net->partials) cudaFree(net->partials);
       B200_CUDA(cudaMalloc(&net->partials, sizeof(float) * total));
+      ++net->config_gen;
       net->partials_cap = total;
     }
     net->partials_batch = batch;
@@ -297,15 +327,19 @@ int net_ensure(b200_net *net, long batch) {
 }
 
 void net_xq_clear(b200_net *net) {
+  if (net->xq.valid) ++net->config_gen;
   net->xq.valid = false;
   net->xq.src = nullptr;
   net->xq.rows = 0;
 }
 
-int net_quantize_input(b200_net *net, const float *x, long batch) {
+int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) {
   const int in = net->dims[0];
-  if (net->xq.valid && net->xq.src == x && net->xq.rows == batch) return B200_OK;
-  net_xq_clear(net);
+  const bool cached = net->xq.valid && net->xq.src == x && net->xq.rows == batch;
+  if (cached && !refresh) return B200_OK;
+  // refresh: same buffers (no captured graph is invalidated), contents re-derived from what x holds NOW — a caller may have
+  // uploaded new data to the same device buffer since the copy was made
+  if (!cached) net_xq_clear(net);
   // TMA needs 16-byte row strides on the uint8 copy; float4 reads need an aligned source
   if (in % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0 || batch <= 0) return B200_OK;
   const size_t bytes = (size_t)batch * in;
@@ -315,6 +349,7 @@ int net_quantize_input(b200_net *net, const float *x, long batch) {
     net->xq.data = nullptr;
     net->xq.cap = 0;
     B200_CUDA(cudaMalloc(&net->xq.data, bytes));
+    ++net->config_gen;
     net->xq.cap = bytes;
   }
   if (!net->xq.flag) B200_CUDA(cudaMalloc(&net->xq.flag, sizeof(int)));
@@ -324,10 +359,13 @@ int net_quantize_input(b200_net *net, const float *x, long batch) {
   int ok = 0;
   B200_CUDA(cudaMemcpyAsync(&ok, net->xq.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
-  if (ok) {
+  if (ok && !cached) {
+    ++net->config_gen;
     net->xq.valid = true;
     net->xq.src = x;
     net->xq.rows = batch;
+  } else if (!ok && cached) {
+    net_xq_clear(net); // the buffer no longer holds 8-bit pixel data
   }
   return B200_OK;
 }
@@ -511,9 +549,12 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   const bool multi = ctx->world > 1 && !net->defer_reduce;
   {
     ProfScope ps(ctx, "finalize");
+    fp.done_count = net->fin_done;
+    fp.loss_part = net->loss_part; fp.n_loss = net->loss_part_n;
+    fp.inv_batch = (double)inv_batch; fp.lam_d = (double)fp.lam;
+    fp.want_gnorm = multi ? 0 : 1;
+    fp.out = out;
     B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);
-    B200_LAUNCH(eval_scalars_kernel, 1, 1024, 0, st, net->loss_part, net->loss_part_n, net->fin_part, net->fin_blocks,
-                (double)inv_batch, (double)fp.lam, multi ? 0 : 1, out);
   }
   if (multi) {
     ProfScope ps(ctx, "allreduce");
@@ -562,6 +603,8 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   cudaSetDevice(ctx->device);
   B200_CUDA(cudaMalloc(&net->fin_part, sizeof(double) * 2 * net->fin_blocks));
   B200_CUDA(cudaMalloc(&net->eval_out, sizeof(EvalOut)));
+  B200_CUDA(cudaMalloc(&net->fin_done, sizeof(unsigned)));
+  B200_CUDA(cudaMemset(net->fin_done, 0, sizeof(unsigned)));
   *out = net;
   return B200_OK;
 }
@@ -578,6 +621,7 @@ int b200_net_destroy(b200_net *net) {
   if (net->partials) cudaFree(net->partials);
   if (net->fin_part) cudaFree(net->fin_part);
   if (net->eval_out) cudaFree(net->eval_out);
+  if (net->fin_done) cudaFree(net->fin_done);
   if (net->params) cudaFree(net->params);
   if (net->grads) cudaFree(net->grads);
   delete net;
@@ -627,6 +671,7 @@ int b200_net_set_precision(b200_net *net, int prec) {
   B200_REQUIRE(net, "null net");
   B200_REQUIRE(prec >= B200_PREC_FP32 && prec <= B200_PREC_TF32, "unknown precision mode");
   net->prec = prec;
+  ++net->config_gen;
   return B200_OK;
 }
 int b200_net_get_precision(b200_net *net) { return net ? net->prec : -1; }
@@ -634,19 +679,21 @@ int b200_net_get_precision(b200_net *net) { return net ? net->prec : -1; }
 int b200_net_set_l2(b200_net *net, float lambda) {
   B200_REQUIRE(net, "null net");
   net->l2 = lambda;
+  ++net->config_gen;
   return B200_OK;
 }
 
 int b200_net_set_global_batch(b200_net *net, long batch_global) {
   B200_REQUIRE(net && batch_global >= 0, "bad argument");
   net->batch_global = batch_global;
+  ++net->config_gen;
   return B200_OK;
 }
 
 int b200_net_quantize_input(b200_net *net, const float *x_dev, long batch, int *quantized) {
   B200_REQUIRE(net && x_dev, "null argument");
   cudaSetDevice(net->ctx->device);
-  B200_TRY(net_quantize_input(net, x_dev, batch));
+  B200_TRY(net_quantize_input(net, x_dev, batch, true));
   if (quantized) *quantized = net->xq.valid ? 1 : 0;
   return B200_OK;
 }

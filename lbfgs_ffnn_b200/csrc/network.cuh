@@ -61,6 +61,11 @@ struct b200_net {
   double *fin_part = nullptr;  // per-CTA partials of ||g||^2 and ||w||^2 (2 per CTA)
   int fin_blocks = 0;
   double *eval_out = nullptr;  // device {loss, gnorm2}
+  unsigned *fin_done = nullptr; // CTAs of finalize_grad_kernel that have finished (the last one reduces the scalars)
+
+  // bumped whenever a device buffer of this net is (re)allocated or a setting that selects kernels changes: captured CUDA
+  // graphs bake both in, so the solvers key their graphs on it
+  long config_gen = 0;
 
   int nlayers() const { return (int)acts.size(); }
 };
@@ -81,7 +86,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
 int net_forward(b200_net *net, const float *params, const float *x, long batch);
 int net_ensure(b200_net *net, long batch);
 // build (or reuse) the uint8 copy of x[batch][in]; no-op unless every element is exactly float(u)/255.0f
-int net_quantize_input(b200_net *net, const float *x, long batch);
+int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh = false);
 void net_xq_clear(b200_net *net);
 // the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);

@@ -10,6 +10,7 @@
 #include "network.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -59,21 +60,21 @@ struct Objective {
   }
 };
 
-struct Timer { // per-iteration CUDA-event timing exactly as src/cuda/lbfgs.cuh:80-91,176-182
+struct Timer { // per-iteration wall time of the stream's work, as src/cuda/lbfgs.cuh:80-91,176-182 records it (cumulative ms).
+  // Host clock around a drained stream instead of the reference's event pair: two event records and an event wait per
+  // iteration were ~5 us of a ~200 us iteration.
   b200_ctx *ctx;
   bool on;
   float elapsed = 0.f;
+  std::chrono::steady_clock::time_point t0;
   int start() {
-    if (on) B200_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    if (on) t0 = std::chrono::steady_clock::now();
     return B200_OK;
   }
   int stop() {
     if (!on) return B200_OK;
-    B200_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
-    B200_CUDA(cudaEventSynchronize(ctx->ev_b));
-    float ms = 0.f;
-    B200_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
-    elapsed += ms;
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    elapsed += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return B200_OK;
   }
 };
@@ -133,6 +134,7 @@ struct b200_lbfgs {
   int m = 0, mp = 1, mod = 1, policy = POLICY_ARMIJO;
   int nblk = 1, apply_blocks = 1;
   char *ws = nullptr;
+  size_t ws_bytes = 0;
   LbfgsView view{};
   double *partials = nullptr, *dot_part = nullptr;
   unsigned *gridbar = nullptr; // {arrivals, generation} of the fused direction kernel's grid-wide barrier
@@ -141,7 +143,7 @@ struct b200_lbfgs {
   // the two scalar read-backs of a steady-state iteration are ONE launch instead of ~10
   cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   long graph_launches[2][2] = {{0, 0}, {0, 0}};
-  const void *gkey[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // net, params, input, target, batch
+  const void *gkey[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // net, params, input, target, batch, net config generation
   bool graphs_ok = true;
   // minimisation state carried across runs
   bool started = false;
@@ -157,11 +159,25 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
   if (opts) o = *opts; else b200_lbfgs_default_opts(&o);
   B200_REQUIRE(o.memory >= 0 && o.memory <= kMaxSlots - 1, "memory must be in [0, 256]");
   B200_CUDA(cudaSetDevice(ctx->device));
+  const bool wolfe = (o.linesearch == B200_LS_WOLFE);
+  const bool want_sharded = ctx->world > 1 && !wolfe && (o.shard_history == 1 || (o.shard_history < 0 && (size_t)n >= (size_t(4) << 20)));
+  for (size_t i = 0; i < ctx->lbfgs_pool.size(); ++i) { // a parked solver of the same shape: reuse work space and graphs
+    b200_lbfgs *c = (b200_lbfgs *)ctx->lbfgs_pool[i];
+    if (c->N == (size_t)n && c->m == o.memory && (c->policy == POLICY_WOLFE) == wolfe && c->sharded == want_sharded) {
+      ctx->lbfgs_pool.erase(ctx->lbfgs_pool.begin() + i);
+      c->o = o;
+      c->started = false; c->cur = 0; c->iter = 0; c->reset_next = 0; c->loss = 0.0; c->gnorm = 0.0;
+      B200_CUDA(cudaMemsetAsync(c->ws, 0, c->ws_bytes, ctx->stream));
+      B200_CUDA(cudaMemsetAsync(c->gridbar, 0, 2 * sizeof(unsigned), ctx->stream));
+      B200_TRY(lbfgs_init_state(c->view, c->m, c->mod, ctx->stream));
+      *out = c;
+      return B200_OK;
+    }
+  }
   b200_lbfgs *s = new b200_lbfgs;
   s->ctx = ctx;
   s->o = o;
   s->m = o.memory;
-  const bool wolfe = (o.linesearch == B200_LS_WOLFE);
   s->policy = wolfe ? POLICY_WOLFE : POLICY_ARMIJO;
   s->mod = wolfe ? s->m + 1 : std::max(s->m, 1);
   s->mp = s->m + 1;
@@ -186,6 +202,7 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
     set_error("cudaMalloc of %zu bytes of L-BFGS work space failed", total);
     return B200_ERR_CUDA;
   }
+  s->ws_bytes = total;
   cudaStream_t st = ctx->stream;
   B200_CUDA(cudaMemsetAsync(s->ws, 0, total, st));
   size_t off = 0;
@@ -217,14 +234,25 @@ static void lbfgs_drop_graphs(b200_lbfgs *s) {
     }
 }
 
-int b200_lbfgs_destroy(b200_lbfgs *s) {
-  if (!s) return B200_OK;
-  cudaSetDevice(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
+static void lbfgs_free(void *p) {
+  b200_lbfgs *s = (b200_lbfgs *)p;
   lbfgs_drop_graphs(s);
   cudaFree(s->ws);
   if (s->gridbar) cudaFree(s->gridbar);
   delete s;
+}
+
+int b200_lbfgs_destroy(b200_lbfgs *s) {
+  if (!s) return B200_OK;
+  b200_ctx *ctx = s->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->lbfgs_pool.size() < 4) { // park it: the next solver of this shape skips cudaMalloc / cudaFree / graph instantiation
+    ctx->lbfgs_pool_free = lbfgs_free;
+    ctx->lbfgs_pool.push_back(s);
+    return B200_OK;
+  }
+  lbfgs_free(s);
   return B200_OK;
 }
 
@@ -259,7 +287,9 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
 
   double cb_loss = 0.0;
-  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch)); // no-op unless x == u/255
+  // uint8 copy of 8-bit pixel inputs (no-op unless x == u/255); re-derived at the start of every minimisation: the caller may
+  // have refilled the same device buffer
+  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch, !s->started));
   if (!s->started) {
     // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
     B200_TRY(obj.eval_async(params, s->gbuf[0], mail, &cb_loss));
@@ -312,7 +342,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
     const bool graphable = net && !wolfe && s->graphs_ok && mode == DOTS_FORM_PAIR && ctx->world == 1 && !ctx->prof.on &&
                            max_ls > 0 && std::getenv("B200_NO_GRAPH") == nullptr && std::getenv("B200_TC_TIMING") == nullptr;
     if (graphable) {
-      const void *key[5] = {net, params, input, target, (const void *)(intptr_t)batch};
+      const void *key[6] = {net, params, input, target, (const void *)(intptr_t)batch, (const void *)(intptr_t)net->config_gen};
       if (memcmp(key, s->gkey, sizeof(key)) != 0) {
         lbfgs_drop_graphs(s);
         memcpy(s->gkey, key, sizeof(key));
@@ -468,7 +498,7 @@ static int lbfgs_run_sharded(b200_lbfgs *s, b200_net *net, float *params, const 
   HostMail *mail = (HostMail *)ctx->h_scalars;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   long evals = 0;
-  if (net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch));
+  if (net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch, true));
   struct Defer { b200_net *n; ~Defer() { n->defer_reduce = false; } } defer{net};
   net->defer_reduce = true;
 
@@ -611,7 +641,7 @@ int b200_gd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user
   obj.n = N;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   double cb_loss = 0.0;
-  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch));
+  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch, true));
   struct ClearQ { b200_net *n; ~ClearQ() { if (n) net_xq_clear(n); } } clear_q{net};
   B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
   B200_CUDA(cudaStreamSynchronize(st));
@@ -677,7 +707,7 @@ int b200_sgd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *use
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   long evals = 0;
   double cb_loss = 0.0;
-  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, total_samples));
+  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, total_samples, true));
   struct ClearQ { b200_net *n; ~ClearQ() { if (n) net_xq_clear(n); } } clear_q{net};
   float current_lr = o.lr;
   const int num_batches = (total_samples + o.batch_size - 1) / o.batch_size;

@@ -346,11 +346,13 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   if (!net->amax_part) {
     B200_CUDA(cudaMalloc(&net->amax_part, sizeof(float) * 2 * net->ctx->num_sms));
     B200_CUDA(cudaMalloc(&net->scale16_inv, sizeof(float)));
+    ++net->config_gen;
   }
   if (want16 && net->delta16_cap < batch) {
     if (net->delta16) cudaFree(net->delta16);
     net->delta16 = nullptr;
     B200_CUDA(cudaMalloc(&net->delta16, sizeof(__half) * 2 * (size_t)in * net->cap));
+    ++net->config_gen;
     net->delta16_cap = net->cap;
   }
   TailParams p{};
