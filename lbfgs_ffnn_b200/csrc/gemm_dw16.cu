@@ -35,9 +35,12 @@ constexpr int kDRawBytes = kDMT * kDRawTile;
 constexpr int kDConvTile = kDK * kDM * 2; // fp16: two feature atoms of [32 K-rows][128 B]
 constexpr int kDConvBytes = kDMT * kDConvTile;
 constexpr int kDAtom = kDK * 128;         // one MN atom column of a stage: [32 K-rows][64 elements]
-constexpr int kDNR = 8, kDNS = 4;         // raw ring; converted-A and B rings share one stage index (one commit frees both)
-constexpr int kDThreads = 384;            // warp 0 raw TMA, 1 MMA issue, 2 TMEM alloc, 3 delta TMA, 4-11 converters (4-7 then run the epilogue)
+constexpr int kDNR = 0, kDNS = 6;         // raw ring; converted-A and B rings share one stage index (one commit frees both)
+constexpr int kDThreads = 256;            // warp 0 X TMA, 1 MMA issue, 2 TMEM alloc, 3 delta TMA, 4-7 epilogue
 constexpr int kDConvThreads = 256;
+constexpr int kDConvGroups = 4;           // converter groups taking K blocks round-robin: a block's wait -> convert -> proxy fence -> arrive
+                                          // chain is ~1 k clk of latency however many threads share it; the MMAs of a block take 640
+constexpr int kDGroupThreads = kDConvThreads / kDConvGroups, kDRowsPerPass = kDGroupThreads / 8, kDPasses = kDK / kDRowsPerPass;
 
 struct Dw16Params {
   int in_dim, out_dim;    // layer 0: in (784), out (<= 128)
@@ -111,8 +114,7 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmD);
-    for (int s = 0; s < kDNR; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), kDConvThreads / 64); }
-    for (int s = 0; s < kDNS; ++s) { mbar_init(conv_full(s), kDConvThreads / 64); mbar_init(b_full(s), 1); mbar_init(st_empty(s), 1); }
+    for (int s = 0; s < kDNS; ++s) { mbar_init(conv_full(s), 1); mbar_init(b_full(s), 1); mbar_init(st_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -128,14 +130,17 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) { // ===== raw uint8 producer: box {128 features, 64 samples} ===================================
+    if (lane == 0) { // ===== X producer: fp16 rows -> MN-major SWIZZLE_128B atoms, two boxes {64 features, 32 samples} per M tile ==
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(raw_empty(s), ph ^ 1);
-        mbar_expect_tx(raw_full(s), kDRawBytes); // ONE box {256 feature bytes, 32 samples}: 256-byte contiguous DRAM segments
-        tma_load_2d(raw_a(s), &tmX, raw_full(s), m0, kb * kDK);
-        if (++s == kDNR) { s = 0; ph ^= 1; }
+        mbar_wait(st_empty(s), ph ^ 1);
+        mbar_expect_tx(conv_full(s), nmt * kDConvTile);
+        for (int t = 0; t < nmt; ++t)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d(conv_a(s) + t * kDConvTile + j * kDAtom, &tmX, conv_full(s), m0 + t * kDM + 64 * j, kb * kDK);
+        if (++s == kDNS) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -184,55 +189,9 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===== converters: raw [64 samples][128 B] -> fp16 MN-major: feature atom j = f / 64 at j * 8192, sample row r at r * 128,
-    // 16-byte chunk c (8 features) at (c ^ (r & 7)) * 16. Eight consecutive lanes take one sample's 128 bytes.
-    // Two groups of four warps take alternate K blocks (two wait -> convert -> proxy fence -> arrive chains in flight).
-    const int tt = threadIdx.x - 128, grp = tt >> 7, t = tt & 127, q = t & 7, rb = t >> 3; // rb = sample rows rb, rb + 16
-    int n = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb, ++n) {
-      if ((n & 1) != grp) continue;
-      const int rs = n % kDNR, cs = n % kDNS;
-      const uint32_t rph = (uint32_t)(n / kDNR) & 1u, cph = (uint32_t)(n / kDNS) & 1u;
-      mbar_wait(raw_full(rs), rph);
-      mbar_wait(st_empty(cs), cph ^ 1);
-      const uint8_t *raw = bp + Plan::kOffRaw + rs * kDRawBytes;
-      uint8_t *conv = bp + Plan::kOffConv + cs * kDConvBytes;
-      uint4 w[2 * kDMT];
-#pragma unroll
-      for (int i = 0; i < 2 * kDMT; ++i)
-        if ((i >> 1) < nmt) w[i] = *reinterpret_cast<const uint4 *>(raw + (rb + 16 * (i & 1)) * (kDMT * kDM) + (i >> 1) * kDM + q * 16);
-#pragma unroll
-      for (int i = 0; i < 2 * kDMT; ++i) {
-        if ((i >> 1) < nmt) {
-          const int r = rb + 16 * (i & 1);
-          uint32_t o[8];
-          u8x4_to_h4_d(w[i].x, o[0], o[1]);
-          u8x4_to_h4_d(w[i].y, o[2], o[3]);
-          u8x4_to_h4_d(w[i].z, o[4], o[5]);
-          u8x4_to_h4_d(w[i].w, o[6], o[7]);
-          const int fl = p.in_dim - (m0 + (i >> 1) * kDM); // local row of the bias (ones) feature, if it falls into this tile
-          if (fl >= 0 && fl < kDM && (fl >> 4) == q) { // feature `in` reads as 1 for every sample: D row `in` = sum_s delta[s][:]
-            const int e = fl & 15;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k == (e >> 1)) o[k] = (e & 1) ? ((o[k] & 0x0000FFFFu) | 0x3C000000u) : ((o[k] & 0xFFFF0000u) | 0x00003C00u);
-          }
-          uint8_t *dst = conv + (i >> 1) * kDConvTile + (q >> 2) * kDAtom;
-          const int c0 = 2 * (q & 3);
-          *reinterpret_cast<uint4 *>(dst + r * 128 + ((c0 ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4 *>(dst + r * 128 + (((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-      }
-      fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) { // one arrival per warp
-        mbar_arrive(conv_full(cs));
-        mbar_arrive(raw_empty(rs));
-      }
-    }
     // ===== epilogue (same warps: warp w owns TMEM lanes 32 * (w % 4) ..): partial[split][f * out + o] = (hi + lo) * scale ====
     const int OUT = p.out_dim;
-    if (warp < 8) {
+    {
     if (nkb > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -367,10 +326,14 @@ int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap 
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     const int n = std::min(1024, (int)(grid.x * grid.y));
-    double tot = 0, iw = 0, ib = 0;
-    for (int i = 0; i < n; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2]; }
-    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting: converted X %.0f, delta %.0f\n", NB,
-            grid.x, grid.y, p.kb_per_split, tot / n, iw / n, ib / n);
+    double tot = 0, iw = 0, ib = 0, cr = 0, cs = 0;
+    for (int i = 0; i < n; ++i) {
+      tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2];
+      cr += (double)(h[4 * i + 3] >> 32); cs += (double)(h[4 * i + 3] & 0xffffffffll);
+    }
+    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting: converted X %.0f, delta %.0f | "
+            "converter group 0 (1/%d of the blocks) waiting: raw %.0f, free slot %.0f\n", NB,
+            grid.x, grid.y, p.kb_per_split, tot / n, iw / n, ib / n, kDConvGroups, cr / n, cs / n);
   }
   return B200_OK;
 }
@@ -395,12 +358,14 @@ int dw16_plan(const b200_net *net, long batch, int *splits) {
 }
 
 // layer 0 [dW; db] partials from the uint8 input copy and the fp16 {hi | lo} delta written by tail_layer(want16)
-int dw16_layer(b200_net *net, const uint8_t *xq, long batch, bool *done) {
+int dw16_layer(b200_net *net, const void *x16, int ld16, long batch, bool *done) {
   *done = false;
-  if (!xq || !net->delta16) return B200_OK;
+  if (!x16 || !net->delta16) return B200_OK;
   const int K0 = net->dims[0], N0 = net->dims[1];
   CUtensorMap tx, td, tout;
-  B200_TRY(make_map_2d_d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K0, batch, K0, kDMT * kDM, kDK, CU_TENSOR_MAP_SWIZZLE_NONE));
+  // K0 + 1 columns: column K0 of the fp16 copy is the ones feature, whose row of D is the bias gradient
+  B200_TRY(make_map_2d_d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x16, K0 + 1, batch, (unsigned long long)ld16 * 2, 64, kDK,
+                         CU_TENSOR_MAP_SWIZZLE_128B));
   B200_TRY(make_map_2d_d(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->delta16, 2 * N0, batch, (unsigned long long)2 * N0 * 2, 64, kDK,
                          CU_TENSOR_MAP_SWIZZLE_128B));
   int splits = 1;

@@ -36,10 +36,10 @@ constexpr int kFM = 128;                   // samples per tile = UMMA M
 constexpr int kFK = 64;                    // K elements per stage (64 uint8 -> 64 fp16 = one 128-byte swizzle row)
 constexpr int kRawBytes = kFM * kFK;       // 8 KB
 constexpr int kConvBytes = kFM * kFK * 2;  // 16 KB
-constexpr int kNR = 4, kNC = 3, kNW = 3; // converted-X and weight rings share one stage index, so ONE tcgen05.commit frees both
-constexpr int kFThreads = 512;
-constexpr int kEpiWarp0 = 4, kEpiThreads = 256, kConvWarp0 = 12, kConvThreads = 128;
-constexpr int kConvGroups = kConvThreads / 128; // groups of four warps taking alternate K blocks (one is enough: measured)
+constexpr int kNR = 0, kNC = 4, kNW = 4; // X and weight rings share one stage index, so ONE tcgen05.commit frees both (no raw ring:
+                                         // the fp16 copy of X arrives by TMA in the UMMA layout)
+constexpr int kFThreads = 384;            // warps 0-3: X TMA, MMA issue, TMEM alloc, weight TMA; warps 4-11: epilogue
+constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
 constexpr int kStageOutBytes = 32 * 128;      // per epilogue warp: one [32 rows][32 floats] TMA-store box
 
 struct F16Params {
@@ -141,8 +141,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWh);
     if (X2) tma_prefetch_desc(&tmWl);
-    for (int s = 0; s < kNR; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 4); }
-    for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), 4); mbar_init(conv_empty(s), 1); }
+    for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), 1); mbar_init(conv_empty(s), 1); }
     for (int s = 0; s < kNW; ++s) mbar_init(w_full(s), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), kEpiThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,15 +164,15 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const int umma_n = min(BN, (p.cols_valid + 31) & ~31);
 
   if (warp == 0) {
-    if (lane == 0) { // ===== raw uint8 producer ==========================================================
+    if (lane == 0) { // ===== X producer: fp16 rows straight from HBM into the K-major SWIZZLE_128B operand tile ===========
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(raw_empty(s), ph ^ 1);
-          mbar_expect_tx(raw_full(s), kRawBytes);
-          tma_load_2d(raw_a(s), &tmX, raw_full(s), kb * kFK, tile * kFM);
-          if (++s == kNR) { s = 0; ph ^= 1; }
+          mbar_wait(conv_empty(s), ph ^ 1);
+          mbar_expect_tx(conv_full(s), kConvBytes);
+          tma_load_2d(conv_a(s), &tmX, conv_full(s), kb * kFK, tile * kFM);
+          if (++s == kNC) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -231,54 +230,6 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       if (p.dbg) { p.dbg[8 * blockIdx.x + 3] = waited; p.dbg[8 * blockIdx.x + 4] = waited_w; p.dbg[8 * blockIdx.x + 5] = waited_tm; }
     }
     __syncwarp();
-  } else if (warp >= kConvWarp0) {
-    // ===== converters: raw [128][64 B] -> fp16 K-major SWIZZLE_128B tile (row r at r*128, 16-byte chunk c at (c ^ (r&7))*16).
-    // Four consecutive lanes take one row's four 16-byte pieces, so a quarter-warp reads 128 contiguous bytes.
-    // Two groups of four warps take alternate K blocks: one block's wait -> load -> convert -> proxy fence -> arrive chain is
-    // ~1 k clk however many threads share it, so two chains in flight are what doubles the converter's throughput.
-    const int tt = threadIdx.x - kConvWarp0 * 32, grp = tt >> 7, t = tt & 127, j = t & 3, rb = t >> 2;
-    long long cw_raw = 0, cw_empty = 0, cw_fence = 0, cw_work = 0;
-    int n = 0; // running K-block index of this CTA (over all its tiles)
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < p.k_blocks; ++kb, ++n) {
-        if ((n % kConvGroups) != grp) continue;
-        const int rs = n % kNR, cs = n % kNC;
-        const uint32_t rph = (uint32_t)(n / kNR) & 1u, cph = (uint32_t)(n / kNC) & 1u;
-        const long long c0 = p.dbg ? clock64() : 0;
-        mbar_wait(raw_full(rs), rph);
-        const long long c1 = p.dbg ? clock64() : 0;
-        mbar_wait(conv_empty(cs), cph ^ 1);
-        if (p.dbg) { cw_raw += c1 - c0; cw_empty += clock64() - c1; }
-        const uint8_t *raw = bp + Plan::kOffRaw + rs * kRawBytes;
-        uint8_t *dst = bp + Plan::kOffConv + cs * kConvBytes;
-        uint4 w[4];
-        if (!(p.dry & 1)) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4 *>(raw + (rb + 32 * i) * kFK + j * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rb + 32 * i;
-          uint4 o0, o1;
-          u8x4_to_h4(w[i].x, o0.x, o0.y);
-          u8x4_to_h4(w[i].y, o0.z, o0.w);
-          u8x4_to_h4(w[i].z, o1.x, o1.y);
-          u8x4_to_h4(w[i].w, o1.z, o1.w);
-          *reinterpret_cast<uint4 *>(dst + r * 128 + (((2 * j) ^ (r & 7)) << 4)) = o0;
-          *reinterpret_cast<uint4 *>(dst + r * 128 + (((2 * j + 1) ^ (r & 7)) << 4)) = o1;
-        }
-        }
-        const long long f0 = p.dbg ? clock64() : 0;
-        fence_async_smem(); // generic-proxy writes -> visible to the tensor core (async proxy)
-        if (p.dbg) cw_fence += clock64() - f0;
-        __syncwarp();
-        if (lane == 0) { // one arrival per warp
-          mbar_arrive(conv_full(cs));
-          mbar_arrive(raw_empty(rs));
-        }
-        if (p.dbg) cw_work += clock64() - f0;
-      }
-    }
-    if (p.dbg && tt == 0) { p.dbg[8 * blockIdx.x + 6] = cw_raw; p.dbg[8 * blockIdx.x + 7] = cw_empty; p.dbg[8 * 1024 + 2 * blockIdx.x] = cw_fence; p.dbg[8 * 1024 + 2 * blockIdx.x + 1] = cw_work; }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue warps 4-11: warp w owns TMEM lanes (= samples) 32*(w%4).., the two warps of a lane quarter split the
     // 32-column chunks. Each warp stages its [32 rows][32 floats] block in shared memory (SWIZZLE_128B, conflict-free 16-byte
@@ -507,10 +458,10 @@ int fwd16_prepare(b200_net *net, const float *params) {
   return B200_OK;
 }
 
-// Layer 0 forward on the uint8 copy of the input (xq). Sets *done when it ran.
-int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t *xq, long batch, bool *done) {
+// Layer 0 forward on the fp16 copy of an 8-bit-pixel input (x16: rows of ld16 halves, value u = 255 x). Sets *done when it ran.
+int fwd16_forward_layer(b200_net *net, int l, const float *params, const void *x16, int ld16, long batch, bool *done) {
   *done = false;
-  if (l != 0 || !xq || !fwd16_shape_ok(net) || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
+  if (l != 0 || !x16 || !fwd16_shape_ok(net) || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
   if (net->w16_params != params) B200_TRY(fwd16_prepare(net, params)); // callers normally prepare before the sweep
   const int K = net->dims[0], N = net->dims[1];
   const bool x2 = net->prec == B200_PREC_TF32X3;
@@ -518,7 +469,8 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const uint8_t
   cudaStream_t st = net->ctx->stream;
   const float *W = params + net->offs[0];
   CUtensorMap tx, twh, twl, tout;
-  B200_TRY(make_map_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, xq, K, batch, K, kFK, kFM, CU_TENSOR_MAP_SWIZZLE_NONE));
+  // only the K real features are visible through this map (the ones column at index K belongs to the dW kernel)
+  B200_TRY(make_map_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x16, K, batch, (unsigned long long)ld16 * 2, kFK, kFM, CU_TENSOR_MAP_SWIZZLE_128B));
   const unsigned bn = N > 64 ? 128 : 64;
   B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16h, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
                        CU_TENSOR_MAP_SWIZZLE_128B));

@@ -8,6 +8,8 @@
 #include "gemm_tc.cuh"
 #include "network.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -243,9 +245,11 @@ __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restri
   }
 }
 
-// x -> u = round(255 x) as uint8; *flag &= (every x is exactly float(u)/255.0f with 0 <= u <= 255)
-__global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n,
-                                                          uint8_t *__restrict__ q, int *flag) {
+// x -> u = round(255 x) as uint8 AND as fp16 (exact: u <= 255 has 8 significant bits); *flag &= (every x is exactly
+// float(u)/255.0f with 0 <= u <= 255). The fp16 rows are [in | 1 | zero padding] with ld16 halves per row: column `in` is the
+// ones feature whose "weight gradient" is the bias gradient (gemm_dw16.cu), and TMA feeds the rows to the tensor cores as they are.
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n, int in, int ld16,
+                                                          uint8_t *__restrict__ q, __half *__restrict__ q16, int *flag) {
   int ok = 1;
   const unsigned long long nv = n / 4;
   for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv;
@@ -253,13 +257,22 @@ __global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restric
     const float4 a = __ldg(reinterpret_cast<const float4 *>(x) + v);
     const float f[4] = {a.x, a.y, a.z, a.w};
     unsigned packed = 0;
+    __half hv[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int u = __float2int_rn(f[e] * 255.0f);
       ok &= (u >= 0 && u <= 255 && __fdiv_rn((float)u, 255.0f) == f[e]) ? 1 : 0;
       packed |= (unsigned)(u & 255) << (8 * e);
+      hv[e] = __int2half_rn(u & 255);
     }
     reinterpret_cast<unsigned *>(q)[v] = packed;
+    const unsigned long long e0 = v * 4, row = e0 / (unsigned)in, col = e0 - row * (unsigned)in; // in % 4 == 0: one row per vector
+    *reinterpret_cast<uint2 *>(q16 + row * ld16 + col) = *reinterpret_cast<const uint2 *>(hv);
+  }
+  const unsigned long long rows = n / (unsigned)in;
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (unsigned long long)gridDim.x * blockDim.x) {
+    for (int c = in; c < ld16; ++c) q16[r * ld16 + c] = __float2half_rn(c == in ? 1.0f : 0.0f);
   }
   if (!__all_sync(0xffffffffu, ok)) {
     if ((threadIdx.x & 31) == 0) atomicAnd(flag, 0);
@@ -344,18 +357,24 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
   if (in % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0 || batch <= 0) return B200_OK;
   const size_t bytes = (size_t)batch * in;
   cudaStream_t st = net->ctx->stream;
+  const int ld16 = (in + 1 + 7) & ~7;
   if (bytes > net->xq.cap) {
     if (net->xq.data) cudaFree(net->xq.data);
+    if (net->xq.data16) cudaFree(net->xq.data16);
     net->xq.data = nullptr;
+    net->xq.data16 = nullptr;
     net->xq.cap = 0;
     B200_CUDA(cudaMalloc(&net->xq.data, bytes));
+    B200_CUDA(cudaMalloc(&net->xq.data16, sizeof(__half) * (size_t)batch * ld16));
+    net->xq.ld16 = ld16;
     ++net->config_gen;
     net->xq.cap = bytes;
   }
   if (!net->xq.flag) B200_CUDA(cudaMalloc(&net->xq.flag, sizeof(int)));
   const int one = 1;
   B200_CUDA(cudaMemcpyAsync(net->xq.flag, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-  B200_LAUNCH(quantize_u8_kernel, 8 * net->ctx->num_sms, 256, 0, st, x, (unsigned long long)bytes, net->xq.data, net->xq.flag);
+  B200_LAUNCH(quantize_u8_kernel, 8 * net->ctx->num_sms, 256, 0, st, x, (unsigned long long)bytes, in, ld16, net->xq.data,
+              (__half *)net->xq.data16, net->xq.flag);
   int ok = 0;
   B200_CUDA(cudaMemcpyAsync(&ok, net->xq.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
@@ -368,6 +387,18 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
     net_xq_clear(net); // the buffer no longer holds 8-bit pixel data
   }
   return B200_OK;
+}
+
+// the fp16 rows matching x (row-aligned sub-range of the quantised input), or nullptr; *ld16 = halves per row
+const void *net_x16_lookup(b200_net *net, const float *x, long batch, int *ld16) {
+  if (!net->xq.valid || !net->xq.data16 || x < net->xq.src) return nullptr;
+  const size_t off = (size_t)(x - net->xq.src);
+  const int in = net->dims[0];
+  if (off % in != 0) return nullptr;
+  const long row0 = (long)(off / in);
+  if (row0 + batch > net->xq.rows) return nullptr;
+  *ld16 = net->xq.ld16;
+  return (const char *)net->xq.data16 + (size_t)row0 * net->xq.ld16 * 2;
 }
 
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch) {
@@ -502,7 +533,11 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       snprintf(nm, sizeof(nm), "dw%d", l);
       ProfScope ps(ctx, nm);
       bool done = false;
-      if (l == 0 && use_dw16) B200_TRY(dw16_layer(net, xq0, batch, &done));
+      if (l == 0 && use_dw16) {
+        int ld16 = 0;
+        const void *x16 = net_x16_lookup(net, x, batch, &ld16);
+        B200_TRY(dw16_layer(net, x16, ld16, batch, &done));
+      }
       if (!done && net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
       if (!done && N <= 16 && K + 1 <= 160 && net->prec != B200_PREC_FP32) {
         const int splits = std::max(1, std::min(net->skinny_splits[l], ceil_div(batch, kSkinnyTile)));
@@ -617,6 +652,7 @@ int b200_net_destroy(b200_net *net) {
   tc_release(net);
   tail_release(net);
   if (net->xq.data) cudaFree(net->xq.data);
+  if (net->xq.data16) cudaFree(net->xq.data16);
   if (net->xq.flag) cudaFree(net->xq.flag);
   if (net->partials) cudaFree(net->partials);
   if (net->fin_part) cudaFree(net->fin_part);

@@ -40,6 +40,8 @@ struct b200_net {
     const float *src = nullptr;
     long rows = 0;
     uint8_t *data = nullptr;
+    void *data16 = nullptr; // fp16 rows [in | 1 | 0-pad], ld16 halves each: TMA-ready operand of the fp16 layer-0 kernels
+    int ld16 = 0;
     size_t cap = 0;
     bool valid = false;
     int *flag = nullptr; // device
@@ -90,6 +92,7 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh =
 void net_xq_clear(b200_net *net);
 // the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
+const void *net_x16_lookup(b200_net *net, const float *x, long batch, int *ld16);
 // the skinny last layer in one pass: forward, loss, both deltas and the [dW_L; db_L] partials (tail_layer.cu)
 bool tail_applicable(const b200_net *net);
 int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16);
