@@ -1,15 +1,17 @@
-// [dW_0 ; db_0] split-K partials of layer 0 on the fp16 tensor cores, for an input that is exactly u/255 (uint8-resident X).
+// [dW_0 ; db_0] split-K partials of layer 0 on the fp16 tensor cores, for an input that is exactly u/255 (8-bit pixels).
 //
 // Replaces CudaDenseLayer::backward's dW SGEMM (K = batch) and the serial sum_rows_kernel (src/cuda/layer.cuh:81-86,
 // src/cuda/kernels.cuh:144-153) for the first layer:
 //     D[f][o] = sum_s X[s][f] * delta[s][o]          f = input feature (M, tiles of 128), o = output neuron, s = sample (K)
-// Operands: A = X^T, converted uint8 -> fp16 (exact) by four warps straight into the UMMA MN-major SWIZZLE_128B layout;
-// B = [delta_hi | delta_lo], the scaled fp16 split of delta written by tail_bwd_kernel (22 mantissa bits), loaded by TMA in
-// MN-major layout. One kind::f16 MMA of N = 2 * out per 16 samples yields D = [hi | lo] in adjacent TMEM columns; the
-// epilogue adds them and undoes the scales (1/255 of X, 1/S of delta). The bias gradient is the row f = in of the same
-// product: the converter plants a row of ones there (sum_s 1 * delta[s][o]), exactly the [W | b] layout of the flat gradient.
-// tcgen05.mma issues at one instruction per ~140-160 clk regardless of N (tools/probe/mma_probe.cu), so the N = 256,
-// K = 16 shape is what makes this 4x faster than the TF32 N = 128, K = 8 kernel it replaces.
+// Operands: A = X^T from the fp16 copy of X (value u, exact), loaded by TMA as MN-major SWIZZLE_128B atoms; B = [delta_hi |
+// delta_lo], the scaled fp16 split of delta written by tail_bwd_kernel (22 mantissa bits), also MN-major by TMA. One kind::f16
+// MMA of N = 2 * out per 16 samples yields D = [hi | lo] in adjacent TMEM columns; the epilogue adds them, undoes the scales
+// (1/255 of X, 1/S of delta) and leaves through TMA tile stores. The bias gradient is the row f = in of the same product: the fp16
+// copy of X carries a column of ones there (sum_s 1 * delta[s][o]), exactly the [W | b] layout of the flat gradient.
+// A CTA owns TWO feature tiles (512 TMEM columns) so that every delta tile fetched from L2 feeds two MMAs, and a slice of the
+// samples (split-K, combined deterministically by finalize_grad_kernel).
+// tcgen05.mma issues at one instruction per ~140-160 clk regardless of N (tools/probe/mma_probe.cu), so the N = 256, K = 16
+// shape is what makes this 4x cheaper in tensor-core instructions than the TF32 N = 128, K = 8 kernel it replaces.
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -30,17 +32,11 @@ constexpr int kDM = 128;                  // input features per M tile = UMMA M
 constexpr int kDMT = 2;                   // M tiles per CTA: every delta tile read from L2 feeds two MMAs (the L2 -> SM path,
                                           // ~43 B/clk per SM, is what bounds a one-tile CTA), accumulators fill the 512 TMEM columns
 constexpr int kDK = 32;                   // samples per stage
-constexpr int kDRawTile = kDK * kDM;      // uint8 [32 samples][128 features]
-constexpr int kDRawBytes = kDMT * kDRawTile;
 constexpr int kDConvTile = kDK * kDM * 2; // fp16: two feature atoms of [32 K-rows][128 B]
 constexpr int kDConvBytes = kDMT * kDConvTile;
 constexpr int kDAtom = kDK * 128;         // one MN atom column of a stage: [32 K-rows][64 elements]
-constexpr int kDNR = 0, kDNS = 6;         // raw ring; converted-A and B rings share one stage index (one commit frees both)
+constexpr int kDNS = 6;                   // A and B rings share one stage index (one commit frees both)
 constexpr int kDThreads = 256;            // warp 0 X TMA, 1 MMA issue, 2 TMEM alloc, 3 delta TMA, 4-7 epilogue
-constexpr int kDConvThreads = 256;
-constexpr int kDConvGroups = 4;           // converter groups taking K blocks round-robin: a block's wait -> convert -> proxy fence -> arrive
-                                          // chain is ~1 k clk of latency however many threads share it; the MMAs of a block take 640
-constexpr int kDGroupThreads = kDConvThreads / kDConvGroups, kDRowsPerPass = kDGroupThreads / 8, kDPasses = kDK / kDRowsPerPass;
 
 struct Dw16Params {
   int in_dim, out_dim;    // layer 0: in (784), out (<= 128)
@@ -55,8 +51,7 @@ template <int NB> struct DPlan { // NB = 2 * out rounded up to 128 / 256: width 
   static constexpr int kBStage = NB * kDK * 2;
   static constexpr int kOffConv = 0;
   static constexpr int kOffB = kDNS * kDConvBytes;
-  static constexpr int kOffRaw = kOffB + kDNS * kBStage;
-  static constexpr int kOffBar = kOffRaw + kDNR * kDRawBytes;
+  static constexpr int kOffBar = kOffB + kDNS * kBStage;
   static constexpr int kTotal = kOffBar + 256 + 1024;
 };
 
@@ -76,14 +71,6 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
 // (64 elements further along M / N) at LBO = one [32 K-rows][128 B] box = 4096 B
 __device__ __forceinline__ uint64_t desc_mn16(uint32_t saddr) { return make_desc(saddr, kDAtom, 1024, 2); }
 
-__device__ __forceinline__ void u8x4_to_h4_d(uint32_t w, uint32_t &lo, uint32_t &hi) {
-  const uint32_t a = __byte_perm(w, 0x64646464u, 0x5140), b = __byte_perm(w, 0x64646464u, 0x7362);
-  const __half2 k = __halves2half2(__ushort_as_half((unsigned short)0x6400), __ushort_as_half((unsigned short)0x6400));
-  const __half2 ra = __hsub2(*reinterpret_cast<const __half2 *>(&a), k), rb = __hsub2(*reinterpret_cast<const __half2 *>(&b), k);
-  lo = *reinterpret_cast<const uint32_t *>(&ra);
-  hi = *reinterpret_cast<const uint32_t *>(&rb);
-}
-
 template <int NB>
 __global__ void __launch_bounds__(kDThreads, 1)
 dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmOut,
@@ -94,15 +81,12 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
   auto conv_a = [&](int s) { return base + Plan::kOffConv + s * kDConvBytes; };
   auto b_a = [&](int s) { return base + Plan::kOffB + s * Plan::kBStage; };
-  auto raw_a = [&](int s) { return base + Plan::kOffRaw + s * kDRawBytes; };
   const uint32_t bars = base + Plan::kOffBar;
-  auto raw_full = [&](int s) { return bars + 8 * s; };
-  auto raw_empty = [&](int s) { return bars + 8 * (kDNR + s); };
-  auto conv_full = [&](int s) { return bars + 8 * (2 * kDNR + s); };
-  auto b_full = [&](int s) { return bars + 8 * (2 * kDNR + kDNS + s); };
-  auto st_empty = [&](int s) { return bars + 8 * (2 * kDNR + 2 * kDNS + s); }; // MMAs of the stage done: A and B tiles reusable
-  const uint32_t acc_full = bars + 8 * (2 * kDNR + 3 * kDNS);
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kDNR + 3 * kDNS + 1));
+  auto conv_full = [&](int s) { return bars + 8 * (s); };
+  auto b_full = [&](int s) { return bars + 8 * (kDNS + s); };
+  auto st_empty = [&](int s) { return bars + 8 * (2 * kDNS + s); }; // MMAs of the stage done: A and B tiles reusable
+  const uint32_t acc_full = bars + 8 * (3 * kDNS);
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (3 * kDNS + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = p.dbg ? clock64() : 0;
@@ -326,14 +310,10 @@ int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap 
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     const int n = std::min(1024, (int)(grid.x * grid.y));
-    double tot = 0, iw = 0, ib = 0, cr = 0, cs = 0;
-    for (int i = 0; i < n; ++i) {
-      tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2];
-      cr += (double)(h[4 * i + 3] >> 32); cs += (double)(h[4 * i + 3] & 0xffffffffll);
-    }
-    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting: converted X %.0f, delta %.0f | "
-            "converter group 0 (1/%d of the blocks) waiting: raw %.0f, free slot %.0f\n", NB,
-            grid.x, grid.y, p.kb_per_split, tot / n, iw / n, ib / n, kDConvGroups, cr / n, cs / n);
+    double tot = 0, iw = 0, ib = 0;
+    for (int i = 0; i < n; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2]; }
+    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting: X %.0f, delta %.0f\n", NB, grid.x,
+            grid.y, p.kb_per_split, tot / n, iw / n, ib / n);
   }
   return B200_OK;
 }

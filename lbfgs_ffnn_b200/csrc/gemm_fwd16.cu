@@ -1,20 +1,25 @@
-// Persistent forward kernel of layer 0 for an input that is exactly u/255 (uint8-resident X), fp16 tensor-core operands.
+// Persistent forward kernel of layer 0 for an input that is exactly u/255 (8-bit pixels), fp16 tensor-core operands.
 //
 // Replaces, for the first dense layer, CudaDenseLayer::forward (src/cuda/layer.cuh:48-58: SGEMM + add_bias_kernel +
 // activation_kernel).
 //
-// Why fp16: u in [0, 255] is exact in fp16, so X needs no hi/lo split; each weight is split ONCE per evaluation into
-// hi = fp16(s_o * w), lo = fp16(s_o * w - hi) with a per-output-neuron power-of-two scale s_o (split_w16_kernel), i.e. 22
-// mantissa bits, and the accumulator is rescaled by 1/(255 s_o) in the epilogue. Two kind::f16 MMAs per K step give
-// fp32-level products at the fp16 rate (4x the 3xTF32 rate) with half the shared memory per K element.
+// Why fp16: u in [0, 255] is exact in fp16, so X needs no hi/lo split: net_quantize_input keeps an fp16 copy of X (value u,
+// half the bytes of the fp32 array) that TMA drops straight into the UMMA K-major SWIZZLE_128B layout. Each weight is split ONCE
+// per evaluation into hi = fp16(s_o * w), lo = fp16(s_o * w - hi) with a per-output-neuron power-of-two scale s_o
+// (split_w16_kernel), i.e. 22 mantissa bits, and the accumulator is rescaled by 1/(255 s_o) in the epilogue. [W_hi; W_lo] is one
+// 2*BN-row B operand, so ONE kind::f16 MMA of N = 256 per 16 features yields D = [hi | lo] in adjacent TMEM columns:
+// fp32-level products, 4x fewer tensor-core instructions than the 3xTF32 N = 128, K = 8 kernel (tcgen05.mma issues at one
+// instruction per ~140-160 clk whatever its N: tools/probe/mma_probe.cu).
 //
-// Structure (one CTA per SM, 512 threads, tiles of 128 samples taken round-robin):
-//   warp 0      TMA producer of the raw uint8 ring   (kNR stages x [128 rows][64 B], straight from HBM)
-//   warp 3      TMA producer of the weight ring      (kNW stages x {hi, lo} [BN rows][64 fp16], L2-resident)
-//   warps 12-15 converters: raw uint8 -> fp16 in the UMMA K-major SWIZZLE_128B layout (kNC stages)
-//   warp 1      tcgen05.mma.kind::f16 issuer; accumulators {hi, lo} DOUBLE-BUFFERED in TMEM (2 x 2 x BN columns)
-//   warps 4-11  epilogue of tile i while the main loop of tile i+1 runs
-// The rings are decoupled on purpose: the old single ring made TMA -> convert -> MMA one latency chain per stage.
+// Structure (one CTA per SM, 384 threads, tiles of 128 samples taken round-robin):
+//   warp 0      TMA producer of the X tiles          (kNC stages x [128 rows][64 fp16], from HBM)
+//   warp 3      TMA producer of the weight tiles     (kNW stages x {hi, lo} [BN rows][64 fp16], L2-resident)
+//   warp 1      tcgen05.mma.kind::f16 issuer; accumulators [hi | lo] DOUBLE-BUFFERED in TMEM (2 x 2 x BN columns)
+//   warps 4-11  epilogue of tile i while the main loop of tile i+1 runs: TMEM -> registers -> scale, bias, activation ->
+//               swizzled shared-memory staging -> TMA tile store
+// History of the measurements that shaped it (profiles/r01_*.md): a uint8 -> fp16 converter stage in shared memory was bound by
+// shared-memory bandwidth (MMA operand reads + TMA fills + converter traffic); per-thread row stores from registers throttled the
+// whole SM (24 k of 50 k clk per CTA) until the epilogue moved to TMA stores; per-MMA descriptor arithmetic bound the issuer.
 #include "gemm_tc.cuh"
 #include "tc_epilogue.cuh"
 #include "tc_ptx.cuh"
@@ -33,11 +38,9 @@ namespace {
 using namespace tcx;
 
 constexpr int kFM = 128;                   // samples per tile = UMMA M
-constexpr int kFK = 64;                    // K elements per stage (64 uint8 -> 64 fp16 = one 128-byte swizzle row)
-constexpr int kRawBytes = kFM * kFK;       // 8 KB
-constexpr int kConvBytes = kFM * kFK * 2;  // 16 KB
-constexpr int kNR = 0, kNC = 4, kNW = 4; // X and weight rings share one stage index, so ONE tcgen05.commit frees both (no raw ring:
-                                         // the fp16 copy of X arrives by TMA in the UMMA layout)
+constexpr int kFK = 64;                    // K elements per stage (64 fp16 = one 128-byte swizzle row)
+constexpr int kConvBytes = kFM * kFK * 2;  // X tile: 16 KB
+constexpr int kNC = 4, kNW = 4;            // X and weight rings share one stage index, so ONE tcgen05.commit frees both
 constexpr int kFThreads = 384;            // warps 0-3: X TMA, MMA issue, TMEM alloc, weight TMA; warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
 constexpr int kStageOutBytes = 32 * 128;      // per epilogue warp: one [32 rows][32 floats] TMA-store box
@@ -49,17 +52,15 @@ struct F16Params {
   const float *colscale; // [N]: 1 / (255 s_o)
   float *out;            // activations [rows][ld_out]
   long ld_out;
-  int dry;               // B200_FWD16_DRY (timing experiments only): 1 = converters skip the conversion, 2 = epilogue skips its stores
   long long *dbg;        // B200_TC_TIMING: per CTA {total, epilogue busy, epilogue waiting for the accumulator, issuer waiting}
 };
 
-static_assert(kNC == kNW, "the converted-X and weight rings share their empty barriers");
+static_assert(kNC == kNW, "the X and weight rings share their empty barriers");
 template <int BN, bool X2> struct FPlan {
   static constexpr int kWStage = BN * 128 * (X2 ? 2 : 1);
   static constexpr int kOffConv = 0;
   static constexpr int kOffW = kNC * kConvBytes;
-  static constexpr int kOffRaw = kOffW + kNW * kWStage;
-  static constexpr int kOffOut = kOffRaw + kNR * kRawBytes; // epilogue staging tiles (TMA store), 1024-byte aligned
+  static constexpr int kOffOut = kOffW + kNW * kWStage; // epilogue staging tiles (TMA store), 1024-byte aligned
   static constexpr int kOffCol = kOffOut + 8 * kStageOutBytes; // colscale[128], bias[128]
   static constexpr int kOffBar = kOffCol + 1024;
   static constexpr int kTotal = kOffBar + 256 + 1024;
@@ -102,15 +103,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// 4 uint8 -> 4 fp16, exact: bytes are planted in the mantissa of 1024.0h (0x6400, ulp 1) and 1024 is subtracted
-__device__ __forceinline__ void u8x4_to_h4(uint32_t w, uint32_t &lo, uint32_t &hi) {
-  const uint32_t a = __byte_perm(w, 0x64646464u, 0x5140), b = __byte_perm(w, 0x64646464u, 0x7362);
-  const __half2 k = __halves2half2(__ushort_as_half((unsigned short)0x6400), __ushort_as_half((unsigned short)0x6400));
-  const __half2 ra = __hsub2(*reinterpret_cast<const __half2 *>(&a), k), rb = __hsub2(*reinterpret_cast<const __half2 *>(&b), k);
-  lo = *reinterpret_cast<const uint32_t *>(&ra);
-  hi = *reinterpret_cast<const uint32_t *>(&rb);
-}
-
 template <int BN, bool X2>
 __global__ void __launch_bounds__(kFThreads, 1)
 fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
@@ -121,17 +113,14 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
   auto conv_a = [&](int s) { return base + Plan::kOffConv + s * kConvBytes; };
   auto w_a = [&](int s, int lo) { return base + Plan::kOffW + s * Plan::kWStage + lo * (BN * 128); };
-  auto raw_a = [&](int s) { return base + Plan::kOffRaw + s * kRawBytes; };
   const uint32_t bars = base + Plan::kOffBar;
-  auto raw_full = [&](int s) { return bars + 8 * s; };
-  auto raw_empty = [&](int s) { return bars + 8 * (kNR + s); };
-  auto conv_full = [&](int s) { return bars + 8 * (2 * kNR + s); };
-  auto conv_empty = [&](int s) { return bars + 8 * (2 * kNR + kNC + s); };
-  auto w_full = [&](int s) { return bars + 8 * (2 * kNR + 2 * kNC + s); };
+  auto conv_full = [&](int s) { return bars + 8 * (s); };
+  auto conv_empty = [&](int s) { return bars + 8 * (kNC + s); };
+  auto w_full = [&](int s) { return bars + 8 * (2 * kNC + s); };
   auto w_empty = [&](int s) { return conv_empty(s); }; // shared: the MMA warp's single commit per K block releases both tiles
-  auto tm_full = [&](int b) { return bars + 8 * (2 * kNR + 2 * kNC + 2 * kNW + b); };
-  auto tm_empty = [&](int b) { return bars + 8 * (2 * kNR + 2 * kNC + 2 * kNW + 2 + b); };
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kNR + 2 * kNC + 2 * kNW + 4));
+  auto tm_full = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + b); };
+  auto tm_empty = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + 2 + b); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kNC + 2 * kNW + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = p.dbg ? clock64() : 0;
@@ -280,7 +269,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0 && !(p.dry & 2)) {
+            if (lane == 0) {
               tma_store_2d(&tmOut, stage_a, c0, tile * kFM + q * 32);
               tma_store_commit();
             }
@@ -404,27 +393,23 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
   static long long *dbg = nullptr;
   static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
   F16Params pp = p;
-  { const char *e = std::getenv("B200_FWD16_DRY"); pp.dry = e ? std::atoi(e) : 0; }
   if (timing) {
-    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 10 * 1024));
-    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 10 * 1024, st));
+    if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 1024));
+    B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * 1024, st));
     pp.dbg = dbg;
   }
   kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, tout, pp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) {
-    std::vector<long long> h(10 * 1024);
+    std::vector<long long> h(8 * 1024);
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < grid; ++i)
       for (int j = 0; j < 8; ++j) a[j] += (double)h[8 * i + j] / grid;
-    double cf = 0, cw = 0;
-    for (int i = 0; i < grid; ++i) { cf += (double)h[8 * 1024 + 2 * i] / grid; cw += (double)h[8 * 1024 + 2 * i + 1] / grid; }
-    fprintf(stderr, "[fwd16 timing] BN %d x2 %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: conv %.0f, "
-            "weights %.0f, tmem %.0f | converter group 0 waits: raw %.0f, conv slot %.0f; proxy fence %.0f, fence..arrive %.0f\n",
-            BN, (int)X2, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], cf, cw);
+    fprintf(stderr, "[fwd16 timing] BN %d x2 %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: X %.0f, "
+            "weights %.0f, tmem %.0f\n", BN, (int)X2, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5]);
   }
   return B200_OK;
 }
