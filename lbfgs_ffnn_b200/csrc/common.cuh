@@ -100,6 +100,15 @@ struct b200_ctx {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   // solver objects parked by b200_lbfgs_destroy for reuse (work space + instantiated CUDA graphs): a solve call from host
   // buffers otherwise pays ~15 ms of cudaMalloc / cudaFree / graph instantiation per call (reference: 6 + 2m DeviceBuffers per solve)
+  // one-shot all-reduce over NVLink peer memory (context.cu: ctx_p2p_setup): every rank owns a symmetric buffer
+  // {2 x [slot_floats floats | loss double], flags[world], epoch}; peers[r] is rank r's buffer mapped into this process
+  struct P2P {
+    bool tried = false, ready = false;
+    size_t slot_floats = 0, slot_bytes = 0;
+    char *local = nullptr;        // this rank's buffer
+    char **peers_dev = nullptr;   // device array of world pointers (own entry = local)
+    std::vector<void *> opened;   // cudaIpcOpenMemHandle results (to close)
+  } p2p;
   std::vector<void *> lbfgs_pool;
   void (*lbfgs_pool_free)(void *) = nullptr;
 };
@@ -124,6 +133,9 @@ struct ProfScope {
 };
 
 int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev); // grad (float) + 1 double
+// collective (every rank calls it with the same n): maps the peers' symmetric buffers; ctx->p2p.ready tells whether the
+// peer-memory all-reduce can be used (all ranks agree), otherwise the callers stay on NCCL
+int ctx_p2p_setup(b200_ctx *ctx, size_t n_floats);
 int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n);
 int ctx_reduce_shards(b200_ctx *ctx, const float *full, float *shard_out, size_t n, size_t chunk);
 int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk);

@@ -100,6 +100,72 @@ int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev) {
   return B200_OK;
 }
 
+// Symmetric buffers for the peer-memory all-reduce. Layout per rank: slot 0 | slot 1 | flags[world] (u32) | epoch (u32), each
+// slot = slot_floats floats (gradient) + one double (loss partial) padded to 256 B. IPC handles travel through an NCCL
+// all-gather, so no extra rendezvous is needed. Any failure (IPC not permitted, no peer access) leaves ready = false on EVERY
+// rank (agreed with an all-reduce) and the callers keep using NCCL.
+int ctx_p2p_setup(b200_ctx *ctx, size_t n_floats) {
+  b200_ctx::P2P &pp = ctx->p2p;
+  if (ctx->world <= 1) return B200_OK;
+  if (pp.tried) return B200_OK; // one attempt per context; a later, larger network simply stays on NCCL
+  pp.tried = true;
+  NcclApi *api = nccl_api();
+  if (!api) return B200_ERR_COMM;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  const int W = ctx->world;
+  const char *env = std::getenv("B200_NO_P2P");
+  int ok = (env == nullptr) ? 1 : 0;
+  pp.slot_floats = (n_floats + 63) & ~size_t(63);
+  pp.slot_bytes = ((pp.slot_floats * 4 + 8) + 255) & ~size_t(255);
+  const size_t total = 2 * pp.slot_bytes + ((sizeof(unsigned) * (W + 1) + 255) & ~size_t(255));
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc(&pp.local, total) != cudaSuccess) ok = 0;
+  if (ok && cudaMemset(pp.local, 0, total) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, pp.local) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // all-gather {ok flag, handle}
+  struct Item { int ok; int pad; cudaIpcMemHandle_t h; };
+  Item item{ok, 0, mine}, *d_item = nullptr, *d_all = nullptr;
+  std::vector<Item> all(W);
+  B200_CUDA(cudaMalloc(&d_item, sizeof(Item)));
+  B200_CUDA(cudaMalloc(&d_all, sizeof(Item) * W));
+  B200_CUDA(cudaMemcpy(d_item, &item, sizeof(Item), cudaMemcpyHostToDevice));
+  B200_NCCL(api, api->AllGather(d_item, d_all, sizeof(Item), ncclChar, comm, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(cudaMemcpy(all.data(), d_all, sizeof(Item) * W, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < W; ++r) ok &= all[r].ok;
+  std::vector<char *> peers(W, nullptr);
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      if (r == ctx->rank) { peers[r] = pp.local; continue; }
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      pp.opened.push_back(ptr);
+      peers[r] = (char *)ptr;
+    }
+  }
+  // agree: everybody opened everybody
+  item.ok = ok;
+  B200_CUDA(cudaMemcpy(d_item, &item, sizeof(Item), cudaMemcpyHostToDevice));
+  B200_NCCL(api, api->AllGather(d_item, d_all, sizeof(Item), ncclChar, comm, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  B200_CUDA(cudaMemcpy(all.data(), d_all, sizeof(Item) * W, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < W; ++r) ok &= all[r].ok;
+  cudaFree(d_item);
+  cudaFree(d_all);
+  if (ok) {
+    B200_CUDA(cudaMalloc(&pp.peers_dev, sizeof(char *) * W));
+    B200_CUDA(cudaMemcpy(pp.peers_dev, peers.data(), sizeof(char *) * W, cudaMemcpyHostToDevice));
+    pp.ready = true;
+  } else {
+    for (void *p : pp.opened) cudaIpcCloseMemHandle(p);
+    pp.opened.clear();
+    cudaGetLastError();
+  }
+  return B200_OK;
+}
+
 // reduce-scatter with exact (possibly uneven) shards: rank i receives sum over ranks of full[i*chunk .. min(n, (i+1)*chunk))
 // in shard_out; one grouped launch of W ncclReduce calls
 int ctx_reduce_shards(b200_ctx *ctx, const float *full, float *shard_out, size_t n, size_t chunk) {
@@ -182,6 +248,9 @@ int b200_ctx_destroy(b200_ctx *ctx) {
   if (ctx->comm) {
     if (NcclApi *api = nccl_api()) api->CommDestroy((ncclComm_t)ctx->comm);
   }
+  for (void *p : ctx->p2p.opened) cudaIpcCloseMemHandle(p);
+  if (ctx->p2p.peers_dev) cudaFree(ctx->p2p.peers_dev);
+  if (ctx->p2p.local) cudaFree(ctx->p2p.local);
   if (ctx->lbfgs_pool_free)
     for (void *p : ctx->lbfgs_pool) ctx->lbfgs_pool_free(p);
   ctx->lbfgs_pool.clear();

@@ -41,17 +41,33 @@ struct FinParams {
   double inv_batch, lam_d;
   int want_gnorm;
   EvalOut *out;
+  // multi-GPU over peer memory: the gradient goes to this rank's symmetric slot (epoch & 1) instead of `grad`, and the last CTA
+  // publishes the loss partial there and raises this rank's flag in every peer's buffer (p2p_reduce_kernel consumes them)
+  char *sym_local;
+  char *const *peers;
+  unsigned long long slot_bytes, slot_floats;
+  int rank, world;
 };
 
 // grad[j] = sum_s partial_l[s][j - off_l] (+ lam * w[j]); per-CTA partials of ||g||^2, ||w||^2.
 // A CTA takes 32 consecutive gradient elements at a time; its 8 warps take the splits round-robin (every
 // load is one coalesced 128-byte row segment, up to 8 in flight per thread), accumulate in fp64 and are
 // combined in a fixed warp order, so the result is deterministic and rounded once.
+__device__ __forceinline__ unsigned *p2p_flags(char *buf, unsigned long long slot_bytes) {
+  return reinterpret_cast<unsigned *>(buf + 2 * slot_bytes);
+}
+
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   __shared__ double sh[8][32];
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double g2 = 0.0, w2 = 0.0;
+  unsigned epoch = 0;
+  float *gdst = p.grad;
+  if (p.sym_local) { // epoch: completed peer all-reduces on this context (advanced by p2p_reduce_kernel)
+    epoch = *reinterpret_cast<volatile unsigned *>(p2p_flags(p.sym_local, p.slot_bytes) + p.world);
+    gdst = reinterpret_cast<float *>(p.sym_local + (epoch & 1u) * p.slot_bytes);
+  }
   const unsigned long long ngroups = (p.n + 31) / 32;
   for (unsigned long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const unsigned long long j = grp * 32 + lane;
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
         w2 += (double)wv * (double)wv;
       }
       const float s = (float)tot;
-      p.grad[j] = s;
+      gdst[j] = s;
       g2 += (double)s * (double)s;
     }
   }
@@ -94,7 +110,7 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   if (threadIdx.x == 0) {
     p.fin_part[2 * blockIdx.x + 0] = a;
     p.fin_part[2 * blockIdx.x + 1] = b;
-    __threadfence();
+    if (p.sym_local) __threadfence_system(); else __threadfence();
     last = atomicAdd(p.done_count, 1u) == gridDim.x - 1;
   }
   __syncthreads();
@@ -111,9 +127,83 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   sg = block_sum(sg, red);
   sw = block_sum(sw, red);
   if (threadIdx.x == 0) {
-    p.out->loss = 0.5 * p.inv_batch * l + 0.5 * p.lam_d * sw;
+    const double loss = 0.5 * p.inv_batch * l + 0.5 * p.lam_d * sw;
+    p.out->loss = loss;
     if (p.want_gnorm) p.out->gnorm2 = sg;
     *p.done_count = 0u;
+    if (p.sym_local) { // publish: loss partial into the slot, then this rank's flag (= epoch + 1) into every peer's buffer
+      *reinterpret_cast<double *>(p.sym_local + (epoch & 1u) * p.slot_bytes + p.slot_floats * 4) = loss;
+      __threadfence_system();
+      for (int r = 0; r < p.world; ++r)
+        if (r != p.rank) *reinterpret_cast<volatile unsigned *>(p2p_flags(p.peers[r], p.slot_bytes) + p.rank) = epoch + 1u;
+    }
+  }
+}
+
+// One-shot all-reduce over NVLink peer memory, fused with ||g||^2: every rank waits until all peers have published their slot of
+// this epoch, then sums the W slots in rank order (identical order on every rank => bit-identical replicas of g) straight out of
+// the peers' memory into grad_out. Replaces ncclAllReduce(grad) + ncclAllReduce(loss) + two norm kernels; at n ~ 1e5 the NCCL
+// ring / tree costs ~35 us of latency, this ~10. Two slots alternate by epoch: a rank can only overwrite a slot after every
+// peer has signalled the NEXT epoch, i.e. after it finished reading this one.
+struct P2PReduceParams {
+  char *const *peers;
+  char *local;
+  unsigned long long slot_bytes, slot_floats, n;
+  int rank, world;
+  float *grad_out;
+  double *fin_part;
+  unsigned *done_count;
+  EvalOut *out;
+};
+__global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p) {
+  __shared__ double red[32];
+  __shared__ bool last;
+  unsigned *flags = p2p_flags(p.local, p.slot_bytes);
+  const unsigned epoch = *reinterpret_cast<volatile unsigned *>(flags + p.world);
+  if (threadIdx.x < p.world && (int)threadIdx.x != p.rank) {
+    const volatile unsigned *f = flags + threadIdx.x;
+    while (*f < epoch + 1u) __nanosleep(64);
+    __threadfence_system();
+  }
+  __syncthreads();
+  const unsigned long long off = (epoch & 1u) * p.slot_bytes;
+  const unsigned long long nv = (p.n + 3) / 4; // slots are padded to 64 floats: whole float4s are always readable
+  double g2 = 0.0;
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (unsigned long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.world; ++r) {
+      const float4 x = __ldcg(reinterpret_cast<const float4 *>(p.peers[r] + off) + v);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    const unsigned long long j = 4 * v;
+    if (j + 3 < p.n) {
+      *reinterpret_cast<float4 *>(p.grad_out + j) = acc;
+      g2 += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
+    } else {
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+      for (int e = 0; e < 4; ++e)
+        if (j + e < p.n) { p.grad_out[j + e] = a[e]; g2 += (double)a[e] * a[e]; }
+    }
+  }
+  g2 = block_sum(g2, red);
+  if (threadIdx.x == 0) {
+    p.fin_part[2 * blockIdx.x] = g2;
+    __threadfence();
+    last = atomicAdd(p.done_count, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(p.fin_part + 2 * i);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    double loss = 0.0;
+    for (int r = 0; r < p.world; ++r) loss += __ldcg(reinterpret_cast<const double *>(p.peers[r] + off + p.slot_floats * 4));
+    p.out->loss = loss;
+    p.out->gnorm2 = s;
+    *p.done_count = 0u;
+    flags[p.world] = epoch + 1u; // this context's epoch: the slot parity of the next evaluation
   }
 }
 
@@ -582,6 +672,8 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   fp.grad = grad_out;
   fp.fin_part = net->fin_part;
   const bool multi = ctx->world > 1 && !net->defer_reduce;
+  if (multi && !ctx->p2p.tried) B200_TRY(ctx_p2p_setup(ctx, net->n)); // collective; the first evaluation is never inside a graph capture
+  const bool p2p = multi && ctx->p2p.ready && net->n <= ctx->p2p.slot_floats && (reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0;
   {
     ProfScope ps(ctx, "finalize");
     fp.done_count = net->fin_done;
@@ -589,9 +681,20 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     fp.inv_batch = (double)inv_batch; fp.lam_d = (double)fp.lam;
     fp.want_gnorm = multi ? 0 : 1;
     fp.out = out;
+    if (p2p) {
+      fp.sym_local = ctx->p2p.local; fp.peers = ctx->p2p.peers_dev;
+      fp.slot_bytes = ctx->p2p.slot_bytes; fp.slot_floats = ctx->p2p.slot_floats;
+      fp.rank = ctx->rank; fp.world = ctx->world;
+    }
     B200_LAUNCH(finalize_grad_kernel, net->fin_blocks, 256, 0, st, fp);
   }
-  if (multi) {
+  if (p2p) {
+    ProfScope ps(ctx, "allreduce_p2p");
+    P2PReduceParams rp{ctx->p2p.peers_dev, ctx->p2p.local, ctx->p2p.slot_bytes, ctx->p2p.slot_floats, net->n, ctx->rank, ctx->world,
+                       grad_out, net->fin_part, net->fin_done, out};
+    const int blocks = std::max(1, std::min(net->fin_blocks, ceil_div((long)((net->n + 3) / 4), 256)));
+    B200_LAUNCH(p2p_reduce_kernel, blocks, 256, 0, st, rp);
+  } else if (multi) {
     ProfScope ps(ctx, "allreduce");
     B200_TRY(ctx_allreduce(ctx, grad_out, net->n, &out->loss));
     B200_LAUNCH(sumsq_part_kernel, net->fin_blocks, 256, 0, st, grad_out, (unsigned long long)net->n, net->fin_part);

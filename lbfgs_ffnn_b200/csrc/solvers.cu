@@ -339,7 +339,9 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
     };
     // Steady-state iterations of the network objective replay a captured graph: direction + first trial evaluation.
     bool first_eval_issued = false;
-    const bool graphable = net && !wolfe && s->graphs_ok && mode == DOTS_FORM_PAIR && ctx->world == 1 && !ctx->prof.on &&
+    // several GPUs: only when the gradient all-reduce runs over peer memory (plain kernels; no NCCL call inside the capture)
+    const bool comm_ok = ctx->world == 1 || (ctx->p2p.ready && N <= ctx->p2p.slot_floats);
+    const bool graphable = net && !wolfe && s->graphs_ok && mode == DOTS_FORM_PAIR && comm_ok && !ctx->prof.on &&
                            max_ls > 0 && std::getenv("B200_NO_GRAPH") == nullptr && std::getenv("B200_TC_TIMING") == nullptr;
     if (graphable) {
       const void *key[6] = {net, params, input, target, (const void *)(intptr_t)batch, (const void *)(intptr_t)net->config_gen};
