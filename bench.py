@@ -10,7 +10,7 @@ MNIST-shaped samples, m = 10, fp32-accurate arithmetic. For N > 1 the 60 000 sam
 and the flat gradient (+ loss) is all-reduced with NCCL once per evaluation ("strong" scaling: total work fixed).
 
 value : iterations/s with X, T and the parameters already resident in HBM (CUDA events on the library's stream,
-        max over ranks). The per-iteration working set (142 MB: see config.l2) exceeds L2 (126 MB); no explicit flush.
+        max over ranks). The per-iteration working set (190 MB: see config.l2) exceeds L2 (126 MB); no explicit flush.
 e2e   : the same K iterations through the public C-ABI solve call starting from PINNED HOST buffers: the timed
         region contains the H2D copy of X, T and the parameters, b200_lbfgs_solve (which returns every
         iteration's loss / gradient norm to the host), and the D2H copy of the final parameters.
@@ -287,13 +287,13 @@ def main():
         for k, (calls, tot) in rep.items():
             kernels[k] = {"launches": calls, "avg_us": 1e3 * tot / calls, "share": tot / total_prof}
         # Algorithmic work per launch of the kernels with a roof (shard = samples on this GPU, fp32-accurate mode):
-        #   fwd0  layer-0 forward: 2*B*784*128 flop; reads X (uint8 when the input is 8-bit pixels, else fp32) + writes A1
+        #   fwd0  layer-0 forward: 2*B*784*128 flop; reads X (exact fp16 copy when the input is 8-bit pixels, else fp32) + writes A1
         #   dw0   layer-0 [dW; db]: 2*B*785*128 flop; reads X + delta_0 (fp16 hi|lo = 4 B/element, or fp32) + writes the split-K partials
         #   tail_fwd / tail_bwd  last layer in two passes: read A1 (+ write delta_0): HBM class
         #   lbfgs_direction  two-loop recursion, (4k+2)*n*4 bytes
         B, K0, N0 = shard, DIMS[0], DIMS[1]
         u8 = args.precision != "fp32"
-        x_bytes = B * K0 * (1 if u8 else 4)
+        x_bytes = B * ((K0 + 1 + 7) // 8 * 8) * 2 if u8 else B * K0 * 4  # 8-bit pixels: the fp16 copy [in | 1 | pad] the GEMMs read
         work = {
             "fwd0": dict(flops=2.0 * B * K0 * N0, bytes=x_bytes + 4.0 * B * N0),
             "dw0": dict(flops=2.0 * B * (K0 + 1) * N0, bytes=x_bytes + 4.0 * B * N0),
@@ -339,7 +339,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "memory": MEMORY, "line_search": "armijo (reference CUDA backend)",
                            "precision": args.precision, "samples_per_gpu": shard, "params": n,
-                           "l2": "no flush: iterations run back to back inside one solver call; per-iteration working set at 60 000 samples = X 47 MB (uint8 copy; 188 MB as fp32) + A1 31 MB + delta 31 MB + split-K partials 16 MB + history 9 MB + T/outputs 8 MB = 142 MB > 126 MB L2",
+                           "l2": "no flush: iterations run back to back inside one solver call; per-iteration working set at 60 000 samples = X 95 MB (exact fp16 copy of the 8-bit pixels; 188 MB as fp32) + A1 31 MB + delta 31 MB + split-K partials 16 MB + history 9 MB + T/outputs 8 MB = 190 MB > 126 MB L2",
                            "evals_per_iteration": res["evals"] / args.steps,
                            "parallelism": f"samples sharded x{world}, NCCL allreduce of grad+loss" if world > 1 else "1 GPU"},
                 "gpu_launches": res["launches"],
