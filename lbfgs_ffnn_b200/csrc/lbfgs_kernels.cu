@@ -303,7 +303,44 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
     }
     __syncwarp();
     double gamma = 1.0, cg = -1.0, gdotp = -gg;
-    if (k > 0) {
+    if (k > 0 && k <= 24) {
+      // short histories: ONE lane runs the recurrences serially out of shared memory. A k-term fp64 dot is k dependent FMAs
+      // (~8 clk each); the warp-shuffle version below pays 5 x 2 shuffles of ~25 clk per sum, 3 sums per step.
+      if (lane == 0) {
+        for (int i = k - 1; i >= 0; --i) {
+          const int pi = physp[i];
+          double s = 0.0;
+          for (int j = i + 1; j < k; ++j) s += alpha[j] * SYp[pi * mp + physp[j]];
+          alpha[i] = rhop[pi] * (sgp[pi] - s);
+        }
+        const int pl = physp[k - 1];
+        const double ys = SYp[pl * mp + pl], yy = YYp[pl * mp + pl];
+        if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
+        else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
+        else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
+          gamma = (fabs(yy) < 1e-12) ? 1.0 : ys / yy;
+          gamma = fmin(fmax(gamma, 1e-6), 1e6);
+        }
+        for (int i = 0; i < k; ++i) {
+          const int pi = physp[i];
+          double s1 = 0.0, s2 = 0.0;
+          for (int j = 0; j < k; ++j) s1 += alpha[j] * YYp[pi * mp + physp[j]];
+          for (int j = 0; j < i; ++j) s2 += dlt[j] * SYp[physp[j] * mp + pi];
+          const double beta = rhop[pi] * (gamma * (ygp[pi] - s1) + s2);
+          dlt[i] = alpha[i] - beta;
+        }
+        cg = -gamma;
+        double gp = 0.0;
+        for (int j = 0; j < k; ++j) {
+          const double csj = -dlt[j], cyj = gamma * alpha[j];
+          lcs[j] = csj;
+          lcy[j] = cyj;
+          if (leader) { a.st.cs[j] = csj; a.st.cy[j] = cyj; }
+          gp += csj * sgp[physp[j]] + cyj * ygp[physp[j]];
+        }
+        gdotp = cg * gg + gp;
+      }
+    } else if (k > 0) {
       for (int i = k - 1; i >= 0; --i) {
         const int pi = physp[i];
         double s = 0.0;

@@ -9,6 +9,7 @@
 // transpose-reduce (lane v ends up with value v), so no shared memory is touched until the per-CTA dW combine.
 // HBM-bound by design (bytes: A_{L-1} + delta_{L-1}); fp32 FFMA throughout, so it serves every precision mode.
 #include "network.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
 
@@ -144,7 +145,10 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
 #pragma unroll
     for (int c = 0; c < FPL; ++c)
 #pragma unroll
-      for (int j = 0; j < OLP; ++j) { p0[j] = fmaf(a0[c], w[c][j], p0[j]); p1[j] = fmaf(a1[c], w[c][j], p1[j]); }
+      for (int j = 0; j < OLP; j += 2) { // packed fp32 FMA: two outputs per issue slot
+        tcx::ffma2(p0[j], p0[j + 1], a0[c], a0[c], w[c][j], w[c][j + 1]);
+        tcx::ffma2(p1[j], p1[j + 1], a1[c], a1[c], w[c][j], w[c][j + 1]);
+      }
     const float z = transpose_reduce<OLP>(p0, p1, lane); // pre-activation of (sample smy, output myj)
     if (myj < OL && smy < b1) {
       const float o = act_apply(p.act_last, z + bj);
@@ -179,10 +183,11 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
 }
 
 // ---- pass 2: delta_{L-1} (fp32 for a dX GEMM and / or scaled fp16 hi|lo for the fp16 dW GEMM) and the [dW_L; db_L] partials ----
-template <int FPL, int OLP>
+template <int FPL, int OLP, bool RELU>
 __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
+  static_assert(OLP % 2 == 0, "packed FMAs take the outputs in pairs");
   constexpr int IN = 32 * FPL;
-  __shared__ float red[(IN + 1) * OLP];
+  __shared__ float red[4 * IN * OLP]; // four copies of the dW accumulators (warps w and w + 4 share one)
   __shared__ float mred[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OL = p.out;
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
   // one sample per warp and step; the next sample's activations and delta_L (48 bytes, the same for every lane) are in
   // flight while this one is processed
-  float a[FPL], an[FPL], an2[FPL];
+  float a[FPL], an[FPL], an2[FPL], an3[FPL];
   float4 dv[3], dn[3];
   auto fetch_a = [&](long s, float (&x)[FPL]) {
 #pragma unroll
@@ -248,8 +253,9 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   long s = b0 + warp;
   fetch_a(s, a); fetch_d(s, dv);
   fetch_a(s + 8, an);
+  fetch_a(s + 16, an2);
   for (; s < b1; s += 8) {
-    fetch_a(s + 16, an2); // activations two samples ahead (HBM latency), delta_L one ahead
+    fetch_a(s + 24, an3); // activations three samples ahead (HBM latency), delta_L one ahead
     fetch_d(s + 8, dn);
     float d[OLP];
     {
@@ -260,22 +266,34 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
     float g[FPL];
 #pragma unroll
     for (int c = 0; c < FPL; ++c) {
-      float x = 0.0f;
+      float xe = 0.0f, xo = 0.0f;
 #pragma unroll
-      for (int j = 0; j < OLP; ++j) {
-        x = fmaf(w[c][j], d[j], x);
-        acc[c][j] = fmaf(a[c], d[j], acc[c][j]);
+      for (int j = 0; j < OLP; j += 2) {
+        tcx::ffma2(xe, xo, w[c][j], w[c][j + 1], d[j], d[j + 1]);
+        tcx::ffma2(acc[c][j], acc[c][j + 1], a[c], a[c], d[j], d[j + 1]);
       }
-      g[c] = x * act_deriv_from_output(p.act_prev, a[c]);
+      const float x = xe + xo;
+      g[c] = RELU ? (a[c] > 0.0f ? x : 0.0f) : x * act_deriv_from_output(p.act_prev, a[c]);
     }
     if (p.delta_prev) store_row<FPL>(p.delta_prev + s * IN + lane * FPL, g);
     if (p.d16) { // [s][0..IN) = hi, [s][IN..2 IN) = lo of S * delta
-      __half hi[FPL], lo[FPL];
+      __align__(8) __half hi[FPL], lo[FPL];
+      if constexpr (FPL % 2 == 0) {
 #pragma unroll
-      for (int c = 0; c < FPL; ++c) {
-        const float x = g[c] * S;
-        hi[c] = __float2half_rn(x);
-        lo[c] = __float2half_rn(x - __half2float(hi[c]));
+        for (int c = 0; c < FPL; c += 2) { // packed conversions: 2 values per instruction
+          const float x0 = g[c] * S, x1 = g[c + 1] * S;
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          *reinterpret_cast<__half2 *>(&hi[c]) = h;
+          *reinterpret_cast<__half2 *>(&lo[c]) = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < FPL; ++c) {
+          const float x = g[c] * S;
+          hi[c] = __float2half_rn(x);
+          lo[c] = __float2half_rn(x - __half2float(hi[c]));
+        }
       }
       __half *row = p.d16 + s * (2 * IN) + lane * FPL;
       if constexpr (FPL == 4) {
@@ -290,38 +308,45 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
       }
     }
 #pragma unroll
-    for (int c = 0; c < FPL; ++c) { a[c] = an[c]; an[c] = an2[c]; }
+    for (int c = 0; c < FPL; ++c) { a[c] = an[c]; an[c] = an2[c]; an2[c] = an3[c]; }
     dv[0] = dn[0]; dv[1] = dn[1]; dv[2] = dn[2];
   }
 
-  // ---- per-CTA combine in a fixed warp order (deterministic), then one partial per CTA -------------------------
-  for (int wv = 0; wv < 8; ++wv) {
-    __syncthreads();
-    if (warp == wv) {
+  // ---- per-CTA combine: warps 0-3 park their accumulators, warps 4-7 add theirs on top, then each thread adds the four copies
+  // of its elements in a fixed order (deterministic; three barriers instead of eight serialised rounds) ---------------------
+  if (warp < 4) {
 #pragma unroll
-      for (int c = 0; c < FPL; ++c)
+    for (int c = 0; c < FPL; ++c)
 #pragma unroll
-        for (int j = 0; j < OLP; ++j) {
-          float *slot = &red[(lane * FPL + c) * OLP + j];
-          *slot = (wv == 0) ? acc[c][j] : *slot + acc[c][j];
-        }
-    }
+      for (int j = 0; j < OLP; ++j) red[warp * (IN * OLP) + (lane * FPL + c) * OLP + j] = acc[c][j];
+  }
+  __syncthreads();
+  if (warp >= 4) {
+#pragma unroll
+    for (int c = 0; c < FPL; ++c)
+#pragma unroll
+      for (int j = 0; j < OLP; ++j) red[(warp - 4) * (IN * OLP) + (lane * FPL + c) * OLP + j] += acc[c][j];
   }
   __syncthreads();
   float *dst = p.partial + (size_t)blockIdx.x * (size_t)(IN + 1) * OL; // the bias row was written by tail_fwd_kernel
   for (int e = threadIdx.x; e < IN * OL; e += blockDim.x) {
     const int i = e / OL, j = e - i * OL;
-    dst[e] = red[i * OLP + j];
+    float v = red[i * OLP + j];
+#pragma unroll
+    for (int wv = 1; wv < 4; ++wv) v += red[wv * (IN * OLP) + i * OLP + j];
+    dst[e] = v;
   }
 }
 
 template <int FPL> int launch_tail(b200_ctx *ctx, const TailParams &p, int grid, cudaStream_t st) {
   if (p.out == 10) {
     { ProfScope ps(ctx, "tail_fwd"); B200_LAUNCH((tail_fwd_kernel<FPL, 10>), grid, 256, 0, st, p); }
-    { ProfScope ps(ctx, "tail_bwd"); B200_LAUNCH((tail_bwd_kernel<FPL, 10>), grid, 256, 0, st, p); }
+    { ProfScope ps(ctx, "tail_bwd"); if (p.act_prev == B200_ACT_RELU) B200_LAUNCH((tail_bwd_kernel<FPL, 10, true>), grid, 256, 0, st, p);
+      else B200_LAUNCH((tail_bwd_kernel<FPL, 10, false>), grid, 256, 0, st, p); }
   } else {
     { ProfScope ps(ctx, "tail_fwd"); B200_LAUNCH((tail_fwd_kernel<FPL, 12>), grid, 256, 0, st, p); }
-    { ProfScope ps(ctx, "tail_bwd"); B200_LAUNCH((tail_bwd_kernel<FPL, 12>), grid, 256, 0, st, p); }
+    { ProfScope ps(ctx, "tail_bwd"); if (p.act_prev == B200_ACT_RELU) B200_LAUNCH((tail_bwd_kernel<FPL, 12, true>), grid, 256, 0, st, p);
+      else B200_LAUNCH((tail_bwd_kernel<FPL, 12, false>), grid, 256, 0, st, p); }
   }
   return B200_OK;
 }
