@@ -140,6 +140,31 @@ int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n);
 int ctx_reduce_shards(b200_ctx *ctx, const float *full, float *shard_out, size_t n, size_t chunk);
 int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk);
 
+// ---- speculative iterations (solvers.cu) -----------------------------------------------------------
+// The L-BFGS loop launches the graph of iteration i+1 BEFORE the host has seen the result of iteration i, assuming the first
+// trial point is accepted (the common case). The kernel that finishes an evaluation decides on the device, with the host's own
+// arithmetic, whether that assumption holds (gate_next); every kernel of a speculatively launched graph returns at once when it
+// does not, so a wrong guess costs a few empty launches and the host falls back to its line search.
+struct SpecState {
+  int gate_next;    // 1: the iteration whose evaluation just finished was accepted at its first trial point and has not converged
+  int pad;
+  double loss_prev; // loss at the start of the iteration being evaluated
+  double c1, tol;
+  const double *alpha0, *gdotp; // first step length and g.p of the direction being evaluated (device header fields)
+};
+__device__ __forceinline__ bool spec_skip(const SpecState *st, int spec) {
+  return spec != 0 && st != nullptr && *reinterpret_cast<const volatile int *>(&st->gate_next) == 0;
+}
+// run by the one thread that has just produced (loss, ||g||^2) of an evaluation
+__device__ __forceinline__ void spec_decide(SpecState *st, double loss, double gnorm2) {
+  if (!st) return;
+  const double alpha = (double)(float)*st->alpha0;
+  const bool ok = loss <= st->loss_prev + st->c1 * alpha * *st->gdotp;
+  const bool conv = sqrt(gnorm2) < st->tol;
+  st->gate_next = (ok && !conv) ? 1 : 0;
+  if (ok) st->loss_prev = loss;
+}
+
 // ---- device helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

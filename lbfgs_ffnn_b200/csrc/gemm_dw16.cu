@@ -44,6 +44,8 @@ struct Dw16Params {
   float *partial;         // [split][(in+1)*out]
   unsigned long long partial_stride;
   const float *scale_inv; // device scalar 1 / S of the fp16 delta
+  const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
+  int spec;
   long long *dbg;
 };
 
@@ -75,6 +77,7 @@ template <int NB>
 __global__ void __launch_bounds__(kDThreads, 1)
 dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmOut,
             const Dw16Params p) {
+  if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
   using Plan = DPlan<NB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -356,6 +359,7 @@ int dw16_layer(b200_net *net, const void *x16, int ld16, long batch, bool *done)
   p.partial = net->partials + net->part_off[0];
   p.partial_stride = (unsigned long long)(K0 + 1) * N0;
   p.scale_inv = net->scale16_inv;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
   const dim3 grid(ceil_div(K0 + 1, kDMT * kDM), splits);
   B200_TRY(make_map_3d_d(&tout, p.partial, N0, K0 + 1, splits, 32, 32));
   if (N0 == 128) B200_TRY(launch_dw16<256>(tx, td, tout, p, grid, net->ctx->stream));

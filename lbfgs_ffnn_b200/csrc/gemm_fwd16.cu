@@ -52,6 +52,8 @@ struct F16Params {
   const float *colscale; // [N]: 1 / (255 s_o)
   float *out;            // activations [rows][ld_out]
   long ld_out;
+  const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
+  int spec;
   long long *dbg;        // B200_TC_TIMING: per CTA {total, epilogue busy, epilogue waiting for the accumulator, issuer waiting}
 };
 
@@ -107,6 +109,7 @@ template <int BN, bool X2>
 __global__ void __launch_bounds__(kFThreads, 1)
 fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
              const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmOut, const F16Params p) {
+  if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
   using Plan = FPlan<BN, X2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -303,7 +306,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 constexpr int kSplitNeurons = 8, kSplitMaxK = 1024;
 __global__ void __launch_bounds__(1024) split_w16_kernel(const float *__restrict__ W, int K, int N, int ldk, float pre,
                                                        __half *__restrict__ wh, __half *__restrict__ wlo,
-                                                       float *__restrict__ colscale) {
+                                                       float *__restrict__ colscale, const SpecState *spec_st, int spec) {
+  if (spec_skip(spec_st, spec)) return;
   __shared__ float red[128][kSplitNeurons + 1];
   __shared__ float sc[kSplitNeurons];
   __shared__ __align__(16) __half th[kSplitNeurons][kSplitMaxK + 8], tl[kSplitNeurons][kSplitMaxK + 8];
@@ -438,7 +442,7 @@ int fwd16_prepare(b200_net *net, const float *params) {
   }
   ProfScope ps(net->ctx, "split16");
   B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, net->ctx->stream, params + net->offs[0], K, N, ldk, 1.0f / 255.0f,
-              (__half *)net->w16h, (__half *)net->w16l, net->colscale);
+              (__half *)net->w16h, (__half *)net->w16l, net->colscale, net->spec_st, net->spec_flag);
   net->w16_params = params;
   return B200_OK;
 }
@@ -471,6 +475,7 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const void *x
   p.bias = W + (size_t)K * N;
   p.colscale = net->colscale;
   p.out = net->act[0]; p.ld_out = N;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
   const int grid = std::min(net->ctx->num_sms, p.tiles);
   if (bn == 128) {
     if (x2) B200_TRY((launch_fwd16<128, true>(tx, twh, twl, tout, p, grid, st)));

@@ -395,6 +395,10 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
         if (sd) { h->head = 0; h->count = 0; h->flags |= FLAG_SD_FALLBACK; }
         h->k = kk; h->cg = cg; h->gdotp = gdotp; h->gamma = gamma;
         h->alpha0 = alpha0;
+        if (a.host_hdr) { // zero-copy mailbox: the host reads it after the graph's end event
+          *a.host_hdr = *h;
+          __threadfence_system();
+        }
       }
       s_k = kk; s_cg = cg; s_alpha0 = alpha0;
     }
@@ -503,7 +507,8 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) { 
 
 template <int RPW, bool PAIR>
 __global__ void __launch_bounds__(kDotsThreads) lbfgs_direction_kernel(const DotsArgs da, const SolveArgs sa, const ApplyArgs aa,
-                                                                      unsigned *bar) {
+                                                                      unsigned *bar, const SpecState *spec_st, int spec) {
+  if (spec_skip(spec_st, spec)) return; // every CTA takes the same branch: nobody reaches the grid barrier
   extern __shared__ double sh[];
   __shared__ int s_head0, s_count0;
   if (threadIdx.x == 0) { s_head0 = da.st.h->head; s_count0 = da.st.h->count; } // before anyone can overwrite the header
@@ -659,7 +664,7 @@ int launch_lbfgs_solve(const SolveArgs &a0, int mp, cudaStream_t st) {
 
 // Fused direction: returns false in *done when the shape does not qualify (the caller then issues the three kernels).
 int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da0, const SolveArgs &sa0, const ApplyArgs &aa, int mp, int nblocks,
-                           unsigned *bar, cudaStream_t st, bool *done) {
+                           unsigned *bar, cudaStream_t st, bool *done, const SpecState *spec_st, int spec) {
   *done = false;
   const size_t smem = solve_smem_bytes(mp, true);
   if (mp > kRowsPerLaunch || smem > 16 * 1024 || !bar) return B200_OK;
@@ -673,7 +678,7 @@ int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da0, const SolveArgs &
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDotsThreads, smem));
     if ((long)per_sm * ctx->num_sms < nblocks) return B200_OK; // the grid barrier needs every CTA resident
-    kern<<<nblocks, kDotsThreads, smem, st>>>(da, sa, aa, bar);
+    kern<<<nblocks, kDotsThreads, smem, st>>>(da, sa, aa, bar, spec_st, spec);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA(cudaGetLastError());
     *done = true;

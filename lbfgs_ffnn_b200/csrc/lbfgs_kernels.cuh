@@ -109,6 +109,7 @@ struct SolveArgs {
   double ext_rho;
   int allreduce_done;    // unused on one GPU (partials are already global)
   int stage_gram;        // set by launch_lbfgs_solve: the Gram blocks fit the shared-memory staging area
+  LbfgsHeader *host_hdr; // optional pinned-host copy of the header, written by the leader (replaces a D2H copy node)
 };
 
 struct ApplyArgs {
@@ -128,7 +129,7 @@ int launch_lbfgs_solve(const SolveArgs &a, int mp, cudaStream_t st);
 int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st);
 // dots + solve + apply in one launch (grid-wide barrier); *done = false when the shape does not qualify
 int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da, const SolveArgs &sa, const ApplyArgs &aa, int mp, int nblocks,
-                           unsigned *bar, cudaStream_t st, bool *done);
+                           unsigned *bar, cudaStream_t st, bool *done, const SpecState *spec_st = nullptr, int spec = 0);
 int lbfgs_dots_blocks(b200_ctx *ctx, size_t n);
 int lbfgs_init_state(LbfgsView v, int m, int mod, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int nblocks, int ncols, double *totals, cudaStream_t st);

@@ -43,6 +43,9 @@ struct FinParams {
   EvalOut *out;
   // multi-GPU over peer memory: the gradient goes to this rank's symmetric slot (epoch & 1) instead of `grad`, and the last CTA
   // publishes the loss partial there and raises this rank's flag in every peer's buffer (p2p_reduce_kernel consumes them)
+  double *host_out;   // optional pinned-host {loss, gnorm2}
+  SpecState *spec_st; // decide the speculation gate after the scalars (single GPU) ...
+  int spec;           // ... and skip the whole kernel when launched speculatively on a wrong guess
   char *sym_local;
   char *const *peers;
   unsigned long long slot_bytes, slot_floats;
@@ -58,6 +61,7 @@ __device__ __forceinline__ unsigned *p2p_flags(char *buf, unsigned long long slo
 }
 
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
+  if (spec_skip(p.spec_st, p.spec)) return;
   __shared__ double sh[8][32];
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,6 +135,10 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
     p.out->loss = loss;
     if (p.want_gnorm) p.out->gnorm2 = sg;
     *p.done_count = 0u;
+    if (!p.sym_local && p.want_gnorm) {
+      spec_decide(p.spec_st, loss, sg);
+      if (p.host_out) { p.host_out[0] = loss; p.host_out[1] = sg; __threadfence_system(); }
+    }
     if (p.sym_local) { // publish: loss partial into the slot, then this rank's flag (= epoch + 1) into every peer's buffer
       *reinterpret_cast<double *>(p.sym_local + (epoch & 1u) * p.slot_bytes + p.slot_floats * 4) = loss;
       __threadfence_system();
@@ -154,8 +162,12 @@ struct P2PReduceParams {
   double *fin_part;
   unsigned *done_count;
   EvalOut *out;
+  SpecState *spec_st;
+  int spec;
+  double *host_out;
 };
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p) {
+  if (spec_skip(p.spec_st, p.spec)) return;
   __shared__ double red[32];
   __shared__ bool last;
   unsigned *flags = p2p_flags(p.local, p.slot_bytes);
@@ -203,6 +215,8 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p
     p.out->loss = loss;
     p.out->gnorm2 = s;
     *p.done_count = 0u;
+    spec_decide(p.spec_st, loss, s);
+    if (p.host_out) { p.host_out[0] = loss; p.host_out[1] = s; __threadfence_system(); }
     flags[p.world] = epoch + 1u; // this context's epoch: the slot parity of the next evaluation
   }
 }
@@ -491,6 +505,14 @@ const void *net_x16_lookup(b200_net *net, const float *x, long batch, int *ld16)
   return (const char *)net->xq.data16 + (size_t)row0 * net->xq.ld16 * 2;
 }
 
+// every kernel of an evaluation of (x, batch) honours the speculation gate: fp16 layer-0 GEMMs + one-pass last layer
+bool net_spec_capable(b200_net *net, const float *x, long batch) {
+  int ld16 = 0;
+  return net->nlayers() == 2 && net->prec != B200_PREC_FP32 && tail_applicable(net) && dw16_applicable(net) &&
+         net_x16_lookup(net, x, batch, &ld16) != nullptr && net->dims[1] % 32 == 0 && net->dims[0] % 16 == 0 && net->dims[0] <= 1024 &&
+         std::getenv("B200_FWD16") == nullptr;
+}
+
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch) {
   if (!net->xq.valid || x < net->xq.src) return nullptr;
   const size_t off = (size_t)(x - net->xq.src);
@@ -681,6 +703,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     fp.inv_batch = (double)inv_batch; fp.lam_d = (double)fp.lam;
     fp.want_gnorm = multi ? 0 : 1;
     fp.out = out;
+    fp.spec_st = net->spec_st; fp.spec = net->spec_flag; fp.host_out = net->host_out;
     if (p2p) {
       fp.sym_local = ctx->p2p.local; fp.peers = ctx->p2p.peers_dev;
       fp.slot_bytes = ctx->p2p.slot_bytes; fp.slot_floats = ctx->p2p.slot_floats;
@@ -691,7 +714,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   if (p2p) {
     ProfScope ps(ctx, "allreduce_p2p");
     P2PReduceParams rp{ctx->p2p.peers_dev, ctx->p2p.local, ctx->p2p.slot_bytes, ctx->p2p.slot_floats, net->n, ctx->rank, ctx->world,
-                       grad_out, net->fin_part, net->fin_done, out};
+                       grad_out, net->fin_part, net->fin_done, out, net->spec_st, net->spec_flag, net->host_out};
     const int blocks = std::max(1, std::min(net->fin_blocks, ceil_div((long)((net->n + 3) / 4), 256)));
     B200_LAUNCH(p2p_reduce_kernel, blocks, 256, 0, st, rp);
   } else if (multi) {

@@ -5,6 +5,8 @@
 
 #include <vector>
 
+namespace b200 { struct SpecState; }
+
 struct b200_net {
   b200_ctx *ctx = nullptr;
   std::vector<int> dims; // nlayers + 1
@@ -68,6 +70,10 @@ struct b200_net {
   // bumped whenever a device buffer of this net is (re)allocated or a setting that selects kernels changes: captured CUDA
   // graphs bake both in, so the solvers key their graphs on it
   long config_gen = 0;
+  // set by the L-BFGS solver around a graph capture: gate of speculatively launched evaluations (common.cuh)
+  b200::SpecState *spec_st = nullptr;
+  int spec_flag = 0;
+  double *host_out = nullptr; // pinned-host {loss, gnorm2}: written by the kernel that finishes the evaluation (zero-copy mailbox)
 
   int nlayers() const { return (int)acts.size(); }
 };
@@ -93,6 +99,7 @@ void net_xq_clear(b200_net *net);
 // the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
 const void *net_x16_lookup(b200_net *net, const float *x, long batch, int *ld16);
+bool net_spec_capable(b200_net *net, const float *x, long batch);
 // the skinny last layer in one pass: forward, loss, both deltas and the [dW_L; db_L] partials (tail_layer.cu)
 bool tail_applicable(const b200_net *net);
 int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16);

@@ -26,7 +26,7 @@ struct HostMail { // pinned mailbox layout (ctx->h_scalars, 64 doubles)
   double pad;
   LbfgsHeader hdr;     // copy of the device header after lbfgs_solve_kernel
 };
-static_assert(sizeof(HostMail) <= 64 * sizeof(double), "mailbox overflow");
+static_assert(2 * sizeof(HostMail) + 16 <= 64 * sizeof(double), "mailbox overflow"); // two mailboxes (graph parity) + a scratch double
 
 // Objective seen by the minimizers: either the library's own network (asynchronous, result on the
 // device) or a caller-supplied LossGradFun (synchronous, loss returned on the host).
@@ -47,7 +47,8 @@ struct Objective {
     ++evals;
     if (net) {
       B200_TRY(net_eval(net, x, input, target, batch, batch_global, grad, (EvalOut *)net->eval_out));
-      B200_CUDA(cudaMemcpyAsync(&mail->loss, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
+      if (!net->host_out) // (graph path: the finishing kernel writes the pinned mailbox itself)
+        B200_CUDA(cudaMemcpyAsync(&mail->loss, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
       return B200_OK;
     }
     // reference calling convention (src/cuda/minimizer_base.cuh:15-16): blocking, loss on the host
@@ -71,9 +72,9 @@ struct Timer { // per-iteration wall time of the stream's work, as src/cuda/lbfg
     if (on) t0 = std::chrono::steady_clock::now();
     return B200_OK;
   }
-  int stop() {
+  int stop(bool drain = true) { // drain = false: the caller has this iteration's results already (work queued behind them may run on)
     if (!on) return B200_OK;
-    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (drain) B200_CUDA(cudaStreamSynchronize(ctx->stream));
     elapsed += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return B200_OK;
   }
@@ -141,10 +142,16 @@ struct b200_lbfgs {
   float *gbuf[2] = {nullptr, nullptr}, *p = nullptr, *x_prev = nullptr, *S = nullptr, *Y = nullptr;
   // one CUDA graph per (gradient-buffer parity, history-reset flag): direction kernels + first trial evaluation +
   // the two scalar read-backs of a steady-state iteration are ONE launch instead of ~10
-  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-  long graph_launches[2][2] = {{0, 0}, {0, 0}};
+  // ... and per launch kind: [][][0] launched after the host has accepted the previous iteration, [][][1] launched speculatively
+  // behind it (every kernel gated on the device-side Armijo decision, common.cuh SpecState)
+  cudaGraphExec_t graph[2][2][2] = {};
+  long graph_launches[2][2][2] = {};
+  SpecState *spec_dev = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}; // end of the graph of each parity
+  bool ahead = false;                     // the graph of the CURRENT iteration is already in flight (launched speculatively)
   const void *gkey[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // net, params, input, target, batch, net config generation
   bool graphs_ok = true;
+  bool spec_capable = false; // the captured evaluation consists of gated kernels only
   // minimisation state carried across runs
   bool started = false;
   int cur = 0, iter = 0, reset_next = 0;
@@ -166,7 +173,7 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
     if (c->N == (size_t)n && c->m == o.memory && (c->policy == POLICY_WOLFE) == wolfe && c->sharded == want_sharded) {
       ctx->lbfgs_pool.erase(ctx->lbfgs_pool.begin() + i);
       c->o = o;
-      c->started = false; c->cur = 0; c->iter = 0; c->reset_next = 0; c->loss = 0.0; c->gnorm = 0.0;
+      c->started = false; c->cur = 0; c->iter = 0; c->reset_next = 0; c->loss = 0.0; c->gnorm = 0.0; c->ahead = false;
       B200_CUDA(cudaMemsetAsync(c->ws, 0, c->ws_bytes, ctx->stream));
       B200_CUDA(cudaMemsetAsync(c->gridbar, 0, 2 * sizeof(unsigned), ctx->stream));
       B200_TRY(lbfgs_init_state(c->view, c->m, c->mod, ctx->stream));
@@ -219,6 +226,9 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
   s->totals = (double *)(s->ws + off); off += totals_bytes;
   if (s->sharded) s->gfull = (float *)(s->ws + off);
   B200_CUDA(cudaMalloc(&s->gridbar, 2 * sizeof(unsigned)));
+  B200_CUDA(cudaMalloc(&s->spec_dev, sizeof(SpecState)));
+  B200_CUDA(cudaMemsetAsync(s->spec_dev, 0, sizeof(SpecState), st));
+  for (int i = 0; i < 2; ++i) B200_CUDA(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
   B200_CUDA(cudaMemsetAsync(s->gridbar, 0, 2 * sizeof(unsigned), st));
   B200_TRY(lbfgs_init_state(s->view, s->m, s->mod, st));
   s->apply_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * ctx->num_sms, (s->ld / 4 + 255) / 256));
@@ -228,10 +238,11 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
 
 static void lbfgs_drop_graphs(b200_lbfgs *s) {
   for (int a = 0; a < 2; ++a)
-    for (int b = 0; b < 2; ++b) {
-      if (s->graph[a][b]) cudaGraphExecDestroy(s->graph[a][b]);
-      s->graph[a][b] = nullptr;
-    }
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < 2; ++c) {
+        if (s->graph[a][b][c]) cudaGraphExecDestroy(s->graph[a][b][c]);
+        s->graph[a][b][c] = nullptr;
+      }
 }
 
 static void lbfgs_free(void *p) {
@@ -239,6 +250,8 @@ static void lbfgs_free(void *p) {
   lbfgs_drop_graphs(s);
   cudaFree(s->ws);
   if (s->gridbar) cudaFree(s->gridbar);
+  if (s->spec_dev) cudaFree(s->spec_dev);
+  for (int i = 0; i < 2; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   delete s;
 }
 
@@ -311,16 +324,21 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
 
     // ---- direction: pair formation of the previous step + two-loop + first trial point, 3 launches ----
     const int mode = (iter > 0 && m > 0) ? DOTS_FORM_PAIR : DOTS_NONE;
-    auto issue_direction = [&]() -> int {
-      DotsArgs da{S, Y, N, ld, s->view, g, params, x_prev, g_new, mode, s->reset_next, 0, s->partials};
-      SolveArgs sa{s->view, s->partials, s->nblk, mode, s->reset_next, s->policy, iter == 0 ? 1 : 0, 0, 0.0, 0, 0};
-      ApplyArgs aa{S, Y, N, ld, s->view, g, p, params, x_prev, 1.0, 0.0f, nullptr};
+    // direction of the iteration whose current gradient is gbuf[par] (the other buffer holds the previous gradient, then receives
+    // the trial evaluation's); mailbox mb
+    auto issue_direction_for = [&](int par, int dmode, int reset, int first, HostMail *mb, const SpecState *sst, int spec,
+                                   bool zero_copy = false) -> int {
+      float *gg = s->gbuf[par], *gn = s->gbuf[par ^ 1];
+      DotsArgs da{S, Y, N, ld, s->view, gg, params, x_prev, gn, dmode, reset, 0, s->partials};
+      SolveArgs sa{s->view, s->partials, s->nblk, dmode, reset, s->policy, first, 0, 0.0, 0, 0, zero_copy ? &mb->hdr : nullptr};
+      ApplyArgs aa{S, Y, N, ld, s->view, gg, p, params, x_prev, 1.0, 0.0f, nullptr};
       bool fused = false;
       if (std::getenv("B200_NO_FUSED_DIRECTION") == nullptr) { // one launch: dots -> grid barrier -> solve (every CTA) -> apply
         ProfScope ps(ctx, "lbfgs_direction");
-        B200_TRY(launch_lbfgs_direction(ctx, da, sa, aa, mp, s->nblk, s->gridbar, st, &fused));
+        B200_TRY(launch_lbfgs_direction(ctx, da, sa, aa, mp, s->nblk, s->gridbar, st, &fused, sst, spec));
       }
       if (!fused) {
+        B200_REQUIRE(!spec, "speculative launch needs the fused direction kernel");
         {
           ProfScope ps(ctx, "lbfgs_dots");
           B200_TRY(launch_lbfgs_dots(da, mp, s->nblk, st));
@@ -334,46 +352,94 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
           B200_TRY(launch_lbfgs_apply(aa, s->apply_blocks, st));
         }
       }
-      B200_CUDA(cudaMemcpyAsync(&mail->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
+      if (!(zero_copy && fused)) B200_CUDA(cudaMemcpyAsync(&mb->hdr, s->view.h, sizeof(LbfgsHeader), cudaMemcpyDeviceToHost, st));
       return B200_OK;
     };
+    auto issue_direction = [&]() -> int { return issue_direction_for(s->cur, mode, s->reset_next, iter == 0 ? 1 : 0, mail, nullptr, 0); };
     // Steady-state iterations of the network objective replay a captured graph: direction + first trial evaluation.
-    bool first_eval_issued = false;
+    bool first_eval_issued = false, spec_in_flight = false;
+    HostMail *mm = mail; // where this iteration's first-trial results land
     // several GPUs: only when the gradient all-reduce runs over peer memory (plain kernels; no NCCL call inside the capture)
     const bool comm_ok = ctx->world == 1 || (ctx->p2p.ready && N <= ctx->p2p.slot_floats);
     const bool graphable = net && !wolfe && s->graphs_ok && mode == DOTS_FORM_PAIR && comm_ok && !ctx->prof.on &&
                            max_ls > 0 && std::getenv("B200_NO_GRAPH") == nullptr && std::getenv("B200_TC_TIMING") == nullptr;
-    if (graphable) {
-      const void *key[6] = {net, params, input, target, (const void *)(intptr_t)batch, (const void *)(intptr_t)net->config_gen};
-      if (memcmp(key, s->gkey, sizeof(key)) != 0) {
-        lbfgs_drop_graphs(s);
-        memcpy(s->gkey, key, sizeof(key));
-      }
-      cudaGraphExec_t &ge = s->graph[s->cur][s->reset_next];
+    // graph of the iteration with gradient parity `par`: capture on first use, then launch
+    auto launch_graph = [&](int par, int reset, int spec) -> int {
+      cudaGraphExec_t &ge = s->graph[par][reset][spec];
       if (!ge) {
         const long l0 = b200_launch_count();
         cudaGraph_t gr = nullptr;
+        const bool gate = s->spec_capable;
+        net->spec_st = gate ? s->spec_dev : nullptr;
+        net->spec_flag = spec;
+        const bool zc = std::getenv("B200_NO_ZERO_COPY") == nullptr; // kernels write the pinned mailbox: no D2H copy nodes in the graph
+        net->host_out = zc ? &mail[par].loss : nullptr;
         bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
-          ok = issue_direction() == B200_OK && obj.eval_async(params, g_new, mail, &cb_loss) == B200_OK;
+          ok = issue_direction_for(par, DOTS_FORM_PAIR, reset, 0, mail + par, gate ? s->spec_dev : nullptr, spec, zc) == B200_OK &&
+               obj.eval_async(params, s->gbuf[par ^ 1], mail + par, &cb_loss) == B200_OK;
           --obj.evals; // counted when the graph is replayed
           ok = (cudaStreamEndCapture(st, &gr) == cudaSuccess) && ok && gr != nullptr;
         }
+        net->spec_st = nullptr;
+        net->spec_flag = 0;
+        net->host_out = nullptr;
         if (ok) ok = cudaGraphInstantiate(&ge, gr, 0) == cudaSuccess;
         if (gr) cudaGraphDestroy(gr);
-        s->graph_launches[s->cur][s->reset_next] = b200_launch_count() - l0;
+        s->graph_launches[par][reset][spec] = b200_launch_count() - l0;
         g_launches.fetch_add(-(b200_launch_count() - l0), std::memory_order_relaxed); // captured, not executed
         if (!ok) {
           cudaGetLastError();
           ge = nullptr;
           s->graphs_ok = false; // fall back to plain launches for the rest of this solver's life
+          return B200_OK;
         }
       }
-      if (ge) {
-        B200_CUDA(cudaGraphLaunch(ge, st));
-        g_launches.fetch_add(s->graph_launches[s->cur][s->reset_next], std::memory_order_relaxed);
-        ++obj.evals;
+      B200_CUDA(cudaGraphLaunch(ge, st));
+      B200_CUDA(cudaEventRecord(s->ev[par], st));
+      g_launches.fetch_add(s->graph_launches[par][reset][spec], std::memory_order_relaxed);
+      ++obj.evals;
+      return B200_OK;
+    };
+    if (graphable) {
+      const void *key[6] = {net, params, input, target, (const void *)(intptr_t)batch, (const void *)(intptr_t)net->config_gen};
+      if (memcmp(key, s->gkey, sizeof(key)) != 0) {
+        lbfgs_drop_graphs(s);
+        memcpy(s->gkey, key, sizeof(key));
+        s->ahead = false;
+        // the evaluation consists of gated kernels only (fp16 layer-0 GEMMs + one-pass last layer + fused direction)?
+        s->spec_capable = std::getenv("B200_NO_SPECULATION") == nullptr && std::getenv("B200_NO_FUSED_DIRECTION") == nullptr &&
+                          mp <= kRowsPerLaunch && net_spec_capable(net, input, batch);
+        if (s->spec_capable) {
+          SpecState hs{};
+          hs.gate_next = 0; hs.loss_prev = loss; hs.c1 = (double)o.c1; hs.tol = (double)o.tol;
+          hs.alpha0 = &s->view.h->alpha0; hs.gdotp = &s->view.h->gdotp;
+          B200_CUDA(cudaMemcpyAsync(s->spec_dev, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+          B200_CUDA(cudaStreamSynchronize(st)); // hs is a stack object
+        }
+      }
+      if (s->ahead) { // launched behind the previous iteration and confirmed by its result
         first_eval_issued = true;
+      } else {
+        if (s->spec_capable) { // the device-side decision of THIS iteration starts from the host's loss
+          double *slot = ctx->h_scalars + 62;
+          *slot = loss;
+          B200_CUDA(cudaMemcpyAsync(&s->spec_dev->loss_prev, slot, sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        const long e0 = obj.evals;
+        B200_TRY(launch_graph(s->cur, s->reset_next, 0));
+        first_eval_issued = obj.evals > e0;
+      }
+      s->ahead = false;
+      if (first_eval_issued) {
+        mm = mail + s->cur;
+        // speculate: the next iteration's graph goes in right behind this one; its kernels return at once unless the device finds
+        // this iteration's first trial point accepted (Armijo) and not converged
+        if (s->spec_capable && s->graphs_ok && it + 1 < iters && m > 0) {
+          const long e0 = obj.evals;
+          B200_TRY(launch_graph(s->cur ^ 1, 0, 1));
+          spec_in_flight = obj.evals > e0;
+        }
       }
     }
     if (!first_eval_issued) B200_TRY(issue_direction());
@@ -387,13 +453,24 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
       double gdotp = 0.0;
       for (int ls = 0; ls < max_ls; ++ls) {
         if (ls > 0) B200_TRY(launch_trial_point(N, x_prev, (float)alpha, p, params, st)); // lbfgs.cuh:116-117
+        HostMail *mr = (ls == 0) ? mm : mail;
         if (!(ls == 0 && first_eval_issued)) B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
-        B200_CUDA(cudaStreamSynchronize(st));
-        if (ls == 0) { alpha = (double)(float)mail->hdr.alpha0; gdotp = mail->hdr.gdotp; }
-        loss_new = net ? mail->loss : cb_loss;
-        gnorm2_new = mail->gnorm2;
+        if (ls == 0 && spec_in_flight) B200_CUDA(cudaEventSynchronize(s->ev[s->cur])); // only THIS iteration's graph
+        else B200_CUDA(cudaStreamSynchronize(st));
+        if (ls == 0) { alpha = (double)(float)mr->hdr.alpha0; gdotp = mr->hdr.gdotp; }
+        loss_new = net ? mr->loss : cb_loss;
+        gnorm2_new = mr->gnorm2;
         evaluated = true;
-        if (loss_new <= loss + (double)o.c1 * alpha * gdotp) { armijo_ok = true; break; }
+        if (loss_new <= loss + (double)o.c1 * alpha * gdotp) {
+          armijo_ok = true;
+          // the speculative graph runs exactly when the device took this branch and the run has not converged
+          if (ls == 0 && spec_in_flight) {
+            if (std::sqrt(gnorm2_new) < (double)o.tol) --obj.evals; else s->ahead = true;
+            spec_in_flight = false;
+          }
+          break;
+        }
+        if (ls == 0 && spec_in_flight) { --obj.evals; spec_in_flight = false; } // gated off on the device: empty launches
         const double denom = 2.0 * (loss_new - loss - gdotp * alpha);
         bool fallback = true;
         if (std::fabs(denom) > 1e-20) {
@@ -467,7 +544,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
     s->loss = loss_new;
     s->gnorm = std::sqrt(gnorm2_new);
     s->iter = iter + 1;
-    B200_TRY(timer.stop());
+    B200_TRY(timer.stop(!s->ahead));
     record(hist, iterations_done, s->loss, s->gnorm, timer.elapsed);
     ++iterations_done;
   }

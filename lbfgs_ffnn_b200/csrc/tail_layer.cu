@@ -37,6 +37,8 @@ struct TailParams {
   int chunk;           // samples per CTA (even)
   int out, ldd, act_last, act_prev;
   float inv_batch;
+  const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
+  int spec;
 };
 
 template <int FPL> struct VecT;
@@ -109,6 +111,7 @@ __device__ __forceinline__ float transpose_reduce(const float (&p0)[OLP], const 
 // OLP: compile-time padded output count (10 = the MNIST fast path, 12 = anything up to 12 with zero-padded weights)
 template <int FPL, int OLP>
 __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
+  if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int IN = 32 * FPL;
   __shared__ double lred[32];
   __shared__ float mred[8];
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
 template <int FPL, int OLP, bool RELU>
 __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   static_assert(OLP % 2 == 0, "packed FMAs take the outputs in pairs");
+  if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int IN = 32 * FPL;
   __shared__ float red[4 * IN * OLP]; // four copies of the dW accumulators (warps w and w + 4 share one)
   __shared__ float mred[8];
@@ -396,6 +400,7 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   p.out = out; p.ldd = net->ldd[L - 1];
   p.act_last = net->acts[L - 1]; p.act_prev = net->acts[L - 2];
   p.inv_batch = inv_batch;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
   const int max_grid = std::min(std::min(net->skinny_splits[L - 1], net->loss_part_cap), 2 * net->ctx->num_sms);
   int grid = std::max(1, std::min(max_grid, ceil_div(batch, 32)));
   p.chunk = ceil_div(ceil_div(batch, grid), 16) * 16;
