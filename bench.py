@@ -317,9 +317,16 @@ def main():
                 rooflines[k] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
             rooflines[k].update({"avg_launch_us": avg_s * 1e6, "share_of_step": tot / total_prof, "alg_flops": w["flops"],
                                  "alg_bytes": w["bytes"], "tensor_TFLOPs": w["flops"] / avg_s / 1e12})
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this command (profiles/r01_traffic.json)
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and world == 1 and args.precision == "tf32x3":
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {})
+        for k in rooflines:
+            rooflines[k]["traffic"] = traffic.get(k)
         if rooflines:
             dom = max(rooflines, key=lambda k: rooflines[k]["share_of_step"])
-            roofline = dict(kernel=dom, traffic=None, **rooflines[dom])
+            roofline = dict(kernel=dom, **rooflines[dom])
             roofline["peak_note"] = (f"{pk['source']} peaks: HBM {pk['hbm']} GB/s, dense 16-bit tensor {tensor_peak} TFLOP/s sustained; the bound is "
                                      f"the larger of bytes/HBM and flops/tensor for the kernel's ALGORITHMIC work; precision mode {args.precision}; "
                                      "lbfgs_direction streams an L2-resident history at this size (latency-bound)")

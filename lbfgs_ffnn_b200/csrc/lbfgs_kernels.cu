@@ -604,6 +604,13 @@ __global__ void __launch_bounds__(256) dot_final_kernel(const double *part, int 
   if (threadIdx.x == 0) *out = s;
 }
 
+// profiling aid: keeps the GPU busy for ~`clocks` SM clocks so that the host can enqueue the next events and launches behind it;
+// without it the first profiled kernel after a host synchronisation is charged the host's launch latency
+__global__ void prof_spacer_kernel(long long clocks) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < clocks) {}
+}
+
 inline int vec_blocks(size_t n, int cap) { return (int)std::max<size_t>(1, std::min<size_t>((size_t)cap, (n + 255) / 256)); }
 
 } // namespace
@@ -717,6 +724,12 @@ int lbfgs_init_state(LbfgsView v, int m, int mod, cudaStream_t st) {
 int launch_lbfgs_store_pair(float *S, float *Y, size_t n, size_t ld, LbfgsView stv, const float *s, const float *y,
                             cudaStream_t stream) {
   B200_LAUNCH(store_pair_kernel, vec_blocks(n, 1184), 256, 0, stream, S, Y, n, ld, stv, s, y);
+  return B200_OK;
+}
+
+int launch_prof_spacer(cudaStream_t st) {
+  prof_spacer_kernel<<<1, 1, 0, st>>>(80000); // ~40 us; not counted as a product launch
+  B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
 

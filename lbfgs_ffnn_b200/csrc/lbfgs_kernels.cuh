@@ -137,6 +137,7 @@ int launch_reduce_partials(const double *partials, int nblocks, int ncols, doubl
 int launch_lbfgs_store_pair(float *S, float *Y, size_t n, size_t ld, LbfgsView st, const float *s, const float *y,
                             cudaStream_t stream);
 
+int launch_prof_spacer(cudaStream_t st); // per-launch profiling only (see lbfgs_kernels.cu)
 // y = x0 + alpha * p
 int launch_trial_point(size_t n, const float *x0, float alpha, const float *p, float *y, cudaStream_t st);
 // two-stage deterministic dot: *out = x.y (double, device). part must hold >= dot_blocks() doubles.

@@ -333,6 +333,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
       SolveArgs sa{s->view, s->partials, s->nblk, dmode, reset, s->policy, first, 0, 0.0, 0, 0, zero_copy ? &mb->hdr : nullptr};
       ApplyArgs aa{S, Y, N, ld, s->view, gg, p, params, x_prev, 1.0, 0.0f, nullptr};
       bool fused = false;
+      if (ctx->prof.on) B200_TRY(launch_prof_spacer(st)); // the events below are then enqueued behind running work, not on an idle GPU
       if (std::getenv("B200_NO_FUSED_DIRECTION") == nullptr) { // one launch: dots -> grid barrier -> solve (every CTA) -> apply
         ProfScope ps(ctx, "lbfgs_direction");
         B200_TRY(launch_lbfgs_direction(ctx, da, sa, aa, mp, s->nblk, s->gridbar, st, &fused, sst, spec));
