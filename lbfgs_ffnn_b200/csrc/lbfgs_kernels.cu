@@ -212,8 +212,15 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
   for (int c0 = 0; c0 < ncols; c0 += 32) {
     const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     double s = 0.0;
-    if (c < ncols)
-      for (int b = sub; b < a.nblocks; b += 8) s += __ldcg(a.partials + (size_t)b * ncols + c);
+    if (c < ncols) {
+      for (int b0 = sub; b0 < a.nblocks; b0 += 64) { // eight independent loads in flight per step, same summation order
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (b0 + 8 * u < a.nblocks) ? __ldcg(a.partials + (size_t)(b0 + 8 * u) * ncols + c) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += t[u];
+      }
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -442,14 +449,24 @@ __device__ __forceinline__ void apply_body(const ApplyArgs &a, int k, double cg_
     const size_t i = v * 4;
     const float4 g4 = ld4c<COHERENT>(a.g, i, a.n, vec);
     double r0 = cg * g4.x, r1 = cg * g4.y, r2 = cg * g4.z, r3 = cg * g4.w;
-    for (int j = 0; j < k; ++j) {
-      const float4 s4 = ld4c<COHERENT>(a.S + (size_t)s_ph[j] * a.ld, i, a.n, vec);
-      const float4 y4 = ld4c<COHERENT>(a.Y + (size_t)s_ph[j] * a.ld, i, a.n, vec);
-      const double cs = s_cs[j] * a.sign, cy = s_cy[j] * a.sign;
-      r0 = fma(cs, (double)s4.x, r0); r1 = fma(cs, (double)s4.y, r1);
-      r2 = fma(cs, (double)s4.z, r2); r3 = fma(cs, (double)s4.w, r3);
-      r0 = fma(cy, (double)y4.x, r0); r1 = fma(cy, (double)y4.y, r1);
-      r2 = fma(cy, (double)y4.z, r2); r3 = fma(cy, (double)y4.w, r3);
+    for (int j0 = 0; j0 < k; j0 += 4) { // four pairs (eight 16-byte loads) in flight per step; same order of the fp64 sums
+      float4 s4[4], y4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, k - 1);
+        s4[u] = ld4c<COHERENT>(a.S + (size_t)s_ph[j] * a.ld, i, a.n, vec);
+        y4[u] = ld4c<COHERENT>(a.Y + (size_t)s_ph[j] * a.ld, i, a.n, vec);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < k) {
+          const double cs = s_cs[j0 + u] * a.sign, cy = s_cy[j0 + u] * a.sign;
+          r0 = fma(cs, (double)s4[u].x, r0); r1 = fma(cs, (double)s4[u].y, r1);
+          r2 = fma(cs, (double)s4[u].z, r2); r3 = fma(cs, (double)s4[u].w, r3);
+          r0 = fma(cy, (double)y4[u].x, r0); r1 = fma(cy, (double)y4[u].y, r1);
+          r2 = fma(cy, (double)y4[u].z, r2); r3 = fma(cy, (double)y4[u].w, r3);
+        }
+      }
     }
     const float4 p4 = make_float4((float)r0, (float)r1, (float)r2, (float)r3);
     st4(a.p, i, a.n, vec, p4);
