@@ -44,6 +44,7 @@ struct Dw16Params {
   float *partial;         // [split][(in+1)*out]
   unsigned long long partial_stride;
   const float *scale_inv; // device scalar 1 / S of the fp16 delta
+  int row0;               // first sample of this evaluation inside the fp16 copy of the input
   const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
   int spec;
   long long *dbg;
@@ -126,7 +127,7 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         for (int t = 0; t < nmt; ++t)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            tma_load_2d(conv_a(s) + t * kDConvTile + j * kDAtom, &tmX, conv_full(s), m0 + t * kDM + 64 * j, kb * kDK);
+            tma_load_3d(conv_a(s) + t * kDConvTile + j * kDAtom, &tmX, conv_full(s), 0, p.row0 + kb * kDK, (m0 + t * kDM) / 64 + j);
         if (++s == kDNS) { s = 0; ph ^= 1; }
       }
     }
@@ -265,6 +266,29 @@ int make_map_2d_d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsi
   return B200_OK;
 }
 
+// fp16 {dim0 contiguous, dim1, dim2} with dense strides, box {box0, box1, 1}, SWIZZLE_128B (the block-major fp16 input copy)
+int make_map_3d_h(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
+                  unsigned box0, unsigned box1) {
+  void *fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {dim0 * 2, dim0 * dim1 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((EncodeTiledFn)fp)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d fp16) failed (%d): dims %llu x %llu x %llu ptr %p", (int)r, dim0, dim1, dim2, ptr);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
 // fp32 {dim0 contiguous, dim1, dim2} with dense strides, box {box0, box1, 1}, SWIZZLE_128B (the split-K partial tensor)
 int make_map_3d_d(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
                   unsigned box0, unsigned box1) {
@@ -341,14 +365,14 @@ int dw16_plan(const b200_net *net, long batch, int *splits) {
 }
 
 // layer 0 [dW; db] partials from the uint8 input copy and the fp16 {hi | lo} delta written by tail_layer(want16)
-int dw16_layer(b200_net *net, const void *x16, int ld16, long batch, bool *done) {
+int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done) {
   *done = false;
-  if (!x16 || !net->delta16) return B200_OK;
+  if (!x16.base || !net->delta16) return B200_OK;
   const int K0 = net->dims[0], N0 = net->dims[1];
   CUtensorMap tx, td, tout;
-  // K0 + 1 columns: column K0 of the fp16 copy is the ones feature, whose row of D is the bias gradient
-  B200_TRY(make_map_2d_d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x16, K0 + 1, batch, (unsigned long long)ld16 * 2, 64, kDK,
-                         CU_TENSOR_MAP_SWIZZLE_128B));
+  // A atoms: box {64 features, 32 samples, 1 block} of the block-major fp16 copy = 4 contiguous KB each; feature K0 reads 1
+  // (its row of D is the bias gradient), blocks past the last one are out of bounds = zero
+  B200_TRY(make_map_3d_h(&tx, x16.base, 64, (unsigned long long)x16.rows_total, (unsigned long long)x16.nblocks, 64, kDK));
   B200_TRY(make_map_2d_d(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->delta16, 2 * N0, batch, (unsigned long long)2 * N0 * 2, 64, kDK,
                          CU_TENSOR_MAP_SWIZZLE_128B));
   int splits = 1;
@@ -359,6 +383,7 @@ int dw16_layer(b200_net *net, const void *x16, int ld16, long batch, bool *done)
   p.partial = net->partials + net->part_off[0];
   p.partial_stride = (unsigned long long)(K0 + 1) * N0;
   p.scale_inv = net->scale16_inv;
+  p.row0 = (int)x16.row0;
   p.spec_st = net->spec_st; p.spec = net->spec_flag;
   const dim3 grid(ceil_div(K0 + 1, kDMT * kDM), splits);
   B200_TRY(make_map_3d_d(&tout, p.partial, N0, K0 + 1, splits, 32, 32));

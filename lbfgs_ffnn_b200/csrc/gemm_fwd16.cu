@@ -47,6 +47,7 @@ constexpr int kStageOutBytes = 32 * 128;      // per epilogue warp: one [32 rows
 
 struct F16Params {
   int rows_valid, cols_valid, k_total, k_blocks, tiles;
+  int row0;              // first sample of this evaluation inside the fp16 copy of the input
   int act;
   const float *bias;     // [N]
   const float *colscale; // [N]: 1 / (255 s_o)
@@ -163,7 +164,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(conv_empty(s), ph ^ 1);
           mbar_expect_tx(conv_full(s), kConvBytes);
-          tma_load_2d(conv_a(s), &tmX, conv_full(s), kb * kFK, tile * kFM);
+          tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
           if (++s == kNC) { s = 0; ph ^= 1; }
         }
       }
@@ -384,6 +385,29 @@ int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsign
   return B200_OK;
 }
 
+// fp16 {dim0 contiguous, dim1, dim2} with dense strides, box {box0, box1, 1}, SWIZZLE_128B (the block-major fp16 input copy)
+int make_map_3d(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
+                unsigned box0, unsigned box1) {
+  void *fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {dim0 * 2, dim0 * dim1 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((EncodeTiledFn)fp)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d fp16) failed (%d): dims %llu x %llu x %llu ptr %p", (int)r, dim0, dim1, dim2, ptr);
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
 template <int BN, bool X2>
 int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const CUtensorMap &tout, const F16Params &p, int grid,
                  cudaStream_t st) {
@@ -448,9 +472,9 @@ int fwd16_prepare(b200_net *net, const float *params) {
 }
 
 // Layer 0 forward on the fp16 copy of an 8-bit-pixel input (x16: rows of ld16 halves, value u = 255 x). Sets *done when it ran.
-int fwd16_forward_layer(b200_net *net, int l, const float *params, const void *x16, int ld16, long batch, bool *done) {
+int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View &x16, long batch, bool *done) {
   *done = false;
-  if (l != 0 || !x16 || !fwd16_shape_ok(net) || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
+  if (l != 0 || !x16.base || !fwd16_shape_ok(net) || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;
   if (net->w16_params != params) B200_TRY(fwd16_prepare(net, params)); // callers normally prepare before the sweep
   const int K = net->dims[0], N = net->dims[1];
   const bool x2 = net->prec == B200_PREC_TF32X3;
@@ -458,8 +482,8 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const void *x
   cudaStream_t st = net->ctx->stream;
   const float *W = params + net->offs[0];
   CUtensorMap tx, twh, twl, tout;
-  // only the K real features are visible through this map (the ones column at index K belongs to the dW kernel)
-  B200_TRY(make_map_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x16, K, batch, (unsigned long long)ld16 * 2, kFK, kFM, CU_TENSOR_MAP_SWIZZLE_128B));
+  // X tiles: box {64 features, 128 samples, 1 block} of the block-major fp16 copy = 16 contiguous KB of DRAM each
+  B200_TRY(make_map_3d(&tx, x16.base, 64, (unsigned long long)x16.rows_total, (unsigned long long)x16.nblocks, 64, kFM));
   const unsigned bn = N > 64 ? 128 : 64;
   B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16h, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
                        CU_TENSOR_MAP_SWIZZLE_128B));
@@ -469,6 +493,7 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const void *x
                        CU_TENSOR_MAP_SWIZZLE_128B)); // activations [batch][N], stored as [32 rows][32 floats] boxes
   F16Params p{};
   p.rows_valid = (int)batch; p.cols_valid = N; p.k_total = K;
+  p.row0 = (int)x16.row0;
   p.k_blocks = ceil_div(K, kFK);
   p.tiles = ceil_div(batch, kFM);
   p.act = net->acts[0];

@@ -693,9 +693,8 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   // layer 0 with an input that is exactly u/255: read the 4x smaller uint8 copy (net_quantize_input)
   const uint8_t *xq = (l == 0 && (tc_mask() & 16) == 0) ? net_xq_lookup(net, in, batch) : nullptr;
   if (xq && !fuse) { // persistent fp16 kernel (gemm_fwd16.cu); the last layer then runs in tail_layer.cu
-    int ld16 = 0;
-    const void *x16 = net_x16_lookup(net, in, batch, &ld16);
-    B200_TRY(fwd16_forward_layer(net, l, params, x16, ld16, batch, done));
+    X16View xv;
+    if (net_x16_view(net, in, batch, &xv)) B200_TRY(fwd16_forward_layer(net, l, params, xv, batch, done));
     if (*done) return B200_OK;
   }
   B200_TRY(tc_ensure_split(net));

@@ -18,12 +18,12 @@ int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done);
 int tc_dw_plan(b200_net *net, int l, long batch, int *splits);
 int tc_split_params(b200_net *net, const float *params);
 // persistent fp16 forward of layer 0 on the uint8 copy of the input (gemm_fwd16.cu)
-int fwd16_forward_layer(b200_net *net, int l, const float *params, const void *x16, int ld16, long batch, bool *done);
+int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View &x16, long batch, bool *done);
 int fwd16_prepare(b200_net *net, const float *params);
 void fwd16_release(b200_net *net);
 // fp16 dW of layer 0 from the uint8 input copy and the fp16 {hi | lo} delta of tail_layer (gemm_dw16.cu)
 bool dw16_applicable(const b200_net *net);
-int dw16_layer(b200_net *net, const void *x16, int ld16, long batch, bool *done);
+int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done);
 void tc_release(b200_net *net);
 
 } // namespace b200

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restri
 // x -> u = round(255 x) as uint8 AND as fp16 (exact: u <= 255 has 8 significant bits); *flag &= (every x is exactly
 // float(u)/255.0f with 0 <= u <= 255). The fp16 rows are [in | 1 | zero padding] with ld16 halves per row: column `in` is the
 // ones feature whose "weight gradient" is the bias gradient (gemm_dw16.cu), and TMA feeds the rows to the tensor cores as they are.
-__global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n, int in, int ld16,
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n, int in, int nblocks16,
                                                           uint8_t *__restrict__ q, __half *__restrict__ q16, int *flag) {
   int ok = 1;
   const unsigned long long nv = n / 4;
@@ -371,12 +371,13 @@ __global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restric
     }
     reinterpret_cast<unsigned *>(q)[v] = packed;
     const unsigned long long e0 = v * 4, row = e0 / (unsigned)in, col = e0 - row * (unsigned)in; // in % 4 == 0: one row per vector
-    *reinterpret_cast<uint2 *>(q16 + row * ld16 + col) = *reinterpret_cast<const uint2 *>(hv);
+    const unsigned long long rows_all = n / (unsigned)in;
+    *reinterpret_cast<uint2 *>(q16 + ((col >> 6) * rows_all + row) * 64 + (col & 63)) = *reinterpret_cast<const uint2 *>(hv);
   }
   const unsigned long long rows = n / (unsigned)in;
   for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
        r += (unsigned long long)gridDim.x * blockDim.x) {
-    for (int c = in; c < ld16; ++c) q16[r * ld16 + c] = __float2half_rn(c == in ? 1.0f : 0.0f);
+    for (int c = in; c < 64 * nblocks16; ++c) q16[((unsigned long long)(c >> 6) * rows + r) * 64 + (c & 63)] = __float2half_rn(c == in ? 1.0f : 0.0f);
   }
   if (!__all_sync(0xffffffffu, ok)) {
     if ((threadIdx.x & 31) == 0) atomicAnd(flag, 0);
@@ -461,7 +462,7 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
   if (in % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0 || batch <= 0) return B200_OK;
   const size_t bytes = (size_t)batch * in;
   cudaStream_t st = net->ctx->stream;
-  const int ld16 = (in + 1 + 7) & ~7;
+  const int nb16 = (in + 1 + 63) / 64;
   if (bytes > net->xq.cap) {
     if (net->xq.data) cudaFree(net->xq.data);
     if (net->xq.data16) cudaFree(net->xq.data16);
@@ -469,15 +470,15 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
     net->xq.data16 = nullptr;
     net->xq.cap = 0;
     B200_CUDA(cudaMalloc(&net->xq.data, bytes));
-    B200_CUDA(cudaMalloc(&net->xq.data16, sizeof(__half) * (size_t)batch * ld16));
-    net->xq.ld16 = ld16;
+    B200_CUDA(cudaMalloc(&net->xq.data16, sizeof(__half) * (size_t)batch * 64 * nb16));
+    net->xq.nblocks16 = nb16;
     ++net->config_gen;
     net->xq.cap = bytes;
   }
   if (!net->xq.flag) B200_CUDA(cudaMalloc(&net->xq.flag, sizeof(int)));
   const int one = 1;
   B200_CUDA(cudaMemcpyAsync(net->xq.flag, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-  B200_LAUNCH(quantize_u8_kernel, 8 * net->ctx->num_sms, 256, 0, st, x, (unsigned long long)bytes, in, ld16, net->xq.data,
+  B200_LAUNCH(quantize_u8_kernel, 8 * net->ctx->num_sms, 256, 0, st, x, (unsigned long long)bytes, in, nb16, net->xq.data,
               (__half *)net->xq.data16, net->xq.flag);
   int ok = 0;
   B200_CUDA(cudaMemcpyAsync(&ok, net->xq.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -493,23 +494,25 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
   return B200_OK;
 }
 
-// the fp16 rows matching x (row-aligned sub-range of the quantised input), or nullptr; *ld16 = halves per row
-const void *net_x16_lookup(b200_net *net, const float *x, long batch, int *ld16) {
-  if (!net->xq.valid || !net->xq.data16 || x < net->xq.src) return nullptr;
+bool net_x16_view(b200_net *net, const float *x, long batch, X16View *v) {
+  if (!net->xq.valid || !net->xq.data16 || x < net->xq.src) return false;
   const size_t off = (size_t)(x - net->xq.src);
   const int in = net->dims[0];
-  if (off % in != 0) return nullptr;
+  if (off % in != 0) return false;
   const long row0 = (long)(off / in);
-  if (row0 + batch > net->xq.rows) return nullptr;
-  *ld16 = net->xq.ld16;
-  return (const char *)net->xq.data16 + (size_t)row0 * net->xq.ld16 * 2;
+  if (row0 + batch > net->xq.rows) return false;
+  v->base = net->xq.data16;
+  v->rows_total = net->xq.rows;
+  v->row0 = row0;
+  v->nblocks = net->xq.nblocks16;
+  return true;
 }
 
 // every kernel of an evaluation of (x, batch) honours the speculation gate: fp16 layer-0 GEMMs + one-pass last layer
 bool net_spec_capable(b200_net *net, const float *x, long batch) {
-  int ld16 = 0;
+  X16View xv;
   return net->nlayers() == 2 && net->prec != B200_PREC_FP32 && tail_applicable(net) && dw16_applicable(net) &&
-         net_x16_lookup(net, x, batch, &ld16) != nullptr && net->dims[1] % 32 == 0 && net->dims[0] % 16 == 0 && net->dims[0] <= 1024 &&
+         net_x16_view(net, x, batch, &xv) && net->dims[1] % 32 == 0 && net->dims[0] % 16 == 0 && net->dims[0] <= 1024 &&
          std::getenv("B200_FWD16") == nullptr;
 }
 
@@ -646,9 +649,8 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       ProfScope ps(ctx, nm);
       bool done = false;
       if (l == 0 && use_dw16) {
-        int ld16 = 0;
-        const void *x16 = net_x16_lookup(net, x, batch, &ld16);
-        B200_TRY(dw16_layer(net, x16, ld16, batch, &done));
+        X16View xv;
+        if (net_x16_view(net, x, batch, &xv)) B200_TRY(dw16_layer(net, xv, batch, &done));
       }
       if (!done && net->prec != B200_PREC_FP32) B200_TRY(tc_dw_layer(net, l, in, batch, &done));
       if (!done && N <= 16 && K + 1 <= 160 && net->prec != B200_PREC_FP32) {

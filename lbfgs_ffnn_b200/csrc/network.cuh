@@ -42,8 +42,11 @@ struct b200_net {
     const float *src = nullptr;
     long rows = 0;
     uint8_t *data = nullptr;
-    void *data16 = nullptr; // fp16 rows [in | 1 | 0-pad], ld16 halves each: TMA-ready operand of the fp16 layer-0 kernels
-    int ld16 = 0;
+    // fp16 copy (value u), FEATURE-BLOCK-major: [nblocks16][rows][64 halves]; block b holds features 64 b .. 64 b + 63 of every
+    // sample, feature `in` reads 1 (the bias-gradient row of dW), the rest of the last block 0. Every operand tile of the fp16 layer-0
+    // kernels ([128 samples][64 features] forward, [32 samples][64 features] dW) is then ONE contiguous chunk of DRAM.
+    void *data16 = nullptr;
+    int nblocks16 = 0;
     size_t cap = 0;
     bool valid = false;
     int *flag = nullptr; // device
@@ -98,7 +101,9 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh =
 void net_xq_clear(b200_net *net);
 // the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
-const void *net_x16_lookup(b200_net *net, const float *x, long batch, int *ld16);
+struct X16View { const void *base; long rows_total, row0; int nblocks; };
+// the fp16 copy and the row range matching x (row-aligned sub-range of the quantised input); false if there is none
+bool net_x16_view(b200_net *net, const float *x, long batch, X16View *v);
 bool net_spec_capable(b200_net *net, const float *x, long batch);
 // the skinny last layer in one pass: forward, loss, both deltas and the [dW_L; db_L] partials (tail_layer.cu)
 bool tail_applicable(const b200_net *net);
