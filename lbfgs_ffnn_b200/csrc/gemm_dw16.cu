@@ -351,7 +351,9 @@ bool dw16_applicable(const b200_net *net) {
   const char *env = std::getenv("B200_DW16"); // debugging aid, read per call: 0 = generic tcgen05 kernel
   if (env && std::atoi(env) == 0) return false;
   const int K0 = net->dims[0], N0 = net->dims[1];
-  return net->nlayers() == 2 && net->prec != B200_PREC_FP32 && K0 % 16 == 0 && (N0 == 64 || N0 == 128) && tail_applicable(net);
+  if (!(net->prec != B200_PREC_FP32 && K0 % 16 == 0 && (N0 == 64 || N0 == 128) && tail_applicable(net))) return false;
+  // two layers: the tail writes the fp16 delta_0; deeper: the DX kernel of layer 1 does, with a chained scale bound
+  return net->nlayers() == 2 || tail_chain16_applicable(net);
 }
 
 // split plan: one CTA per (feature tile, split); never more CTAs than SMs

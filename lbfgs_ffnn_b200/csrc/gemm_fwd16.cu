@@ -307,9 +307,14 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 constexpr int kSplitNeurons = 8, kSplitMaxK = 1024;
 __global__ void __launch_bounds__(1024) split_w16_kernel(const float *__restrict__ W, int K, int N, int ldk, float pre,
                                                        __half *__restrict__ wh, __half *__restrict__ wlo,
-                                                       float *__restrict__ colscale, const SpecState *spec_st, int spec) {
+                                                       float *__restrict__ colscale, const SpecState *spec_st, int spec,
+                                                       const ChainW chain) {
   if (spec_skip(spec_st, spec)) return;
   __shared__ float red[128][kSplitNeurons + 1];
+  if (chain.nl > 0 && blockIdx.x == gridDim.x - 1) { // the extra CTA (see ChainW, network.cuh)
+    chain_cw_block(chain, &red[0][0]);
+    return;
+  }
   __shared__ float sc[kSplitNeurons];
   __shared__ __align__(16) __half th[kSplitNeurons][kSplitMaxK + 8], tl[kSplitNeurons][kSplitMaxK + 8];
   const int o = threadIdx.x & (kSplitNeurons - 1), kq = threadIdx.x / kSplitNeurons, o0 = blockIdx.x * kSplitNeurons;
@@ -455,6 +460,7 @@ static bool fwd16_shape_ok(const b200_net *net) {
 // profiled apart from the GEMM). No-op when the fp16 forward does not apply.
 int fwd16_prepare(b200_net *net, const float *params) {
   net->w16_params = nullptr;
+  net->chain_ready = false;
   if (!fwd16_shape_ok(net)) return B200_OK;
   const int K = net->dims[0], N = net->dims[1];
   const int ldk = (K + 7) & ~7;
@@ -464,9 +470,15 @@ int fwd16_prepare(b200_net *net, const float *params) {
     B200_CUDA(cudaMalloc(&net->colscale, sizeof(float) * N));
     ++net->config_gen;
   }
+  ChainW chain{};
+  if (net->nlayers() > 2 && dw16_applicable(net)) {
+    B200_TRY(tail_ensure_scalars(net));
+    tail_chain_fill(net, params, &chain);
+    net->chain_ready = true;
+  }
   ProfScope ps(net->ctx, "split16");
-  B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons), 1024, 0, net->ctx->stream, params + net->offs[0], K, N, ldk, 1.0f / 255.0f,
-              (__half *)net->w16h, (__half *)net->w16l, net->colscale, net->spec_st, net->spec_flag);
+  B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons) + (chain.nl > 0 ? 1 : 0), 1024, 0, net->ctx->stream, params + net->offs[0], K, N,
+              ldk, 1.0f / 255.0f, (__half *)net->w16h, (__half *)net->w16l, net->colscale, net->spec_st, net->spec_flag, chain);
   net->w16_params = params;
   return B200_OK;
 }

@@ -17,6 +17,7 @@
 // accumulator, i.e. fp32-level products at one third of the TF32 rate with no extra HBM traffic.
 // DW is split-K over the batch with per-split partial tiles (deterministic, combined in fp64 by
 // finalize_grad_kernel); the bias gradient is one extra N=16 MMA per K step against a tile of ones.
+#include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 #include "tc_epilogue.cuh"
@@ -42,6 +43,7 @@ constexpr int kLastBytes = (128 + 1) * kLastCols * 4;  // [W_last | b_last] stag
 
 enum { MAJOR_K = 0, MAJOR_MN = 1 };
 enum { TC_FWD = 0, TC_DX = 1, TC_DW = 2 };
+constexpr int kShallowKBlocks = 8; // FWD / DX in 3xTF32 with at most this many K blocks of 32 run the two-stage variant
 
 struct TcParams {
   int rows_valid;   // FWD/DX: batch, DW: out
@@ -65,6 +67,10 @@ struct TcParams {
   int ld_delta_last;     // row stride of delta_last (out rounded up to 4)
   float inv_batch;
   double *loss_part;     // [gridDim.x * 4]
+  // DX of layer 1 feeding the fp16 dW GEMM of layer 0 (gemm_dw16.cu): delta_0 leaves as S * delta in fp16 {hi | lo},
+  // row s = [cols_valid hi | cols_valid lo], INSTEAD of the fp32 rows in `out`; S is the device scalar *scale16
+  __half *d16;
+  const float *scale16;
   long long *dbg;        // B200_TC_TIMING=1: per-CTA {main loop, epilogue} clock64 durations
 };
 
@@ -73,7 +79,9 @@ using namespace tcx;
 // U8: 0 = both operands fp32 in HBM; 1 = the A operand (FWD: the input X) is stored as uint8 = 255*x;
 //     2 = the B operand (DW: X) is. A uint8 operand is converted to fp32 in shared memory by the splitter warps;
 //     it is exact in TF32, so it needs no lo tile and contributes no lo*hi product.
-template <int BN, bool X3, int U8>
+// SHALLOW: two stages, for GEMMs with a handful of K blocks (the middle layers of a deep net): a 3xTF32 stage is 48 KB at BN = 64,
+// so two stages let TWO CTAs share an SM (256 TMEM columns each) where the deep pipeline ran one CTA per SM in 3.2 waves
+template <int BN, bool X3, int U8, int SHALLOW = 0>
 struct SmemPlan {
   static constexpr int kBTileBytes = BN * BK * 4;
   static constexpr bool kSplitA = X3 && U8 != 1, kSplitB = X3 && U8 != 2;
@@ -89,7 +97,7 @@ struct SmemPlan {
   static constexpr int kFit = (200 * 1024) / kStageBytes;
   // uint8-A forward kernel: HBM-light (4 KB per K block), epilogue-heavy -> 2 stages so that TWO CTAs fit an SM and one's
   // epilogue overlaps the other's main loop
-  static constexpr int kStages = (U8 == 1 && kStageBytes * 2 <= 104 * 1024) ? 2
+  static constexpr int kStages = SHALLOW ? 2 : (U8 == 1 && kStageBytes * 2 <= 104 * 1024) ? 2
                                : (kStageBytes * 3 <= 100 * 1024) ? 3 : (kFit > 6 ? 6 : (kFit < 2 ? 2 : kFit));
   static constexpr int kTxBytes = (U8 == 1 ? BM * BK : kATileBytes) + (U8 == 2 ? BN * BK : kBTileBytes);
   static constexpr int kOnes = (U8 == 1) ? 0 : kOnesBytes; // the ones tile is a dW-only operand; the uint8-A kernel is forward-only
@@ -97,11 +105,11 @@ struct SmemPlan {
   static constexpr int kTotal = kBarOffset + 128 + 1024; // barriers + tmem slot + alignment slack
 };
 
-template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8>
-__global__ void __launch_bounds__(kTcThreads, ((SmemPlan<BN, X3, U8>::kTotal + 1024) * 2 <= 227 * 1024) ? 2 : 1)
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8, int SHALLOW = 0>
+__global__ void __launch_bounds__(kTcThreads, ((SmemPlan<BN, X3, U8, SHALLOW>::kTotal + 1024) * 2 <= 227 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
-  using Plan = SmemPlan<BN, X3, U8>;
+  using Plan = SmemPlan<BN, X3, U8, SHALLOW>;
   constexpr bool kSplitA = Plan::kSplitA, kSplitB = Plan::kSplitB;
   // FWD / DX: the B operand is the weight matrix, the same for every CTA: its hi / lo parts are split ONCE per
   // evaluation into two global arrays (split_params_kernel) and arrive as two TMA loads; only A is split in-kernel
@@ -347,6 +355,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (j < p.last_out) tgt[j] = __ldg(p.targets + trow * p.last_out + j);
     }
   }
+  // DX: act'(A_{l-1}) of this warp's first 32 x 32 block, one column per lane (full 128-byte segments), fetched while the MMAs
+  // are still running; later blocks are fetched ahead of their TMEM load
+  float auxv[32];
+  auto fetch_aux = [&](int c0) {
+    const long wr0 = (long)m0 + (warp & 3) * 32;
+    const int rok = (int)max(0L, min(32L, (long)p.rows_valid - wr0));
+    const float *ab = p.aux + wr0 * p.ld_out + n0 + c0 + lane;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) auxv[rr] = (rr < rok && n0 + c0 + 32 <= p.cols_valid) ? __ldg(ab + (long)rr * p.ld_out) : 0.0f;
+  };
+  if (ROLE == TC_DX) fetch_aux((warp >> 2) * 32);
   if (nkb > 0) {
     mbar_wait(bar_accum, 0);
     tc_fence_after();
@@ -396,6 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int j = 0; j < (BN + 63) / 64; ++j) relu_mask[j] = 0u;
     for (int c0 = half * 32; c0 < umma_n; c0 += 64) {
       uint32_t v[32];
+      if (ROLE == TC_DX && c0 != half * 32) fetch_aux(c0);
       load_chunk(c0, v);
       if (U8 != 0) { // uint8 operand = 255 * x: undo the scale once per accumulator element
 #pragma unroll
@@ -405,7 +425,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ROLE == TC_FWD || ROLE == TC_DX) {
         if (gcol0 + 32 <= p.cols_valid) {
           float r[32];
-          const float *aux = (ROLE == TC_DX && row_ok) ? p.aux + grow * p.ld_out + gcol0 : nullptr;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if (ROLE == TC_FWD) {
@@ -426,16 +445,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   ffma2(z[8], z[9], a, a, w2.x, w2.y); ffma2(z[10], z[11], a, a, w2.z, w2.w);
                 }
               }
-            } else {
-              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row_ok) a4 = __ldg(reinterpret_cast<const float4 *>(aux) + q);
-              r[4 * q + 0] = __uint_as_float(v[4 * q + 0]) * act_deriv_c<ACT>(p.act, a4.x);
-              r[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * act_deriv_c<ACT>(p.act, a4.y);
-              r[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * act_deriv_c<ACT>(p.act, a4.z);
-              r[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * act_deriv_c<ACT>(p.act, a4.w);
             }
           }
-          store_block_coalesced(r, scratch, p.out + wrow0 * p.ld_out + gcol0, p.ld_out, rows_ok, lane);
+          if (ROLE == TC_DX) {
+            // accumulators through the transpose scratch; act'(A_{l-1}) is applied on the far side, where lanes run along a
+            // row: the loads of A_{l-1} and the stores are then full 128-byte segments (a per-thread row read touches 32 lines
+            // per instruction)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            if (p.d16) {
+              // fp16 {hi | lo} of S * delta: a lane packs its element as {hi, lo}, swaps with its neighbour, and the even lane
+              // stores the hi pair of columns (2i, 2i + 1), the odd lane their lo pair: two 64-byte runs per instruction
+              const float S = __ldg(p.scale16);
+              __half *gb = p.d16 + wrow0 * (2L * p.cols_valid) + gcol0 + ((lane & 1) ? p.cols_valid : 0);
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float x = scratch[rr * 33 + lane] * act_deriv_c<ACT>(p.act, auxv[rr]) * S;
+                const __half h = __float2half_rn(x);
+                const __half lo = __float2half_rn(x - __half2float(h));
+                const uint32_t mine = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(lo) << 16);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                const uint32_t word = (lane & 1) ? ((other >> 16) | (mine & 0xffff0000u)) : ((mine & 0xffffu) | (other << 16));
+                if (rr < rows_ok) reinterpret_cast<uint32_t *>(gb + (long)rr * (2L * p.cols_valid))[lane >> 1] = word;
+              }
+            } else {
+              float *gbase = p.out + wrow0 * p.ld_out + gcol0;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                if (rr < rows_ok) gbase[(long)rr * p.ld_out + lane] = scratch[rr * 33 + lane] * act_deriv_c<ACT>(p.act, auxv[rr]);
+            }
+            __syncwarp();
+          } else {
+            store_block_coalesced(r, scratch, p.out + wrow0 * p.ld_out + gcol0, p.ld_out, rows_ok, lane);
+          }
         } else if (row_ok) {
           float *dst = p.out + grow * p.ld_out + gcol0;
           const float *aux = (ROLE == TC_DX) ? p.aux + grow * p.ld_out + gcol0 : nullptr;
@@ -616,10 +659,10 @@ int make_map_u8(CUtensorMap *tm, const uint8_t *ptr, unsigned long long dim0, un
 
 bool tma_ok(const float *ptr, long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (ld % 4) == 0; }
 
-template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8>
+template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8, int SHALLOW = 0>
 int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tblo, const TcParams &p, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<A_MAJOR, B_MAJOR, ROLE, BN, X3, U8>;
-  constexpr int smem = SmemPlan<BN, X3, U8>::kTotal;
+  auto kern = gemm_tc_kernel<A_MAJOR, B_MAJOR, ROLE, BN, X3, U8, SHALLOW>;
+  constexpr int smem = SmemPlan<BN, X3, U8, SHALLOW>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -734,7 +777,9 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
     if (N <= 64) B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64, 1>(x3, ta, tb, tblo, p, g64, st)));
     else B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 128, 1>(x3, ta, tb, tblo, p, g128, st)));
   } else {
-    if (N <= 64) B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64>(x3, ta, tb, tblo, p, g64, st)));
+    if (x3 && p.k_blocks <= kShallowKBlocks && !p.fuse_last)
+      B200_TRY((launch_tc<MAJOR_K, MAJOR_MN, TC_FWD, 64, true, 0, 1>(ta, tb, tblo, p, dim3(g64.x, ceil_div(N, 64)), st)));
+    else if (N <= 64) B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 64>(x3, ta, tb, tblo, p, g64, st)));
     else B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_MN, TC_FWD, 128>(x3, ta, tb, tblo, p, g128, st)));
   }
   *done = true;
@@ -742,8 +787,10 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
 }
 
 // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
-int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *done) {
+int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *done, bool *emit16) {
   *done = false;
+  const bool want16 = emit16 && *emit16 && net->delta16 && net->scale16;
+  if (emit16) *emit16 = false;
   if (!(tc_mask() & 2)) return B200_OK;
   const int Kin = net->dims[l], Nout = net->dims[l + 1]; // contraction over out, result width in
   const float *W = params + net->offs[l];
@@ -761,10 +808,15 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
   p.act = net->acts[l - 1];
   p.acc_scale = 1.0f;
   p.out = net->delta[l - 1]; p.ld_out = Kin; p.aux = net->act[l - 1];
+  if (want16) { p.d16 = (__half *)net->delta16; p.scale16 = net->scale16; }
   cudaStream_t st = net->ctx->stream;
   const float *Whi = x3 ? net->w_hi + net->offs[l] : W, *Wlo = x3 ? net->w_lo + net->offs[l] : W;
   CUtensorMap tblo;
-  if (Kin <= 64) {
+  if (x3 && p.k_blocks <= kShallowKBlocks) {
+    B200_TRY(make_map(&tb, Whi, Nout, Kin, Nout, 64, MAJOR_K));
+    B200_TRY(make_map(&tblo, Wlo, Nout, Kin, Nout, 64, MAJOR_K));
+    B200_TRY((launch_tc<MAJOR_K, MAJOR_K, TC_DX, 64, true, 0, 1>(ta, tb, tblo, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 64)), st)));
+  } else if (Kin <= 64) {
     B200_TRY(make_map(&tb, Whi, Nout, Kin, Nout, 64, MAJOR_K)); // B: {K = out, N = in}, box {32, BN}
     B200_TRY(make_map(&tblo, Wlo, Nout, Kin, Nout, 64, MAJOR_K));
     B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 64>(x3, ta, tb, tblo, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 64)), st)));
@@ -773,6 +825,7 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
     B200_TRY(make_map(&tblo, Wlo, Nout, Kin, Nout, 128, MAJOR_K));
     B200_TRY((launch_tc_prec<MAJOR_K, MAJOR_K, TC_DX, 128>(x3, ta, tb, tblo, p, dim3(ceil_div(batch, BM), ceil_div(Kin, 128)), st)));
   }
+  if (emit16) *emit16 = want16;
   *done = true;
   return B200_OK;
 }

@@ -12,7 +12,9 @@ struct TcFuseLast { // request to fuse the last layer + loss + deltas into the p
 };
 int tc_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch, const TcFuseLast *fuse,
                      bool *done, bool *fused);
-int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *done);
+// emit16 (in/out): write delta_{l-1} as scaled fp16 {hi | lo} into net->delta16 instead of fp32 (see gemm_dw16.cu); false on
+// return when the fp32 rows were written after all
+int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *done, bool *emit16 = nullptr);
 int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done);
 // split-K plan of the tensor-core dW kernel: returns K blocks per split, *splits = number of splits
 int tc_dw_plan(b200_net *net, int l, long batch, int *splits);

@@ -558,6 +558,7 @@ int net_forward(b200_net *net, const float *params, const float *x, long batch) 
   B200_TRY(net_ensure(net, batch));
   B200_TRY(tc_split_params(net, params));
   net->w16_params = nullptr;
+  net->chain_ready = false;
   if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
   const float *cur = x;
   for (int l = 0; l < net->nlayers(); ++l) {
@@ -586,6 +587,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
 
   B200_TRY(tc_split_params(net, params));
   net->w16_params = nullptr;
+  net->chain_ready = false;
   if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
   // forward sweep
   const float *cur = x;
@@ -593,12 +595,13 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   bool tail_done = false;  // ... or by the one-pass last-layer kernel, which also produces the [dW_L; db_L] partials
   const bool use_tail = tail_applicable(net);
   const uint8_t *xq0 = (use_tail && net->prec != B200_PREC_FP32 && dw16_applicable(net)) ? net_xq_lookup(net, x, batch) : nullptr;
-  const bool use_dw16 = xq0 != nullptr; // layer-0 dW on the fp16 tensor cores: the tail writes delta_0 as scaled fp16 {hi | lo}
+  const bool use_dw16 = xq0 != nullptr && (L == 2 || net->chain_ready); // layer-0 dW on the fp16 tensor cores: the tail writes delta_0 as scaled fp16 {hi | lo}
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
     if (last && fused_last) break;
     if (last && use_tail) {
-      B200_TRY(tail_layer(net, params, t, batch, inv_batch, /*want32=*/!use_dw16, /*want16=*/use_dw16));
+      B200_TRY(tail_layer(net, params, t, batch, inv_batch, /*want32=*/!use_dw16 || L > 2, /*want16=*/use_dw16 && L == 2,
+                          /*chain16=*/use_dw16 && L > 2));
       tail_done = true;
       break;
     }
@@ -618,6 +621,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   net->last_batch = batch;
 
   // backward sweep
+  bool d16_ready = use_dw16 && L == 2; // fp16 {hi | lo} delta_0 in net->delta16
   for (int l = L - 1; l >= 0; --l) {
     const int K = net->dims[l], N = net->dims[l + 1];
     const float *W = params + net->offs[l];
@@ -627,7 +631,11 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       snprintf(nm, sizeof(nm), "dx%d", l);
       ProfScope ps(ctx, nm);
       bool done = false;
-      if (net->prec != B200_PREC_FP32) B200_TRY(tc_dx_layer(net, l, params, batch, &done));
+      if (net->prec != B200_PREC_FP32) {
+        bool emit16 = (l == 1 && use_dw16 && L > 2);
+        B200_TRY(tc_dx_layer(net, l, params, batch, &done, &emit16));
+        if (emit16) d16_ready = true;
+      }
       if (!done) {
         GemmParams p{};
         p.A = net->delta[l]; p.lda = net->ldd[l];
@@ -648,7 +656,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       snprintf(nm, sizeof(nm), "dw%d", l);
       ProfScope ps(ctx, nm);
       bool done = false;
-      if (l == 0 && use_dw16) {
+      if (l == 0 && d16_ready) {
         X16View xv;
         if (net_x16_view(net, x, batch, &xv)) B200_TRY(dw16_layer(net, xv, batch, &done));
       }

@@ -59,7 +59,8 @@ struct b200_net {
   float *colscale = nullptr;
   const float *w16_params = nullptr; // parameter vector the fp16 split currently holds (per evaluation)
   // one-pass last layer (tail_layer.cu): per-CTA max |delta_L|, scaled fp16 {hi | lo} copy of delta_{L-1} and 1 / its scale
-  float *amax_part = nullptr, *scale16_inv = nullptr;
+  float *amax_part = nullptr, *scale16_inv = nullptr, *scale16 = nullptr, *chain_cw = nullptr; // scale16: the scale itself, chain_cw: see ChainW
+  bool chain_ready = false; // chain_cw holds the factor of the current evaluation's parameters
   void *delta16 = nullptr;
   long delta16_cap = 0;
 
@@ -107,7 +108,77 @@ bool net_x16_view(b200_net *net, const float *x, long batch, X16View *v);
 bool net_spec_capable(b200_net *net, const float *x, long batch);
 // the skinny last layer in one pass: forward, loss, both deltas and the [dW_L; db_L] partials (tail_layer.cu)
 bool tail_applicable(const b200_net *net);
-int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16);
+// want16: delta_{L-1} also (or only) as scaled fp16 {hi | lo} in net->delta16 (two-layer nets: it feeds gemm_dw16.cu directly).
+// chain16 (deeper nets): size net->delta16 for delta_0 and derive its scale from max |delta_L| and the weights of layers 1..L-1;
+// the DX kernel of layer 1 then writes it (tc_dx_layer, emit16)
+int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16,
+               bool chain16 = false);
+bool tail_chain16_applicable(const b200_net *net);
+int tail_ensure_scalars(b200_net *net);
+
+// Weight-dependent factor of the fp16 scale of delta_0 in a net with more than two layers: prod_{l=1..L-1} max_f ||W_l[f,:]||_1
+// (|act'| <= 1, so max |delta_0| <= max |delta_L| * this). Computed once per evaluation by an extra CTA of the weight-split
+// kernel (gemm_fwd16.cu); the last-layer backward kernel multiplies it with max |delta_L| and publishes the scale.
+constexpr int kMaxChain = 8;
+struct ChainW {
+  const float *W[kMaxChain]; // layer l: [in][out]
+  int in[kMaxChain], out[kMaxChain];
+  int nl;                    // 0: nothing to do
+  float *cw_out;
+};
+void tail_chain_fill(const b200_net *net, const float *params, ChainW *c);
+#ifdef __CUDACC__
+__device__ __forceinline__ void chain_cw_block(const ChainW &c, float *red /* [kMaxChain * 32] shared */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int total = 0;
+  for (int l = 0; l < c.nl; ++l) total += c.in[l];
+  float cw[kMaxChain];
+#pragma unroll
+  for (int l = 0; l < kMaxChain; ++l) cw[l] = 0.0f;
+  // one warp per row of any W_l, four rows at a time with all their loads in flight together (the CTA is otherwise a chain of
+  // L2 latencies and the long pole of the launch)
+  for (int g0 = warp; g0 < total; g0 += 4 * nw) {
+    float r[4];
+    int ll[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int g = g0 + u * nw, l = 0;
+      const bool ok = g < total;
+      if (!ok) g = 0;
+      while (g >= c.in[l]) { g -= c.in[l]; ++l; }
+      ll[u] = ok ? l : -1;
+      const int out = c.out[l];
+      const float *row = c.W[l] + (size_t)g * out;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (ok && lane + 32 * k < out) ? fabsf(__ldg(row + lane + 32 * k)) : 0.0f;
+      float s = (v[0] + v[1]) + (v[2] + v[3]);
+      if (ok) for (int o = lane + 128; o < out; o += 32) s += fabsf(__ldg(row + o));
+      r[u] = s;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r[u] += __shfl_xor_sync(0xffffffffu, r[u], o);
+#pragma unroll
+      for (int l = 0; l < kMaxChain; ++l) if (ll[u] == l) cw[l] = fmaxf(cw[l], r[u]);
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int l = 0; l < kMaxChain; ++l) red[l * 32 + warp] = cw[l];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float prod = 1.0f;
+    for (int l = 0; l < c.nl; ++l) {
+      float m = red[l * 32];
+      for (int i = 1; i < nw; ++i) m = fmaxf(m, red[l * 32 + i]);
+      prod *= m;
+    }
+    *c.cw_out = prod;
+  }
+}
+#endif
 void tail_release(b200_net *net);
 
 } // namespace b200

@@ -29,6 +29,8 @@ struct TailParams {
   float *delta_prev;   // [B][in] fp32 (nullptr: not needed)
   __half *d16;         // [B][2 in] fp16 {hi | lo} of S * delta_prev (nullptr: not needed)
   float *scale16_inv;  // device scalar 1 / S
+  const float *chain_cw; // deeper nets: block 0 publishes S (and 1 / S) of delta_0 = f(max |delta_L| * *chain_cw) for the DX kernel
+  float *scale16;
   float *amax_part;    // [grid] per-CTA max |delta_L|
   int n_amax;
   float *partial;      // [grid][(in+1)*out]
@@ -229,6 +231,23 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
     S = ldexpf(1.0f, 14 - e);
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.scale16_inv = ldexpf(1.0f, e - 14);
   }
+  if (p.chain_cw && blockIdx.x == 0) { // block-uniform
+    float m = 0.0f;
+    for (int i = threadIdx.x; i < p.n_amax; i += blockDim.x) m = fmaxf(m, __ldg(p.amax_part + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) mred[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, mred[i]);
+      const float bound = m * __ldg(p.chain_cw);
+      int e = 0;
+      if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &e);
+      e = max(-100, min(100, e));
+      *p.scale16 = ldexpf(1.0f, 14 - e);
+      *p.scale16_inv = ldexpf(1.0f, e - 14);
+    }
+  }
   float acc[FPL][OLP];
 #pragma unroll
   for (int c = 0; c < FPL; ++c)
@@ -369,18 +388,15 @@ bool tail_applicable(const b200_net *net) {
 // Runs the last layer forward, loss, delta_L, delta_{L-1} and the [dW_L; db_L] partials. Requires net_ensure(batch) and the
 // penultimate activations in net->act[L-2]. want16: also (or, with !want32, only) write delta_{L-1} as scaled fp16 {hi | lo}
 // into net->delta16 for the fp16 dW GEMM of layer L-2 (gemm_dw16.cu), with 1 / scale in net->scale16_inv.
-int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16) {
+int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16,
+               bool chain16) {
   const int L = net->nlayers();
   const int in = net->dims[L - 1], out = net->dims[L];
-  if (!net->amax_part) {
-    B200_CUDA(cudaMalloc(&net->amax_part, sizeof(float) * 2 * net->ctx->num_sms));
-    B200_CUDA(cudaMalloc(&net->scale16_inv, sizeof(float)));
-    ++net->config_gen;
-  }
-  if (want16 && net->delta16_cap < batch) {
+  B200_TRY(tail_ensure_scalars(net));
+  if ((want16 || chain16) && net->delta16_cap < batch) {
     if (net->delta16) cudaFree(net->delta16);
     net->delta16 = nullptr;
-    B200_CUDA(cudaMalloc(&net->delta16, sizeof(__half) * 2 * (size_t)in * net->cap));
+    B200_CUDA(cudaMalloc(&net->delta16, sizeof(__half) * 2 * (size_t)net->dims[1] * net->cap)); // rows of delta_0 (L == 2: in == dims[1])
     ++net->config_gen;
     net->delta16_cap = net->cap;
   }
@@ -394,6 +410,7 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   p.d16 = want16 ? (__half *)net->delta16 : nullptr;
   p.scale16_inv = net->scale16_inv;
   p.amax_part = net->amax_part;
+  if (chain16) { p.chain_cw = net->chain_cw; p.scale16 = net->scale16; }
   p.partial = net->partials + net->part_off[L - 1];
   p.loss_part = net->loss_part;
   p.batch = batch;
@@ -414,11 +431,38 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   return B200_OK;
 }
 
+// deeper nets: one CTA scans the weight matrices of layers 1..L-1 (ChainW), so they must be small
+bool tail_chain16_applicable(const b200_net *net) {
+  const int L = net->nlayers();
+  if (L < 3 || L - 1 > kMaxChain) return false;
+  size_t total = 0;
+  for (int l = 1; l < L; ++l) total += (size_t)net->dims[l] * net->dims[l + 1];
+  return total <= (size_t)1 << 18;
+}
+
+int tail_ensure_scalars(b200_net *net) {
+  if (!net->amax_part) {
+    B200_CUDA(cudaMalloc(&net->amax_part, sizeof(float) * 2 * net->ctx->num_sms));
+    B200_CUDA(cudaMalloc(&net->scale16_inv, 3 * sizeof(float)));
+    net->scale16 = net->scale16_inv + 1;
+    net->chain_cw = net->scale16_inv + 2;
+    ++net->config_gen;
+  }
+  return B200_OK;
+}
+
+void tail_chain_fill(const b200_net *net, const float *params, ChainW *c) {
+  const int L = net->nlayers();
+  c->nl = L - 1;
+  for (int l = 1; l < L; ++l) { c->W[l - 1] = params + net->offs[l]; c->in[l - 1] = net->dims[l]; c->out[l - 1] = net->dims[l + 1]; }
+  c->cw_out = net->chain_cw;
+}
+
 void tail_release(b200_net *net) {
   if (net->amax_part) cudaFree(net->amax_part);
   if (net->scale16_inv) cudaFree(net->scale16_inv);
   if (net->delta16) cudaFree(net->delta16);
-  net->amax_part = net->scale16_inv = nullptr;
+  net->amax_part = net->scale16_inv = net->scale16 = net->chain_cw = nullptr;
   net->delta16 = nullptr;
   net->delta16_cap = 0;
 }

@@ -78,9 +78,10 @@ def test_fp16_path_parity(handle, oracle, dims, acts, batch):
 
 @pytest.mark.parametrize("env", [{"B200_DW16": "0"}, {"B200_TAIL": "0"}, {"B200_FWD16": "0"},
                                  {"B200_FWD16": "0", "B200_TAIL": "0", "B200_DW16": "0"}])
-def test_each_new_kernel_against_the_generic_path(handle, oracle, env):
+@pytest.mark.parametrize("which", [0, 5])
+def test_each_new_kernel_against_the_generic_path(handle, oracle, env, which):
     """the same evaluation with one (or all) of the new kernels replaced by the generic tcgen05 / FFMA kernels"""
-    dims, acts, batch = NETS[0][0], NETS[0][1], 2500
+    dims, acts, batch = NETS[which][0], NETS[which][1], 2500
     onet, w, X, T = make_problem(oracle, dims, acts, batch)
     lo, go = onet.loss_grad(w, X, T)
     l1, g1, o1 = _eval(handle, dims, acts, w, X, T, "tf32x3")
@@ -101,9 +102,10 @@ def test_tail_serves_the_other_precision_modes(handle, oracle, prec, tol_l, tol_
         assert rel_l2(g, go) <= tol_g, (prec, dims, rel_l2(g, go))
 
 
-def test_full_size_fp16_path(handle, oracle):
-    """BASELINE configs[1] size: 60 000 samples, 469 tiles over 148 persistent CTAs, 37-way split-K in dw16"""
-    dims, acts = NETS[0]
+@pytest.mark.parametrize("which", [0, 5])
+def test_full_size_fp16_path(handle, oracle, which):
+    """BASELINE configs[1] / configs[2] size: 60 000 samples, 469 tiles over 148 persistent CTAs, 37-way split-K in dw16"""
+    dims, acts = NETS[which]
     onet, w, X, T = make_problem(oracle, dims, acts, 60000)
     lo, go = onet.loss_grad(w, X, T)
     loss, g, _ = _eval(handle, dims, acts, w, X, T, "tf32x3")
@@ -111,9 +113,11 @@ def test_full_size_fp16_path(handle, oracle):
     assert abs(loss - lo) <= 2e-5 * abs(lo) and rel_l2(g, go) <= 5e-5, (loss, lo, rel_l2(g, go))
 
 
-def test_scaled_fp16_operands_survive_extreme_weights(handle, oracle):
-    """per-neuron power-of-two scales: weights spanning 1e-6 .. 1e+3 across neurons, and a huge / tiny delta"""
-    dims, acts, batch = NETS[0][0], NETS[0][1], 700
+@pytest.mark.parametrize("which", [0, 5])
+def test_scaled_fp16_operands_survive_extreme_weights(handle, oracle, which):
+    """per-neuron power-of-two scales: weights spanning 1e-6 .. 1e+3 across neurons, and a huge / tiny delta. In the deep net
+    delta_0 is scaled by a bound chained through the weight matrices of the later layers (tail_layer.cu)"""
+    dims, acts, batch = NETS[which][0], NETS[which][1], 700
     onet, w, X, T = make_problem(oracle, dims, acts, batch)
     rs = np.random.RandomState(5)
     w = w.copy()
