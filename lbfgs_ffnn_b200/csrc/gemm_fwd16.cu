@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(1024) split_w16_kernel(const float *__restrict
                                                        const ChainW chain) {
   if (spec_skip(spec_st, spec)) return;
   __shared__ float red[128][kSplitNeurons + 1];
-  if (chain.nl > 0 && blockIdx.x == gridDim.x - 1) { // the extra CTA (see ChainW, network.cuh)
-    chain_cw_block(chain, &red[0][0]);
+  if (chain.nl > 0 && blockIdx.x >= gridDim.x - chain.nctas) { // the extra CTAs (see ChainW, network.cuh)
+    chain_cw_block(chain, (int)(blockIdx.x - (gridDim.x - chain.nctas)), &red[0][0]);
     return;
   }
   __shared__ float sc[kSplitNeurons];
@@ -477,7 +477,7 @@ int fwd16_prepare(b200_net *net, const float *params) {
     net->chain_ready = true;
   }
   ProfScope ps(net->ctx, "split16");
-  B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons) + (chain.nl > 0 ? 1 : 0), 1024, 0, net->ctx->stream, params + net->offs[0], K, N,
+  B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons) + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, params + net->offs[0], K, N,
               ldk, 1.0f / 255.0f, (__half *)net->w16h, (__half *)net->w16l, net->colscale, net->spec_st, net->spec_flag, chain);
   net->w16_params = params;
   return B200_OK;

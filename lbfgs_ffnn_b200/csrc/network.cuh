@@ -117,65 +117,46 @@ bool tail_chain16_applicable(const b200_net *net);
 int tail_ensure_scalars(b200_net *net);
 
 // Weight-dependent factor of the fp16 scale of delta_0 in a net with more than two layers: prod_{l=1..L-1} max_f ||W_l[f,:]||_1
-// (|act'| <= 1, so max |delta_0| <= max |delta_L| * this). Computed once per evaluation by an extra CTA of the weight-split
-// kernel (gemm_fwd16.cu); the last-layer backward kernel multiplies it with max |delta_L| and publishes the scale.
-constexpr int kMaxChain = 8;
+// (|act'| <= 1, so max |delta_0| <= max |delta_L| * this). Computed once per evaluation by a few extra CTAs of the weight-split
+// kernel (gemm_fwd16.cu), one warp per row of any W_l so that each CTA costs one memory latency; they leave per-layer maxima
+// per CTA, and block 0 of the last-layer backward kernel combines them with max |delta_L| and publishes the scale.
+constexpr int kMaxChain = 8, kChainRowsPerCta = 32, kMaxChainCtas = 64;
 struct ChainW {
   const float *W[kMaxChain]; // layer l: [in][out]
   int in[kMaxChain], out[kMaxChain];
   int nl;                    // 0: nothing to do
-  float *cw_out;
+  int nctas;                 // ceil(total rows / kChainRowsPerCta)
+  float *cw_part;            // [nctas][kMaxChain]
 };
 void tail_chain_fill(const b200_net *net, const float *params, ChainW *c);
 #ifdef __CUDACC__
-__device__ __forceinline__ void chain_cw_block(const ChainW &c, float *red /* [kMaxChain * 32] shared */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// cta: index among the chain CTAs; red: kMaxChain * 32 floats of shared memory; needs blockDim.x >= 32 * kChainRowsPerCta
+__device__ __forceinline__ void chain_cw_block(const ChainW &c, int cta, float *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int total = 0;
   for (int l = 0; l < c.nl; ++l) total += c.in[l];
-  float cw[kMaxChain];
+  int g = cta * kChainRowsPerCta + warp, l = 0;
+  const bool ok = warp < kChainRowsPerCta && g < total;
+  if (!ok) g = 0;
+  while (g >= c.in[l]) { g -= c.in[l]; ++l; }
+  const int out = c.out[l];
+  const float *row = c.W[l] + (size_t)g * out;
+  float v[4];
 #pragma unroll
-  for (int l = 0; l < kMaxChain; ++l) cw[l] = 0.0f;
-  // one warp per row of any W_l, four rows at a time with all their loads in flight together (the CTA is otherwise a chain of
-  // L2 latencies and the long pole of the launch)
-  for (int g0 = warp; g0 < total; g0 += 4 * nw) {
-    float r[4];
-    int ll[4];
+  for (int k = 0; k < 4; ++k) v[k] = (ok && lane + 32 * k < out) ? fabsf(__ldg(row + lane + 32 * k)) : 0.0f;
+  float s = (v[0] + v[1]) + (v[2] + v[3]);
+  if (ok) for (int o = lane + 128; o < out; o += 32) s += fabsf(__ldg(row + o));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int g = g0 + u * nw, l = 0;
-      const bool ok = g < total;
-      if (!ok) g = 0;
-      while (g >= c.in[l]) { g -= c.in[l]; ++l; }
-      ll[u] = ok ? l : -1;
-      const int out = c.out[l];
-      const float *row = c.W[l] + (size_t)g * out;
-      float v[4];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0 && warp < kChainRowsPerCta)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (ok && lane + 32 * k < out) ? fabsf(__ldg(row + lane + 32 * k)) : 0.0f;
-      float s = (v[0] + v[1]) + (v[2] + v[3]);
-      if (ok) for (int o = lane + 128; o < out; o += 32) s += fabsf(__ldg(row + o));
-      r[u] = s;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) r[u] += __shfl_xor_sync(0xffffffffu, r[u], o);
-#pragma unroll
-      for (int l = 0; l < kMaxChain; ++l) if (ll[u] == l) cw[l] = fmaxf(cw[l], r[u]);
-    }
-  }
-  if (lane == 0)
-#pragma unroll
-    for (int l = 0; l < kMaxChain; ++l) red[l * 32 + warp] = cw[l];
+    for (int j = 0; j < kMaxChain; ++j) red[j * 32 + warp] = (ok && j == l) ? s : 0.0f;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float prod = 1.0f;
-    for (int l = 0; l < c.nl; ++l) {
-      float m = red[l * 32];
-      for (int i = 1; i < nw; ++i) m = fmaxf(m, red[l * 32 + i]);
-      prod *= m;
-    }
-    *c.cw_out = prod;
+  if (warp == 0) { // lane j reduces layer j
+    float m = 0.0f;
+    if (lane < kMaxChain)
+      for (int i = 0; i < kChainRowsPerCta; ++i) m = fmaxf(m, red[lane * 32 + i]);
+    if (lane < kMaxChain) c.cw_part[cta * kMaxChain + lane] = m;
   }
 }
 #endif

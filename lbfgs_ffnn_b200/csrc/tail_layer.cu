@@ -29,7 +29,9 @@ struct TailParams {
   float *delta_prev;   // [B][in] fp32 (nullptr: not needed)
   __half *d16;         // [B][2 in] fp16 {hi | lo} of S * delta_prev (nullptr: not needed)
   float *scale16_inv;  // device scalar 1 / S
-  const float *chain_cw; // deeper nets: block 0 publishes S (and 1 / S) of delta_0 = f(max |delta_L| * *chain_cw) for the DX kernel
+  // deeper nets: block 0 publishes S (and 1 / S) of delta_0 from max |delta_L| and the per-layer row-norm maxima (ChainW)
+  const float *chain_cw;
+  int chain_nl, chain_nctas;
   float *scale16;
   float *amax_part;    // [grid] per-CTA max |delta_L|
   int n_amax;
@@ -240,7 +242,12 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int i = 1; i < 8; ++i) m = fmaxf(m, mred[i]);
-      const float bound = m * __ldg(p.chain_cw);
+      float bound = m;
+      for (int l = 0; l < p.chain_nl; ++l) {
+        float cwl = 0.0f;
+        for (int i = 0; i < p.chain_nctas; ++i) cwl = fmaxf(cwl, __ldg(p.chain_cw + i * kMaxChain + l));
+        bound *= cwl;
+      }
       int e = 0;
       if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &e);
       e = max(-100, min(100, e));
@@ -410,7 +417,11 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   p.d16 = want16 ? (__half *)net->delta16 : nullptr;
   p.scale16_inv = net->scale16_inv;
   p.amax_part = net->amax_part;
-  if (chain16) { p.chain_cw = net->chain_cw; p.scale16 = net->scale16; }
+  if (chain16) {
+    ChainW c{};
+    tail_chain_fill(net, params, &c);
+    p.chain_cw = net->chain_cw; p.chain_nl = c.nl; p.chain_nctas = c.nctas; p.scale16 = net->scale16;
+  }
   p.partial = net->partials + net->part_off[L - 1];
   p.loss_part = net->loss_part;
   p.batch = batch;
@@ -431,19 +442,21 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   return B200_OK;
 }
 
-// deeper nets: one CTA scans the weight matrices of layers 1..L-1 (ChainW), so they must be small
+// deeper nets: a few CTAs scan the weight matrices of layers 1..L-1, one warp per row (ChainW), so they must be small
 bool tail_chain16_applicable(const b200_net *net) {
   const int L = net->nlayers();
   if (L < 3 || L - 1 > kMaxChain) return false;
   size_t total = 0;
   for (int l = 1; l < L; ++l) total += (size_t)net->dims[l] * net->dims[l + 1];
-  return total <= (size_t)1 << 18;
+  int rows = 0;
+  for (int l = 1; l < L; ++l) rows += net->dims[l];
+  return total <= (size_t)1 << 20 && rows <= kChainRowsPerCta * kMaxChainCtas;
 }
 
 int tail_ensure_scalars(b200_net *net) {
   if (!net->amax_part) {
     B200_CUDA(cudaMalloc(&net->amax_part, sizeof(float) * 2 * net->ctx->num_sms));
-    B200_CUDA(cudaMalloc(&net->scale16_inv, 3 * sizeof(float)));
+    B200_CUDA(cudaMalloc(&net->scale16_inv, (2 + kMaxChain * kMaxChainCtas) * sizeof(float)));
     net->scale16 = net->scale16_inv + 1;
     net->chain_cw = net->scale16_inv + 2;
     ++net->config_gen;
@@ -455,7 +468,10 @@ void tail_chain_fill(const b200_net *net, const float *params, ChainW *c) {
   const int L = net->nlayers();
   c->nl = L - 1;
   for (int l = 1; l < L; ++l) { c->W[l - 1] = params + net->offs[l]; c->in[l - 1] = net->dims[l]; c->out[l - 1] = net->dims[l + 1]; }
-  c->cw_out = net->chain_cw;
+  int rows = 0;
+  for (int l = 1; l < L; ++l) rows += net->dims[l];
+  c->nctas = ceil_div(rows, kChainRowsPerCta);
+  c->cw_part = net->chain_cw;
 }
 
 void tail_release(b200_net *net) {
