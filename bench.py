@@ -147,7 +147,16 @@ def main():
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
                     help="tf32x3 (default): fp32-accurate hi/lo split on the tensor cores; fp32: FFMA; tf32: single pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--net", default=None,
+                    help="layer widths, e.g. 784-128-64-10 (BASELINE.json configs[2], the deep net); default: configs[1], the headline")
     args = ap.parse_args()
+    if args.net:
+        global DIMS, ACTS, FLOP_PER_SAMPLE, WORKLOAD
+        DIMS = [int(v) for v in args.net.split("-")]
+        ACTS = ["relu"] * (len(DIMS) - 2) + ["linear"]
+        pairs = list(zip(DIMS[:-1], DIMS[1:]))
+        FLOP_PER_SAMPLE = 2 * (2 * sum(a * b for a, b in pairs) + sum(a * b for a, b in pairs[1:]))
+        WORKLOAD = f"lbfgs_m{MEMORY}_mlp{args.net}_B{TOTAL_SAMPLES}_fullbatch"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,8 +306,8 @@ def main():
         work = {
             "fwd0": dict(flops=2.0 * B * K0 * N0, bytes=x_bytes + 4.0 * B * N0),
             "dw0": dict(flops=2.0 * B * (K0 + 1) * N0, bytes=x_bytes + 4.0 * B * N0),
-            "tail_fwd": dict(flops=2.0 * B * N0 * DIMS[2], bytes=4.0 * B * (N0 + 3 * DIMS[2])),
-            "tail_bwd": dict(flops=4.0 * B * N0 * DIMS[2], bytes=4.0 * B * (2 * N0 + DIMS[2])),
+            "tail_fwd": dict(flops=2.0 * B * DIMS[-2] * DIMS[-1], bytes=4.0 * B * (DIMS[-2] + 3 * DIMS[-1])),
+            "tail_bwd": dict(flops=4.0 * B * DIMS[-2] * DIMS[-1], bytes=4.0 * B * (2 * DIMS[-2] + DIMS[-1])),
             "lbfgs_direction": dict(flops=0.0, bytes=(4.0 * MEMORY + 2) * n * 4),
         }
         tensor_peak = pk["bf16_sustained"]  # kind::f16 MMAs: the measured dense 16-bit figure (TF32 is half of it)
@@ -320,7 +329,7 @@ def main():
         # DRAM bytes per launch from the committed `ncu --set full` capture of this command (profiles/r01_traffic.json)
         traffic = {}
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and world == 1 and args.precision == "tf32x3":
+        if os.path.exists(tpath) and world == 1 and args.precision == "tf32x3" and not args.net:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {})
         for k in rooflines:
             rooflines[k]["traffic"] = traffic.get(k)

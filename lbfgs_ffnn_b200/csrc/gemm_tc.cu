@@ -460,14 +460,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float S = __ldg(p.scale16);
               __half *gb = p.d16 + wrow0 * (2L * p.cols_valid) + gcol0 + ((lane & 1) ? p.cols_valid : 0);
 #pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                const float x = scratch[rr * 33 + lane] * act_deriv_c<ACT>(p.act, auxv[rr]) * S;
-                const __half h = __float2half_rn(x);
-                const __half lo = __float2half_rn(x - __half2float(h));
-                const uint32_t mine = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(lo) << 16);
-                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                const uint32_t word = (lane & 1) ? ((other >> 16) | (mine & 0xffff0000u)) : ((mine & 0xffffu) | (other << 16));
-                if (rr < rows_ok) reinterpret_cast<uint32_t *>(gb + (long)rr * (2L * p.cols_valid))[lane >> 1] = word;
+              for (int rr = 0; rr < 32; rr += 2) { // two rows per step: packed fp32 <-> fp16 conversions (the scalar ones issue at 1/4 rate)
+                const float xa = scratch[rr * 33 + lane] * act_deriv_c<ACT>(p.act, auxv[rr]) * S;
+                const float xb = scratch[(rr + 1) * 33 + lane] * act_deriv_c<ACT>(p.act, auxv[rr + 1]) * S;
+                const __half2 h2 = __floats2half2_rn(xa, xb);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(xa - hf.x, xb - hf.y);
+                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2), lb = *reinterpret_cast<const uint32_t *>(&l2);
+                const uint32_t mine_a = __byte_perm(hb, lb, 0x5410), mine_b = __byte_perm(hb, lb, 0x7632); // {hi, lo} of each row
+                const uint32_t other_a = __shfl_xor_sync(0xffffffffu, mine_a, 1), other_b = __shfl_xor_sync(0xffffffffu, mine_b, 1);
+                // even lane: hi pair {own, neighbour}; odd lane: lo pair {neighbour, own}
+                const uint32_t wa = (lane & 1) ? __byte_perm(other_a, mine_a, 0x7632) : __byte_perm(mine_a, other_a, 0x5410);
+                const uint32_t wb = (lane & 1) ? __byte_perm(other_b, mine_b, 0x7632) : __byte_perm(mine_b, other_b, 0x5410);
+                if (rr < rows_ok) reinterpret_cast<uint32_t *>(gb + (long)rr * (2L * p.cols_valid))[lane >> 1] = wa;
+                if (rr + 1 < rows_ok) reinterpret_cast<uint32_t *>(gb + (long)(rr + 1) * (2L * p.cols_valid))[lane >> 1] = wb;
               }
             } else {
               float *gbase = p.out + wrow0 * p.ld_out + gcol0;
