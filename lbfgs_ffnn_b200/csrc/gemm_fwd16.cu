@@ -449,6 +449,10 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
 
 } // namespace
 
+int tc_make_map_2d_f32(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigned long long dim1, unsigned box0, unsigned box1) {
+  return make_map_2d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ptr, dim0, dim1, dim0 * 4, box0, box1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 static bool fwd16_shape_ok(const b200_net *net) {
   const char *env = std::getenv("B200_FWD16"); // debugging aid, read per call: 0 = use the generic tcgen05 kernel
   if (env && std::atoi(env) == 0) return false;

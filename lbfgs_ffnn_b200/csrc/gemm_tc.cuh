@@ -4,6 +4,8 @@
 
 #include "network.cuh"
 
+#include <cuda.h>
+
 namespace b200 {
 
 struct TcFuseLast { // request to fuse the last layer + loss + deltas into the penultimate layer's forward epilogue
@@ -27,5 +29,8 @@ void fwd16_release(b200_net *net);
 bool dw16_applicable(const b200_net *net);
 int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done);
 void tc_release(b200_net *net);
+
+// 2-D fp32 tensor map {dim0 contiguous, dim1 rows} with SWIZZLE_128B (gemm_fwd16.cu)
+int tc_make_map_2d_f32(CUtensorMap *tm, const float *ptr, unsigned long long dim0, unsigned long long dim1, unsigned box0, unsigned box1);
 
 } // namespace b200

@@ -9,6 +9,7 @@
 // transpose-reduce (lane v ends up with value v), so no shared memory is touched until the per-CTA dW combine.
 // HBM-bound by design (bytes: A_{L-1} + delta_{L-1}); fp32 FFMA throughout, so it serves every precision mode.
 #include "network.cuh"
+#include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
@@ -57,6 +58,15 @@ template <int FPL> __device__ __forceinline__ void load_row(const float *p, floa
 #pragma unroll
   for (int c = 0; c < FPL; ++c) a[c] = f[c];
 }
+template <int FPL> __device__ __forceinline__ void load_row_shared(const float *p, float (&a)[FPL]) {
+  using V = typename VecT<FPL>::type;
+  const V v = *reinterpret_cast<const V *>(p);
+  const float *f = reinterpret_cast<const float *>(&v);
+#pragma unroll
+  for (int c = 0; c < FPL; ++c) a[c] = f[c];
+}
+constexpr int kFwdStages = 5;  // tail_fwd: steps (2 rows per warp) in flight per warp
+constexpr int kBwdStages = 5;  // tail_bwd: steps (2 rows + their delta_L per warp) in flight per warp
 template <int FPL> __device__ __forceinline__ void store_row(float *p, const float (&a)[FPL]) {
   using V = typename VecT<FPL>::type;
   V v;
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
   __shared__ float mred[8];
   __shared__ float dbred[8][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int OL = p.out;
+  const int OL = (OLP == 10) ? 10 : p.out; // launch_tail: the 10-wide instantiation serves exactly out == 10
   float w[FPL][OLP];
 #pragma unroll
   for (int c = 0; c < FPL; ++c)
@@ -132,17 +142,39 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
   double lsum = 0.0;
   float amax = 0.0f, accd = 0.0f; // accd: this lane's (sample parity, output) share of db_L = sum_s delta_L[s][:]
   const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
-  float a0[FPL], a1[FPL], n0[FPL], n1[FPL];
-  auto fetch = [&](long s, float (&x0)[FPL], float (&x1)[FPL]) {
-#pragma unroll
-    for (int c = 0; c < FPL; ++c) { x0[c] = 0.0f; x1[c] = 0.0f; }
-    if (s < b1) load_row<FPL>(p.A + s * IN + lane * FPL, x0);
-    if (s + 1 < b1) load_row<FPL>(p.A + (s + 1) * IN + lane * FPL, x1);
+  // Activations arrive through a per-warp ring of bulk async copies (two rows = one step of this warp per stage, kFwdStages
+  // steps ahead): with register prefetch one step ahead a warp kept 1 KB in flight, 16 KB per SM, and the kernel ran at the
+  // 1.6 TB/s that Little's law gives for that; the ring keeps kFwdStages KB per warp in flight. Each warp is producer and consumer
+  // of its own slots, so there is no cross-warp synchronisation.
+  __shared__ __align__(128) float ring[8][kFwdStages][2 * IN];
+  __shared__ __align__(8) unsigned long long bars[8][kFwdStages];
+  const uint32_t ring_w = tcx::smem_u32(&ring[warp][0][0]), bar_w = tcx::smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+    for (int st = 0; st < kFwdStages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
+    tcx::fence_mbar_init();
+  }
+  __syncwarp();
+  auto issue = [&](long s, int st) { // lane 0: rows s, s + 1 of this warp's step (clipped at the end of the CTA's slice)
+    if (s < b1) {
+      const uint32_t bytes = (uint32_t)min(2L, b1 - s) * (IN * 4);
+      tcx::mbar_expect_tx(bar_w + 8 * st, bytes);
+      tcx::bulk_load_1d(ring_w + st * (2 * IN * 4), p.A + s * IN, bytes, bar_w + 8 * st);
+    }
   };
+  float a0[FPL], a1[FPL];
   long s = b0 + 2 * warp;
-  fetch(s, a0, a1);
+  if (lane == 0)
+    for (int st = 0; st < kFwdStages; ++st) issue(s + 16L * st, st);
+  int st = 0;
+  uint32_t ph = 0;
   for (; s < b1; s += 16) {
-    fetch(s + 16, n0, n1); // next pair of this warp: in flight while this pair is processed
+    tcx::mbar_wait(bar_w + 8 * st, ph);
+    load_row_shared<FPL>(&ring[warp][st][lane * FPL], a0);
+    load_row_shared<FPL>(&ring[warp][st][IN + lane * FPL], a1);
+    if (s + 1 >= b1) {
+#pragma unroll
+      for (int c = 0; c < FPL; ++c) a1[c] = 0.0f;
+    }
     const long smy = s + half;
     float tj = 0.0f;
     if (myj < OL && smy < b1) tj = __ldg(p.T + smy * OL + myj);
@@ -167,8 +199,9 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
       amax = fmaxf(amax, fabsf(dl));
       accd += dl;
     }
-#pragma unroll
-    for (int c = 0; c < FPL; ++c) { a0[c] = n0[c]; a1[c] = n1[c]; }
+    __syncwarp(); // every lane has consumed its part of the slot: refill it for the step kFwdStages ahead
+    if (lane == 0) issue(s + 16L * kFwdStages, st);
+    if (++st == kFwdStages) { st = 0; ph ^= 1; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -189,16 +222,180 @@ __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
   }
 }
 
+// ---- pass 1, sample-per-lane form ------------------------------------------------------------------------------------------
+// A lane owns one SAMPLE of a 32-sample tile and all OLP pre-activations of it, so no cross-lane reduction is needed (the
+// feature-per-lane form above spends 40 % of its instructions in the transpose-reduce). The tile's activations arrive in stages
+// of 32 features x 32 samples = one TMA box {32 floats, 32 rows} with SWIZZLE_128B: row r's 16-byte chunk c lands at chunk
+// c ^ (r & 7) of its 128-byte row, so the lanes' reads down a column of rows are conflict-free (a linear copy would put all 32 on
+// one bank, and per-row bulk copies into padded rows serialise on the uniform datapath: 32 issues per stage). Rows past the
+// batch are zero-filled. W_L sits in shared memory and is read as broadcasts. 16 warps per CTA, one CTA per SM, kF2Stages stages
+// in flight per warp; a warp's tiles are g = cta + grid * (warp + 16 i).
+// Per-CTA results as in tail_fwd_kernel (loss, max |delta_L|, bias row of the [dW_L; db_L] partial); tail_bwd_kernel runs on a
+// larger grid (n_bwd partials): the bias rows of the partials this grid does not own are zeroed here.
+constexpr int kF2Warps = 16, kF2Stages = 3, kF2StageBytes = 32 * 32 * 4;
+template <int IN> struct Fwd2Plan {
+  static constexpr int NH = IN / 32;
+  static constexpr int kWFloats = (IN + 1) * 12;
+  static constexpr int kSmemBytes = kF2Warps * kF2Stages * kF2StageBytes + kWFloats * 4 + 1024;
+};
+template <int FPL, int OLP>
+__global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p, int n_bwd) {
+  if (spec_skip(p.spec_st, p.spec)) return;
+  constexpr int IN = 32 * FPL;
+  constexpr int NH = Fwd2Plan<IN>::NH;
+  extern __shared__ uint8_t fsm_raw[];
+  const uint32_t base = (tcx::smem_u32(fsm_raw) + 1023u) & ~1023u; // the swizzle pattern is a function of the shared-memory address
+  uint8_t *bp = fsm_raw + (base - tcx::smem_u32(fsm_raw));
+  float *Ws = reinterpret_cast<float *>(bp + kF2Warps * kF2Stages * kF2StageBytes); // [IN + 1][12]: W_L rows zero padded; row IN = bias
+  __shared__ __align__(8) unsigned long long bars[kF2Warps][kF2Stages];
+  __shared__ double lred[32];
+  __shared__ float mred[kF2Warps];
+  __shared__ float dbred[kF2Warps][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OL = (OLP == 10) ? 10 : p.out;
+  for (int e = threadIdx.x; e < (IN + 1) * 12; e += blockDim.x) {
+    const int f = e / 12, j = e - f * 12;
+    Ws[e] = (j < OL) ? __ldg(p.W + (size_t)f * OL + j) : 0.0f;
+  }
+  const uint32_t ring_w = base + warp * (kF2Stages * kF2StageBytes), bar_w = tcx::smem_u32(&bars[warp][0]);
+  const uint8_t *ring_mine = bp + warp * (kF2Stages * kF2StageBytes);
+  if (lane == 0) {
+    for (int st = 0; st < kF2Stages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
+    tcx::fence_mbar_init();
+  }
+  if (threadIdx.x == 0) tcx::tma_prefetch_desc(&tmA);
+  __syncthreads();
+  const long ntiles = (p.batch + 31) / 32;
+  const long g0 = blockIdx.x + (long)gridDim.x * warp, gstep = (long)gridDim.x * kF2Warps;
+  const long my_tiles = g0 < ntiles ? (ntiles - g0 + gstep - 1) / gstep : 0;
+  const long nq = my_tiles * NH; // stages this warp consumes: (tile round i, feature block h) = (q / NH, q % NH)
+  auto issue = [&](long q) {     // lane 0
+    if (q < nq) {
+      const int st = (int)(q % kF2Stages);
+      tcx::mbar_expect_tx(bar_w + 8 * st, kF2StageBytes);
+      tcx::tma_load_2d(ring_w + st * kF2StageBytes, &tmA, bar_w + 8 * st, (int)(q % NH) * 32, (int)((g0 + (q / NH) * gstep) * 32));
+    }
+  };
+  if (lane == 0)
+    for (int q = 0; q < kF2Stages; ++q) issue(q);
+
+  double lsum = 0.0;
+  float amax = 0.0f;
+  float accd[OLP];
+#pragma unroll
+  for (int j = 0; j < OLP; ++j) accd[j] = 0.0f;
+  long q = 0;
+  for (long i = 0; i < my_tiles; ++i) {
+    const long s = (g0 + i * gstep) * 32 + lane; // this lane's sample
+    const bool ok = s < p.batch;
+    float tg[OLP];
+#pragma unroll
+    for (int j = 0; j < OLP; ++j) tg[j] = (ok && j < OL) ? __ldg(p.T + s * OL + j) : 0.0f; // in flight during the dot products
+    float z[OLP];
+#pragma unroll
+    for (int j = 0; j < OLP; ++j) z[j] = 0.0f;
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h, ++q) {
+      const int st = (int)(q % kF2Stages);
+      tcx::mbar_wait(bar_w + 8 * st, (uint32_t)((q / kF2Stages) & 1));
+      const float4 *ar = reinterpret_cast<const float4 *>(ring_mine + st * kF2StageBytes + lane * 128);
+      const float4 *wr = reinterpret_cast<const float4 *>(Ws + (size_t)h * 32 * 12);
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        const float4 av = ar[c ^ (lane & 7)];
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 w0 = wr[(4 * c + e) * 3 + 0], w1 = wr[(4 * c + e) * 3 + 1];
+          tcx::ffma2(z[0], z[1], a4[e], a4[e], w0.x, w0.y);
+          tcx::ffma2(z[2], z[3], a4[e], a4[e], w0.z, w0.w);
+          tcx::ffma2(z[4], z[5], a4[e], a4[e], w1.x, w1.y);
+          tcx::ffma2(z[6], z[7], a4[e], a4[e], w1.z, w1.w);
+          if constexpr (OLP == 10) {
+            const float2 w2 = *reinterpret_cast<const float2 *>(&wr[(4 * c + e) * 3 + 2]);
+            tcx::ffma2(z[8], z[9], a4[e], a4[e], w2.x, w2.y);
+          } else {
+            const float4 w2 = wr[(4 * c + e) * 3 + 2];
+            tcx::ffma2(z[8], z[9], a4[e], a4[e], w2.x, w2.y);
+            tcx::ffma2(z[10], z[11], a4[e], a4[e], w2.z, w2.w);
+          }
+        }
+      }
+      __syncwarp(); // the stage has been read by every lane
+      if (lane == 0) issue(q + kF2Stages);
+    }
+    if (ok) {
+      const float *brow = Ws + (size_t)IN * 12;
+      float o[12], dl[12];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) { o[j] = 0.0f; dl[j] = 0.0f; }
+#pragma unroll
+      for (int j = 0; j < OLP; ++j) {
+        if (j < OL) {
+          o[j] = act_apply(p.act_last, z[j] + brow[j]);
+          const float d = o[j] - tg[j];
+          dl[j] = d * p.inv_batch * act_deriv_from_output(p.act_last, o[j]);
+          lsum += (double)d * (double)d;
+          amax = fmaxf(amax, fabsf(dl[j]));
+          accd[j] += dl[j];
+        }
+      }
+      float *orow = p.out_last + s * OL;
+      if (OL == 10) { // 40-byte rows: 8-byte aligned
+#pragma unroll
+        for (int j = 0; j < 10; j += 2) *reinterpret_cast<float2 *>(orow + j) = make_float2(o[j], o[j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < OLP; ++j) if (j < OL) orow[j] = o[j];
+      }
+      float *drow = p.delta_last + s * p.ldd; // ldd = out rounded up to 4: the padding is written as zeros
+#pragma unroll
+      for (int j = 0; j < 12; j += 4)
+        if (j < p.ldd) *reinterpret_cast<float4 *>(drow + j) = make_float4(dl[j], dl[j + 1], dl[j + 2], dl[j + 3]);
+    }
+  }
+  // ---- per-CTA results (fixed order: deterministic) ----
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+#pragma unroll
+  for (int j = 0; j < OLP; ++j) {
+    float v = accd[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) dbred[warp][j] = v;
+  }
+  if (lane == 0) mred[warp] = amax;
+  const double tot = block_sum(lsum, lred); // (contains the __syncthreads that publishes mred and dbred)
+  const size_t pstride = (size_t)(IN + 1) * OL;
+  if (threadIdx.x < OL) {
+    float v = dbred[0][threadIdx.x];
+    for (int i = 1; i < kF2Warps; ++i) v += dbred[i][threadIdx.x];
+    p.partial[(size_t)blockIdx.x * pstride + (size_t)IN * OL + threadIdx.x] = v;
+    for (int c = blockIdx.x + gridDim.x; c < n_bwd; c += gridDim.x) p.partial[(size_t)c * pstride + (size_t)IN * OL + threadIdx.x] = 0.0f;
+  }
+  if (threadIdx.x == 0) {
+    p.loss_part[blockIdx.x] = tot;
+    float m = mred[0];
+    for (int i = 1; i < kF2Warps; ++i) m = fmaxf(m, mred[i]);
+    p.amax_part[blockIdx.x] = m;
+  }
+}
+
 // ---- pass 2: delta_{L-1} (fp32 for a dX GEMM and / or scaled fp16 hi|lo for the fp16 dW GEMM) and the [dW_L; db_L] partials ----
 template <int FPL, int OLP, bool RELU>
 __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   static_assert(OLP % 2 == 0, "packed FMAs take the outputs in pairs");
   if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int IN = 32 * FPL;
-  __shared__ float red[4 * IN * OLP]; // four copies of the dW accumulators (warps w and w + 4 share one)
+  // the activation ring of the main loop and, after it, four copies of the dW accumulators (warps w and w + 4 share one)
+  constexpr int kRingFloats = 8 * kBwdStages * 2 * IN, kRedFloats = 4 * IN * OLP;
+  __shared__ __align__(128) float ring_red[kRingFloats > kRedFloats ? kRingFloats : kRedFloats];
+  __shared__ __align__(16) float ring_d[8][kBwdStages][2 * 12];
+  __shared__ __align__(8) unsigned long long bars[8][kBwdStages];
+  float *red = ring_red;
   __shared__ float mred[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int OL = p.out;
+  const int OL = (OLP == 10) ? 10 : p.out; // launch_tail: the 10-wide instantiation serves exactly out == 10
   float w[FPL][OLP];
 #pragma unroll
   for (int c = 0; c < FPL; ++c)
@@ -262,34 +459,33 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
     for (int j = 0; j < OLP; ++j) acc[c][j] = 0.0f;
 
   const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
-  // one sample per warp and step; the next sample's activations and delta_L (48 bytes, the same for every lane) are in
-  // flight while this one is processed
-  float a[FPL], an[FPL], an2[FPL], an3[FPL];
-  float4 dv[3], dn[3];
-  auto fetch_a = [&](long s, float (&x)[FPL]) {
-#pragma unroll
-    for (int c = 0; c < FPL; ++c) x[c] = 0.0f;
-    if (s < b1) load_row<FPL>(p.A + s * IN + lane * FPL, x);
-  };
-  auto fetch_d = [&](long s, float4 (&y)[3]) { // delta_L of one sample: 48 bytes, L2-resident (tail_fwd_kernel just wrote it)
-    y[0] = y[1] = y[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // two consecutive samples per warp and step; their activations (2 IN floats) and delta_L (2 ldd floats, broadcast to every
+  // lane) arrive through a per-warp ring of bulk async copies kBwdStages steps ahead (see tail_fwd_kernel)
+  float *ring_mine = ring_red + warp * (kBwdStages * 2 * IN);
+  const uint32_t ring_w = tcx::smem_u32(ring_mine), ringd_w = tcx::smem_u32(&ring_d[warp][0][0]);
+  const uint32_t bar_w = tcx::smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+    for (int st = 0; st < kBwdStages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
+    tcx::fence_mbar_init();
+  }
+  __syncwarp();
+  const int ldd = p.ldd;
+  auto issue = [&](long s, int st) { // lane 0
     if (s < b1) {
-      const float4 *dp = reinterpret_cast<const float4 *>(p.delta_last + s * p.ldd);
-      y[0] = __ldg(dp);
-      if (p.ldd > 4) y[1] = __ldg(dp + 1);
-      if (p.ldd > 8) y[2] = __ldg(dp + 2);
+      const uint32_t rows = (uint32_t)min(2L, b1 - s);
+      tcx::mbar_expect_tx(bar_w + 8 * st, rows * (IN * 4 + ldd * 4));
+      tcx::bulk_load_1d(ring_w + st * (2 * IN * 4), p.A + s * IN, rows * (IN * 4), bar_w + 8 * st);
+      tcx::bulk_load_1d(ringd_w + st * 96, p.delta_last + s * ldd, rows * (ldd * 4), bar_w + 8 * st);
     }
   };
-  long s = b0 + warp;
-  fetch_a(s, a); fetch_d(s, dv);
-  fetch_a(s + 8, an);
-  fetch_a(s + 16, an2);
-  for (; s < b1; s += 8) {
-    fetch_a(s + 24, an3); // activations three samples ahead (HBM latency), delta_L one ahead
-    fetch_d(s + 8, dn);
+  auto process = [&](long s, const float *arow, const float *drow) { // one sample: delta_{L-1}[s][:] and the dW update
+    float a[FPL];
+    load_row_shared<FPL>(arow + lane * FPL, a);
     float d[OLP];
     {
-      const float t[12] = {dv[0].x, dv[0].y, dv[0].z, dv[0].w, dv[1].x, dv[1].y, dv[1].z, dv[1].w, dv[2].x, dv[2].y, dv[2].z, dv[2].w};
+      const float4 *dp = reinterpret_cast<const float4 *>(drow);
+      const float4 d0 = dp[0], d1 = ldd > 4 ? dp[1] : make_float4(0.f, 0.f, 0.f, 0.f), d2 = ldd > 8 ? dp[2] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float t[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
 #pragma unroll
       for (int j = 0; j < OLP; ++j) d[j] = (j < OL) ? t[j] : 0.0f;
     }
@@ -337,10 +533,22 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
         row[IN] = lo[0];
       }
     }
-#pragma unroll
-    for (int c = 0; c < FPL; ++c) { a[c] = an[c]; an[c] = an2[c]; an2[c] = an3[c]; }
-    dv[0] = dn[0]; dv[1] = dn[1]; dv[2] = dn[2];
+  };
+  long s = b0 + 2 * warp;
+  if (lane == 0)
+    for (int st = 0; st < kBwdStages; ++st) issue(s + 16L * st, st);
+  int st = 0;
+  uint32_t ph = 0;
+  for (; s < b1; s += 16) {
+    tcx::mbar_wait(bar_w + 8 * st, ph);
+    const float *ar = ring_mine + st * (2 * IN), *dr = &ring_d[warp][st][0];
+    process(s, ar, dr);
+    if (s + 1 < b1) process(s + 1, ar + IN, dr + ldd);
+    __syncwarp(); // the slot has been consumed by every lane: refill it for the step kBwdStages ahead
+    if (lane == 0) issue(s + 16L * kBwdStages, st);
+    if (++st == kBwdStages) { st = 0; ph ^= 1; }
   }
+  __syncthreads(); // every warp is done with its ring (nothing is in flight: each copy issued was waited for) before `red` reuses it
 
   // ---- per-CTA combine: warps 0-3 park their accumulators, warps 4-7 add theirs on top, then each thread adds the four copies
   // of its elements in a fixed order (deterministic; three barriers instead of eight serialised rounds) ---------------------
@@ -368,13 +576,34 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   }
 }
 
-template <int FPL> int launch_tail(b200_ctx *ctx, const TailParams &p, int grid, cudaStream_t st) {
+template <int FPL, int OLP> int launch_tail_fwd2(const TailParams &p, int grid_fwd, int grid_bwd, cudaStream_t st) {
+  auto kern = tail_fwd2_kernel<FPL, OLP>;
+  constexpr int smem = Fwd2Plan<32 * FPL>::kSmemBytes;
+  CUtensorMap tmA; // A_{L-1} [batch][IN] fp32: box {32 features, 32 samples}
+  B200_TRY(tc_make_map_2d_f32(&tmA, p.A, 32 * FPL, (unsigned long long)p.batch, 32, 32));
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid_fwd, kF2Warps * 32, smem, st>>>(tmA, p, grid_bwd);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// grid_fwd > 0: sample-per-lane forward on its own grid (p.n_amax = grid_fwd); else the feature-per-lane forward on `grid`
+template <int FPL> int launch_tail(b200_ctx *ctx, const TailParams &p, int grid, int grid_fwd, cudaStream_t st) {
   if (p.out == 10) {
-    { ProfScope ps(ctx, "tail_fwd"); B200_LAUNCH((tail_fwd_kernel<FPL, 10>), grid, 256, 0, st, p); }
+    { ProfScope ps(ctx, "tail_fwd");
+      if (grid_fwd > 0) B200_TRY((launch_tail_fwd2<FPL, 10>(p, grid_fwd, grid, st)));
+      else B200_LAUNCH((tail_fwd_kernel<FPL, 10>), grid, 256, 0, st, p); }
     { ProfScope ps(ctx, "tail_bwd"); if (p.act_prev == B200_ACT_RELU) B200_LAUNCH((tail_bwd_kernel<FPL, 10, true>), grid, 256, 0, st, p);
       else B200_LAUNCH((tail_bwd_kernel<FPL, 10, false>), grid, 256, 0, st, p); }
   } else {
-    { ProfScope ps(ctx, "tail_fwd"); B200_LAUNCH((tail_fwd_kernel<FPL, 12>), grid, 256, 0, st, p); }
+    { ProfScope ps(ctx, "tail_fwd");
+      if (grid_fwd > 0) B200_TRY((launch_tail_fwd2<FPL, 12>(p, grid_fwd, grid, st)));
+      else B200_LAUNCH((tail_fwd_kernel<FPL, 12>), grid, 256, 0, st, p); }
     { ProfScope ps(ctx, "tail_bwd"); if (p.act_prev == B200_ACT_RELU) B200_LAUNCH((tail_bwd_kernel<FPL, 12, true>), grid, 256, 0, st, p);
       else B200_LAUNCH((tail_bwd_kernel<FPL, 12, false>), grid, 256, 0, st, p); }
   }
@@ -433,12 +662,18 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   int grid = std::max(1, std::min(max_grid, ceil_div(batch, 32)));
   p.chunk = ceil_div(ceil_div(batch, grid), 16) * 16;
   grid = ceil_div(batch, p.chunk);
-  p.n_amax = grid;
-  if (in == 128) B200_TRY(launch_tail<4>(net->ctx, p, grid, net->ctx->stream));
-  else if (in == 64) B200_TRY(launch_tail<2>(net->ctx, p, grid, net->ctx->stream));
-  else B200_TRY(launch_tail<1>(net->ctx, p, grid, net->ctx->stream));
+  // forward: sample-per-lane kernel on one CTA per SM (B200_TAIL_FWD=1: the feature-per-lane kernel on the backward's grid)
+  const char *fenv = std::getenv("B200_TAIL_FWD");
+  const bool fwd2 = !(fenv && std::atoi(fenv) == 1) && (reinterpret_cast<uintptr_t>(p.A) & 15u) == 0 && (p.ldd % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.delta_last) & 15u) == 0 && (out != 10 || (reinterpret_cast<uintptr_t>(p.out_last) & 7u) == 0);
+  // (never more forward CTAs than backward partials: each forward CTA leaves its bias-gradient row in the partial of its index)
+  const int grid_fwd = fwd2 ? std::max(1, std::min(std::min(std::min(net->ctx->num_sms, net->loss_part_cap), grid), (int)ceil_div(batch, 32))) : 0;
+  p.n_amax = fwd2 ? grid_fwd : grid;
+  if (in == 128) B200_TRY(launch_tail<4>(net->ctx, p, grid, grid_fwd, net->ctx->stream));
+  else if (in == 64) B200_TRY(launch_tail<2>(net->ctx, p, grid, grid_fwd, net->ctx->stream));
+  else B200_TRY(launch_tail<1>(net->ctx, p, grid, grid_fwd, net->ctx->stream));
   net->splits_used[L - 1] = grid;
-  net->loss_part_n = grid;
+  net->loss_part_n = fwd2 ? grid_fwd : grid;
   return B200_OK;
 }
 

@@ -3,7 +3,8 @@
 Kernels under test (all reached through the C ABI):
   fwd16   gemm_fwd16.cu  persistent forward of layer 0: exact fp16 X  x  scaled fp16 {hi, lo} weights (22 mantissa bits)
   dw16    gemm_dw16.cu   split-K [dW_0; db_0]: X^T x [delta_hi | delta_lo], bias gradient from the ones column of the fp16 X copy
-  tail    tail_layer.cu  last layer forward + loss + both deltas + [dW_L; db_L] in two passes over A_{L-1} (fp32 FFMA)
+  tail    tail_layer.cu  last layer forward + loss + both deltas + [dW_L; db_L] in two passes over A_{L-1} (fp32 FFMA); the forward
+          pass has a sample-per-lane form (default) and a feature-per-lane form (B200_TAIL_FWD=1)
   lbfgs_direction_kernel  dots -> grid barrier -> solve -> apply in one launch
 Each can be switched off with an environment variable read per call, so the same network is evaluated through the generic
 kernels and through the new ones and both are compared with the fp64 oracle.
@@ -21,7 +22,7 @@ from helpers import make_gpu_net, make_problem, upload
 
 pytestmark = pytest.mark.gpu
 
-TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16")
+TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16", "B200_TAIL_FWD")
 
 
 def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True):
@@ -76,7 +77,7 @@ def test_fp16_path_parity(handle, oracle, dims, acts, batch):
     assert rel_l2(out, fo) <= 2e-5, rel_l2(out, fo)
 
 
-@pytest.mark.parametrize("env", [{"B200_DW16": "0"}, {"B200_TAIL": "0"}, {"B200_FWD16": "0"},
+@pytest.mark.parametrize("env", [{"B200_DW16": "0"}, {"B200_TAIL": "0"}, {"B200_FWD16": "0"}, {"B200_TAIL_FWD": "1"},
                                  {"B200_FWD16": "0", "B200_TAIL": "0", "B200_DW16": "0"}])
 @pytest.mark.parametrize("which", [0, 5])
 def test_each_new_kernel_against_the_generic_path(handle, oracle, env, which):
