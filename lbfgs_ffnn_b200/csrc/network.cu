@@ -90,6 +90,14 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += (double)t[u];
       }
+      if (sp < L.splits && sp + 40 >= L.splits) { // at most five slices left for this warp (37-way split-K of layer 0): loads go out together
+        float t[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) t[u] = (sp + 8 * u < L.splits) ? __ldg(src + (unsigned long long)(sp + 8 * u) * L.size) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) acc += (double)t[u];
+        sp += 40;
+      }
       for (; sp < L.splits; sp += 8) acc += (double)__ldg(src + (unsigned long long)sp * L.size);
     }
     __syncthreads();

@@ -253,18 +253,13 @@ __global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __gri
   __shared__ float dbred[kF2Warps][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OL = (OLP == 10) ? 10 : p.out;
-  for (int e = threadIdx.x; e < (IN + 1) * 12; e += blockDim.x) {
-    const int f = e / 12, j = e - f * 12;
-    Ws[e] = (j < OL) ? __ldg(p.W + (size_t)f * OL + j) : 0.0f;
-  }
   const uint32_t ring_w = base + warp * (kF2Stages * kF2StageBytes), bar_w = tcx::smem_u32(&bars[warp][0]);
   const uint8_t *ring_mine = bp + warp * (kF2Stages * kF2StageBytes);
-  if (lane == 0) {
+  if (lane == 0) { // a warp's barriers and ring are its own: its first loads go out before the CTA-wide weight staging below
     for (int st = 0; st < kF2Stages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
     tcx::fence_mbar_init();
   }
-  if (threadIdx.x == 0) tcx::tma_prefetch_desc(&tmA);
-  __syncthreads();
+  __syncwarp();
   const long ntiles = (p.batch + 31) / 32;
   const long g0 = blockIdx.x + (long)gridDim.x * warp, gstep = (long)gridDim.x * kF2Warps;
   const long my_tiles = g0 < ntiles ? (ntiles - g0 + gstep - 1) / gstep : 0;
@@ -278,6 +273,11 @@ __global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __gri
   };
   if (lane == 0)
     for (int q = 0; q < kF2Stages; ++q) issue(q);
+  for (int e = threadIdx.x; e < (IN + 1) * 12; e += blockDim.x) {
+    const int f = e / 12, j = e - f * 12;
+    Ws[e] = (j < OL) ? __ldg(p.W + (size_t)f * OL + j) : 0.0f;
+  }
+  __syncthreads();
 
   double lsum = 0.0;
   float amax = 0.0f;
@@ -395,6 +395,29 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   float *red = ring_red;
   __shared__ float mred[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
+  // two consecutive samples per warp and step; their activations (2 IN floats) and delta_L (2 ldd floats, broadcast to every
+  // lane) arrive through a per-warp ring of bulk async copies kBwdStages steps ahead (see tail_fwd_kernel)
+  float *ring_mine = ring_red + warp * (kBwdStages * 2 * IN);
+  const uint32_t ring_w = tcx::smem_u32(ring_mine), ringd_w = tcx::smem_u32(&ring_d[warp][0][0]);
+  const uint32_t bar_w = tcx::smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+    for (int st = 0; st < kBwdStages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
+    tcx::fence_mbar_init();
+  }
+  __syncwarp();
+  const int ldd = p.ldd;
+  auto issue = [&](long s, int st) { // lane 0
+    if (s < b1) {
+      const uint32_t rows = (uint32_t)min(2L, b1 - s);
+      tcx::mbar_expect_tx(bar_w + 8 * st, rows * (IN * 4 + ldd * 4));
+      tcx::bulk_load_1d(ring_w + st * (2 * IN * 4), p.A + s * IN, rows * (IN * 4), bar_w + 8 * st);
+      tcx::bulk_load_1d(ringd_w + st * 96, p.delta_last + s * ldd, rows * (ldd * 4), bar_w + 8 * st);
+    }
+  };
+  long s = b0 + 2 * warp;
+  if (lane == 0) // first loads out before the weight / scale prologue below
+    for (int st0 = 0; st0 < kBwdStages; ++st0) issue(s + 16L * st0, st0);
   const int OL = (OLP == 10) ? 10 : p.out; // launch_tail: the 10-wide instantiation serves exactly out == 10
   float w[FPL][OLP];
 #pragma unroll
@@ -458,26 +481,6 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
 #pragma unroll
     for (int j = 0; j < OLP; ++j) acc[c][j] = 0.0f;
 
-  const long b0 = (long)blockIdx.x * p.chunk, b1 = min(p.batch, b0 + (long)p.chunk);
-  // two consecutive samples per warp and step; their activations (2 IN floats) and delta_L (2 ldd floats, broadcast to every
-  // lane) arrive through a per-warp ring of bulk async copies kBwdStages steps ahead (see tail_fwd_kernel)
-  float *ring_mine = ring_red + warp * (kBwdStages * 2 * IN);
-  const uint32_t ring_w = tcx::smem_u32(ring_mine), ringd_w = tcx::smem_u32(&ring_d[warp][0][0]);
-  const uint32_t bar_w = tcx::smem_u32(&bars[warp][0]);
-  if (lane == 0) {
-    for (int st = 0; st < kBwdStages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
-    tcx::fence_mbar_init();
-  }
-  __syncwarp();
-  const int ldd = p.ldd;
-  auto issue = [&](long s, int st) { // lane 0
-    if (s < b1) {
-      const uint32_t rows = (uint32_t)min(2L, b1 - s);
-      tcx::mbar_expect_tx(bar_w + 8 * st, rows * (IN * 4 + ldd * 4));
-      tcx::bulk_load_1d(ring_w + st * (2 * IN * 4), p.A + s * IN, rows * (IN * 4), bar_w + 8 * st);
-      tcx::bulk_load_1d(ringd_w + st * 96, p.delta_last + s * ldd, rows * (ldd * 4), bar_w + 8 * st);
-    }
-  };
   auto process = [&](long s, const float *arow, const float *drow) { // one sample: delta_{L-1}[s][:] and the dW update
     float a[FPL];
     load_row_shared<FPL>(arow + lane * FPL, a);
@@ -534,9 +537,6 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
       }
     }
   };
-  long s = b0 + 2 * warp;
-  if (lane == 0)
-    for (int st = 0; st < kBwdStages; ++st) issue(s + 16L * st, st);
   int st = 0;
   uint32_t ph = 0;
   for (; s < b1; s += 16) {
