@@ -253,13 +253,18 @@ __global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __gri
   __shared__ float dbred[kF2Warps][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OL = (OLP == 10) ? 10 : p.out;
+  for (int e = threadIdx.x; e < (IN + 1) * 12; e += blockDim.x) {
+    const int f = e / 12, j = e - f * 12;
+    Ws[e] = (j < OL) ? __ldg(p.W + (size_t)f * OL + j) : 0.0f;
+  }
   const uint32_t ring_w = base + warp * (kF2Stages * kF2StageBytes), bar_w = tcx::smem_u32(&bars[warp][0]);
   const uint8_t *ring_mine = bp + warp * (kF2Stages * kF2StageBytes);
-  if (lane == 0) { // a warp's barriers and ring are its own: its first loads go out before the CTA-wide weight staging below
+  if (lane == 0) {
     for (int st = 0; st < kF2Stages; ++st) tcx::mbar_init(bar_w + 8 * st, 1);
     tcx::fence_mbar_init();
   }
-  __syncwarp();
+  if (threadIdx.x == 0) tcx::tma_prefetch_desc(&tmA);
+  __syncthreads();
   const long ntiles = (p.batch + 31) / 32;
   const long g0 = blockIdx.x + (long)gridDim.x * warp, gstep = (long)gridDim.x * kF2Warps;
   const long my_tiles = g0 < ntiles ? (ntiles - g0 + gstep - 1) / gstep : 0;
@@ -273,11 +278,6 @@ __global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __gri
   };
   if (lane == 0)
     for (int q = 0; q < kF2Stages; ++q) issue(q);
-  for (int e = threadIdx.x; e < (IN + 1) * 12; e += blockDim.x) {
-    const int f = e / 12, j = e - f * 12;
-    Ws[e] = (j < OL) ? __ldg(p.W + (size_t)f * OL + j) : 0.0f;
-  }
-  __syncthreads();
 
   double lsum = 0.0;
   float amax = 0.0f;
