@@ -487,7 +487,7 @@ int fwd16_prepare(b200_net *net, const float *params) {
   return B200_OK;
 }
 
-// Layer 0 forward on the fp16 copy of an 8-bit-pixel input (x16: rows of ld16 halves, value u = 255 x). Sets *done when it ran.
+// Layer 0 forward on the fp16 copy of an 8-bit-pixel input (x16: feature-block-major [blocks of 64 features][rows][64] halves, value u = 255 x). Sets *done when it ran.
 int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View &x16, long batch, bool *done) {
   *done = false;
   if (l != 0 || !x16.base || !fwd16_shape_ok(net) || (reinterpret_cast<uintptr_t>(net->act[0]) & 15u)) return B200_OK;

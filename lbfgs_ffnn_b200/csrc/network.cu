@@ -358,8 +358,9 @@ __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restri
 }
 
 // x -> u = round(255 x) as uint8 AND as fp16 (exact: u <= 255 has 8 significant bits); *flag &= (every x is exactly
-// float(u)/255.0f with 0 <= u <= 255). The fp16 rows are [in | 1 | zero padding] with ld16 halves per row: column `in` is the
-// ones feature whose "weight gradient" is the bias gradient (gemm_dw16.cu), and TMA feeds the rows to the tensor cores as they are.
+// float(u)/255.0f with 0 <= u <= 255). The fp16 copy is feature-block-major, [nblocks16][rows][64]: features [in | 1 | zero padding];
+// column `in` is the ones feature whose "weight gradient" is the bias gradient (gemm_dw16.cu), and every operand tile of the layer-0
+// GEMMs is one contiguous chunk that TMA feeds to the tensor cores as it is.
 __global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n, int in, int nblocks16,
                                                           uint8_t *__restrict__ q, __half *__restrict__ q16, int *flag) {
   int ok = 1;
