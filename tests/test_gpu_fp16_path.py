@@ -209,3 +209,23 @@ def test_fused_direction_kernel_matches_the_three_kernel_path(handle, oracle, m)
     assert np.array_equal(out[True][1], out[False][1])
     ref = onet.lbfgs(w, X, T, m=m, max_iters=iters, tol=0.0, policy="cuda")
     assert np.allclose(out[True][0], ref["loss"], rtol=2e-3)
+
+
+@pytest.mark.parametrize("dims", [[784, 64, 32, 10], [784, 128, 128, 10], [784, 128, 64, 32, 10], [784, 64, 64, 64, 5],
+                                  [784, 128, 64, 64, 64, 10], [256, 128, 64, 10]])
+def test_deeper_nets_chain_the_fp16_delta_scale(handle, oracle, dims):
+    """three to six layers: the layer-1 dX kernel emits the fp16 delta_0 with the scale bound chained through every later
+    weight matrix, the middle layers run the two-stage generic kernel (tools/shape_sweep.py sweeps more shapes)"""
+    acts = ["relu"] * (len(dims) - 2) + ["linear"]
+    for batch in (33, 1500):
+        X, _ = P.synthetic_mnist(batch, seed=5)
+        X = np.ascontiguousarray(X[:, :dims[0]])
+        rs = np.random.RandomState(1)
+        T = np.zeros((batch, dims[-1]), dtype=np.float32)
+        T[np.arange(batch), rs.randint(0, dims[-1], batch)] = 1
+        onet = oracle.OracleNet(dims, acts)
+        w = onet.init_params_cuda_rule(123).astype(np.float32)
+        lo, go = onet.loss_grad(w, X, T)
+        loss, g, _ = _eval(handle, dims, acts, w, X, T, "tf32x3")
+        assert abs(loss - lo) <= 2e-5 * abs(lo), (dims, batch, loss, lo)
+        assert rel_l2(g, go) <= 2e-5, (dims, batch, rel_l2(g, go))
