@@ -73,7 +73,10 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
     gdst = reinterpret_cast<float *>(p.sym_local + (epoch & 1u) * p.slot_bytes);
   }
   const unsigned long long ngroups = (p.n + 31) / 32;
-  for (unsigned long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  // groups are taken from the END of the vector first: the last layer's elements have the most slices (one per CTA of the
+  // last-layer backward kernel, ~300) and would otherwise start in the final pass of the loop, as the kernel's long pole
+  for (unsigned long long it = blockIdx.x; it < ngroups; it += gridDim.x) {
+    const unsigned long long grp = ngroups - 1 - it;
     const unsigned long long j = grp * 32 + lane;
     double acc = 0.0;
     if (j < p.n) {
