@@ -240,6 +240,9 @@ int b200_convert_f64_to_f32(b200_ctx *ctx, const double *src_dev, float *dst_dev
 
 /* kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
 long b200_launch_count(void);
+/* The B200_* debugging switches of the environment are read once, when the library is first used; nothing on the
+ * per-iteration path calls getenv. Tests that flip a switch in a running process call this to re-read them. */
+int b200_debug_reload_env(void);
 
 #ifdef __cplusplus
 }

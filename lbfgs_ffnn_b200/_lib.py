@@ -115,6 +115,7 @@ SYMBOLS = {
     "b200_vec_trial_point": (_i, [_vp, _sz, _vp, _f, _vp, _vp]),
     "b200_convert_f64_to_f32": (_i, [_vp, _vp, _vp, _sz]),
     "b200_launch_count": (_l, []),
+    "b200_debug_reload_env": (_i, []),
 }
 
 _lib = None

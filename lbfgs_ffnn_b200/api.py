@@ -578,3 +578,8 @@ def slbfgs_sample_stream(seed, N, b, count):
 
 def launch_count():
     return lib().b200_launch_count()
+
+
+def reload_env():
+    """re-read the B200_* debugging switches (the library reads the environment once, at first use)"""
+    check(lib().b200_debug_reload_env())

@@ -52,6 +52,25 @@ extern std::atomic<long> g_launches;
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---- debugging switches (environment), read ONCE at library load and again only by b200_debug_reload_env(): nothing on the
+// per-iteration path calls getenv -------------------------------------------------------------------
+struct EnvFlags {
+  bool no_fused_direction = false; // B200_NO_FUSED_DIRECTION: three-kernel direction (dots, solve, apply)
+  bool no_graph = false;           // B200_NO_GRAPH: plain launches instead of the captured iteration graph
+  bool tc_timing = false;          // B200_TC_TIMING: per-CTA clock64 instrumentation of the tcgen05 kernels
+  bool no_zero_copy = false;       // B200_NO_ZERO_COPY: D2H copy nodes instead of kernels writing the pinned mailbox
+  bool no_speculation = false;     // B200_NO_SPECULATION: never launch the next iteration's graph ahead of the host
+  bool no_p2p = false;             // B200_NO_P2P: NCCL all-reduce instead of the peer-memory one
+  bool nvtx = false;               // B200_NVTX: NVTX ranges around direction / evaluation / collective
+  int fwd16 = -1, dw16 = -1, tail = -1, tail_fwd = -1; // B200_FWD16 / _DW16 / _TAIL / _TAIL_FWD: -1 unset, else the integer
+  int mid16 = -1;                  // B200_MID16: 0 = hidden layers on the generic TF32 kernels
+  int tc_mask = 7;                 // B200_TC_MASK: bit0 FWD, bit1 DX, bit2 DW on the tensor cores; bit3 / bit4 see gemm_tc.cu
+  int dw_bn = 0;                   // B200_DW_BN: 128 / 256, 0 = by precision mode
+  long p2p_spin_limit = 0;         // B200_P2P_SPIN_LIMIT: polls before p2p_reduce_kernel gives up on a peer (0 = default)
+};
+const EnvFlags &env();
+void env_reload();
+
 // ---- NCCL, loaded lazily with dlopen so the single-GPU path has no NCCL dependency -------------
 struct NcclApi;
 NcclApi *nccl_api(); // nullptr (and error set) if libnccl cannot be loaded
@@ -85,6 +104,10 @@ struct Profiler {
 } // namespace b200
 
 // ---- context ---------------------------------------------------------------------------------------
+namespace b200 {
+constexpr int kHostScalars = 128;
+constexpr int kHostErrSlot = 64; // h_scalars[kHostErrSlot] != 0: a device-side wait gave up (p2p_reduce_kernel: dead or stalled peer)
+} // namespace b200
 struct b200_ctx {
   b200::Profiler prof;
   int device = 0;
@@ -95,7 +118,7 @@ struct b200_ctx {
   void *comm = nullptr; // ncclComm_t
   int rank = 0, world = 1;
   // small pinned host mailbox for scalar read-backs
-  double *h_scalars = nullptr; // 64 doubles, pinned
+  double *h_scalars = nullptr; // kHostScalars doubles, pinned (zero-copy: kernels write results and error flags into it)
   double *d_scalars = nullptr; // 64 doubles, device
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   // solver objects parked by b200_lbfgs_destroy for reuse (work space + instantiated CUDA graphs): a solve call from host
@@ -104,7 +127,8 @@ struct b200_ctx {
   // {2 x [slot_floats floats | loss double], flags[world], epoch}; peers[r] is rank r's buffer mapped into this process
   struct P2P {
     bool tried = false, ready = false;
-    size_t slot_floats = 0, slot_bytes = 0;
+    long gen = 0; // bumped whenever the buffers are (re)made: captured graphs bake their addresses in
+    size_t slot_floats = 0, slot_bytes = 0, req_floats = 0;
     char *local = nullptr;        // this rank's buffer
     char **peers_dev = nullptr;   // device array of world pointers (own entry = local)
     std::vector<void *> opened;   // cudaIpcOpenMemHandle results (to close)
@@ -136,6 +160,8 @@ int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev); // gr
 // collective (every rank calls it with the same n): maps the peers' symmetric buffers; ctx->p2p.ready tells whether the
 // peer-memory all-reduce can be used (all ranks agree), otherwise the callers stay on NCCL
 int ctx_p2p_setup(b200_ctx *ctx, size_t n_floats);
+// after a stream synchronisation: B200_ERR_COMM if a device-side wait on a peer timed out since the last check
+int ctx_check_device_error(b200_ctx *ctx);
 int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n);
 int ctx_reduce_shards(b200_ctx *ctx, const float *full, float *shard_out, size_t n, size_t chunk);
 int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk);

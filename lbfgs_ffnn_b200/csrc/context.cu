@@ -26,6 +26,34 @@ void set_error(const char *fmt, ...) {
   t_error = buf;
 }
 
+static EnvFlags g_env;
+static std::once_flag g_env_once;
+void env_reload() {
+  auto flag = [](const char *n) { return std::getenv(n) != nullptr; };
+  auto num = [](const char *n, int dflt) { const char *e = std::getenv(n); return e ? std::atoi(e) : dflt; };
+  EnvFlags e;
+  e.no_fused_direction = flag("B200_NO_FUSED_DIRECTION");
+  e.no_graph = flag("B200_NO_GRAPH");
+  e.tc_timing = flag("B200_TC_TIMING");
+  e.no_zero_copy = flag("B200_NO_ZERO_COPY");
+  e.no_speculation = flag("B200_NO_SPECULATION");
+  e.no_p2p = flag("B200_NO_P2P");
+  e.nvtx = flag("B200_NVTX");
+  e.fwd16 = num("B200_FWD16", -1);
+  e.dw16 = num("B200_DW16", -1);
+  e.tail = num("B200_TAIL", -1);
+  e.tail_fwd = num("B200_TAIL_FWD", -1);
+  e.mid16 = num("B200_MID16", -1);
+  e.tc_mask = num("B200_TC_MASK", 7);
+  e.dw_bn = num("B200_DW_BN", 0);
+  if (const char *s = std::getenv("B200_P2P_SPIN_LIMIT")) e.p2p_spin_limit = std::atol(s);
+  g_env = e;
+}
+const EnvFlags &env() {
+  std::call_once(g_env_once, env_reload);
+  return g_env;
+}
+
 struct NcclApi {
   void *handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -107,14 +135,30 @@ int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev) {
 int ctx_p2p_setup(b200_ctx *ctx, size_t n_floats) {
   b200_ctx::P2P &pp = ctx->p2p;
   if (ctx->world <= 1) return B200_OK;
-  if (pp.tried) return B200_OK; // one attempt per context; a later, larger network simply stays on NCCL
-  pp.tried = true;
+  if (pp.tried && n_floats <= pp.req_floats) return B200_OK;
   NcclApi *api = nccl_api();
   if (!api) return B200_ERR_COMM;
   ncclComm_t comm = (ncclComm_t)ctx->comm;
   const int W = ctx->world;
-  const char *env = std::getenv("B200_NO_P2P");
-  int ok = (env == nullptr) ? 1 : 0;
+  if (pp.tried) {
+    // a larger network than the buffers were sized for (every rank gets here at the same evaluation): nobody may still be reading
+    // the old slots when they are unmapped, so drain and meet the peers first
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    B200_TRY(ctx_allreduce_f64(ctx, ctx->d_scalars + 63, 1));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (void *p : pp.opened) cudaIpcCloseMemHandle(p);
+    pp.opened.clear();
+    if (pp.peers_dev) cudaFree(pp.peers_dev);
+    if (pp.local) cudaFree(pp.local);
+    pp.peers_dev = nullptr;
+    pp.local = nullptr;
+    pp.ready = false;
+    cudaGetLastError();
+  }
+  pp.tried = true;
+  pp.req_floats = n_floats;
+  ++pp.gen;
+  int ok = env().no_p2p ? 0 : 1;
   pp.slot_floats = (n_floats + 63) & ~size_t(63);
   pp.slot_bytes = ((pp.slot_floats * 4 + 8) + 255) & ~size_t(255);
   const size_t total = 2 * pp.slot_bytes + ((sizeof(unsigned) * (W + 1) + 255) & ~size_t(255));
@@ -197,6 +241,15 @@ int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk) {
   return B200_OK;
 }
 
+int ctx_check_device_error(b200_ctx *ctx) {
+  volatile double *flag = ctx->h_scalars + kHostErrSlot;
+  if (*flag == 0.0) return B200_OK;
+  *flag = 0.0;
+  set_error("rank %d: a peer did not publish its gradient slot within the wait limit of the peer-memory all-reduce "
+            "(dead or stalled rank); results of this evaluation are invalid", ctx->rank);
+  return B200_ERR_COMM;
+}
+
 int ctx_allreduce_f64(b200_ctx *ctx, double *v, size_t n) {
   if (ctx->world <= 1) return B200_OK;
   NcclApi *api = nccl_api();
@@ -214,6 +267,11 @@ extern "C" {
 const char *b200_last_error(void) { return t_error.c_str(); }
 int b200_abi_version(void) { return B200_ABI_VERSION; }
 long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int b200_debug_reload_env(void) {
+  env(); // (first use reads the environment itself)
+  env_reload();
+  return B200_OK;
+}
 
 int b200_ctx_create(int device, b200_ctx **out) {
   B200_REQUIRE(out, "null out pointer");
@@ -232,7 +290,8 @@ int b200_ctx_create(int device, b200_ctx **out) {
   ctx->num_sms = prop.multiProcessorCount;
   B200_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
-  B200_CUDA(cudaMallocHost(&ctx->h_scalars, sizeof(double) * 64));
+  B200_CUDA(cudaMallocHost(&ctx->h_scalars, sizeof(double) * kHostScalars));
+  memset(ctx->h_scalars, 0, sizeof(double) * kHostScalars);
   B200_CUDA(cudaMalloc(&ctx->d_scalars, sizeof(double) * 64));
   B200_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
   B200_CUDA(cudaEventCreate(&ctx->ev_a));

@@ -322,7 +322,7 @@ int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap 
     attr_set = true;
   }
   static long long *dbg = nullptr;
-  static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
+  const bool timing = env().tc_timing;
   Dw16Params pp = p;
   if (timing) {
     if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 4 * 1024));
@@ -348,8 +348,7 @@ int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap 
 } // namespace
 
 bool dw16_applicable(const b200_net *net) {
-  const char *env = std::getenv("B200_DW16"); // debugging aid, read per call: 0 = generic tcgen05 kernel
-  if (env && std::atoi(env) == 0) return false;
+  if (env().dw16 == 0) return false; // debugging aid: 0 = generic tcgen05 kernel
   const int K0 = net->dims[0], N0 = net->dims[1];
   if (!(net->prec != B200_PREC_FP32 && K0 % 16 == 0 && (N0 == 64 || N0 == 128) && tail_applicable(net))) return false;
   // two layers: the tail writes the fp16 delta_0; deeper: the DX kernel of layer 1 does, with a chained scale bound

@@ -424,7 +424,7 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
     attr_set = true;
   }
   static long long *dbg = nullptr;
-  static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
+  const bool timing = env().tc_timing;
   F16Params pp = p;
   if (timing) {
     if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 1024));
@@ -454,8 +454,7 @@ int tc_make_map_2d_f32(CUtensorMap *tm, const float *ptr, unsigned long long dim
 }
 
 static bool fwd16_shape_ok(const b200_net *net) {
-  const char *env = std::getenv("B200_FWD16"); // debugging aid, read per call: 0 = use the generic tcgen05 kernel
-  if (env && std::atoi(env) == 0) return false;
+  if (env().fwd16 == 0) return false; // debugging aid: 0 = use the generic tcgen05 kernel
   const int K = net->dims[0], N = net->dims[1];
   return net->nlayers() >= 2 && net->prec != B200_PREC_FP32 && K % 16 == 0 && K <= kSplitMaxK && N % 32 == 0 && N <= 128;
 }

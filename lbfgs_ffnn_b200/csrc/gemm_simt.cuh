@@ -45,6 +45,8 @@ struct GemmParams {
   long ldd;
   float inv_batch;    // FWD_LAST: 1/B_global
   double *loss_part;  // FWD_LAST: one partial per CTA
+  const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
+  int spec;
 };
 
 constexpr int kBM = 128, kBK = 16, kThreads = 256, kPad = 4;
@@ -125,6 +127,7 @@ __device__ __forceinline__ void tile_store(const TileRegs<MN, KC> &r, float *__r
 
 template <int TN, bool A_KC, bool B_KC, int EPI>
 __global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const GemmParams p) {
+  if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int BN = 16 * TN;
   constexpr int kLdA = kBM + kPad, kLdB = BN + kPad;
   __shared__ __align__(16) float sA[2][kBK * kLdA];

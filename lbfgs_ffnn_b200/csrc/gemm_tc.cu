@@ -72,6 +72,8 @@ struct TcParams {
   __half *d16;
   const float *scale16;
   long long *dbg;        // B200_TC_TIMING=1: per-CTA {main loop, epilogue} clock64 durations
+  const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
+  int spec;
 };
 
 using namespace tcx;
@@ -109,6 +111,7 @@ template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8, int SHALL
 __global__ void __launch_bounds__(kTcThreads, ((SmemPlan<BN, X3, U8, SHALLOW>::kTotal + 1024) * 2 <= 227 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
   using Plan = SmemPlan<BN, X3, U8, SHALLOW>;
   constexpr bool kSplitA = Plan::kSplitA, kSplitB = Plan::kSplitB;
   // FWD / DX: the B operand is the weight matrix, the same for every CTA: its hi / lo parts are split ONCE per
@@ -663,6 +666,14 @@ int make_map_u8(CUtensorMap *tm, const uint8_t *ptr, unsigned long long dim0, un
   return B200_OK;
 }
 
+// speculation gate of the evaluation being launched (host-side, single-threaded per context like the rest of the library)
+const SpecState *g_tc_spec_st = nullptr;
+int g_tc_spec = 0;
+struct TcSpecScope {
+  explicit TcSpecScope(const b200_net *net) { g_tc_spec_st = net->spec_st; g_tc_spec = net->spec_flag; }
+  ~TcSpecScope() { g_tc_spec_st = nullptr; g_tc_spec = 0; }
+};
+
 bool tma_ok(const float *ptr, long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (ld % 4) == 0; }
 
 template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8, int SHALLOW = 0>
@@ -675,8 +686,9 @@ int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &t
     attr_set = true;
   }
   static long long *dbg = nullptr;
-  static const bool timing = std::getenv("B200_TC_TIMING") != nullptr;
+  const bool timing = env().tc_timing;
   TcParams pp = p;
+  pp.spec_st = g_tc_spec_st; pp.spec = g_tc_spec; // set by the tc_*_layer entry points from the network being evaluated
   if (timing) {
     if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 4 * 4096));
     B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 4 * 4096, st));
@@ -709,7 +721,8 @@ int launch_tc_prec(bool x3, const CUtensorMap &ta, const CUtensorMap &tb, const 
 }
 
 __global__ void __launch_bounds__(256) split_params_kernel(const float *__restrict__ w, unsigned long long n, float *__restrict__ hi,
-                                                         float *__restrict__ lo) {
+                                                         float *__restrict__ lo, const SpecState *spec_st, int spec) {
+  if (spec_skip(spec_st, spec)) return;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const float a = w[i];
@@ -719,10 +732,7 @@ __global__ void __launch_bounds__(256) split_params_kernel(const float *__restri
   }
 }
 
-int tc_mask() { // debugging aid: B200_TC_MASK bit0 = FWD, bit1 = DX, bit2 = DW (default all); read per call
-  const char *e = std::getenv("B200_TC_MASK");
-  return e ? std::atoi(e) : 7;
-}
+int tc_mask() { return env().tc_mask; } // debugging aid: B200_TC_MASK bit0 = FWD, bit1 = DX, bit2 = DW (default all)
 
 } // namespace
 
@@ -735,6 +745,7 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   *done = false;
   if (fused) *fused = false;
   if (!(tc_mask() & 1)) return B200_OK;
+  TcSpecScope spec_scope(net);
   const int K = net->dims[l], N = net->dims[l + 1];
   const float *W = params + net->offs[l];
   if (!tma_ok(in, K) || !tma_ok(W, N) || !tma_ok(net->act[l], N) || N % 32 != 0) return B200_OK;
@@ -798,6 +809,7 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
   const bool want16 = emit16 && *emit16 && net->delta16 && net->scale16;
   if (emit16) *emit16 = false;
   if (!(tc_mask() & 2)) return B200_OK;
+  TcSpecScope spec_scope(net);
   const int Kin = net->dims[l], Nout = net->dims[l + 1]; // contraction over out, result width in
   const float *W = params + net->offs[l];
   if (!tma_ok(net->delta[l], net->ldd[l]) || !tma_ok(W, Nout) || !tma_ok(net->delta[l - 1], Kin) || net->ldd[l - 1] != Kin ||
@@ -840,8 +852,7 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
 // N tile of the dW kernel: 256 columns (fewer re-reads of delta) except in 3xTF32, where a 256-wide stage is 72-96 KB and
 // only two fit — the TMA -> split/convert -> MMA chain then runs latency-bound; 128-wide stages pipeline three deep
 static int tc_dw_bn(const b200_net *net) {
-  const char *e = std::getenv("B200_DW_BN");
-  if (e) return std::atoi(e) == 128 ? 128 : 256;
+  if (env().dw_bn) return env().dw_bn == 128 ? 128 : 256;
   return net->prec == B200_PREC_TF32X3 ? 128 : 256;
 }
 
@@ -859,6 +870,7 @@ int tc_dw_plan(b200_net *net, int l, long batch, int *splits) {
 int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
   *done = false;
   if (!(tc_mask() & 4)) return B200_OK;
+  TcSpecScope spec_scope(net);
   const int Kin = net->dims[l], Nout = net->dims[l + 1];
   if (!tma_ok(net->delta[l], net->ldd[l]) || !tma_ok(in, Kin)) return B200_OK;
   const bool x3 = net->prec == B200_PREC_TF32X3;
@@ -906,7 +918,8 @@ static int tc_ensure_split(b200_net *net) {
     ++net->config_gen;
   }
   const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)4 * net->ctx->num_sms, (net->n + 255) / 256));
-  B200_LAUNCH(split_params_kernel, blocks, 256, 0, net->ctx->stream, params, (unsigned long long)net->n, net->w_hi, net->w_lo);
+  B200_LAUNCH(split_params_kernel, blocks, 256, 0, net->ctx->stream, params, (unsigned long long)net->n, net->w_hi, net->w_lo,
+              net->spec_st, net->spec_flag);
   return B200_OK;
 }
 

@@ -176,6 +176,8 @@ struct P2PReduceParams {
   SpecState *spec_st;
   int spec;
   double *host_out;
+  double *host_err;          // pinned-host flag: set when a peer's slot did not arrive within spin_limit polls
+  unsigned long long spin_limit;
 };
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p) {
   if (spec_skip(p.spec_st, p.spec)) return;
@@ -184,8 +186,20 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p
   unsigned *flags = p2p_flags(p.local, p.slot_bytes);
   const unsigned epoch = *reinterpret_cast<volatile unsigned *>(flags + p.world);
   if (threadIdx.x < p.world && (int)threadIdx.x != p.rank) {
+    // bounded wait: a dead or stalled peer must not hang every other rank inside a kernel. On a timeout the flag goes up in the
+    // host mailbox (the solvers turn it into B200_ERR_COMM at their next synchronisation) and the kernel runs to completion on
+    // whatever the slot holds.
     const volatile unsigned *f = flags + threadIdx.x;
-    while (*f < epoch + 1u) __nanosleep(64);
+    unsigned ns = 32;
+    unsigned long long polls = 0;
+    while (*f < epoch + 1u) {
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+      if (++polls > p.spin_limit) {
+        if (p.host_err) { *p.host_err = 1.0; __threadfence_system(); }
+        break;
+      }
+    }
     __threadfence_system();
   }
   __syncthreads();
@@ -305,7 +319,8 @@ constexpr int kSkinnyTile = 64;
 template <int FPL>
 __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int ldd, int in,
                                                         int out, long batch, int chunk, float *__restrict__ partial,
-                                                        unsigned long long pstride) {
+                                                        unsigned long long pstride, const SpecState *spec_st, int spec) {
+  if (spec_skip(spec_st, spec)) return;
   __shared__ __align__(16) float sd[kSkinnyTile][16];
   __shared__ float red[32 * FPL * 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -459,6 +474,7 @@ int net_ensure(b200_net *net, long batch) {
 void net_xq_clear(b200_net *net) {
   if (net->xq.valid) ++net->config_gen;
   net->xq.valid = false;
+  net->xq.user = false;
   net->xq.src = nullptr;
   net->xq.rows = 0;
 }
@@ -520,12 +536,12 @@ bool net_x16_view(b200_net *net, const float *x, long batch, X16View *v) {
   return true;
 }
 
-// every kernel of an evaluation of (x, batch) honours the speculation gate: fp16 layer-0 GEMMs + one-pass last layer
+// Every kernel of an evaluation honours the speculation gate (common.cuh), so any network can be evaluated speculatively; what
+// remains excluded is what enqueues something other than the library's own kernels behind the gate: the NCCL fall-back of the
+// gradient all-reduce (the solver checks that itself) and the debugging variants.
 bool net_spec_capable(b200_net *net, const float *x, long batch) {
-  X16View xv;
-  return net->nlayers() == 2 && net->prec != B200_PREC_FP32 && tail_applicable(net) && dw16_applicable(net) &&
-         net_x16_view(net, x, batch, &xv) && net->dims[1] % 32 == 0 && net->dims[0] % 16 == 0 && net->dims[0] <= 1024 &&
-         std::getenv("B200_FWD16") == nullptr;
+  (void)x; (void)batch;
+  return env().fwd16 < 0 && !env().tc_timing;
 }
 
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch) {
@@ -550,6 +566,7 @@ static int launch_fwd_layer(b200_net *net, int l, const float *params, const flo
   p.vecB = aligned16(W) && (N % 4 == 0);
   p.a_ones_row = -1;
   p.k_chunk = K;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
   p.bias = W + (size_t)K * N;
   p.act = net->acts[l];
   p.out = net->act[l]; p.ldo = N;
@@ -657,6 +674,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         p.vecB = aligned16(W) && (N % 4 == 0);
         p.a_ones_row = -1;
         p.k_chunk = N;
+        p.spec_st = net->spec_st; p.spec = net->spec_flag;
         p.act = net->acts[l - 1];
         p.out = net->delta[l - 1]; p.ldo = net->ldd[l - 1];
         p.aux = net->act[l - 1]; p.ld_aux = K;
@@ -679,8 +697,10 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         const int s_used = ceil_div(batch, chunk);
         float *part = net->partials + net->part_off[l];
         const unsigned long long ps = (unsigned long long)(K + 1) * N;
-        if (K + 1 <= 96) B200_LAUNCH(skinny_dw_kernel<3>, s_used, 256, 0, st, in, net->delta[l], net->ldd[l], K, N, batch, chunk, part, ps);
-        else B200_LAUNCH(skinny_dw_kernel<5>, s_used, 256, 0, st, in, net->delta[l], net->ldd[l], K, N, batch, chunk, part, ps);
+        if (K + 1 <= 96) B200_LAUNCH(skinny_dw_kernel<3>, s_used, 256, 0, st, in, net->delta[l], net->ldd[l], K, N, batch, chunk, part, ps,
+                                     net->spec_st, net->spec_flag);
+        else B200_LAUNCH(skinny_dw_kernel<5>, s_used, 256, 0, st, in, net->delta[l], net->ldd[l], K, N, batch, chunk, part, ps,
+                         net->spec_st, net->spec_flag);
         net->splits_used[l] = s_used;
         done = true;
       }
@@ -693,6 +713,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         p.vecB = aligned16(p.B) && (N % 4 == 0);
         p.a_ones_row = K;
         p.k_chunk = net->k_chunk[l];
+        p.spec_st = net->spec_st; p.spec = net->spec_flag;
         p.out = net->partials + net->part_off[l];
         B200_TRY((launch_gemm_simt<false, false, EPI_DW>(p, net->splits[l], st)));
         net->splits_used[l] = net->splits[l];
@@ -716,7 +737,9 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   fp.grad = grad_out;
   fp.fin_part = net->fin_part;
   const bool multi = ctx->world > 1 && !net->defer_reduce;
-  if (multi && !ctx->p2p.tried) B200_TRY(ctx_p2p_setup(ctx, net->n)); // collective; the first evaluation is never inside a graph capture
+  // collective (every rank evaluates the same networks in the same order); the first evaluation of a network is never inside a
+  // graph capture. A network larger than the buffers were made for re-makes them.
+  if (multi && (!ctx->p2p.tried || net->n > ctx->p2p.req_floats)) B200_TRY(ctx_p2p_setup(ctx, net->n));
   const bool p2p = multi && ctx->p2p.ready && net->n <= ctx->p2p.slot_floats && (reinterpret_cast<uintptr_t>(grad_out) & 15u) == 0;
   {
     ProfScope ps(ctx, "finalize");
@@ -736,7 +759,9 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   if (p2p) {
     ProfScope ps(ctx, "allreduce_p2p");
     P2PReduceParams rp{ctx->p2p.peers_dev, ctx->p2p.local, ctx->p2p.slot_bytes, ctx->p2p.slot_floats, net->n, ctx->rank, ctx->world,
-                       grad_out, net->fin_part, net->fin_done, out, net->spec_st, net->spec_flag, net->host_out};
+                       grad_out, net->fin_part, net->fin_done, out, net->spec_st, net->spec_flag, net->host_out,
+                       ctx->h_scalars + kHostErrSlot,
+                       (unsigned long long)(env().p2p_spin_limit > 0 ? env().p2p_spin_limit : 20000000L)}; // ~20 s at 1 us per poll
     const int blocks = std::max(1, std::min(net->fin_blocks, ceil_div((long)((net->n + 3) / 4), 256)));
     B200_LAUNCH(p2p_reduce_kernel, blocks, 256, 0, st, rp);
   } else if (multi) {
@@ -763,6 +788,8 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   for (int l = 0; l <= nlayers; ++l) B200_REQUIRE(dims[l] > 0, "layer dimensions must be positive");
   for (int l = 0; l < nlayers; ++l) B200_REQUIRE(acts[l] >= 0 && acts[l] <= 3, "unknown activation");
   b200_net *net = new b200_net;
+  static std::atomic<unsigned long long> next_uid{1};
+  net->uid = next_uid.fetch_add(1);
   net->ctx = ctx;
   net->dims.assign(dims, dims + nlayers + 1);
   net->acts.assign(acts, acts + nlayers);
@@ -796,6 +823,7 @@ int b200_net_destroy(b200_net *net) {
   if (!net) return B200_OK;
   cudaSetDevice(net->ctx->device);
   cudaStreamSynchronize(net->ctx->stream);
+  lbfgs_pool_forget_net(net->ctx, net->uid);
   free_batch_buffers(net);
   tc_release(net);
   tail_release(net);
@@ -878,6 +906,7 @@ int b200_net_quantize_input(b200_net *net, const float *x_dev, long batch, int *
   B200_REQUIRE(net && x_dev, "null argument");
   cudaSetDevice(net->ctx->device);
   B200_TRY(net_quantize_input(net, x_dev, batch, true));
+  if (net->xq.valid) net->xq.user = true;
   if (quantized) *quantized = net->xq.valid ? 1 : 0;
   return B200_OK;
 }

@@ -9,6 +9,7 @@ namespace b200 { struct SpecState; }
 
 struct b200_net {
   b200_ctx *ctx = nullptr;
+  unsigned long long uid = 0; // unique per created network (never reused, unlike the address): the solvers key captured graphs on it
   std::vector<int> dims; // nlayers + 1
   std::vector<int> acts; // nlayers
   std::vector<size_t> offs;
@@ -49,6 +50,8 @@ struct b200_net {
     int nblocks16 = 0;
     size_t cap = 0;
     bool valid = false;
+    bool user = false;   // built by the caller through b200_net_quantize_input (kept until b200_net_clear_input_cache); a copy the
+                         // solvers made themselves lives only as long as the minimisation that made it
     int *flag = nullptr; // device
   } xq;
 
@@ -100,6 +103,10 @@ int net_ensure(b200_net *net, long batch);
 // build (or reuse) the uint8 copy of x[batch][in]; no-op unless every element is exactly float(u)/255.0f
 int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh = false);
 void net_xq_clear(b200_net *net);
+// end of a minimisation: drop the copy unless the caller built it explicitly (the caller may refill x afterwards)
+inline void net_xq_release_solver(b200_net *net) { if (net && !net->xq.user) net_xq_clear(net); }
+// graphs captured by parked L-BFGS solvers bake this network's buffers in: dropped when the network is destroyed (solvers.cu)
+void lbfgs_pool_forget_net(b200_ctx *ctx, unsigned long long net_uid);
 // the uint8 rows matching x (a row-aligned sub-range of the quantised input), or nullptr
 const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
 struct X16View { const void *base; long rows_total, row0; int nblocks; };

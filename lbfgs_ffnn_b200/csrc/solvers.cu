@@ -88,12 +88,6 @@ void record(b200_history *h, int idx, double loss, double gnorm, float ms) {
   h->size = std::max(h->size, idx + 1);
 }
 
-long batch_global_of(b200_ctx *, long) {
-  // sample-sharded multi-GPU: the 1/B of the loss is the global batch; 0 lets net_eval resolve it
-  // (b200_net_set_global_batch, else shard batch x ranks)
-  return 0;
-}
-
 } // namespace
 
 } // namespace b200
@@ -149,9 +143,12 @@ struct b200_lbfgs {
   SpecState *spec_dev = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr}; // end of the graph of each parity
   bool ahead = false;                     // the graph of the CURRENT iteration is already in flight (launched speculatively)
-  const void *gkey[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // net, params, input, target, batch, net config generation
+  // net uid (not its address: a new network can be allocated where a destroyed one lived), params, input, target, batch, net config
+  // generation, generation of the peer-memory all-reduce buffers
+  unsigned long long gkey[7] = {0, 0, 0, 0, 0, 0, 0};
   bool graphs_ok = true;
   bool spec_capable = false; // the captured evaluation consists of gated kernels only
+  b200_net *last_net = nullptr; // network whose input cache this minimisation (re)built
   // minimisation state carried across runs
   bool started = false;
   int cur = 0, iter = 0, reset_next = 0;
@@ -177,6 +174,15 @@ int b200_lbfgs_create(b200_ctx *ctx, int n, const b200_lbfgs_opts *opts, b200_lb
       B200_CUDA(cudaMemsetAsync(c->ws, 0, c->ws_bytes, ctx->stream));
       B200_CUDA(cudaMemsetAsync(c->gridbar, 0, 2 * sizeof(unsigned), ctx->stream));
       B200_TRY(lbfgs_init_state(c->view, c->m, c->mod, ctx->stream));
+      // the device-side Armijo / convergence gate of the kept graphs reads c1 and tol from spec_dev: they must be THIS solve's
+      // (a stale pair lets host and device disagree on whether a speculative iteration ran)
+      {
+        SpecState hs{};
+        hs.c1 = (double)o.c1; hs.tol = (double)o.tol;
+        hs.alpha0 = &c->view.h->alpha0; hs.gdotp = &c->view.h->gdotp;
+        B200_CUDA(cudaMemcpyAsync(c->spec_dev, &hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream)); // hs is a stack object
+      }
       *out = c;
       return B200_OK;
     }
@@ -260,6 +266,8 @@ int b200_lbfgs_destroy(b200_lbfgs *s) {
   b200_ctx *ctx = s->ctx;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (s->last_net) net_xq_release_solver(s->last_net); // end of the minimisation: the caller may refill x
+  s->last_net = nullptr;
   if (ctx->lbfgs_pool.size() < 4) { // park it: the next solver of this shape skips cudaMalloc / cudaFree / graph instantiation
     ctx->lbfgs_pool_free = lbfgs_free;
     ctx->lbfgs_pool.push_back(s);
@@ -268,6 +276,21 @@ int b200_lbfgs_destroy(b200_lbfgs *s) {
   lbfgs_free(s);
   return B200_OK;
 }
+
+} // extern "C"
+namespace b200 {
+void lbfgs_pool_forget_net(b200_ctx *ctx, unsigned long long net_uid) {
+  for (void *p : ctx->lbfgs_pool) {
+    b200_lbfgs *c = (b200_lbfgs *)p;
+    if (c->gkey[0] == net_uid) {
+      lbfgs_drop_graphs(c);
+      memset(c->gkey, 0, sizeof(c->gkey));
+    }
+    if (c->last_net && c->last_net->uid == net_uid) c->last_net = nullptr;
+  }
+}
+} // namespace b200
+extern "C" {
 
 static int lbfgs_run_sharded(b200_lbfgs *s, b200_net *net, float *params, const float *input, const float *target, int batch,
                              int iters, b200_history *hist);
@@ -294,7 +317,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   double *dot_part = s->dot_part;
 
   HostMail *mail = (HostMail *)ctx->h_scalars;
-  Objective obj{ctx, net, fn, user, input, target, batch, batch_global_of(ctx, batch)};
+  Objective obj{ctx, net, fn, user, input, target, batch, 0 /* 1/B: net_eval resolves it (b200_net_set_global_batch, else shard batch x ranks) */};
   obj.d_part = dot_part;
   obj.n = N;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
@@ -302,7 +325,10 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   double cb_loss = 0.0;
   // uint8 copy of 8-bit pixel inputs (no-op unless x == u/255); re-derived at the start of every minimisation: the caller may
   // have refilled the same device buffer
-  if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch, !s->started));
+  if (net && net->prec != B200_PREC_FP32) {
+    B200_TRY(net_quantize_input(net, input, batch, !s->started));
+    s->last_net = net;
+  }
   if (!s->started) {
     // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
     B200_TRY(obj.eval_async(params, s->gbuf[0], mail, &cb_loss));
@@ -334,7 +360,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
       ApplyArgs aa{S, Y, N, ld, s->view, gg, p, params, x_prev, 1.0, 0.0f, nullptr};
       bool fused = false;
       if (ctx->prof.on) B200_TRY(launch_prof_spacer(st)); // the events below are then enqueued behind running work, not on an idle GPU
-      if (std::getenv("B200_NO_FUSED_DIRECTION") == nullptr) { // one launch: dots -> grid barrier -> solve (every CTA) -> apply
+      if (!env().no_fused_direction) { // one launch: dots -> grid barrier -> solve (every CTA) -> apply
         ProfScope ps(ctx, "lbfgs_direction");
         B200_TRY(launch_lbfgs_direction(ctx, da, sa, aa, mp, s->nblk, s->gridbar, st, &fused, sst, spec));
       }
@@ -363,7 +389,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
     // several GPUs: only when the gradient all-reduce runs over peer memory (plain kernels; no NCCL call inside the capture)
     const bool comm_ok = ctx->world == 1 || (ctx->p2p.ready && N <= ctx->p2p.slot_floats);
     const bool graphable = net && !wolfe && s->graphs_ok && mode == DOTS_FORM_PAIR && comm_ok && !ctx->prof.on &&
-                           max_ls > 0 && std::getenv("B200_NO_GRAPH") == nullptr && std::getenv("B200_TC_TIMING") == nullptr;
+                           max_ls > 0 && !env().no_graph && !env().tc_timing;
     // graph of the iteration with gradient parity `par`: capture on first use, then launch
     auto launch_graph = [&](int par, int reset, int spec) -> int {
       cudaGraphExec_t &ge = s->graph[par][reset][spec];
@@ -373,7 +399,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
         const bool gate = s->spec_capable;
         net->spec_st = gate ? s->spec_dev : nullptr;
         net->spec_flag = spec;
-        const bool zc = std::getenv("B200_NO_ZERO_COPY") == nullptr; // kernels write the pinned mailbox: no D2H copy nodes in the graph
+        const bool zc = !env().no_zero_copy; // kernels write the pinned mailbox: no D2H copy nodes in the graph
         net->host_out = zc ? &mail[par].loss : nullptr;
         bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
@@ -403,13 +429,15 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
       return B200_OK;
     };
     if (graphable) {
-      const void *key[6] = {net, params, input, target, (const void *)(intptr_t)batch, (const void *)(intptr_t)net->config_gen};
+      const unsigned long long key[7] = {net->uid, (unsigned long long)(uintptr_t)params, (unsigned long long)(uintptr_t)input,
+                                         (unsigned long long)(uintptr_t)target, (unsigned long long)batch,
+                                         (unsigned long long)net->config_gen, (unsigned long long)ctx->p2p.gen};
       if (memcmp(key, s->gkey, sizeof(key)) != 0) {
         lbfgs_drop_graphs(s);
         memcpy(s->gkey, key, sizeof(key));
         s->ahead = false;
         // the evaluation consists of gated kernels only (fp16 layer-0 GEMMs + one-pass last layer + fused direction)?
-        s->spec_capable = std::getenv("B200_NO_SPECULATION") == nullptr && std::getenv("B200_NO_FUSED_DIRECTION") == nullptr &&
+        s->spec_capable = !env().no_speculation && !env().no_fused_direction &&
                           mp <= kRowsPerLaunch && net_spec_capable(net, input, batch);
         if (s->spec_capable) {
           SpecState hs{};
@@ -458,6 +486,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
         if (!(ls == 0 && first_eval_issued)) B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
         if (ls == 0 && spec_in_flight) B200_CUDA(cudaEventSynchronize(s->ev[s->cur])); // only THIS iteration's graph
         else B200_CUDA(cudaStreamSynchronize(st));
+        if (ctx->world > 1) B200_TRY(ctx_check_device_error(ctx));
         if (ls == 0) { alpha = (double)(float)mr->hdr.alpha0; gdotp = mr->hdr.gdotp; }
         loss_new = net ? mr->loss : cb_loss;
         gnorm2_new = mr->gnorm2;
@@ -578,7 +607,10 @@ static int lbfgs_run_sharded(b200_lbfgs *s, b200_net *net, float *params, const 
   HostMail *mail = (HostMail *)ctx->h_scalars;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   long evals = 0;
-  if (net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch, true));
+  if (net->prec != B200_PREC_FP32) {
+    B200_TRY(net_quantize_input(net, input, batch, !s->started));
+    s->last_net = net;
+  }
   struct Defer { b200_net *n; ~Defer() { n->defer_reduce = false; } } defer{net};
   net->defer_reduce = true;
 
@@ -686,8 +718,7 @@ int b200_lbfgs_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *u
   b200_lbfgs *s = nullptr;
   B200_TRY(b200_lbfgs_create(ctx, n, opts, &s));
   const int status = b200_lbfgs_run(s, net, fn, user, params, input, target, batch, s->o.max_iters, hist);
-  b200_lbfgs_destroy(s);
-  if (net) net_xq_clear(net); // the caller may change x after the solve
+  b200_lbfgs_destroy(s); // (also drops the input cache this solve built: the caller may change x after the solve)
   return status;
 }
 
@@ -716,13 +747,13 @@ int b200_gd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user
   if (o.momentum > 0.0f) B200_CUDA(cudaMemsetAsync(vel, 0, sizeof(float) * N, st)); // gd.cuh:54-56
 
   HostMail *mail = (HostMail *)ctx->h_scalars;
-  Objective obj{ctx, net, fn, user, input, target, batch, batch_global_of(ctx, batch)};
+  Objective obj{ctx, net, fn, user, input, target, batch, 0 /* 1/B: net_eval resolves it (b200_net_set_global_batch, else shard batch x ranks) */};
   obj.d_part = dot_part;
   obj.n = N;
   Timer timer{ctx, hist != nullptr && o.record_timing != 0};
   double cb_loss = 0.0;
   if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, batch, true));
-  struct ClearQ { b200_net *n; ~ClearQ() { if (n) net_xq_clear(n); } } clear_q{net};
+  struct ClearQ { b200_net *n; ~ClearQ() { net_xq_release_solver(n); } } clear_q{net};
   B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
   B200_CUDA(cudaStreamSynchronize(st));
   double loss = net ? mail->loss : cb_loss;
@@ -735,6 +766,7 @@ int b200_gd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user
     else B200_TRY(launch_axpy(N, -o.lr, grad, params, st));                                             // :83-84
     B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
     B200_CUDA(cudaStreamSynchronize(st));
+    if (ctx->world > 1) B200_TRY(ctx_check_device_error(ctx));
     loss = net ? mail->loss : cb_loss;
     gnorm = std::sqrt(mail->gnorm2);
     B200_TRY(timer.stop());
@@ -788,7 +820,7 @@ int b200_sgd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *use
   long evals = 0;
   double cb_loss = 0.0;
   if (net && net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, total_samples, true));
-  struct ClearQ { b200_net *n; ~ClearQ() { if (n) net_xq_clear(n); } } clear_q{net};
+  struct ClearQ { b200_net *n; ~ClearQ() { net_xq_release_solver(n); } } clear_q{net};
   float current_lr = o.lr;
   const int num_batches = (total_samples + o.batch_size - 1) / o.batch_size;
   float prev_epoch_loss_avg = std::numeric_limits<float>::infinity();

@@ -613,8 +613,7 @@ template <int FPL> int launch_tail(b200_ctx *ctx, const TailParams &p, int grid,
 } // namespace
 
 bool tail_applicable(const b200_net *net) {
-  const char *env = std::getenv("B200_TAIL"); // debugging aid, read per call: 0 = per-layer kernels
-  if (env && std::atoi(env) == 0) return false;
+  if (env().tail == 0) return false; // debugging aid: 0 = per-layer kernels
   const int L = net->nlayers();
   if (L < 2) return false;
   const int in = net->dims[L - 1], out = net->dims[L];
@@ -663,8 +662,7 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   p.chunk = ceil_div(ceil_div(batch, grid), 16) * 16;
   grid = ceil_div(batch, p.chunk);
   // forward: sample-per-lane kernel on one CTA per SM (B200_TAIL_FWD=1: the feature-per-lane kernel on the backward's grid)
-  const char *fenv = std::getenv("B200_TAIL_FWD");
-  const bool fwd2 = !(fenv && std::atoi(fenv) == 1) && (reinterpret_cast<uintptr_t>(p.A) & 15u) == 0 && (p.ldd % 4) == 0 &&
+  const bool fwd2 = env().tail_fwd != 1 && (reinterpret_cast<uintptr_t>(p.A) & 15u) == 0 && (p.ldd % 4) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.delta_last) & 15u) == 0 && (out != 10 || (reinterpret_cast<uintptr_t>(p.out_last) & 7u) == 0);
   // (never more forward CTAs than backward partials: each forward CTA leaves its bias-gradient row in the partial of its index)
   const int grid_fwd = fwd2 ? std::max(1, std::min(std::min(std::min(net->ctx->num_sms, net->loss_part_cap), grid), (int)ceil_div(batch, 32))) : 0;

@@ -69,6 +69,8 @@ def _declare(L):
     L.oracle_gd_mlp.restype = C.c_int
     L.oracle_gd_mlp.argtypes = [C.c_void_p, dp, dp, dp, C.c_long, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int,
                                 dp, dp]
+    L.oracle_sgd_mlp_cpu_policy.restype = C.c_int
+    L.oracle_sgd_mlp_cpu_policy.argtypes = [C.c_void_p, dp, dp, dp, C.c_long, C.c_int, C.c_double, C.c_int, C.c_uint, dp, dp]
     L.oracle_sgd_mlp_cuda_policy.restype = C.c_int
     L.oracle_sgd_mlp_cuda_policy.argtypes = [C.c_void_p, dp, dp, dp, C.c_long, C.c_int, C.c_double, C.c_double,
                                              C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, dp, dp]
@@ -173,6 +175,16 @@ class OracleNet:
         it = lib().oracle_sgd_mlp_cuda_policy(self.h, _p(x, C.c_double), _p(X, C.c_double), _p(T, C.c_double), B,
                                               batch_size, lr, momentum, decay_rate, decay_step, max_iters, tol,
                                               1 if record else 0, _p(hl, C.c_double), _p(hg, C.c_double))
+        return dict(params=x, iters=it, loss=hl[:it], gnorm=hg[:it])
+
+    def sgd_cpu_policy(self, params, X, T, batch_size, lr, max_iters=10, seed=123):
+        """reference CPU SGD (src/minimizer/s_gd.hpp:63-170): random mini-batches, no momentum"""
+        x = _f64(params).copy()
+        X, T = _f64(X), _f64(T)
+        N = X.size // self.dims[0]
+        hl, hg = np.zeros(max_iters), np.zeros(max_iters)
+        it = lib().oracle_sgd_mlp_cpu_policy(self.h, _p(x, C.c_double), _p(X, C.c_double), _p(T, C.c_double), N, batch_size,
+                                             lr, max_iters, seed, _p(hl, C.c_double), _p(hg, C.c_double))
         return dict(params=x, iters=it, loss=hl[:it], gnorm=hg[:it])
 
     def slbfgs(self, params, X, T, batch_size, M=10, L=10, b_H=0, step=0.02, max_iters=5, tol=1e-4, seed=123):

@@ -9,16 +9,17 @@
 // initial parameters, std::normal_distribution<double/float> — the very objects the
 // reference uses (src/minimizer/s_lbfgs.hpp:143-161, src/network.hpp:52-69).
 //
-// The reference's CPU path cannot be compiled here: every header includes Eigen
-// (src/common.hpp:8), Eigen 3.4.0 is an un-vendored system dependency
-// (enviroment/Dockerfile:14) and is absent from this image. Eigen is only used for
-// dense double GEMM / dot / norm, so the restatement is exact up to summation order.
-//
-// Parity pinning: the L-BFGS restatement is pinned on the reference's own known-answer
-// tests (tests/main.cpp Rosenbrock/Ackley/Rastrigin, see tests/test_oracle_kat.py).
-// The MLP objective has NO golden vector in the reference: it is pinned
-// by an independent numpy float64 restatement and central finite differences instead
-// => "parity unpinned by the reference for the MLP objective".
+// Parity pinning — PINNED to outputs of the reference's own code, two ways:
+//  * CPU: the reference's CPU sources (src/unified_launcher.hpp and everything it includes) compile UNMODIFIED against an
+//    Eigen-API stand-in (oracle/ref_cpu/; Eigen 3.4.0 is an un-vendored system dependency, enviroment/Dockerfile:14, absent from
+//    this image; it is only used for dense double GEMM / dot / norm) into oracle/_ref/libref_cpu.so. Its outputs on seeded
+//    inputs are committed as tests/golden/golden_ref_cpu.json (tests/golden/make_golden_ref_cpu.py) and
+//    tests/test_oracle_vs_reference_cpu.py holds this file to them: objective 1e-13, weak-Wolfe L-BFGS trajectory, GD, SGD
+//    (random mini-batches) and S-LBFGS parameters after every epoch 1e-8 .. 1e-6 (both sides fp64; summation order differs).
+//  * CUDA: the reference's CUDA backend compiles as it is (oracle/ref_cuda/ -> oracle/_ref/libref_cuda.so); its outputs on a
+//    B200 are tests/golden/golden_ref_cuda.json, checked by tests/test_oracle.py and, live, by tests/test_gpu_vs_reference_cuda.py.
+// Further: the reference's analytic known-answer tests (tests/main.cpp Rosenbrock / Ackley / Rastrigin), an independent numpy
+// fp64 restatement and central finite differences (tests/test_oracle.py).
 //
 // Layout contract (identical to the reference, src/layer.hpp:100-114,
 // src/cuda/layer.cuh:48-58): matrices are column-major. X is in x B (sample b is the
@@ -734,6 +735,41 @@ int slbfgs_solve(Vec &weights, const BatchF &f, const BatchG &batch_g, int m, in
 }
 
 // ----------------------------------------------------------------------------------
+// CPU SGD: StochasticGradientDescent::stochastic_solve (src/minimizer/s_gd.hpp:63-145) with the closures of
+// UnifiedSGD_CPU::optimize (src/unified_optimization.hpp:219-300): m = N / b random mini-batches per epoch drawn with the
+// partial Fisher-Yates sampler (s_gd.hpp:148-170, the same draws as the S-LBFGS one) from one mt19937(kDefaultSeed);
+// w -= step * mean-gradient; no momentum, no decay, no tolerance test; per epoch the recorder takes the full loss (the mean
+// of the per-sample 0.5 ||out - y||^2, :116-120) and the norm of the full gradient (:126-131).
+// ----------------------------------------------------------------------------------
+int cpu_sgd_solve(Vec &w, const BatchF &full_loss, const BatchG &batch_g, int m, int b, double step, int N, int max_iters,
+                  unsigned seed, History *hist) {
+  int iters = 0;
+  std::mt19937 rng(seed);
+  const size_t dim = w.size();
+  Idx full(N);
+  std::iota(full.begin(), full.end(), 0);
+  auto t0 = std::chrono::steady_clock::now();
+  while (iters < max_iters) {
+    for (int t = 0; t < m; ++t) {
+      Idx mb = sample_minibatch_indices(N, b, rng);
+      Vec g(dim, 0.0);
+      batch_g(w, mb, g);
+      for (size_t i = 0; i < dim; ++i) w[i] = w[i] - step * g[i];
+    }
+    if (hist) {
+      const double loss = full_loss(w, full);
+      Vec fg(dim, 0.0);
+      batch_g(w, full, fg);
+      hist->loss.push_back(loss);
+      hist->gnorm.push_back(norm(fg));
+      hist->ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+    ++iters;
+  }
+  return iters;
+}
+
+// ----------------------------------------------------------------------------------
 // analytic test functions of tests/main.cpp (the reference's only known-answer tests)
 // ----------------------------------------------------------------------------------
 Objective make_rosenbrock() { // tests/main.cpp:73-108
@@ -1065,6 +1101,27 @@ int oracle_slbfgs_mlp(void *h, double *params, const double *X, const double *T,
   if (trace_idx) for (long i = 0; i < std::min<long>(trace_cap, (long)tr.batch_idx_flat.size()); ++i) trace_idx[i] = tr.batch_idx_flat[i];
   if (anchor_picks) for (size_t i = 0; i < tr.anchor_pick.size() && (int)i < max_iters; ++i) anchor_picks[i] = tr.anchor_pick[i];
   if (pairs_after) for (size_t i = 0; i < tr.pairs_after_epoch.size() && (int)i < max_iters; ++i) pairs_after[i] = tr.pairs_after_epoch[i];
+  return iters;
+}
+
+// CPU SGD (UnifiedSGD_CPU::optimize + StochasticGradientDescent::stochastic_solve): random mini-batches, plain objective
+// (no L2 term: the closure at unified_optimization.hpp:245-269 divides by the batch size and adds nothing).
+int oracle_sgd_mlp_cpu_policy(void *h, double *params, const double *X, const double *T, long N, int batch_size, double step,
+                              int max_iters, unsigned seed, double *hist_loss, double *hist_gnorm) {
+  Net &net = *(Net *)h;
+  int m = (int)(N / batch_size); // unified_optimization.hpp:232-233
+  if (m == 0) m = 1;
+  Vec w(params, params + net.nparams);
+  auto to_u32 = [](const Idx &idx) { std::vector<uint32_t> v(idx.size()); for (size_t i = 0; i < idx.size(); ++i) v[i] = (uint32_t)idx[i]; return v; };
+  BatchG bg = [&](const Vec &wv, const Idx &idx, Vec &g) {
+    auto v = to_u32(idx);
+    oracle_slbfgs_batch_grad(h, wv.data(), X, T, N, ((long)idx.size() == N) ? nullptr : v.data(), (long)idx.size(), 0.0, g.data());
+  };
+  BatchF fl = [&](const Vec &wv, const Idx &) { return net_loss(net, wv.data(), X, T, N); };
+  History hist;
+  const int iters = cpu_sgd_solve(w, fl, bg, m, batch_size, step, (int)N, max_iters, seed, &hist);
+  std::copy(w.begin(), w.end(), params);
+  copy_hist(hist, max_iters, hist_loss, hist_gnorm, nullptr);
   return iters;
 }
 

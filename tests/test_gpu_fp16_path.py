@@ -32,6 +32,7 @@ def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True):
             os.environ.pop(k, None)
         for k, v in (env or {}).items():
             os.environ[k] = v
+        P.api.reload_env()
         B = X.shape[0]
         net = make_gpu_net(handle, dims, acts, w, precision=prec)
         dx, dt = upload(X), upload(T)
@@ -48,6 +49,7 @@ def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+        P.api.reload_env()
 
 
 def problem8(oracle, dims, acts, batch, seed=123):
@@ -195,6 +197,7 @@ def test_fused_direction_kernel_matches_the_three_kernel_path(handle, oracle, m)
             os.environ.pop("B200_NO_FUSED_DIRECTION", None)
         else:
             os.environ["B200_NO_FUSED_DIRECTION"] = "1"
+        P.api.reload_env()
         try:
             net = make_gpu_net(handle, dims, acts, w, precision="fp32")
             s = P.CudaLBFGS(handle)
@@ -204,6 +207,7 @@ def test_fused_direction_kernel_matches_the_three_kernel_path(handle, oracle, m)
             out[fused] = (rec.copy_to_host()[0], net.get_params())
         finally:
             os.environ.pop("B200_NO_FUSED_DIRECTION", None)
+            P.api.reload_env()
     # identical arithmetic in the same order: bit-identical trajectories
     assert np.array_equal(out[True][0], out[False][0])
     assert np.array_equal(out[True][1], out[False][1])

@@ -27,6 +27,7 @@ def _check(handle, oracle, dims, acts, batch, prec, mask=None):
         os.environ.pop("B200_TC_MASK", None)
     else:
         os.environ["B200_TC_MASK"] = str(mask)
+    P.api.reload_env()
     try:
         onet, w, X, T = make_problem(oracle, dims, acts, batch)
         loss_o, g_o = onet.loss_grad(w, X, T)
@@ -39,6 +40,7 @@ def _check(handle, oracle, dims, acts, batch, prec, mask=None):
         return abs(loss - loss_o) / abs(loss_o), rel_l2(g, g_o), rel_l2(out, onet.forward(w, X))
     finally:
         os.environ.pop("B200_TC_MASK", None)
+        P.api.reload_env()
 
 
 @pytest.mark.parametrize("mask,name", [(1, "fwd+fused-last"), (9, "fwd"), (2, "dx"), (4, "dw"), (15, "all-unfused"), (7, "all")])

@@ -19,7 +19,7 @@ for dims, acts in (([784, 128, 10], ["relu", "linear"]), ([784, 128, 64, 10], ["
         for prec in ("tf32x3", "tf32", "fp32"):
             row = {"net": "-".join(map(str, dims)), "B": B, "prec": prec}
             for mode in ("1", "0"):
-                os.environ["B200_DW16"] = mode
+                os.environ["B200_DW16"] = mode; P.api.reload_env()
                 net = make_gpu_net(h, dims, acts, w, precision=prec)
                 assert net.quantize_input(dx, B)
                 loss = net.compute_loss_and_grad(dx, dt, B)
@@ -33,7 +33,7 @@ dx, dt = upload(X), upload(T)
 for dims, acts in (([784, 128, 10], ["relu", "linear"]), ([784, 128, 64, 10], ["relu", "relu", "linear"])):
     for prec in ("tf32x3", "tf32"):
         for mode in ("111", "110", "100"):
-            os.environ["B200_FWD16"] = mode[0]; os.environ["B200_TAIL"] = mode[1]; os.environ["B200_DW16"] = mode[2]
+            os.environ["B200_FWD16"] = mode[0]; os.environ["B200_TAIL"] = mode[1]; os.environ["B200_DW16"] = mode[2]; P.api.reload_env()
             net = make_gpu_net(h, dims, acts, None, precision=prec)
             net.quantize_input(dx, B)
             for _ in range(3): net.compute_loss_and_grad(dx, dt, B)

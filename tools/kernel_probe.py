@@ -14,6 +14,7 @@ for dims, acts in (([784,128,10],["relu","linear"]), ([784,128,64,10],["relu","r
         for mask in ((None,) if prec == "fp32" else (None, "15")):
             if mask: os.environ["B200_TC_MASK"] = mask
             else: os.environ.pop("B200_TC_MASK", None)
+            P.api.reload_env()
             net = P.CudaNetwork(h)
             for i, a in enumerate(acts): net.addLayer(dims[i], dims[i+1], a)
             net.bindParams(123); net.set_precision(prec)

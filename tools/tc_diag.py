@@ -15,7 +15,7 @@ for dims, acts in [([784,128,10],["relu","linear"]), ([784,128,64,10],["relu","r
   dx,dt = upload(X),upload(T)
   for prec in ["fp32","tf32x3","tf32"]:
     for mask in ([7] if prec=="fp32" else [1,9,2,4,15,7]):
-      os.environ["B200_TC_MASK"]=str(mask)
+      os.environ["B200_TC_MASK"]=str(mask); P.api.reload_env()
       net = make_gpu_net(h,dims,acts,w,precision=prec)
       l = net.compute_loss_and_grad(dx,dt,B); g = net.get_grads()
       print(dims, prec, mask, 'loss rel %.2e'%(abs(l-lo)/abs(lo)), 'grad rel %.2e'%rel_l2(g,go), flush=True)
