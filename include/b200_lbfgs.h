@@ -113,6 +113,10 @@ int b200_net_loss_grad_async(b200_net *net, const float *params_dev, const float
 /* copy_output_to_host (network.cuh:121-126) */
 int b200_net_copy_output_to_host(b200_net *net, float *host, size_t n);
 int b200_net_last_batch(b200_net *net);
+/* the activations of layer `layer` (0 = first hidden layer ... nlayers-1 = the output, i.e. copy_output_to_host) left by the last
+ * forward / loss_grad call: n <= out_layer * last_batch floats, sample-major [batch][out]. The reference keeps them in
+ * CudaNetwork::activations_ (network.cuh:133-147) without an accessor; the parity tests read the hidden layers' signs. */
+int b200_net_copy_activation_to_host(b200_net *net, int layer, float *host, size_t n);
 /* UnifiedLauncher<CudaBackend>::evaluate (src/unified_launcher.hpp:154-199) on the device:
  * forward + MSE (mean over batch*out) + arg-max accuracy (percent). t_dev is out x batch. */
 int b200_net_evaluate(b200_net *net, const float *x_dev, const float *t_dev, long batch, double *mse, double *accuracy);
@@ -192,9 +196,16 @@ typedef struct b200_sgd_opts { /* src/cuda/sgd.cuh:156-163 */
   int input_dim;               /* must be set (sgd.cuh:61-65) */
   int output_dim;
   int record_timing;
+  int sampling;                /* 0 (default): sequential slices, the CUDA backend's CudaSGD (sgd.cuh:100-109).
+                                * 1: the CPU backend's StochasticGradientDescent (src/minimizer/s_gd.hpp:63-170 with the closures of
+                                *    UnifiedSGD_CPU, src/unified_optimization.hpp:219-300): N / batch_size random mini-batches per
+                                *    epoch drawn by the partial Fisher-Yates sampler from one mt19937(seed), w -= lr * mean gradient,
+                                *    no decay and no stopping test; momentum is honoured if > 0 (the CPU class has none). */
+  unsigned seed;               /* sampling == 1: 123 (kDefaultSeed) */
 } b200_sgd_opts;
 void b200_sgd_default_opts(b200_sgd_opts *o);
-/* CudaSGD::solve (src/cuda/sgd.cuh:50-153): sequential unshuffled mini-batches by pointer offset. */
+/* CudaSGD::solve (src/cuda/sgd.cuh:50-153): sequential unshuffled mini-batches by pointer offset; or, with
+ * opts->sampling == 1, the reference CPU backend's random-mini-batch SGD on the GPU (network objective only). */
 int b200_sgd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user, int n, float *params,
                    const float *input, const float *target, int total_samples, const b200_sgd_opts *opts,
                    b200_history *hist);

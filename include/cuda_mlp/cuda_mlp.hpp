@@ -185,7 +185,9 @@ public:
   void setTolerance(CudaScalar tol) { tol_ = tol; }
   int iterations() const noexcept { return last_iterations_; }
   long evaluations() const noexcept { return last_evaluations_; }
-  void setLineSearchParams(int max_iters, CudaScalar c1, CudaScalar rho) { max_line_iters_ = max_iters; c1_ = c1; rho_ = rho; }
+  void setLineSearchParams(int max_iters, CudaScalar c1, CudaScalar rho) { // minimizer_base.cuh:38-45: at least one trial
+    max_line_iters_ = max_iters < 1 ? 1 : max_iters; c1_ = c1; rho_ = rho;
+  }
   void setRecorder(::IterationRecorder<CudaBackend> *recorder) { recorder_ = recorder; }
   /// Fast path: the library's own network objective evaluated at `params` (no callback, loss stays on the
   /// device between kernels). run_cuda_solver_once's lambda (src/unified_optimization.hpp:483-491) is exactly this.
@@ -267,10 +269,14 @@ public:
   void setBatchSize(int b) { batch_size_ = b; }
   void setLearningRateDecay(CudaScalar rate, int step) { decay_rate_ = rate; decay_step_ = step; }
   void setDimensions(int in, int out) { input_dim_ = in; output_dim_ = out; }
+  /// Sequential (default) = the CUDA backend's slices; Random = the CPU backend's mini-batches (src/minimizer/s_gd.hpp:63-170) on the GPU
+  enum class Sampling { Sequential = 0, Random = 1 };
+  void setSampling(Sampling s, unsigned seed = 123) { sampling_ = s; seed_ = seed; }
   void solve(int n, CudaScalar *params, const CudaScalar *input, const CudaScalar *target, int total_samples,
              const LossGradFun &loss_grad) override {
     b200_sgd_opts o;
     b200_sgd_default_opts(&o);
+    o.sampling = (int)sampling_; o.seed = seed_;
     o.max_iters = max_iters_; o.tol = tol_; o.lr = lr_; o.momentum = momentum_; o.decay_rate = decay_rate_;
     o.decay_step = decay_step_; o.batch_size = batch_size_; o.input_dim = input_dim_; o.output_dim = output_dim_;
     b200_history h{};
@@ -284,6 +290,8 @@ public:
 private:
   CudaScalar lr_ = 0.01f, momentum_ = 0.9f, decay_rate_ = 1.0f;
   int decay_step_ = 0, batch_size_ = 64, input_dim_ = 0, output_dim_ = 0;
+  Sampling sampling_ = Sampling::Sequential;
+  unsigned seed_ = 123;
 };
 
 /// S-LBFGS on the GPU: SLBFGS::stochastic_solve (src/minimizer/s_lbfgs.hpp:165-290) with the objective of

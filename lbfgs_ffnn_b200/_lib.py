@@ -37,7 +37,7 @@ class GdOpts(C.Structure):
 class SgdOpts(C.Structure):
     _fields_ = [("max_iters", C.c_int), ("tol", C.c_float), ("lr", C.c_float), ("momentum", C.c_float),
                 ("decay_rate", C.c_float), ("decay_step", C.c_int), ("batch_size", C.c_int), ("input_dim", C.c_int),
-                ("output_dim", C.c_int), ("record_timing", C.c_int)]
+                ("output_dim", C.c_int), ("record_timing", C.c_int), ("sampling", C.c_int), ("seed", C.c_uint)]
 
 
 class SlbfgsOpts(C.Structure):
@@ -92,6 +92,7 @@ SYMBOLS = {
     "b200_net_loss_grad_async": (_i, [_vp, _vp, _vp, _vp, _l, _vp, _vp]),
     "b200_net_copy_output_to_host": (_i, [_vp, _vp, _sz]),
     "b200_net_last_batch": (_i, [_vp]),
+    "b200_net_copy_activation_to_host": (_i, [_vp, _i, _vp, _sz]),
     "b200_net_evaluate": (_i, [_vp, _vp, _vp, _l, _pd, _pd]),
     "b200_lbfgs_default_opts": (None, [C.POINTER(LbfgsOpts)]),
     "b200_lbfgs_solve": (_i, [_vp, _vp, LOSS_GRAD_FN, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(LbfgsOpts),

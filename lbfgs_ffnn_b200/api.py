@@ -239,6 +239,13 @@ class CudaNetwork:
     def last_batch(self):
         return lib().b200_net_last_batch(self._h)
 
+    def copy_activation_to_host(self, layer):
+        """activations of `layer` (0 = first hidden layer) left by the last forward / loss_grad call, shape (batch, out)"""
+        b, out = self.last_batch(), self.dims[layer + 1]
+        a = np.empty(b * out, dtype=np.float32)
+        check(lib().b200_net_copy_activation_to_host(self._h, int(layer), a.ctypes.data_as(C.c_void_p), a.size))
+        return a.reshape(b, out)
+
     def evaluate(self, input_dev, target_dev, batch):
         mse, acc = C.c_double(), C.c_double()
         check(lib().b200_net_evaluate(self._h, C.c_void_p(_ptr(input_dev)), C.c_void_p(_ptr(target_dev)), int(batch),
@@ -350,7 +357,7 @@ class CudaMinimizerBase:
         self.tol_ = float(tol)
 
     def setLineSearchParams(self, max_iters, c1, rho):
-        self.max_line_iters_, self.c1_, self.rho_ = int(max_iters), float(c1), float(rho)
+        self.max_line_iters_, self.c1_, self.rho_ = max(1, int(max_iters)), float(c1), float(rho)  # minimizer_base.cuh:38-45
 
     def setRecorder(self, recorder):
         self.recorder_ = recorder
@@ -469,6 +476,7 @@ class CudaSGD(CudaMinimizerBase):
         super().__init__(handle)
         self.lr_, self.momentum_, self.decay_rate_, self.decay_step_ = 0.01, 0.9, 1.0, 0  # sgd.cuh:156-163
         self.batch_size_, self.input_dim_, self.output_dim_ = 64, 0, 0
+        self.sampling_, self.seed_ = 0, 123
 
     def setLearningRate(self, lr):
         self.lr_ = float(lr)
@@ -485,12 +493,17 @@ class CudaSGD(CudaMinimizerBase):
     def setDimensions(self, in_dim, out_dim):
         self.input_dim_, self.output_dim_ = int(in_dim), int(out_dim)
 
+    def setSampling(self, mode, seed=123):
+        """'sequential' (the CUDA backend's CudaSGD) or 'random' (the CPU backend's s_gd.hpp mini-batches, on the GPU)"""
+        self.sampling_, self.seed_ = {"sequential": 0, "random": 1}[mode], int(seed)
+
     def solve(self, n, params, input_dev, target_dev, total_samples, loss_grad):
         o = _lib.SgdOpts()
         lib().b200_sgd_default_opts(C.byref(o))
         o.max_iters, o.tol, o.lr, o.momentum = self.max_iters_, self.tol_, self.lr_, self.momentum_
         o.decay_rate, o.decay_step, o.batch_size = self.decay_rate_, self.decay_step_, self.batch_size_
         o.input_dim, o.output_dim = self.input_dim_, self.output_dim_
+        o.sampling, o.seed = self.sampling_, self.seed_
         cb, net_h = self._callback(loss_grad)
         h = self._history()
         check(lib().b200_sgd_solve(self.handle._h, net_h, cb, None, int(n), C.c_void_p(_ptr(params) or 0),

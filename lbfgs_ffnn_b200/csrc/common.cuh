@@ -5,6 +5,7 @@
 #include "../../include/b200_lbfgs.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only (NVTX 3): ranges cost nothing unless a tool is attached
 
 #include <atomic>
 #include <cstdarg>
@@ -139,11 +140,18 @@ struct b200_ctx {
 
 namespace b200 {
 
-// brackets the launches issued during its lifetime with two events when profiling is enabled
+// brackets the launches issued during its lifetime with two events when profiling is enabled, and with an NVTX range
+// (B200_NVTX=1) so that a timeline tool shows direction / evaluation / collective phases by name
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char *name) : on(env().nvtx) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 struct ProfScope {
   b200_ctx *ctx;
   cudaEvent_t b = nullptr;
-  ProfScope(b200_ctx *c, const char *name) : ctx(c) {
+  NvtxRange nvtx;
+  ProfScope(b200_ctx *c, const char *name) : ctx(c), nvtx(name) {
     if (!c->prof.on) return;
     cudaEvent_t a = c->prof.get();
     b = c->prof.get();

@@ -27,6 +27,7 @@ int fwd16_prepare(b200_net *net, const float *params);
 void fwd16_release(b200_net *net);
 // fp16 dW of layer 0 from the uint8 input copy and the fp16 {hi | lo} delta of tail_layer (gemm_dw16.cu)
 bool dw16_applicable(const b200_net *net);
+int dw16_plan(const b200_net *net, long batch, int *splits); // K blocks per split; *splits = slices of the batch
 int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done);
 void tc_release(b200_net *net);
 

@@ -458,7 +458,12 @@ int net_ensure(b200_net *net, long batch) {
       int s_tc = 1;
       tc_dw_plan(net, l, batch, &s_tc); // room for whichever path runs
       net->skinny_splits[l] = 2 * net->ctx->num_sms;
-      total += (size_t)std::max(std::max(s, s_tc), net->skinny_splits[l]) * M * N;
+      int s_16 = 1;
+      if (l == 0) dw16_plan(net, batch, &s_16);
+      // (the per-CTA partials of the skinny / one-pass last-layer kernels exist only for narrow layers: reserving them for a
+      // 4096-wide layer would be 2 * SMs copies of a 67 MB matrix)
+      const int s_skinny = (N <= 16) ? net->skinny_splits[l] : 1;
+      total += (size_t)std::max(std::max(std::max(s, s_tc), s_16), s_skinny) * M * N;
     }
     if (total > net->partials_cap) {
       if (net->partials) cudaFree(net->partials);
@@ -607,6 +612,7 @@ int net_forward(b200_net *net, const float *params, const float *x, long batch) 
 int net_eval(b200_net *net, const float *params, const float *x, const float *t, long batch, long batch_global,
              float *grad_out, EvalOut *out) {
   B200_REQUIRE(net && params && x && t && grad_out && out, "null argument");
+  NvtxRange nvtx_eval("evaluation");
   B200_TRY(net_ensure(net, batch));
   b200_ctx *ctx = net->ctx;
   cudaStream_t st = ctx->stream;
@@ -955,6 +961,16 @@ int b200_net_copy_output_to_host(b200_net *net, float *host, size_t n) {
 }
 
 int b200_net_last_batch(b200_net *net) { return net ? (int)net->last_batch : 0; }
+
+int b200_net_copy_activation_to_host(b200_net *net, int layer, float *host, size_t n) {
+  B200_REQUIRE(net && host, "null argument");
+  B200_REQUIRE(layer >= 0 && layer < net->nlayers(), "no such layer");
+  B200_REQUIRE(net->act[layer] && net->last_batch > 0, "no forward pass has run");
+  B200_REQUIRE(n <= (size_t)net->dims[layer + 1] * net->last_batch, "more elements requested than the last batch produced");
+  B200_CUDA(cudaMemcpyAsync(host, net->act[layer], sizeof(float) * n, cudaMemcpyDeviceToHost, net->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  return B200_OK;
+}
 
 int b200_net_evaluate(b200_net *net, const float *x_dev, const float *t_dev, long batch, double *mse, double *accuracy) {
   B200_REQUIRE(net && net->params && x_dev && t_dev, "null argument / params not bound");

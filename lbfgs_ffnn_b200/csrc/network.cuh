@@ -168,5 +168,9 @@ __device__ __forceinline__ void chain_cw_block(const ChainW &c, int cta, float *
 }
 #endif
 void tail_release(b200_net *net);
+// the reference CPU backend's random-mini-batch SGD (src/minimizer/s_gd.hpp:63-170) on the GPU (slbfgs.cu: shares the sampler
+// and the row gather of S-LBFGS)
+int sgd_random_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const float *input, const float *target, int total_samples,
+                     const b200_sgd_opts &o, b200_history *hist);
 
 } // namespace b200

@@ -109,6 +109,81 @@ inline int vblocks(size_t n) { return (int)std::max<size_t>(1, std::min<size_t>(
 
 } // namespace
 
+// StochasticGradientDescent::stochastic_solve (src/minimizer/s_gd.hpp:63-145) with the objective closures of UnifiedSGD_CPU
+// (src/unified_optimization.hpp:219-300): per epoch m = N / b mini-batches of b random indices (the sampler above: the same
+// draws as s_gd.hpp:148-170) from ONE mt19937(seed); w -= step * (mean gradient of the batch). No L2 term, no decay, no stop
+// test. All index lists of an epoch are drawn up front and uploaded once: an epoch runs without a host synchronisation.
+// Recorder (:122-139): full-batch loss and full-gradient norm after every epoch.
+int sgd_random_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const float *input, const float *target, int total_samples,
+                     const b200_sgd_opts &o, b200_history *hist) {
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long launches0 = b200_launch_count();
+  const int N = total_samples, b = std::min(o.batch_size, N);
+  int m = N / o.batch_size; // unified_optimization.hpp:232-233
+  if (m == 0) m = 1;
+  const int in_dim = net->dims.front(), out_dim = net->dims.back();
+  const size_t Nn = (size_t)n;
+  const size_t vec = (sizeof(float) * Nn + 255) & ~size_t(255);
+  const size_t xb_bytes = (sizeof(float) * (size_t)b * in_dim + 255) & ~size_t(255);
+  const size_t tb_bytes = (sizeof(float) * (size_t)b * out_dim + 255) & ~size_t(255);
+  const size_t idx_bytes = (sizeof(uint32_t) * (size_t)m * b + 255) & ~size_t(255);
+  char *ws = nullptr;
+  B200_CUDA(cudaMalloc(&ws, 2 * vec + xb_bytes + tb_bytes + idx_bytes + 256));
+  struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
+  float *grad = (float *)ws, *vel = (float *)(ws + vec);
+  float *Xb = (float *)(ws + 2 * vec), *Tb = (float *)(ws + 2 * vec + xb_bytes);
+  uint32_t *d_idx = (uint32_t *)(ws + 2 * vec + xb_bytes + tb_bytes);
+  EvalOut *scratch = (EvalOut *)(ws + 2 * vec + xb_bytes + tb_bytes + idx_bytes);
+  if (o.momentum > 0.0f) B200_CUDA(cudaMemsetAsync(vel, 0, sizeof(float) * Nn, st));
+  uint32_t *h_idx = nullptr;
+  B200_CUDA(cudaMallocHost(&h_idx, sizeof(uint32_t) * (size_t)m * b));
+  struct FreeHost { uint32_t *p; ~FreeHost() { cudaFreeHost(p); } } free_h{h_idx};
+  Sampler sampler(o.seed, (size_t)N);
+  double *h_mail = ctx->h_scalars;
+  long evals = 0;
+  int iters = 0;
+  float elapsed = 0.f;
+  cudaEvent_t ev0 = ctx->ev_a, ev1 = ctx->ev_b;
+  while (iters < o.max_iters) {
+    if (hist) B200_CUDA(cudaEventRecord(ev0, st));
+    for (int t = 0; t < m; ++t) sampler.draw((size_t)N, (size_t)b, h_idx + (size_t)t * b);
+    B200_CUDA(cudaMemcpyAsync(d_idx, h_idx, sizeof(uint32_t) * (size_t)m * b, cudaMemcpyHostToDevice, st));
+    for (int t = 0; t < m; ++t) {
+      B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(b, 8)), 256, 0, st, input, target, d_idx + (size_t)t * b, b, in_dim,
+                  out_dim, Xb, Tb);
+      ++evals;
+      B200_TRY(net_eval(net, params, Xb, Tb, b, b, grad, scratch)); // grad /= current_bs (:266)
+      if (o.momentum > 0.0f) B200_TRY(launch_momentum_step(Nn, o.momentum, o.lr, grad, vel, params, st));
+      else B200_TRY(launch_axpy(Nn, -o.lr, grad, params, st));       // w = w - step * grad_est (s_gd.hpp:104)
+    }
+    if (hist) {
+      ++evals;
+      B200_TRY(net_eval(net, params, input, target, N, N, grad, (EvalOut *)net->eval_out));
+      B200_CUDA(cudaMemcpyAsync(h_mail, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaEventRecord(ev1, st));
+      B200_CUDA(cudaEventSynchronize(ev1));
+      float ms = 0.f;
+      B200_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+      elapsed += ms;
+      if (iters < hist->capacity) {
+        if (hist->loss) hist->loss[iters] = (float)h_mail[0];
+        if (hist->grad_norm) hist->grad_norm[iters] = (float)std::sqrt(h_mail[1]);
+        if (hist->time_ms) hist->time_ms[iters] = elapsed;
+        hist->size = iters + 1;
+      }
+    }
+    ++iters;
+  }
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (hist) {
+    hist->iterations = iters;
+    hist->evaluations = evals;
+    hist->launches = b200_launch_count() - launches0;
+  }
+  return B200_OK;
+}
+
 } // namespace b200
 
 using namespace b200;

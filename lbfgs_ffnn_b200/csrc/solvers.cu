@@ -109,7 +109,7 @@ void b200_gd_default_opts(b200_gd_opts *o) {
 void b200_sgd_default_opts(b200_sgd_opts *o) {
   if (!o) return;
   o->max_iters = 200; o->tol = 1e-6f; o->lr = 0.01f; o->momentum = 0.9f; o->decay_rate = 1.0f; o->decay_step = 0;
-  o->batch_size = 64; o->input_dim = 0; o->output_dim = 0; o->record_timing = 1;
+  o->batch_size = 64; o->input_dim = 0; o->output_dim = 0; o->record_timing = 1; o->sampling = 0; o->seed = 123;
 }
 
 // ===================================================================================================
@@ -343,6 +343,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   const int max_ls = o.max_line_iters;
   for (int it = 0; it < iters; ++it) {
     const int iter = s->iter;
+    NvtxRange nvtx_iter("lbfgs_iteration");
     B200_TRY(timer.start());
     if (s->gnorm < (double)o.tol) break; // lbfgs.cuh:92-93 / lbfgs.hpp:53-55
     float *g = s->gbuf[s->cur], *g_new = s->gbuf[s->cur ^ 1];
@@ -800,6 +801,10 @@ int b200_sgd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *use
   }
   B200_REQUIRE(o.batch_size > 0, "batch_size must be positive");
   B200_REQUIRE(ctx->world == 1, "CudaSGD is single-GPU (sequential mini-batches)");
+  if (o.sampling == 1) {
+    B200_REQUIRE(net, "random mini-batches need the library's network objective (rows are gathered on the device)");
+    return sgd_random_solve(ctx, net, n, params, input, target, total_samples, o, hist);
+  }
   B200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const long launches0 = b200_launch_count();

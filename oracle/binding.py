@@ -56,6 +56,8 @@ def _declare(L):
     L.oracle_loss_grad.restype = C.c_double
     L.oracle_loss_grad.argtypes = [C.c_void_p, dp, dp, dp, C.c_long, dp]
     L.oracle_forward.argtypes = [C.c_void_p, dp, dp, C.c_long, dp]
+    L.oracle_loss_grad_masked.restype = C.c_double
+    L.oracle_loss_grad_masked.argtypes = [C.c_void_p, dp, dp, dp, C.c_long, C.POINTER(C.c_uint8), dp]
     L.oracle_slbfgs_batch_grad.restype = C.c_double
     L.oracle_slbfgs_batch_grad.argtypes = [C.c_void_p, dp, dp, dp, C.c_long, up, C.c_long, C.c_double, dp]
     L.oracle_direction.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, C.c_int, dp]
@@ -122,6 +124,17 @@ class OracleNet:
         g = np.empty(self.n, dtype=np.float64)
         loss = lib().oracle_loss_grad(self.h, _p(params, C.c_double), _p(X, C.c_double), _p(T, C.c_double), B,
                                       _p(g, C.c_double))
+        return loss, g
+
+    def loss_grad_masked(self, params, X, T, masks):
+        """loss / gradient with the ReLU pattern of the hidden layers imposed: masks = [uint8 (B, out_l) for each hidden layer]"""
+        params, X, T = _f64(params), _f64(X), _f64(T)
+        B = X.size // self.dims[0]
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.uint8).ravel() for m in masks]))
+        assert flat.size == B * sum(self.dims[1:-1])
+        g = np.empty(self.n, dtype=np.float64)
+        loss = lib().oracle_loss_grad_masked(self.h, _p(params, C.c_double), _p(X, C.c_double), _p(T, C.c_double), B,
+                                             _p(flat, C.c_uint8), _p(g, C.c_double))
         return loss, g
 
     def forward(self, params, X):

@@ -98,6 +98,7 @@ struct Net {
   // caches (layer.hpp:86-87 input_cache/z_cache, network.hpp:30-31)
   std::vector<Vec> z, a, delta;
 
+  const uint8_t *masks = nullptr; // imposed ReLU activation pattern of the hidden layers, [layer][B][out] (see layer_forward)
   int nlayers() const { return (int)acts.size(); }
 };
 
@@ -119,8 +120,11 @@ Net *net_create(int nlayers, const int *dims, const int *acts) {
 }
 
 // z = W*in + b ; out = act(z)   (layer.hpp:100-111). in: K x B, out: M x B col-major.
+// mask (optional, ReLU layers only): the activation pattern is IMPOSED instead of derived from the sign of z — unit (b, o) passes
+// z through iff mask[b * M + o] != 0 (and its derivative is that 0 / 1). Used by the parity tests to evaluate the fp64 objective on
+// the activation pattern an fp32 evaluation took (pre-activations within rounding of zero pick a side at random in fp32).
 void layer_forward(const double *W, const double *bias, int M, int K, int act, const double *in, long B, double *z,
-                   double *out) {
+                   double *out, const uint8_t *mask = nullptr) {
 #pragma omp parallel for schedule(static)
   for (long b = 0; b < B; ++b) {
     double *zb = z + (size_t)b * M;
@@ -135,7 +139,7 @@ void layer_forward(const double *W, const double *bias, int M, int K, int act, c
     double *ob = out + (size_t)b * M;
     for (int o = 0; o < M; ++o) {
       zb[o] += bias[o];
-      ob[o] = act_apply(act, zb[o]);
+      ob[o] = (mask && act == kReLU) ? (mask[(size_t)b * M + o] ? zb[o] : 0.0) : act_apply(act, zb[o]);
     }
   }
 }
@@ -143,10 +147,11 @@ void layer_forward(const double *W, const double *bias, int M, int K, int act, c
 // dZ = next_grad .* act'(z); dW += dZ*in^T; db += rowsum(dZ); prev = W^T dZ (layer.hpp:113-128)
 // next_grad is overwritten with dZ.
 void layer_backward(const double *W, int M, int K, int act, const double *in, const double *z, double *next_grad, long B,
-                    double *dW, double *db, double *prev) {
+                    double *dW, double *db, double *prev, const uint8_t *mask = nullptr) {
   const size_t tot = (size_t)M * B;
 #pragma omp parallel for schedule(static)
-  for (long idx = 0; idx < (long)tot; ++idx) next_grad[idx] *= act_prime(act, z[idx]);
+  for (long idx = 0; idx < (long)tot; ++idx)
+    next_grad[idx] *= (mask && act == kReLU) ? (mask[idx] ? 1.0 : 0.0) : act_prime(act, z[idx]);
 
   // dW[o + k*M] += sum_b dZ[o + b*M] * in[k + b*K]; parallel over k => deterministic for any thread count
 #pragma omp parallel for schedule(static)
@@ -181,12 +186,15 @@ void layer_backward(const double *W, int M, int K, int act, const double *in, co
 // Network::forward (network.hpp:73-88). Returns pointer to the output activations (out x B).
 const double *net_forward(Net &n, const double *params, const double *X, long B) {
   const double *cur = X;
+  const uint8_t *mk = n.masks;
   for (int l = 0; l < n.nlayers(); ++l) {
     const int K = n.dims[l], M = n.dims[l + 1];
     n.z[l].resize((size_t)M * B);
     n.a[l].resize((size_t)M * B);
     const double *W = params + n.offs[l];
-    layer_forward(W, W + (size_t)M * K, M, K, n.acts[l], cur, B, n.z[l].data(), n.a[l].data());
+    layer_forward(W, W + (size_t)M * K, M, K, n.acts[l], cur, B, n.z[l].data(), n.a[l].data(),
+                  (mk && l + 1 < n.nlayers()) ? mk : nullptr);
+    if (mk) mk += (size_t)M * B;
     cur = n.a[l].data();
   }
   return cur;
@@ -222,6 +230,11 @@ double net_loss_grad(Net &n, const double *params, const double *X, const double
     s += diff[i] * diff[i];
   }
   // Network::backward (network.hpp:91-102)
+  std::vector<const uint8_t *> lmask(L, nullptr);
+  if (n.masks) {
+    const uint8_t *mk = n.masks;
+    for (int l = 0; l + 1 < L; ++l) { lmask[l] = mk; mk += (size_t)n.dims[l + 1] * B; }
+  }
   for (int l = L - 1; l >= 0; --l) {
     const int K = n.dims[l], M = n.dims[l + 1];
     const double *W = params + n.offs[l];
@@ -232,7 +245,7 @@ double net_loss_grad(Net &n, const double *params, const double *X, const double
       prev = n.delta[l - 1].data();
     }
     layer_backward(W, M, K, n.acts[l], in, n.z[l].data(), n.delta[l].data(), B, grad + n.offs[l],
-                   grad + n.offs[l] + (size_t)M * K, prev);
+                   grad + n.offs[l] + (size_t)M * K, prev, lmask[l]);
   }
   const double inv = (B > 0) ? 1.0 / (double)B : 0.0;
   if (inv != 0.0)
@@ -905,6 +918,16 @@ double oracle_loss(void *h, const double *params, const double *X, const double 
 }
 double oracle_loss_grad(void *h, const double *params, const double *X, const double *T, long B, double *grad) {
   return net_loss_grad(*(Net *)h, params, X, T, B, grad);
+}
+// loss and gradient with the ReLU activation pattern of the hidden layers imposed (masks: hidden layer 0's [B][out] bytes,
+// then hidden layer 1's, ...). Test infrastructure for the "which side of zero did fp32 land on" question.
+double oracle_loss_grad_masked(void *h, const double *params, const double *X, const double *T, long B, const uint8_t *masks,
+                               double *grad) {
+  Net &n = *(Net *)h;
+  n.masks = masks;
+  const double loss = net_loss_grad(n, params, X, T, B, grad);
+  n.masks = nullptr;
+  return loss;
 }
 void oracle_forward(void *h, const double *params, const double *X, long B, double *out) {
   Net &n = *(Net *)h;

@@ -44,50 +44,109 @@ inline double dot(const double *a, const double *b, Index n) {
   return (s0 + s1) + (s2 + s3);
 }
 
-// C (m x n) = A (m x k) * B (k x n), all column-major with leading dimensions lda, ldb, ldc. Threads split the columns of C.
-inline void gemm_nn(Index m, Index n, Index k, const double *A, Index lda, const double *B, Index ldb, double *C, Index ldc) {
-#pragma omp parallel for schedule(static) if (m * n * k > (Index)1 << 16)
-  for (Index jb = 0; jb < n; jb += 8) {
-    const Index jn = std::min<Index>(8, n - jb);
-    for (Index j = 0; j < jn; ++j) std::fill(C + (jb + j) * ldc, C + (jb + j) * ldc + m, 0.0);
-    for (Index p = 0; p < k; ++p) {
-      const double *a = A + p * lda;
-      for (Index j = 0; j < jn; ++j) {
-        const double b = B[p + (jb + j) * ldb];
-        double *c = C + (jb + j) * ldc;
-        for (Index i = 0; i < m; ++i) c[i] += a[i] * b;
-      }
+// Dense GEMMs. Register-tiled 8 x 6 micro-kernels on 4-wide double vectors (AVX2 + FMA at -march=x86-64-v3) so that the CPU
+// arm of bench.py is not handicapped by the stand-in: Eigen's own GEMM is a tuned, packed kernel of the same kind.
+typedef double v4d __attribute__((vector_size(32), aligned(8)));
+static inline v4d ld4(const double *p) { return *reinterpret_cast<const v4d *>(p); }
+static inline void st4(double *p, v4d v) { *reinterpret_cast<v4d *>(p) = v; }
+static inline v4d bc4(double x) { return v4d{x, x, x, x}; }
+
+// acc[8 x 6] (+)= sum_p A[i0 .. i0+8, p] * Bval(p, j) for p in [p0, p1); A column-major (lda); B element (p, j) at B[p * bp + j * bj]
+template <bool ACCUM>
+static inline void micro_8x6(const double *A, Index lda, const double *B, Index bp, Index bj, Index p0, Index p1, double *C, Index ldc) {
+  v4d c00 = bc4(0), c01 = bc4(0), c10 = bc4(0), c11 = bc4(0), c20 = bc4(0), c21 = bc4(0);
+  v4d c30 = bc4(0), c31 = bc4(0), c40 = bc4(0), c41 = bc4(0), c50 = bc4(0), c51 = bc4(0);
+  for (Index p = p0; p < p1; ++p) {
+    const double *a = A + p * lda;
+    const v4d a0 = ld4(a), a1 = ld4(a + 4);
+    const double *b = B + p * bp;
+    v4d x;
+    x = bc4(b[0]);      c00 += a0 * x; c01 += a1 * x;
+    x = bc4(b[bj]);     c10 += a0 * x; c11 += a1 * x;
+    x = bc4(b[2 * bj]); c20 += a0 * x; c21 += a1 * x;
+    x = bc4(b[3 * bj]); c30 += a0 * x; c31 += a1 * x;
+    x = bc4(b[4 * bj]); c40 += a0 * x; c41 += a1 * x;
+    x = bc4(b[5 * bj]); c50 += a0 * x; c51 += a1 * x;
+  }
+  const v4d r[6][2] = {{c00, c01}, {c10, c11}, {c20, c21}, {c30, c31}, {c40, c41}, {c50, c51}};
+  for (int j = 0; j < 6; ++j) {
+    double *c = C + j * ldc;
+    if (ACCUM) { st4(c, ld4(c) + r[j][0]); st4(c + 4, ld4(c + 4) + r[j][1]); }
+    else { st4(c, r[j][0]); st4(c + 4, r[j][1]); }
+  }
+}
+// the same for ragged edges (mr <= 8 rows, nr <= 6 columns)
+template <bool ACCUM>
+static inline void micro_edge(Index mr, Index nr, const double *A, Index lda, const double *B, Index bp, Index bj, Index p0, Index p1,
+                              double *C, Index ldc) {
+  double acc[6][8] = {};
+  for (Index p = p0; p < p1; ++p) {
+    const double *a = A + p * lda, *b = B + p * bp;
+    for (Index j = 0; j < nr; ++j) {
+      const double x = b[j * bj];
+      for (Index i = 0; i < mr; ++i) acc[j][i] += a[i] * x;
+    }
+  }
+  for (Index j = 0; j < nr; ++j)
+    for (Index i = 0; i < mr; ++i) C[i + j * ldc] = (ACCUM ? C[i + j * ldc] : 0.0) + acc[j][i];
+}
+// C tile block (rows [0, m), columns [j0, j1)) (+)= A[:, p0:p1] * Bview[p0:p1, j0:j1]
+template <bool ACCUM>
+static inline void gemm_block(Index m, Index j0, Index j1, const double *A, Index lda, const double *B, Index bp, Index bj, Index p0,
+                              Index p1, double *C, Index ldc) {
+  for (Index j = j0; j < j1; j += 6) {
+    const Index nr = std::min<Index>(6, j1 - j);
+    for (Index i = 0; i < m; i += 8) {
+      const Index mr = std::min<Index>(8, m - i);
+      if (mr == 8 && nr == 6) micro_8x6<ACCUM>(A + i, lda, B + j * bj, bp, bj, p0, p1, C + i + j * ldc, ldc);
+      else micro_edge<ACCUM>(mr, nr, A + i, lda, B + j * bj, bp, bj, p0, p1, C + i + j * ldc, ldc);
     }
   }
 }
-// C (m x n) = A^T * B with A stored k x m (column-major): C[i][j] = dot(A[:, i], B[:, j]). Threads split the columns of C.
-inline void gemm_tn(Index m, Index n, Index k, const double *A, Index lda, const double *B, Index ldb, double *C, Index ldc) {
+
+// C (m x n) = A (m x k) * B (k x n), all column-major with leading dimensions lda, ldb, ldc. Threads split the columns of C;
+// K is walked in slices so that the A panel of a slice stays in cache across the column blocks of a thread.
+inline void gemm_nn(Index m, Index n, Index k, const double *A, Index lda, const double *B, Index ldb, double *C, Index ldc) {
+  const Index kc = 256, nc = 96;
 #pragma omp parallel for schedule(static) if (m * n * k > (Index)1 << 16)
-  for (Index j = 0; j < n; ++j)
-    for (Index i = 0; i < m; ++i) C[i + j * ldc] = dot(A + i * lda, B + j * ldb, k);
+  for (Index jb = 0; jb < n; jb += nc) {
+    const Index j1 = std::min<Index>(n, jb + nc);
+    for (Index p0 = 0; p0 < k; p0 += kc) {
+      const Index p1 = std::min<Index>(k, p0 + kc);
+      if (p0 == 0) gemm_block<false>(m, jb, j1, A, lda, B, 1, ldb, p0, p1, C, ldc);
+      else gemm_block<true>(m, jb, j1, A, lda, B, 1, ldb, p0, p1, C, ldc);
+    }
+    if (k == 0)
+      for (Index j = jb; j < j1; ++j) std::fill(C + j * ldc, C + j * ldc + m, 0.0);
+  }
 }
-// C (m x n) = A (m x k) * B^T with B stored n x k (column-major): a sum of k rank-1 updates. Threads take slices of k with
-// private accumulators that are added in thread order.
+// C (m x n) = A^T * B with A stored k x m (column-major): A is the small operand here (a weight matrix), so it is transposed
+// once and the product runs through the same kernel.
+inline void gemm_tn(Index m, Index n, Index k, const double *A, Index lda, const double *B, Index ldb, double *C, Index ldc) {
+  std::vector<double> At((size_t)(m * k));
+  for (Index i = 0; i < m; ++i)
+    for (Index p = 0; p < k; ++p) At[(size_t)(i + p * m)] = A[p + i * lda];
+  gemm_nn(m, n, k, At.data(), m, B, ldb, C, ldc);
+}
+// C (m x n) = A (m x k) * B^T with B stored n x k (column-major): a sum of k rank-1 updates (the dW product: k = samples).
+// Threads take slices of k with private accumulators, walked in chunks that keep both panels in cache, and the accumulators are
+// added in thread order.
 inline void gemm_nt(Index m, Index n, Index k, const double *A, Index lda, const double *B, Index ldb, double *C, Index ldc) {
   int nt = 1;
 #ifdef _OPENMP
   nt = (m * n * k > (Index)1 << 18) ? omp_get_max_threads() : 1;
 #endif
   nt = (int)std::max<Index>(1, std::min<Index>(nt, k / 64 + 1));
-  std::vector<std::vector<double>> acc(nt, std::vector<double>((size_t)(m * n), 0.0));
+  std::vector<std::vector<double>> acc(nt);
 #pragma omp parallel for schedule(static) num_threads(nt)
   for (int t = 0; t < nt; ++t) {
-    const Index p0 = k * t / nt, p1 = k * (t + 1) / nt;
+    acc[t].assign((size_t)(m * n), 0.0);
+    const Index s0 = k * t / nt, s1 = k * (t + 1) / nt, kc = 64;
     double *c = acc[t].data();
-    for (Index p = p0; p < p1; ++p) {
-      const double *a = A + p * lda, *b = B + p * ldb;
-      for (Index j = 0; j < n; ++j) {
-        const double bj = b[j];
-        double *cj = c + j * m;
-        for (Index i = 0; i < m; ++i) cj[i] += a[i] * bj;
-      }
-    }
+    for (Index p0 = s0; p0 < s1; p0 += kc)
+      gemm_block<true>(m, 0, n, A, lda, B, ldb, 1, p0, std::min<Index>(s1, p0 + kc), c, m); // B(p, j) = B[j + p * ldb]
   }
+#pragma omp parallel for schedule(static) if (m * n > 1 << 14)
   for (Index j = 0; j < n; ++j)
     for (Index i = 0; i < m; ++i) {
       double s = 0.0;

@@ -18,14 +18,14 @@ import pytest
 
 import lbfgs_ffnn_b200 as P
 from conftest import rel_l2
-from helpers import make_gpu_net, make_problem, upload
+from helpers import make_gpu_net, make_problem, relu_pattern_of, upload
 
 pytestmark = pytest.mark.gpu
 
 TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16", "B200_TAIL_FWD")
 
 
-def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True):
+def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True, want_pattern=False):
     saved = {k: os.environ.get(k) for k in TOGGLES}
     try:
         for k in TOGGLES:
@@ -40,9 +40,10 @@ def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True):
             assert net.quantize_input(dx, B) is True
         loss = net.compute_loss_and_grad(dx, dt, B)
         g = net.get_grads()
+        pattern = relu_pattern_of(net, acts) if want_pattern else None
         net.forward_only(dx, B)
         out = net.copy_output_to_host().reshape(B, dims[-1])
-        return loss, g, out
+        return (loss, g, out, pattern) if want_pattern else (loss, g, out)
     finally:
         for k, v in saved.items():
             if v is None:
@@ -110,10 +111,11 @@ def test_full_size_fp16_path(handle, oracle, which):
     """BASELINE configs[1] / configs[2] size: 60 000 samples, 469 tiles over 148 persistent CTAs, 37-way split-K in dw16"""
     dims, acts = NETS[which]
     onet, w, X, T = make_problem(oracle, dims, acts, 60000)
-    lo, go = onet.loss_grad(w, X, T)
-    loss, g, _ = _eval(handle, dims, acts, w, X, T, "tf32x3")
-    # 7.7 M ReLU units: a few sit within rounding of zero and flip against the fp64 oracle (see test_gpu_tensorcore.py)
-    assert abs(loss - lo) <= 2e-5 * abs(lo) and rel_l2(g, go) <= 5e-5, (loss, lo, rel_l2(g, go))
+    loss, g, _, pattern = _eval(handle, dims, acts, w, X, T, "tf32x3", want_pattern=True)
+    # 7.7 M ReLU units: a few sit within fp32 rounding of zero and land on the other side of it than in fp64; the fp64 objective is
+    # evaluated on the pattern the GPU took (helpers.oracle_on_gpu_pattern) and the bound is the one of every other size
+    lo, go = onet.loss_grad_masked(w, X, T, pattern)
+    assert abs(loss - lo) <= 2e-5 * abs(lo) and rel_l2(g, go) <= 2e-5, (loss, lo, rel_l2(g, go))
 
 
 @pytest.mark.parametrize("which", [0, 5])

@@ -207,6 +207,56 @@ def test_lbfgs_generic_callback_rosenbrock(handle):
     assert 0 < s.iterations() < 400
 
 
+# The reference's known-answer suite (tests/main.cpp) through the GPU minimizer's generic LossGradFun mode. Its thresholds
+# (||grad|| <= 1e-8 .. 1e-10, ||x - 1|| <= 1e-8) are those of the double-precision CPU minimizers; the CUDA interface is
+# float (CudaScalar, src/cuda/common.cuh:11): x lives in fp32, so the attainable gradient norm is ~ ||Hessian|| * ulp(x).
+# The bounds below are those fp32 analogues, and the fp64 oracle run of the same algorithm (pinned to the reference's CPU
+# code) must land on the same minimiser.
+KAT = {  # name: (x0, iterations, ||grad f(x)|| bound in fp32, memory)
+    "rosenbrock": (np.array([-1.2, 1.0, -1.2, 1.0]), 300, 2e-3, 16),                      # tests/main.cpp:135-155
+    "ackley": (np.array([10.0, -5.0, 1.0]), 300, 2e-3, 16),                                # :242-257
+    "rastrigin": (np.array([4.0 if i % 2 == 0 else -4.0 for i in range(500)]), 300, 3e-2, 16),  # :48-64, n = 500
+}
+
+
+@pytest.mark.parametrize("policy", ["armijo", "wolfe"])
+@pytest.mark.parametrize("fn", list(KAT))
+def test_reference_kat_suite_on_the_gpu_minimizer(handle, oracle, fn, policy):
+    x0, iters, gbound, m = KAT[fn]
+    n = x0.size
+    dxp = upload(x0.astype(np.float32))
+    calls = [0]
+
+    def loss_grad(params, grad, inp, tgt, batch):  # LossGradFun (src/cuda/minimizer_base.cuh:15-16): device pointers in, loss out
+        x = api._d2h(params, n).astype(np.float64)
+        f, g = oracle.analytic_eval(fn, x)
+        api._h2d(grad, g.astype(np.float32))
+        calls[0] += 1
+        return f
+
+    s = P.CudaLBFGS(handle)
+    s.setMemory(m); s.setMaxIterations(iters); s.setTolerance(gbound * 0.1)
+    s.setLineSearchPolicy(policy)
+    if policy == "wolfe":
+        s.setLineSearchParams(50, 1e-4, 0.5)
+    s.solve(n, dxp, dxp, dxp, 1, loss_grad)
+    x = dxp.copy_to_host().astype(np.float64)
+    f, g = oracle.analytic_eval(fn, x)
+    f0, _ = oracle.analytic_eval(fn, x0)
+    ref = oracle.lbfgs_analytic(fn, x0, m=m, max_iters=4000, tol=1e-12, policy="cuda" if policy == "armijo" else "cpu")
+    print(f"\n[{fn} {policy}] iterations {s.iterations()} calls {calls[0]} f {f0:.3e} -> {f:.3e} ||grad|| {np.linalg.norm(g):.2e} "
+          f"| fp64 oracle: f {ref['f']:.3e} ||grad|| {ref['gnorm']:.1e}, ||x - x_oracle|| {np.linalg.norm(x - ref['x']):.2e}")
+    assert np.linalg.norm(g) <= gbound, np.linalg.norm(g)
+    assert f < f0
+    if fn == "rosenbrock":
+        assert np.linalg.norm(x - 1.0) <= 1e-5  # the global minimum at 1 (reference: 1e-8 in double)
+        assert ref["gnorm"] <= 1e-10 and np.linalg.norm(ref["x"] - 1.0) <= 1e-8  # the oracle meets the reference's own thresholds
+    if fn == "rastrigin":
+        # both descend from (+-4) to the nearest local minimiser (+-3.98): same point up to fp32 resolution
+        assert ref["gnorm"] <= 1e-8
+        assert np.max(np.abs(x - ref["x"])) <= 1e-5
+
+
 def test_lbfgs_invalid_args_are_silent(handle):
     s = P.CudaLBFGS(handle)
     s.solve(0, None, 0, 0, 0, None)  # src/cuda/lbfgs.cuh:45-48
@@ -291,3 +341,23 @@ def test_launcher_end_to_end(handle, oracle, tmp_path):
     assert last < 0.5 * first and acc > 50.0
     tm, ta = L.test()
     assert tm > 0 and 0 <= ta <= 100
+
+
+@pytest.mark.parametrize("dims,acts,B,bs", [([784, 128, 10], ["relu", "linear"], 1000, 128), ([784, 128, 64, 10], ["relu", "relu", "linear"], 900, 100)])
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_sgd_random_batches_cpu_variant(handle, oracle, dims, acts, B, bs, prec):
+    """the CPU backend's SGD (src/minimizer/s_gd.hpp:63-170 + UnifiedSGD_CPU closures) on the GPU: random mini-batches from the
+    same mt19937(123) stream; the oracle's restatement is pinned to the reference's own code (test_oracle_vs_reference_cpu.py)"""
+    onet, w, X, T = make_problem(oracle, dims, acts, B)
+    ref = onet.sgd_cpu_policy(w, X, T, batch_size=bs, lr=0.05, max_iters=4)
+    net = make_gpu_net(handle, dims, acts, w, precision=prec)
+    s = P.CudaSGD(handle)
+    s.setLearningRate(0.05); s.setMomentum(0.0); s.setBatchSize(bs); s.setMaxIterations(4); s.setTolerance(0.0)
+    s.setDimensions(dims[0], dims[-1]); s.setSampling("random", 123)
+    rec = P.IterationRecorder(); rec.init(4); s.setRecorder(rec)
+    s.solve(net.params_size(), net.params_data(), upload(X), upload(T), B, net)
+    loss, gn, _ = rec.copy_to_host()
+    assert s.iterations() == 4 and loss.size == 4
+    assert np.allclose(loss, ref["loss"], rtol=1e-4), (loss, ref["loss"])
+    assert np.allclose(gn, ref["gnorm"], rtol=1e-3)
+    assert rel_l2(net.get_params(), ref["params"]) <= 1e-4

@@ -13,7 +13,7 @@ import pytest
 
 import lbfgs_ffnn_b200 as P
 from conftest import rel_l2
-from helpers import make_gpu_net, make_problem, upload
+from helpers import make_gpu_net, make_problem, oracle_on_gpu_pattern, upload
 
 pytestmark = pytest.mark.gpu
 
@@ -22,7 +22,7 @@ NETS = [([784, 128, 10], ["relu", "linear"]), ([784, 128, 64, 10], ["relu", "rel
         ([784, 256, 128, 64, 10], ["tanh", "sigmoid", "relu", "linear"]), ([96, 64, 32, 12], ["relu", "tanh", "linear"])]
 
 
-def _check(handle, oracle, dims, acts, batch, prec, mask=None):
+def _check(handle, oracle, dims, acts, batch, prec, mask=None, impose_pattern=False):
     if mask is None:
         os.environ.pop("B200_TC_MASK", None)
     else:
@@ -35,6 +35,8 @@ def _check(handle, oracle, dims, acts, batch, prec, mask=None):
         dx, dt = upload(X), upload(T)
         loss = net.compute_loss_and_grad(dx, dt, batch)
         g = net.get_grads()
+        if impose_pattern:  # the fp64 objective on the ReLU pattern this evaluation took (helpers.oracle_on_gpu_pattern)
+            loss_o, g_o = oracle_on_gpu_pattern(onet, net, acts, w, X, T)
         net.forward_only(dx, batch)
         out = net.copy_output_to_host().reshape(batch, dims[-1])
         return abs(loss - loss_o) / abs(loss_o), rel_l2(g, g_o), rel_l2(out, onet.forward(w, X))
@@ -68,12 +70,12 @@ def test_tc_loss_grad_parity(handle, oracle, dims, acts, batch, prec):
 def test_tc_full_size(handle, oracle, prec):
     """BASELINE configs[1]/[2] size: 60 000 samples (K = 60 000 reduction in dW)"""
     for dims, acts in NETS[:2]:
-        el, eg, eo = _check(handle, oracle, dims, acts, 60000, prec)
-        # 11.5 M ReLU units at 60 000 samples: a handful sit within fp32 rounding of zero and flip relative to the
-        # fp64 oracle, which moves the gradient by ~1e-5 even on the exact-fp32 FFMA path (measured 9.3e-6 on the
-        # deep net); the tensor-core modes get 2.5x that as their stated bound here
-        tol_g = max(TOL[prec], 5e-5)
-        assert el <= TOL[prec] and eg <= tol_g and eo <= TOL[prec], (dims, el, eg, eo)
+        # 11.5 M ReLU units at 60 000 samples: a handful sit within fp32 rounding of zero and land on the other side of it than
+        # in fp64 (any fp32 evaluation does that, the reference's CUDA backend included). The comparison is therefore made on the
+        # activation pattern the GPU took — same bound as at every other size, no 60 000-sample exemption;
+        # tests/test_gpu_parity_full_size.py holds the headline mode to the north-star 1e-5 there and counts the units.
+        el, eg, eo = _check(handle, oracle, dims, acts, 60000, prec, impose_pattern=True)
+        assert el <= TOL[prec] and eg <= TOL[prec] and eo <= TOL[prec], (dims, el, eg, eo)
 
 
 def test_tc_lbfgs_trajectory(handle, oracle):
@@ -102,8 +104,10 @@ def test_u8_input_path(handle, oracle, dims, acts, batch, prec):
     assert net.quantize_input(dx, batch) is True
     loss = net.compute_loss_and_grad(dx, dt, batch)
     g = net.get_grads()
+    if batch >= 60000:  # on the ReLU pattern the GPU took (see test_tc_full_size): same bound as the smaller batches
+        loss_o, g_o = oracle_on_gpu_pattern(onet, net, acts, w, X, T)
     tol_l = TOL[prec] if prec == "tf32x3" else 2e-3
-    tol_g = max(TOL[prec], 5e-5) if batch >= 60000 else TOL[prec]
+    tol_g = TOL[prec]
     if prec == "tf32" and batch < 100:
         tol_g = 1.0
     assert abs(loss - loss_o) <= tol_l * abs(loss_o), (loss, loss_o)
@@ -114,7 +118,7 @@ def test_u8_input_path(handle, oracle, dims, acts, batch, prec):
     g_f = net.get_grads()
     if prec == "tf32x3":
         assert abs(loss - loss_f) <= 5e-6 * abs(loss_f)
-        assert rel_l2(g, g_f) <= tol_g
+        assert rel_l2(g, g_f) <= (5e-5 if batch >= 60000 else tol_g)  # two fp32 evaluations may each take their own pattern
 
 
 def test_u8_input_rejected_when_not_quantised(handle, oracle):

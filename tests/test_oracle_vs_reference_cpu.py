@@ -112,6 +112,7 @@ def test_goldens_regenerate_from_the_reference_sources(oracle):
     net = rc.RefCpuNet(case["dims"])
     w0, X, T = case_problem(case)
     loss, grad = net.loss_grad(w0, X, T)
-    assert loss == g["objective"]["loss"]
+    assert abs(loss - g["objective"]["loss"]) <= 1e-13 * abs(loss)  # (the summation order of the stand-in's GEMM depends on the thread count)
+    _close(grad, g["objective"]["grad"], 1e-12)
     r = net.full_batch("lbfgs", w0, X, T, max_iters=case["lbfgs_iters"], tolerance=0.0, m_param=case["m"])
-    np.testing.assert_allclose(r["loss"], g["lbfgs"]["loss"], rtol=1e-13)
+    np.testing.assert_allclose(r["loss"], g["lbfgs"]["loss"], rtol=1e-7)
