@@ -214,7 +214,7 @@ def test_lbfgs_generic_callback_rosenbrock(handle):
 # code) must land on the same minimiser.
 KAT = {  # name: (x0, iterations, ||grad f(x)|| bound in fp32, memory)
     "rosenbrock": (np.array([-1.2, 1.0, -1.2, 1.0]), 300, 2e-3, 16),                      # tests/main.cpp:135-155
-    "ackley": (np.array([10.0, -5.0, 1.0]), 300, 2e-3, 16),                                # :242-257
+    "ackley": (np.array([10.0, -5.0, 1.0]), 300, 1e-2, 16),                                # :242-257 (|x| ~ 10: ulp 1e-6, |H| ~ 1e3)
     "rastrigin": (np.array([4.0 if i % 2 == 0 else -4.0 for i in range(500)]), 300, 3e-2, 16),  # :48-64, n = 500
 }
 
@@ -321,6 +321,33 @@ def test_slbfgs_parity(handle, oracle, M, rtol):
     assert np.allclose(loss, ref["loss"], rtol=rtol), (loss, ref["loss"])
     assert np.allclose(gn, ref["gnorm"], rtol=10 * rtol), (gn, ref["gnorm"])
     assert loss[-1] < loss[0]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_slbfgs_parity_at_config3_size(handle, oracle, prec):
+    """BASELINE configs[3] at full size: 784-128-64-10, N = 60 000, mini-batch 1000 (60 inner steps per epoch), b_H = 5000, L = 10.
+    M = 0 keeps the run on the SVRG part (index streams, anchor picks, variance-reduced steps, L2 term, recorder), which must match
+    the fp64 oracle — itself pinned to the reference's own S-LBFGS code after every epoch (test_oracle_vs_reference_cpu.py) — to
+    2e-4 on the per-epoch loss; the M = 10 run (curvature pairs from the reference's eps = 1e-4 finite differences, a few ulps of
+    the fp32 weights) is reported and held to the stated 5e-2."""
+    dims, acts, N = [784, 128, 64, 10], ["relu", "relu", "linear"], 60000
+    onet, w, X, T = make_problem(oracle, dims, acts, N)
+    dx, dt = upload(X), upload(T)
+    for M, rtol, epochs in ((0, 2e-4, 2), (10, 5e-2, 2)):
+        ref = onet.slbfgs(w, X, T, batch_size=1000, M=M, L=10, b_H=5000, step=0.02, max_iters=epochs, tol=0.0, seed=123)
+        net = make_gpu_net(handle, dims, acts, w, precision=prec)
+        s = P.CudaSLBFGS(handle)
+        s.setMaxIterations(epochs); s.setTolerance(0.0); s.setStepSize(0.02); s.setBatchSize(1000)
+        s.setMemory(M); s.setUpdateInterval(10); s.setHessianBatchSize(5000)
+        rec = P.IterationRecorder(); rec.init(epochs); s.setRecorder(rec)
+        s.solve(net.params_size(), net.params_data(), dx, dt, N, net)
+        loss, gn, _ = rec.copy_to_host()
+        err = np.max(np.abs(loss - ref["loss"]) / np.abs(ref["loss"]))
+        print(f"\n[S-LBFGS configs[3] {prec} M={M}] per-epoch loss {loss} vs oracle {ref['loss']}: max rel {err:.2e}; "
+              f"||g|| {gn} vs {ref['gnorm']}; launches {s.last_launches_}")
+        assert loss.size == epochs
+        assert err <= rtol, (M, loss, ref["loss"])
+        assert np.allclose(gn, ref["gnorm"], rtol=10 * rtol), (gn, ref["gnorm"])
 
 
 def test_launcher_end_to_end(handle, oracle, tmp_path):
