@@ -48,6 +48,7 @@ struct Dw16Params {
   const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
   int spec;
   long long *dbg;
+  const float *rowscale;  // FOLD: [128] 1 / t_f of the activation pair
 };
 
 template <int NB> struct DPlan { // NB = 2 * out rounded up to 128 / 256: width of [delta_hi | delta_lo]
@@ -74,7 +75,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
 // (64 elements further along M / N) at LBO = one [32 K-rows][128 B] box = 4096 B
 __device__ __forceinline__ uint64_t desc_mn16(uint32_t saddr) { return make_desc(saddr, kDAtom, 1024, 2); }
 
-template <int NB>
+// FOLD (hidden layer 1, b200_net::Mid16): the A operand is an activation PAIR — M tile 0 holds the hi halves of the 128
+// features, tile 1 their lo halves — so the two accumulators of a CTA are two terms of the same product and the epilogue adds
+// them (with the hi | lo column halves of the delta pair: four terms), scales row f by 1 / (t_f S) and writes ONE 128-row tile.
+template <int NB, bool FOLD>
 __global__ void __launch_bounds__(kDThreads, 1)
 dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmOut,
             const Dw16Params p) {
@@ -189,15 +193,25 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     // tile store {output, feature, split}: full lines, and rows past feature `in` are clipped by the tensor map.
     const uint32_t stage_a = base + (warp - 4) * 4096;
     uint8_t *stage_p = bp + (warp - 4) * 4096;
-    for (int t2 = 0; t2 < nmt; ++t2) {
+    for (int t2 = 0; t2 < (FOLD ? 1 : nmt); ++t2) {
       const int row = (warp & 3) * 32 + lane, f = m0 + t2 * kDM + row;
-      const float scale = (f < p.in_dim) ? sinv * (1.0f / 255.0f) : sinv;
+      const float scale = FOLD ? sinv * __ldg(p.rowscale + row) : ((f < p.in_dim) ? sinv * (1.0f / 255.0f) : sinv);
       const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t2 * NB);
       for (int c0 = 0; c0 < OUT; c0 += 32) {
         uint32_t v[32], w[32];
         if (nkb > 0) {
           tmem_ld32(lane_addr + c0, v);
           tmem_ld32(lane_addr + NB / 2 + c0, w);
+          if (FOLD) { // + the lo-feature tile's two column halves
+            uint32_t v2[32], w2[32];
+            tmem_ld32(lane_addr + NB + c0, v2);
+            tmem_ld32(lane_addr + NB + NB / 2 + c0, w2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+              w[j] = __float_as_uint(__uint_as_float(w[j]) + __uint_as_float(w2[j]));
+            }
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = 0u; w[j] = 0u; }
@@ -312,9 +326,9 @@ int make_map_3d_d(CUtensorMap *tm, const float *ptr, unsigned long long dim0, un
   return B200_OK;
 }
 
-template <int NB>
+template <int NB, bool FOLD>
 int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap &tout, const Dw16Params &p, dim3 grid, cudaStream_t st) {
-  auto kern = dw16_kernel<NB>;
+  auto kern = dw16_kernel<NB, FOLD>;
   constexpr int smem = DPlan<NB>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
@@ -388,10 +402,47 @@ int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done) {
   p.spec_st = net->spec_st; p.spec = net->spec_flag;
   const dim3 grid(ceil_div(K0 + 1, kDMT * kDM), splits);
   B200_TRY(make_map_3d_d(&tout, p.partial, N0, K0 + 1, splits, 32, 32));
-  if (N0 == 128) B200_TRY(launch_dw16<256>(tx, td, tout, p, grid, net->ctx->stream));
-  else B200_TRY(launch_dw16<128>(tx, td, tout, p, grid, net->ctx->stream));
+  if (N0 == 128) B200_TRY((launch_dw16<256, false>(tx, td, tout, p, grid, net->ctx->stream)));
+  else B200_TRY((launch_dw16<128, false>(tx, td, tout, p, grid, net->ctx->stream)));
   net->splits_used[0] = splits;
   *done = true;
+  return B200_OK;
+}
+
+// split plan of the mid16 dW: ONE group of two M tiles (hi / lo of the 128 features), so up to one split per SM
+int mid16_dw_plan(const b200_net *net, long batch, int *splits) {
+  const int kblocks = ceil_div(batch, kDK);
+  const int s = std::max(1, std::min(net->ctx->num_sms, kblocks));
+  const int per = ceil_div(kblocks, s);
+  *splits = ceil_div(kblocks, per);
+  return per;
+}
+
+// mid16: dW_1 partials = A_1^T delta_1 from the two fp16 pairs (b200_net::Mid16); the bias gradient comes from the last-layer
+// backward kernel's column sums (db_part)
+int mid16_dw_layer1(b200_net *net, long batch) {
+  b200_net::Mid16 &m = net->m16;
+  const int K1 = net->dims[1], N1 = net->dims[2];
+  CUtensorMap tx, td, tout;
+  B200_TRY(make_map_3d_h(&tx, m.a16, 64, (unsigned long long)batch, (unsigned long long)(2 * K1 / 64), 64, kDK));
+  B200_TRY(make_map_2d_d(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, m.d16, 2 * N1, batch, (unsigned long long)2 * N1 * 2, 64, kDK,
+                         CU_TENSOR_MAP_SWIZZLE_128B));
+  int splits = 1;
+  const int per = mid16_dw_plan(net, batch, &splits);
+  Dw16Params p{};
+  p.in_dim = 2 * K1 - 1; p.out_dim = N1; // (in_dim + 1 = the 256 rows of the pair: both M tiles hold features)
+  p.k_blocks = ceil_div(batch, kDK); p.kb_per_split = per;
+  p.partial = net->partials + net->part_off[1];
+  p.partial_stride = (unsigned long long)(K1 + 1) * N1;
+  p.scale_inv = m.scale1_inv;
+  p.rowscale = m.tinv;
+  p.row0 = 0;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
+  const dim3 grid(1, splits);
+  B200_TRY(make_map_3d_d(&tout, p.partial, N1, K1 + 1, splits, 32, 32));
+  if (N1 == 128) B200_TRY((launch_dw16<256, true>(tx, td, tout, p, grid, net->ctx->stream)));
+  else B200_TRY((launch_dw16<128, true>(tx, td, tout, p, grid, net->ctx->stream)));
+  net->splits_used[1] = splits;
   return B200_OK;
 }
 

@@ -40,7 +40,10 @@ using namespace tcx;
 constexpr int kFM = 128;                   // samples per tile = UMMA M
 constexpr int kFK = 64;                    // K elements per stage (64 fp16 = one 128-byte swizzle row)
 constexpr int kConvBytes = kFM * kFK * 2;  // X tile: 16 KB
-constexpr int kNC = 4, kNW = 4;            // X and weight rings share one stage index, so ONE tcgen05.commit frees both
+// X and weight rings share one stage index (template parameter NS), so ONE tcgen05.commit frees both
+enum { EPI_F32 = 0,     // activations as fp32 rows (layer 0 of a two-layer net, layer 1 of a three-layer net)
+       EPI_EMIT16 = 1,  // activations ONLY as the per-feature-scaled fp16 pair, block-major (b200_net::Mid16::a16)
+       EPI_DX = 2 };    // dX role: A = delta pair, B = W^T; epilogue: * act'(A_prev) from the pair, emits delta_prev's fp16 pair
 constexpr int kFThreads = 384;            // warps 0-3: X TMA, MMA issue, TMEM alloc, weight TMA; warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
 constexpr int kStageOutBytes = 32 * 128;      // per epilogue warp: one [32 rows][32 floats] TMA-store box
@@ -56,18 +59,27 @@ struct F16Params {
   const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
   int spec;
   long long *dbg;        // B200_TC_TIMING: per CTA {total, epilogue busy, epilogue waiting for the accumulator, issuer waiting}
+  int x_block_first;     // coordinates of the A-operand map are {0, block, row} instead of {0, row, block} (row-major pair rows)
+  // EPI_EMIT16
+  const float *tscale;   // [N]: t_f
+  int nb_out;            // blocks of 64 features of the output pair (the lo blocks start at nb_out)
+  // EPI_DX
+  const float *scale_in_inv; // device scalar: 1 / scale of the A operand (delta pair)
+  const float *scale_out;    // device scalar: scale of the emitted pair
 };
 
-static_assert(kNC == kNW, "the X and weight rings share their empty barriers");
-template <int BN, bool X2> struct FPlan {
+template <int BN, bool X2, int EPI, int NS> struct FPlan {
   static constexpr int kWStage = BN * 128 * (X2 ? 2 : 1);
   static constexpr int kOffConv = 0;
-  static constexpr int kOffW = kNC * kConvBytes;
-  static constexpr int kOffOut = kOffW + kNW * kWStage; // epilogue staging tiles (TMA store), 1024-byte aligned
-  static constexpr int kOffCol = kOffOut + 8 * kStageOutBytes; // colscale[128], bias[128]
+  static constexpr int kOffW = NS * kConvBytes;
+  static constexpr int kOffOut = kOffW + NS * kWStage; // epilogue staging tiles (TMA store), 1024-byte aligned
+  static constexpr int kAuxTile = (BN / 64) * kConvBytes; // EPI_DX: hi blocks of the previous layer's activation pair, [128 rows][64] each
+  static constexpr int kOffAux = kOffOut + 8 * kStageOutBytes;
+  static constexpr int kOffCol = kOffAux + (EPI == EPI_DX ? 2 * kAuxTile : 0); // colscale[128], bias[128]
   static constexpr int kOffBar = kOffCol + 1024;
   static constexpr int kTotal = kOffBar + 256 + 1024;
   static constexpr int kTmemCols = (4 * BN <= 256) ? 256 : 512;
+  static_assert(kTotal <= 227 * 1024, "shared memory plan exceeds the SM");
 };
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -106,12 +118,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BN, bool X2>
+template <int BN, bool X2, int EPI, int NS>
 __global__ void __launch_bounds__(kFThreads, 1)
 fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
-             const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmOut, const F16Params p) {
+             const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmOut,
+             const __grid_constant__ CUtensorMap tmAux, const F16Params p) {
   if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
-  using Plan = FPlan<BN, X2>;
+  using Plan = FPlan<BN, X2, EPI, NS>;
+  constexpr int kNC = NS, kNW = NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
@@ -124,7 +138,10 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   auto w_empty = [&](int s) { return conv_empty(s); }; // shared: the MMA warp's single commit per K block releases both tiles
   auto tm_full = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + b); };
   auto tm_empty = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + 2 + b); };
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kNC + 2 * kNW + 4));
+  auto aux_full = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + 4 + b); };
+  auto aux_empty = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + 6 + b); };
+  auto aux_a = [&](int b) { return base + Plan::kOffAux + b * Plan::kAuxTile; };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * kNC + 2 * kNW + 8));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = p.dbg ? clock64() : 0;
@@ -136,7 +153,11 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     if (X2) tma_prefetch_desc(&tmWl);
     for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), 1); mbar_init(conv_empty(s), 1); }
     for (int s = 0; s < kNW; ++s) mbar_init(w_full(s), 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), kEpiThreads / 32); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), kEpiThreads / 32);
+      mbar_init(aux_full(b), 1); mbar_init(aux_empty(b), kEpiThreads / 32);
+    }
+    if (EPI == EPI_DX) tma_prefetch_desc(&tmAux);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -147,8 +168,10 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   }
   float *colsc = reinterpret_cast<float *>(bp + Plan::kOffCol), *biass = colsc + 128;
   for (int i = threadIdx.x; i < 128; i += kFThreads) {
-    colsc[i] = (i < p.cols_valid) ? __ldg(p.colscale + i) : 0.0f;
-    biass[i] = (i < p.cols_valid) ? __ldg(p.bias + i) : 0.0f;
+    // EMIT16 (ReLU / Linear only): t_f act(z) = act(t_f z) for t_f > 0, so the pair's scale is folded into colscale and bias
+    const float t = (EPI == EPI_EMIT16 && i < p.cols_valid) ? __ldg(p.tscale + i) : 1.0f;
+    colsc[i] = (i < p.cols_valid) ? __ldg(p.colscale + i) * t : 0.0f;
+    biass[i] = (i < p.cols_valid && EPI != EPI_DX) ? __ldg(p.bias + i) * t : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -160,11 +183,20 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     if (lane == 0) { // ===== X producer: fp16 rows straight from HBM into the K-major SWIZZLE_128B operand tile ===========
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        if (EPI == EPI_DX) { // the hi blocks of A_prev's pair for this tile's act' (double-buffered like the accumulators)
+          const int buf = it & 1;
+          mbar_wait(aux_empty(buf), ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(aux_full(buf), Plan::kAuxTile);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b) tma_load_3d(aux_a(buf) + b * kConvBytes, &tmAux, aux_full(buf), 0, p.row0 + tile * kFM, b);
+        }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(conv_empty(s), ph ^ 1);
           mbar_expect_tx(conv_full(s), kConvBytes);
-          tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
+          if (p.x_block_first) tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, kb, p.row0 + tile * kFM);
+          else tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
           if (++s == kNC) { s = 0; ph ^= 1; }
         }
       }
@@ -242,8 +274,11 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(tm_full(buf), (it >> 1) & 1);
         tc_fence_after();
+        if (EPI == EPI_DX) mbar_wait(aux_full(buf), (it >> 1) & 1);
         const long long t1 = p.dbg ? clock64() : 0;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
+        float s_in = 1.0f, s_out = 1.0f;
+        if (EPI == EPI_DX) { s_in = __ldg(p.scale_in_inv); s_out = __ldg(p.scale_out); }
 #pragma unroll
         for (int i = 0; i < BN / 64; ++i) {
           const int c0 = half * 32 + 64 * i;
@@ -261,27 +296,90 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
             if (lane == 0) tma_store_wait_read(); // the previous block of this warp has left the staging tile
             __syncwarp();
+            if constexpr (EPI == EPI_F32) {
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
-              const float4 s4 = colsc4[c0 / 4 + qq], b4 = bias4[c0 / 4 + qq];
-              float4 r;
-              r.x = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 0]), s4.x, b4.x));
-              r.y = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 1]), s4.y, b4.y));
-              r.z = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 2]), s4.z, b4.z));
-              r.w = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 3]), s4.w, b4.w));
-              *reinterpret_cast<float4 *>(stage_p + lane * 128 + ((qq ^ (lane & 7)) << 4)) = r;
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmOut, stage_a, c0, tile * kFM + q * 32);
-              tma_store_commit();
+              for (int qq = 0; qq < 8; ++qq) {
+                const float4 s4 = colsc4[c0 / 4 + qq], b4 = bias4[c0 / 4 + qq];
+                float4 r;
+                r.x = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 0]), s4.x, b4.x));
+                r.y = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 1]), s4.y, b4.y));
+                r.z = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 2]), s4.z, b4.z));
+                r.w = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 3]), s4.w, b4.w));
+                *reinterpret_cast<float4 *>(stage_p + lane * 128 + ((qq ^ (lane & 7)) << 4)) = r;
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmOut, stage_a, c0, tile * kFM + q * 32);
+                tma_store_commit();
+              }
+            } else {
+              // the 32 values of this thread's row as a scaled fp16 pair: hi = fp16(x), lo = fp16(x - hi). Staged as two plain
+              // [32 rows][32 halves] blocks (64-byte rows; the few bank conflicts of these 8 stores per block do not show) and
+              // stored by TMA: EMIT16 into blocks c0/64 (hi) and nb_out + c0/64 (lo) of the block-major pair, DX into columns
+              // c0 (hi) and cols + c0 (lo) of the row-major pair
+              float x[32];
+              if constexpr (EPI == EPI_EMIT16) {
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                  const float4 s4 = colsc4[c0 / 4 + qq], b4 = bias4[c0 / 4 + qq]; // (both carry t_f)
+                  x[4 * qq + 0] = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 0]), s4.x, b4.x));
+                  x[4 * qq + 1] = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 1]), s4.y, b4.y));
+                  x[4 * qq + 2] = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 2]), s4.z, b4.z));
+                  x[4 * qq + 3] = act_apply_c<ACT>(p.act, fmaf(__uint_as_float(v[4 * qq + 3]), s4.w, b4.w));
+                }
+              } else { // EPI_DX: (delta W^T) * colscale / S_in, * act'(A_prev) read from the hi block of its pair, * S_out
+                const int row = q * 32 + lane;
+                const uint8_t *ap = bp + Plan::kOffAux + buf * Plan::kAuxTile + (c0 >> 6) * kConvBytes + row * 128;
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8) {
+                  const uint4 hv = *reinterpret_cast<const uint4 *>(ap + (((((c0 & 63) >> 3) + k8) ^ (row & 7)) << 4));
+                  const __half2 *h2 = reinterpret_cast<const __half2 *>(&hv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 af = __half22float2(h2[e]);
+                    const int j = 8 * k8 + 2 * e;
+                    const float g0 = __uint_as_float(v[j]) * colsc[c0 + j] * s_in, g1 = __uint_as_float(v[j + 1]) * colsc[c0 + j + 1] * s_in;
+                    x[j] = (ACT == B200_ACT_RELU ? (af.x > 0.0f ? g0 : 0.0f) : g0) * s_out;
+                    x[j + 1] = (ACT == B200_ACT_RELU ? (af.y > 0.0f ? g1 : 0.0f) : g1) * s_out;
+                  }
+                }
+              }
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) {
+                __align__(16) __half2 hh[4], ll[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x0 = x[8 * k8 + 2 * e], x1 = x[8 * k8 + 2 * e + 1];
+                  const __half2 h = __floats2half2_rn(x0, x1);
+                  const float2 hf = __half22float2(h);
+                  hh[e] = h;
+                  ll[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                }
+                *reinterpret_cast<uint4 *>(stage_p + lane * 64 + k8 * 16) = *reinterpret_cast<const uint4 *>(hh);
+                *reinterpret_cast<uint4 *>(stage_p + 2048 + lane * 64 + k8 * 16) = *reinterpret_cast<const uint4 *>(ll);
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (EPI == EPI_EMIT16) {
+                  tma_store_3d(&tmOut, stage_a, c0 & 63, tile * kFM + q * 32, c0 >> 6);
+                  tma_store_3d(&tmOut, stage_a + 2048, c0 & 63, tile * kFM + q * 32, p.nb_out + (c0 >> 6));
+                } else {
+                  tma_store_2d(&tmOut, stage_a, c0, tile * kFM + q * 32);
+                  tma_store_2d(&tmOut, stage_a + 2048, p.cols_valid + c0, tile * kFM + q * 32);
+                }
+                tma_store_commit();
+              }
             }
           }
         }
         tc_fence_before(); // accumulator consumed: the issuer may start tile it+2 in this buffer
         __syncwarp();
-        if (lane == 0) mbar_arrive(tm_empty(buf));
+        if (lane == 0) {
+          mbar_arrive(tm_empty(buf));
+          if (EPI == EPI_DX) mbar_arrive(aux_empty(buf));
+        }
         if (p.dbg) { const long long t2 = clock64(); waiting += t1 - t0; busy += t2 - t1; }
       }
       if (lane == 0) tma_store_wait_all();
@@ -300,63 +398,121 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   }
 }
 
-// W_l [K][N] fp32 (N contiguous) -> wh, wl [N][ldk] fp16 (K contiguous) with a per-neuron power-of-two scale:
-// s_o * max_k |w| in [2^13, 2^14) (fp16 overflows at 65504); colscale[o] = pre / s_o. One CTA of 1024 threads per 8 neurons
-// (one 32-byte sector per weight row), 128 K-slices per neuron: every weight is loaded ONCE (<= 8 per thread, all in flight
-// together), kept in registers across the max reduction, split, and written out through a shared-memory transpose.
+// Operand preparation, once per evaluation. A job turns one weight matrix (elements (r, n) at W[r * sr + n * sn]: r the
+// contraction index, n the output row) into the scaled fp16 pair wh, wl [rows n][ldk] (contraction index contiguous):
+//     v = W(r, n) * rscale[r]          (rscale: 1 / t_r of the layer that produced the A operand, or none)
+//     s_n = 2^(14 - e), max_r |v| in [2^(e-1), 2^e)  =>  s_n * max |v| in [2^13, 2^14)   (fp16 overflows at 65504)
+//     hi = fp16(s_n v), lo = fp16(s_n v - hi), colscale[n] = pre / s_n; with dup = 2 the row is written twice, [v | v]: the hi
+//     and the lo blocks of a K-stacked A operand meet the same weights.
+// A job may also bound the layer's outputs for the consumer of its activations (EPI_EMIT16): bound_n = sum_r |W(r, n)| + |b_n|
+// (inputs in [0, 1]; 1 for tanh / sigmoid) and t_n = 2^(14 - ceil(log2 bound)).
+// One CTA of 1024 threads per 8 output rows (one 32-byte sector per weight row when sn == 1), 128 slices of the contraction
+// index per row: every weight is loaded ONCE (<= 8 per thread, all in flight together), kept in registers across the
+// reductions, split, and written out through a shared-memory transpose.
 constexpr int kSplitNeurons = 8, kSplitMaxK = 1024;
-__global__ void __launch_bounds__(1024) split_w16_kernel(const float *__restrict__ W, int K, int N, int ldk, float pre,
-                                                       __half *__restrict__ wh, __half *__restrict__ wlo,
-                                                       float *__restrict__ colscale, const SpecState *spec_st, int spec,
-                                                       const ChainW chain) {
+struct PrepJob {
+  const float *W;
+  int R, Nn;            // contraction length, output rows
+  long sr, sn;
+  int ldk, dup;
+  float pre;
+  const float *rscale;  // [R] or nullptr
+  __half *wh, *wl;
+  float *colscale;
+  // output bound (optional): mode 0 none, 1 = L1 bound of the pre-activation, 2 = 1 (bounded activation)
+  int bound_mode;
+  const float *bias;
+  float *tscale, *tinv;
+  int nblocks;          // CTAs of this job
+};
+__global__ void __launch_bounds__(1024) prep_w16_kernel(const PrepJob j0, const PrepJob j1, const SpecState *spec_st, int spec,
+                                                      const ChainW chain) {
   if (spec_skip(spec_st, spec)) return;
-  __shared__ float red[128][kSplitNeurons + 1];
+  __shared__ float red[128][kSplitNeurons + 1], red1[128][kSplitNeurons + 1];
   if (chain.nl > 0 && blockIdx.x >= gridDim.x - chain.nctas) { // the extra CTAs (see ChainW, network.cuh)
     chain_cw_block(chain, (int)(blockIdx.x - (gridDim.x - chain.nctas)), &red[0][0]);
     return;
   }
+  const bool second = (int)blockIdx.x >= j0.nblocks;
+  const PrepJob &j = second ? j1 : j0;
   __shared__ float sc[kSplitNeurons];
   __shared__ __align__(16) __half th[kSplitNeurons][kSplitMaxK + 8], tl[kSplitNeurons][kSplitMaxK + 8];
-  const int o = threadIdx.x & (kSplitNeurons - 1), kq = threadIdx.x / kSplitNeurons, o0 = blockIdx.x * kSplitNeurons;
-  const bool ok = o0 + o < N;
+  const int o = threadIdx.x & (kSplitNeurons - 1), kq = threadIdx.x / kSplitNeurons;
+  const int o0 = ((int)blockIdx.x - (second ? j0.nblocks : 0)) * kSplitNeurons;
+  const bool ok = o0 + o < j.Nn;
   float v[kSplitMaxK / 128];
-  float amax = 0.0f;
+  float amax = 0.0f, l1 = 0.0f;
 #pragma unroll
   for (int i = 0; i < kSplitMaxK / 128; ++i) {
     const int k = kq + 128 * i;
-    v[i] = (ok && k < K) ? __ldg(W + (size_t)k * N + o0 + o) : 0.0f;
+    v[i] = (ok && k < j.R) ? __ldg(j.W + (size_t)k * j.sr + (size_t)(o0 + o) * j.sn) : 0.0f;
   }
 #pragma unroll
-  for (int i = 0; i < kSplitMaxK / 128; ++i) amax = fmaxf(amax, fabsf(v[i]));
+  for (int i = 0; i < kSplitMaxK / 128; ++i) {
+    l1 += fabsf(v[i]);
+    if (j.rscale) { const int k = kq + 128 * i; v[i] *= (k < j.R) ? __ldg(j.rscale + k) : 0.0f; }
+    amax = fmaxf(amax, fabsf(v[i]));
+  }
   red[kq][o] = amax;
+  red1[kq][o] = l1;
   __syncthreads();
   if (threadIdx.x < kSplitNeurons) {
-    float m = 0.0f;
-    for (int i = 0; i < 128; ++i) m = fmaxf(m, red[i][threadIdx.x]);
+    float m = 0.0f, b1 = 0.0f;
+    for (int i = 0; i < 128; ++i) { m = fmaxf(m, red[i][threadIdx.x]); b1 += red1[i][threadIdx.x]; }
     int e = 0;
     if (m > 0.0f && m < 3.0e38f) frexpf(m, &e); // m = f * 2^e, f in [0.5, 1)
     e = max(-100, min(100, e));
     sc[threadIdx.x] = ldexpf(1.0f, 14 - e);      // s * m in [2^13, 2^14)
-    if (o0 + threadIdx.x < N) colscale[o0 + threadIdx.x] = pre * ldexpf(1.0f, e - 14);
+    const int n = o0 + threadIdx.x;
+    if (n < j.Nn) {
+      j.colscale[n] = j.pre * ldexpf(1.0f, e - 14);
+      if (j.bound_mode) {
+        float bound = 1.0f;
+        if (j.bound_mode == 1) bound = b1 * 1.0001f + fabsf(__ldg(j.bias + n)) + 1e-30f; // (fp32 summation slack)
+        int eb = 0;
+        frexpf(bound, &eb);
+        eb = max(-100, min(100, eb));
+        j.tscale[n] = ldexpf(1.0f, 14 - eb);
+        j.tinv[n] = ldexpf(1.0f, eb - 14);
+      }
+    }
   }
   __syncthreads();
   const float s = sc[o];
 #pragma unroll
   for (int i = 0; i < kSplitMaxK / 128; ++i) {
     const int k = kq + 128 * i;
-    const float x = v[i] * s;
-    const __half h = __float2half_rn(x);
-    th[o][k] = h;
-    tl[o][k] = __float2half_rn(x - __half2float(h));
+    if (k < j.R) {
+      const float x = v[i] * s;
+      const __half h = __float2half_rn(x);
+      const __half l = __float2half_rn(x - __half2float(h));
+      th[o][k] = h;
+      tl[o][k] = l;
+      if (j.dup == 2) { th[o][j.R + k] = h; tl[o][j.R + k] = l; }
+    }
   }
+  for (int k = j.dup * j.R + kq; k < j.ldk; k += 128) { th[o][k] = __float2half_rn(0.0f); tl[o][k] = __float2half_rn(0.0f); } // row padding
   __syncthreads();
-  const int vec_per_row = ldk / 8; // ldk is a multiple of 8: 16-byte stores
+  const int vec_per_row = j.ldk / 8; // ldk is a multiple of 8: 16-byte stores
   for (int idx = threadIdx.x; idx < kSplitNeurons * vec_per_row; idx += 1024) {
     const int oo = idx / vec_per_row, kv = idx - oo * vec_per_row;
-    if (o0 + oo < N) {
-      *reinterpret_cast<uint4 *>(wh + (size_t)(o0 + oo) * ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&th[oo][8 * kv]);
-      *reinterpret_cast<uint4 *>(wlo + (size_t)(o0 + oo) * ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&tl[oo][8 * kv]);
+    if (o0 + oo < j.Nn) {
+      *reinterpret_cast<uint4 *>(j.wh + (size_t)(o0 + oo) * j.ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&th[oo][8 * kv]);
+      *reinterpret_cast<uint4 *>(j.wl + (size_t)(o0 + oo) * j.ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&tl[oo][8 * kv]);
     }
+  }
+}
+
+// fp32 A_1 from its fp16 pair (debug read-back of a hidden activation that only exists as the pair)
+__global__ void __launch_bounds__(256) pair_to_f32_kernel(const __half *__restrict__ a16, long rows, int width, const float *__restrict__ tinv,
+                                                          float *__restrict__ out) {
+  const int nb = width / 64;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * width; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / width;
+    const int f = (int)(i - r * width);
+    const float hi = __half2float(a16[((long)(f >> 6) * rows + r) * 64 + (f & 63)]);
+    const float lo = __half2float(a16[((long)(nb + (f >> 6)) * rows + r) * 64 + (f & 63)]);
+    out[i] = (hi + lo) * tinv[f];
   }
 }
 
@@ -364,18 +520,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsigned long long dim0, unsigned long long dim1,
-                unsigned long long stride_bytes, unsigned box0, unsigned box1, CUtensorMapSwizzle sw) {
+EncodeTiledFn encode_tiled() {
   static EncodeTiledFn fn = [] {
     void *f = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
     return (EncodeTiledFn)f;
   }();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return B200_ERR_CUDA;
-  }
+  if (!fn) set_error("cuTensorMapEncodeTiled is not available from the driver");
+  return fn;
+}
+
+int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsigned long long dim0, unsigned long long dim1,
+                unsigned long long stride_bytes, unsigned box0, unsigned box1, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return B200_ERR_CUDA;
   cuuint64_t dims[2] = {dim0, dim1};
   cuuint64_t strides[1] = {stride_bytes};
   cuuint32_t box[2] = {box0, box1};
@@ -390,34 +549,36 @@ int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsign
   return B200_OK;
 }
 
-// fp16 {dim0 contiguous, dim1, dim2} with dense strides, box {box0, box1, 1}, SWIZZLE_128B (the block-major fp16 input copy)
-int make_map_3d(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
-                unsigned box0, unsigned box1) {
-  void *fp = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return B200_ERR_CUDA;
-  }
+// fp16 {dim0 contiguous, dim1, dim2}, strides in bytes for dim1 / dim2, box {box0, box1, box2}
+int make_map_3d_ex(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
+                   unsigned long long stride1, unsigned long long stride2, unsigned box0, unsigned box1, unsigned box2,
+                   CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return B200_ERR_CUDA;
   cuuint64_t dims[3] = {dim0, dim1, dim2};
-  cuuint64_t strides[2] = {dim0 * 2, dim0 * dim1 * 2};
-  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint64_t strides[2] = {stride1, stride2};
+  cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = ((EncodeTiledFn)fp)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
-                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(3d fp16) failed (%d): dims %llu x %llu x %llu ptr %p", (int)r, dim0, dim1, dim2, ptr);
+    set_error("cuTensorMapEncodeTiled(3d fp16) failed (%d): dims %llu x %llu x %llu strides %llu, %llu ptr %p", (int)r, dim0, dim1, dim2,
+              stride1, stride2, ptr);
     return B200_ERR_CUDA;
   }
   return B200_OK;
 }
+// the block-major fp16 copies [blocks][rows][64]: dense strides, box {box0, box1, 1}
+int make_map_3d(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
+                unsigned box0, unsigned box1, CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
+  return make_map_3d_ex(tm, ptr, dim0, dim1, dim2, dim0 * 2, dim0 * dim1 * 2, box0, box1, 1, sw);
+}
 
-template <int BN, bool X2>
-int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const CUtensorMap &tout, const F16Params &p, int grid,
-                 cudaStream_t st) {
-  auto kern = fwd16_kernel<BN, X2>;
-  constexpr int smem = FPlan<BN, X2>::kTotal;
+template <int BN, bool X2, int EPI, int NS>
+int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const CUtensorMap &tout, const CUtensorMap &taux,
+                 const F16Params &p, int grid, cudaStream_t st) {
+  auto kern = fwd16_kernel<BN, X2, EPI, NS>;
+  constexpr int smem = FPlan<BN, X2, EPI, NS>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -431,7 +592,7 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
     B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * 1024, st));
     pp.dbg = dbg;
   }
-  kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, tout, pp);
+  kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, tout, taux, pp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) {
@@ -441,8 +602,8 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < grid; ++i)
       for (int j = 0; j < 8; ++j) a[j] += (double)h[8 * i + j] / grid;
-    fprintf(stderr, "[fwd16 timing] BN %d x2 %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: X %.0f, "
-            "weights %.0f, tmem %.0f\n", BN, (int)X2, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5]);
+    fprintf(stderr, "[fwd16 timing] BN %d x2 %d epi %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: X %.0f, "
+            "weights %.0f, tmem %.0f\n", BN, (int)X2, EPI, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5]);
   }
   return B200_OK;
 }
@@ -459,8 +620,65 @@ static bool fwd16_shape_ok(const b200_net *net) {
   return net->nlayers() >= 2 && net->prec != B200_PREC_FP32 && K % 16 == 0 && K <= kSplitMaxK && N % 32 == 0 && N <= 128;
 }
 
+// ---- hidden layer 1 of a three-layer net on the fp16 kernels (b200_net::Mid16) ----------------------------------------------
+bool mid16_applicable(const b200_net *net) {
+  if (env().mid16 == 0 || env().fwd16 == 0 || env().dw16 == 0 || env().tail == 0) return false;
+  if (net->nlayers() != 3 || net->prec != B200_PREC_TF32X3) return false;
+  const int N0 = net->dims[1], N1 = net->dims[2];
+  // A_1's act' is read back from the hi half of its pair: exact for ReLU / Linear only (the sign of a, or nothing)
+  const bool act0_ok = net->acts[0] == B200_ACT_RELU || net->acts[0] == B200_ACT_LINEAR;
+  // (N0 == 128: the hi and the lo halves of A_1's pair are exactly the two M tiles of a dW CTA)
+  return fwd16_shape_ok(net) && dw16_applicable(net) && tail_applicable(net) && act0_ok && N0 == 128 && (N1 == 64 || N1 == 128);
+}
+
+int mid16_ensure(b200_net *net, long batch) {
+  b200_net::Mid16 &m = net->m16;
+  const int N0 = net->dims[1], N1 = net->dims[2];
+  if (!m.tscale) {
+    B200_CUDA(cudaMalloc(&m.tscale, sizeof(float) * (2 * N0 + N1 + N0 + 4)));
+    m.tinv = m.tscale + N0;
+    m.colscale_f = m.tinv + N0;
+    m.colscale_d = m.colscale_f + N1;
+    m.scale1_inv = m.colscale_d + N0;
+    B200_CUDA(cudaMalloc(&m.wfh, sizeof(__half) * (size_t)N1 * 2 * N0));
+    B200_CUDA(cudaMalloc(&m.wfl, sizeof(__half) * (size_t)N1 * 2 * N0));
+    B200_CUDA(cudaMalloc(&m.wdh, sizeof(__half) * (size_t)N0 * 2 * N1));
+    B200_CUDA(cudaMalloc(&m.wdl, sizeof(__half) * (size_t)N0 * 2 * N1));
+    B200_CUDA(cudaMalloc(&m.db_part, sizeof(float) * (size_t)2 * net->ctx->num_sms * N1));
+    ++net->config_gen;
+  }
+  if (m.a16_rows < net->cap || m.d16_rows < net->cap) {
+    if (m.a16) cudaFree(m.a16);
+    if (m.d16) cudaFree(m.d16);
+    m.a16 = m.d16 = nullptr;
+    B200_CUDA(cudaMalloc(&m.a16, sizeof(__half) * 2 * (size_t)N0 * net->cap));
+    B200_CUDA(cudaMalloc(&m.d16, sizeof(__half) * 2 * (size_t)N1 * net->cap));
+    m.a16_rows = m.d16_rows = net->cap;
+    ++net->config_gen;
+  }
+  (void)batch;
+  return B200_OK;
+}
+
+void mid16_release(b200_net *net) {
+  b200_net::Mid16 &m = net->m16;
+  for (void *p : {(void *)m.tscale, m.wfh, m.wfl, m.wdh, m.wdl, (void *)m.db_part, m.a16, m.d16})
+    if (p) cudaFree(p);
+  m = b200_net::Mid16{};
+}
+
+int mid16_reconstruct_act0(b200_net *net) {
+  b200_net::Mid16 &m = net->m16;
+  if (!m.act0_stale || !m.a16 || net->last_batch <= 0) return B200_OK;
+  const long total = net->last_batch * net->dims[1];
+  B200_LAUNCH(pair_to_f32_kernel, (int)std::min<long>(1184, (total + 255) / 256), 256, 0, net->ctx->stream, (const __half *)m.a16,
+              net->last_batch, net->dims[1], m.tinv, net->act[0]);
+  m.act0_stale = false;
+  return B200_OK;
+}
+
 // Per evaluation, before the forward sweep: the scaled fp16 {hi, lo} split of W_0 (its own launch, so that it is timed and
-// profiled apart from the GEMM). No-op when the fp16 forward does not apply.
+// profiled apart from the GEMM) and, on the mid16 path, the operands of layer 1. No-op when the fp16 forward does not apply.
 int fwd16_prepare(b200_net *net, const float *params) {
   net->w16_params = nullptr;
   net->chain_ready = false;
@@ -479,9 +697,41 @@ int fwd16_prepare(b200_net *net, const float *params) {
     tail_chain_fill(net, params, &chain);
     net->chain_ready = true;
   }
-  ProfScope ps(net->ctx, "split16");
-  B200_LAUNCH(split_w16_kernel, ceil_div(N, kSplitNeurons) + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, params + net->offs[0], K, N,
-              ldk, 1.0f / 255.0f, (__half *)net->w16h, (__half *)net->w16l, net->colscale, net->spec_st, net->spec_flag, chain);
+  const float *W0 = params + net->offs[0];
+  PrepJob j0{};
+  j0.W = W0; j0.R = K; j0.Nn = N; j0.sr = N; j0.sn = 1; j0.ldk = ldk; j0.dup = 1; j0.pre = 1.0f / 255.0f;
+  j0.wh = (__half *)net->w16h; j0.wl = (__half *)net->w16l; j0.colscale = net->colscale;
+  j0.nblocks = ceil_div(N, kSplitNeurons);
+  PrepJob j1{}; // (no CTAs)
+  const bool mid = net->m16.on;
+  if (mid) {
+    b200_net::Mid16 &m = net->m16;
+    const int N1 = net->dims[2];
+    const float *W1 = params + net->offs[1];
+    const bool bounded = net->acts[0] == B200_ACT_TANH || net->acts[0] == B200_ACT_SIGMOID;
+    j0.bound_mode = bounded ? 2 : 1;
+    j0.bias = W0 + (size_t)K * N; j0.tscale = m.tscale; j0.tinv = m.tinv;
+    // dX operand of layer 1: rows = layer-1 inputs f, contraction over its outputs o (W_1 is [f][o], o contiguous)
+    j1.W = W1; j1.R = N1; j1.Nn = N; j1.sr = 1; j1.sn = N1; j1.ldk = 2 * N1; j1.dup = 2; j1.pre = 1.0f;
+    j1.wh = (__half *)m.wdh; j1.wl = (__half *)m.wdl; j1.colscale = m.colscale_d;
+    j1.nblocks = ceil_div(N, kSplitNeurons);
+  }
+  {
+    ProfScope ps(net->ctx, "split16");
+    B200_LAUNCH(prep_w16_kernel, j0.nblocks + j1.nblocks + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, j0, j1,
+                net->spec_st, net->spec_flag, chain);
+    if (mid) { // forward operand of layer 1: needs 1 / t_k of layer 0's outputs, written by the launch above
+      b200_net::Mid16 &m = net->m16;
+      const int N1 = net->dims[2];
+      PrepJob f{};
+      f.W = params + net->offs[1]; f.R = N; f.Nn = N1; f.sr = N1; f.sn = 1; f.ldk = 2 * N; f.dup = 2; f.pre = 1.0f;
+      f.rscale = m.tinv; f.wh = (__half *)m.wfh; f.wl = (__half *)m.wfl; f.colscale = m.colscale_f;
+      f.nblocks = ceil_div(N1, kSplitNeurons);
+      PrepJob none{};
+      ChainW nochain{};
+      B200_LAUNCH(prep_w16_kernel, f.nblocks, 1024, 0, net->ctx->stream, f, none, net->spec_st, net->spec_flag, nochain);
+    }
+  }
   net->w16_params = params;
   return B200_OK;
 }
@@ -493,6 +743,7 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View
   if (net->w16_params != params) B200_TRY(fwd16_prepare(net, params)); // callers normally prepare before the sweep
   const int K = net->dims[0], N = net->dims[1];
   const bool x2 = net->prec == B200_PREC_TF32X3;
+  const bool emit16 = net->m16.on; // A_1 leaves only as the scaled fp16 pair (layer 1 runs on the fp16 kernels)
   const int ldk = (K + 7) & ~7;
   cudaStream_t st = net->ctx->stream;
   const float *W = params + net->offs[0];
@@ -504,8 +755,11 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View
                        CU_TENSOR_MAP_SWIZZLE_128B));
   B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->w16l, ldk, N, (unsigned long long)ldk * 2, kFK, bn,
                        CU_TENSOR_MAP_SWIZZLE_128B));
-  B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, net->act[0], N, batch, (unsigned long long)N * 4, 32, 32,
-                       CU_TENSOR_MAP_SWIZZLE_128B)); // activations [batch][N], stored as [32 rows][32 floats] boxes
+  if (emit16) // the pair [2 N / 64 blocks][batch][64]: stored as plain {32 halves, 32 rows} boxes
+    B200_TRY(make_map_3d(&tout, net->m16.a16, 64, (unsigned long long)batch, (unsigned long long)(2 * N / 64), 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  else
+    B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, net->act[0], N, batch, (unsigned long long)N * 4, 32, 32,
+                         CU_TENSOR_MAP_SWIZZLE_128B)); // activations [batch][N], stored as [32 rows][32 floats] boxes
   F16Params p{};
   p.rows_valid = (int)batch; p.cols_valid = N; p.k_total = K;
   p.row0 = (int)x16.row0;
@@ -516,15 +770,83 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View
   p.colscale = net->colscale;
   p.out = net->act[0]; p.ld_out = N;
   p.spec_st = net->spec_st; p.spec = net->spec_flag;
+  p.tscale = net->m16.tscale; p.nb_out = N / 64;
   const int grid = std::min(net->ctx->num_sms, p.tiles);
-  if (bn == 128) {
-    if (x2) B200_TRY((launch_fwd16<128, true>(tx, twh, twl, tout, p, grid, st)));
-    else B200_TRY((launch_fwd16<128, false>(tx, twh, twl, tout, p, grid, st)));
+  if (emit16) {
+    if (bn == 128) B200_TRY((launch_fwd16<128, true, EPI_EMIT16, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+    else B200_TRY((launch_fwd16<64, true, EPI_EMIT16, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+    net->m16.act0_stale = true;
+  } else if (bn == 128) {
+    if (x2) B200_TRY((launch_fwd16<128, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+    else B200_TRY((launch_fwd16<128, false, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
   } else {
-    if (x2) B200_TRY((launch_fwd16<64, true>(tx, twh, twl, tout, p, grid, st)));
-    else B200_TRY((launch_fwd16<64, false>(tx, twh, twl, tout, p, grid, st)));
+    if (x2) B200_TRY((launch_fwd16<64, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+    else B200_TRY((launch_fwd16<64, false, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
   }
   *done = true;
+  return B200_OK;
+}
+
+// mid16: A_2 = act(A_1 W_1 + b_1) with A_1 as its fp16 pair: the layer-0 kernel on that copy, K = 2 * width (hi blocks, then lo
+// blocks, against weight rows written twice). Output fp32 rows (the last-layer kernels read them).
+int mid16_forward_layer1(b200_net *net, const float *params, long batch) {
+  b200_net::Mid16 &m = net->m16;
+  const int K = net->dims[1], N = net->dims[2];
+  cudaStream_t st = net->ctx->stream;
+  const float *W = params + net->offs[1];
+  CUtensorMap tx, twh, twl, tout;
+  B200_TRY(make_map_3d(&tx, m.a16, 64, (unsigned long long)batch, (unsigned long long)(2 * K / 64), 64, kFM));
+  const unsigned bn = N > 64 ? 128 : 64;
+  B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, m.wfh, 2 * K, N, (unsigned long long)2 * K * 2, kFK, bn, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, m.wfl, 2 * K, N, (unsigned long long)2 * K * 2, kFK, bn, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, net->act[1], N, batch, (unsigned long long)N * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  F16Params p{};
+  p.rows_valid = (int)batch; p.cols_valid = N; p.k_total = 2 * K;
+  p.row0 = 0;
+  p.k_blocks = 2 * K / kFK;
+  p.tiles = ceil_div(batch, kFM);
+  p.act = net->acts[1];
+  p.bias = W + (size_t)K * N;
+  p.colscale = m.colscale_f;
+  p.out = net->act[1]; p.ld_out = N;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
+  const int grid = std::min(net->ctx->num_sms, p.tiles);
+  if (bn == 128) B200_TRY((launch_fwd16<128, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+  else B200_TRY((launch_fwd16<64, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+  return B200_OK;
+}
+
+// mid16: delta_0 = (delta_1 W_1^T) .* act_0'(A_1), both deltas as scaled fp16 pairs: A = delta_1's pair [rows][hi N1 | lo N1]
+// (two "blocks" of a row), B = W_1^T rows written twice, act' from the hi blocks of A_1's pair, output = delta_0's pair
+// [rows][hi N0 | lo N0] in net->delta16 with the chained scale (tail_layer.cu) for layer 0's dW kernel.
+int mid16_dx_layer1(b200_net *net, long batch) {
+  b200_net::Mid16 &m = net->m16;
+  const int N0 = net->dims[1], N1 = net->dims[2];
+  cudaStream_t st = net->ctx->stream;
+  CUtensorMap tx, twh, twl, tout, taux;
+  // dims ordered so that the strides ascend: {64 halves, N1 / 64 * 2 blocks (128 B apart), rows (2 N1 halves apart)}
+  B200_TRY(make_map_3d_ex(&tx, m.d16, 64, (unsigned long long)(2 * N1 / 64), (unsigned long long)batch, 128, (unsigned long long)2 * N1 * 2,
+                          64, 1, kFM, CU_TENSOR_MAP_SWIZZLE_128B));
+  const unsigned bn = N0 > 64 ? 128 : 64;
+  B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, m.wdh, 2 * N1, N0, (unsigned long long)2 * N1 * 2, kFK, bn, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, m.wdl, 2 * N1, N0, (unsigned long long)2 * N1 * 2, kFK, bn, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->delta16, 2 * N0, batch, (unsigned long long)2 * N0 * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  B200_TRY(make_map_3d(&taux, m.a16, 64, (unsigned long long)batch, (unsigned long long)(2 * N0 / 64), 64, kFM));
+  F16Params p{};
+  p.rows_valid = (int)batch; p.cols_valid = N0; p.k_total = 2 * N1;
+  p.row0 = 0;
+  p.k_blocks = 2 * N1 / kFK;
+  p.tiles = ceil_div(batch, kFM);
+  p.act = net->acts[0];
+  p.colscale = m.colscale_d;
+  p.bias = m.colscale_d; // (unused by this epilogue)
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
+  p.x_block_first = 1;
+  p.scale_in_inv = m.scale1_inv;
+  p.scale_out = net->scale16;
+  const int grid = std::min(net->ctx->num_sms, p.tiles);
+  if (bn == 128) B200_TRY((launch_fwd16<128, true, EPI_DX, 2>(tx, twh, twl, tout, taux, p, grid, st)));
+  else B200_TRY((launch_fwd16<64, true, EPI_DX, 2>(tx, twh, twl, tout, taux, p, grid, st)));
   return B200_OK;
 }
 
@@ -534,6 +856,7 @@ void fwd16_release(b200_net *net) {
   if (net->colscale) cudaFree(net->colscale);
   net->w16h = net->w16l = nullptr;
   net->colscale = nullptr;
+  mid16_release(net);
 }
 
 } // namespace b200

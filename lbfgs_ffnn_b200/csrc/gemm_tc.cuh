@@ -29,6 +29,11 @@ void fwd16_release(b200_net *net);
 bool dw16_applicable(const b200_net *net);
 int dw16_plan(const b200_net *net, long batch, int *splits); // K blocks per split; *splits = slices of the batch
 int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done);
+// hidden layer 1 of a three-layer net on the fp16 kernels (b200_net::Mid16): gemm_fwd16.cu / gemm_dw16.cu
+int mid16_forward_layer1(b200_net *net, const float *params, long batch);
+int mid16_dx_layer1(b200_net *net, long batch);
+int mid16_dw_layer1(b200_net *net, long batch);
+int mid16_dw_plan(const b200_net *net, long batch, int *splits);
 void tc_release(b200_net *net);
 
 // 2-D fp32 tensor map {dim0 contiguous, dim1 rows} with SWIZZLE_128B (gemm_fwd16.cu)

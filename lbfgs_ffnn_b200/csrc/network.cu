@@ -21,12 +21,15 @@ namespace {
 
 constexpr int kMaxLayers = 16;
 
+// a contiguous run of gradient elements [off, off + size) whose split-K partials are `splits` slices `stride` floats apart
+// starting at partials + part_off (a layer's [dW; db], or — when they come from different kernels — its dW and its db apart)
 struct FinLayer {
-  unsigned long long off, size, part_off;
+  unsigned long long off, size, stride;
+  const float *part; // slice 0
   int splits;
 };
 struct FinParams {
-  FinLayer L[kMaxLayers];
+  FinLayer L[2 * kMaxLayers];
   int nl;
   unsigned long long n;
   const float *partials;
@@ -84,24 +87,24 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
 #pragma unroll 1
       while (l + 1 < p.nl && j >= p.L[l + 1].off) ++l;
       const FinLayer &L = p.L[l];
-      const float *src = p.partials + L.part_off + (j - L.off);
+      const float *src = L.part + (j - L.off);
       int sp = warp;
       for (; sp + 56 < L.splits; sp += 64) {
         float t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = __ldg(src + (unsigned long long)(sp + 8 * u) * L.size);
+        for (int u = 0; u < 8; ++u) t[u] = __ldg(src + (unsigned long long)(sp + 8 * u) * L.stride);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += (double)t[u];
       }
       if (sp < L.splits && sp + 40 >= L.splits) { // at most five slices left for this warp (37-way split-K of layer 0): loads go out together
         float t[5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) t[u] = (sp + 8 * u < L.splits) ? __ldg(src + (unsigned long long)(sp + 8 * u) * L.size) : 0.0f;
+        for (int u = 0; u < 5; ++u) t[u] = (sp + 8 * u < L.splits) ? __ldg(src + (unsigned long long)(sp + 8 * u) * L.stride) : 0.0f;
 #pragma unroll
         for (int u = 0; u < 5; ++u) acc += (double)t[u];
         sp += 40;
       }
-      for (; sp < L.splits; sp += 8) acc += (double)__ldg(src + (unsigned long long)sp * L.size);
+      for (; sp < L.splits; sp += 8) acc += (double)__ldg(src + (unsigned long long)sp * L.stride);
     }
     __syncthreads();
     sh[warp][lane] = acc;
@@ -460,6 +463,7 @@ int net_ensure(b200_net *net, long batch) {
       net->skinny_splits[l] = 2 * net->ctx->num_sms;
       int s_16 = 1;
       if (l == 0) dw16_plan(net, batch, &s_16);
+      if (l == 1) mid16_dw_plan(net, batch, &s_16);
       // (the per-CTA partials of the skinny / one-pass last-layer kernels exist only for narrow layers: reserving them for a
       // 4096-wide layer would be 2 * SMs copies of a 67 MB matrix)
       const int s_skinny = (N <= 16) ? net->skinny_splits[l] : 1;
@@ -590,9 +594,15 @@ static int launch_fwd_layer(b200_net *net, int l, const float *params, const flo
 
 int net_forward(b200_net *net, const float *params, const float *x, long batch) {
   B200_TRY(net_ensure(net, batch));
-  B200_TRY(tc_split_params(net, params));
   net->w16_params = nullptr;
   net->chain_ready = false;
+  X16View xv0;
+  const bool mid = mid16_applicable(net) && net_x16_view(net, x, batch, &xv0);
+  net->m16.on = mid;
+  net->m16.act0_stale = false;
+  net->split_src = nullptr;
+  if (mid) B200_TRY(mid16_ensure(net, batch));
+  else B200_TRY(tc_split_params(net, params));
   if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
   const float *cur = x;
   for (int l = 0; l < net->nlayers(); ++l) {
@@ -600,6 +610,11 @@ int net_forward(b200_net *net, const float *params, const float *x, long batch) 
     char nm[16];
     snprintf(nm, sizeof(nm), "fwdonly%d", l);
     ProfScope ps(net->ctx, nm);
+    if (mid && l == 1) {
+      B200_TRY(mid16_forward_layer1(net, params, batch));
+      cur = net->act[1];
+      continue;
+    }
     if (net->prec != B200_PREC_FP32 && l + 1 < net->nlayers())
       B200_TRY(tc_forward_layer(net, l, params, cur, batch, nullptr, &done, nullptr));
     if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, false, nullptr, 0.f));
@@ -620,9 +635,16 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   if (batch_global <= 0) batch_global = net->batch_global > 0 ? net->batch_global : batch * ctx->world;
   const float inv_batch = 1.0f / (float)batch_global;
 
-  B200_TRY(tc_split_params(net, params));
   net->w16_params = nullptr;
   net->chain_ready = false;
+  // hidden layer 1 on the fp16 kernels (b200_net::Mid16): needs the fp16 copy of an 8-bit-pixel input for layer 0
+  X16View xv0;
+  const bool mid = mid16_applicable(net) && net_x16_view(net, x, batch, &xv0);
+  net->m16.on = mid;
+  net->m16.act0_stale = false;
+  net->split_src = nullptr;
+  if (mid) B200_TRY(mid16_ensure(net, batch));
+  else B200_TRY(tc_split_params(net, params)); // (the TF32 hi / lo split of the parameters feeds the generic kernels only)
   if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
   // forward sweep
   const float *cur = x;
@@ -634,9 +656,16 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
     if (last && fused_last) break;
+    if (mid && l == 1) {
+      ProfScope ps(ctx, "fwd1");
+      B200_TRY(mid16_forward_layer1(net, params, batch));
+      cur = net->act[1];
+      continue;
+    }
     if (last && use_tail) {
-      B200_TRY(tail_layer(net, params, t, batch, inv_batch, /*want32=*/!use_dw16 || L > 2, /*want16=*/use_dw16 && L == 2,
-                          /*chain16=*/use_dw16 && L > 2));
+      // mid: delta_1 leaves only as its fp16 pair (feeds both the dX and the dW kernel of layer 1)
+      B200_TRY(tail_layer(net, params, t, batch, inv_batch, /*want32=*/!mid && (!use_dw16 || L > 2),
+                          /*want16=*/mid || (use_dw16 && L == 2), /*chain16=*/use_dw16 && L > 2));
       tail_done = true;
       break;
     }
@@ -649,6 +678,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         const TcFuseLast fuse{t, inv_batch};
         B200_TRY(tc_forward_layer(net, l, params, cur, batch, use_tail ? nullptr : &fuse, &done, &fused_last));
       }
+      B200_REQUIRE(done || !mid, "the fp16 layer-0 kernel did not take the layer the mid16 path was planned on");
       if (!done) B200_TRY(launch_fwd_layer(net, l, params, cur, batch, last, t, inv_batch));
     }
     cur = net->act[l];
@@ -666,7 +696,12 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       snprintf(nm, sizeof(nm), "dx%d", l);
       ProfScope ps(ctx, nm);
       bool done = false;
-      if (net->prec != B200_PREC_FP32) {
+      if (mid && l == 1) {
+        B200_TRY(mid16_dx_layer1(net, batch));
+        d16_ready = true;
+        done = true;
+      }
+      if (!done && net->prec != B200_PREC_FP32) {
         bool emit16 = (l == 1 && use_dw16 && L > 2);
         B200_TRY(tc_dx_layer(net, l, params, batch, &done, &emit16));
         if (emit16) d16_ready = true;
@@ -692,6 +727,10 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       snprintf(nm, sizeof(nm), "dw%d", l);
       ProfScope ps(ctx, nm);
       bool done = false;
+      if (mid && l == 1) {
+        B200_TRY(mid16_dw_layer1(net, batch));
+        done = true;
+      }
       if (l == 0 && d16_ready) {
         X16View xv;
         if (net_x16_view(net, x, batch, &xv)) B200_TRY(dw16_layer(net, xv, batch, &done));
@@ -729,12 +768,21 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
 
   // split-K reduction straight into the caller's gradient buffer (+ L2 term, + ||g||^2 partials)
   FinParams fp{};
-  fp.nl = L;
+  fp.nl = 0;
   for (int l = 0; l < L; ++l) {
-    fp.L[l].off = net->offs[l];
-    fp.L[l].size = (unsigned long long)(net->dims[l] + 1) * net->dims[l + 1];
-    fp.L[l].part_off = net->part_off[l];
-    fp.L[l].splits = net->splits_used[l];
+    FinLayer &f = fp.L[fp.nl++];
+    f.off = net->offs[l];
+    f.size = f.stride = (unsigned long long)(net->dims[l] + 1) * net->dims[l + 1];
+    f.part = net->partials + net->part_off[l];
+    f.splits = net->splits_used[l];
+    if (l == 1 && mid) { // dW_1 from the split-K kernel, db_1 from the last-layer backward kernel's column sums
+      f.size = (unsigned long long)net->dims[1] * net->dims[2];
+      FinLayer &b = fp.L[fp.nl++];
+      b.off = f.off + f.size;
+      b.size = b.stride = (unsigned long long)net->dims[2];
+      b.part = net->m16.db_part;
+      b.splits = net->m16.db_splits;
+    }
   }
   fp.n = net->n;
   fp.partials = net->partials;
@@ -967,6 +1015,7 @@ int b200_net_copy_activation_to_host(b200_net *net, int layer, float *host, size
   B200_REQUIRE(layer >= 0 && layer < net->nlayers(), "no such layer");
   B200_REQUIRE(net->act[layer] && net->last_batch > 0, "no forward pass has run");
   B200_REQUIRE(n <= (size_t)net->dims[layer + 1] * net->last_batch, "more elements requested than the last batch produced");
+  if (layer == 0) B200_TRY(mid16_reconstruct_act0(net)); // (A_1 may exist only as its fp16 pair)
   B200_CUDA(cudaMemcpyAsync(host, net->act[layer], sizeof(float) * n, cudaMemcpyDeviceToHost, net->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(net->ctx->stream));
   return B200_OK;

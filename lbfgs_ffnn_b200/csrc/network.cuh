@@ -67,6 +67,30 @@ struct b200_net {
   void *delta16 = nullptr;
   long delta16_cap = 0;
 
+  // ---- hidden layer 1 of a three-layer net on the fp16 tensor-core kernels ("mid16", gemm_fwd16.cu / gemm_dw16.cu) -------------
+  // Layer 0's epilogue leaves A_1 ONLY as a per-feature-scaled fp16 pair, block-major like the input copy:
+  //   a16 = [2 nb][rows][64] halves, blocks 0 .. nb-1 = hi(t_f a), nb .. 2 nb-1 = lo, t_f a power of two with t_f * bound_f in
+  //   [2^13, 2^14) and bound_f = sum_k |W_0[k][f]| + |b_f| >= |a| (x in [0, 1]; 1 for tanh / sigmoid);
+  // layer 1 forward is the layer-0 kernel again on that copy (K = 2 * width: the lo blocks meet the same weights), its dW is the
+  // split-K kernel with the hi and lo feature tiles folded in the epilogue, its dX the forward kernel on delta_1's fp16 pair
+  // with an act'(A_1) epilogue that emits delta_0's pair for layer 0's dW.
+  struct Mid16 {
+    bool on = false;        // this evaluation runs the path (decided per evaluation in net_eval / net_forward)
+    void *a16 = nullptr;    // A_1 pair
+    long a16_rows = 0;
+    float *tscale = nullptr, *tinv = nullptr; // [dims[1]]: t_f and 1 / t_f
+    void *wfh = nullptr, *wfl = nullptr;      // forward operand of layer 1: [dims[2]][2 dims[1]] hi / lo of s_o W_1[k][o] / t_k
+    float *colscale_f = nullptr;              // [dims[2]]: 1 / s_o
+    void *wdh = nullptr, *wdl = nullptr;      // dX operand of layer 1: [dims[1]][2 dims[2]] hi / lo of s_k W_1[k][o]
+    float *colscale_d = nullptr;              // [dims[1]]: 1 / s_k
+    void *d16 = nullptr;    // delta_1 pair [rows][2 dims[2]] (written by the last-layer backward kernel)
+    long d16_rows = 0;
+    float *scale1_inv = nullptr; // device scalar: 1 / (scale of the delta_1 pair)
+    float *db_part = nullptr;    // [tail grid][dims[2]]: per-CTA column sums of delta_1 (= the db_1 partials)
+    int db_splits = 0;
+    bool act0_stale = false;     // act[0] (fp32) does not hold A_1 of the last evaluation: only a16 does
+  } m16;
+
   double *loss_part = nullptr; // per-CTA partials of sum diff^2
   int loss_part_cap = 0, loss_part_n = 0;
   double *fin_part = nullptr;  // per-CTA partials of ||g||^2 and ||w||^2 (2 per CTA)
@@ -121,6 +145,11 @@ bool tail_applicable(const b200_net *net);
 int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16,
                bool chain16 = false);
 bool tail_chain16_applicable(const b200_net *net);
+// hidden layer 1 on the fp16 kernels (see b200_net::Mid16): shape / mode test, buffers, per-evaluation operand preparation
+bool mid16_applicable(const b200_net *net);
+int mid16_ensure(b200_net *net, long batch);
+void mid16_release(b200_net *net);
+int mid16_reconstruct_act0(b200_net *net); // fp32 A_1 from the pair, into act[0] (debug read-back)
 int tail_ensure_scalars(b200_net *net);
 
 // Weight-dependent factor of the fp16 scale of delta_0 in a net with more than two layers: prod_{l=1..L-1} max_f ||W_l[f,:]||_1

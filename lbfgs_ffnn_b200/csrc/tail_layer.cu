@@ -29,7 +29,9 @@ struct TailParams {
   float *delta_last;   // [B][ldd]
   float *delta_prev;   // [B][in] fp32 (nullptr: not needed)
   __half *d16;         // [B][2 in] fp16 {hi | lo} of S * delta_prev (nullptr: not needed)
-  float *scale16_inv;  // device scalar 1 / S
+  float *scale16_inv;  // device scalar 1 / S of the chained delta_0 pair (deeper nets, block 0 of the backward kernel writes it)
+  float *scale_d16_inv; // device scalar 1 / S of the d16 pair this kernel writes
+  float *db_prev_part; // [grid][in] per-CTA column sums of delta_{L-1} (= the db_{L-1} partials), or nullptr
   // deeper nets: block 0 publishes S (and 1 / S) of delta_0 from max |delta_L| and the per-layer row-norm maxima (ChainW)
   const float *chain_cw;
   int chain_nl, chain_nctas;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
     if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &e);
     e = max(-100, min(100, e));
     S = ldexpf(1.0f, 14 - e);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.scale16_inv = ldexpf(1.0f, e - 14);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.scale_d16_inv = ldexpf(1.0f, e - 14);
   }
   if (p.chain_cw && blockIdx.x == 0) { // block-uniform
     float m = 0.0f;
@@ -480,6 +482,9 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
   for (int c = 0; c < FPL; ++c)
 #pragma unroll
     for (int j = 0; j < OLP; ++j) acc[c][j] = 0.0f;
+  float gsum[FPL]; // column sums of delta_{L-1} over this warp's samples (db_{L-1})
+#pragma unroll
+  for (int c = 0; c < FPL; ++c) gsum[c] = 0.0f;
 
   auto process = [&](long s, const float *arow, const float *drow) { // one sample: delta_{L-1}[s][:] and the dW update
     float a[FPL];
@@ -503,6 +508,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
       }
       const float x = xe + xo;
       g[c] = RELU ? (a[c] > 0.0f ? x : 0.0f) : x * act_deriv_from_output(p.act_prev, a[c]);
+      gsum[c] += g[c];
     }
     if (p.delta_prev) store_row<FPL>(p.delta_prev + s * IN + lane * FPL, g);
     if (p.d16) { // [s][0..IN) = hi, [s][IN..2 IN) = lo of S * delta
@@ -574,6 +580,18 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
     for (int wv = 1; wv < 4; ++wv) v += red[wv * (IN * OLP) + i * OLP + j];
     dst[e] = v;
   }
+  if (p.db_prev_part) { // per-CTA column sums of delta_{L-1}, warps combined in a fixed order
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < FPL; ++c) red[warp * IN + lane * FPL + c] = gsum[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < IN; i += blockDim.x) {
+      float v = red[i];
+#pragma unroll
+      for (int wv = 1; wv < 8; ++wv) v += red[wv * IN + i];
+      p.db_prev_part[(size_t)blockIdx.x * IN + i] = v;
+    }
+  }
 }
 
 template <int FPL, int OLP> int launch_tail_fwd2(const TailParams &p, int grid_fwd, int grid_bwd, cudaStream_t st) {
@@ -625,10 +643,11 @@ bool tail_applicable(const b200_net *net) {
 // into net->delta16 for the fp16 dW GEMM of layer L-2 (gemm_dw16.cu), with 1 / scale in net->scale16_inv.
 int tail_layer(b200_net *net, const float *params, const float *t, long batch, float inv_batch, bool want32, bool want16,
                bool chain16) {
+  const bool mid = net->m16.on; // delta_{L-1} = delta_1 leaves as its own fp16 pair (and its column sums), delta_0's scale is chained
   const int L = net->nlayers();
   const int in = net->dims[L - 1], out = net->dims[L];
   B200_TRY(tail_ensure_scalars(net));
-  if ((want16 || chain16) && net->delta16_cap < batch) {
+  if (((want16 && !mid) || chain16) && net->delta16_cap < batch) {
     if (net->delta16) cudaFree(net->delta16);
     net->delta16 = nullptr;
     B200_CUDA(cudaMalloc(&net->delta16, sizeof(__half) * 2 * (size_t)net->dims[1] * net->cap)); // rows of delta_0 (L == 2: in == dims[1])
@@ -642,8 +661,10 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   p.out_last = net->act[L - 1];
   p.delta_last = net->delta[L - 1];
   p.delta_prev = want32 ? net->delta[L - 2] : nullptr;
-  p.d16 = want16 ? (__half *)net->delta16 : nullptr;
+  p.d16 = want16 ? (__half *)(mid ? net->m16.d16 : net->delta16) : nullptr;
   p.scale16_inv = net->scale16_inv;
+  p.scale_d16_inv = mid ? net->m16.scale1_inv : net->scale16_inv;
+  p.db_prev_part = mid ? net->m16.db_part : nullptr;
   p.amax_part = net->amax_part;
   if (chain16) {
     ChainW c{};
@@ -671,6 +692,7 @@ int tail_layer(b200_net *net, const float *params, const float *t, long batch, f
   else if (in == 64) B200_TRY(launch_tail<2>(net->ctx, p, grid, grid_fwd, net->ctx->stream));
   else B200_TRY(launch_tail<1>(net->ctx, p, grid, grid_fwd, net->ctx->stream));
   net->splits_used[L - 1] = grid;
+  if (mid) net->m16.db_splits = grid;
   net->loss_part_n = fwd2 ? grid_fwd : grid;
   return B200_OK;
 }

@@ -22,7 +22,7 @@ from helpers import make_gpu_net, make_problem, relu_pattern_of, upload
 
 pytestmark = pytest.mark.gpu
 
-TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16", "B200_TAIL_FWD")
+TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16", "B200_TAIL_FWD", "B200_MID16")
 
 
 def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True, want_pattern=False):
@@ -80,7 +80,7 @@ def test_fp16_path_parity(handle, oracle, dims, acts, batch):
     assert rel_l2(out, fo) <= 2e-5, rel_l2(out, fo)
 
 
-@pytest.mark.parametrize("env", [{"B200_DW16": "0"}, {"B200_TAIL": "0"}, {"B200_FWD16": "0"}, {"B200_TAIL_FWD": "1"},
+@pytest.mark.parametrize("env", [{"B200_DW16": "0"}, {"B200_TAIL": "0"}, {"B200_FWD16": "0"}, {"B200_TAIL_FWD": "1"}, {"B200_MID16": "0"},
                                  {"B200_FWD16": "0", "B200_TAIL": "0", "B200_DW16": "0"}])
 @pytest.mark.parametrize("which", [0, 5])
 def test_each_new_kernel_against_the_generic_path(handle, oracle, env, which):
