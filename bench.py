@@ -178,7 +178,7 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def reference_cuda_rate(dims, acts, dX, dT, samples, iters=20, warmup=5):
+def reference_cuda_rate(dims, acts, dX, dT, samples, iters=40, warmup=10):
     """the reference's CUDA backend (cuBLAS) on this GPU, same workload, from the same starting point rule"""
     try:
         from oracle import ref_cuda_binding as rcu
@@ -188,11 +188,16 @@ def reference_cuda_rate(dims, acts, dX, dT, samples, iters=20, warmup=5):
         net = rcu.RefCudaNet(dims, [act_id[a] for a in acts])
         net.bind_params(123)
         net.solve("lbfgs", dX.data_ptr(), dT.data_ptr(), samples, warmup, memory=MEMORY, record=False)  # cuBLAS init, allocations
-        net.bind_params(123)
-        r = net.solve("lbfgs", dX.data_ptr(), dT.data_ptr(), samples, iters, memory=MEMORY, record=False)
+        best = None
+        for _ in range(2):  # best of two runs: the comparator should not lose to a cold cuBLAS heuristic or a clock ramp
+            net.bind_params(123)
+            r = net.solve("lbfgs", dX.data_ptr(), dT.data_ptr(), samples, iters, memory=MEMORY, record=False)
+            if best is None or r["total_ms"] / max(1, r["iters"]) < best["total_ms"] / max(1, best["iters"]):
+                best = r
+        r = best
         net.close()
         return dict(value=r["iters"] / (r["total_ms"] / 1e3), unit="iterations/s", iterations=int(r["iters"]),
-                    sample=f"{iters} L-BFGS iterations (after a {warmup}-iteration warm-up solve) of the reference CUDA backend "
+                    sample=f"best of two runs of {iters} L-BFGS iterations (after a {warmup}-iteration warm-up solve) of the reference CUDA backend "
                            "(cuBLAS SGEMM + src/cuda/*.cuh, compiled unmodified for sm_100a: oracle/_ref/libref_cuda.so) on the same GPU, "
                            f"same {samples} samples, m = {MEMORY}, device-resident inputs")
     except Exception as e:  # comparator only: never fail the bench line over it

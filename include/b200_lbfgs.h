@@ -222,6 +222,17 @@ typedef struct b200_slbfgs_opts { /* UnifiedSLBFGS_CPU::optimize (src/unified_op
   float epsilon;                  /* 1e-4 finite-difference step */
   unsigned seed;                  /* 123 (kDefaultSeed) */
   int record;                     /* 1: full loss + full gradient norm per epoch (s_lbfgs.hpp:274-284) */
+  int pair_eval;                  /* 1: the two evaluations of a step (w_t and the anchor; u + eps s and u - eps s) run as ONE
+                                   * forward/backward of the stacked "pair network" on the shared mini-batch, with
+                                   * v = g_t - g_k + mu / y = (g+ - g-)/(2 eps) formed as the gradients are read back;
+                                   * 0: two separate evaluations (same results to rounding) */
+  float hvp_step_scale;           /* 256: the +-eps*s pair of the finite-difference Hessian-vector product is evaluated at
+                                   * +-(scale*eps)*s and divided by 2*scale*eps. The reference computes the pair in double; in
+                                   * fp32, eps*s = 1e-4*s is below one ulp of most weights (|s|/|w| ~ 1e-3), so at scale 1 the
+                                   * displacement w +- eps*s itself is mostly rounding: y is noise, and the quasi-Newton update
+                                   * built on it diverges in some runs (NaN after 1-3 epochs, measured: DESIGN.md). From scale
+                                   * ~256 on the result no longer depends on the arithmetic mode or on how the pair is
+                                   * evaluated (3 digits). 1 = the reference's step verbatim. */
 } b200_slbfgs_opts;
 void b200_slbfgs_default_opts(b200_slbfgs_opts *o);
 /* SLBFGS::stochastic_solve (src/minimizer/s_lbfgs.hpp:165-290) on the GPU. New functionality: the reference

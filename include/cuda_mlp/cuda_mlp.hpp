@@ -304,13 +304,14 @@ public:
   void setMemory(int m) { M_ = m; }
   void setUpdateInterval(int L) { L_ = L; }
   void setHessianBatchSize(int b) { b_H_ = b; }
+  void setHvpStepScale(CudaScalar s) { hvp_scale_ = s; } // b200_slbfgs_opts::hvp_step_scale (1 = the reference's step verbatim)
   void solve(int n, CudaScalar *params, const CudaScalar *input, const CudaScalar *target, int total_samples,
              const LossGradFun &) override {
     if (!net_) { std::cerr << "B200 error: CudaSLBFGS needs setNetwork()\n"; std::abort(); }
     b200_slbfgs_opts o;
     b200_slbfgs_default_opts(&o);
     o.max_iters = max_iters_; o.tol = tol_; o.step_size = step_; o.batch_size = batch_; o.memory = M_; o.L = L_;
-    o.b_H = b_H_; o.record = recorder_ ? 1 : 0;
+    o.b_H = b_H_; o.record = recorder_ ? 1 : 0; o.hvp_step_scale = hvp_scale_;
     b200_history h{};
     begin_history(h);
     b200_check(b200_slbfgs_solve(handle_.get(), net_->get(), n, params, input, target, total_samples, &o, &h), "CudaSLBFGS::solve");
@@ -318,7 +319,7 @@ public:
   }
 
 private:
-  CudaScalar step_ = 0.01f;
+  CudaScalar step_ = 0.01f, hvp_scale_ = 256.0f;
   int batch_ = 128, M_ = 10, L_ = 10, b_H_ = 0;
 };
 

@@ -43,7 +43,7 @@ class SgdOpts(C.Structure):
 class SlbfgsOpts(C.Structure):
     _fields_ = [("max_iters", C.c_int), ("tol", C.c_float), ("step_size", C.c_float), ("batch_size", C.c_int),
                 ("memory", C.c_int), ("L", C.c_int), ("b_H", C.c_int), ("lam", C.c_float), ("epsilon", C.c_float),
-                ("seed", C.c_uint), ("record", C.c_int)]
+                ("seed", C.c_uint), ("record", C.c_int), ("pair_eval", C.c_int), ("hvp_step_scale", C.c_float)]
 
 
 # every symbol include/b200_lbfgs.h declares: name -> (restype, argtypes)

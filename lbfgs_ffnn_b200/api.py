@@ -520,6 +520,8 @@ class CudaSLBFGS(CudaMinimizerBase):
         self.tol_ = 1e-4
         self.step_size_, self.batch_size_, self.M_, self.L_, self.b_H_ = 0.01, 128, 10, 10, 0
         self.lambda_, self.epsilon_, self.seed_ = 1e-4, 1e-4, 123
+        self.hvp_step_scale_ = 256.0  # include/b200_lbfgs.h: b200_slbfgs_opts::hvp_step_scale
+        self.pair_eval_ = 1          # b200_slbfgs_opts::pair_eval
 
     def setStepSize(self, s):
         self.step_size_ = float(s)
@@ -539,12 +541,22 @@ class CudaSLBFGS(CudaMinimizerBase):
     def setSeed(self, seed):
         self.seed_ = int(seed)
 
+    def setPairEvaluation(self, on):
+        """True (default): both evaluations of a step in one forward/backward of the stacked pair network"""
+        self.pair_eval_ = 1 if on else 0
+
+    def setHvpStepScale(self, scale):
+        """1 = the reference's finite-difference step verbatim; default 256 (fp32 resolution, see include/b200_lbfgs.h)"""
+        self.hvp_step_scale_ = float(scale)
+
     def solve(self, n, params, input_dev, target_dev, total_samples, net):
         o = _lib.SlbfgsOpts()
         lib().b200_slbfgs_default_opts(C.byref(o))
         o.max_iters, o.tol, o.step_size, o.batch_size = self.max_iters_, self.tol_, self.step_size_, self.batch_size_
         o.memory, o.L, o.b_H, o.lam, o.epsilon, o.seed = self.M_, self.L_, self.b_H_, self.lambda_, self.epsilon_, self.seed_
         o.record = 1 if self.recorder_ is not None else 0
+        o.hvp_step_scale = self.hvp_step_scale_
+        o.pair_eval = self.pair_eval_
         h = self._history()
         check(lib().b200_slbfgs_solve(self.handle._h, net._h, int(n), C.c_void_p(_ptr(params) or 0),
                                       C.c_void_p(_ptr(input_dev)), C.c_void_p(_ptr(target_dev)), int(total_samples),

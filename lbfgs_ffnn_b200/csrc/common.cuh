@@ -164,6 +164,12 @@ struct ProfScope {
   }
 };
 
+// Handles may be destroyed in any order (a garbage-collected host language does): objects that hold a pointer to another handle
+// ask whether it is still alive before touching it.
+bool ctx_is_live(const b200_ctx *ctx);
+void net_register(unsigned long long uid, void *net); // nullptr: unregister
+void *net_lookup(unsigned long long uid);             // nullptr once the network has been destroyed
+
 int ctx_allreduce(b200_ctx *ctx, float *grad, size_t n, double *loss_dev); // grad (float) + 1 double
 // collective (every rank calls it with the same n): maps the peers' symmetric buffers; ctx->p2p.ready tells whether the
 // peer-memory all-reduce can be used (all ranks agree), otherwise the callers stay on NCCL

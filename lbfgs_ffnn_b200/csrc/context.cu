@@ -10,7 +10,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <set>
 
 namespace b200 {
 
@@ -52,6 +54,23 @@ void env_reload() {
 const EnvFlags &env() {
   std::call_once(g_env_once, env_reload);
   return g_env;
+}
+
+static std::mutex g_live_mu;
+static std::set<const b200_ctx *> g_live_ctx;
+static std::map<unsigned long long, void *> g_live_nets;
+bool ctx_is_live(const b200_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  return g_live_ctx.count(ctx) != 0;
+}
+void net_register(unsigned long long uid, void *net) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  if (net) g_live_nets[uid] = net; else g_live_nets.erase(uid);
+}
+void *net_lookup(unsigned long long uid) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  auto it = g_live_nets.find(uid);
+  return it == g_live_nets.end() ? nullptr : it->second;
 }
 
 struct NcclApi {
@@ -296,12 +315,14 @@ int b200_ctx_create(int device, b200_ctx **out) {
   B200_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
   B200_CUDA(cudaEventCreate(&ctx->ev_a));
   B200_CUDA(cudaEventCreate(&ctx->ev_b));
+  { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.insert(ctx); }
   *out = ctx;
   return B200_OK;
 }
 
 int b200_ctx_destroy(b200_ctx *ctx) {
-  if (!ctx) return B200_OK;
+  if (!ctx || !ctx_is_live(ctx)) return B200_OK;
+  { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.erase(ctx); }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) {

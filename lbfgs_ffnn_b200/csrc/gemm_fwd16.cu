@@ -400,12 +400,10 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
 // Operand preparation, once per evaluation. A job turns one weight matrix (elements (r, n) at W[r * sr + n * sn]: r the
 // contraction index, n the output row) into the scaled fp16 pair wh, wl [rows n][ldk] (contraction index contiguous):
-//     v = W(r, n) * rscale[r]          (rscale: 1 / t_r of the layer that produced the A operand, or none)
+//     v = W(r, n) * rscale[r]          (rscale: 1 / t_r of the layer that produced the A operand, see rs_mode; or none)
 //     s_n = 2^(14 - e), max_r |v| in [2^(e-1), 2^e)  =>  s_n * max |v| in [2^13, 2^14)   (fp16 overflows at 65504)
 //     hi = fp16(s_n v), lo = fp16(s_n v - hi), colscale[n] = pre / s_n; with dup = 2 the row is written twice, [v | v]: the hi
 //     and the lo blocks of a K-stacked A operand meet the same weights.
-// A job may also bound the layer's outputs for the consumer of its activations (EPI_EMIT16): bound_n = sum_r |W(r, n)| + |b_n|
-// (inputs in [0, 1]; 1 for tanh / sigmoid) and t_n = 2^(14 - ceil(log2 bound)).
 // One CTA of 1024 threads per 8 output rows (one 32-byte sector per weight row when sn == 1), 128 slices of the contraction
 // index per row: every weight is loaded ONCE (<= 8 per thread, all in flight together), kept in registers across the
 // reductions, split, and written out through a shared-memory transpose.
@@ -416,32 +414,65 @@ struct PrepJob {
   long sr, sn;
   int ldk, dup;
   float pre;
-  const float *rscale;  // [R] or nullptr
   __half *wh, *wl;
   float *colscale;
-  // output bound (optional): mode 0 none, 1 = L1 bound of the pre-activation, 2 = 1 (bounded activation)
-  int bound_mode;
-  const float *bias;
-  float *tscale, *tinv;
+  // rscale computed here (so that this job does not wait for another launch): the A operand is the pair of the PREVIOUS layer's
+  // activations, whose per-feature scale t_k comes from the bound sum_r |Wp(r, k)| + |bp_k| over that layer's weights Wp
+  // ([rs_R][128], k contiguous; inputs in [0, 1]) — mode 1 — or is 1 for a bounded activation (mode 2). Every CTA of the job
+  // computes all 128 scales with the same arithmetic (identical results); the first one publishes t_k and 1 / t_k.
+  int rs_mode;
+  const float *rs_W, *rs_bias;
+  int rs_R;
+  float *rs_tscale, *rs_tinv;
   int nblocks;          // CTAs of this job
 };
-__global__ void __launch_bounds__(1024) prep_w16_kernel(const PrepJob j0, const PrepJob j1, const SpecState *spec_st, int spec,
-                                                      const ChainW chain) {
+__global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ PrepJob j0, const __grid_constant__ PrepJob j1,
+                                                      const __grid_constant__ PrepJob j2, const SpecState *spec_st, int spec,
+                                                      const __grid_constant__ ChainW chain) {
   if (spec_skip(spec_st, spec)) return;
-  __shared__ float red[128][kSplitNeurons + 1], red1[128][kSplitNeurons + 1];
+  __shared__ float red[128][kSplitNeurons + 1];
   if (chain.nl > 0 && blockIdx.x >= gridDim.x - chain.nctas) { // the extra CTAs (see ChainW, network.cuh)
     chain_cw_block(chain, (int)(blockIdx.x - (gridDim.x - chain.nctas)), &red[0][0]);
     return;
   }
-  const bool second = (int)blockIdx.x >= j0.nblocks;
-  const PrepJob &j = second ? j1 : j0;
-  __shared__ float sc[kSplitNeurons];
+  const int which = (int)blockIdx.x < j0.nblocks ? 0 : ((int)blockIdx.x < j0.nblocks + j1.nblocks ? 1 : 2);
+  const PrepJob &j = *(which == 0 ? &j0 : (which == 1 ? &j1 : &j2)); // (a pointer into the parameter space: no local copy)
+  __shared__ float sc[kSplitNeurons], rs_sh[128];
   __shared__ __align__(16) __half th[kSplitNeurons][kSplitMaxK + 8], tl[kSplitNeurons][kSplitMaxK + 8];
   const int o = threadIdx.x & (kSplitNeurons - 1), kq = threadIdx.x / kSplitNeurons;
-  const int o0 = ((int)blockIdx.x - (second ? j0.nblocks : 0)) * kSplitNeurons;
+  const int o0 = ((int)blockIdx.x - (which == 0 ? 0 : (which == 1 ? j0.nblocks : j0.nblocks + j1.nblocks))) * kSplitNeurons;
   const bool ok = o0 + o < j.Nn;
+  if (j.rs_mode) { // block-uniform
+    const int k = threadIdx.x & 127, slice = threadIdx.x >> 7;
+    float a = 0.0f;
+    if (j.rs_mode == 1) { // 8 slices of the contraction index per feature; 16 loads in flight per thread
+      for (int r0 = slice; r0 < j.rs_R; r0 += 8 * 16) {
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = (r0 + 8 * u < j.rs_R) ? fabsf(__ldg(j.rs_W + (size_t)(r0 + 8 * u) * 128 + k)) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a += t[u];
+      }
+    }
+    red[k][slice] = a;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float bound = 1.0f;
+      if (j.rs_mode == 1) {
+        float b1 = 0.0f;
+        for (int i = 0; i < 8; ++i) b1 += red[k][i];
+        bound = b1 * 1.0001f + fabsf(__ldg(j.rs_bias + k)) + 1e-30f; // (fp32 summation slack)
+      }
+      int eb = 0;
+      frexpf(bound, &eb);
+      eb = max(-100, min(100, eb));
+      rs_sh[k] = ldexpf(1.0f, eb - 14);
+      if (o0 == 0) { j.rs_tscale[k] = ldexpf(1.0f, 14 - eb); j.rs_tinv[k] = ldexpf(1.0f, eb - 14); }
+    }
+    __syncthreads();
+  }
   float v[kSplitMaxK / 128];
-  float amax = 0.0f, l1 = 0.0f;
+  float amax = 0.0f;
 #pragma unroll
   for (int i = 0; i < kSplitMaxK / 128; ++i) {
     const int k = kq + 128 * i;
@@ -449,33 +480,20 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const PrepJob j0, const 
   }
 #pragma unroll
   for (int i = 0; i < kSplitMaxK / 128; ++i) {
-    l1 += fabsf(v[i]);
-    if (j.rscale) { const int k = kq + 128 * i; v[i] *= (k < j.R) ? __ldg(j.rscale + k) : 0.0f; }
+    if (j.rs_mode) { const int k = kq + 128 * i; v[i] *= (k < 128) ? rs_sh[k] : 0.0f; } // (R <= 128 on this path)
     amax = fmaxf(amax, fabsf(v[i]));
   }
   red[kq][o] = amax;
-  red1[kq][o] = l1;
   __syncthreads();
   if (threadIdx.x < kSplitNeurons) {
-    float m = 0.0f, b1 = 0.0f;
-    for (int i = 0; i < 128; ++i) { m = fmaxf(m, red[i][threadIdx.x]); b1 += red1[i][threadIdx.x]; }
+    float m = 0.0f;
+    for (int i = 0; i < 128; ++i) m = fmaxf(m, red[i][threadIdx.x]);
     int e = 0;
     if (m > 0.0f && m < 3.0e38f) frexpf(m, &e); // m = f * 2^e, f in [0.5, 1)
     e = max(-100, min(100, e));
     sc[threadIdx.x] = ldexpf(1.0f, 14 - e);      // s * m in [2^13, 2^14)
     const int n = o0 + threadIdx.x;
-    if (n < j.Nn) {
-      j.colscale[n] = j.pre * ldexpf(1.0f, e - 14);
-      if (j.bound_mode) {
-        float bound = 1.0f;
-        if (j.bound_mode == 1) bound = b1 * 1.0001f + fabsf(__ldg(j.bias + n)) + 1e-30f; // (fp32 summation slack)
-        int eb = 0;
-        frexpf(bound, &eb);
-        eb = max(-100, min(100, eb));
-        j.tscale[n] = ldexpf(1.0f, 14 - eb);
-        j.tinv[n] = ldexpf(1.0f, eb - 14);
-      }
-    }
+    if (n < j.Nn) j.colscale[n] = j.pre * ldexpf(1.0f, e - 14);
   }
   __syncthreads();
   const float s = sc[o];
@@ -702,35 +720,26 @@ int fwd16_prepare(b200_net *net, const float *params) {
   j0.W = W0; j0.R = K; j0.Nn = N; j0.sr = N; j0.sn = 1; j0.ldk = ldk; j0.dup = 1; j0.pre = 1.0f / 255.0f;
   j0.wh = (__half *)net->w16h; j0.wl = (__half *)net->w16l; j0.colscale = net->colscale;
   j0.nblocks = ceil_div(N, kSplitNeurons);
-  PrepJob j1{}; // (no CTAs)
-  const bool mid = net->m16.on;
-  if (mid) {
+  PrepJob j1{}, j2{}; // (no CTAs)
+  if (net->m16.on) {
     b200_net::Mid16 &m = net->m16;
     const int N1 = net->dims[2];
     const float *W1 = params + net->offs[1];
-    const bool bounded = net->acts[0] == B200_ACT_TANH || net->acts[0] == B200_ACT_SIGMOID;
-    j0.bound_mode = bounded ? 2 : 1;
-    j0.bias = W0 + (size_t)K * N; j0.tscale = m.tscale; j0.tinv = m.tinv;
     // dX operand of layer 1: rows = layer-1 inputs f, contraction over its outputs o (W_1 is [f][o], o contiguous)
     j1.W = W1; j1.R = N1; j1.Nn = N; j1.sr = 1; j1.sn = N1; j1.ldk = 2 * N1; j1.dup = 2; j1.pre = 1.0f;
     j1.wh = (__half *)m.wdh; j1.wl = (__half *)m.wdl; j1.colscale = m.colscale_d;
     j1.nblocks = ceil_div(N, kSplitNeurons);
+    // forward operand of layer 1, rows scaled by 1 / t_k of layer 0's outputs (computed inside the job from W_0: N == 128)
+    j2.W = W1; j2.R = N; j2.Nn = N1; j2.sr = N1; j2.sn = 1; j2.ldk = 2 * N; j2.dup = 2; j2.pre = 1.0f;
+    j2.wh = (__half *)m.wfh; j2.wl = (__half *)m.wfl; j2.colscale = m.colscale_f;
+    j2.rs_mode = (net->acts[0] == B200_ACT_TANH || net->acts[0] == B200_ACT_SIGMOID) ? 2 : 1;
+    j2.rs_W = W0; j2.rs_bias = W0 + (size_t)K * N; j2.rs_R = K; j2.rs_tscale = m.tscale; j2.rs_tinv = m.tinv;
+    j2.nblocks = ceil_div(N1, kSplitNeurons);
   }
   {
     ProfScope ps(net->ctx, "split16");
-    B200_LAUNCH(prep_w16_kernel, j0.nblocks + j1.nblocks + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, j0, j1,
-                net->spec_st, net->spec_flag, chain);
-    if (mid) { // forward operand of layer 1: needs 1 / t_k of layer 0's outputs, written by the launch above
-      b200_net::Mid16 &m = net->m16;
-      const int N1 = net->dims[2];
-      PrepJob f{};
-      f.W = params + net->offs[1]; f.R = N; f.Nn = N1; f.sr = N1; f.sn = 1; f.ldk = 2 * N; f.dup = 2; f.pre = 1.0f;
-      f.rscale = m.tinv; f.wh = (__half *)m.wfh; f.wl = (__half *)m.wfl; f.colscale = m.colscale_f;
-      f.nblocks = ceil_div(N1, kSplitNeurons);
-      PrepJob none{};
-      ChainW nochain{};
-      B200_LAUNCH(prep_w16_kernel, f.nblocks, 1024, 0, net->ctx->stream, f, none, net->spec_st, net->spec_flag, nochain);
-    }
+    B200_LAUNCH(prep_w16_kernel, j0.nblocks + j1.nblocks + j2.nblocks + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, j0,
+                j1, j2, net->spec_st, net->spec_flag, chain);
   }
   net->w16_params = params;
   return B200_OK;

@@ -844,6 +844,7 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   b200_net *net = new b200_net;
   static std::atomic<unsigned long long> next_uid{1};
   net->uid = next_uid.fetch_add(1);
+  net_register(net->uid, net);
   net->ctx = ctx;
   net->dims.assign(dims, dims + nlayers + 1);
   net->acts.assign(acts, acts + nlayers);
@@ -875,9 +876,14 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
 
 int b200_net_destroy(b200_net *net) {
   if (!net) return B200_OK;
-  cudaSetDevice(net->ctx->device);
-  cudaStreamSynchronize(net->ctx->stream);
-  lbfgs_pool_forget_net(net->ctx, net->uid);
+  net_register(net->uid, nullptr);
+  if (ctx_is_live(net->ctx)) { // (the context may have been destroyed first: its stream and pooled solvers went with it)
+    cudaSetDevice(net->ctx->device);
+    cudaStreamSynchronize(net->ctx->stream);
+    lbfgs_pool_forget_net(net->ctx, net->uid);
+  } else {
+    cudaDeviceSynchronize();
+  }
   free_batch_buffers(net);
   tc_release(net);
   tail_release(net);

@@ -55,7 +55,8 @@ struct Sampler {
 // rows of X / T selected by idx into contiguous batch buffers (one warp per sample row)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ X, const float *__restrict__ T,
                                                           const uint32_t *__restrict__ idx, int count, int in_dim,
-                                                          int out_dim, float *__restrict__ Xb, float *__restrict__ Tb) {
+                                                          int out_dim, float *__restrict__ Xb, float *__restrict__ Tb,
+                                                          float *__restrict__ Tb2 = nullptr) { // Tb2: rows [T | T] for the pair network
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < count; i += warps) {
@@ -68,7 +69,11 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
     } else {
       for (int c = lane; c < in_dim; c += 32) xd[c] = __ldg(xs + c);
     }
-    for (int c = lane; c < out_dim; c += 32) Tb[(size_t)i * out_dim + c] = __ldg(T + src * out_dim + c);
+    for (int c = lane; c < out_dim; c += 32) {
+      const float tv = __ldg(T + src * out_dim + c);
+      Tb[(size_t)i * out_dim + c] = tv;
+      if (Tb2) { Tb2[(size_t)i * 2 * out_dim + c] = tv; Tb2[(size_t)i * 2 * out_dim + out_dim + c] = tv; }
+    }
   }
 }
 
@@ -103,6 +108,66 @@ __global__ void __launch_bounds__(256) hvp_diff_kernel(size_t n, const float *__
                                                        float inv_2eps, float *__restrict__ y) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = (gp[i] - gm[i]) * inv_2eps;
+}
+
+// ---- the two evaluations of a step as ONE forward/backward ---------------------------------------------------------------
+// Both evaluations of an inner step (w_t and the anchor) and both of a curvature pair (u + eps s, u - eps s) see the SAME
+// mini-batch. They run as a single evaluation of the "pair network": the two parameter sets stacked along the output dimension,
+//   layer 0: W = [W_a | W_b] (in x 2 out);   layer l >= 1: W = blockdiag(W_a, W_b) (2 in x 2 out);   b = [b_a | b_b];   T = [T | T]
+// so X is read once, every kernel is launched once, and the loss is L_a + L_b: its gradient holds g_a and g_b in the diagonal
+// blocks (the off-diagonal blocks belong to weights that are identically zero and are ignored). Exact: the zero blocks add
+// exact zeros to every sum. pack_pair_kernel builds the stacked parameters, unpack_pair_kernel reads the two gradients back
+// and forms the quantity the algorithm wants in the same pass: v = g_a - g_b + mu (s_lbfgs.hpp:225-228) or
+// y = (g_a - g_b) / (2 eps) (:100).
+struct PairLayout {
+  int nl;
+  int in[16], out[16];               // of ONE network
+  unsigned long long off[16], poff[16]; // parameter offsets of layer l in one network / in the pair network
+};
+__global__ void __launch_bounds__(256) pack_pair_kernel(const PairLayout L, unsigned long long n_pair, const float *__restrict__ wa,
+                                                        const float *__restrict__ wb, float *__restrict__ wp) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pair;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < L.nl && i >= L.poff[l + 1]) ++l;
+    const unsigned long long e = i - L.poff[l];
+    const int K = L.in[l], N = L.out[l], Kp = (l == 0) ? K : 2 * K, Np = 2 * N;
+    float v = 0.0f;
+    if (e < (unsigned long long)Kp * Np) {
+      const int kp = (int)(e / Np), op = (int)(e - (unsigned long long)kp * Np);
+      const bool second = op >= N;
+      const int o = second ? op - N : op;
+      if (l == 0) v = (second ? wb : wa)[L.off[l] + (unsigned long long)kp * N + o];
+      else if ((kp >= K) == second) v = (second ? wb : wa)[L.off[l] + (unsigned long long)(second ? kp - K : kp) * N + o];
+    } else {
+      const int op = (int)(e - (unsigned long long)Kp * Np);
+      v = (op >= N ? wb : wa)[L.off[l] + (unsigned long long)K * N + (op >= N ? op - N : op)];
+    }
+    wp[i] = v;
+  }
+}
+// out[i] = (g_a[i] - g_b[i]) * scale + (add ? add[i] : 0)
+__global__ void __launch_bounds__(256) unpack_pair_kernel(const PairLayout L, unsigned long long n, const float *__restrict__ gp,
+                                                          float scale, const float *__restrict__ add, float *__restrict__ out) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < L.nl && i >= L.off[l + 1]) ++l;
+    const unsigned long long e = i - L.off[l];
+    const int K = L.in[l], N = L.out[l], Kp = (l == 0) ? K : 2 * K, Np = 2 * N;
+    unsigned long long ia, ib;
+    if (e < (unsigned long long)K * N) {
+      const int k = (int)(e / N), o = (int)(e - (unsigned long long)k * N);
+      ia = L.poff[l] + (unsigned long long)k * Np + o;
+      ib = L.poff[l] + (unsigned long long)(l == 0 ? k : K + k) * Np + N + o;
+    } else {
+      const int o = (int)(e - (unsigned long long)K * N);
+      ia = L.poff[l] + (unsigned long long)Kp * Np + o;
+      ib = ia + N;
+    }
+    const float d = (gp[ia] - gp[ib]) * scale;
+    out[i] = add ? d + add[i] : d;
+  }
 }
 
 inline int vblocks(size_t n) { return (int)std::max<size_t>(1, std::min<size_t>(1184, (n + 255) / 256)); }
@@ -194,6 +259,7 @@ void b200_slbfgs_default_opts(b200_slbfgs_opts *o) {
   if (!o) return;
   o->max_iters = 100; o->tol = 1e-4f; o->step_size = 0.01f; o->batch_size = 128; // UnifiedConfig defaults, unified_optimization.hpp:26-48
   o->memory = 10; o->L = 10; o->b_H = 0; o->lambda = 1e-4f; o->epsilon = 1e-4f; o->seed = 123; o->record = 1;
+  o->hvp_step_scale = 256.0f; o->pair_eval = 1;
 }
 
 int b200_slbfgs_sample_stream(unsigned seed, long N, long b, int count, uint32_t *out_host) {
@@ -213,6 +279,7 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   b200_slbfgs_opts o;
   if (opts) o = *opts; else b200_slbfgs_default_opts(&o);
   B200_REQUIRE(o.batch_size > 0 && o.L > 0 && o.memory >= 0 && o.memory <= kMaxSlots - 1, "bad S-LBFGS options");
+  const float fd_eps = o.epsilon * (o.hvp_step_scale > 0.0f ? o.hvp_step_scale : 1.0f); // see b200_slbfgs_opts::hvp_step_scale
   B200_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const long launches0 = b200_launch_count();
@@ -233,6 +300,26 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   net->l2 = o.lambda;
   struct RestoreL2 { b200_net *n; float v; ~RestoreL2() { n->l2 = v; } } restore{net, old_l2};
 
+  // the pair network (see pack_pair_kernel): same activations, every width but the input doubled
+  const bool use_pair = o.pair_eval != 0 && net->nlayers() <= 16;
+  b200_net *pair = nullptr;
+  struct FreePair { b200_net **p; ~FreePair() { if (*p) b200_net_destroy(*p); } } free_pair{&pair};
+  PairLayout PL{};
+  size_t n_pair = 0;
+  if (use_pair) {
+    std::vector<int> pd(net->dims), pa(net->acts);
+    for (size_t l = 1; l < pd.size(); ++l) pd[l] *= 2;
+    B200_TRY(b200_net_create(ctx, net->nlayers(), pd.data(), pa.data(), &pair));
+    pair->prec = net->prec;
+    pair->l2 = o.lambda;
+    PL.nl = net->nlayers();
+    for (int l = 0; l < PL.nl; ++l) {
+      PL.in[l] = net->dims[l]; PL.out[l] = net->dims[l + 1];
+      PL.off[l] = net->offs[l]; PL.poff[l] = pair->offs[l];
+    }
+    n_pair = pair->n;
+  }
+
   // ---- workspace ---------------------------------------------------------------------------------
   const int nblk = lbfgs_dots_blocks(ctx, Nn);
   const int ncols = kDotsCols * mp + 1;
@@ -240,6 +327,8 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   const size_t part_bytes = (sizeof(double) * (size_t)nblk * ncols + 255) & ~size_t(255);
   const size_t vec = sizeof(float) * ld;
   const int nvec = 13 + (L + 1) + 2 * mp; // wt mu gt gk v d u uprev s y wp wm gfull | w_history | S Y
+  const size_t pvec = (sizeof(float) * n_pair + 255) & ~size_t(255);          // pair network: parameters, gradient
+  const size_t tb2_bytes = use_pair ? 2 * ((sizeof(float) * (size_t)(std::max(b, b_H) / W) * out_dim + 255) & ~size_t(255)) : 0;
   const int maxb = std::max(b, b_H) / W;
   const size_t xb_bytes = (sizeof(float) * (size_t)maxb * in_dim + 255) & ~size_t(255);
   const size_t tb_bytes = (sizeof(float) * (size_t)maxb * out_dim + 255) & ~size_t(255);
@@ -247,7 +336,8 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   const size_t idx_cap = (size_t)m_inner * (b / W) + (size_t)(m_inner / L + 1) * (b_H / W);
   const size_t idx_bytes = (sizeof(uint32_t) * idx_cap + 255) & ~size_t(255);
   char *ws = nullptr;
-  const size_t total = state_bytes + part_bytes + vec * nvec + xb_bytes + tb_bytes + idx_bytes + 2 * sizeof(EvalOut) + 256;
+  const size_t total = state_bytes + part_bytes + vec * nvec + xb_bytes + tb_bytes + idx_bytes + 2 * sizeof(EvalOut) + 256 +
+                       2 * pvec + tb2_bytes;
   B200_CUDA(cudaMalloc(&ws, total));
   struct Free { char *p; ~Free() { cudaFree(p); } } free_ws{ws};
   B200_CUDA(cudaMemsetAsync(ws, 0, total, st));
@@ -263,7 +353,16 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   float *S = (float *)take(vec * mp), *Y = (float *)take(vec * mp);
   float *Xb = (float *)take(xb_bytes), *Tb = (float *)take(tb_bytes);
   uint32_t *d_idx = (uint32_t *)take(idx_bytes);
-  EvalOut *ev_scratch = (EvalOut *)take(sizeof(EvalOut));
+  EvalOut *ev_scratch = (EvalOut *)take((sizeof(EvalOut) + 255) & ~size_t(255));
+  float *pw = use_pair ? (float *)take(pvec) : nullptr, *pg = use_pair ? (float *)take(pvec) : nullptr;
+  float *Tb2 = use_pair ? (float *)take(tb2_bytes) : nullptr;
+  // one forward/backward of the pair network at (wa, wb) on the gathered batch; out = (g_a - g_b) * scale (+ add)
+  auto pair_eval = [&](const float *wa, const float *wb, int rows, int rows_global, float scale, const float *add, float *out) -> int {
+    B200_LAUNCH(pack_pair_kernel, vblocks(n_pair), 256, 0, st, PL, (unsigned long long)n_pair, wa, wb, pw);
+    B200_TRY(net_eval(pair, pw, Xb, Tb2, rows, rows_global, pg, ev_scratch));
+    B200_LAUNCH(unpack_pair_kernel, vblocks(Nn), 256, 0, st, PL, (unsigned long long)Nn, pg, scale, add, out);
+    return B200_OK;
+  };
   B200_TRY(lbfgs_init_state(view, M, mod, st));
   uint32_t *h_idx = nullptr;
   B200_CUDA(cudaMallocHost(&h_idx, sizeof(uint32_t) * idx_cap));
@@ -332,11 +431,15 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
     for (int t = 0; t < m_inner; ++t) {
       const int bl = b / W;
       B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(bl, 8)), 256, 0, st, input, target, d_idx + mb_off[t], bl,
-                  in_dim, out_dim, Xb, Tb);
+                  in_dim, out_dim, Xb, Tb, Tb2);
       evals += 2;
-      B200_TRY(net_eval(net, wt, Xb, Tb, bl, b, gt, ev_scratch));
-      B200_TRY(net_eval(net, params, Xb, Tb, bl, b, gk, ev_scratch));
-      B200_LAUNCH(vr_combine_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, mu, v);
+      if (use_pair) { // both gradients from ONE forward/backward, v = g_t - g_k + mu formed as they are read back
+        B200_TRY(pair_eval(wt, params, bl, b, 1.0f, mu, v));
+      } else {
+        B200_TRY(net_eval(net, wt, Xb, Tb, bl, b, gt, ev_scratch));
+        B200_TRY(net_eval(net, params, Xb, Tb, bl, b, gk, ev_scratch));
+        B200_LAUNCH(vr_combine_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, mu, v);
+      }
       // direction = H v (two-loop on the current ring), w_t -= eta * direction, history push (:230-233)
       DotsArgs da{S, Y, Nn, ld, view, v, nullptr, nullptr, nullptr, DOTS_NONE, 0, 0, partials};
       B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
@@ -351,15 +454,19 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
       if (t > 0 && t % L == 0) {
         const int cnt = std::min(wh_pushes, L + 1);
         B200_LAUNCH(hvp_points_kernel, vblocks(Nn), 256, 0, st, Nn, ld, Wh, cnt, u, u_prev, have_u_prev ? 1 : 0,
-                    o.epsilon, s, wp, wm);
+                    fd_eps, s, wp, wm);
         if (have_u_prev) {
           const int hl = b_H / W;
           B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(hl, 8)), 256, 0, st, input, target, d_idx + hb_off[t],
-                      hl, in_dim, out_dim, Xb, Tb);
+                      hl, in_dim, out_dim, Xb, Tb, Tb2);
           evals += 2;
-          B200_TRY(net_eval(net, wp, Xb, Tb, hl, b_H, gt, ev_scratch));
-          B200_TRY(net_eval(net, wm, Xb, Tb, hl, b_H, gk, ev_scratch));
-          B200_LAUNCH(hvp_diff_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, 1.0f / (2.0f * o.epsilon), y);
+          if (use_pair) { // the +- eps s pair in one forward/backward, y = (g+ - g-) / (2 eps) formed as they are read back
+            B200_TRY(pair_eval(wp, wm, hl, b_H, 1.0f / (2.0f * fd_eps), nullptr, y));
+          } else {
+            B200_TRY(net_eval(net, wp, Xb, Tb, hl, b_H, gt, ev_scratch));
+            B200_TRY(net_eval(net, wm, Xb, Tb, hl, b_H, gk, ev_scratch));
+            B200_LAUNCH(hvp_diff_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, 1.0f / (2.0f * fd_eps), y);
+          }
           if (M > 0) {
             B200_TRY(launch_lbfgs_store_pair(S, Y, Nn, ld, view, s, y, st));
             DotsArgs dp{S, Y, Nn, ld, view, v, nullptr, nullptr, nullptr, DOTS_PAIR_IN_SLOT, 0, 0, partials};

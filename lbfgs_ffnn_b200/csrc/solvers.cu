@@ -148,7 +148,7 @@ struct b200_lbfgs {
   unsigned long long gkey[7] = {0, 0, 0, 0, 0, 0, 0};
   bool graphs_ok = true;
   bool spec_capable = false; // the captured evaluation consists of gated kernels only
-  b200_net *last_net = nullptr; // network whose input cache this minimisation (re)built
+  unsigned long long last_net_uid = 0; // network whose input cache this minimisation (re)built (uid: it may be destroyed first)
   // minimisation state carried across runs
   bool started = false;
   int cur = 0, iter = 0, reset_next = 0;
@@ -264,10 +264,15 @@ static void lbfgs_free(void *p) {
 int b200_lbfgs_destroy(b200_lbfgs *s) {
   if (!s) return B200_OK;
   b200_ctx *ctx = s->ctx;
+  if (!ctx_is_live(ctx)) { // the context went first (and with it the stream): nothing to park it in
+    cudaDeviceSynchronize();
+    lbfgs_free(s);
+    return B200_OK;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (s->last_net) net_xq_release_solver(s->last_net); // end of the minimisation: the caller may refill x
-  s->last_net = nullptr;
+  if (s->last_net_uid) net_xq_release_solver((b200_net *)net_lookup(s->last_net_uid)); // end of the minimisation: the caller may refill x
+  s->last_net_uid = 0;
   if (ctx->lbfgs_pool.size() < 4) { // park it: the next solver of this shape skips cudaMalloc / cudaFree / graph instantiation
     ctx->lbfgs_pool_free = lbfgs_free;
     ctx->lbfgs_pool.push_back(s);
@@ -286,7 +291,7 @@ void lbfgs_pool_forget_net(b200_ctx *ctx, unsigned long long net_uid) {
       lbfgs_drop_graphs(c);
       memset(c->gkey, 0, sizeof(c->gkey));
     }
-    if (c->last_net && c->last_net->uid == net_uid) c->last_net = nullptr;
+    if (c->last_net_uid == net_uid) c->last_net_uid = 0;
   }
 }
 } // namespace b200
@@ -327,7 +332,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
   // have refilled the same device buffer
   if (net && net->prec != B200_PREC_FP32) {
     B200_TRY(net_quantize_input(net, input, batch, !s->started));
-    s->last_net = net;
+    s->last_net_uid = net->uid;
   }
   if (!s->started) {
     // loss = loss_grad(params, grad, ...)   lbfgs.cuh:78 / lbfgs.hpp:44
@@ -610,7 +615,7 @@ static int lbfgs_run_sharded(b200_lbfgs *s, b200_net *net, float *params, const 
   long evals = 0;
   if (net->prec != B200_PREC_FP32) {
     B200_TRY(net_quantize_input(net, input, batch, !s->started));
-    s->last_net = net;
+    s->last_net_uid = net->uid;
   }
   struct Defer { b200_net *n; ~Defer() { n->defer_reduce = false; } } defer{net};
   net->defer_reduce = true;
