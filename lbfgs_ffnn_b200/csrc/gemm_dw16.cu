@@ -37,6 +37,7 @@ constexpr int kDConvBytes = kDMT * kDConvTile;
 constexpr int kDAtom = kDK * 128;         // one MN atom column of a stage: [32 K-rows][64 elements]
 constexpr int kDNS = 6;                   // A and B rings share one stage index (one commit frees both)
 constexpr int kDThreads = 256;            // warp 0 X TMA, 1 MMA issue, 2 TMEM alloc, 3 delta TMA, 4-7 epilogue
+constexpr int kMinKbPerSplit = 12;        // split-K plan: K blocks (of 32 samples) a slice holds at least
 
 struct Dw16Params {
   int in_dim, out_dim;    // layer 0: in (784), out (<= 128)
@@ -373,7 +374,9 @@ bool dw16_applicable(const b200_net *net) {
 int dw16_plan(const b200_net *net, long batch, int *splits) {
   const int tiles = ceil_div(net->dims[0] + 1, kDMT * kDM);
   const int kblocks = ceil_div(batch, kDK);
-  const int s = std::max(1, std::min(net->ctx->num_sms / tiles, kblocks));
+  // at least kMinKbPerSplit K blocks per slice: a short shard (several GPUs, mini-batches) then writes fewer slices, and the
+  // combine pass (finalize_grad_kernel), whose cost is the number of slices, shrinks with it
+  const int s = std::max(1, std::min(net->ctx->num_sms / tiles, ceil_div(kblocks, kMinKbPerSplit)));
   const int per = ceil_div(kblocks, s);
   *splits = ceil_div(kblocks, per);
   return per;
@@ -412,7 +415,7 @@ int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done) {
 // split plan of the mid16 dW: ONE group of two M tiles (hi / lo of the 128 features), so up to one split per SM
 int mid16_dw_plan(const b200_net *net, long batch, int *splits) {
   const int kblocks = ceil_div(batch, kDK);
-  const int s = std::max(1, std::min(net->ctx->num_sms, kblocks));
+  const int s = std::max(1, std::min(net->ctx->num_sms, ceil_div(kblocks, kMinKbPerSplit)));
   const int per = ceil_div(kblocks, s);
   *splits = ceil_div(kblocks, per);
   return per;

@@ -67,4 +67,20 @@ if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu.log 2>&1
   echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu.log
 fi
+if has ncufull; then  # the top kernels once, full metric set (DRAM bytes, pipe utilisation, stall reasons)
+  CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-cuda"
+  timeout 300 $CMD > $OUT/${TAG}_ncufull_plain.log 2>&1 && \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"fwd16_kernel|dw16_kernel|lbfgs_direction_kernel|finalize_grad_kernel|tail_" -s 60 -c 14 -o $OUT/${TAG}_full $CMD > $OUT/${TAG}_ncufull.log 2>&1
+  echo "ncufull rc=$?"; tail -3 $OUT/${TAG}_ncufull.log
+fi
+if has racecheck; then
+  timeout 300 python tools/sanitize_case.py > $OUT/${TAG}_sanitize_plain.log 2>&1 && \
+  timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_case.py > $OUT/${TAG}_racecheck.log 2>&1
+  echo "racecheck rc=$?"; tail -12 $OUT/${TAG}_racecheck.log
+fi
+if has memcheck; then
+  timeout 300 python tools/sanitize_case.py > $OUT/${TAG}_sanitize_plain.log 2>&1 && \
+  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_case.py > $OUT/${TAG}_memcheck.log 2>&1
+  echo "memcheck rc=$?"; tail -12 $OUT/${TAG}_memcheck.log
+fi
 echo "session $TAG done"
