@@ -239,6 +239,9 @@ def main():
     ap.add_argument("--config", default="lbfgs", choices=["lbfgs", "slbfgs", "gd", "sgd", "c5"],
                     help="lbfgs (default) = the headline; the others are secondary lines (bench_extra.py)")
     ap.add_argument("--samples", type=int, default=None, help="override the sample count (testing)")
+    ap.add_argument("--float-input", action="store_true",
+                    help="inputs that are NOT 8-bit pixels (x = u/255 + noise): layer 0 cannot use the exact fp16 copy and runs the "
+                         "generic 3xTF32 tcgen05 kernels on the fp32 array (secondary line: the headline workload is image data)")
     args = ap.parse_args()
     global DIMS, ACTS, TOTAL_SAMPLES
     if args.net:
@@ -257,7 +260,7 @@ def main():
         bench_extra.run(args, rank, local_rank, world)
         return
     args.warmup = max(args.warmup, 3)
-    WORKLOAD = workload_name(DIMS)
+    WORKLOAD = workload_name(DIMS) + ("_floatinput" if args.float_input else "")
     FLOP_PER_SAMPLE = flop_per_sample(DIMS)
 
     import torch
@@ -278,6 +281,8 @@ def main():
     assert TOTAL_SAMPLES % world == 0
     shard = TOTAL_SAMPLES // world
     Xh, Th = P.synthetic_mnist(TOTAL_SAMPLES)
+    if args.float_input:  # same images plus sub-quantum noise: no longer exactly float(u)/255.0f
+        Xh = (Xh + np.float32(1e-3) * np.random.RandomState(7).rand(*Xh.shape).astype(np.float32)).astype(np.float32)
     Xs = torch.from_numpy(Xh[rank * shard:(rank + 1) * shard]).pin_memory()
     Ts = torch.from_numpy(Th[rank * shard:(rank + 1) * shard]).pin_memory()
 
@@ -428,7 +433,7 @@ def main():
         #   tail_fwd / tail_bwd  last layer in two passes over the penultimate activations
         #   lbfgs_direction  two-loop recursion, (4k+2)*n*4 bytes
         B, K0, N0 = shard, DIMS[0], DIMS[1]
-        u8 = args.precision != "fp32"
+        u8 = args.precision != "fp32" and not args.float_input
         x_bytes = B * ((K0 + 1 + 63) // 64 * 64) * 2 if u8 else B * K0 * 4  # 8-bit pixels: the block-major fp16 copy [in | 1 | pad]
         work = {
             "fwd0": dict(flops=2.0 * B * K0 * N0, bytes=x_bytes + 4.0 * B * N0),

@@ -235,3 +235,24 @@ def test_deeper_nets_chain_the_fp16_delta_scale(handle, oracle, dims):
         loss, g, _ = _eval(handle, dims, acts, w, X, T, "tf32x3")
         assert abs(loss - lo) <= 2e-5 * abs(lo), (dims, batch, loss, lo)
         assert rel_l2(g, go) <= 2e-5, (dims, batch, rel_l2(g, go))
+
+
+@pytest.mark.parametrize("which", [0, 5])
+@pytest.mark.parametrize("batch", [1000, 60000])
+def test_evaluation_is_bit_reproducible(handle, oracle, which, batch):
+    """the same evaluation 12 times: every kernel combines its partial results in a fixed order, so loss and gradient must be
+    BIT-identical run to run. (compute-sanitizer is closed on this pool — profiles/r02_sanitizer.md — so this is the race detector
+    the suite has for the mbarrier / TMA / TMEM pipelines: a missing wait or fence shows up as a run that differs.)"""
+    dims, acts = NETS[which]
+    onet, w, X, T = make_problem(oracle, dims, acts, batch)
+    net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
+    dx, dt = upload(X), upload(T)
+    assert net.quantize_input(dx, batch)
+    ref_loss, ref_g = None, None
+    for rep in range(12):
+        loss = net.compute_loss_and_grad(dx, dt, batch)
+        g = net.get_grads()
+        if rep == 0:
+            ref_loss, ref_g = loss, g
+        else:
+            assert loss == ref_loss and np.array_equal(g, ref_g), rep
