@@ -752,7 +752,7 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   const bool x3 = net->prec == B200_PREC_TF32X3;
   // layer 0 with an input that is exactly u/255: read the 4x smaller uint8 copy (net_quantize_input)
   const uint8_t *xq = (l == 0 && (tc_mask() & 16) == 0) ? net_xq_lookup(net, in, batch) : nullptr;
-  if (xq && !fuse) { // persistent fp16 kernel (gemm_fwd16.cu); the last layer then runs in tail_layer.cu
+  if (l == 0 && (tc_mask() & 16) == 0 && !fuse) { // persistent fp16 kernel (gemm_fwd16.cu); the last layer then runs in tail_layer.cu
     X16View xv;
     if (net_x16_view(net, in, batch, &xv)) B200_TRY(fwd16_forward_layer(net, l, params, xv, batch, done));
     if (*done) return B200_OK;

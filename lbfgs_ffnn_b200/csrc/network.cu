@@ -483,6 +483,7 @@ int net_ensure(b200_net *net, long batch) {
 void net_xq_clear(b200_net *net) {
   if (net->xq.valid) ++net->config_gen;
   net->xq.valid = false;
+  net->xg.src = nullptr;
   net->xq.user = false;
   net->xq.src = nullptr;
   net->xq.rows = 0;
@@ -531,7 +532,38 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
   return B200_OK;
 }
 
+void *net_gather16_buffer(b200_net *net, long rows) {
+  if (!net->xq.valid || !net->xq.data16) return nullptr;
+  if (rows > net->xg.cap) {
+    if (net->xg.data16) cudaFree(net->xg.data16);
+    net->xg.data16 = nullptr;
+    net->xg.cap = 0;
+    if (cudaMalloc(&net->xg.data16, sizeof(__half) * (size_t)rows * 64 * net->xq.nblocks16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    net->xg.cap = rows;
+    ++net->config_gen;
+  }
+  net->xg.src = nullptr; // (contents about to change)
+  return net->xg.data16;
+}
+void net_gather16_register(b200_net *net, const float *src, long rows) {
+  net->xg.src = src;
+  net->xg.rows = rows;
+}
+const void *net_x16_source(const b200_net *net, long *rows_total, int *nblocks) {
+  if (!net->xq.valid || !net->xq.data16) return nullptr;
+  *rows_total = net->xq.rows;
+  *nblocks = net->xq.nblocks16;
+  return net->xq.data16;
+}
+
 bool net_x16_view(b200_net *net, const float *x, long batch, X16View *v) {
+  if (net->xg.src == x && net->xg.rows == batch && net->xg.data16 && net->xq.valid) { // a gathered mini-batch
+    v->base = net->xg.data16;
+    v->rows_total = batch;
+    v->row0 = 0;
+    v->nblocks = net->xq.nblocks16;
+    return true;
+  }
   if (!net->xq.valid || !net->xq.data16 || x < net->xq.src) return false;
   const size_t off = (size_t)(x - net->xq.src);
   const int in = net->dims[0];
@@ -603,7 +635,7 @@ int net_forward(b200_net *net, const float *params, const float *x, long batch) 
   net->split_src = nullptr;
   if (mid) B200_TRY(mid16_ensure(net, batch));
   else B200_TRY(tc_split_params(net, params));
-  if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
+  if (net->prec != B200_PREC_FP32 && net_x16_view(net, x, batch, &xv0)) B200_TRY(fwd16_prepare(net, params));
   const float *cur = x;
   for (int l = 0; l < net->nlayers(); ++l) {
     bool done = false;
@@ -645,14 +677,14 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   net->split_src = nullptr;
   if (mid) B200_TRY(mid16_ensure(net, batch));
   else B200_TRY(tc_split_params(net, params)); // (the TF32 hi / lo split of the parameters feeds the generic kernels only)
-  if (net->prec != B200_PREC_FP32 && net_xq_lookup(net, x, batch)) B200_TRY(fwd16_prepare(net, params));
+  const bool have16 = net->prec != B200_PREC_FP32 && net_x16_view(net, x, batch, &xv0); // fp16 copy of this batch (input slice or gathered)
+  if (have16) B200_TRY(fwd16_prepare(net, params));
   // forward sweep
   const float *cur = x;
   bool fused_last = false; // last layer, loss, delta_L and delta_{L-1} produced by the penultimate layer's epilogue
   bool tail_done = false;  // ... or by the one-pass last-layer kernel, which also produces the [dW_L; db_L] partials
   const bool use_tail = tail_applicable(net);
-  const uint8_t *xq0 = (use_tail && net->prec != B200_PREC_FP32 && dw16_applicable(net)) ? net_xq_lookup(net, x, batch) : nullptr;
-  const bool use_dw16 = xq0 != nullptr && (L == 2 || net->chain_ready); // layer-0 dW on the fp16 tensor cores: the tail writes delta_0 as scaled fp16 {hi | lo}
+  const bool use_dw16 = use_tail && have16 && dw16_applicable(net) && (L == 2 || net->chain_ready); // layer-0 dW on the fp16 tensor cores: the tail writes delta_0 as scaled fp16 {hi | lo}
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
     if (last && fused_last) break;
@@ -890,6 +922,7 @@ int b200_net_destroy(b200_net *net) {
   if (net->xq.data) cudaFree(net->xq.data);
   if (net->xq.data16) cudaFree(net->xq.data16);
   if (net->xq.flag) cudaFree(net->xq.flag);
+  if (net->xg.data16) cudaFree(net->xg.data16);
   if (net->partials) cudaFree(net->partials);
   if (net->fin_part) cudaFree(net->fin_part);
   if (net->eval_out) cudaFree(net->eval_out);

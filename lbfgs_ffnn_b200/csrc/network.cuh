@@ -55,6 +55,16 @@ struct b200_net {
     int *flag = nullptr; // device
   } xq;
 
+  // a mini-batch GATHERED from the quantised input (S-LBFGS, random-batch SGD): rows idx[i] of the fp16 copy above, collected
+  // into the same block-major layout, next to the fp32 rows the caller passes to net_eval (slbfgs.cu: gather16_rows_kernel).
+  // While registered, evaluations of exactly (src, rows) run the fp16 layer-0 kernels like a slice of the input would.
+  struct GatherQ {
+    const float *src = nullptr; // the gathered fp32 rows (identity of the view)
+    long rows = 0;
+    void *data16 = nullptr;     // [nblocks16][cap][64] halves, used with rows_total = rows
+    long cap = 0;
+  } xg;
+
   float *w_hi = nullptr, *w_lo = nullptr; // 3xTF32: hi / lo split of the parameter vector of the current evaluation
   const float *split_src = nullptr;       // parameters of the current evaluation whose TF32 split has not been launched yet (lazy)
   // fp16 forward of layer 0 on a uint8 input (gemm_fwd16.cu): per-neuron-scaled hi / lo fp16 weights [out][ldk], 1/(255 s_o)
@@ -136,6 +146,11 @@ const uint8_t *net_xq_lookup(b200_net *net, const float *x, long batch);
 struct X16View { const void *base; long rows_total, row0; int nblocks; };
 // the fp16 copy and the row range matching x (row-aligned sub-range of the quantised input); false if there is none
 bool net_x16_view(b200_net *net, const float *x, long batch, X16View *v);
+// gathered mini-batches (b200_net::GatherQ): buffer for up to `rows` rows (nullptr unless the input is quantised), and the
+// registration of the batch just gathered into it as the fp16 view of the fp32 rows `src`
+void *net_gather16_buffer(b200_net *net, long rows);
+void net_gather16_register(b200_net *net, const float *src, long rows);
+const void *net_x16_source(const b200_net *net, long *rows_total, int *nblocks); // the quantised input's fp16 copy, or nullptr
 bool net_spec_capable(b200_net *net, const float *x, long batch);
 // the skinny last layer in one pass: forward, loss, both deltas and the [dW_L; db_L] partials (tail_layer.cu)
 bool tail_applicable(const b200_net *net);

@@ -77,6 +77,31 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
   }
 }
 
+// the same rows of the quantised input's fp16 copy (block-major [nblocks][rows_src][64] halves) into a block-major copy of the
+// mini-batch [nblocks][count][64]: one warp per (sample, block) pair moves one 128-byte run
+__global__ void __launch_bounds__(256) gather16_rows_kernel(const uint32_t *__restrict__ src16, long rows_src, int nblocks,
+                                                            const uint32_t *__restrict__ idx, int count, uint32_t *__restrict__ dst16) {
+  const int lane = threadIdx.x & 31;
+  const long warps = ((long)gridDim.x * blockDim.x) >> 5;
+  const long total = (long)count * nblocks;
+  for (long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    const int b = (int)(w / count), i = (int)(w - (long)b * count);
+    dst16[((long)b * count + i) * 32 + lane] = __ldg(src16 + ((long)b * rows_src + idx[i]) * 32 + lane);
+  }
+}
+// gathers the fp16 rows next to the fp32 ones and registers them as the batch's fp16 view (no-op unless the input is quantised)
+static int gather16(b200_net *net, const float *Xb, const uint32_t *d_idx, int count, cudaStream_t st) {
+  long rows_src = 0;
+  int nb = 0;
+  const void *src = net_x16_source(net, &rows_src, &nb);
+  void *dst = src ? net_gather16_buffer(net, count) : nullptr;
+  if (!dst) return B200_OK;
+  B200_LAUNCH(gather16_rows_kernel, std::min(1184, ceil_div((long)count * nb, 8)), 256, 0, st, (const uint32_t *)src, rows_src, nb, d_idx,
+              count, (uint32_t *)dst);
+  net_gather16_register(net, Xb, count);
+  return B200_OK;
+}
+
 // v = g_t - g_k + mu   (s_lbfgs.hpp:225-228)
 __global__ void __launch_bounds__(256) vr_combine_kernel(size_t n, const float *__restrict__ gt, const float *__restrict__ gk,
                                                          const float *__restrict__ mu, float *__restrict__ v) {
@@ -210,6 +235,9 @@ int sgd_random_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const f
   int iters = 0;
   float elapsed = 0.f;
   cudaEvent_t ev0 = ctx->ev_a, ev1 = ctx->ev_b;
+  // 8-bit-pixel inputs: the fp16 copy of the data set (and of every gathered mini-batch) feeds the fp16 layer-0 kernels
+  if (net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, N, true));
+  struct ClearQ { b200_net *n; ~ClearQ() { net_xq_release_solver(n); } } clear_q{net};
   while (iters < o.max_iters) {
     if (hist) B200_CUDA(cudaEventRecord(ev0, st));
     for (int t = 0; t < m; ++t) sampler.draw((size_t)N, (size_t)b, h_idx + (size_t)t * b);
@@ -217,6 +245,7 @@ int sgd_random_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const f
     for (int t = 0; t < m; ++t) {
       B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(b, 8)), 256, 0, st, input, target, d_idx + (size_t)t * b, b, in_dim,
                   out_dim, Xb, Tb);
+      B200_TRY(gather16(net, Xb, d_idx + (size_t)t * b, b, st));
       ++evals;
       B200_TRY(net_eval(net, params, Xb, Tb, b, b, grad, scratch)); // grad /= current_bs (:266)
       if (o.momentum > 0.0f) B200_TRY(launch_momentum_step(Nn, o.momentum, o.lr, grad, vel, params, st));
@@ -296,6 +325,10 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   // multi-GPU: every rank holds the full data set; each batch's index list is split into W contiguous chunks
   B200_REQUIRE(b % W == 0 && b_H % W == 0 && N % W == 0, "batch sizes must be divisible by the number of ranks");
 
+  // 8-bit-pixel inputs: the fp16 copy of the data set (every rank holds all of it) feeds the full-batch evaluations through its
+  // row slices and the mini-batches through gathered copies (gather16)
+  if (net->prec != B200_PREC_FP32) B200_TRY(net_quantize_input(net, input, total_samples, true));
+  struct ClearQ { b200_net *n; ~ClearQ() { net_xq_release_solver(n); } } clear_q{net};
   const float old_l2 = net->l2;
   net->l2 = o.lambda;
   struct RestoreL2 { b200_net *n; float v; ~RestoreL2() { n->l2 = v; } } restore{net, old_l2};
@@ -353,7 +386,8 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
   float *S = (float *)take(vec * mp), *Y = (float *)take(vec * mp);
   float *Xb = (float *)take(xb_bytes), *Tb = (float *)take(tb_bytes);
   uint32_t *d_idx = (uint32_t *)take(idx_bytes);
-  EvalOut *ev_scratch = (EvalOut *)take((sizeof(EvalOut) + 255) & ~size_t(255));
+  EvalOut *ev_scratch = (EvalOut *)take(128);
+  unsigned *gridbar = (unsigned *)take(128); // {arrivals, generation} of the fused direction kernel's grid barrier (zeroed with ws)
   float *pw = use_pair ? (float *)take(pvec) : nullptr, *pg = use_pair ? (float *)take(pvec) : nullptr;
   float *Tb2 = use_pair ? (float *)take(tb2_bytes) : nullptr;
   // one forward/backward of the pair network at (wa, wb) on the gathered batch; out = (g_a - g_b) * scale (+ add)
@@ -436,18 +470,23 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
       if (use_pair) { // both gradients from ONE forward/backward, v = g_t - g_k + mu formed as they are read back
         B200_TRY(pair_eval(wt, params, bl, b, 1.0f, mu, v));
       } else {
+        B200_TRY(gather16(net, Xb, d_idx + mb_off[t], bl, st));
         B200_TRY(net_eval(net, wt, Xb, Tb, bl, b, gt, ev_scratch));
         B200_TRY(net_eval(net, params, Xb, Tb, bl, b, gk, ev_scratch));
         B200_LAUNCH(vr_combine_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, mu, v);
       }
       // direction = H v (two-loop on the current ring), w_t -= eta * direction, history push (:230-233)
       DotsArgs da{S, Y, Nn, ld, view, v, nullptr, nullptr, nullptr, DOTS_NONE, 0, 0, partials};
-      B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
       SolveArgs sa{view, partials, nblk, DOTS_NONE, 0, POLICY_SLBFGS, 0, 0, 0.0, 0};
-      B200_TRY(launch_lbfgs_solve(sa, mp, st));
       float *wh_slot = Wh + (size_t)(wh_pushes % (L + 1)) * ld;
       ApplyArgs aa{S, Y, Nn, ld, view, v, d, wt, nullptr, -1.0, -o.step_size, wh_slot};
-      B200_TRY(launch_lbfgs_apply(aa, apply_blocks, st));
+      bool fused_dir = false; // dots -> grid barrier -> solve -> apply in one launch (histories of <= 32 slots)
+      B200_TRY(launch_lbfgs_direction(ctx, da, sa, aa, mp, nblk, gridbar, st, &fused_dir, nullptr, 0));
+      if (!fused_dir) {
+        B200_TRY(launch_lbfgs_dots(da, mp, nblk, st));
+        B200_TRY(launch_lbfgs_solve(sa, mp, st));
+        B200_TRY(launch_lbfgs_apply(aa, apply_blocks, st));
+      }
       ++wh_pushes;
 
       // 3. curvature pair every L steps (:236-261)
@@ -463,6 +502,7 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
           if (use_pair) { // the +- eps s pair in one forward/backward, y = (g+ - g-) / (2 eps) formed as they are read back
             B200_TRY(pair_eval(wp, wm, hl, b_H, 1.0f / (2.0f * fd_eps), nullptr, y));
           } else {
+            B200_TRY(gather16(net, Xb, d_idx + hb_off[t], hl, st));
             B200_TRY(net_eval(net, wp, Xb, Tb, hl, b_H, gt, ev_scratch));
             B200_TRY(net_eval(net, wm, Xb, Tb, hl, b_H, gk, ev_scratch));
             B200_LAUNCH(hvp_diff_kernel, vblocks(Nn), 256, 0, st, Nn, gt, gk, 1.0f / (2.0f * fd_eps), y);
