@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace b200 {
@@ -44,11 +45,10 @@ extern std::atomic<long> g_launches;
   } while (0)
 
 // every kernel launch in the library goes through this so b200_launch_count() is exact
-#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
-  do {                                                                          \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
-    ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
-    B200_CUDA(cudaGetLastError());                                              \
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                                   \
+  do {                                                                                                        \
+    B200_CUDA(::b200::launch_ex(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), 1, __VA_ARGS__)); \
+    ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                               \
   } while (0)
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
@@ -65,12 +65,49 @@ struct EnvFlags {
   bool nvtx = false;               // B200_NVTX: NVTX ranges around direction / evaluation / collective
   int fwd16 = -1, dw16 = -1, tail = -1, tail_fwd = -1; // B200_FWD16 / _DW16 / _TAIL / _TAIL_FWD: -1 unset, else the integer
   int mid16 = -1;                  // B200_MID16: 0 = hidden layers on the generic TF32 kernels
+  int pair = 0;                    // B200_PAIR: bit0 = layer-0 forward as CTA pairs (cta_group::2, weights split between the two SMs)
+  bool pdl = true;                 // B200_PDL=0: plain stream order instead of programmatic dependent launches
+  int dw_tail = 0;                 // B200_DW_TAIL=1: the one-tile last feature group of the fp16 dW kernel gets fewer, longer slices
+  int ring = 0;                    // B200_RING: bit0 layer-0 forward, bit1 layer-0 dW: deeper X ring than weight / delta ring
+  int diag = 0;                    // B200_DIAG: timing experiments of the fp16 kernels (parts switched off; results are wrong)
   int tc_mask = 7;                 // B200_TC_MASK: bit0 FWD, bit1 DX, bit2 DW on the tensor cores; bit3 / bit4 see gemm_tc.cu
   int dw_bn = 0;                   // B200_DW_BN: 128 / 256, 0 = by precision mode
   long p2p_spin_limit = 0;         // B200_P2P_SPIN_LIMIT: polls before p2p_reduce_kernel gives up on a peer (0 = default)
 };
 const EnvFlags &env();
 void env_reload();
+
+// ---- launches -------------------------------------------------------------------------------------
+// Programmatic dependent launch (B200_PDL, default on): every kernel of the library starts with pdl_enter() — it lets the
+// NEXT kernel of the stream be launched at once (griddepcontrol.launch_dependents) and then waits until the PREVIOUS one has
+// completed and its memory is visible (griddepcontrol.wait). Launch latency, CTA rasterisation and whatever a kernel does
+// before it touches global memory overlap the tail of its predecessor; a CUDA graph captured from these launches carries
+// programmatic edges. Every kernel waits before it returns on every path, so completion stays transitive along the stream.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned na = 0;
+  if (env().pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster_x; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // ---- NCCL, loaded lazily with dlopen so the single-GPU path has no NCCL dependency -------------
 struct NcclApi;

@@ -46,6 +46,11 @@ void env_reload() {
   e.tail = num("B200_TAIL", -1);
   e.tail_fwd = num("B200_TAIL_FWD", -1);
   e.mid16 = num("B200_MID16", -1);
+  e.pair = num("B200_PAIR", 0);
+  e.diag = num("B200_DIAG", 0);
+  e.ring = num("B200_RING", 0);
+  e.dw_tail = num("B200_DW_TAIL", 0);
+  e.pdl = num("B200_PDL", 1) != 0;
   e.tc_mask = num("B200_TC_MASK", 7);
   e.dw_bn = num("B200_DW_BN", 0);
   if (const char *s = std::getenv("B200_P2P_SPIN_LIMIT")) e.p2p_spin_limit = std::atol(s);

@@ -35,13 +35,17 @@ constexpr int kDK = 32;                   // samples per stage
 constexpr int kDConvTile = kDK * kDM * 2; // fp16: two feature atoms of [32 K-rows][128 B]
 constexpr int kDConvBytes = kDMT * kDConvTile;
 constexpr int kDAtom = kDK * 128;         // one MN atom column of a stage: [32 K-rows][64 elements]
-constexpr int kDNS = 6;                   // A and B rings share one stage index (one commit frees both)
+constexpr int kDNS = 6;                   // default depth: A and B rings share one stage index (one commit frees both)
 constexpr int kDThreads = 256;            // warp 0 X TMA, 1 MMA issue, 2 TMEM alloc, 3 delta TMA, 4-7 epilogue
 constexpr int kMinKbPerSplit = 12;        // split-K plan: K blocks (of 32 samples) a slice holds at least
 
 struct Dw16Params {
   int in_dim, out_dim;    // layer 0: in (784), out (<= 128)
   int k_blocks, kb_per_split;
+  // grid: full_groups * splits CTAs that own two feature tiles (split-major, so the CTAs of one slice of the samples run side
+  // by side and share its delta tiles in L2), then tail_splits CTAs for a last group that holds ONE tile: it has half the MMAs
+  // per K block, so it gets fewer, longer slices and the CTAs finish together (784 + 1 features = 3 full groups + 17 rows)
+  int full_groups, splits, tail_splits, kb_per_tail;
   float *partial;         // [split][(in+1)*out]
   unsigned long long partial_stride;
   const float *scale_inv; // device scalar 1 / S of the fp16 delta
@@ -49,15 +53,18 @@ struct Dw16Params {
   const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
   int spec;
   long long *dbg;
+  int diag;               // B200_DIAG (timing experiments only): bit0 no X loads, bit1 no delta loads, bit2 no MMAs, bit3 no stores
   const float *rowscale;  // FOLD: [128] 1 / t_f of the activation pair
 };
 
-template <int NB> struct DPlan { // NB = 2 * out rounded up to 128 / 256: width of [delta_hi | delta_lo]
+// NX / ND: depth of the X ring (HBM) and of the delta ring (L2-resident after the first feature group has read it)
+template <int NB, int NX = kDNS, int ND = kDNS> struct DPlan { // NB = 2 * out rounded up to 128 / 256: width of [delta_hi | delta_lo]
   static constexpr int kBStage = NB * kDK * 2;
   static constexpr int kOffConv = 0;
-  static constexpr int kOffB = kDNS * kDConvBytes;
-  static constexpr int kOffBar = kOffB + kDNS * kBStage;
-  static constexpr int kTotal = kOffBar + 256 + 1024;
+  static constexpr int kOffB = NX * kDConvBytes;
+  static constexpr int kOffBar = kOffB + ND * kBStage;
+  static constexpr int kTotal = kOffBar + 512 + 1024;
+  static_assert(kTotal <= 227 * 1024, "shared memory plan exceeds the SM");
 };
 
 __device__ __forceinline__ void umma_f16_d(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -79,12 +86,13 @@ __device__ __forceinline__ uint64_t desc_mn16(uint32_t saddr) { return make_desc
 // FOLD (hidden layer 1, b200_net::Mid16): the A operand is an activation PAIR — M tile 0 holds the hi halves of the 128
 // features, tile 1 their lo halves — so the two accumulators of a CTA are two terms of the same product and the epilogue adds
 // them (with the hi | lo column halves of the delta pair: four terms), scales row f by 1 / (t_f S) and writes ONE 128-row tile.
-template <int NB, bool FOLD>
+template <int NB, bool FOLD, int NX, int ND>
 __global__ void __launch_bounds__(kDThreads, 1)
 dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmOut,
             const Dw16Params p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
-  using Plan = DPlan<NB>;
+  using Plan = DPlan<NB, NX, ND>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
@@ -92,22 +100,29 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   auto b_a = [&](int s) { return base + Plan::kOffB + s * Plan::kBStage; };
   const uint32_t bars = base + Plan::kOffBar;
   auto conv_full = [&](int s) { return bars + 8 * (s); };
-  auto b_full = [&](int s) { return bars + 8 * (kDNS + s); };
-  auto st_empty = [&](int s) { return bars + 8 * (2 * kDNS + s); }; // MMAs of the stage done: A and B tiles reusable
-  const uint32_t acc_full = bars + 8 * (3 * kDNS);
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (3 * kDNS + 1));
+  auto b_full = [&](int s) { return bars + 8 * (NX + s); };
+  auto st_empty = [&](int s) { return bars + 8 * (NX + ND + s); }; // MMAs of the stage done: the A tile (NX == ND: and the B tile) reusable
+  auto b_empty = [&](int s) { return NX == ND ? st_empty(s) : bars + 8 * (2 * NX + ND + s); };
+  const uint32_t acc_full = bars + 8 * (2 * NX + 2 * ND);
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bp + Plan::kOffBar + 8 * (2 * NX + 2 * ND + 1));
+  static_assert(2 * NX + 2 * ND + 2 <= 64, "barrier table");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = p.dbg ? clock64() : 0;
-  const int m0 = blockIdx.x * (kDMT * kDM);
+  const bool tail_cta = (int)blockIdx.x >= p.full_groups * p.splits;
+  const int split = tail_cta ? (int)blockIdx.x - p.full_groups * p.splits : (int)blockIdx.x / p.full_groups;
+  const int group = tail_cta ? p.full_groups : (int)blockIdx.x - split * p.full_groups;
+  const int per = tail_cta ? p.kb_per_tail : p.kb_per_split;
+  const int m0 = group * (kDMT * kDM);
   const int nmt = min(kDMT, (p.in_dim + 1 - m0 + kDM - 1) / kDM); // M tiles of this CTA that hold features (the last group may hold one)
-  const int kb_begin = blockIdx.y * p.kb_per_split, kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+  const int kb_begin = split * per, kb_end = min(p.k_blocks, kb_begin + per);
   const int nkb = max(0, kb_end - kb_begin);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmD);
-    for (int s = 0; s < kDNS; ++s) { mbar_init(conv_full(s), 1); mbar_init(b_full(s), 1); mbar_init(st_empty(s), 1); }
+    for (int s = 0; s < NX; ++s) { mbar_init(conv_full(s), 1); mbar_init(st_empty(s), 1); }
+    for (int s = 0; s < ND; ++s) { mbar_init(b_full(s), 1); if (NX != ND) mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -128,12 +143,13 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(st_empty(s), ph ^ 1);
+        if (p.diag & 1) { mbar_arrive(conv_full(s)); if (++s == NX) { s = 0; ph ^= 1; } continue; }
         mbar_expect_tx(conv_full(s), nmt * kDConvTile);
         for (int t = 0; t < nmt; ++t)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_3d(conv_a(s) + t * kDConvTile + j * kDAtom, &tmX, conv_full(s), 0, p.row0 + kb * kDK, (m0 + t * kDM) / 64 + j);
-        if (++s == kDNS) { s = 0; ph ^= 1; }
+        if (++s == NX) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -142,11 +158,12 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(st_empty(s), ph ^ 1);
+        mbar_wait(b_empty(s), ph ^ 1);
+        if (p.diag & 2) { mbar_arrive(b_full(s)); if (++s == ND) { s = 0; ph ^= 1; } continue; }
         mbar_expect_tx(b_full(s), Plan::kBStage);
 #pragma unroll
         for (int j = 0; j < NB / 64; ++j) tma_load_2d(b_a(s) + j * kDAtom, &tmD, b_full(s), 64 * j, kb * kDK);
-        if (++s == kDNS) { s = 0; ph ^= 1; }
+        if (++s == ND) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -154,20 +171,20 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     if (lane == 0) { // ===== MMA issuer ======================================================================
       const uint32_t idesc = make_idesc_f16_mn(NB);
       const uint64_t dA0 = desc_mn16(conv_a(0)), dB0 = desc_mn16(b_a(0));
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, sb = 0;
+      uint32_t ph = 0, phb = 0;
       long long waited = 0, waited_b = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(conv_full(s), ph);
         const long long t1 = p.dbg ? clock64() : 0;
-        mbar_wait(b_full(s), ph);
+        mbar_wait(b_full(sb), phb);
         if (p.dbg) { waited += t1 - t0; waited_b += clock64() - t1; }
         tc_fence_after();
-        const uint64_t da = dA0 + (uint64_t)(s * (kDConvBytes >> 4)), db = dB0 + (uint64_t)(s * (Plan::kBStage >> 4));
+        const uint64_t da = dA0 + (uint64_t)(s * (kDConvBytes >> 4)), db = dB0 + (uint64_t)(sb * (Plan::kBStage >> 4));
 #pragma unroll
         for (int t = 0; t < kDMT; ++t) {
-          if (t < nmt) {
+          if (t < nmt && !(p.diag & 4)) {
 #pragma unroll
             for (int ks = 0; ks < kDK / 16; ++ks) // 16 samples = two 8-row K groups = 2048 B further into every atom
               umma_f16_d(tmem_base + t * NB, da + t * (kDConvTile >> 4) + 128 * ks, db + 128 * ks, idesc,
@@ -175,10 +192,12 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
           }
         }
         umma_commit(st_empty(s));
-        if (++s == kDNS) { s = 0; ph ^= 1; }
+        if constexpr (NX != ND) umma_commit(b_empty(sb));
+        if (++s == NX) { s = 0; ph ^= 1; }
+        if (++sb == ND) { sb = 0; phb ^= 1; }
       }
       umma_commit(acc_full);
-      if (p.dbg) { p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = waited; p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x) + 2] = waited_b; }
+      if (p.dbg) { p.dbg[4 * blockIdx.x + 1] = waited; p.dbg[4 * blockIdx.x + 2] = waited_b; }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -230,8 +249,8 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tmOut, stage_a, c0, m0 + t2 * kDM + (warp & 3) * 32, blockIdx.y);
+        if (lane == 0 && !(p.diag & 8)) {
+          tma_store_3d(&tmOut, stage_a, c0, m0 + t2 * kDM + (warp & 3) * 32, split);
           tma_store_commit();
         }
       }
@@ -241,7 +260,7 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  if (p.dbg && threadIdx.x == 0) p.dbg[4 * (blockIdx.y * gridDim.x + blockIdx.x)] = clock64() - t_start;
+  if (p.dbg && threadIdx.x == 0) p.dbg[4 * blockIdx.x] = clock64() - t_start;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kDMT * NB)) : "memory");
@@ -327,10 +346,10 @@ int make_map_3d_d(CUtensorMap *tm, const float *ptr, unsigned long long dim0, un
   return B200_OK;
 }
 
-template <int NB, bool FOLD>
+template <int NB, bool FOLD, int NX = kDNS, int ND = kDNS>
 int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap &tout, const Dw16Params &p, dim3 grid, cudaStream_t st) {
-  auto kern = dw16_kernel<NB, FOLD>;
-  constexpr int smem = DPlan<NB>::kTotal;
+  auto kern = dw16_kernel<NB, FOLD, NX, ND>;
+  constexpr int smem = DPlan<NB, NX, ND>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -339,23 +358,25 @@ int launch_dw16(const CUtensorMap &tx, const CUtensorMap &td, const CUtensorMap 
   static long long *dbg = nullptr;
   const bool timing = env().tc_timing;
   Dw16Params pp = p;
+  pp.diag = env().diag;
   if (timing) {
     if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 4 * 1024));
     B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 4 * 1024, st));
     pp.dbg = dbg;
   }
-  kern<<<grid, kDThreads, smem, st>>>(tx, td, tout, pp);
+  B200_CUDA(launch_ex(kern, grid, dim3(kDThreads), (size_t)smem, st, 1, tx, td, tout, pp));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  B200_CUDA(cudaGetLastError());
   if (timing) {
     std::vector<long long> h(4 * 1024);
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    const int n = std::min(1024, (int)(grid.x * grid.y));
-    double tot = 0, iw = 0, ib = 0;
-    for (int i = 0; i < n; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2]; }
-    fprintf(stderr, "[dw16 timing] NB %d grid %ux%u K blocks/CTA %d: per CTA total %.0f clk, issuer waiting: X %.0f, delta %.0f\n", NB, grid.x,
-            grid.y, p.kb_per_split, tot / n, iw / n, ib / n);
+    const int n = std::min(1024, (int)grid.x), nf = std::min(n, p.full_groups * p.splits);
+    double tot = 0, iw = 0, ib = 0, tot_t = 0;
+    for (int i = 0; i < nf; ++i) { tot += h[4 * i]; iw += h[4 * i + 1]; ib += h[4 * i + 2]; }
+    for (int i = nf; i < n; ++i) tot_t += h[4 * i];
+    fprintf(stderr, "[dw16 timing] NB %d rings %d/%d grid %d x %d + %d, K blocks/CTA %d (tail %d): per CTA total %.0f clk (tail CTAs %.0f), issuer waiting: "
+            "X %.0f, delta %.0f\n", NB, NX, ND, p.full_groups, p.splits, p.tail_splits, p.kb_per_split, p.kb_per_tail, tot / std::max(1, nf),
+            tot_t / std::max(1, n - nf), iw / std::max(1, nf), ib / std::max(1, nf));
   }
   return B200_OK;
 }
@@ -370,16 +391,39 @@ bool dw16_applicable(const b200_net *net) {
   return net->nlayers() == 2 || tail_chain16_applicable(net);
 }
 
-// split plan: one CTA per (feature tile, split); never more CTAs than SMs
-int dw16_plan(const b200_net *net, long batch, int *splits) {
-  const int tiles = ceil_div(net->dims[0] + 1, kDMT * kDM);
+// Split plan: one CTA per (group of two feature tiles, slice of the samples), never more CTAs than SMs. A last group that holds
+// one tile only (tail) runs half the MMAs per K block: it is given ~0.6x as many, longer slices (its CTAs still fetch whole delta
+// tiles), so that all CTAs finish together. Returns the K blocks per slice of the full groups.
+struct Dw16Plan { int full_groups, splits, per, tail_splits, per_tail, tail_row0; };
+static Dw16Plan dw16_plan_full(const b200_net *net, long batch) {
+  Dw16Plan pl{};
+  const int rows = net->dims[0] + 1, group_rows = kDMT * kDM;
   const int kblocks = ceil_div(batch, kDK);
+  const int rem = rows % group_rows;
+  const bool tail = rem > 0 && rem <= kDM && env().dw_tail != 0;
+  pl.full_groups = tail ? rows / group_rows : ceil_div(rows, group_rows);
   // at least kMinKbPerSplit K blocks per slice: a short shard (several GPUs, mini-batches) then writes fewer slices, and the
   // combine pass (finalize_grad_kernel), whose cost is the number of slices, shrinks with it
-  const int s = std::max(1, std::min(net->ctx->num_sms / tiles, ceil_div(kblocks, kMinKbPerSplit)));
-  const int per = ceil_div(kblocks, s);
-  *splits = ceil_div(kblocks, per);
-  return per;
+  const int by_k = ceil_div(kblocks, kMinKbPerSplit);
+  const int sms = net->ctx->num_sms;
+  int s = tail ? (int)((double)sms / (pl.full_groups + 0.6)) : sms / std::max(1, pl.full_groups);
+  s = std::max(1, std::min(s, by_k));
+  pl.per = ceil_div(kblocks, s);
+  pl.splits = ceil_div(kblocks, pl.per);
+  if (tail) {
+    int st = std::min(sms - pl.full_groups * pl.splits, (int)(0.6 * pl.splits + 0.5));
+    st = std::max(1, std::min(st, pl.splits));
+    if (pl.full_groups == 0) { st = std::max(1, std::min(sms, by_k)); }
+    pl.per_tail = ceil_div(kblocks, st);
+    pl.tail_splits = ceil_div(kblocks, pl.per_tail);
+    pl.tail_row0 = pl.full_groups * group_rows;
+  }
+  return pl;
+}
+int dw16_plan(const b200_net *net, long batch, int *splits) {
+  const Dw16Plan pl = dw16_plan_full(net, batch);
+  *splits = std::max(pl.splits, pl.tail_splits); // slices the partial buffer must hold
+  return pl.per;
 }
 
 // layer 0 [dW; db] partials from the uint8 input copy and the fp16 {hi | lo} delta written by tail_layer(want16)
@@ -393,21 +437,26 @@ int dw16_layer(b200_net *net, const X16View &x16, long batch, bool *done) {
   B200_TRY(make_map_3d_h(&tx, x16.base, 64, (unsigned long long)x16.rows_total, (unsigned long long)x16.nblocks, 64, kDK));
   B200_TRY(make_map_2d_d(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, net->delta16, 2 * N0, batch, (unsigned long long)2 * N0 * 2, 64, kDK,
                          CU_TENSOR_MAP_SWIZZLE_128B));
-  int splits = 1;
-  const int per = dw16_plan(net, batch, &splits);
+  const Dw16Plan pl = dw16_plan_full(net, batch);
+  const int splits = std::max(pl.splits, pl.tail_splits);
   Dw16Params p{};
   p.in_dim = K0; p.out_dim = N0;
-  p.k_blocks = ceil_div(batch, kDK); p.kb_per_split = per;
+  p.k_blocks = ceil_div(batch, kDK); p.kb_per_split = pl.per;
+  p.full_groups = pl.full_groups; p.splits = pl.full_groups > 0 ? pl.splits : 0; p.tail_splits = pl.tail_splits; p.kb_per_tail = pl.per_tail;
   p.partial = net->partials + net->part_off[0];
   p.partial_stride = (unsigned long long)(K0 + 1) * N0;
   p.scale_inv = net->scale16_inv;
   p.row0 = (int)x16.row0;
   p.spec_st = net->spec_st; p.spec = net->spec_flag;
-  const dim3 grid(ceil_div(K0 + 1, kDMT * kDM), splits);
+  const dim3 grid(p.full_groups * p.splits + p.tail_splits);
   B200_TRY(make_map_3d_d(&tout, p.partial, N0, K0 + 1, splits, 32, 32));
-  if (N0 == 128) B200_TRY((launch_dw16<256, false>(tx, td, tout, p, grid, net->ctx->stream)));
+  if (N0 == 128 && (env().ring & 2)) B200_TRY((launch_dw16<256, false, 8, 4>(tx, td, tout, p, grid, net->ctx->stream)));
+  else if (N0 == 128) B200_TRY((launch_dw16<256, false>(tx, td, tout, p, grid, net->ctx->stream)));
   else B200_TRY((launch_dw16<128, false>(tx, td, tout, p, grid, net->ctx->stream)));
-  net->splits_used[0] = splits;
+  // finalize_grad_kernel combines exactly the slices each row range has: rows [0, tail_row0) splits, the rest tail_splits
+  net->splits_used[0] = pl.full_groups > 0 ? pl.splits : pl.tail_splits;
+  net->dw0_tail_row0 = (pl.tail_splits > 0 && pl.full_groups > 0) ? pl.tail_row0 : -1;
+  net->dw0_tail_splits = pl.tail_splits;
   *done = true;
   return B200_OK;
 }
@@ -435,13 +484,14 @@ int mid16_dw_layer1(b200_net *net, long batch) {
   Dw16Params p{};
   p.in_dim = 2 * K1 - 1; p.out_dim = N1; // (in_dim + 1 = the 256 rows of the pair: both M tiles hold features)
   p.k_blocks = ceil_div(batch, kDK); p.kb_per_split = per;
+  p.full_groups = 1; p.splits = splits; p.tail_splits = 0; p.kb_per_tail = per;
   p.partial = net->partials + net->part_off[1];
   p.partial_stride = (unsigned long long)(K1 + 1) * N1;
   p.scale_inv = m.scale1_inv;
   p.rowscale = m.tinv;
   p.row0 = 0;
   p.spec_st = net->spec_st; p.spec = net->spec_flag;
-  const dim3 grid(1, splits);
+  const dim3 grid(splits);
   B200_TRY(make_map_3d_d(&tout, p.partial, N1, K1 + 1, splits, 32, 32));
   if (N1 == 128) B200_TRY((launch_dw16<256, true>(tx, td, tout, p, grid, net->ctx->stream)));
   else B200_TRY((launch_dw16<128, true>(tx, td, tout, p, grid, net->ctx->stream)));

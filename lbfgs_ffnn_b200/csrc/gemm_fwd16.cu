@@ -40,7 +40,8 @@ using namespace tcx;
 constexpr int kFM = 128;                   // samples per tile = UMMA M
 constexpr int kFK = 64;                    // K elements per stage (64 fp16 = one 128-byte swizzle row)
 constexpr int kConvBytes = kFM * kFK * 2;  // X tile: 16 KB
-// X and weight rings share one stage index (template parameter NS), so ONE tcgen05.commit frees both
+// X ring: NS stages; weight ring: NW stages (default NS: one stage index, ONE tcgen05.commit frees both tiles; NW != NS: the X
+// ring, which comes from HBM, is made deeper than the ring of the weights, which come from L2, and each gets its own commit)
 enum { EPI_F32 = 0,     // activations as fp32 rows (layer 0 of a two-layer net, layer 1 of a three-layer net)
        EPI_EMIT16 = 1,  // activations ONLY as the per-feature-scaled fp16 pair, block-major (b200_net::Mid16::a16)
        EPI_DX = 2 };    // dX role: A = delta pair, B = W^T; epilogue: * act'(A_prev) from the pair, emits delta_prev's fp16 pair
@@ -59,6 +60,7 @@ struct F16Params {
   const SpecState *spec_st; // speculative launch on a wrong guess: return at once (common.cuh)
   int spec;
   long long *dbg;        // B200_TC_TIMING: per CTA {total, epilogue busy, epilogue waiting for the accumulator, issuer waiting}
+  int diag;              // B200_DIAG (timing experiments only, results are wrong): bit0 no X loads, bit1 no weight loads, bit2 no MMAs, bit3 no stores
   int x_block_first;     // coordinates of the A-operand map are {0, block, row} instead of {0, row, block} (row-major pair rows)
   // EPI_EMIT16
   const float *tscale;   // [N]: t_f
@@ -68,31 +70,46 @@ struct F16Params {
   const float *scale_out;    // device scalar: scale of the emitted pair
 };
 
-template <int BN, bool X2, int EPI, int NS> struct FPlan {
-  static constexpr int kWStage = BN * 128 * (X2 ? 2 : 1);
+// PAIR: two CTAs of a cluster work as ONE tcgen05 cta_group::2 unit on two neighbouring sample tiles (M = 256). The B operand
+// [W_hi; W_lo] is split between them — the even CTA (the leader) stages W_hi, the odd one W_lo — so a K block costs each SM 16 KB
+// of X + 16 KB of weights instead of 16 + 32: the weight re-stream out of L2 (2/3 of this kernel's L2 -> SM bytes, the path that
+// bounds it: profiles/r02_*) is halved. Same MMA shapes per SM and the same accumulation order, so the results are bit-identical
+// to the one-CTA form.
+template <int BN, bool X2, int EPI, int NS, bool PAIR = false, int NW = NS> struct FPlan {
+  static_assert(!PAIR || X2, "the pair form splits [W_hi; W_lo] between the two CTAs");
+  static constexpr int kWStage = BN * 128 * ((X2 && !PAIR) ? 2 : 1);
   static constexpr int kOffConv = 0;
   static constexpr int kOffW = NS * kConvBytes;
-  static constexpr int kOffOut = kOffW + NS * kWStage; // epilogue staging tiles (TMA store), 1024-byte aligned
+  static constexpr int kOffOut = kOffW + NW * kWStage; // epilogue staging tiles (TMA store), 1024-byte aligned
   static constexpr int kAuxTile = (BN / 64) * kConvBytes; // EPI_DX: hi blocks of the previous layer's activation pair, [128 rows][64] each
   static constexpr int kOffAux = kOffOut + 8 * kStageOutBytes;
   static constexpr int kOffCol = kOffAux + (EPI == EPI_DX ? 2 * kAuxTile : 0); // colscale[128], bias[128]
   static constexpr int kOffBar = kOffCol + 1024;
-  static constexpr int kTotal = kOffBar + 256 + 1024;
+  static constexpr int kTotal = kOffBar + 512 + 1024; // 64 barrier slots, then the slack of the 1024-byte alignment
   static constexpr int kTmemCols = (4 * BN <= 256) ? 256 : 512;
   static_assert(kTotal <= 227 * 1024, "shared memory plan exceeds the SM");
 };
 
+template <bool PAIR = false>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
-// fp32 accumulate, fp16 x fp16, both operands K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kFM >> 4) << 24);
+// fp32 accumulate, fp16 x fp16, both operands K-major, M = 128 (one CTA) or 256 (a CTA pair)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = kFM) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -115,17 +132,30 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BN, bool X2, int EPI, int NS>
+template <int BN, bool X2, int EPI, int NS, bool PAIR, int NW>
 __global__ void __launch_bounds__(kFThreads, 1)
 fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
              const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmOut,
              const __grid_constant__ CUtensorMap tmAux, const F16Params p) {
-  if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
-  using Plan = FPlan<BN, X2, EPI, NS>;
-  constexpr int kNC = NS, kNW = NS;
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
+  if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation (both CTAs of a pair read the same flag)
+  using Plan = FPlan<BN, X2, EPI, NS, PAIR, NW>;
+  // work units: sample tiles (one CTA) or pairs of neighbouring sample tiles (a CTA pair: rank r takes tile 2 * unit + r)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int units = PAIR ? (p.tiles + 1) >> 1 : p.tiles;
+  auto tile_of = [&](int unit) { return PAIR ? 2 * unit + (int)rank : unit; };
+  constexpr int kNC = NS, kNW = NW;
+  static_assert(2 * kNC + 2 * kNW + 9 <= 64, "barrier table");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
@@ -135,7 +165,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   auto conv_full = [&](int s) { return bars + 8 * (s); };
   auto conv_empty = [&](int s) { return bars + 8 * (kNC + s); };
   auto w_full = [&](int s) { return bars + 8 * (2 * kNC + s); };
-  auto w_empty = [&](int s) { return conv_empty(s); }; // shared: the MMA warp's single commit per K block releases both tiles
+  // (equal ring depths: shared with conv_empty, the MMA warp's single commit per K block releases both tiles)
+  auto w_empty = [&](int s) { return kNW == kNC ? conv_empty(s) : bars + 8 * (2 * kNC + kNW + s); };
   auto tm_full = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + b); };
   auto tm_empty = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + 2 + b); };
   auto aux_full = [&](int b) { return bars + 8 * (2 * kNC + 2 * kNW + 4 + b); };
@@ -145,6 +176,9 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = p.dbg ? clock64() : 0;
+  if (p.dbg && threadIdx.x == 0) p.dbg[8 * blockIdx.x + 6] = (long long)globaltimer_ns();
+  // PAIR: the "full" barriers and tm_empty that count are the LEADER's (same offsets in its shared memory)
+  const uint32_t lead_off = PAIR ? mapa_shared(bars, 0) - bars : 0u;
 
   // ---- one-time setup -----------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -152,19 +186,23 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tma_prefetch_desc(&tmWh);
     if (X2) tma_prefetch_desc(&tmWl);
     for (int s = 0; s < kNC; ++s) { mbar_init(conv_full(s), 1); mbar_init(conv_empty(s), 1); }
-    for (int s = 0; s < kNW; ++s) mbar_init(w_full(s), 1);
+    for (int s = 0; s < kNW; ++s) { mbar_init(w_full(s), 1); if (kNW != kNC) mbar_init(w_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), kEpiThreads / 32);
+      mbar_init(tm_full(b), 1); mbar_init(tm_empty(b), (PAIR ? 2 : 1) * (kEpiThreads / 32)); // (PAIR: both CTAs' epilogue warps)
       mbar_init(aux_full(b), 1); mbar_init(aux_empty(b), kEpiThreads / 32);
     }
     if (EPI == EPI_DX) tma_prefetch_desc(&tmAux);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
-                 "r"((uint32_t)Plan::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      tmem_alloc_pair(smem_u32((const void *)tmem_slot), (uint32_t)Plan::kTmemCols);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                   "r"((uint32_t)Plan::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   float *colsc = reinterpret_cast<float *>(bp + Plan::kOffCol), *biass = colsc + 128;
   for (int i = threadIdx.x; i < 128; i += kFThreads) {
@@ -174,7 +212,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     biass[i] = (i < p.cols_valid && EPI != EPI_DX) ? __ldg(p.bias + i) * t : 0.0f;
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int umma_n = min(BN, (p.cols_valid + 31) & ~31);
@@ -184,7 +223,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      for (int unit = unit0; unit < units; unit += unit_step, ++it) {
+        const int tile = tile_of(unit);
         if (EPI == EPI_DX) { // the hi blocks of A_prev's pair for this tile's act' (double-buffered like the accumulators)
           const int buf = it & 1;
           mbar_wait(aux_empty(buf), ((it >> 1) & 1) ^ 1);
@@ -194,9 +234,16 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(conv_empty(s), ph ^ 1);
-          mbar_expect_tx(conv_full(s), kConvBytes);
-          if (p.x_block_first) tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, kb, p.row0 + tile * kFM);
-          else tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
+          if (p.diag & 1) { if (leader) mbar_arrive(conv_full(s)); }
+          else if constexpr (PAIR) { // both CTAs' tiles are counted on the leader's barrier
+            if (leader) mbar_expect_tx(conv_full(s), 2 * kConvBytes);
+            if (p.x_block_first) tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, kb, p.row0 + tile * kFM);
+            else tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, p.row0 + tile * kFM, kb);
+          } else {
+            mbar_expect_tx(conv_full(s), kConvBytes);
+            if (p.x_block_first) tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, kb, p.row0 + tile * kFM);
+            else tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
+          }
           if (++s == kNC) { s = 0; ph ^= 1; }
         }
       }
@@ -206,31 +253,38 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     if (lane == 0) { // ===== weight producer ===========================================================
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < units; unit += unit_step) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(w_empty(s), ph ^ 1);
-          mbar_expect_tx(w_full(s), Plan::kWStage);
-          tma_load_2d(w_a(s, 0), &tmWh, w_full(s), kb * kFK, 0);
-          if (X2) tma_load_2d(w_a(s, 1), &tmWl, w_full(s), kb * kFK, 0);
+          if (p.diag & 2) { if (leader) mbar_arrive(w_full(s)); }
+          else if constexpr (PAIR) { // this CTA's half of B = [W_hi; W_lo]: rows 0 .. BN-1 (hi) in the leader, BN .. 2 BN-1 (lo) in the peer
+            if (leader) mbar_expect_tx(w_full(s), 2 * Plan::kWStage);
+            tma_load_2d_pair(w_a(s, 0), leader ? &tmWh : &tmWl, w_full(s) + lead_off, kb * kFK, 0);
+          } else {
+            mbar_expect_tx(w_full(s), Plan::kWStage);
+            tma_load_2d(w_a(s, 0), &tmWh, w_full(s), kb * kFK, 0);
+            if (X2) tma_load_2d(w_a(s, 1), &tmWl, w_full(s), kb * kFK, 0);
+          }
           if (++s == kNW) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) { // ===== MMA issuer ================================================================
+    if (lane == 0 && leader) { // ===== MMA issuer (PAIR: the leader issues for both CTAs) ==============================
       // One MMA per K step: with the lo tile stored right behind the hi tile, B = [W_hi; W_lo] is a single 2*BN-row K-major
       // operand and D = [hi | lo] lands in adjacent TMEM columns. Descriptors are built once; per stage / K step only the
       // 14-bit start-address field moves (the issuing thread is otherwise bound by descriptor arithmetic, not by the tensor pipe).
-      const uint32_t idesc = make_idesc_f16(X2 ? 2 * BN : umma_n);
+      const uint32_t idesc = make_idesc_f16(X2 ? 2 * BN : umma_n, PAIR ? 2 * kFM : kFM);
       const uint64_t dA0 = desc_k_major(conv_a(0)), dB0 = desc_k_major(w_a(0, 0));
       int cs = 0, ws = 0, it = 0;
       uint32_t cph = 0, wph = 0;
-      long long waited = 0, waited_w = 0, waited_tm = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      long long waited = 0, waited_w = 0, waited_tm = 0, t_mma = 0, t_commit = 0;
+      for (int unit = unit0; unit < units; unit += unit_step, ++it) {
         const int buf = it & 1;
         const uint32_t d_acc = tmem_base + (uint32_t)(buf * 2 * BN);
         const long long tt0 = p.dbg ? clock64() : 0;
+        if (p.dbg && blockIdx.x == 0 && it < 8) { p.dbg[4096 + 2 * it] = tt0; p.dbg[4096 + 2 * it + 1] = (long long)globaltimer_ns(); }
         mbar_wait(tm_empty(buf), ((it >> 1) & 1) ^ 1);
         if (p.dbg) waited_tm += clock64() - tt0;
         tc_fence_after();
@@ -239,19 +293,28 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           mbar_wait(conv_full(cs), cph);
           const long long t0b = p.dbg ? clock64() : 0;
           mbar_wait(w_full(ws), wph);
-          if (p.dbg) { waited += t0b - t0; waited_w += clock64() - t0b; }
+          const long long t1 = p.dbg ? clock64() : 0;
+          if (p.dbg) { waited += t0b - t0; waited_w += t1 - t0b; }
           tc_fence_after();
           const int nks = min(kFK / 16, (p.k_total - kb * kFK + 15) / 16);
           const uint64_t da = dA0 + (uint64_t)(cs * (kConvBytes >> 4)), db = dB0 + (uint64_t)(ws * (Plan::kWStage >> 4));
 #pragma unroll
           for (int ks = 0; ks < kFK / 16; ++ks)
-            if (ks < nks) umma_f16(d_acc, da + 2 * ks, db + 2 * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(conv_empty(cs)); // == w_empty(ws): kNC == kNW and both rings advance together
+            if (ks < nks && !(p.diag & 4)) umma_f16<PAIR>(d_acc, da + 2 * ks, db + 2 * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          const long long t2 = p.dbg ? clock64() : 0;
+          if (p.dbg) t_mma += t2 - t1;
+          if constexpr (PAIR) umma_commit_pair(conv_empty(cs)); // frees the stage in both CTAs
+          else umma_commit(conv_empty(cs)); // (== w_empty(ws) when both rings have the same depth)
+          if constexpr (kNW != kNC) { if constexpr (PAIR) umma_commit_pair(w_empty(ws)); else umma_commit(w_empty(ws)); }
+          if (p.dbg) t_commit += clock64() - t2;
           if (++cs == kNC) { cs = 0; cph ^= 1; }
           if (++ws == kNW) { ws = 0; wph ^= 1; }
         }
-        umma_commit(tm_full(buf));
+        if constexpr (PAIR) umma_commit_pair(tm_full(buf));
+        else umma_commit(tm_full(buf));
       }
+      if (p.dbg && blockIdx.x == 0 && it < 8) { p.dbg[4096 + 2 * it] = clock64(); p.dbg[4096 + 2 * it + 1] = (long long)globaltimer_ns(); p.dbg[4096 + 16] = it; }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[4096 + 20] = t_mma; p.dbg[4096 + 21] = t_commit; }
       if (p.dbg) { p.dbg[8 * blockIdx.x + 3] = waited; p.dbg[8 * blockIdx.x + 4] = waited_w; p.dbg[8 * blockIdx.x + 5] = waited_tm; }
     }
     __syncwarp();
@@ -269,7 +332,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       uint8_t *stage_p = bp + Plan::kOffOut + (warp - kEpiWarp0) * kStageOutBytes;
       long long busy = 0, waiting = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      for (int unit = unit0; unit < units; unit += unit_step, ++it) {
+        const int tile = tile_of(unit); // (PAIR, odd tile count: the peer's last tile lies past the batch; its stores are clipped)
         const int buf = it & 1;
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(tm_full(buf), (it >> 1) & 1);
@@ -282,7 +346,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < BN / 64; ++i) {
           const int c0 = half * 32 + 64 * i;
-          if (c0 < p.cols_valid) {
+          if (c0 < p.cols_valid && !(p.diag & 16)) {
             uint32_t v[32];
             tmem_ld32_nowait(lane_addr + c0, v);
             if (X2) { // hi + lo accumulators, added in RN fp32
@@ -309,7 +373,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
               }
               fence_async_smem();
               __syncwarp();
-              if (lane == 0) {
+              if (lane == 0 && !(p.diag & 8)) {
                 tma_store_2d(&tmOut, stage_a, c0, tile * kFM + q * 32);
                 tma_store_commit();
               }
@@ -361,7 +425,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
               }
               fence_async_smem();
               __syncwarp();
-              if (lane == 0) {
+              if (lane == 0 && !(p.diag & 8)) {
                 if constexpr (EPI == EPI_EMIT16) {
                   tma_store_3d(&tmOut, stage_a, c0 & 63, tile * kFM + q * 32, c0 >> 6);
                   tma_store_3d(&tmOut, stage_a + 2048, c0 & 63, tile * kFM + q * 32, p.nb_out + (c0 >> 6));
@@ -377,7 +441,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         tc_fence_before(); // accumulator consumed: the issuer may start tile it+2 in this buffer
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tm_empty(buf));
+          if constexpr (PAIR) mbar_arrive_cluster(tm_empty(buf) + lead_off); // the leader's issuer waits for both CTAs' epilogues
+          else mbar_arrive(tm_empty(buf));
           if (EPI == EPI_DX) mbar_arrive(aux_empty(buf));
         }
         if (p.dbg) { const long long t2 = clock64(); waiting += t1 - t0; busy += t2 - t1; }
@@ -390,11 +455,13 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     else epilogue(IntTag<-1>{});
   }
   tc_fence_before();
-  __syncthreads();
-  if (p.dbg && threadIdx.x == 0) p.dbg[8 * blockIdx.x] = clock64() - t_start;
+  if constexpr (PAIR) cluster_sync_all(); // neither CTA leaves while the other may still signal its barriers or feed its MMAs
+  else __syncthreads();
+  if (p.dbg && threadIdx.x == 0) { p.dbg[8 * blockIdx.x] = clock64() - t_start; p.dbg[8 * blockIdx.x + 7] = (long long)globaltimer_ns(); }
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Plan::kTmemCols) : "memory");
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)Plan::kTmemCols);
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Plan::kTmemCols) : "memory");
   }
 }
 
@@ -429,6 +496,7 @@ struct PrepJob {
 __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ PrepJob j0, const __grid_constant__ PrepJob j1,
                                                       const __grid_constant__ PrepJob j2, const SpecState *spec_st, int spec,
                                                       const __grid_constant__ ChainW chain) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return;
   __shared__ float red[128][kSplitNeurons + 1];
   if (chain.nl > 0 && blockIdx.x >= gridDim.x - chain.nctas) { // the extra CTAs (see ChainW, network.cuh)
@@ -524,6 +592,7 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
 // fp32 A_1 from its fp16 pair (debug read-back of a hidden activation that only exists as the pair)
 __global__ void __launch_bounds__(256) pair_to_f32_kernel(const __half *__restrict__ a16, long rows, int width, const float *__restrict__ tinv,
                                                           float *__restrict__ out) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   const int nb = width / 64;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * width; i += (long)gridDim.x * blockDim.x) {
     const long r = i / width;
@@ -592,11 +661,11 @@ int make_map_3d(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsig
   return make_map_3d_ex(tm, ptr, dim0, dim1, dim2, dim0 * 2, dim0 * dim1 * 2, box0, box1, 1, sw);
 }
 
-template <int BN, bool X2, int EPI, int NS>
+template <int BN, bool X2, int EPI, int NS, bool PAIR = false, int NW = NS>
 int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const CUtensorMap &tout, const CUtensorMap &taux,
                  const F16Params &p, int grid, cudaStream_t st) {
-  auto kern = fwd16_kernel<BN, X2, EPI, NS>;
-  constexpr int smem = FPlan<BN, X2, EPI, NS>::kTotal;
+  auto kern = fwd16_kernel<BN, X2, EPI, NS, PAIR, NW>;
+  constexpr int smem = FPlan<BN, X2, EPI, NS, PAIR, NW>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -605,12 +674,13 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
   static long long *dbg = nullptr;
   const bool timing = env().tc_timing;
   F16Params pp = p;
+  pp.diag = env().diag;
   if (timing) {
     if (!dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 1024));
     B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * 1024, st));
     pp.dbg = dbg;
   }
-  kern<<<grid, kFThreads, smem, st>>>(tx, twh, twl, tout, taux, pp);
+  B200_CUDA(launch_ex(kern, dim3((unsigned)grid), dim3(kFThreads), (size_t)smem, st, PAIR ? 2 : 1, tx, twh, twl, tout, taux, pp)); // (PAIR: clusters of two CTAs = the two SMs of a TPC)
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) {
@@ -618,10 +688,21 @@ int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMa
     B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < grid; ++i)
-      for (int j = 0; j < 8; ++j) a[j] += (double)h[8 * i + j] / grid;
-    fprintf(stderr, "[fwd16 timing] BN %d x2 %d epi %d grid %d tiles %d: per CTA total %.0f clk | epilogue busy %.0f, waiting %.0f | issuer waits: X %.0f, "
-            "weights %.0f, tmem %.0f\n", BN, (int)X2, EPI, grid, p.tiles, a[0], a[1], a[2], a[3], a[4], a[5]);
+    long long t_first = h[6], t_last = h[7], t_first_end = h[7], t_last_start = h[6];
+    for (int i = 0; i < grid; ++i) {
+      for (int j = 0; j < 6; ++j) a[j] += (double)h[8 * i + j] / grid;
+      a[6] = 0; a[7] += (double)(h[8 * i + 7] - h[8 * i + 6]) / grid; // (ns of this CTA)
+      t_first = std::min(t_first, h[8 * i + 6]); t_last = std::max(t_last, h[8 * i + 7]);
+      t_first_end = std::min(t_first_end, h[8 * i + 7]); t_last_start = std::max(t_last_start, h[8 * i + 6]);
+    }
+    fprintf(stderr, "[fwd16 timing] BN %d x2 %d epi %d pair %d grid %d tiles %d: per CTA total %.0f clk = %.0f ns (%.2f clk/ns) | epilogue busy %.0f, "
+            "waiting %.0f | issuer waits: X %.0f, weights %.0f, tmem %.0f | first CTA start -> last CTA end %.1f us, starts spread %.1f us, "
+            "ends spread %.1f us\n", BN, (int)X2, EPI, (int)PAIR, grid, p.tiles, a[0], a[7] - a[6], a[0] / (a[7] - a[6]), a[1], a[2], a[3], a[4], a[5],
+            (t_last - t_first) * 1e-3, (t_last_start - t_first) * 1e-3, (t_last - t_first_end) * 1e-3);
+    fprintf(stderr, "   CTA 0 issuer, per tile: ");
+    for (int i = 0; i < (int)h[4096 + 16] && i < 7; ++i)
+      fprintf(stderr, "%lld clk / %lld ns; ", h[4096 + 2 * (i + 1)] - h[4096 + 2 * i], h[4096 + 2 * (i + 1) + 1] - h[4096 + 2 * i + 1]);
+    fprintf(stderr, " | CTA 0 issuer: fence + MMA issue %lld clk, commit %lld clk\n", h[4096 + 20], h[4096 + 21]);
   }
   return B200_OK;
 }
@@ -781,12 +862,20 @@ int fwd16_forward_layer(b200_net *net, int l, const float *params, const X16View
   p.spec_st = net->spec_st; p.spec = net->spec_flag;
   p.tscale = net->m16.tscale; p.nb_out = N / 64;
   const int grid = std::min(net->ctx->num_sms, p.tiles);
+  // CTA pairs (cta_group::2) when there are at least two sample tiles per pair of SMs to share a weight stream over
+  const bool pair = x2 && bn == 128 && (env().pair & 1) && p.tiles >= 4;
+  const int grid_pair = 2 * std::min(net->ctx->num_sms / 2, (p.tiles + 1) / 2);
+  const bool deep_x = (env().ring & 1) != 0; // X ring (HBM) 6 stages deep, weight ring (L2) 3
   if (emit16) {
-    if (bn == 128) B200_TRY((launch_fwd16<128, true, EPI_EMIT16, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+    if (pair) B200_TRY((launch_fwd16<128, true, EPI_EMIT16, 6, true>(tx, twh, twl, tout, tout, p, grid_pair, st)));
+    else if (bn == 128 && deep_x) B200_TRY((launch_fwd16<128, true, EPI_EMIT16, 6, false, 3>(tx, twh, twl, tout, tout, p, grid, st)));
+    else if (bn == 128) B200_TRY((launch_fwd16<128, true, EPI_EMIT16, 4>(tx, twh, twl, tout, tout, p, grid, st)));
     else B200_TRY((launch_fwd16<64, true, EPI_EMIT16, 4>(tx, twh, twl, tout, tout, p, grid, st)));
     net->m16.act0_stale = true;
   } else if (bn == 128) {
-    if (x2) B200_TRY((launch_fwd16<128, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
+    if (pair) B200_TRY((launch_fwd16<128, true, EPI_F32, 6, true>(tx, twh, twl, tout, tout, p, grid_pair, st)));
+    else if (x2 && deep_x) B200_TRY((launch_fwd16<128, true, EPI_F32, 6, false, 3>(tx, twh, twl, tout, tout, p, grid, st)));
+    else if (x2) B200_TRY((launch_fwd16<128, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
     else B200_TRY((launch_fwd16<128, false, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));
   } else {
     if (x2) B200_TRY((launch_fwd16<64, true, EPI_F32, 4>(tx, twh, twl, tout, tout, p, grid, st)));

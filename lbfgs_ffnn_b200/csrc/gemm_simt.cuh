@@ -127,6 +127,7 @@ __device__ __forceinline__ void tile_store(const TileRegs<MN, KC> &r, float *__r
 
 template <int TN, bool A_KC, bool B_KC, int EPI>
 __global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const GemmParams p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int BN = 16 * TN;
   constexpr int kLdA = kBM + kPad, kLdB = BN + kPad;

@@ -111,6 +111,7 @@ template <int A_MAJOR, int B_MAJOR, int ROLE, int BN, bool X3, int U8, int SHALL
 __global__ void __launch_bounds__(kTcThreads, ((SmemPlan<BN, X3, U8, SHALLOW>::kTotal + 1024) * 2 <= 227 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation
   using Plan = SmemPlan<BN, X3, U8, SHALLOW>;
   constexpr bool kSplitA = Plan::kSplitA, kSplitB = Plan::kSplitB;
@@ -694,7 +695,7 @@ int launch_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &t
     B200_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 4 * 4096, st));
     pp.dbg = dbg;
   }
-  kern<<<grid, kTcThreads, smem, st>>>(ta, tb, tblo, pp);
+  B200_CUDA(launch_ex(kern, grid, dim3(kTcThreads), (size_t)smem, st, 1, ta, tb, tblo, pp));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   if (timing) { // debugging aid: average main-loop and epilogue duration per CTA, in SM clocks
@@ -722,6 +723,7 @@ int launch_tc_prec(bool x3, const CUtensorMap &ta, const CUtensorMap &tb, const 
 
 __global__ void __launch_bounds__(256) split_params_kernel(const float *__restrict__ w, unsigned long long n, float *__restrict__ hi,
                                                          float *__restrict__ lo, const SpecState *spec_st, int spec) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {

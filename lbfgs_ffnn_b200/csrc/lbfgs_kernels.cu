@@ -173,6 +173,7 @@ __device__ __forceinline__ void dots_body(const DotsArgs &a) {
 }
 template <int RPW, bool PAIR>
 __global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs a) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   dots_body<RPW, PAIR>(a);
 }
 
@@ -415,6 +416,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
 }
 
 __global__ void __launch_bounds__(256) lbfgs_solve_kernel(const SolveArgs a) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   extern __shared__ double sh[];
   solve_body(a, sh, true, a.st.h->head, a.st.h->count, nullptr);
 }
@@ -483,6 +485,7 @@ __device__ __forceinline__ void apply_body(const ApplyArgs &a, int k, double cg_
 }
 
 __global__ void __launch_bounds__(256) lbfgs_apply_kernel(const ApplyArgs a) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double s_cs[kMaxSlots], s_cy[kMaxSlots];
   __shared__ int s_ph[kMaxSlots];
   const LbfgsHeader *h = a.st.h;
@@ -525,6 +528,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) { 
 template <int RPW, bool PAIR>
 __global__ void __launch_bounds__(kDotsThreads) lbfgs_direction_kernel(const DotsArgs da, const SolveArgs sa, const ApplyArgs aa,
                                                                       unsigned *bar, const SpecState *spec_st, int spec) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return; // every CTA takes the same branch: nobody reaches the grid barrier
   extern __shared__ double sh[];
   __shared__ int s_head0, s_count0;
@@ -542,6 +546,7 @@ __global__ void __launch_bounds__(kDotsThreads) lbfgs_direction_kernel(const Dot
 // totals[c] = sum_b partials[b][c] in a fixed order (sharded history: the totals are then all-reduced over ranks)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nblocks, int ncols,
                                                              double *__restrict__ totals) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (int c0 = blockIdx.x * 32; c0 < ncols; c0 += gridDim.x * 32) {
     const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     double s = 0.0;
@@ -555,6 +560,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__re
 }
 
 __global__ void lbfgs_init_kernel(LbfgsView v, int m, int mod) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   const int mp = m + 1;
   for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { v.SY[i] = 0.0; v.YY[i] = 0.0; }
   for (int i = threadIdx.x; i < mp; i += blockDim.x) {
@@ -570,6 +576,7 @@ __global__ void lbfgs_init_kernel(LbfgsView v, int m, int mod) {
 // copy an explicit (s, y) pair into slot `head` (the Gram update happens in the following dots/solve)
 __global__ void __launch_bounds__(256) store_pair_kernel(float *S, float *Y, size_t n, size_t ld, LbfgsView st,
                                                          const float *s, const float *y) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   const int w = st.h->head;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     S[(size_t)w * ld + i] = s[i];
@@ -580,19 +587,23 @@ __global__ void __launch_bounds__(256) store_pair_kernel(float *S, float *Y, siz
 // ---- BLAS-1 replacements -----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) trial_point_kernel(size_t n, const float *__restrict__ x0, float alpha,
                                                           const float *__restrict__ p, float *__restrict__ y) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, p[i], x0[i]);
 }
 __global__ void __launch_bounds__(256) axpy_kernel(size_t n, float alpha, const float *__restrict__ x, float *y) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, x[i], y[i]);
 }
 __global__ void __launch_bounds__(256) scal_kernel(size_t n, float alpha, float *x) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     x[i] *= alpha;
 }
 __global__ void __launch_bounds__(256) momentum_step_kernel(size_t n, float mu, float lr, const float *__restrict__ g,
                                                             float *v, float *x) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     // v = mu*v; v += -lr*g; x += v  (src/cuda/gd.cuh:77-81: scal, axpy, axpy)
     const float vv = fmaf(-lr, g[i], mu * v[i]);
@@ -601,11 +612,13 @@ __global__ void __launch_bounds__(256) momentum_step_kernel(size_t n, float mu, 
   }
 }
 __global__ void __launch_bounds__(256) f64_to_f32_kernel(size_t n, const double *__restrict__ s, float *__restrict__ d) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     d[i] = (float)s[i];
 }
 __global__ void __launch_bounds__(256) dot_part_kernel(const float *__restrict__ x, const float *__restrict__ y, size_t n,
                                                        double *part) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double red[32];
   double s = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -614,6 +627,7 @@ __global__ void __launch_bounds__(256) dot_part_kernel(const float *__restrict__
   if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) dot_final_kernel(const double *part, int nparts, double *out) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[i];
@@ -624,6 +638,7 @@ __global__ void __launch_bounds__(256) dot_final_kernel(const double *part, int 
 // profiling aid: keeps the GPU busy for ~`clocks` SM clocks so that the host can enqueue the next events and launches behind it;
 // without it the first profiled kernel after a host synchronisation is charged the host's launch latency
 __global__ void prof_spacer_kernel(long long clocks) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   const long long t0 = clock64();
   while (clock64() - t0 < clocks) {}
 }
@@ -702,7 +717,7 @@ int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da0, const SolveArgs &
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDotsThreads, smem));
     if ((long)per_sm * ctx->num_sms < nblocks) return B200_OK; // the grid barrier needs every CTA resident
-    kern<<<nblocks, kDotsThreads, smem, st>>>(da, sa, aa, bar, spec_st, spec);
+    B200_CUDA(launch_ex(kern, dim3(nblocks), dim3(kDotsThreads), (size_t)smem, st, 1, da, sa, aa, bar, spec_st, spec));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA(cudaGetLastError());
     *done = true;

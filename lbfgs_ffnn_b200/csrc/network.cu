@@ -64,6 +64,7 @@ __device__ __forceinline__ unsigned *p2p_flags(char *buf, unsigned long long slo
 }
 
 __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return;
   __shared__ double sh[8][32];
   __shared__ double red[32];
@@ -183,6 +184,7 @@ struct P2PReduceParams {
   unsigned long long spin_limit;
 };
 __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return;
   __shared__ double red[32];
   __shared__ bool last;
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p
 __global__ void __launch_bounds__(1024) eval_scalars_kernel(const double *loss_part, int n_loss, const double *fin_part,
                                                            int n_fin, double inv_batch, double lam, int want_gnorm,
                                                            EvalOut *out) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double red[32];
   double l = 0.0, g2 = 0.0, w2 = 0.0;
   for (int i = threadIdx.x; i < n_loss; i += blockDim.x) l += loss_part[i];
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(1024) eval_scalars_kernel(const double *loss_p
 }
 
 __global__ void __launch_bounds__(256) sumsq_part_kernel(const float *x, unsigned long long n, double *part) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double red[32];
   double s = 0.0;
   for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(256) sumsq_part_kernel(const float *x, unsigne
   if (threadIdx.x == 0) part[2 * blockIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) gnorm_from_parts_kernel(const double *part, int nparts, EvalOut *out) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[2 * i];
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(256) gnorm_from_parts_kernel(const double *par
 // per sample arg-max of prediction vs target (first maximum wins, strict >), squared error sum.
 __global__ void __launch_bounds__(256) evaluate_kernel(const float *out, const float *tgt, long batch, int od,
                                                        double *part) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   __shared__ double red[32];
   double se = 0.0, correct = 0.0;
   for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < batch; b += (long)gridDim.x * blockDim.x) {
@@ -323,6 +329,7 @@ template <int FPL>
 __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restrict__ A, const float *__restrict__ D, int ldd, int in,
                                                         int out, long batch, int chunk, float *__restrict__ partial,
                                                         unsigned long long pstride, const SpecState *spec_st, int spec) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return;
   __shared__ __align__(16) float sd[kSkinnyTile][16];
   __shared__ float red[32 * FPL * 16];
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(256, 2) skinny_dw_kernel(const float *__restri
 // GEMMs is one contiguous chunk that TMA feeds to the tensor cores as it is.
 __global__ void __launch_bounds__(256) quantize_u8_kernel(const float *__restrict__ x, unsigned long long n, int in, int nblocks16,
                                                           uint8_t *__restrict__ q, __half *__restrict__ q16, int *flag) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   int ok = 1;
   const unsigned long long nv = n / 4;
   for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv;
@@ -763,6 +771,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         B200_TRY(mid16_dw_layer1(net, batch));
         done = true;
       }
+      if (l == 0) net->dw0_tail_row0 = -1; // (set by dw16_layer when its last feature group has its own number of slices)
       if (l == 0 && d16_ready) {
         X16View xv;
         if (net_x16_view(net, x, batch, &xv)) B200_TRY(dw16_layer(net, xv, batch, &done));
@@ -807,6 +816,13 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     f.size = f.stride = (unsigned long long)(net->dims[l] + 1) * net->dims[l + 1];
     f.part = net->partials + net->part_off[l];
     f.splits = net->splits_used[l];
+    if (l == 0 && net->dw0_tail_row0 >= 0) { // the last feature group of the fp16 dW kernel has its own number of slices
+      const unsigned long long head = (unsigned long long)net->dw0_tail_row0 * net->dims[1];
+      FinLayer &t = fp.L[fp.nl++];
+      t = f;
+      t.off = f.off + head; t.size = f.size - head; t.part = f.part + head; t.splits = net->dw0_tail_splits;
+      f.size = head; // (f stays valid: fp.L is an array)
+    }
     if (l == 1 && mid) { // dW_1 from the split-K kernel, db_1 from the last-layer backward kernel's column sums
       f.size = (unsigned long long)net->dims[1] * net->dims[2];
       FinLayer &b = fp.L[fp.nl++];

@@ -32,6 +32,7 @@ struct b200_net {
   std::vector<int> splits, k_chunk; // FFMA split-K plan
   std::vector<int> skinny_splits;   // split plan of the skinny (out <= 16) dW kernel
   std::vector<int> splits_used;     // splits written by the last evaluation (either path)
+  int dw0_tail_row0 = -1, dw0_tail_splits = 0; // fp16 layer-0 dW (gemm_dw16.cu): rows from tail_row0 on have tail_splits slices
   std::vector<size_t> part_off;
   float *partials = nullptr;
   size_t partials_cap = 0;

@@ -56,7 +56,8 @@ struct Sampler {
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ X, const float *__restrict__ T,
                                                           const uint32_t *__restrict__ idx, int count, int in_dim,
                                                           int out_dim, float *__restrict__ Xb, float *__restrict__ Tb,
-                                                          float *__restrict__ Tb2 = nullptr) { // Tb2: rows [T | T] for the pair network
+                                                          float *__restrict__ Tb2 = nullptr) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh) // Tb2: rows [T | T] for the pair network
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < count; i += warps) {
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
 // mini-batch [nblocks][count][64]: one warp per (sample, block) pair moves one 128-byte run
 __global__ void __launch_bounds__(256) gather16_rows_kernel(const uint32_t *__restrict__ src16, long rows_src, int nblocks,
                                                             const uint32_t *__restrict__ idx, int count, uint32_t *__restrict__ dst16) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   const int lane = threadIdx.x & 31;
   const long warps = ((long)gridDim.x * blockDim.x) >> 5;
   const long total = (long)count * nblocks;
@@ -105,6 +107,7 @@ static int gather16(b200_net *net, const float *Xb, const uint32_t *d_idx, int c
 // v = g_t - g_k + mu   (s_lbfgs.hpp:225-228)
 __global__ void __launch_bounds__(256) vr_combine_kernel(size_t n, const float *__restrict__ gt, const float *__restrict__ gk,
                                                          const float *__restrict__ mu, float *__restrict__ v) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     v[i] = (gt[i] - gk[i]) + mu[i];
 }
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(256) hvp_points_kernel(size_t n, size_t ld, co
                                                          float *__restrict__ u, const float *__restrict__ u_prev,
                                                          int have_prev, float eps, float *__restrict__ s,
                                                          float *__restrict__ wp, float *__restrict__ wm) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float acc = 0.0f;
     for (int r = 0; r < count; ++r) acc += W[(size_t)r * ld + i]; // slot order == logical order only up to rotation: a sum
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(256) hvp_points_kernel(size_t n, size_t ld, co
 // y = (g+ - g-) / (2 eps)   (s_lbfgs.hpp:100)
 __global__ void __launch_bounds__(256) hvp_diff_kernel(size_t n, const float *__restrict__ gp, const float *__restrict__ gm,
                                                        float inv_2eps, float *__restrict__ y) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = (gp[i] - gm[i]) * inv_2eps;
 }
@@ -151,6 +156,7 @@ struct PairLayout {
 };
 __global__ void __launch_bounds__(256) pack_pair_kernel(const PairLayout L, unsigned long long n_pair, const float *__restrict__ wa,
                                                         const float *__restrict__ wb, float *__restrict__ wp) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pair;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     int l = 0;
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(256) pack_pair_kernel(const PairLayout L, unsi
 // out[i] = (g_a[i] - g_b[i]) * scale + (add ? add[i] : 0)
 __global__ void __launch_bounds__(256) unpack_pair_kernel(const PairLayout L, unsigned long long n, const float *__restrict__ gp,
                                                           float scale, const float *__restrict__ add, float *__restrict__ out) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     int l = 0;
@@ -244,7 +251,7 @@ int sgd_random_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const f
     B200_CUDA(cudaMemcpyAsync(d_idx, h_idx, sizeof(uint32_t) * (size_t)m * b, cudaMemcpyHostToDevice, st));
     for (int t = 0; t < m; ++t) {
       B200_LAUNCH(gather_rows_kernel, std::min(1184, ceil_div(b, 8)), 256, 0, st, input, target, d_idx + (size_t)t * b, b, in_dim,
-                  out_dim, Xb, Tb);
+                  out_dim, Xb, Tb, (float *)nullptr);
       B200_TRY(gather16(net, Xb, d_idx + (size_t)t * b, b, st));
       ++evals;
       B200_TRY(net_eval(net, params, Xb, Tb, b, b, grad, scratch)); // grad /= current_bs (:266)

@@ -127,6 +127,7 @@ __device__ __forceinline__ float transpose_reduce(const float (&p0)[OLP], const 
 // OLP: compile-time padded output count (10 = the MNIST fast path, 12 = anything up to 12 with zero-padded weights)
 template <int FPL, int OLP>
 __global__ void __launch_bounds__(256, 2) tail_fwd_kernel(const TailParams p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int IN = 32 * FPL;
   __shared__ double lred[32];
@@ -242,6 +243,7 @@ template <int IN> struct Fwd2Plan {
 };
 template <int FPL, int OLP>
 __global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __grid_constant__ CUtensorMap tmA, const TailParams p, int n_bwd) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int IN = 32 * FPL;
   constexpr int NH = Fwd2Plan<IN>::NH;
@@ -386,6 +388,7 @@ __global__ void __launch_bounds__(kF2Warps * 32, 1) tail_fwd2_kernel(const __gri
 // ---- pass 2: delta_{L-1} (fp32 for a dX GEMM and / or scaled fp16 hi|lo for the fp16 dW GEMM) and the [dW_L; db_L] partials ----
 template <int FPL, int OLP, bool RELU>
 __global__ void __launch_bounds__(256, 2) tail_bwd_kernel(const TailParams p) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   static_assert(OLP % 2 == 0, "packed FMAs take the outputs in pairs");
   if (spec_skip(p.spec_st, p.spec)) return;
   constexpr int IN = 32 * FPL;
@@ -604,7 +607,7 @@ template <int FPL, int OLP> int launch_tail_fwd2(const TailParams &p, int grid_f
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  kern<<<grid_fwd, kF2Warps * 32, smem, st>>>(tmA, p, grid_bwd);
+  B200_CUDA(launch_ex(kern, dim3(grid_fwd), dim3(kF2Warps * 32), (size_t)smem, st, 1, tmA, p, grid_bwd));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
   return B200_OK;

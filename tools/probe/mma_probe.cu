@@ -11,8 +11,13 @@ __device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uin
 }
 __host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
 
+__device__ __forceinline__ bool elect_one() { // one lane of a converged warp; the compiler knows the branch it guards is single-threaded
+  uint32_t pred = 0, laneid = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %2;\n\t@px mov.s32 %1, 1;\n\tmov.s32 %0, rx;\n\t}" : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 // mode: 0 = n MMAs into one accumulator; 1 = alternate two accumulators; 2 = one accumulator + commit every 4; kind: 0 f16, 1 tf32
-__global__ void probe(int n, int N, int mode, int kind, int same_a, long long *out) {
+__global__ void probe(int n, int N, int mode, int kind, int same_a, long long *out, int elect) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   __shared__ uint32_t slot;
@@ -28,7 +33,27 @@ __global__ void probe(int n, int N, int mode, int kind, int same_a, long long *o
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = slot;
-  if (threadIdx.x == 0) {
+  if (elect && threadIdx.x < 32) { // the whole warp runs the loop; one elected lane issues
+    const uint32_t id = kind == 0 ? idesc_f16(N) : make_idesc(0, 0, N);
+    const uint64_t dA = desc_k_major(base), dB = desc_k_major(base + 64 * 1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+      const uint64_t da = dA + (same_a ? 0 : (uint64_t)(((i & 3) * 2) + ((i >> 2) & 3) * 1024)), db = dB + (uint64_t)((i & 3) * 2);
+      const uint32_t d = tm + ((mode == 1 && (i & 1)) ? 256u : 0u);
+      if (elect_one()) {
+        if (kind == 0) umma_f16(d, da, db, id, i > 0);
+        else umma_tf32(d, da, db, id, i > 0);
+        if (mode == 2 && (i & 3) == 3) umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (elect_one()) umma_commit(smem_u32(&bar2));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar2), 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (!elect && threadIdx.x == 0) {
     const uint32_t id = kind == 0 ? idesc_f16(N) : make_idesc(0, 0, N);
     const uint64_t dA = desc_k_major(base), dB = desc_k_major(base + 64 * 1024);
     const long long t0 = clock64();
@@ -57,15 +82,16 @@ int main() {
   for (int kind = 0; kind < 2; ++kind)
     for (int N : {64, 128, 256})
       for (int mode = 0; mode < 3; ++mode)
-        for (int same_a = 0; same_a < 2; ++same_a) {
+        for (int elect = 0; elect < 2; ++elect) {
+          const int same_a = 0;
           long long h[2] = {0, 0};
           for (int rep = 0; rep < 2; ++rep) {
-            probe<<<1, 128, 200 * 1024>>>(n, N, mode, kind, same_a, d);
+            probe<<<1, 128, 200 * 1024>>>(n, N, mode, kind, same_a, d, elect);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
             cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
           }
-          fflush(stdout); printf("kind %s N %3d mode %d same_a %d : issue %.1f clk/mma, complete %.1f clk/mma\n", kind ? "tf32" : "f16 ", N, mode, same_a,
+          fflush(stdout); printf("kind %s N %3d mode %d elect %d : issue %.1f clk/mma, complete %.1f clk/mma\n", kind ? "tf32" : "f16 ", N, mode, elect,
                  (double)h[0] / n, (double)h[1] / n);
         }
   return 0;
