@@ -46,7 +46,7 @@ void env_reload() {
   e.tail = num("B200_TAIL", -1);
   e.tail_fwd = num("B200_TAIL_FWD", -1);
   e.mid16 = num("B200_MID16", -1);
-  e.pair = num("B200_PAIR", 0);
+  e.pair = num("B200_PAIR", 1);
   e.diag = num("B200_DIAG", 0);
   e.ring = num("B200_RING", 0);
   e.dw_tail = num("B200_DW_TAIL", 0);

@@ -138,37 +138,48 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) { // ===== X producer: fp16 rows -> MN-major SWIZZLE_128B atoms, two boxes {64 features, 32 samples} per M tile ==
+    { // ===== X producer: fp16 rows -> MN-major SWIZZLE_128B atoms, two boxes {64 features, 32 samples} per M tile (whole warp in
+      // the loop, one elected lane issues) ==
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(st_empty(s), ph ^ 1);
-        if (p.diag & 1) { mbar_arrive(conv_full(s)); if (++s == NX) { s = 0; ph ^= 1; } continue; }
-        mbar_expect_tx(conv_full(s), nmt * kDConvTile);
-        for (int t = 0; t < nmt; ++t)
+        if (elect_one()) {
+          if (p.diag & 1) mbar_arrive(conv_full(s));
+          else {
+            mbar_expect_tx(conv_full(s), nmt * kDConvTile);
+            for (int t = 0; t < nmt; ++t)
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_3d(conv_a(s) + t * kDConvTile + j * kDAtom, &tmX, conv_full(s), 0, p.row0 + kb * kDK, (m0 + t * kDM) / 64 + j);
+              for (int j = 0; j < 2; ++j)
+                tma_load_3d(conv_a(s) + t * kDConvTile + j * kDAtom, &tmX, conv_full(s), 0, p.row0 + kb * kDK, (m0 + t * kDM) / 64 + j);
+          }
+        }
+        __syncwarp();
         if (++s == NX) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 3) {
-    if (lane == 0) { // ===== delta producer: NB / 64 boxes {64 halves, 64 samples}, MN-major SWIZZLE_128B ==========
+    { // ===== delta producer: NB / 64 boxes {64 halves, 64 samples}, MN-major SWIZZLE_128B ==========
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(b_empty(s), ph ^ 1);
-        if (p.diag & 2) { mbar_arrive(b_full(s)); if (++s == ND) { s = 0; ph ^= 1; } continue; }
-        mbar_expect_tx(b_full(s), Plan::kBStage);
+        if (elect_one()) {
+          if (p.diag & 2) mbar_arrive(b_full(s));
+          else {
+            mbar_expect_tx(b_full(s), Plan::kBStage);
 #pragma unroll
-        for (int j = 0; j < NB / 64; ++j) tma_load_2d(b_a(s) + j * kDAtom, &tmD, b_full(s), 64 * j, kb * kDK);
+            for (int j = 0; j < NB / 64; ++j) tma_load_2d(b_a(s) + j * kDAtom, &tmD, b_full(s), 64 * j, kb * kDK);
+          }
+        }
+        __syncwarp();
         if (++s == ND) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) { // ===== MMA issuer ======================================================================
+    { // ===== MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues the tcgen05 instructions ====
       const uint32_t idesc = make_idesc_f16_mn(NB);
       const uint64_t dA0 = desc_mn16(conv_a(0)), dB0 = desc_mn16(b_a(0));
       int s = 0, sb = 0;
@@ -182,22 +193,27 @@ dw16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         if (p.dbg) { waited += t1 - t0; waited_b += clock64() - t1; }
         tc_fence_after();
         const uint64_t da = dA0 + (uint64_t)(s * (kDConvBytes >> 4)), db = dB0 + (uint64_t)(sb * (Plan::kBStage >> 4));
+        const int nt = (p.diag & 4) ? 0 : nmt;
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < kDMT; ++t) {
-          if (t < nmt && !(p.diag & 4)) {
+          for (int t = 0; t < kDMT; ++t) {
+            if (t < nt) {
 #pragma unroll
-            for (int ks = 0; ks < kDK / 16; ++ks) // 16 samples = two 8-row K groups = 2048 B further into every atom
-              umma_f16_d(tmem_base + t * NB, da + t * (kDConvTile >> 4) + 128 * ks, db + 128 * ks, idesc,
-                         (kb > kb_begin || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < kDK / 16; ++ks) // 16 samples = two 8-row K groups = 2048 B further into every atom
+                umma_f16_d(tmem_base + t * NB, da + t * (kDConvTile >> 4) + 128 * ks, db + 128 * ks, idesc,
+                           (kb > kb_begin || ks > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(st_empty(s));
+          if constexpr (NX != ND) umma_commit(b_empty(sb));
         }
-        umma_commit(st_empty(s));
-        if constexpr (NX != ND) umma_commit(b_empty(sb));
+        __syncwarp();
         if (++s == NX) { s = 0; ph ^= 1; }
         if (++sb == ND) { sb = 0; phb ^= 1; }
       }
-      umma_commit(acc_full);
-      if (p.dbg) { p.dbg[4 * blockIdx.x + 1] = waited; p.dbg[4 * blockIdx.x + 2] = waited_b; }
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
+      if (p.dbg && lane == 0) { p.dbg[4 * blockIdx.x + 1] = waited; p.dbg[4 * blockIdx.x + 2] = waited_b; }
     }
     __syncwarp();
   } else if (warp >= 4) {

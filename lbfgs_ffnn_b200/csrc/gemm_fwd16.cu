@@ -219,7 +219,8 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const int umma_n = min(BN, (p.cols_valid + 31) & ~31);
 
   if (warp == 0) {
-    if (lane == 0) { // ===== X producer: fp16 rows straight from HBM into the K-major SWIZZLE_128B operand tile ===========
+    { // ===== X producer: fp16 rows straight from HBM into the K-major SWIZZLE_128B operand tile (whole warp in the loop, one
+      // elected lane issues: the TMA instructions then need no loop over the active lanes) ===========
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -228,53 +229,63 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         if (EPI == EPI_DX) { // the hi blocks of A_prev's pair for this tile's act' (double-buffered like the accumulators)
           const int buf = it & 1;
           mbar_wait(aux_empty(buf), ((it >> 1) & 1) ^ 1);
-          mbar_expect_tx(aux_full(buf), Plan::kAuxTile);
+          if (elect_one()) {
+            mbar_expect_tx(aux_full(buf), Plan::kAuxTile);
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b) tma_load_3d(aux_a(buf) + b * kConvBytes, &tmAux, aux_full(buf), 0, p.row0 + tile * kFM, b);
+            for (int b = 0; b < BN / 64; ++b) tma_load_3d(aux_a(buf) + b * kConvBytes, &tmAux, aux_full(buf), 0, p.row0 + tile * kFM, b);
+          }
+          __syncwarp();
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(conv_empty(s), ph ^ 1);
-          if (p.diag & 1) { if (leader) mbar_arrive(conv_full(s)); }
-          else if constexpr (PAIR) { // both CTAs' tiles are counted on the leader's barrier
-            if (leader) mbar_expect_tx(conv_full(s), 2 * kConvBytes);
-            if (p.x_block_first) tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, kb, p.row0 + tile * kFM);
-            else tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, p.row0 + tile * kFM, kb);
-          } else {
-            mbar_expect_tx(conv_full(s), kConvBytes);
-            if (p.x_block_first) tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, kb, p.row0 + tile * kFM);
-            else tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
+          if (elect_one()) {
+            if (p.diag & 1) { if (leader) mbar_arrive(conv_full(s)); }
+            else if constexpr (PAIR) { // both CTAs' tiles are counted on the leader's barrier
+              if (leader) mbar_expect_tx(conv_full(s), 2 * kConvBytes);
+              if (p.x_block_first) tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, kb, p.row0 + tile * kFM);
+              else tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, p.row0 + tile * kFM, kb);
+            } else {
+              mbar_expect_tx(conv_full(s), kConvBytes);
+              if (p.x_block_first) tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, kb, p.row0 + tile * kFM);
+              else tma_load_3d(conv_a(s), &tmX, conv_full(s), 0, p.row0 + tile * kFM, kb);
+            }
           }
+          __syncwarp();
           if (++s == kNC) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 3) {
-    if (lane == 0) { // ===== weight producer ===========================================================
+    { // ===== weight producer ===========================================================
       int s = 0;
       uint32_t ph = 0;
       for (int unit = unit0; unit < units; unit += unit_step) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(w_empty(s), ph ^ 1);
-          if (p.diag & 2) { if (leader) mbar_arrive(w_full(s)); }
-          else if constexpr (PAIR) { // this CTA's half of B = [W_hi; W_lo]: rows 0 .. BN-1 (hi) in the leader, BN .. 2 BN-1 (lo) in the peer
-            if (leader) mbar_expect_tx(w_full(s), 2 * Plan::kWStage);
-            tma_load_2d_pair(w_a(s, 0), leader ? &tmWh : &tmWl, w_full(s) + lead_off, kb * kFK, 0);
-          } else {
-            mbar_expect_tx(w_full(s), Plan::kWStage);
-            tma_load_2d(w_a(s, 0), &tmWh, w_full(s), kb * kFK, 0);
-            if (X2) tma_load_2d(w_a(s, 1), &tmWl, w_full(s), kb * kFK, 0);
+          if (elect_one()) {
+            if (p.diag & 2) { if (leader) mbar_arrive(w_full(s)); }
+            else if constexpr (PAIR) { // this CTA's half of B = [W_hi; W_lo]: rows 0 .. BN-1 (hi) in the leader, BN .. 2 BN-1 (lo) in the peer
+              if (leader) mbar_expect_tx(w_full(s), 2 * Plan::kWStage);
+              tma_load_2d_pair(w_a(s, 0), leader ? &tmWh : &tmWl, w_full(s) + lead_off, kb * kFK, 0);
+            } else {
+              mbar_expect_tx(w_full(s), Plan::kWStage);
+              tma_load_2d(w_a(s, 0), &tmWh, w_full(s), kb * kFK, 0);
+              if (X2) tma_load_2d(w_a(s, 1), &tmWl, w_full(s), kb * kFK, 0);
+            }
           }
+          __syncwarp();
           if (++s == kNW) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && leader) { // ===== MMA issuer (PAIR: the leader issues for both CTAs) ==============================
+    if (leader) { // ===== MMA issuer (PAIR: the leader issues for both CTAs). The WHOLE warp runs the loop (uniform control flow,
+      // operands in uniform registers) and one elected lane issues the tcgen05 instructions. =====================================
       // One MMA per K step: with the lo tile stored right behind the hi tile, B = [W_hi; W_lo] is a single 2*BN-row K-major
       // operand and D = [hi | lo] lands in adjacent TMEM columns. Descriptors are built once; per stage / K step only the
-      // 14-bit start-address field moves (the issuing thread is otherwise bound by descriptor arithmetic, not by the tensor pipe).
+      // 14-bit start-address field moves.
       const uint32_t idesc = make_idesc_f16(X2 ? 2 * BN : umma_n, PAIR ? 2 * kFM : kFM);
       const uint64_t dA0 = desc_k_major(conv_a(0)), dB0 = desc_k_major(w_a(0, 0));
       int cs = 0, ws = 0, it = 0;
@@ -284,7 +295,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const int buf = it & 1;
         const uint32_t d_acc = tmem_base + (uint32_t)(buf * 2 * BN);
         const long long tt0 = p.dbg ? clock64() : 0;
-        if (p.dbg && blockIdx.x == 0 && it < 8) { p.dbg[4096 + 2 * it] = tt0; p.dbg[4096 + 2 * it + 1] = (long long)globaltimer_ns(); }
+        if (p.dbg && blockIdx.x == 0 && it < 8 && lane == 0) { p.dbg[4096 + 2 * it] = tt0; p.dbg[4096 + 2 * it + 1] = (long long)globaltimer_ns(); }
         mbar_wait(tm_empty(buf), ((it >> 1) & 1) ^ 1);
         if (p.dbg) waited_tm += clock64() - tt0;
         tc_fence_after();
@@ -296,26 +307,32 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           const long long t1 = p.dbg ? clock64() : 0;
           if (p.dbg) { waited += t0b - t0; waited_w += t1 - t0b; }
           tc_fence_after();
-          const int nks = min(kFK / 16, (p.k_total - kb * kFK + 15) / 16);
+          const int nks = (p.diag & 4) ? 0 : min(kFK / 16, (p.k_total - kb * kFK + 15) / 16);
           const uint64_t da = dA0 + (uint64_t)(cs * (kConvBytes >> 4)), db = dB0 + (uint64_t)(ws * (Plan::kWStage >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kFK / 16; ++ks)
-            if (ks < nks && !(p.diag & 4)) umma_f16<PAIR>(d_acc, da + 2 * ks, db + 2 * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          const long long t2 = p.dbg ? clock64() : 0;
-          if (p.dbg) t_mma += t2 - t1;
-          if constexpr (PAIR) umma_commit_pair(conv_empty(cs)); // frees the stage in both CTAs
-          else umma_commit(conv_empty(cs)); // (== w_empty(ws) when both rings have the same depth)
-          if constexpr (kNW != kNC) { if constexpr (PAIR) umma_commit_pair(w_empty(ws)); else umma_commit(w_empty(ws)); }
-          if (p.dbg) t_commit += clock64() - t2;
+            for (int ks = 0; ks < kFK / 16; ++ks)
+              if (ks < nks) umma_f16<PAIR>(d_acc, da + 2 * ks, db + 2 * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_commit_pair(conv_empty(cs)); // frees the stage in both CTAs
+            else umma_commit(conv_empty(cs)); // (== w_empty(ws) when both rings have the same depth)
+            if constexpr (kNW != kNC) { if constexpr (PAIR) umma_commit_pair(w_empty(ws)); else umma_commit(w_empty(ws)); }
+          }
+          __syncwarp();
+          if (p.dbg) t_mma += clock64() - t1;
           if (++cs == kNC) { cs = 0; cph ^= 1; }
           if (++ws == kNW) { ws = 0; wph ^= 1; }
         }
-        if constexpr (PAIR) umma_commit_pair(tm_full(buf));
-        else umma_commit(tm_full(buf));
+        if (elect_one()) {
+          if constexpr (PAIR) umma_commit_pair(tm_full(buf));
+          else umma_commit(tm_full(buf));
+        }
+        __syncwarp();
       }
-      if (p.dbg && blockIdx.x == 0 && it < 8) { p.dbg[4096 + 2 * it] = clock64(); p.dbg[4096 + 2 * it + 1] = (long long)globaltimer_ns(); p.dbg[4096 + 16] = it; }
-      if (p.dbg && blockIdx.x == 0) { p.dbg[4096 + 20] = t_mma; p.dbg[4096 + 21] = t_commit; }
-      if (p.dbg) { p.dbg[8 * blockIdx.x + 3] = waited; p.dbg[8 * blockIdx.x + 4] = waited_w; p.dbg[8 * blockIdx.x + 5] = waited_tm; }
+      if (p.dbg && blockIdx.x == 0 && it < 8 && lane == 0) {
+        p.dbg[4096 + 2 * it] = clock64(); p.dbg[4096 + 2 * it + 1] = (long long)globaltimer_ns(); p.dbg[4096 + 16] = it;
+        p.dbg[4096 + 20] = t_mma; p.dbg[4096 + 21] = t_commit;
+      }
+      if (p.dbg && lane == 0) { p.dbg[8 * blockIdx.x + 3] = waited; p.dbg[8 * blockIdx.x + 4] = waited_w; p.dbg[8 * blockIdx.x + 5] = waited_tm; }
     }
     __syncwarp();
   } else if (warp >= kEpiWarp0) {

@@ -3,6 +3,7 @@
 #include "lbfgs_kernels.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace b200 {
 
@@ -41,7 +42,9 @@ __device__ __forceinline__ void st4(float *p, size_t i, size_t n, bool vec, floa
 // of the CTA, so the shuffle reduction happens once per kernel, not once per tile.
 // RPW = rows per warp (compile-time so the accumulators stay in registers).
 // ------------------------------------------------------------------------------------------------
-template <int RPW, bool PAIR>
+// HS = 2 (fused direction kernel, 16 warps): warps 8-15 take the second half of every tile row of the SAME ring rows, so a warp
+// waits for one round of loads per row instead of two; the halves are combined through shared memory in a fixed order.
+template <int RPW, bool PAIR, int HS = 1>
 __device__ __forceinline__ void dots_body(const DotsArgs &a) {
   __shared__ __align__(16) double sh_g[kDotsTile];
   __shared__ __align__(16) double sh_s[PAIR ? kDotsTile : 2];
@@ -49,8 +52,10 @@ __device__ __forceinline__ void dots_body(const DotsArgs &a) {
   __shared__ int sh_rows[kMaxSlots];
   __shared__ int sh_nrows, sh_w;
   __shared__ double sh_red[32];
+  __shared__ double sh_half[HS == 2 ? 2 * RPW * kDotsWarps * kDotsCols : 1];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) % kDotsWarps, whalf = (tid >> 5) / kDotsWarps;
+  const bool stager = tid < kDotsThreads; // (HS == 2: the first 256 threads stage the tile)
   const int mp = a.st.h->mp, mod = a.st.h->mod;
   if (tid == 0) {
     int head = a.st.h->head, count = a.st.h->count;
@@ -85,7 +90,7 @@ __device__ __forceinline__ void dots_body(const DotsArgs &a) {
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t base = tile * kDotsTile;
     __syncthreads(); // previous tile fully consumed
-    { // stage: one float4 per thread
+    if (stager) { // stage: one float4 per thread
       const size_t i = base + (size_t)tid * 4;
       const float4 g4 = ld4(a.g, i, a.n, vec);
       if (a.row_begin == 0) gg += (double)g4.x * g4.x + (double)g4.y * g4.y + (double)g4.z * g4.z + (double)g4.w * g4.w;
@@ -119,6 +124,7 @@ __device__ __forceinline__ void dots_body(const DotsArgs &a) {
       const bool self = PAIR && (p == w) && (a.mode == DOTS_FORM_PAIR); // row being written this pass: use smem copy
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
+        if (HS == 2 && half != whalf) continue;
         float4 sv[4], yv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -165,7 +171,16 @@ __device__ __forceinline__ void dots_body(const DotsArgs &a) {
 #pragma unroll
     for (int c = 0; c < kDotsCols; ++c) {
       const double v = warp_sum(acc[r][c]);
-      if (lane == 0 && ri < nrows) out[sh_rows[ri] * kDotsCols + c] = v;
+      if (HS == 2) { if (lane == 0) sh_half[((whalf * RPW + r) * kDotsWarps + warp) * kDotsCols + c] = v; }
+      else if (lane == 0 && ri < nrows) out[sh_rows[ri] * kDotsCols + c] = v;
+    }
+  }
+  if (HS == 2) {
+    __syncthreads();
+    if (tid < RPW * kDotsWarps * kDotsCols) {
+      const int c = tid % kDotsCols, wr = tid / kDotsCols, w_ = wr % kDotsWarps, r = wr / kDotsWarps;
+      const int ri = a.row_begin + w_ + r * kDotsWarps;
+      if (ri < nrows) out[sh_rows[ri] * kDotsCols + c] = sh_half[tid] + sh_half[RPW * kDotsWarps * kDotsCols + tid];
     }
   }
   gg = block_sum(gg, sh_red);
@@ -192,7 +207,12 @@ struct SolveLocal {
 // `leader` CTAs write the device state; in the fused direction kernel every CTA runs this redundantly on the same inputs
 // (identical results) so that no second grid-wide barrier is needed, and only CTA 0 is the leader. head_in / count_in: the
 // ring header as it was BEFORE this direction (the leader overwrites it while other CTAs may still be reading).
-__device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool leader, int head_in, int count_in, SolveLocal *res) {
+// STAGED (compile time): the Gram blocks are known to sit in shared memory, so the recurrences read them with shared-memory
+// loads; otherwise a.stage_gram decides at run time and the accesses are generic
+template <bool STAGED = false>
+__device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool leader, int head_in, int count_in, SolveLocal *res,
+                                           long long *dbg = nullptr) {
+  const long long td0 = dbg ? clock64() : 0;
   // sh: tot[ncols] | alpha[mp] | dlt[mp] | cs[mp] | cy[mp] | (staged) SY[mp*mp] | YY[mp*mp] | rho, sg, yg [mp] | phys[mp] (int)
   LbfgsHeader *h = a.st.h;
   const int mp = h->mp, mod = h->mod;
@@ -200,7 +220,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
   double *tot = sh, *alpha = sh + ncols, *dlt = alpha + mp, *lcs = dlt + mp, *lcy = lcs + mp;
   __shared__ int s_head, s_count, s_w, s_k;
   __shared__ double s_cg, s_alpha0;
-  const bool stage = a.stage_gram != 0;
+  const bool stage = STAGED || a.stage_gram != 0;
   double *SYp = a.st.SY, *YYp = a.st.YY, *rhop = a.st.rho, *sgp = a.st.sg, *ygp = a.st.yg;
   int *physp = a.st.phys;
   if (stage) {
@@ -208,25 +228,46 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
     physp = reinterpret_cast<int *>(ygp + mp);
   }
 
-  // fixed-order (deterministic) reduction of the per-CTA partials: 8 threads per column, each a strided
-  // slice of the blocks, combined by shuffles — ~nblocks/8 dependent loads instead of nblocks
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+  // fixed-order (deterministic) reduction of the per-CTA partials. Short histories (all columns fit the CTA with several
+  // threads each): ONE pass, every thread sums a strided slice of the blocks with 16 loads in flight per step and the threads
+  // of a column are combined by shuffles, i.e. ~nblocks / (16 tpc) dependent L2 round trips. Otherwise 32 columns at a time,
+  // 8 threads per column.
+  int tpc = 1;
+  while (tpc < 8 && ncols * (tpc * 2) <= (int)blockDim.x) tpc *= 2;
+  if (tpc >= 2) {
+    const int c = threadIdx.x / tpc, sub = threadIdx.x % tpc;
     double s = 0.0;
     if (c < ncols) {
-      for (int b0 = sub; b0 < a.nblocks; b0 += 64) { // eight independent loads in flight per step, same summation order
-        double t[8];
+      for (int b0 = sub; b0 < a.nblocks; b0 += 16 * tpc) {
+        double t[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = (b0 + 8 * u < a.nblocks) ? __ldcg(a.partials + (size_t)(b0 + 8 * u) * ncols + c) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += t[u];
+        for (int u = 0; u < 16; ++u) t[u] = (b0 + tpc * u < a.nblocks) ? __ldcg(a.partials + (size_t)(b0 + tpc * u) * ncols + c) : 0.0;
+        s += (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) +
+             (((t[8] + t[9]) + (t[10] + t[11])) + ((t[12] + t[13]) + (t[14] + t[15])));
       }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    for (int o = 1; o < tpc; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (c < ncols && sub == 0) tot[c] = s;
+  } else {
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int c = c0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+      double s = 0.0;
+      if (c < ncols) {
+        for (int b0 = sub; b0 < a.nblocks; b0 += 64) { // eight independent loads in flight per step, same summation order
+          double t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = (b0 + 8 * u < a.nblocks) ? __ldcg(a.partials + (size_t)(b0 + 8 * u) * ncols + c) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) s += t[u];
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (c < ncols && sub == 0) tot[c] = s;
+    }
   }
+  const long long td1 = dbg ? clock64() : 0;
   if (stage) { // everything the 2k dependent recurrence steps touch lives in shared memory (an L2 round trip per step otherwise)
     for (int i = threadIdx.x; i < mp * mp; i += blockDim.x) { SYp[i] = a.st.SY[i]; YYp[i] = a.st.YY[i]; }
     for (int i = threadIdx.x; i < mp; i += blockDim.x) { rhop[i] = a.st.rho[i]; sgp[i] = a.st.sg[i]; ygp[i] = a.st.yg[i]; }
@@ -299,6 +340,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
   }
   __syncthreads();
 
+  const long long td2 = dbg ? clock64() : 0;
   // two-loop recurrences on the Gram blocks: warp 0, lanes parallel over the inner sums
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
@@ -311,43 +353,74 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
     }
     __syncwarp();
     double gamma = 1.0, cg = -1.0, gdotp = -gg;
-    if (k > 0 && k <= 24) {
-      // short histories: ONE lane runs the recurrences serially out of shared memory. A k-term fp64 dot is k dependent FMAs
-      // (~8 clk each); the warp-shuffle version below pays 5 x 2 shuffles of ~25 clk per sum, 3 sums per step.
-      if (lane == 0) {
-        for (int i = k - 1; i >= 0; --i) {
-          const int pi = physp[i];
-          double s = 0.0;
-          for (int j = i + 1; j < k; ++j) s += alpha[j] * SYp[pi * mp + physp[j]];
-          alpha[i] = rhop[pi] * (sgp[pi] - s);
+    if (k > 0 && k <= 32) {
+      // Histories of up to 32 pairs: lane i owns logical slot i and both recurrences run in their column (axpy) form — at step j
+      // the lane of slot j finishes its value, broadcasts it with one shuffle and every lane still waiting folds it into its own
+      // running sum. The dependent chain is one shuffle + one FMA per slot (~50 clk) instead of the j-term dot product a single
+      // lane used to walk through shared memory (the old form took ~15 k clk at k = 10: 40 % of the whole direction kernel).
+      if (dbg && lane == 0) dbg[4] = clock64() - td2;
+      const bool on = lane < k;
+      const int pi = on ? physp[lane] : 0;
+      const double rho_i = on ? rhop[pi] : 0.0, sg_i = on ? sgp[pi] : 0.0, yg_i = on ? ygp[pi] : 0.0;
+      // the matrix entries this lane needs come out of shared memory BEFORE the chains start (they do not depend on them):
+      // row i of S^T Y and Y^T Y and column i of S^T Y in logical order, pre-multiplied by rho_i where the recurrences use them so
+      const double *sy_row = SYp + pi * mp, *yy_row = YYp + pi * mp;
+      // alpha_j = rho_j (s_j.g - sum_{l > j} alpha_l s_j.y_l): lane i keeps a_i = rho_i (s_i.g - partial sum); the chain per slot is
+      // one shuffle + one FMA
+      double av = rho_i * sg_i, alpha_i = 0.0;
+      {
+        double m_next = -rho_i * sy_row[physp[k - 1]];
+        for (int j = k - 1; j >= 0; --j) {
+          const double mj = m_next;
+          if (j > 0) m_next = -rho_i * sy_row[physp[j - 1]];
+          const double aj = __shfl_sync(0xffffffffu, av, j);
+          if (lane == j) alpha_i = aj;
+          if (lane < j) av = fma(aj, mj, av);
         }
-        const int pl = physp[k - 1];
-        const double ys = SYp[pl * mp + pl], yy = YYp[pl * mp + pl];
-        if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
-        else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
-        else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
-          gamma = (fabs(yy) < 1e-12) ? 1.0 : ys / yy;
-          gamma = fmin(fmax(gamma, 1e-6), 1e6);
-        }
-        for (int i = 0; i < k; ++i) {
-          const int pi = physp[i];
-          double s1 = 0.0, s2 = 0.0;
-          for (int j = 0; j < k; ++j) s1 += alpha[j] * YYp[pi * mp + physp[j]];
-          for (int j = 0; j < i; ++j) s2 += dlt[j] * SYp[physp[j] * mp + pi];
-          const double beta = rhop[pi] * (gamma * (ygp[pi] - s1) + s2);
-          dlt[i] = alpha[i] - beta;
-        }
-        cg = -gamma;
-        double gp = 0.0;
-        for (int j = 0; j < k; ++j) {
-          const double csj = -dlt[j], cyj = gamma * alpha[j];
-          lcs[j] = csj;
-          lcy[j] = cyj;
-          if (leader) { a.st.cs[j] = csj; a.st.cy[j] = cyj; }
-          gp += csj * sgp[physp[j]] + cyj * ygp[physp[j]];
-        }
-        gdotp = cg * gg + gp;
       }
+      if (dbg && lane == 0) dbg[5] = clock64() - td2;
+      const int pl = physp[k - 1];
+      const double ys = SYp[pl * mp + pl], yy = YYp[pl * mp + pl];
+      if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
+      else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
+      else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
+        gamma = (fabs(yy) < 1e-12) ? 1.0 : ys / yy;
+        gamma = fmin(fmax(gamma, 1e-6), 1e6);
+      }
+      // sum_j alpha_j y_i.y_j: no dependence on the second recurrence; four partial sums keep the FMA chain short
+      double s1p[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int j0 = 0; j0 < k; j0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(j0 + u, k - 1);
+          const double aj = __shfl_sync(0xffffffffu, alpha_i, j);
+          s1p[u] = fma(j0 + u < k ? aj : 0.0, yy_row[physp[j]], s1p[u]);
+        }
+      }
+      const double s1 = (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]);
+      if (dbg && lane == 0) dbg[6] = clock64() - td2;
+      // delta_j = alpha_j - rho_j (gamma (y_j.g - s1_j) + sum_{l < j} delta_l s_l.y_j): lane i keeps d_i = alpha_i - rho_i (...)
+      double dv = alpha_i - rho_i * (gamma * (yg_i - s1)), dlt_i = 0.0;
+      {
+        double m_next = -rho_i * SYp[physp[0] * mp + pi];
+        for (int j = 0; j < k; ++j) {
+          const double mj = m_next;
+          if (j + 1 < k) m_next = -rho_i * SYp[physp[j + 1] * mp + pi];
+          const double dj = __shfl_sync(0xffffffffu, dv, j);
+          if (lane == j) dlt_i = dj;
+          if (lane > j) dv = fma(dj, mj, dv);
+        }
+      }
+      if (dbg && lane == 0) dbg[7] = clock64() - td2;
+      cg = -gamma;
+      const double csj = -dlt_i, cyj = gamma * alpha_i;
+      if (on) {
+        lcs[lane] = csj;
+        lcy[lane] = cyj;
+        if (leader) { a.st.cs[lane] = csj; a.st.cy[lane] = cyj; }
+      }
+      const double gp = warp_sum(on ? csj * sg_i + cyj * yg_i : 0.0);
+      gdotp = cg * gg + gp;
     } else if (k > 0) {
       for (int i = k - 1; i >= 0; --i) {
         const int pi = physp[i];
@@ -391,6 +464,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
       gdotp = cg * gg + gp;
     }
     __syncwarp();
+    if (dbg && lane == 0) dbg[2] = clock64() - td2;
     if (lane == 0) {
       int kk = k;
       // non-descent direction: steepest descent + history reset (src/cuda/lbfgs.cuh:97-104).
@@ -412,6 +486,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
     }
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) { dbg[0] = td1 - td0; dbg[1] = td2 - td1; dbg[3] = clock64() - td2; }
   if (res) { res->k = s_k; res->cg = s_cg; res->alpha0 = s_alpha0; res->cs = lcs; res->cy = lcy; res->phys = physp; }
 }
 
@@ -436,7 +511,8 @@ template <bool COHERENT> __device__ __forceinline__ float4 ld4c(const float *p, 
   return v;
 }
 
-template <bool COHERENT>
+// U: history pairs whose loads are in flight together (2 U 16-byte loads per step)
+template <bool COHERENT, int U = 4>
 __device__ __forceinline__ void apply_body(const ApplyArgs &a, int k, double cg_in, double alpha0_in, const double *s_cs,
                                            const double *s_cy, const int *s_ph) {
   const double cg = cg_in * a.sign;
@@ -451,16 +527,16 @@ __device__ __forceinline__ void apply_body(const ApplyArgs &a, int k, double cg_
     const size_t i = v * 4;
     const float4 g4 = ld4c<COHERENT>(a.g, i, a.n, vec);
     double r0 = cg * g4.x, r1 = cg * g4.y, r2 = cg * g4.z, r3 = cg * g4.w;
-    for (int j0 = 0; j0 < k; j0 += 4) { // four pairs (eight 16-byte loads) in flight per step; same order of the fp64 sums
-      float4 s4[4], y4[4];
+    for (int j0 = 0; j0 < k; j0 += U) { // U pairs (2 U 16-byte loads) in flight per step; same order of the fp64 sums
+      float4 s4[U], y4[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int j = min(j0 + u, k - 1);
         s4[u] = ld4c<COHERENT>(a.S + (size_t)s_ph[j] * a.ld, i, a.n, vec);
         y4[u] = ld4c<COHERENT>(a.Y + (size_t)s_ph[j] * a.ld, i, a.n, vec);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (j0 + u < k) {
           const double cs = s_cs[j0 + u] * a.sign, cy = s_cy[j0 + u] * a.sign;
           r0 = fma(cs, (double)s4[u].x, r0); r1 = fma(cs, (double)s4[u].y, r1);
@@ -525,22 +601,29 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) { 
   __syncthreads();
 }
 
-template <int RPW, bool PAIR>
-__global__ void __launch_bounds__(kDotsThreads) lbfgs_direction_kernel(const DotsArgs da, const SolveArgs sa, const ApplyArgs aa,
-                                                                      unsigned *bar, const SpecState *spec_st, int spec) {
+template <int RPW, bool PAIR, int HS>
+__global__ void __launch_bounds__(kDotsThreads * HS) lbfgs_direction_kernel(const DotsArgs da, const SolveArgs sa, const ApplyArgs aa,
+                                                                      unsigned *bar, const SpecState *spec_st, int spec, long long *dbg) {
   pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return; // every CTA takes the same branch: nobody reaches the grid barrier
   extern __shared__ double sh[];
   __shared__ int s_head0, s_count0;
+  const long long t0 = dbg ? clock64() : 0;
   if (threadIdx.x == 0) { s_head0 = da.st.h->head; s_count0 = da.st.h->count; } // before anyone can overwrite the header
-  dots_body<RPW, PAIR>(da); // (its barriers publish s_head0 / s_count0)
+  dots_body<RPW, PAIR, HS>(da); // (its barriers publish s_head0 / s_count0)
+  const long long t1 = dbg ? clock64() : 0;
   grid_barrier(bar, gridDim.x);
+  const long long t2 = dbg ? clock64() : 0;
   __shared__ SolveLocal res;
   SolveLocal r;
-  solve_body(sa, sh, blockIdx.x == 0, s_head0, s_count0, &r);
+  solve_body<true>(sa, sh, blockIdx.x == 0, s_head0, s_count0, &r, (dbg && blockIdx.x <= 1) ? dbg + 4096 + 8 * blockIdx.x : nullptr);
   if (threadIdx.x == 0) res = r;
   __syncthreads();
-  apply_body<true>(aa, res.k, res.cg, res.alpha0, res.cs, res.cy, res.phys);
+  const long long t3 = dbg ? clock64() : 0;
+  apply_body<true, 6>(aa, res.k, res.cg, res.alpha0, res.cs, res.cy, res.phys);
+  if (dbg && threadIdx.x == 0) { // B200_TC_TIMING: phases of this CTA in SM clocks
+    dbg[4 * blockIdx.x + 0] = t1 - t0; dbg[4 * blockIdx.x + 1] = t2 - t1; dbg[4 * blockIdx.x + 2] = t3 - t2; dbg[4 * blockIdx.x + 3] = clock64() - t3;
+  }
 }
 
 // totals[c] = sum_b partials[b][c] in a fixed order (sharded history: the totals are then all-reduced over ranks)
@@ -713,25 +796,40 @@ int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da0, const SolveArgs &
   da.row_begin = 0;
   SolveArgs sa = sa0;
   sa.stage_gram = 1;
-  auto run = [&](auto kern) -> int {
+  auto run = [&](auto kern, int threads) -> int {
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDotsThreads, smem));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if ((long)per_sm * ctx->num_sms < nblocks) return B200_OK; // the grid barrier needs every CTA resident
-    B200_CUDA(launch_ex(kern, dim3(nblocks), dim3(kDotsThreads), (size_t)smem, st, 1, da, sa, aa, bar, spec_st, spec));
+    static long long *dbg = nullptr;
+    const bool timing = env().tc_timing;
+    if (timing && !dbg) B200_CUDA(cudaMalloc(&dbg, sizeof(long long) * (4 * 1024 + 64)));
+    B200_CUDA(launch_ex(kern, dim3(nblocks), dim3(threads), (size_t)smem, st, 1, da, sa, aa, bar, spec_st, spec, timing ? dbg : (long long *)nullptr));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA(cudaGetLastError());
+    if (timing) {
+      std::vector<long long> h(4 * 1024 + 64);
+      B200_CUDA(cudaMemcpyAsync(h.data(), dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "[solve timing] CTA 0 / CTA 1: partial reduction %lld / %lld clk, Gram staging + update + header %lld / %lld, recurrences %lld / %lld, "
+              "recurrences + tail %lld / %lld | CTA 1 cumulative: ring order %lld, first recurrence %lld, s1 %lld, second recurrence %lld\n", h[4096], h[4104], h[4097], h[4105], h[4098], h[4106], h[4099], h[4107], h[4108], h[4109], h[4110], h[4111]);
+      double a[4] = {0, 0, 0, 0};
+      for (int i = 0; i < nblocks && i < 1024; ++i) for (int j = 0; j < 4; ++j) a[j] += (double)h[4 * i + j] / std::min(nblocks, 1024);
+      fprintf(stderr, "[direction timing] %d CTAs, mp %d: dots %.0f clk, grid barrier %.0f, reduce + solve %.0f (CTA 0: %lld), apply %.0f\n", nblocks, mp,
+              a[0], a[1], a[2], h[2], a[3]);
+    }
     *done = true;
     return B200_OK;
   };
-#define B200_DIR_CASE(R)                                                      \
-  case R:                                                                     \
-    if (pair) return run(lbfgs_direction_kernel<R, true>);                    \
-    return run(lbfgs_direction_kernel<R, false>);
+  // up to two rows per warp: 16 warps, the two halves of a tile row on different warps (one round of loads per row)
+#define B200_DIR_CASE(R, HS)                                                              \
+  case R:                                                                                 \
+    if (pair) return run(lbfgs_direction_kernel<R, true, HS>, kDotsThreads * HS);         \
+    return run(lbfgs_direction_kernel<R, false, HS>, kDotsThreads * HS);
   switch (rpw) {
-    B200_DIR_CASE(1)
-    B200_DIR_CASE(2)
-    B200_DIR_CASE(3)
-    B200_DIR_CASE(4)
+    B200_DIR_CASE(1, 2)
+    B200_DIR_CASE(2, 2)
+    B200_DIR_CASE(3, 1)
+    B200_DIR_CASE(4, 1)
   default:
     return B200_OK;
   }

@@ -88,6 +88,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a converged warp. The branch it guards is known to the compiler to run in a single thread, so uniform-datapath
+// instructions inside it (UTCHMMA, UTMALDG, UTCBAR) are issued directly instead of inside a loop over the active lanes.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %2;\n\t@px mov.s32 %1, 1;\n\tmov.s32 %0, rx;\n\t}"
+               : "+r"(laneid), "+r"(pred)
+               : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // ---- CTA pairs (cta_group::2): two CTAs of a cluster on the SMs of one TPC issue ONE tcgen05.mma of M = 256; each CTA holds
 // its 128 rows of A, HALF of the N rows of B and the accumulator of its own 128 rows. Only the even CTA (the leader) issues
 // MMAs and owns the "full" barriers; both CTAs' TMA loads signal those, and tcgen05.commit multicasts to both CTAs. ----------
