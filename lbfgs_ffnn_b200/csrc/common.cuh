@@ -243,6 +243,36 @@ __device__ __forceinline__ void spec_decide(SpecState *st, double loss, double g
 }
 
 // ---- device helpers -------------------------------------------------------------------------------
+// Compiler-only barrier for memory operations: a batch of independent loads written before it is ISSUED before anything after it.
+// Without it nvcc sinks each load of an unrolled batch next to its first use (fewer live registers), and an in-order SM then
+// waits one full L2 round trip per load instead of one per batch.
+__device__ __forceinline__ void loads_in_flight() { asm volatile("" ::: "memory"); }
+// Loads that stay where they are written (volatile asm statements keep their order): a batch of them is issued back to back.
+__device__ __forceinline__ float ldg_pinned(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// acc + (t0 + ... + t7) in fp64, a fixed tree; volatile like the loads, so that it stays BEHIND a batch of ldg_pinned (the
+// compiler otherwise converts and adds each value right after its load, which stalls an in-order SM once per load)
+__device__ __forceinline__ double sum8_pinned(double acc, float t0, float t1, float t2, float t3, float t4, float t5, float t6, float t7) {
+  double r;
+  asm volatile(
+      "{\n\t.reg .f64 d<8>;\n\t"
+      "cvt.f64.f32 d0, %2;\n\tcvt.f64.f32 d1, %3;\n\tcvt.f64.f32 d2, %4;\n\tcvt.f64.f32 d3, %5;\n\t"
+      "cvt.f64.f32 d4, %6;\n\tcvt.f64.f32 d5, %7;\n\tcvt.f64.f32 d6, %8;\n\tcvt.f64.f32 d7, %9;\n\t"
+      "add.f64 d0, d0, d1;\n\tadd.f64 d2, d2, d3;\n\tadd.f64 d4, d4, d5;\n\tadd.f64 d6, d6, d7;\n\t"
+      "add.f64 d0, d0, d2;\n\tadd.f64 d4, d4, d6;\n\tadd.f64 d0, d0, d4;\n\tadd.f64 %0, %1, d0;\n\t}"
+      : "=d"(r)
+      : "d"(acc), "f"(t0), "f"(t1), "f"(t2), "f"(t3), "f"(t4), "f"(t5), "f"(t6), "f"(t7));
+  return r;
+}
+__device__ __forceinline__ double ldcg_pinned(const double *p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -37,6 +37,7 @@ struct FinParams {
   float lam;
   float *grad;
   double *fin_part; // [gridDim.x][2] = {sum g^2, sum w^2}
+  const float *zero; // a float 0 in global memory: where the loads of slices past the last one point
   // the LAST CTA to finish also reduces the scalars (what eval_scalars_kernel did in a launch of its own)
   unsigned *done_count; // zero on entry, reset by the last CTA
   const double *loss_part;
@@ -77,51 +78,72 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
     gdst = reinterpret_cast<float *>(p.sym_local + (epoch & 1u) * p.slot_bytes);
   }
   const unsigned long long ngroups = (p.n + 31) / 32;
-  // groups are taken from the END of the vector first: the last layer's elements have the most slices (one per CTA of the
-  // last-layer backward kernel, ~300) and would otherwise start in the final pass of the loop, as the kernel's long pole
-  for (unsigned long long it = blockIdx.x; it < ngroups; it += gridDim.x) {
-    const unsigned long long grp = ngroups - 1 - it;
-    const unsigned long long j = grp * 32 + lane;
-    double acc = 0.0;
-    if (j < p.n) {
-      int l = 0;
+  // A group = 32 consecutive gradient elements (one coalesced 128-byte segment per slice). Two passes over the groups:
+  //  (1) "thin" groups (at most kThinSplits slices, e.g. the 37-way split-K of layer 0): ONE WARP per group with every slice load
+  //      in flight at once, no shared memory and no barrier — eight groups per CTA at a time;
+  //  (2) "fat" groups (hundreds of slices: one per CTA of the last-layer kernels / per SM of the mid-layer dW): the CTA's 8 warps
+  //      take the slices round-robin (up to 8 loads in flight per thread) and are combined in a fixed warp order.
+  // Either way an element is summed in fp64 in a fixed order: deterministic, rounded once.
+  constexpr int kThinSplits = 40;
+  auto layer_of = [&](unsigned long long j) {
+    int l = 0;
 #pragma unroll 1
-      while (l + 1 < p.nl && j >= p.L[l + 1].off) ++l;
-      const FinLayer &L = p.L[l];
+    while (l + 1 < p.nl && j >= p.L[l + 1].off) ++l;
+    return l;
+  };
+  auto emit = [&](unsigned long long j, double tot) {
+    if (p.lam != 0.0f) {
+      const float wv = __ldg(p.w + j);
+      tot = fma((double)p.lam, (double)wv, tot);
+      w2 += (double)wv * (double)wv;
+    }
+    const float s = (float)tot;
+    gdst[j] = s;
+    g2 += (double)s * (double)s;
+  };
+  // (2) first: the long poles start at once. Uniform per CTA: the class of a group is that of its first element's layer.
+  for (unsigned long long it = blockIdx.x; it < ngroups; it += gridDim.x) {
+    const unsigned long long grp = ngroups - 1 - it; // (from the END: the last layer's elements have the most slices)
+    if (p.L[layer_of(grp * 32)].splits <= kThinSplits) continue;
+    const unsigned long long j0 = grp * 32 + lane;
+    const unsigned long long j = j0 < p.n ? j0 : p.n - 1; // (lanes past the end repeat the last element and are not emitted)
+    double acc = 0.0;
+    {
+      const FinLayer &L = p.L[layer_of(j)];
       const float *src = L.part + (j - L.off);
-      int sp = warp;
-      for (; sp + 56 < L.splits; sp += 64) {
-        float t[8];
+      for (int sp = warp; sp < L.splits; sp += 128) { // 16 slices of this warp in flight per step
+        float t[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) t[u] = __ldg(src + (unsigned long long)(sp + 8 * u) * L.stride);
+        for (int u = 0; u < 16; ++u) t[u] = ldg_pinned(sp + 8 * u < L.splits ? src + (unsigned long long)(sp + 8 * u) * L.stride : p.zero);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += (double)t[u];
+        for (int u = 0; u < 16; u += 8) acc = sum8_pinned(acc, t[u], t[u + 1], t[u + 2], t[u + 3], t[u + 4], t[u + 5], t[u + 6], t[u + 7]);
       }
-      if (sp < L.splits && sp + 40 >= L.splits) { // at most five slices left for this warp (37-way split-K of layer 0): loads go out together
-        float t[5];
-#pragma unroll
-        for (int u = 0; u < 5; ++u) t[u] = (sp + 8 * u < L.splits) ? __ldg(src + (unsigned long long)(sp + 8 * u) * L.stride) : 0.0f;
-#pragma unroll
-        for (int u = 0; u < 5; ++u) acc += (double)t[u];
-        sp += 40;
-      }
-      for (; sp < L.splits; sp += 8) acc += (double)__ldg(src + (unsigned long long)sp * L.stride);
     }
     __syncthreads();
     sh[warp][lane] = acc;
     __syncthreads();
-    if (warp == 0 && j < p.n) {
-      double tot = ((sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane])) +
-                   ((sh[4][lane] + sh[5][lane]) + (sh[6][lane] + sh[7][lane]));
-      if (p.lam != 0.0f) {
-        const float wv = __ldg(p.w + j);
-        tot = fma((double)p.lam, (double)wv, tot);
-        w2 += (double)wv * (double)wv;
-      }
-      const float s = (float)tot;
-      gdst[j] = s;
-      g2 += (double)s * (double)s;
+    if (warp == 0 && j0 < p.n)
+      emit(j, ((sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane])) + ((sh[4][lane] + sh[5][lane]) + (sh[6][lane] + sh[7][lane])));
+  }
+  // (1)
+  for (unsigned long long grp = (unsigned long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (unsigned long long)gridDim.x * 8) {
+    if (p.L[layer_of(grp * 32)].splits > kThinSplits) continue; // (warp-uniform)
+    const unsigned long long j0 = grp * 32 + lane;
+    const bool live = j0 < p.n;
+    const unsigned long long j = live ? j0 : p.n - 1; // (every lane stays in the loop: the warp-level barrier below needs them all)
+    const FinLayer &L = p.L[layer_of(j)]; // (a group that straddles two layers: each lane follows its own)
+    const float *src = L.part + (j - L.off);
+    double acc = 0.0;
+    for (int sp0 = 0; sp0 < L.splits; sp0 += kThinSplits) {
+      float t[kThinSplits];
+#pragma unroll
+      for (int u = 0; u < kThinSplits; ++u) t[u] = ldg_pinned(sp0 + u < L.splits ? src + (unsigned long long)(sp0 + u) * L.stride : p.zero);
+      // (pinned: the 40 loads are issued back to back, ONE L2 round trip per batch)
+#pragma unroll
+      for (int u = 0; u < kThinSplits; u += 8) acc = sum8_pinned(acc, t[u], t[u + 1], t[u + 2], t[u + 3], t[u + 4], t[u + 5], t[u + 6], t[u + 7]);
     }
+    if (!live) continue;
+    emit(j, acc);
   }
   const double a = block_sum(g2, red);
   const double b = block_sum(w2, red);
@@ -137,10 +159,24 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   // loss = 0.5 * inv_batch * sum(loss_part) + 0.5 * lam * sum(w^2 parts); gnorm2 = sum(g^2 parts): fixed order (deterministic)
   __threadfence();
   double l = 0.0, sg = 0.0, sw = 0.0;
-  for (int i = threadIdx.x; i < p.n_loss; i += blockDim.x) l += __ldcg(p.loss_part + i);
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
-    sg += __ldcg(p.fin_part + 2 * i);
-    sw += __ldcg(p.fin_part + 2 * i + 1);
+  { // every load of this thread in flight before the first add (fixed order per thread)
+    double tl[4], tg[4], tw[4];
+    for (int i0 = threadIdx.x; i0 < p.n_loss; i0 += 4 * blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) tl[u] = (i0 + u * (int)blockDim.x < p.n_loss) ? __ldcg(p.loss_part + i0 + u * blockDim.x) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) l += tl[u];
+    }
+    for (int i0 = threadIdx.x; i0 < (int)gridDim.x; i0 += 4 * blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        const double2 v = (i < (int)gridDim.x) ? __ldcg(reinterpret_cast<const double2 *>(p.fin_part) + i) : make_double2(0.0, 0.0);
+        tg[u] = v.x; tw[u] = v.y;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { sg += tg[u]; sw += tw[u]; }
+    }
   }
   l = block_sum(l, red);
   sg = block_sum(sg, red);
@@ -838,6 +874,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   fp.lam = net->l2 / (float)ctx->world; // each rank adds its share; the all-reduce sums them
   fp.grad = grad_out;
   fp.fin_part = net->fin_part;
+  fp.zero = reinterpret_cast<const float *>(net->fin_part + 2 * net->fin_blocks);
   const bool multi = ctx->world > 1 && !net->defer_reduce;
   // collective (every rank evaluates the same networks in the same order); the first evaluation of a network is never inside a
   // graph capture. A network larger than the buffers were made for re-makes them.
@@ -912,9 +949,10 @@ int b200_net_create(b200_ctx *ctx, int nlayers, const int *dims, const int *acts
   net->skinny_splits.assign(nlayers, 1);
   net->k_chunk.assign(nlayers, 16);
   net->part_off.assign(nlayers, 0);
-  net->fin_blocks = std::max(1, std::min(8 * ctx->num_sms, ceil_div((long)net->n, 32)));
+  net->fin_blocks = std::max(1, std::min(4 * ctx->num_sms, ceil_div((long)net->n, 256))); // (a warp per group of 32 elements)
   cudaSetDevice(ctx->device);
-  B200_CUDA(cudaMalloc(&net->fin_part, sizeof(double) * 2 * net->fin_blocks));
+  B200_CUDA(cudaMalloc(&net->fin_part, sizeof(double) * (2 * net->fin_blocks + 2))); // (+ a zero: FinParams::zero)
+  B200_CUDA(cudaMemset(net->fin_part, 0, sizeof(double) * (2 * net->fin_blocks + 2)));
   B200_CUDA(cudaMalloc(&net->eval_out, sizeof(EvalOut)));
   B200_CUDA(cudaMalloc(&net->fin_done, sizeof(unsigned)));
   B200_CUDA(cudaMemset(net->fin_done, 0, sizeof(unsigned)));
