@@ -83,6 +83,9 @@ void env_reload();
 // completed and its memory is visible (griddepcontrol.wait). Launch latency, CTA rasterisation and whatever a kernel does
 // before it touches global memory overlap the tail of its predecessor; a CUDA graph captured from these launches carries
 // programmatic edges. Every kernel waits before it returns on every path, so completion stays transitive along the stream.
+// Measured (B200): launch-bound paths gain most — S-LBFGS 70 -> 92 epochs/s, GD 4 610 -> 5 850 it/s; the L-BFGS iteration 0.5 %.
+// Tried and rejected: running the tcgen05 kernels' set-up (barriers, TMEM allocation) BEFORE the wait. A successor's
+// tcgen05.alloc then blocks on an SM whose columns the predecessor's CTA still holds, and S-LBFGS epochs became 3x slower.
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
