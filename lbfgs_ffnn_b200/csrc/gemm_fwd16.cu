@@ -528,24 +528,35 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
   const int o0 = ((int)blockIdx.x - (which == 0 ? 0 : (which == 1 ? j0.nblocks : j0.nblocks + j1.nblocks))) * kSplitNeurons;
   const bool ok = o0 + o < j.Nn;
   if (j.rs_mode) { // block-uniform
-    const int k = threadIdx.x & 127, slice = threadIdx.x >> 7;
-    float a = 0.0f;
-    if (j.rs_mode == 1) { // 8 slices of the contraction index per feature; 16 loads in flight per thread
-      for (int r0 = slice; r0 < j.rs_R; r0 += 8 * 16) {
-        float t[16];
+    // 32 slices of the contraction index x 32 groups of four features: every thread's (<= 32) 16-byte loads are in flight in
+    // two batches, the partial sums meet in shared memory (the split tiles' space, not yet in use)
+    float *part = reinterpret_cast<float *>(&th[0][0]); // [32 slices][128 features]
+    static_assert(sizeof(th) >= 32 * 128 * sizeof(float), "partial sums of the feature bounds");
+    const int k4 = (threadIdx.x & 31) * 4, slice = threadIdx.x >> 5;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool w_vec = (reinterpret_cast<uintptr_t>(j.rs_W) & 15u) == 0; // (the caller's parameter buffer)
+    if (j.rs_mode == 1) {
+      for (int r0 = slice; r0 < j.rs_R; r0 += 32 * 16) {
+        float4 t[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) t[u] = (r0 + 8 * u < j.rs_R) ? fabsf(__ldg(j.rs_W + (size_t)(r0 + 8 * u) * 128 + k)) : 0.0f;
+        for (int u = 0; u < 16; ++u)
+          t[u] = (r0 + 32 * u >= j.rs_R) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                 : w_vec ? __ldg(reinterpret_cast<const float4 *>(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4))
+                         : make_float4(__ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4), __ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4 + 1),
+                                       __ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4 + 2), __ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4 + 3));
 #pragma unroll
-        for (int u = 0; u < 16; ++u) a += t[u];
+        for (int u = 0; u < 16; ++u) { a4.x += fabsf(t[u].x); a4.y += fabsf(t[u].y); a4.z += fabsf(t[u].z); a4.w += fabsf(t[u].w); }
       }
     }
-    red[k][slice] = a;
+    *reinterpret_cast<float4 *>(part + slice * 128 + k4) = a4;
     __syncthreads();
+    const int k = threadIdx.x & 127;
     if (threadIdx.x < 128) {
       float bound = 1.0f;
       if (j.rs_mode == 1) {
         float b1 = 0.0f;
-        for (int i = 0; i < 8; ++i) b1 += red[k][i];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) b1 += (part[i * 128 + k] + part[(i + 1) * 128 + k]) + (part[(i + 2) * 128 + k] + part[(i + 3) * 128 + k]);
         bound = b1 * 1.0001f + fabsf(__ldg(j.rs_bias + k)) + 1e-30f; // (fp32 summation slack)
       }
       int eb = 0;
@@ -570,9 +581,21 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
   }
   red[kq][o] = amax;
   __syncthreads();
+  // max over the 128 slices of each of the 8 rows: 256 threads take four slices each, shuffles combine the four parts a warp
+  // holds per row, the eight warps meet in shared memory (a 128-step serial scan per row cost ~2 us of a ~8 us kernel)
+  __shared__ float red2[8][kSplitNeurons];
+  if (threadIdx.x < 256) {
+    const int oo = threadIdx.x & (kSplitNeurons - 1), part = threadIdx.x >> 3; // 32 parts of 4 slices
+    float m = fmaxf(fmaxf(red[4 * part][oo], red[4 * part + 1][oo]), fmaxf(red[4 * part + 2][oo], red[4 * part + 3][oo]));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    if ((threadIdx.x & 31) < kSplitNeurons) red2[threadIdx.x >> 5][oo] = m;
+  }
+  __syncthreads();
   if (threadIdx.x < kSplitNeurons) {
     float m = 0.0f;
-    for (int i = 0; i < 128; ++i) m = fmaxf(m, red[i][threadIdx.x]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, red2[i][threadIdx.x]);
     int e = 0;
     if (m > 0.0f && m < 3.0e38f) frexpf(m, &e); // m = f * 2^e, f in [0.5, 1)
     e = max(-100, min(100, e));
