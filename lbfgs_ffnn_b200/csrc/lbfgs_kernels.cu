@@ -232,8 +232,8 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
   // threads each): ONE pass, every thread sums a strided slice of the blocks with 16 loads in flight per step and the threads
   // of a column are combined by shuffles, i.e. ~nblocks / (16 tpc) dependent L2 round trips. Otherwise 32 columns at a time,
   // 8 threads per column.
-  int tpc = 1;
-  while (tpc < 8 && ncols * (tpc * 2) <= (int)blockDim.x) tpc *= 2;
+  int tpc = 1; // (from 256 threads whatever the CTA size: the fused and the stand-alone solve then sum in the same order)
+  while (tpc < 8 && ncols * (tpc * 2) <= 256) tpc *= 2;
   if (tpc >= 2) {
     const int c = threadIdx.x / tpc, sub = threadIdx.x % tpc;
     double s = 0.0;

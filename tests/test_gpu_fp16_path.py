@@ -22,7 +22,7 @@ from helpers import make_gpu_net, make_problem, relu_pattern_of, upload
 
 pytestmark = pytest.mark.gpu
 
-TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16", "B200_TAIL_FWD", "B200_MID16")
+TOGGLES = ("B200_FWD16", "B200_TAIL", "B200_DW16", "B200_TAIL_FWD", "B200_MID16", "B200_PAIR", "B200_PDL", "B200_RING")
 
 
 def _eval(handle, dims, acts, w, X, T, prec, env=None, quantize=True, want_pattern=False):
@@ -256,3 +256,47 @@ def test_evaluation_is_bit_reproducible(handle, oracle, which, batch):
             ref_loss, ref_g = loss, g
         else:
             assert loss == ref_loss and np.array_equal(g, ref_g), rep
+
+
+@pytest.mark.parametrize("dims,acts", [([784, 128, 64, 10], ["relu", "relu", "linear"]), ([784, 128, 10], ["relu", "linear"])])
+@pytest.mark.parametrize("batch", [700, 5000])
+def test_cta_pair_forward_is_bit_identical_to_the_one_cta_form(handle, oracle, dims, acts, batch):
+    """cta_group::2 (two SMs share one M = 256 MMA, the weights split between them) runs the same MMA shapes per SM in the same
+    order as the one-CTA kernel: loss, gradient and outputs must agree bit for bit; so must the deeper X ring (B200_RING=1)"""
+    onet, w, X, T = problem8(oracle, dims, acts, batch)
+    base = _eval(handle, dims, acts, w, X, T, "tf32x3", env={"B200_PAIR": "0"})
+    for env in ({"B200_PAIR": "1"}, {"B200_PAIR": "0", "B200_RING": "3"}):
+        got = _eval(handle, dims, acts, w, X, T, "tf32x3", env=env)
+        assert got[0] == base[0], env
+        assert np.array_equal(got[1], base[1]), env
+        assert np.array_equal(got[2], base[2]), env
+    lo, go = onet.loss_grad(w, X, T)
+    assert abs(base[0] - lo) <= 2e-5 * abs(lo) and rel_l2(base[1], go) <= 2e-5
+
+
+def test_programmatic_dependent_launch_changes_no_result(handle, oracle):
+    """B200_PDL=0 (plain stream order) against the default (every kernel launched programmatically, griddepcontrol.wait at its
+    top): a 12-iteration L-BFGS run through the captured graph must produce the same losses and parameters bit for bit"""
+    dims, acts, batch, iters = [784, 128, 64, 10], ["relu", "relu", "linear"], 3000, 12
+    onet, w, X, T = problem8(oracle, dims, acts, batch)
+    dx, dt = upload(X), upload(T)
+    out = {}
+    saved = os.environ.get("B200_PDL")
+    try:
+        for pdl in ("1", "0"):
+            os.environ["B200_PDL"] = pdl
+            P.api.reload_env()
+            net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
+            s = P.CudaLBFGS(handle)
+            s.setMemory(10); s.setMaxIterations(iters); s.setTolerance(0.0)
+            rec = P.IterationRecorder(); rec.init(iters); s.setRecorder(rec)
+            s.solve(net.params_size(), net.params_data(), dx, dt, batch, net)
+            out[pdl] = (rec.copy_to_host()[0], net.get_params())
+    finally:
+        if saved is None:
+            os.environ.pop("B200_PDL", None)
+        else:
+            os.environ["B200_PDL"] = saved
+        P.api.reload_env()
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.array_equal(out["1"][1], out["0"][1])
