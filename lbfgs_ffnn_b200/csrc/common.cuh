@@ -68,6 +68,7 @@ struct EnvFlags {
   int pair = 1;                    // B200_PAIR: bit0 = layer-0 forward as CTA pairs (cta_group::2, weights split between the two SMs)
   bool pdl = true;                 // B200_PDL=0: plain stream order instead of programmatic dependent launches
   int dw_tail = 0;                 // B200_DW_TAIL=1: the one-tile last feature group of the fp16 dW kernel gets fewer, longer slices
+  int side = 1;                    // B200_SIDE=0: no side stream (every kernel of an evaluation in one stream)
   int ring = 0;                    // B200_RING: bit0 layer-0 forward, bit1 layer-0 dW: deeper X ring than weight / delta ring
   int diag = 0;                    // B200_DIAG: timing experiments of the fp16 kernels (parts switched off; results are wrong)
   int tc_mask = 7;                 // B200_TC_MASK: bit0 FWD, bit1 DX, bit2 DW on the tensor cores; bit3 / bit4 see gemm_tc.cu
@@ -155,6 +156,10 @@ struct b200_ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  // side stream for work off the critical path of an evaluation (the dW of a middle layer runs beside the dX / dW chain that
+  // follows it): forked from and joined to `stream` with the two events, also inside a stream capture
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // multi-GPU (one process per GPU)
   void *comm = nullptr; // ncclComm_t
   int rank = 0, world = 1;

@@ -49,6 +49,7 @@ void env_reload() {
   e.pair = num("B200_PAIR", 1);
   e.diag = num("B200_DIAG", 0);
   e.ring = num("B200_RING", 0);
+  e.side = num("B200_SIDE", 1);
   e.dw_tail = num("B200_DW_TAIL", 0);
   e.pdl = num("B200_PDL", 1) != 0;
   e.tc_mask = num("B200_TC_MASK", 7);
@@ -318,6 +319,9 @@ int b200_ctx_create(int device, b200_ctx **out) {
   memset(ctx->h_scalars, 0, sizeof(double) * kHostScalars);
   B200_CUDA(cudaMalloc(&ctx->d_scalars, sizeof(double) * 64));
   B200_CUDA(cudaMemset(ctx->d_scalars, 0, sizeof(double) * 64));
+  B200_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreate(&ctx->ev_a));
   B200_CUDA(cudaEventCreate(&ctx->ev_b));
   { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx.insert(ctx); }
@@ -340,6 +344,9 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     for (void *p : ctx->lbfgs_pool) ctx->lbfgs_pool_free(p);
   ctx->lbfgs_pool.clear();
   for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   cudaEventDestroy(ctx->ev_a);
   cudaEventDestroy(ctx->ev_b);
   cudaFreeHost(ctx->h_scalars);

@@ -763,10 +763,13 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
 
   // backward sweep
   bool d16_ready = use_dw16 && L == 2; // fp16 {hi | lo} delta_0 in net->delta16
+  bool side_pending = false;
   for (int l = L - 1; l >= 0; --l) {
     const int K = net->dims[l], N = net->dims[l + 1];
     const float *W = params + net->offs[l];
     const float *in = (l == 0) ? x : net->act[l - 1];
+    const bool side_dw1 = mid && l == 1 && env().side && ctx->side_stream && !ctx->prof.on;
+    if (side_dw1) B200_CUDA(cudaEventRecord(ctx->ev_fork, st)); // (before dX_1 is launched: dW_1 does not wait for it)
     if (l > 0 && !(l == L - 1 && (fused_last || tail_done))) { // delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
       char nm[16];
       snprintf(nm, sizeof(nm), "dx%d", l);
@@ -804,7 +807,19 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
       ProfScope ps(ctx, nm);
       bool done = false;
       if (mid && l == 1) {
-        B200_TRY(mid16_dw_layer1(net, batch));
+        if (side_dw1) {
+          // dW_1 needs A_1 and delta_1 only: it runs on the side stream, beside the dX_1 (launched first) -> dW_0 chain; its
+          // CTAs fill the SMs that chain leaves idle in its last rounds, and it is joined before the split-K combine
+          B200_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+          ctx->stream = ctx->side_stream;
+          const int rc = mid16_dw_layer1(net, batch);
+          ctx->stream = st;
+          B200_TRY(rc);
+          B200_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+          side_pending = true;
+        } else {
+          B200_TRY(mid16_dw_layer1(net, batch));
+        }
         done = true;
       }
       if (l == 0) net->dw0_tail_row0 = -1; // (set by dw16_layer when its last feature group has its own number of slices)
@@ -843,6 +858,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
     }
   }
 
+  if (side_pending) B200_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
   // split-K reduction straight into the caller's gradient buffer (+ L2 term, + ||g||^2 partials)
   FinParams fp{};
   fp.nl = 0;
