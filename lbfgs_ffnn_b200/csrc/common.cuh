@@ -275,6 +275,11 @@ __device__ __forceinline__ double sum8_pinned(double acc, float t0, float t1, fl
       : "d"(acc), "f"(t0), "f"(t1), "f"(t2), "f"(t3), "f"(t4), "f"(t5), "f"(t6), "f"(t7));
   return r;
 }
+__device__ __forceinline__ float4 ldcg4_pinned(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ double ldcg_pinned(const double *p) {
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   if (threadIdx.x == 0) {
     p.fin_part[2 * blockIdx.x + 0] = a;
     p.fin_part[2 * blockIdx.x + 1] = b;
-    if (p.sym_local) __threadfence_system(); else __threadfence();
+    __threadfence(); // (peer-memory form: the LAST CTA's system-scope fence below publishes what it has observed of the others)
     last = atomicAdd(p.done_count, 1u) == gridDim.x - 1;
   }
   __syncthreads();
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p
     unsigned long long polls = 0;
     while (*f < epoch + 1u) {
       __nanosleep(ns);
-      if (ns < 1024) ns <<= 1;
+      if (ns < 256) ns <<= 1; // (the wake-up granularity is part of the all-reduce latency)
       if (++polls > p.spin_limit) {
         if (p.host_err) { *p.host_err = 1.0; __threadfence_system(); }
         break;
@@ -245,13 +245,26 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const P2PReduceParams p
   }
   __syncthreads();
   const unsigned long long off = (epoch & 1u) * p.slot_bytes;
+  const char *peer[8]; // (the mapped peer buffers: loaded once, not once per element)
+#pragma unroll
+  for (int u = 0; u < 8; ++u) peer[u] = p.peers[u < p.world ? u : 0];
   const unsigned long long nv = (p.n + 3) / 4; // slots are padded to 64 floats: whole float4s are always readable
   double g2 = 0.0;
   for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (unsigned long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < p.world; ++r) {
-      const float4 x = __ldcg(reinterpret_cast<const float4 *>(p.peers[r] + off) + v);
-      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    if (p.world <= 8) { // the peer loads of a step go out together: ONE NVLink round trip, not one per rank (pinned: the compiler
+      float4 x[8];      // otherwise pairs every load with its add)
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u < p.world) x[u] = ldcg4_pinned(reinterpret_cast<const float4 *>(peer[u] + off) + v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (u < p.world) { acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w; } // rank order
+    } else {
+      for (int r = 0; r < p.world; ++r) {
+        const float4 x = __ldcg(reinterpret_cast<const float4 *>(p.peers[r] + off) + v);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
     }
     const unsigned long long j = 4 * v;
     if (j + 3 < p.n) {

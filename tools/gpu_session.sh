@@ -70,7 +70,7 @@ fi
 if has ncufull; then  # the top kernels once, full metric set (DRAM bytes, pipe utilisation, stall reasons)
   CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-reference-cuda"
   timeout 300 $CMD > $OUT/${TAG}_ncufull_plain.log 2>&1 && \
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"fwd16_kernel|dw16_kernel|lbfgs_direction_kernel|finalize_grad_kernel|tail_" -s 60 -c 14 -o $OUT/${TAG}_full $CMD > $OUT/${TAG}_ncufull.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"fwd16_kernel|dw16_kernel|lbfgs_direction_kernel|finalize_grad_kernel|tail_|prep_w16" -s 66 -c 16 -o $OUT/${TAG}_full $CMD > $OUT/${TAG}_ncufull.log 2>&1
   echo "ncufull rc=$?"; tail -3 $OUT/${TAG}_ncufull.log
 fi
 if has racecheck; then

@@ -31,17 +31,20 @@ for k, v in agg.items():
 json.dump(dict(command="ncu --set full --clock-control none --import-source on -k regex:... -s 60 -c 14 python bench.py --steps 5 --warmup 3 "
                        "--no-cpu-baseline --no-reference-cuda", note="cold-cache, serialised launches: compare shares, not absolutes",
                kernels=summary), open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.json"), "w"), indent=1)
-scope = {"fwd0": ("fwd16_kernel<128, 1, 1, 4>", ["gemm_fwd16.cu"]), "fwd1": ("fwd16_kernel<64, 1, 0, 4>", ["gemm_fwd16.cu"]),
-         "dx1": ("fwd16_kernel<128, 1, 2, 2>", ["gemm_fwd16.cu"]), "dw1": ("dw16_kernel<128, 1>", ["gemm_dw16.cu"]),
-         "dw0": ("dw16_kernel<256, 0>", ["gemm_dw16.cu"]), "tail_fwd": ("tail_fwd2_kernel<2, 10>", ["tail_layer.cu"]),
-         "tail_bwd": ("tail_bwd_kernel<2, 10, 1>", ["tail_layer.cu"]), "lbfgs_direction": ("lbfgs_direction_kernel<2, 1>", ["lbfgs_kernels.cu"]),
-         "finalize": ("finalize_grad_kernel", ["network.cu"])}
+# bench scope -> (prefix of the kernel's name in the capture, sources whose hash guards the figure)
+scope = {"fwd0": ("fwd16_kernel<128, 1, 1,", ["gemm_fwd16.cu"]), "fwd1": ("fwd16_kernel<64, 1, 0,", ["gemm_fwd16.cu"]),
+         "dx1": ("fwd16_kernel<128, 1, 2,", ["gemm_fwd16.cu"]), "dw1": ("dw16_kernel<128, 1,", ["gemm_dw16.cu"]),
+         "dw0": ("dw16_kernel<256, 0,", ["gemm_dw16.cu"]), "tail_fwd": ("tail_fwd2_kernel<2, 10", ["tail_layer.cu"]),
+         "tail_bwd": ("tail_bwd_kernel<2, 10, 1", ["tail_layer.cu"]), "lbfgs_direction": ("lbfgs_direction_kernel<2, 1", ["lbfgs_kernels.cu"]),
+         "finalize": ("finalize_grad_kernel", ["network.cu"]), "split16": ("prep_w16_kernel", ["gemm_fwd16.cu"])}
 sha = lambda rel: hashlib.sha1(open(os.path.join(ROOT, rel), "rb").read()).hexdigest()[:12]
 traffic = dict(workload="lbfgs_m10_mlp784-128-64-10_B60000_fullbatch", precision="tf32x3", capture=f"profiles/{tag}_ncu_full_summary.json (ncu --set full, B200)",
                dram_bytes_per_launch={}, sources={})
-for s, (k, files) in scope.items():
-    if k in summary:
+out_name = sys.argv[3] if len(sys.argv) > 3 else "r02_traffic.json"
+for s, (pref, files) in scope.items():
+    k = next((name for name in summary if name.startswith(pref)), None)
+    if k:
         traffic["dram_bytes_per_launch"][s] = summary[k]["dram_bytes"]
         traffic["sources"][s] = [[f"lbfgs_ffnn_b200/csrc/{f}", sha(f"lbfgs_ffnn_b200/csrc/{f}")] for f in files]
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w"), indent=1)
+json.dump(traffic, open(os.path.join(ROOT, "profiles", out_name), "w"), indent=1)
 print(json.dumps(summary, indent=1))
