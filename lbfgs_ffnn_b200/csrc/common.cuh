@@ -68,6 +68,7 @@ struct EnvFlags {
   int pair = 1;                    // B200_PAIR: bit0 = layer-0 forward as CTA pairs (cta_group::2, weights split between the two SMs)
   bool pdl = true;                 // B200_PDL=0: plain stream order instead of programmatic dependent launches
   int dw_tail = 0;                 // B200_DW_TAIL=1: the one-tile last feature group of the fp16 dW kernel gets fewer, longer slices
+  int prep_pub = 1;                // B200_PREP_PUB=0: every CTA of the layer-1 forward job recomputes the 128 feature scales from W_0
   int side = 1;                    // B200_SIDE=0: no side stream (every kernel of an evaluation in one stream)
   int ring = 0;                    // B200_RING: bit0 layer-0 forward, bit1 layer-0 dW: deeper X ring than weight / delta ring
   int diag = 0;                    // B200_DIAG: timing experiments of the fp16 kernels (parts switched off; results are wrong)
@@ -275,6 +276,17 @@ __device__ __forceinline__ double sum8_pinned(double acc, float t0, float t1, fl
       : "d"(acc), "f"(t0), "f"(t1), "f"(t2), "f"(t3), "f"(t4), "f"(t5), "f"(t6), "f"(t7));
   return r;
 }
+__device__ __forceinline__ float4 ldg4_pinned(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// Every use of t[0..15] below this point depends on it, and it depends on all sixteen values: the loads that produce them are
+// issued first, whatever arithmetic follows (no instruction is emitted).
+#define B200_PIN16_C(t, c)                                                                                                       \
+  asm volatile("" : "+f"(t[0].c), "+f"(t[1].c), "+f"(t[2].c), "+f"(t[3].c), "+f"(t[4].c), "+f"(t[5].c), "+f"(t[6].c), "+f"(t[7].c), \
+                    "+f"(t[8].c), "+f"(t[9].c), "+f"(t[10].c), "+f"(t[11].c), "+f"(t[12].c), "+f"(t[13].c), "+f"(t[14].c), "+f"(t[15].c))
+#define B200_PIN16_F4(t) do { B200_PIN16_C(t, x); B200_PIN16_C(t, y); B200_PIN16_C(t, z); B200_PIN16_C(t, w); } while (0)
 __device__ __forceinline__ float4 ldcg4_pinned(const float4 *p) {
   float4 v;
   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));

@@ -50,6 +50,7 @@ void env_reload() {
   e.diag = num("B200_DIAG", 0);
   e.ring = num("B200_RING", 0);
   e.side = num("B200_SIDE", 1);
+  e.prep_pub = num("B200_PREP_PUB", 1);
   e.dw_tail = num("B200_DW_TAIL", 0);
   e.pdl = num("B200_PDL", 1) != 0;
   e.tc_mask = num("B200_TC_MASK", 7);

@@ -504,15 +504,22 @@ struct PrepJob {
   // activations, whose per-feature scale t_k comes from the bound sum_r |Wp(r, k)| + |bp_k| over that layer's weights Wp
   // ([rs_R][128], k contiguous; inputs in [0, 1]) — mode 1 — or is 1 for a bounded activation (mode 2). Every CTA of the job
   // computes all 128 scales with the same arithmetic (identical results); the first one publishes t_k and 1 / t_k.
+  // Mode 3 (default when the launch also prepares that previous layer, job 0): the job-0 CTAs, which hold the previous layer's
+  // weights in registers anyway, publish t_k and 1 / t_k of their 8 neurons (pub_*) and count themselves in sync[0]; the CTAs of
+  // this job fetch their own weights, wait for the count (all CTAs of the launch are co-resident: at most ~45 of 1024 threads)
+  // and read the 128 scales — instead of every CTA re-reading all of W_0 (401 KB through one SM's L2 port: ~8 us of a 17 us kernel).
   int rs_mode;
   const float *rs_W, *rs_bias;
   int rs_R;
   float *rs_tscale, *rs_tinv;
+  float *pub_tscale, *pub_tinv; // job 0 as the publisher (nullptr: not)
+  const float *pub_bias;
   int nblocks;          // CTAs of this job
 };
+// sync: {publishers that have finished, CTAs of the jobs that have finished}; the last CTA to finish zeroes both
 __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ PrepJob j0, const __grid_constant__ PrepJob j1,
                                                       const __grid_constant__ PrepJob j2, const SpecState *spec_st, int spec,
-                                                      const __grid_constant__ ChainW chain) {
+                                                      const __grid_constant__ ChainW chain, unsigned *sync) {
   pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return;
   __shared__ float red[128][kSplitNeurons + 1];
@@ -527,7 +534,23 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
   const int o = threadIdx.x & (kSplitNeurons - 1), kq = threadIdx.x / kSplitNeurons;
   const int o0 = ((int)blockIdx.x - (which == 0 ? 0 : (which == 1 ? j0.nblocks : j0.nblocks + j1.nblocks))) * kSplitNeurons;
   const bool ok = o0 + o < j.Nn;
-  if (j.rs_mode) { // block-uniform
+  float v[kSplitMaxK / 128]; // this thread's weights: in flight while the scales below are computed / waited for
+#pragma unroll
+  for (int i = 0; i < kSplitMaxK / 128; ++i) {
+    const int k = kq + 128 * i;
+    v[i] = (ok && k < j.R) ? __ldg(j.W + (size_t)k * j.sr + (size_t)(o0 + o) * j.sn) : 0.0f;
+  }
+  if (j.rs_mode == 3) { // block-uniform: the scales come from the job-0 CTAs of this launch
+    if (threadIdx.x == 0) {
+      const volatile unsigned *c = sync;
+      unsigned long long polls = 0;
+      while (*c < (unsigned)j0.nblocks && ++polls < (1ull << 22)) __nanosleep(64); // (bounded: never hang the device)
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) rs_sh[threadIdx.x] = __ldcg(j.rs_tinv + threadIdx.x);
+    __syncthreads();
+  } else if (j.rs_mode) { // block-uniform
     // 32 slices of the contraction index x 32 groups of four features: every thread's (<= 32) 16-byte loads are in flight in
     // two batches, the partial sums meet in shared memory (the split tiles' space, not yet in use)
     float *part = reinterpret_cast<float *>(&th[0][0]); // [32 slices][128 features]
@@ -538,12 +561,20 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
     if (j.rs_mode == 1) {
       for (int r0 = slice; r0 < j.rs_R; r0 += 32 * 16) {
         float4 t[16];
+        if (w_vec) { // sixteen 16-byte loads in flight (pinned: the compiler otherwise pairs each load with its add, one L2 round
+                     // trip per row; rows past the end re-read the last row and are masked out)
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-          t[u] = (r0 + 32 * u >= j.rs_R) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                 : w_vec ? __ldg(reinterpret_cast<const float4 *>(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4))
-                         : make_float4(__ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4), __ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4 + 1),
-                                       __ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4 + 2), __ldg(j.rs_W + (size_t)(r0 + 32 * u) * 128 + k4 + 3));
+          for (int u = 0; u < 16; ++u) t[u] = ldg4_pinned(reinterpret_cast<const float4 *>(j.rs_W + (size_t)min(r0 + 32 * u, j.rs_R - 1) * 128 + k4));
+          B200_PIN16_F4(t);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) if (r0 + 32 * u >= j.rs_R) t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float *q = j.rs_W + (size_t)min(r0 + 32 * u, j.rs_R - 1) * 128 + k4;
+            t[u] = (r0 + 32 * u >= j.rs_R) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 16; ++u) { a4.x += fabsf(t[u].x); a4.y += fabsf(t[u].y); a4.z += fabsf(t[u].z); a4.w += fabsf(t[u].w); }
       }
@@ -567,19 +598,21 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
     }
     __syncthreads();
   }
-  float v[kSplitMaxK / 128];
   float amax = 0.0f;
-#pragma unroll
-  for (int i = 0; i < kSplitMaxK / 128; ++i) {
-    const int k = kq + 128 * i;
-    v[i] = (ok && k < j.R) ? __ldg(j.W + (size_t)k * j.sr + (size_t)(o0 + o) * j.sn) : 0.0f;
-  }
 #pragma unroll
   for (int i = 0; i < kSplitMaxK / 128; ++i) {
     if (j.rs_mode) { const int k = kq + 128 * i; v[i] *= (k < 128) ? rs_sh[k] : 0.0f; } // (R <= 128 on this path)
     amax = fmaxf(amax, fabsf(v[i]));
   }
   red[kq][o] = amax;
+  __shared__ float reds[128][kSplitNeurons + 1], red2s[8][kSplitNeurons];
+  const bool publish = which == 0 && j.pub_tscale != nullptr; // block-uniform
+  if (publish) {
+    float asum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kSplitMaxK / 128; ++i) asum += fabsf(v[i]);
+    reds[kq][o] = asum;
+  }
   __syncthreads();
   // max over the 128 slices of each of the 8 rows: 256 threads take four slices each, shuffles combine the four parts a warp
   // holds per row, the eight warps meet in shared memory (a 128-step serial scan per row cost ~2 us of a ~8 us kernel)
@@ -590,6 +623,12 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
     if ((threadIdx.x & 31) < kSplitNeurons) red2[threadIdx.x >> 5][oo] = m;
+    if (publish) {
+      float a = (reds[4 * part][oo] + reds[4 * part + 1][oo]) + (reds[4 * part + 2][oo] + reds[4 * part + 3][oo]);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if ((threadIdx.x & 31) < kSplitNeurons) red2s[threadIdx.x >> 5][oo] = a;
+    }
   }
   __syncthreads();
   if (threadIdx.x < kSplitNeurons) {
@@ -602,8 +641,23 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
     sc[threadIdx.x] = ldexpf(1.0f, 14 - e);      // s * m in [2^13, 2^14)
     const int n = o0 + threadIdx.x;
     if (n < j.Nn) j.colscale[n] = j.pre * ldexpf(1.0f, e - 14);
+    if (publish && n < j.Nn) { // t_n of this layer's output n (the next layer's input feature): bound sum_k |W(k, n)| + |b_n|
+      float b1 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b1 += red2s[i][threadIdx.x];
+      const float bound = b1 * 1.0001f + fabsf(__ldg(j.pub_bias + n)) + 1e-30f; // (fp32 summation slack)
+      int eb = 0;
+      frexpf(bound, &eb);
+      eb = max(-100, min(100, eb));
+      j.pub_tscale[n] = ldexpf(1.0f, 14 - eb);
+      j.pub_tinv[n] = ldexpf(1.0f, eb - 14);
+    }
   }
   __syncthreads();
+  if (publish && threadIdx.x == 0) { // (the barrier above ordered the eight writers before this thread)
+    __threadfence();
+    atomicAdd(sync, 1u);
+  }
   const float s = sc[o];
 #pragma unroll
   for (int i = 0; i < kSplitMaxK / 128; ++i) {
@@ -625,6 +679,17 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
     if (o0 + oo < j.Nn) {
       *reinterpret_cast<uint4 *>(j.wh + (size_t)(o0 + oo) * j.ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&th[oo][8 * kv]);
       *reinterpret_cast<uint4 *>(j.wl + (size_t)(o0 + oo) * j.ldk + 8 * kv) = *reinterpret_cast<const uint4 *>(&tl[oo][8 * kv]);
+    }
+  }
+  if (sync) { // the last CTA of the jobs to finish re-arms the two counters for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(sync + 1, 1u) == (unsigned)(j0.nblocks + j1.nblocks + j2.nblocks) - 1u) {
+        sync[0] = 0u;
+        sync[1] = 0u;
+        __threadfence();
+      }
     }
   }
 }
@@ -784,6 +849,8 @@ int mid16_ensure(b200_net *net, long batch) {
     B200_CUDA(cudaMalloc(&m.wdh, sizeof(__half) * (size_t)N0 * 2 * N1));
     B200_CUDA(cudaMalloc(&m.wdl, sizeof(__half) * (size_t)N0 * 2 * N1));
     B200_CUDA(cudaMalloc(&m.db_part, sizeof(float) * (size_t)2 * net->ctx->num_sms * N1));
+    B200_CUDA(cudaMalloc(&m.prep_sync, sizeof(unsigned) * 2));
+    B200_CUDA(cudaMemset(m.prep_sync, 0, sizeof(unsigned) * 2));
     ++net->config_gen;
   }
   if (m.a16_rows < net->cap || m.d16_rows < net->cap) {
@@ -801,7 +868,7 @@ int mid16_ensure(b200_net *net, long batch) {
 
 void mid16_release(b200_net *net) {
   b200_net::Mid16 &m = net->m16;
-  for (void *p : {(void *)m.tscale, m.wfh, m.wfl, m.wdh, m.wdl, (void *)m.db_part, m.a16, m.d16})
+  for (void *p : {(void *)m.tscale, m.wfh, m.wfl, m.wdh, m.wdl, (void *)m.db_part, m.a16, m.d16, (void *)m.prep_sync})
     if (p) cudaFree(p);
   m = b200_net::Mid16{};
 }
@@ -842,6 +909,7 @@ int fwd16_prepare(b200_net *net, const float *params) {
   j0.wh = (__half *)net->w16h; j0.wl = (__half *)net->w16l; j0.colscale = net->colscale;
   j0.nblocks = ceil_div(N, kSplitNeurons);
   PrepJob j1{}, j2{}; // (no CTAs)
+  unsigned *sync = nullptr;
   if (net->m16.on) {
     b200_net::Mid16 &m = net->m16;
     const int N1 = net->dims[2];
@@ -856,11 +924,19 @@ int fwd16_prepare(b200_net *net, const float *params) {
     j2.rs_mode = (net->acts[0] == B200_ACT_TANH || net->acts[0] == B200_ACT_SIGMOID) ? 2 : 1;
     j2.rs_W = W0; j2.rs_bias = W0 + (size_t)K * N; j2.rs_R = K; j2.rs_tscale = m.tscale; j2.rs_tinv = m.tinv;
     j2.nblocks = ceil_div(N1, kSplitNeurons);
+    if (j2.rs_mode == 1 && env().prep_pub) { // job 0 (the CTAs that hold W_0 anyway) publishes the scales, job 2 waits for them
+      j0.pub_tscale = m.tscale; j0.pub_tinv = m.tinv; j0.pub_bias = j2.rs_bias;
+      j2.rs_mode = 3;
+      sync = m.prep_sync;
+    }
   }
+  if (env().diag & 32) { j1.nblocks = 0; j2.nblocks = 0; }  // (timing experiments: results are wrong)
+  if (env().diag & 64) { j2.rs_mode = 0; j0.pub_tscale = nullptr; sync = nullptr; }
+  if (env().diag & 128) chain.nl = 0;
   {
     ProfScope ps(net->ctx, "split16");
     B200_LAUNCH(prep_w16_kernel, j0.nblocks + j1.nblocks + j2.nblocks + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, j0,
-                j1, j2, net->spec_st, net->spec_flag, chain);
+                j1, j2, net->spec_st, net->spec_flag, chain, sync);
   }
   net->w16_params = params;
   return B200_OK;

@@ -9,6 +9,15 @@ namespace b200 {
 
 namespace {
 
+// a / b in double without the ~40-instruction IEEE division routine on the kernel's serial path: fp32 reciprocal refined by
+// two Newton steps (relative error ~1e-16, not correctly rounded; b normal and finite)
+__device__ __forceinline__ double div_fast(double a, double b) {
+  double r = (double)(1.0f / (float)b);
+  r = fma(fma(-b, r, 1.0), r, r);
+  r = fma(fma(-b, r, 1.0), r, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q); // one correction of the quotient
+}
 __device__ __forceinline__ int ring_phys(int head, int count, int mod, int logical) {
   int start = (head - count) % mod; // src/cuda/lbfgs.cuh:225-230
   if (start < 0) start += mod;
@@ -323,7 +332,7 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
       // S-LBFGS: |y^T s| > 1e-10 (src/minimizer/s_lbfgs.hpp:253-258)
       const bool accept = a.force_accept ? true : (a.policy == POLICY_SLBFGS ? fabs(ys) > 1e-10 : ys > 1e-10);
       if (accept) {
-        const double r = a.force_accept ? a.ext_rho : 1.0 / ys;
+        const double r = a.force_accept ? a.ext_rho : ((fabs(ys) > 1e-30 && fabs(ys) < 1e30) ? div_fast(1.0, ys) : 1.0 / ys);
         if (stage || leader) rhop[w] = r;
         if (wr_global) a.st.rho[w] = r;
         head = (head + 1) % mod;
@@ -381,10 +390,12 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
       if (dbg && lane == 0) dbg[5] = clock64() - td2;
       const int pl = physp[k - 1];
       const double ys = SYp[pl * mp + pl], yy = YYp[pl * mp + pl];
-      if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ys / yy : 1.0; // src/cuda/lbfgs.cuh:244-247
-      else if (a.policy == POLICY_WOLFE) gamma = ys / yy;                 // src/minimizer/lbfgs.hpp:124-125
-      else {                                                              // src/minimizer/s_lbfgs.hpp:116-124
-        gamma = (fabs(yy) < 1e-12) ? 1.0 : ys / yy;
+      const bool yy_ok = fabs(yy) > 1e-30 && fabs(yy) < 1e30; // (float range of the seed reciprocal; else the IEEE routine)
+      const double ratio = yy_ok ? div_fast(ys, yy) : ys / yy;
+      if (a.policy == POLICY_ARMIJO) gamma = (yy > 0.0) ? ratio : 1.0; // src/cuda/lbfgs.cuh:244-247
+      else if (a.policy == POLICY_WOLFE) gamma = ratio;                 // src/minimizer/lbfgs.hpp:124-125
+      else {                                                            // src/minimizer/s_lbfgs.hpp:116-124
+        gamma = (fabs(yy) < 1e-12) ? 1.0 : ratio;
         gamma = fmin(fmax(gamma, 1e-6), 1e6);
       }
       // sum_j alpha_j y_i.y_j: no dependence on the second recurrence; four partial sums keep the FMA chain short
@@ -471,8 +482,8 @@ __device__ __forceinline__ void solve_body(const SolveArgs &a, double *sh, bool 
       // The CPU backend has no such check (src/minimizer/lbfgs.hpp:56-65).
       const bool sd = a.policy == POLICY_ARMIJO && kk > 0 && !(gdotp < 0.0);
       if (sd) { kk = 0; cg = -1.0; gdotp = -gg; gamma = 1.0; }
-      const double gn = sqrt(gg);
-      const double alpha0 = a.first_iter ? fmin(1.0, 1.0 / gn) : 1.0; // lbfgs.cuh:108, lbfgs.hpp:60-61
+      double alpha0 = 1.0; // lbfgs.cuh:108, lbfgs.hpp:60-61
+      if (a.first_iter) alpha0 = fmin(1.0, 1.0 / sqrt(gg)); // (the square root and the division only where they are used)
       if (leader) {
         if (sd) { h->head = 0; h->count = 0; h->flags |= FLAG_SD_FALLBACK; }
         h->k = kk; h->cg = cg; h->gdotp = gdotp; h->gamma = gamma;

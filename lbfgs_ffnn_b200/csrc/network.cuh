@@ -90,6 +90,7 @@ struct b200_net {
     void *a16 = nullptr;    // A_1 pair
     long a16_rows = 0;
     float *tscale = nullptr, *tinv = nullptr; // [dims[1]]: t_f and 1 / t_f
+    unsigned *prep_sync = nullptr;            // two counters of prep_w16_kernel (publishers done, CTAs done)
     void *wfh = nullptr, *wfl = nullptr;      // forward operand of layer 1: [dims[2]][2 dims[1]] hi / lo of s_o W_1[k][o] / t_k
     float *colscale_f = nullptr;              // [dims[2]]: 1 / s_o
     void *wdh = nullptr, *wdl = nullptr;      // dX operand of layer 1: [dims[1]][2 dims[2]] hi / lo of s_k W_1[k][o]
