@@ -46,6 +46,8 @@ void env_reload() {
   e.tail = num("B200_TAIL", -1);
   e.tail_fwd = num("B200_TAIL_FWD", -1);
   e.mid16 = num("B200_MID16", -1);
+  e.wide16 = num("B200_WIDE16", 1);
+  e.wide_chunk = num("B200_WIDE_CHUNK", 0);
   e.pair = num("B200_PAIR", 1);
   e.diag = num("B200_DIAG", 0);
   e.ring = num("B200_RING", 0);

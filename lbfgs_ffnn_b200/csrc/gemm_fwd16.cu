@@ -44,7 +44,9 @@ constexpr int kConvBytes = kFM * kFK * 2;  // X tile: 16 KB
 // ring, which comes from HBM, is made deeper than the ring of the weights, which come from L2, and each gets its own commit)
 enum { EPI_F32 = 0,     // activations as fp32 rows (layer 0 of a two-layer net, layer 1 of a three-layer net)
        EPI_EMIT16 = 1,  // activations ONLY as the per-feature-scaled fp16 pair, block-major (b200_net::Mid16::a16)
-       EPI_DX = 2 };    // dX role: A = delta pair, B = W^T; epilogue: * act'(A_prev) from the pair, emits delta_prev's fp16 pair
+       EPI_DX = 2,      // dX role: A = delta pair, B = W^T; epilogue: * act'(A_prev) from the pair, emits delta_prev's fp16 pair
+       EPI_WIDE = 3 };  // wide layers (WIDE form below): fp32 rows out; forward (bias, activation), dX (* act'(A_prev) read as fp32)
+                        // or plain (dW) by the run-time fields of F16Params
 constexpr int kFThreads = 384;            // warps 0-3: X TMA, MMA issue, TMEM alloc, weight TMA; warps 4-11: epilogue
 constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
 constexpr int kStageOutBytes = 32 * 128;      // per epilogue warp: one [32 rows][32 floats] TMA-store box
@@ -68,6 +70,13 @@ struct F16Params {
   // EPI_DX
   const float *scale_in_inv; // device scalar: 1 / scale of the A operand (delta pair)
   const float *scale_out;    // device scalar: scale of the emitted pair
+  // WIDE
+  int n_tiles;               // tiles of BN output columns (units = sample-tile pairs x n_tiles, n fastest)
+  int k_chunk;               // K blocks accumulated in TMEM before the epilogue warps add them to their fp32 registers
+  const float *sa_inv, *sb_inv; // device scalars: 1 / scale of the A pair, 1 / scale of the B pair
+  const float *aux32;        // dX: A_prev as fp32 rows (act' is taken from it), else nullptr
+  long ld_aux;
+  int ones_row;              // row of the A operand that holds unscaled ones (the bias-gradient row of a dW), or -1
 };
 
 // PAIR: two CTAs of a cluster work as ONE tcgen05 cta_group::2 unit on two neighbouring sample tiles (M = 256). The B operand
@@ -75,11 +84,16 @@ struct F16Params {
 // of X + 16 KB of weights instead of 16 + 32: the weight re-stream out of L2 (2/3 of this kernel's L2 -> SM bytes, the path that
 // bounds it: profiles/r02_*) is halved. Same MMA shapes per SM and the same accumulation order, so the results are bit-identical
 // to the one-CTA form.
-template <int BN, bool X2, int EPI, int NS, bool PAIR = false, int NW = NS> struct FPlan {
+// WIDE (layers with hundreds of output columns, gemm "wide16" entry points at the end of this file): units are (pair of sample
+// tiles, tile of BN output columns); the A operand is a pair too, and BOTH its tiles of a K block (hi, lo) sit in one stage and
+// meet the same weight stage (two MMAs per K step), so a K block of 64 costs an SM 32 KB of A + 16 KB of B out of L2.
+template <int BN, bool X2, int EPI, int NS, bool PAIR = false, int NW = NS, bool WIDE = false> struct FPlan {
   static_assert(!PAIR || X2, "the pair form splits [W_hi; W_lo] between the two CTAs");
+  static_assert(!WIDE || (PAIR && X2 && BN == 128 && NW == NS && EPI == EPI_WIDE), "the wide form is a CTA-pair kernel");
+  static constexpr int kXStage = kConvBytes * (WIDE ? 2 : 1);
   static constexpr int kWStage = BN * 128 * ((X2 && !PAIR) ? 2 : 1);
   static constexpr int kOffConv = 0;
-  static constexpr int kOffW = NS * kConvBytes;
+  static constexpr int kOffW = NS * kXStage;
   static constexpr int kOffOut = kOffW + NW * kWStage; // epilogue staging tiles (TMA store), 1024-byte aligned
   static constexpr int kAuxTile = (BN / 64) * kConvBytes; // EPI_DX: hi blocks of the previous layer's activation pair, [128 rows][64] each
   static constexpr int kOffAux = kOffOut + 8 * kStageOutBytes;
@@ -140,26 +154,29 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BN, bool X2, int EPI, int NS, bool PAIR, int NW>
+template <int BN, bool X2, int EPI, int NS, bool PAIR, int NW, bool WIDE>
 __global__ void __launch_bounds__(kFThreads, 1)
 fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
              const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmOut,
              const __grid_constant__ CUtensorMap tmAux, const F16Params p) {
   pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(p.spec_st, p.spec)) return; // before any barrier / TMEM allocation (both CTAs of a pair read the same flag)
-  using Plan = FPlan<BN, X2, EPI, NS, PAIR, NW>;
-  // work units: sample tiles (one CTA) or pairs of neighbouring sample tiles (a CTA pair: rank r takes tile 2 * unit + r)
+  using Plan = FPlan<BN, X2, EPI, NS, PAIR, NW, WIDE>;
+  // work units: sample tiles (one CTA) or pairs of neighbouring sample tiles (a CTA pair: rank r takes tile 2 * unit + r);
+  // WIDE: (pair of sample tiles, tile of BN output columns), the column tile running fastest
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int units = PAIR ? (p.tiles + 1) >> 1 : p.tiles;
-  auto tile_of = [&](int unit) { return PAIR ? 2 * unit + (int)rank : unit; };
+  const int n_tiles = WIDE ? p.n_tiles : 1;
+  const int units = (PAIR ? (p.tiles + 1) >> 1 : p.tiles) * n_tiles;
+  auto tile_of = [&](int unit) { return WIDE ? 2 * (unit / n_tiles) + (int)rank : (PAIR ? 2 * unit + (int)rank : unit); };
+  auto nt_of = [&](int unit) { return WIDE ? unit % n_tiles : 0; };
   constexpr int kNC = NS, kNW = NW;
   static_assert(2 * kNC + 2 * kNW + 9 <= 64, "barrier table");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
-  auto conv_a = [&](int s) { return base + Plan::kOffConv + s * kConvBytes; };
+  auto conv_a = [&](int s) { return base + Plan::kOffConv + s * Plan::kXStage; };
   auto w_a = [&](int s, int lo) { return base + Plan::kOffW + s * Plan::kWStage + lo * (BN * 128); };
   const uint32_t bars = base + Plan::kOffBar;
   auto conv_full = [&](int s) { return bars + 8 * (s); };
@@ -205,6 +222,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     }
   }
   float *colsc = reinterpret_cast<float *>(bp + Plan::kOffCol), *biass = colsc + 128;
+  if constexpr (!WIDE)
   for (int i = threadIdx.x; i < 128; i += kFThreads) {
     // EMIT16 (ReLU / Linear only): t_f act(z) = act(t_f z) for t_f > 0, so the pair's scale is folded into colscale and bias
     const float t = (EPI == EPI_EMIT16 && i < p.cols_valid) ? __ldg(p.tscale + i) : 1.0f;
@@ -216,7 +234,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int umma_n = min(BN, (p.cols_valid + 31) & ~31);
+  const int umma_n = WIDE ? BN : min(BN, (p.cols_valid + 31) & ~31);
 
   if (warp == 0) {
     { // ===== X producer: fp16 rows straight from HBM into the K-major SWIZZLE_128B operand tile (whole warp in the loop, one
@@ -240,7 +258,11 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           mbar_wait(conv_empty(s), ph ^ 1);
           if (elect_one()) {
             if (p.diag & 1) { if (leader) mbar_arrive(conv_full(s)); }
-            else if constexpr (PAIR) { // both CTAs' tiles are counted on the leader's barrier
+            else if constexpr (WIDE) { // the hi and the lo tile of this K block, of both CTAs, counted on the leader's barrier
+              if (leader) mbar_expect_tx(conv_full(s), 4 * kConvBytes);
+              tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, kb, p.row0 + tile * kFM);
+              tma_load_3d_pair(conv_a(s) + kConvBytes, &tmX, conv_full(s) + lead_off, 0, p.k_blocks + kb, p.row0 + tile * kFM);
+            } else if constexpr (PAIR) { // both CTAs' tiles are counted on the leader's barrier
               if (leader) mbar_expect_tx(conv_full(s), 2 * kConvBytes);
               if (p.x_block_first) tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, kb, p.row0 + tile * kFM);
               else tma_load_3d_pair(conv_a(s), &tmX, conv_full(s) + lead_off, 0, p.row0 + tile * kFM, kb);
@@ -261,11 +283,15 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       for (int unit = unit0; unit < units; unit += unit_step) {
+        const int wrow0 = nt_of(unit) * BN; // (WIDE: the rows of the B operand of this unit's column tile)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(w_empty(s), ph ^ 1);
           if (elect_one()) {
             if (p.diag & 2) { if (leader) mbar_arrive(w_full(s)); }
-            else if constexpr (PAIR) { // this CTA's half of B = [W_hi; W_lo]: rows 0 .. BN-1 (hi) in the leader, BN .. 2 BN-1 (lo) in the peer
+            else if constexpr (WIDE) { // the leader stages B_hi, the peer B_lo: [B_hi; B_lo] is the N = 256 operand of the pair
+              if (leader) mbar_expect_tx(w_full(s), 2 * Plan::kWStage);
+              tma_load_2d_pair(w_a(s, 0), leader ? &tmWh : &tmWl, w_full(s) + lead_off, kb * kFK, wrow0);
+            } else if constexpr (PAIR) { // this CTA's half of B = [W_hi; W_lo]: rows 0 .. BN-1 (hi) in the leader, BN .. 2 BN-1 (lo) in the peer
               if (leader) mbar_expect_tx(w_full(s), 2 * Plan::kWStage);
               tma_load_2d_pair(w_a(s, 0), leader ? &tmWh : &tmWl, w_full(s) + lead_off, kb * kFK, 0);
             } else {
@@ -291,6 +317,47 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       int cs = 0, ws = 0, it = 0;
       uint32_t cph = 0, wph = 0;
       long long waited = 0, waited_w = 0, waited_tm = 0, t_mma = 0, t_commit = 0;
+      if constexpr (WIDE) {
+        // The tensor core's fp32 accumulate truncates (a bias of ~3e-8 of the accumulator per accumulating MMA): the contraction
+        // is cut into chunks of p.k_chunk K blocks, each chunk accumulated from zero in one of the two TMEM buffers and added to
+        // fp32 registers (round to nearest) by the epilogue warps while the next chunk runs in the other buffer.
+        int cnt = 0;
+        for (int unit = unit0; unit < units; unit += unit_step) {
+          for (int kb0 = 0; kb0 < p.k_blocks; kb0 += p.k_chunk, ++cnt) {
+            const int buf = cnt & 1;
+            const uint32_t d_acc = tmem_base + (uint32_t)(buf * 2 * BN);
+            const long long tt0 = p.dbg ? clock64() : 0;
+            mbar_wait(tm_empty(buf), ((cnt >> 1) & 1) ^ 1);
+            if (p.dbg) waited_tm += clock64() - tt0;
+            tc_fence_after();
+            const int kb1 = min(p.k_blocks, kb0 + p.k_chunk);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              const long long t0 = p.dbg ? clock64() : 0;
+              mbar_wait(conv_full(cs), cph);
+              const long long t0b = p.dbg ? clock64() : 0;
+              mbar_wait(w_full(ws), wph);
+              if (p.dbg) { const long long t1 = clock64(); waited += t0b - t0; waited_w += t1 - t0b; }
+              tc_fence_after();
+              const uint64_t da = dA0 + (uint64_t)(cs * (Plan::kXStage >> 4)), db = dB0 + (uint64_t)(ws * (Plan::kWStage >> 4));
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < kFK / 16; ++ks) {
+                  umma_f16<PAIR>(d_acc, da + 2 * ks, db + 2 * ks, idesc, (kb > kb0 || ks > 0) ? 1u : 0u); // A_hi x [B_hi; B_lo]
+                  umma_f16<PAIR>(d_acc, da + (kConvBytes >> 4) + 2 * ks, db + 2 * ks, idesc, 1u);          // A_lo x [B_hi; B_lo]
+                }
+                umma_commit_pair(conv_empty(cs)); // frees the stage (A and B tiles) in both CTAs
+              }
+              __syncwarp();
+              if (++cs == kNC) { cs = 0; cph ^= 1; }
+              if (++ws == kNW) { ws = 0; wph ^= 1; }
+            }
+            if (elect_one()) umma_commit_pair(tm_full(buf));
+            __syncwarp();
+          }
+        }
+        if (p.dbg && lane == 0) { p.dbg[8 * blockIdx.x + 3] = waited; p.dbg[8 * blockIdx.x + 4] = waited_w; p.dbg[8 * blockIdx.x + 5] = waited_tm; }
+      }
+      if constexpr (!WIDE)
       for (int unit = unit0; unit < units; unit += unit_step, ++it) {
         const int buf = it & 1;
         const uint32_t d_acc = tmem_base + (uint32_t)(buf * 2 * BN);
@@ -308,7 +375,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           if (p.dbg) { waited += t0b - t0; waited_w += t1 - t0b; }
           tc_fence_after();
           const int nks = (p.diag & 4) ? 0 : min(kFK / 16, (p.k_total - kb * kFK + 15) / 16);
-          const uint64_t da = dA0 + (uint64_t)(cs * (kConvBytes >> 4)), db = dB0 + (uint64_t)(ws * (Plan::kWStage >> 4));
+          const uint64_t da = dA0 + (uint64_t)(cs * (Plan::kXStage >> 4)), db = dB0 + (uint64_t)(ws * (Plan::kWStage >> 4));
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < kFK / 16; ++ks)
@@ -349,6 +416,73 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       uint8_t *stage_p = bp + Plan::kOffOut + (warp - kEpiWarp0) * kStageOutBytes;
       long long busy = 0, waiting = 0;
       int it = 0;
+      if constexpr (WIDE) {
+        int cnt = 0;
+        for (int unit = unit0; unit < units; unit += unit_step) {
+          const int tile = tile_of(unit);
+          float accr[BN / 64][32]; // this thread's row of the tile, its BN / 64 chunks of 32 columns, summed over the K chunks in RN fp32
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accr[i][j] = 0.0f;
+          for (int kb0 = 0; kb0 < p.k_blocks; kb0 += p.k_chunk, ++cnt) {
+            const int buf = cnt & 1;
+            const long long t0 = p.dbg ? clock64() : 0;
+            mbar_wait(tm_full(buf), (cnt >> 1) & 1);
+            if (p.dbg) waiting += clock64() - t0;
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) {
+              const int c0 = half * 32 + 64 * i;
+              uint32_t v[32], w[32];
+              tmem_ld32_nowait(lane_addr + c0, v);
+              tmem_ld32_nowait(lane_addr + BN + c0, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accr[i][j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+            }
+            tc_fence_before(); // chunk consumed: the issuer may start chunk cnt + 2 in this buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tm_empty(buf) + lead_off);
+          }
+          // out = acc / (S_A S_B) [+ bias -> activation | * act'(A_prev)]; the row of ones of a dW's A operand is unscaled
+          const long grow = (long)tile * kFM + q * 32 + lane;
+          const float sb = __ldg(p.sb_inv), sc = (grow == (long)p.ones_row) ? sb : __ldg(p.sa_inv) * sb;
+          const bool rok = grow < (long)p.rows_valid;
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) {
+            const int col0 = nt_of(unit) * BN + half * 32 + 64 * i;
+            const float4 *ap = reinterpret_cast<const float4 *>(p.aux32 + (rok ? grow : 0) * p.ld_aux + col0);
+            if (lane == 0) tma_store_wait_read(); // the previous block of this warp has left the staging tile
+            __syncwarp();
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              float4 r;
+              r.x = accr[i][4 * qq + 0] * sc; r.y = accr[i][4 * qq + 1] * sc; r.z = accr[i][4 * qq + 2] * sc; r.w = accr[i][4 * qq + 3] * sc;
+              if (p.aux32) {
+                const float4 a = rok ? __ldg(ap + qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r.x *= act_deriv_c<ACT>(p.act, a.x); r.y *= act_deriv_c<ACT>(p.act, a.y);
+                r.z *= act_deriv_c<ACT>(p.act, a.z); r.w *= act_deriv_c<ACT>(p.act, a.w);
+              } else if (p.bias) {
+                const float *bp4 = p.bias + col0 + 4 * qq; // (the same address in every lane: one broadcast load each)
+                r.x = act_apply_c<ACT>(p.act, r.x + __ldg(bp4)); r.y = act_apply_c<ACT>(p.act, r.y + __ldg(bp4 + 1));
+                r.z = act_apply_c<ACT>(p.act, r.z + __ldg(bp4 + 2)); r.w = act_apply_c<ACT>(p.act, r.w + __ldg(bp4 + 3));
+              }
+              *reinterpret_cast<float4 *>(stage_p + lane * 128 + ((qq ^ (lane & 7)) << 4)) = r;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmOut, stage_a, col0, tile * kFM + q * 32);
+              tma_store_commit();
+            }
+          }
+        }
+        if (lane == 0) tma_store_wait_all();
+        if (p.dbg && threadIdx.x == kEpiWarp0 * 32) p.dbg[8 * blockIdx.x + 2] = waiting;
+      }
+      if constexpr (!WIDE)
       for (int unit = unit0; unit < units; unit += unit_step, ++it) {
         const int tile = tile_of(unit); // (PAIR, odd tile count: the peer's last tile lies past the batch; its stores are clipped)
         const int buf = it & 1;
@@ -766,11 +900,11 @@ int make_map_3d(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsig
   return make_map_3d_ex(tm, ptr, dim0, dim1, dim2, dim0 * 2, dim0 * dim1 * 2, box0, box1, 1, sw);
 }
 
-template <int BN, bool X2, int EPI, int NS, bool PAIR = false, int NW = NS>
+template <int BN, bool X2, int EPI, int NS, bool PAIR = false, int NW = NS, bool WIDE = false>
 int launch_fwd16(const CUtensorMap &tx, const CUtensorMap &twh, const CUtensorMap &twl, const CUtensorMap &tout, const CUtensorMap &taux,
                  const F16Params &p, int grid, cudaStream_t st) {
-  auto kern = fwd16_kernel<BN, X2, EPI, NS, PAIR, NW>;
-  constexpr int smem = FPlan<BN, X2, EPI, NS, PAIR, NW>::kTotal;
+  auto kern = fwd16_kernel<BN, X2, EPI, NS, PAIR, NW, WIDE>;
+  constexpr int smem = FPlan<BN, X2, EPI, NS, PAIR, NW, WIDE>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1064,6 +1198,307 @@ int mid16_dx_layer1(b200_net *net, long batch) {
   return B200_OK;
 }
 
+
+// ---- wide hidden layers on the fp16 pair kernels (b200_net::Wide16) ---------------------------------------------------------
+// Replaces, for layers whose GEMMs are compute-bound (BASELINE configs[4]: 784-4096-4096-10), the three cublasSgemm calls of
+// CudaDenseLayer (src/cuda/layer.cuh:51-54 forward, :81-84 dW, :89-92 dX) and their element-wise kernels. The generic kernel
+// (gemm_tc.cu) runs them as 3xTF32 with N = 128, K = 8 MMAs at the 133-clk issue floor of cta_group::1; here both operands are
+// fp16 pairs and a CTA pair issues M = 256, N = 256, K = 16 MMAs (130 clk): four products per K step (hi hi, hi lo, lo hi, lo lo)
+// in two instructions.
+namespace {
+
+// per-CTA max |x| over a linear array (padding columns of a delta buffer are zero)
+__global__ void __launch_bounds__(256) wide_amax_kernel(const float *__restrict__ x, unsigned long long n, float *__restrict__ part,
+                                                      const SpecState *spec_st, int spec) {
+  pdl_enter();
+  if (spec_skip(spec_st, spec)) return;
+  float m = 0.0f;
+  const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+  const unsigned long long n4 = vec ? n / 4 : 0;
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (unsigned long long i = 4 * n4 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    part[blockIdx.x] = m;
+  }
+}
+
+// x[rows][ld] (cols valid) -> P[rows][hi Cp | lo Cp] and (PT != nullptr) PT[cols (+ ones)][hi Rp | lo Rp], zero padded; the scale
+// S = 2^(14 - e) with max |x| in [2^(e-1), 2^e) from the per-CTA maxima; block 0 publishes {S, 1 / S}
+__global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict__ x, long rows, int cols, long ld, const float *__restrict__ part,
+                                                       int npart, __half *__restrict__ P, int Cp, __half *__restrict__ PT, long Rp, int ones,
+                                                       float *__restrict__ scal, const SpecState *spec_st, int spec) {
+  pdl_enter();
+  if (spec_skip(spec_st, spec)) return;
+  __shared__ float red[8];
+  __shared__ __half th[64][72], tl[64][72]; // [column of the tile][row of the tile] (rows padded: 16-byte reads at 144-byte pitch)
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < npart; i += 256) m = fmaxf(m, __ldcg(part + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i]);
+  int e = 0;
+  if (m > 0.0f && m < 3.0e38f) frexpf(m, &e);
+  e = max(-100, min(100, e));
+  const float S = ldexpf(1.0f, 14 - e);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scal[0] = S; scal[1] = ldexpf(1.0f, e - 14); }
+  const long ldp = 2L * Cp, ldt = 2L * Rp;
+  const int tiles_c = Cp / 64;
+  const long tiles = (Rp / 64) * (long)tiles_c;
+  const int tr_ = threadIdx.x >> 4, tc4 = (threadIdx.x & 15) * 4;
+  for (long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long r0 = (t / tiles_c) * 64;
+    const int c0 = (int)(t % tiles_c) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = tr_ + 16 * i;
+      const long r = r0 + rr;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (r < rows && c0 + tc4 + k < cols) ? __ldg(x + r * ld + c0 + tc4 + k) * S : 0.0f;
+      __align__(8) __half h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        h[k] = __float2half_rn(v[k]);
+        l[k] = __float2half_rn(v[k] - __half2float(h[k]));
+        th[tc4 + k][rr] = h[k];
+        tl[tc4 + k][rr] = l[k];
+      }
+      if (r < rows) {
+        *reinterpret_cast<uint2 *>(P + r * ldp + c0 + tc4) = *reinterpret_cast<const uint2 *>(h);
+        *reinterpret_cast<uint2 *>(P + r * ldp + Cp + c0 + tc4) = *reinterpret_cast<const uint2 *>(l);
+      }
+    }
+    if (PT) {
+      __syncthreads();
+      const int col = threadIdx.x >> 2, seg = (threadIdx.x & 3) * 16;
+      if (c0 + col < cols) {
+        __half *q = PT + (long)(c0 + col) * ldt + r0 + seg;
+        *reinterpret_cast<uint4 *>(q) = *reinterpret_cast<const uint4 *>(&th[col][seg]);
+        *reinterpret_cast<uint4 *>(q + 8) = *reinterpret_cast<const uint4 *>(&th[col][seg + 8]);
+        *reinterpret_cast<uint4 *>(q + Rp) = *reinterpret_cast<const uint4 *>(&tl[col][seg]);
+        *reinterpret_cast<uint4 *>(q + Rp + 8) = *reinterpret_cast<const uint4 *>(&tl[col][seg + 8]);
+      }
+      __syncthreads();
+    }
+  }
+  if (PT && ones) { // row `cols` of the transpose: unscaled ones over the valid rows (the bias-gradient row of the dW GEMM)
+    __half *q = PT + (long)cols * ldt;
+    for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < Rp; r += (long)gridDim.x * blockDim.x) {
+      q[r] = __float2half_rn(r < rows ? 1.0f : 0.0f);
+      q[Rp + r] = __float2half_rn(0.0f);
+    }
+  }
+}
+
+inline long up64(long v) { return (v + 63) / 64 * 64; }
+
+int wide_buf(b200_net *net, b200_net::Wide16::Buf &b, size_t halves) {
+  if (b.halves >= halves) return B200_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.halves = 0;
+  B200_CUDA(cudaMalloc(&b.p, halves * sizeof(__half)));
+  b.halves = halves;
+  ++net->config_gen;
+  return B200_OK;
+}
+
+int wide_ensure(b200_net *net) {
+  b200_net::Wide16 &w = net->w16x;
+  const int L = net->nlayers();
+  if ((int)w.a.size() != L) {
+    w.a.resize(L); w.aT.resize(L); w.wf.resize(L); w.wd.resize(L);
+    w.a_ready.assign(L, 0); w.w_ready.assign(L, 0); w.d_ready.assign(L, 0);
+  }
+  if (!w.scal) {
+    B200_CUDA(cudaMalloc(&w.scal, sizeof(float) * 8 * L));
+    w.amax_n = 4 * net->ctx->num_sms;
+    B200_CUDA(cudaMalloc(&w.amax_part, sizeof(float) * w.amax_n));
+    ++net->config_gen;
+  }
+  return B200_OK;
+}
+
+// split x[rows][ld] into P (and PT); scal -> {S, 1 / S}
+int wide_split(b200_net *net, const float *x, long rows, int cols, long ld, void *P, int Cp, void *PT, long Rp, int ones, float *scal) {
+  b200_net::Wide16 &w = net->w16x;
+  cudaStream_t st = net->ctx->stream;
+  const unsigned long long n = (unsigned long long)rows * ld - (unsigned long long)(ld - cols); // (the last row ends at its last valid column)
+  const int ga = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)w.amax_n, (n + 1023) / 1024));
+  B200_LAUNCH(wide_amax_kernel, ga, 256, 0, st, x, n, w.amax_part, net->spec_st, net->spec_flag);
+  const long tiles = (Rp / 64) * (long)(Cp / 64);
+  const int gs = (int)std::max<long>(1, std::min<long>(8L * net->ctx->num_sms, tiles));
+  B200_LAUNCH(wide_split_kernel, gs, 256, 0, st, x, rows, cols, ld, (const float *)w.amax_part, ga, (__half *)P, Cp, (__half *)PT, Rp, ones, scal,
+              net->spec_st, net->spec_flag);
+  return B200_OK;
+}
+
+int wide_weights(b200_net *net, int l, const float *params) {
+  b200_net::Wide16 &w = net->w16x;
+  if (w.w_ready[l]) return B200_OK;
+  const int K = net->dims[l], N = net->dims[l + 1];
+  const long Kp = up64(K), Np = up64(N);
+  B200_TRY(wide_buf(net, w.wd[l], (size_t)K * 2 * Np));
+  B200_TRY(wide_buf(net, w.wf[l], (size_t)N * 2 * Kp));
+  // W_l [K][N]: P = [K][hi Np | lo Np] (dX: rows = the columns of delta_{l-1}), PT = [N][hi Kp | lo Kp] (forward: rows = outputs)
+  B200_TRY(wide_split(net, params + net->offs[l], K, N, N, w.wd[l].p, (int)Np, w.wf[l].p, Kp, 0, w.scal + 8 * l + 2));
+  w.w_ready[l] = 1;
+  return B200_OK;
+}
+
+int wide_input(b200_net *net, int l, const float *in, long batch) {
+  b200_net::Wide16 &w = net->w16x;
+  if (w.a_ready[l]) return B200_OK;
+  const int K = net->dims[l];
+  const long Kp = up64(K), Bp = up64(net->cap);
+  B200_TRY(wide_buf(net, w.a[l], (size_t)net->cap * 2 * Kp));
+  B200_TRY(wide_buf(net, w.aT[l], (size_t)(K + 1) * 2 * Bp));
+  B200_TRY(wide_split(net, in, batch, K, K, w.a[l].p, (int)Kp, w.aT[l].p, up64(batch), 1, w.scal + 8 * l));
+  w.a_ready[l] = 1;
+  return B200_OK;
+}
+
+int wide_delta(b200_net *net, int l, long batch) {
+  b200_net::Wide16 &w = net->w16x;
+  if (w.d_ready[l]) return B200_OK;
+  const int N = net->dims[l + 1];
+  const long Np = up64(N), Bp = up64(net->cap);
+  int maxN = 0;
+  for (int j = 0; j < net->nlayers(); ++j) maxN = std::max(maxN, net->dims[j + 1]);
+  B200_TRY(wide_buf(net, w.d, (size_t)net->cap * 2 * up64(maxN)));
+  B200_TRY(wide_buf(net, w.dT, (size_t)maxN * 2 * Bp));
+  B200_TRY(wide_split(net, net->delta[l], batch, N, net->ldd[l], w.d.p, (int)Np, w.dT.p, up64(batch), 0, w.scal + 8 * l + 4));
+  std::fill(w.d_ready.begin(), w.d_ready.end(), 0); // (one buffer for every layer: it now holds layer l's)
+  w.d_ready[l] = 1;
+  return B200_OK;
+}
+
+// C[rows][ncols] = A B^T / (S_A S_B): A = pair rows [rows][hi Kc | lo Kc] (Kc the padded contraction length), B = pair rows
+// [ncols][hi Kc | lo Kc]
+struct WideGemm {
+  const void *A; long rows; const void *B; int ncols; long Kc;
+  float *out; long ld_out;
+  const float *sa_inv, *sb_inv, *bias, *aux32; long ld_aux; int act, ones_row;
+};
+int wide_gemm(b200_net *net, const WideGemm &g) {
+  CUtensorMap tx, twh, twl, tout;
+  // A: dims ordered so that the strides ascend {64 halves, 2 Kc / 64 blocks (128 B apart), rows}
+  B200_TRY(make_map_3d_ex(&tx, g.A, 64, (unsigned long long)(2 * g.Kc / 64), (unsigned long long)g.rows, 128, (unsigned long long)2 * g.Kc * 2, 64, 1,
+                          kFM, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&twh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, g.B, (unsigned long long)g.Kc, (unsigned long long)g.ncols,
+                       (unsigned long long)2 * g.Kc * 2, kFK, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (const __half *)g.B + g.Kc, (unsigned long long)g.Kc, (unsigned long long)g.ncols,
+                       (unsigned long long)2 * g.Kc * 2, kFK, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, g.out, (unsigned long long)g.ncols, (unsigned long long)g.rows,
+                       (unsigned long long)g.ld_out * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  F16Params p{};
+  p.rows_valid = (int)g.rows; p.cols_valid = g.ncols; p.k_total = (int)g.Kc;
+  p.row0 = 0;
+  p.k_blocks = (int)(g.Kc / kFK);
+  p.tiles = ceil_div(g.rows, kFM);
+  p.n_tiles = g.ncols / 128;
+  p.k_chunk = env().wide_chunk > 0 ? env().wide_chunk : 4;
+  p.act = g.act;
+  p.bias = g.bias;
+  p.out = g.out; p.ld_out = g.ld_out;
+  p.spec_st = net->spec_st; p.spec = net->spec_flag;
+  p.x_block_first = 1;
+  p.sa_inv = g.sa_inv; p.sb_inv = g.sb_inv;
+  p.aux32 = g.aux32; p.ld_aux = g.ld_aux;
+  p.ones_row = g.ones_row;
+  const long units = (long)((p.tiles + 1) / 2) * p.n_tiles;
+  const int grid = 2 * (int)std::min<long>(net->ctx->num_sms / 2, units);
+  return launch_fwd16<128, true, EPI_WIDE, 4, true, 4, true>(tx, twh, twl, tout, tout, p, grid, net->ctx->stream);
+}
+
+} // namespace
+
+bool wide16_applicable(const b200_net *net, int l, int role) {
+  if (!env().wide16 || net->prec != B200_PREC_TF32X3 || net->m16.on) return false;
+  const int K = net->dims[l], N = net->dims[l + 1];
+  if (K < 256 || N < 256 || N % 128 != 0) return false;
+  if (l == 0 && fwd16_shape_ok(net)) return false;
+  if (role == 1 && (l == 0 || K % 128 != 0 || net->ldd[l - 1] % 4 != 0)) return false; // (dX: the output tile is 128 columns of delta_{l-1})
+  return true;
+}
+
+void wide16_begin(b200_net *net) {
+  b200_net::Wide16 &w = net->w16x;
+  std::fill(w.a_ready.begin(), w.a_ready.end(), 0);
+  std::fill(w.w_ready.begin(), w.w_ready.end(), 0);
+  std::fill(w.d_ready.begin(), w.d_ready.end(), 0);
+}
+
+// A_l = act(A_{l-1} W_l + b_l)
+int wide16_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch) {
+  B200_TRY(wide_ensure(net));
+  b200_net::Wide16 &w = net->w16x;
+  const int K = net->dims[l], N = net->dims[l + 1];
+  B200_TRY(wide_weights(net, l, params));
+  B200_TRY(wide_input(net, l, in, batch));
+  WideGemm g{};
+  g.A = w.a[l].p; g.rows = batch; g.B = w.wf[l].p; g.ncols = N; g.Kc = up64(K);
+  g.out = net->act[l]; g.ld_out = N;
+  g.sa_inv = w.scal + 8 * l + 1; g.sb_inv = w.scal + 8 * l + 3;
+  g.bias = params + net->offs[l] + (size_t)K * N; g.act = net->acts[l]; g.ones_row = -1;
+  return wide_gemm(net, g);
+}
+
+// delta_{l-1} = (delta_l W_l^T) .* act'_{l-1}(A_{l-1})
+int wide16_dx_layer(b200_net *net, int l, const float *params, long batch) {
+  B200_TRY(wide_ensure(net));
+  b200_net::Wide16 &w = net->w16x;
+  const int K = net->dims[l], N = net->dims[l + 1];
+  B200_TRY(wide_weights(net, l, params));
+  B200_TRY(wide_delta(net, l, batch));
+  WideGemm g{};
+  g.A = w.d.p; g.rows = batch; g.B = w.wd[l].p; g.ncols = K; g.Kc = up64(N);
+  g.out = net->delta[l - 1]; g.ld_out = net->ldd[l - 1];
+  g.sa_inv = w.scal + 8 * l + 5; g.sb_inv = w.scal + 8 * l + 3;
+  g.aux32 = net->act[l - 1]; g.ld_aux = K; g.act = net->acts[l - 1]; g.ones_row = -1;
+  return wide_gemm(net, g);
+}
+
+// [dW_l; db_l] = [A_{l-1} | 1]^T delta_l, one slice (the whole batch) straight into the layer's partial
+int wide16_dw_layer(b200_net *net, int l, const float *in, long batch) {
+  B200_TRY(wide_ensure(net));
+  b200_net::Wide16 &w = net->w16x;
+  const int K = net->dims[l], N = net->dims[l + 1];
+  B200_TRY(wide_input(net, l, in, batch)); // (made by the forward pass of this evaluation)
+  B200_TRY(wide_delta(net, l, batch));
+  WideGemm g{};
+  g.A = w.aT[l].p; g.rows = K + 1; g.B = w.dT.p; g.ncols = N; g.Kc = up64(batch);
+  g.out = net->partials + net->part_off[l]; g.ld_out = N;
+  g.sa_inv = w.scal + 8 * l + 1; g.sb_inv = w.scal + 8 * l + 5;
+  g.act = B200_ACT_LINEAR; g.ones_row = K;
+  B200_TRY(wide_gemm(net, g));
+  net->splits_used[l] = 1;
+  return B200_OK;
+}
+
+void wide16_release(b200_net *net) {
+  b200_net::Wide16 &w = net->w16x;
+  for (auto *v : {&w.a, &w.aT, &w.wf, &w.wd})
+    for (auto &b : *v) if (b.p) cudaFree(b.p);
+  if (w.d.p) cudaFree(w.d.p);
+  if (w.dT.p) cudaFree(w.dT.p);
+  if (w.scal) cudaFree(w.scal);
+  if (w.amax_part) cudaFree(w.amax_part);
+  w = b200_net::Wide16{};
+}
+
 void fwd16_release(b200_net *net) {
   if (net->w16h) cudaFree(net->w16h);
   if (net->w16l) cudaFree(net->w16l);
@@ -1071,6 +1506,7 @@ void fwd16_release(b200_net *net) {
   net->w16h = net->w16l = nullptr;
   net->colscale = nullptr;
   mid16_release(net);
+  wide16_release(net);
 }
 
 } // namespace b200

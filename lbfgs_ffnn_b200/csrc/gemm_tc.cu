@@ -747,6 +747,11 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   *done = false;
   if (fused) *fused = false;
   if (!(tc_mask() & 1)) return B200_OK;
+  if (wide16_applicable(net, l, 0)) { // wide layer: both operands as fp16 pairs on the CTA-pair kernel (gemm_fwd16.cu)
+    B200_TRY(wide16_forward_layer(net, l, params, in, batch));
+    *done = true;
+    return B200_OK;
+  }
   TcSpecScope spec_scope(net);
   const int K = net->dims[l], N = net->dims[l + 1];
   const float *W = params + net->offs[l];
@@ -811,6 +816,11 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
   const bool want16 = emit16 && *emit16 && net->delta16 && net->scale16;
   if (emit16) *emit16 = false;
   if (!(tc_mask() & 2)) return B200_OK;
+  if (wide16_applicable(net, l, 1)) {
+    B200_TRY(wide16_dx_layer(net, l, params, batch));
+    *done = true;
+    return B200_OK;
+  }
   TcSpecScope spec_scope(net);
   const int Kin = net->dims[l], Nout = net->dims[l + 1]; // contraction over out, result width in
   const float *W = params + net->offs[l];
@@ -872,6 +882,11 @@ int tc_dw_plan(b200_net *net, int l, long batch, int *splits) {
 int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
   *done = false;
   if (!(tc_mask() & 4)) return B200_OK;
+  if (wide16_applicable(net, l, 2) && (reinterpret_cast<uintptr_t>(net->partials + net->part_off[l]) & 15u) == 0) {
+    B200_TRY(wide16_dw_layer(net, l, in, batch));
+    *done = true;
+    return B200_OK;
+  }
   TcSpecScope spec_scope(net);
   const int Kin = net->dims[l], Nout = net->dims[l + 1];
   if (!tma_ok(net->delta[l], net->ldd[l]) || !tma_ok(in, Kin)) return B200_OK;

@@ -690,6 +690,7 @@ int net_forward(b200_net *net, const float *params, const float *x, long batch) 
   net->m16.on = mid;
   net->m16.act0_stale = false;
   net->split_src = nullptr;
+  wide16_begin(net);
   if (mid) B200_TRY(mid16_ensure(net, batch));
   else B200_TRY(tc_split_params(net, params));
   if (net->prec != B200_PREC_FP32 && net_x16_view(net, x, batch, &xv0)) B200_TRY(fwd16_prepare(net, params));
@@ -732,6 +733,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
   net->m16.on = mid;
   net->m16.act0_stale = false;
   net->split_src = nullptr;
+  wide16_begin(net);
   if (mid) B200_TRY(mid16_ensure(net, batch));
   else B200_TRY(tc_split_params(net, params)); // (the TF32 hi / lo split of the parameters feeds the generic kernels only)
   const bool have16 = net->prec != B200_PREC_FP32 && net_x16_view(net, x, batch, &xv0); // fp16 copy of this batch (input slice or gathered)

@@ -103,6 +103,21 @@ struct b200_net {
     bool act0_stale = false;     // act[0] (fp32) does not hold A_1 of the last evaluation: only a16 does
   } m16;
 
+  // ---- wide hidden layers (hundreds to thousands of columns: BASELINE configs[4]) on the fp16 pair kernels ("wide16", end of
+  // gemm_fwd16.cu). Activations, deltas and weights stay fp32 in HBM as on the generic path; each GEMM operand is split once per
+  // evaluation into a pair hi = fp16(S v), lo = fp16(S v - hi) with ONE power-of-two scale S per matrix (S max|v| in
+  // [2^13, 2^14)), row-major [rows][hi Cp | lo Cp] and, for the dW of the layer, transposed [cols (+ a row of ones)][hi Rp | lo Rp].
+  struct Wide16 {
+    struct Buf { void *p = nullptr; size_t halves = 0; };
+    std::vector<Buf> a, aT;   // per layer l: its input A_{l-1} (forward A operand) and the transpose + ones row (dW A operand)
+    std::vector<Buf> wf, wd;  // per layer l: W_l as [out][hi Kp | lo Kp] (forward B operand) and [in][hi Np | lo Np] (dX B operand)
+    Buf d, dT;                // delta_l of the layer being worked on: [rows][hi Np | lo Np] (dX A operand), [out][hi Bp | lo Bp] (dW B operand)
+    std::vector<char> a_ready, w_ready, d_ready; // this evaluation has made them
+    float *scal = nullptr;    // device: per layer {S_a, 1/S_a, S_w, 1/S_w, S_d, 1/S_d, -, -}
+    float *amax_part = nullptr; // device: per-CTA maxima of the matrix being split
+    int amax_n = 0;
+  } w16x;
+
   double *loss_part = nullptr; // per-CTA partials of sum diff^2
   int loss_part_cap = 0, loss_part_n = 0;
   double *fin_part = nullptr;  // per-CTA partials of ||g||^2 and ||w||^2 (2 per CTA)
@@ -214,6 +229,13 @@ __device__ __forceinline__ void chain_cw_block(const ChainW &c, int cta, float *
 }
 #endif
 void tail_release(b200_net *net);
+// wide hidden layers on the fp16 pair kernels (b200_net::Wide16, gemm_fwd16.cu). role: 0 forward, 1 dX, 2 dW
+bool wide16_applicable(const b200_net *net, int l, int role);
+void wide16_begin(b200_net *net); // start of an evaluation: no operand has been split yet
+int wide16_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch);
+int wide16_dx_layer(b200_net *net, int l, const float *params, long batch);
+int wide16_dw_layer(b200_net *net, int l, const float *in, long batch);
+void wide16_release(b200_net *net);
 // the reference CPU backend's random-mini-batch SGD (src/minimizer/s_gd.hpp:63-170) on the GPU (slbfgs.cu: shares the sampler
 // and the row gather of S-LBFGS)
 int sgd_random_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const float *input, const float *target, int total_samples,
