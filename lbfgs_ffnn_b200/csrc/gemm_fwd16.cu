@@ -1235,9 +1235,20 @@ __global__ void __launch_bounds__(256) wide_amax_kernel(const float *__restrict_
 
 // x[rows][ld] (cols valid) -> P[rows][hi Cp | lo Cp] and (PT != nullptr) PT[cols (+ ones)][hi Rp | lo Rp], zero padded; the scale
 // S = 2^(14 - e) with max |x| in [2^(e-1), 2^e) from the per-CTA maxima; block 0 publishes {S, 1 / S}
+// GEN: x is not read but generated, element (r, c) = act'(a[r][c]) * sum_j dl[r][j] Wl[c][j]: the dX of a skinny last layer
+// (src/cuda/layer.cuh:89-103 with out <= 12) fused with the split of its result — delta_{L-1} then exists only as the pair. The
+// per-CTA maxima are those of delta_L, and the scale comes from the bound max |delta_L| * max_c sum_j |Wl[c][j]| (|act'| <= 1).
+constexpr int kGenMaxOut = 12;
+struct WideGen {
+  const float *dl; long ldl; int out;
+  const float *Wl;  // [cols][out]
+  const float *a;   // [rows][cols] activations whose act' multiplies
+  int act;
+};
+template <bool GEN>
 __global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict__ x, long rows, int cols, long ld, const float *__restrict__ part,
                                                        int npart, __half *__restrict__ P, int Cp, __half *__restrict__ PT, long Rp, int ones,
-                                                       float *__restrict__ scal, const SpecState *spec_st, int spec) {
+                                                       float *__restrict__ scal, const SpecState *spec_st, int spec, const WideGen gen) {
   pdl_enter();
   if (spec_skip(spec_st, spec)) return;
   __shared__ float red[8];
@@ -1249,6 +1260,21 @@ __global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i]);
+  if constexpr (GEN) { // * max_c sum_j |Wl[c][j]|
+    float wn = 0.0f;
+    for (int c = threadIdx.x; c < cols; c += 256) {
+      float sum = 0.0f;
+      for (int j = 0; j < gen.out; ++j) sum += fabsf(__ldg(gen.Wl + (long)c * gen.out + j));
+      wn = fmaxf(wn, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wn = fmaxf(wn, __shfl_xor_sync(0xffffffffu, wn, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wn;
+    __syncthreads();
+    for (int i = 0; i < 8; ++i) wn = fmaxf(wn, red[i]);
+    m *= wn * 1.0001f; // (fp32 summation slack)
+  }
   int e = 0;
   if (m > 0.0f && m < 3.0e38f) frexpf(m, &e);
   e = max(-100, min(100, e));
@@ -1256,32 +1282,93 @@ __global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict
   if (blockIdx.x == 0 && threadIdx.x == 0) { scal[0] = S; scal[1] = ldexpf(1.0f, e - 14); }
   const long ldp = 2L * Cp, ldt = 2L * Rp;
   const int tiles_c = Cp / 64;
-  const long tiles = (Rp / 64) * (long)tiles_c;
+  const long tiles_r = Rp / 64;
+  // a CTA keeps one tile column (the grid is a multiple of tiles_c) and walks down the rows: GEN loads its four columns of the last
+  // layer's weights once. A thread owns 4 consecutive rows x 4 consecutive columns of the 64 x 64 tile.
+  const int G = gridDim.x / tiles_c;
+  const int c0 = (int)(blockIdx.x % tiles_c) * 64;
   const int tr_ = threadIdx.x >> 4, tc4 = (threadIdx.x & 15) * 4;
-  for (long t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const long r0 = (t / tiles_c) * 64;
-    const int c0 = (int)(t % tiles_c) * 64;
+  const bool vec = (cols % 4 == 0) && (GEN ? ((reinterpret_cast<uintptr_t>(gen.a) & 15u) == 0)
+                                           : (ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0));
+  float wl[GEN ? 4 : 1][GEN ? kGenMaxOut : 1];
+  if constexpr (GEN) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = tr_ + 16 * i;
-      const long r = r0 + rr;
-      float v[4];
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (r < rows && c0 + tc4 + k < cols) ? __ldg(x + r * ld + c0 + tc4 + k) * S : 0.0f;
-      __align__(8) __half h[4], l[4];
+      for (int j = 0; j < kGenMaxOut; ++j)
+        wl[k][j] = (j < gen.out && c0 + tc4 + k < cols) ? __ldg(gen.Wl + (long)(c0 + tc4 + k) * gen.out + j) : 0.0f;
+  }
+  const bool dl_vec = GEN && gen.out == kGenMaxOut && gen.ldl == kGenMaxOut && (reinterpret_cast<uintptr_t>(gen.dl) & 15u) == 0;
+  for (long rb = blockIdx.x / tiles_c; rb < tiles_r; rb += G) {
+    const long r0 = rb * 64;
+    float v[4][4];
+    { // the tile's values, every load of the thread in flight together
+      float4 raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long r = r0 + 4 * tr_ + i;
+        const float *src = GEN ? gen.a + r * (long)cols + c0 + tc4 : x + r * ld + c0 + tc4;
+        if (r < rows && vec && c0 + tc4 + 3 < cols) raw[i] = __ldg(reinterpret_cast<const float4 *>(src));
+        else {
+          raw[i].x = (r < rows && c0 + tc4 + 0 < cols) ? __ldg(src + 0) : 0.0f;
+          raw[i].y = (r < rows && c0 + tc4 + 1 < cols) ? __ldg(src + 1) : 0.0f;
+          raw[i].z = (r < rows && c0 + tc4 + 2 < cols) ? __ldg(src + 2) : 0.0f;
+          raw[i].w = (r < rows && c0 + tc4 + 3 < cols) ? __ldg(src + 3) : 0.0f;
+        }
+      }
+      if constexpr (GEN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long r = r0 + 4 * tr_ + i;
+          float dl[kGenMaxOut];
+          if (dl_vec && r < rows) {
+#pragma unroll
+            for (int j4 = 0; j4 < kGenMaxOut / 4; ++j4) {
+              const float4 d4 = __ldg(reinterpret_cast<const float4 *>(gen.dl + r * gen.ldl) + j4);
+              dl[4 * j4] = d4.x; dl[4 * j4 + 1] = d4.y; dl[4 * j4 + 2] = d4.z; dl[4 * j4 + 3] = d4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kGenMaxOut; ++j) dl[j] = (j < gen.out && r < rows) ? __ldg(gen.dl + r * gen.ldl + j) : 0.0f;
+          }
+          const float av[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kGenMaxOut; ++j) acc = fmaf(dl[j], wl[k][j], acc);
+            const bool ok = r < rows && c0 + tc4 + k < cols;
+            v[i][k] = ok ? acc * act_deriv_from_output(gen.act, av[k]) * S : 0.0f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i][0] = raw[i].x * S; v[i][1] = raw[i].y * S; v[i][2] = raw[i].z * S; v[i][3] = raw[i].w * S; }
+      }
+    }
+    __align__(8) __half h[4][4], l[4][4]; // [row i][col k]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        h[k] = __float2half_rn(v[k]);
-        l[k] = __float2half_rn(v[k] - __half2float(h[k]));
-        th[tc4 + k][rr] = h[k];
-        tl[tc4 + k][rr] = l[k];
+        h[i][k] = __float2half_rn(v[i][k]);
+        l[i][k] = __float2half_rn(v[i][k] - __half2float(h[i][k]));
       }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long r = r0 + 4 * tr_ + i;
       if (r < rows) {
-        *reinterpret_cast<uint2 *>(P + r * ldp + c0 + tc4) = *reinterpret_cast<const uint2 *>(h);
-        *reinterpret_cast<uint2 *>(P + r * ldp + Cp + c0 + tc4) = *reinterpret_cast<const uint2 *>(l);
+        *reinterpret_cast<uint2 *>(P + r * ldp + c0 + tc4) = *reinterpret_cast<const uint2 *>(h[i]);
+        *reinterpret_cast<uint2 *>(P + r * ldp + Cp + c0 + tc4) = *reinterpret_cast<const uint2 *>(l[i]);
       }
     }
     if (PT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { // four consecutive rows of column tc4 + k: one 8-byte store each for hi and lo
+        __align__(8) __half hc[4] = {h[0][k], h[1][k], h[2][k], h[3][k]}, lc[4] = {l[0][k], l[1][k], l[2][k], l[3][k]};
+        *reinterpret_cast<uint2 *>(&th[tc4 + k][4 * tr_]) = *reinterpret_cast<const uint2 *>(hc);
+        *reinterpret_cast<uint2 *>(&tl[tc4 + k][4 * tr_]) = *reinterpret_cast<const uint2 *>(lc);
+      }
       __syncthreads();
       const int col = threadIdx.x >> 2, seg = (threadIdx.x & 3) * 16;
       if (c0 + col < cols) {
@@ -1331,6 +1418,13 @@ int wide_ensure(b200_net *net) {
   return B200_OK;
 }
 
+// grid of the split kernel: a multiple of the tile columns (a CTA keeps its tile column), ~8 CTAs per SM
+int wide_split_grid(const b200_net *net, long Rp, long Cp) {
+  const long tiles_c = Cp / 64, tiles_r = Rp / 64;
+  const long G = std::max<long>(1, std::min<long>(tiles_r, (8L * net->ctx->num_sms) / tiles_c));
+  return (int)(tiles_c * G);
+}
+
 // split x[rows][ld] into P (and PT); scal -> {S, 1 / S}
 int wide_split(b200_net *net, const float *x, long rows, int cols, long ld, void *P, int Cp, void *PT, long Rp, int ones, float *scal) {
   b200_net::Wide16 &w = net->w16x;
@@ -1338,10 +1432,9 @@ int wide_split(b200_net *net, const float *x, long rows, int cols, long ld, void
   const unsigned long long n = (unsigned long long)rows * ld - (unsigned long long)(ld - cols); // (the last row ends at its last valid column)
   const int ga = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)w.amax_n, (n + 1023) / 1024));
   B200_LAUNCH(wide_amax_kernel, ga, 256, 0, st, x, n, w.amax_part, net->spec_st, net->spec_flag);
-  const long tiles = (Rp / 64) * (long)(Cp / 64);
-  const int gs = (int)std::max<long>(1, std::min<long>(8L * net->ctx->num_sms, tiles));
-  B200_LAUNCH(wide_split_kernel, gs, 256, 0, st, x, rows, cols, ld, (const float *)w.amax_part, ga, (__half *)P, Cp, (__half *)PT, Rp, ones, scal,
-              net->spec_st, net->spec_flag);
+  const int gs = wide_split_grid(net, Rp, Cp);
+  B200_LAUNCH(wide_split_kernel<false>, gs, 256, 0, st, x, rows, cols, ld, (const float *)w.amax_part, ga, (__half *)P, Cp, (__half *)PT, Rp, ones, scal,
+              net->spec_st, net->spec_flag, WideGen{});
   return B200_OK;
 }
 
@@ -1469,6 +1562,42 @@ int wide16_dx_layer(b200_net *net, int l, const float *params, long batch) {
   g.sa_inv = w.scal + 8 * l + 5; g.sb_inv = w.scal + 8 * l + 3;
   g.aux32 = net->act[l - 1]; g.ld_aux = K; g.act = net->acts[l - 1]; g.ones_row = -1;
   return wide_gemm(net, g);
+}
+
+// The layer below a skinny last layer (out <= 12): its delta pair straight from delta_L, W_L and act'(A_{L-1}) — replaces the last
+// layer's dX GEMM + activation_deriv (src/cuda/layer.cuh:89-103), whose fp32 result (2 GB at configs[4]'s per-GPU share) would be
+// written only to be read back twice (maximum, split).
+bool wide16_last_dx_applicable(const b200_net *net) {
+  const int L = net->nlayers();
+  if (L < 2 || net->dims[L] > kGenMaxOut || !env().wide16 || (env().wide16 & 2)) return false; // (B200_WIDE16=3: separate dX + split)
+  const int l = L - 2;
+  return wide16_applicable(net, l, 2) && (l == 0 || wide16_applicable(net, l, 1));
+}
+
+int wide16_last_dx(b200_net *net, const float *params, long batch) {
+  B200_TRY(wide_ensure(net));
+  b200_net::Wide16 &w = net->w16x;
+  const int L = net->nlayers(), l = L - 2;
+  const int N = net->dims[l + 1], out = net->dims[L];
+  const long Np = up64(N), Bp = up64(net->cap);
+  int maxN = 0;
+  for (int j = 0; j < L; ++j) maxN = std::max(maxN, net->dims[j + 1]);
+  B200_TRY(wide_buf(net, w.d, (size_t)net->cap * 2 * up64(maxN)));
+  B200_TRY(wide_buf(net, w.dT, (size_t)maxN * 2 * Bp));
+  cudaStream_t st = net->ctx->stream;
+  const float *dl = net->delta[L - 1];
+  const long ldl = net->ldd[L - 1];
+  const unsigned long long n = (unsigned long long)batch * ldl - (unsigned long long)(ldl - out);
+  const int ga = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)w.amax_n, (n + 1023) / 1024));
+  B200_LAUNCH(wide_amax_kernel, ga, 256, 0, st, dl, n, w.amax_part, net->spec_st, net->spec_flag);
+  const long Rp = up64(batch);
+  const int gs = wide_split_grid(net, Rp, Np);
+  WideGen gen{dl, ldl, out, params + net->offs[L - 1], net->act[l], net->acts[l]};
+  B200_LAUNCH(wide_split_kernel<true>, gs, 256, 0, st, (const float *)nullptr, batch, N, (long)N, (const float *)w.amax_part, ga, (__half *)w.d.p, (int)Np,
+              (__half *)w.dT.p, Rp, 0, w.scal + 8 * l + 4, net->spec_st, net->spec_flag, gen);
+  std::fill(w.d_ready.begin(), w.d_ready.end(), 0);
+  w.d_ready[l] = 1;
+  return B200_OK;
 }
 
 // [dW_l; db_l] = [A_{l-1} | 1]^T delta_l, one slice (the whole batch) straight into the layer's partial

@@ -795,6 +795,10 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         d16_ready = true;
         done = true;
       }
+      if (!done && l == L - 1 && net->prec == B200_PREC_TF32X3 && wide16_last_dx_applicable(net)) {
+        B200_TRY(wide16_last_dx(net, params, batch)); // delta_{L-1} only as the fp16 pair the wide kernels of layer L-1 read
+        done = true;
+      }
       if (!done && net->prec != B200_PREC_FP32) {
         bool emit16 = (l == 1 && use_dw16 && L > 2);
         B200_TRY(tc_dx_layer(net, l, params, batch, &done, &emit16));
