@@ -205,6 +205,7 @@ def run(args, rank, local_rank, world):
         flops = {"fwd0": 2.0 * Bs * 784 * 4096, "fwd1": 2.0 * Bs * 4096 * 4096, "dx1": 2.0 * Bs * 4096 * 4096,
                  "dw1": 2.0 * Bs * 4097 * 4096, "dw0": 2.0 * Bs * 785 * 4096}
         tensor_peak = pk["bf16_sustained"]
+        wide16 = args.precision == "tf32x3" and os.environ.get("B200_WIDE16", "1") != "0"
         kern, roofs = {}, {}
         tot_prof = sum(v[1] for v in rep.values()) or 1.0
         for k, (calls, tot) in rep.items():
@@ -214,6 +215,14 @@ def run(args, rank, local_rank, world):
                 ach = flops[k] / avg_s / 1e12
                 roofs[k] = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
                             "avg_launch_us": avg_s * 1e6, "share_of_step": tot / tot_prof, "alg_flops": flops[k]}
+                if wide16:
+                    # fp32-accurate mode on 16-bit tensor cores: every algorithmic product is issued as four fp16 products
+                    # (hi hi, hi lo, lo hi, lo lo: two M = 256, N = 256, K = 16 MMAs per K step), so the tensor pipe does 4x the
+                    # algorithmic flops; the scope's time also holds the operand splits (one pass over each fp32 matrix)
+                    roofs[k]["issued_flops"] = 4.0 * flops[k]
+                    roofs[k]["tensor_pipe_frac"] = 4.0 * ach / tensor_peak
+                    roofs[k]["note"] = ("wide16: fp16 pair operands, CTA-pair tcgen05 MMAs; frac = algorithmic flops / 16-bit dense peak "
+                                        "(ceiling 0.25 in this mode), tensor_pipe_frac = issued flops / peak")
         # direction: (4k+2) * n_local * 4 bytes over the rank's slice of the history, k = m once the ring is full
         n_local = n if world == 1 else (n + world - 1) // world
         dir_bytes = (4.0 * memory + 2) * n_local * 4
