@@ -1409,7 +1409,11 @@ int wide_ensure(b200_net *net) {
     w.a.resize(L); w.aT.resize(L); w.wf.resize(L); w.wd.resize(L);
     w.a_ready.assign(L, 0); w.w_ready.assign(L, 0); w.d_ready.assign(L, 0);
   }
-  if (!w.scal) {
+  if (!w.scal || w.scal_layers < L) {
+    if (w.scal) cudaFree(w.scal);
+    if (w.amax_part) cudaFree(w.amax_part);
+    w.scal = w.amax_part = nullptr;
+    w.scal_layers = L;
     B200_CUDA(cudaMalloc(&w.scal, sizeof(float) * 8 * L));
     w.amax_n = 4 * net->ctx->num_sms;
     B200_CUDA(cudaMalloc(&w.amax_part, sizeof(float) * w.amax_n));

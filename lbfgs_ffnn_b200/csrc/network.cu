@@ -134,6 +134,14 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
     const FinLayer &L = p.L[layer_of(j)]; // (a group that straddles two layers: each lane follows its own)
     const float *src = L.part + (j - L.off);
     double acc = 0.0;
+    if (__all_sync(0xffffffffu, L.splits <= 4)) { // wide layers (one slice per layer: gemm "wide16") and tiny batches: four loads, not 40
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = ldg_pinned(u < L.splits ? src + (unsigned long long)u * L.stride : p.zero);
+      acc = ((double)t[0] + (double)t[1]) + ((double)t[2] + (double)t[3]); // (the tree of the general form: same bits)
+      if (live) emit(j, acc);
+      continue;
+    }
     for (int sp0 = 0; sp0 < L.splits; sp0 += kThinSplits) {
       float t[kThinSplits];
 #pragma unroll

@@ -115,7 +115,7 @@ struct b200_net {
     std::vector<char> a_ready, w_ready, d_ready; // this evaluation has made them
     float *scal = nullptr;    // device: per layer {S_a, 1/S_a, S_w, 1/S_w, S_d, 1/S_d, -, -}
     float *amax_part = nullptr; // device: per-CTA maxima of the matrix being split
-    int amax_n = 0;
+    int amax_n = 0, scal_layers = 0;
   } w16x;
 
   double *loss_part = nullptr; // per-CTA partials of sum diff^2
