@@ -66,6 +66,7 @@ struct EnvFlags {
   int fwd16 = -1, dw16 = -1, tail = -1, tail_fwd = -1; // B200_FWD16 / _DW16 / _TAIL / _TAIL_FWD: -1 unset, else the integer
   int mid16 = -1;                  // B200_MID16: 0 = hidden layers on the generic TF32 kernels
   int wide16 = 1;                  // B200_WIDE16=0: wide hidden layers on the generic TF32 kernels instead of the fp16 pair kernels
+  long wide16_min = 1L << 30;      // B200_WIDE16_MIN: smallest GEMM (samples x in x out multiply-adds) that takes the wide kernels
   int wide_chunk = 0;              // B200_WIDE_CHUNK: K blocks of 64 per TMEM accumulation chunk of the wide kernels (0 = default 4)
   int pair = 1;                    // B200_PAIR: bit0 = layer-0 forward as CTA pairs (cta_group::2, weights split between the two SMs)
   bool pdl = true;                 // B200_PDL=0: plain stream order instead of programmatic dependent launches

@@ -58,6 +58,7 @@ void env_reload() {
   e.tc_mask = num("B200_TC_MASK", 7);
   e.dw_bn = num("B200_DW_BN", 0);
   if (const char *s = std::getenv("B200_P2P_SPIN_LIMIT")) e.p2p_spin_limit = std::atol(s);
+  if (const char *s = std::getenv("B200_WIDE16_MIN")) e.wide16_min = std::atol(s);
   g_env = e;
 }
 const EnvFlags &env() {
@@ -272,7 +273,12 @@ int ctx_allgather_shards(b200_ctx *ctx, float *full, size_t n, size_t chunk) {
 int ctx_check_device_error(b200_ctx *ctx) {
   volatile double *flag = ctx->h_scalars + kHostErrSlot;
   if (*flag == 0.0) return B200_OK;
+  const double code = *flag;
   *flag = 0.0;
+  if (code == 2.0) {
+    set_error("prep_w16_kernel: the layer-0 CTAs did not publish the feature scales within the wait limit; results of this evaluation are invalid");
+    return B200_ERR_CUDA;
+  }
   set_error("rank %d: a peer did not publish its gradient slot within the wait limit of the peer-memory all-reduce "
             "(dead or stalled rank); results of this evaluation are invalid", ctx->rank);
   return B200_ERR_COMM;

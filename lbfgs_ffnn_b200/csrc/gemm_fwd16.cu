@@ -653,7 +653,7 @@ struct PrepJob {
 // sync: {publishers that have finished, CTAs of the jobs that have finished}; the last CTA to finish zeroes both
 __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ PrepJob j0, const __grid_constant__ PrepJob j1,
                                                       const __grid_constant__ PrepJob j2, const SpecState *spec_st, int spec,
-                                                      const __grid_constant__ ChainW chain, unsigned *sync) {
+                                                      const __grid_constant__ ChainW chain, unsigned *sync, double *host_err) {
   pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   if (spec_skip(spec_st, spec)) return;
   __shared__ float red[128][kSplitNeurons + 1];
@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(1024) prep_w16_kernel(const __grid_constant__ 
       const volatile unsigned *c = sync;
       unsigned long long polls = 0;
       while (*c < (unsigned)j0.nblocks && ++polls < (1ull << 22)) __nanosleep(64); // (bounded: never hang the device)
+      if (*c < (unsigned)j0.nblocks && host_err) { *host_err = 2.0; __threadfence_system(); } // reported at the caller's next synchronisation
       __threadfence();
     }
     __syncthreads();
@@ -984,7 +985,7 @@ int mid16_ensure(b200_net *net, long batch) {
     B200_CUDA(cudaMalloc(&m.wdl, sizeof(__half) * (size_t)N0 * 2 * N1));
     B200_CUDA(cudaMalloc(&m.db_part, sizeof(float) * (size_t)2 * net->ctx->num_sms * N1));
     B200_CUDA(cudaMalloc(&m.prep_sync, sizeof(unsigned) * 2));
-    B200_CUDA(cudaMemset(m.prep_sync, 0, sizeof(unsigned) * 2));
+    B200_CUDA(cudaMemsetAsync(m.prep_sync, 0, sizeof(unsigned) * 2, net->ctx->stream)); // (ordered before the first launch that counts in it)
     ++net->config_gen;
   }
   if (m.a16_rows < net->cap || m.d16_rows < net->cap) {
@@ -1070,7 +1071,7 @@ int fwd16_prepare(b200_net *net, const float *params) {
   {
     ProfScope ps(net->ctx, "split16");
     B200_LAUNCH(prep_w16_kernel, j0.nblocks + j1.nblocks + j2.nblocks + (chain.nl > 0 ? chain.nctas : 0), 1024, 0, net->ctx->stream, j0,
-                j1, j2, net->spec_st, net->spec_flag, chain, sync);
+                j1, j2, net->spec_st, net->spec_flag, chain, sync, net->ctx->h_scalars + kHostErrSlot);
   }
   net->w16_params = params;
   return B200_OK;
@@ -1522,10 +1523,13 @@ int wide_gemm(b200_net *net, const WideGemm &g) {
 
 } // namespace
 
-bool wide16_applicable(const b200_net *net, int l, int role) {
+bool wide16_applicable(const b200_net *net, int l, int role, long batch) {
   if (!env().wide16 || net->prec != B200_PREC_TF32X3 || net->m16.on) return false;
   const int K = net->dims[l], N = net->dims[l + 1];
   if (K < 256 || N < 256 || N % 128 != 0) return false;
+  // below ~1e9 multiply-adds a GEMM is launch- and latency-bound (S-LBFGS mini-batches on the 256-wide pair network): the two
+  // extra launches of an operand split cost more than the tensor time saved (B200_WIDE16_MIN, in multiply-adds)
+  if ((double)batch * K * N < (double)env().wide16_min) return false;
   if (l == 0 && fwd16_shape_ok(net)) return false;
   if (role == 1 && (l == 0 || K % 128 != 0 || net->ldd[l - 1] % 4 != 0)) return false; // (dX: the output tile is 128 columns of delta_{l-1})
   return true;
@@ -1571,11 +1575,11 @@ int wide16_dx_layer(b200_net *net, int l, const float *params, long batch) {
 // The layer below a skinny last layer (out <= 12): its delta pair straight from delta_L, W_L and act'(A_{L-1}) — replaces the last
 // layer's dX GEMM + activation_deriv (src/cuda/layer.cuh:89-103), whose fp32 result (2 GB at configs[4]'s per-GPU share) would be
 // written only to be read back twice (maximum, split).
-bool wide16_last_dx_applicable(const b200_net *net) {
+bool wide16_last_dx_applicable(const b200_net *net, long batch) {
   const int L = net->nlayers();
   if (L < 2 || net->dims[L] > kGenMaxOut || !env().wide16 || (env().wide16 & 2)) return false; // (B200_WIDE16=3: separate dX + split)
   const int l = L - 2;
-  return wide16_applicable(net, l, 2) && (l == 0 || wide16_applicable(net, l, 1));
+  return wide16_applicable(net, l, 2, batch) && (l == 0 || wide16_applicable(net, l, 1, batch));
 }
 
 int wide16_last_dx(b200_net *net, const float *params, long batch) {

@@ -747,7 +747,7 @@ int tc_forward_layer(b200_net *net, int l, const float *params, const float *in,
   *done = false;
   if (fused) *fused = false;
   if (!(tc_mask() & 1)) return B200_OK;
-  if (wide16_applicable(net, l, 0)) { // wide layer: both operands as fp16 pairs on the CTA-pair kernel (gemm_fwd16.cu)
+  if (wide16_applicable(net, l, 0, batch)) { // wide layer: both operands as fp16 pairs on the CTA-pair kernel (gemm_fwd16.cu)
     B200_TRY(wide16_forward_layer(net, l, params, in, batch));
     *done = true;
     return B200_OK;
@@ -816,7 +816,7 @@ int tc_dx_layer(b200_net *net, int l, const float *params, long batch, bool *don
   const bool want16 = emit16 && *emit16 && net->delta16 && net->scale16;
   if (emit16) *emit16 = false;
   if (!(tc_mask() & 2)) return B200_OK;
-  if (wide16_applicable(net, l, 1)) {
+  if (wide16_applicable(net, l, 1, batch)) {
     B200_TRY(wide16_dx_layer(net, l, params, batch));
     *done = true;
     return B200_OK;
@@ -882,7 +882,7 @@ int tc_dw_plan(b200_net *net, int l, long batch, int *splits) {
 int tc_dw_layer(b200_net *net, int l, const float *in, long batch, bool *done) {
   *done = false;
   if (!(tc_mask() & 4)) return B200_OK;
-  if (wide16_applicable(net, l, 2) && (reinterpret_cast<uintptr_t>(net->partials + net->part_off[l]) & 15u) == 0) {
+  if (wide16_applicable(net, l, 2, batch) && (reinterpret_cast<uintptr_t>(net->partials + net->part_off[l]) & 15u) == 0) {
     B200_TRY(wide16_dw_layer(net, l, in, batch));
     *done = true;
     return B200_OK;

@@ -803,7 +803,7 @@ int net_eval(b200_net *net, const float *params, const float *x, const float *t,
         d16_ready = true;
         done = true;
       }
-      if (!done && l == L - 1 && net->prec == B200_PREC_TF32X3 && wide16_last_dx_applicable(net)) {
+      if (!done && l == L - 1 && net->prec == B200_PREC_TF32X3 && wide16_last_dx_applicable(net, batch)) {
         B200_TRY(wide16_last_dx(net, params, batch)); // delta_{L-1} only as the fp16 pair the wide kernels of layer L-1 read
         done = true;
       }
@@ -1132,7 +1132,7 @@ int b200_net_loss_grad(b200_net *net, const float *x_dev, const float *t_dev, lo
   B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
   if (loss_host) *loss_host = (float)ctx->h_scalars[0];
-  return B200_OK;
+  return ctx_check_device_error(ctx); // (a device-side wait that gave up during this evaluation)
 }
 
 int b200_net_copy_output_to_host(b200_net *net, float *host, size_t n) {

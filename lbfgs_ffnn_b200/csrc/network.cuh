@@ -230,13 +230,13 @@ __device__ __forceinline__ void chain_cw_block(const ChainW &c, int cta, float *
 #endif
 void tail_release(b200_net *net);
 // wide hidden layers on the fp16 pair kernels (b200_net::Wide16, gemm_fwd16.cu). role: 0 forward, 1 dX, 2 dW
-bool wide16_applicable(const b200_net *net, int l, int role);
+bool wide16_applicable(const b200_net *net, int l, int role, long batch);
 void wide16_begin(b200_net *net); // start of an evaluation: no operand has been split yet
 int wide16_forward_layer(b200_net *net, int l, const float *params, const float *in, long batch);
 int wide16_dx_layer(b200_net *net, int l, const float *params, long batch);
 int wide16_dw_layer(b200_net *net, int l, const float *in, long batch);
 // the delta pair of the layer below a skinny last layer, generated from delta_L (no fp32 delta_{L-1} is written)
-bool wide16_last_dx_applicable(const b200_net *net);
+bool wide16_last_dx_applicable(const b200_net *net, long batch);
 int wide16_last_dx(b200_net *net, const float *params, long batch);
 void wide16_release(b200_net *net);
 // the reference CPU backend's random-mini-batch SGD (src/minimizer/s_gd.hpp:63-170) on the GPU (slbfgs.cu: shares the sampler

@@ -422,7 +422,7 @@ int b200_slbfgs_solve(b200_ctx *ctx, b200_net *net, int n, float *params, const 
     B200_TRY(net_eval(net, w, x_shard, t_shard, shard_N, N, g, (EvalOut *)net->eval_out));
     B200_CUDA(cudaMemcpyAsync(h_mail, net->eval_out, sizeof(EvalOut), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    return B200_OK;
+    return ctx_check_device_error(ctx);
   };
 
   bool have_u_prev = false;   // !u_list.empty()

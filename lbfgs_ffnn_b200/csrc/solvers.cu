@@ -492,7 +492,7 @@ int b200_lbfgs_run(b200_lbfgs *s, b200_net *net, b200_loss_grad_fn fn, void *use
         if (!(ls == 0 && first_eval_issued)) B200_TRY(obj.eval_async(params, g_new, mail, &cb_loss));
         if (ls == 0 && spec_in_flight) B200_CUDA(cudaEventSynchronize(s->ev[s->cur])); // only THIS iteration's graph
         else B200_CUDA(cudaStreamSynchronize(st));
-        if (ctx->world > 1) B200_TRY(ctx_check_device_error(ctx));
+        B200_TRY(ctx_check_device_error(ctx));
         if (ls == 0) { alpha = (double)(float)mr->hdr.alpha0; gdotp = mr->hdr.gdotp; }
         loss_new = net ? mr->loss : cb_loss;
         gnorm2_new = mr->gnorm2;
@@ -772,7 +772,7 @@ int b200_gd_solve(b200_ctx *ctx, b200_net *net, b200_loss_grad_fn fn, void *user
     else B200_TRY(launch_axpy(N, -o.lr, grad, params, st));                                             // :83-84
     B200_TRY(obj.eval_async(params, grad, mail, &cb_loss));
     B200_CUDA(cudaStreamSynchronize(st));
-    if (ctx->world > 1) B200_TRY(ctx_check_device_error(ctx));
+    B200_TRY(ctx_check_device_error(ctx));
     loss = net ? mail->loss : cb_loss;
     gnorm = std::sqrt(mail->gnorm2);
     B200_TRY(timer.stop());

@@ -34,11 +34,12 @@ def _problem(oracle, dims, acts, batch, seed=5):
 
 
 def _eval(handle, dims, acts, w, X, T, env=None, launches=False):
-    keys = ("B200_WIDE16", "B200_WIDE_CHUNK")
+    keys = ("B200_WIDE16", "B200_WIDE_CHUNK", "B200_WIDE16_MIN")
     saved = {k: os.environ.get(k) for k in keys}
     try:
         for k in keys:
             os.environ.pop(k, None)
+        os.environ["B200_WIDE16_MIN"] = "0"  # (by default GEMMs below 2^30 multiply-adds stay on the generic kernels)
         for k, v in (env or {}).items():
             os.environ[k] = v
         P.api.reload_env()
@@ -122,17 +123,36 @@ def test_wide_evaluation_is_bit_reproducible(handle, oracle):
         assert loss == ref[0] and np.array_equal(g, ref[1])
 
 
+def test_small_gemms_stay_on_the_generic_kernels(handle, oracle):
+    """the default threshold (B200_WIDE16_MIN = 2^30 multiply-adds): a 1000-sample evaluation of a 256-wide net launches exactly what
+    it launches with the wide path switched off"""
+    dims, acts = NETS[0]
+    onet, w, X, T = _problem(oracle, dims, acts, 1000)
+    a = _eval(handle, dims, acts, w, X, T, env={"B200_WIDE16_MIN": str(1 << 30)}, launches=True)
+    b = _eval(handle, dims, acts, w, X, T, env={"B200_WIDE16": "0"}, launches=True)
+    assert a[4] == b[4] and np.array_equal(a[1], b[1])
+
+
 def test_lbfgs_on_a_wide_net_follows_the_oracle(handle, oracle):
     """five L-BFGS iterations (reference CUDA policy: Armijo) on a wide net: the loss trajectory of the fp64 oracle within 1e-3"""
     dims, acts = [784, 512, 256, 10], ["relu", "relu", "linear"]
     onet, w, X, T = _problem(oracle, dims, acts, 2000)
-    net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
-    dx, dt = upload(X), upload(T)
-    net.quantize_input(dx, 2000)
-    s = P.CudaLBFGS(handle)
-    s.setMemory(10); s.setMaxIterations(5); s.setTolerance(0.0)
-    rec = P.IterationRecorder(); rec.init(5); s.setRecorder(rec)
-    s.solve(net.params_size(), net.params_data(), dx, dt, 2000, net)
+    os.environ["B200_WIDE16_MIN"] = "0"
+    P.api.reload_env()
+    try:
+        net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
+        dx, dt = upload(X), upload(T)
+        net.quantize_input(dx, 2000)
+        s = P.CudaLBFGS(handle)
+        s.setMemory(10); s.setMaxIterations(5); s.setTolerance(0.0)
+        rec = P.IterationRecorder(); rec.init(5); s.setRecorder(rec)
+        n0 = P.api.launch_count()
+        s.solve(net.params_size(), net.params_data(), dx, dt, 2000, net)
+        launches = P.api.launch_count() - n0
+        l, _, _ = rec.copy_to_host()
+    finally:
+        os.environ.pop("B200_WIDE16_MIN", None)
+        P.api.reload_env()
     ref = onet.lbfgs(w, X, T, m=10, max_iters=5, tol=0.0, policy="cuda")
-    l, _, _ = rec.copy_to_host()
     assert np.allclose(l, ref["loss"], rtol=1e-3), (l, ref["loss"])
+    assert launches > 0

@@ -5,6 +5,7 @@ import os, sys, json, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
+os.environ.setdefault("B200_WIDE16_MIN", "0")  # small shapes too
 import lbfgs_ffnn_b200 as P
 from oracle import binding as ob
 from helpers import make_gpu_net, upload
