@@ -1247,7 +1247,7 @@ struct WideGen {
   int act;
 };
 template <bool GEN>
-__global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict__ x, long rows, int cols, long ld, const float *__restrict__ part,
+__global__ void __launch_bounds__(256, 3) wide_split_kernel(const float *__restrict__ x, long rows, int cols, long ld, const float *__restrict__ part,
                                                        int npart, __half *__restrict__ P, int Cp, __half *__restrict__ PT, long Rp, int ones,
                                                        float *__restrict__ scal, const SpecState *spec_st, int spec, const WideGen gen) {
   pdl_enter();
@@ -1291,55 +1291,69 @@ __global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict
   const int tr_ = threadIdx.x >> 4, tc4 = (threadIdx.x & 15) * 4;
   const bool vec = (cols % 4 == 0) && (GEN ? ((reinterpret_cast<uintptr_t>(gen.a) & 15u) == 0)
                                            : (ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0));
-  float wl[GEN ? 4 : 1][GEN ? kGenMaxOut : 1];
+  // GEN: the last layer's weights of this CTA's 64 columns (once) and delta_L of the tile's 64 rows (per tile) in shared memory,
+  // [.][out] padded to 13 floats; a thread's 4 x 4 values are then 16 accumulators fed by 8 shared-memory loads per output j
+  // (output-major: a thread's four columns / four rows of one output j are ONE conflict-free 16-byte load)
+  __shared__ __align__(16) float wls[GEN ? kGenMaxOut : 1][GEN ? 64 : 1], dls[GEN ? kGenMaxOut : 1][GEN ? 64 : 1];
   if constexpr (GEN) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < kGenMaxOut; ++j)
-        wl[k][j] = (j < gen.out && c0 + tc4 + k < cols) ? __ldg(gen.Wl + (long)(c0 + tc4 + k) * gen.out + j) : 0.0f;
+    for (int e = threadIdx.x; e < 64 * kGenMaxOut; e += 256) {
+      const int c = e / kGenMaxOut, j = e - c * kGenMaxOut;
+      wls[j][c] = (j < gen.out && c0 + c < cols) ? __ldg(gen.Wl + (long)(c0 + c) * gen.out + j) : 0.0f;
+    }
   }
-  const bool dl_vec = GEN && gen.out == kGenMaxOut && gen.ldl == kGenMaxOut && (reinterpret_cast<uintptr_t>(gen.dl) & 15u) == 0;
+  // this thread's 4 x 4 values of tile row rb (zero past the edges); the loads of the NEXT tile are issued before the current one is
+  // processed, so a thread always has a tile's worth of loads in flight
+  auto load_tile = [&](long rb, float4 (&dst)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long r = rb * 64 + 4 * tr_ + i;
+      const float *src = GEN ? gen.a + r * (long)cols + c0 + tc4 : x + r * ld + c0 + tc4;
+      if (r < rows && vec && c0 + tc4 + 3 < cols) dst[i] = __ldg(reinterpret_cast<const float4 *>(src));
+      else {
+        dst[i].x = (r < rows && c0 + tc4 + 0 < cols) ? __ldg(src + 0) : 0.0f;
+        dst[i].y = (r < rows && c0 + tc4 + 1 < cols) ? __ldg(src + 1) : 0.0f;
+        dst[i].z = (r < rows && c0 + tc4 + 2 < cols) ? __ldg(src + 2) : 0.0f;
+        dst[i].w = (r < rows && c0 + tc4 + 3 < cols) ? __ldg(src + 3) : 0.0f;
+      }
+    }
+  };
+  float4 nxt[4];
+  if ((long)(blockIdx.x / tiles_c) < tiles_r) load_tile(blockIdx.x / tiles_c, nxt);
   for (long rb = blockIdx.x / tiles_c; rb < tiles_r; rb += G) {
     const long r0 = rb * 64;
     float v[4][4];
-    { // the tile's values, every load of the thread in flight together
+    {
       float4 raw[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long r = r0 + 4 * tr_ + i;
-        const float *src = GEN ? gen.a + r * (long)cols + c0 + tc4 : x + r * ld + c0 + tc4;
-        if (r < rows && vec && c0 + tc4 + 3 < cols) raw[i] = __ldg(reinterpret_cast<const float4 *>(src));
-        else {
-          raw[i].x = (r < rows && c0 + tc4 + 0 < cols) ? __ldg(src + 0) : 0.0f;
-          raw[i].y = (r < rows && c0 + tc4 + 1 < cols) ? __ldg(src + 1) : 0.0f;
-          raw[i].z = (r < rows && c0 + tc4 + 2 < cols) ? __ldg(src + 2) : 0.0f;
-          raw[i].w = (r < rows && c0 + tc4 + 3 < cols) ? __ldg(src + 3) : 0.0f;
-        }
-      }
+      for (int i = 0; i < 4; ++i) raw[i] = nxt[i];
+      if (rb + G < tiles_r) load_tile(rb + G, nxt);
       if constexpr (GEN) {
+        for (int e = threadIdx.x; e < 64 * kGenMaxOut; e += 256) { // delta_L of the tile's rows (zero past the batch / past `out`)
+          const int rr = e / kGenMaxOut, j = e - rr * kGenMaxOut;
+          dls[j][rr] = (j < gen.out && r0 + rr < rows) ? __ldg(gen.dl + (r0 + rr) * gen.ldl + j) : 0.0f;
+        }
+        __syncthreads(); // (also orders the first tile after the staging of wls)
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][k] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kGenMaxOut; ++j) {
+          const float4 d4 = *reinterpret_cast<const float4 *>(&dls[j][4 * tr_]), w4 = *reinterpret_cast<const float4 *>(&wls[j][tc4]);
+          const float d[4] = {d4.x, d4.y, d4.z, d4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(d[i], wv[k], acc[i][k]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const long r = r0 + 4 * tr_ + i;
-          float dl[kGenMaxOut];
-          if (dl_vec && r < rows) {
-#pragma unroll
-            for (int j4 = 0; j4 < kGenMaxOut / 4; ++j4) {
-              const float4 d4 = __ldg(reinterpret_cast<const float4 *>(gen.dl + r * gen.ldl) + j4);
-              dl[4 * j4] = d4.x; dl[4 * j4 + 1] = d4.y; dl[4 * j4 + 2] = d4.z; dl[4 * j4 + 3] = d4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kGenMaxOut; ++j) dl[j] = (j < gen.out && r < rows) ? __ldg(gen.dl + r * gen.ldl + j) : 0.0f;
-          }
-          const float av[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+          const float av[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w}; // (zero past the edges: act' of it times a zero sum)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int j = 0; j < kGenMaxOut; ++j) acc = fmaf(dl[j], wl[k][j], acc);
-            const bool ok = r < rows && c0 + tc4 + k < cols;
-            v[i][k] = ok ? acc * act_deriv_from_output(gen.act, av[k]) * S : 0.0f;
+            const bool ok = r0 + 4 * tr_ + i < rows && c0 + tc4 + k < cols;
+            v[i][k] = ok ? acc[i][k] * act_deriv_from_output(gen.act, av[k]) * S : 0.0f;
           }
         }
       } else {
@@ -1380,6 +1394,8 @@ __global__ void __launch_bounds__(256) wide_split_kernel(const float *__restrict
         *reinterpret_cast<uint4 *>(q + Rp + 8) = *reinterpret_cast<const uint4 *>(&tl[col][seg + 8]);
       }
       __syncthreads();
+    } else if constexpr (GEN) {
+      __syncthreads(); // dls is refilled by the next tile
     }
   }
   if (PT && ones) { // row `cols` of the transpose: unscaled ones over the valid rows (the bias-gradient row of the dW GEMM)
