@@ -73,6 +73,8 @@ struct F16Params {
   // WIDE
   int n_tiles;               // tiles of BN output columns (units = sample-tile pairs x n_tiles, n fastest)
   int k_chunk;               // K blocks accumulated in TMEM before the epilogue warps add them to their fp32 registers
+  int k_slices, kb_per_slice; // split-K: a unit is (tile pair, column tile, slice of the contraction); slice s is stored at index s of
+                             // the third dimension of the output map (the dW of a layer with few output tiles: one partial per slice)
   const float *sa_inv, *sb_inv; // device scalars: 1 / scale of the A pair, 1 / scale of the B pair
   const float *aux32;        // dX: A_prev as fp32 rows (act' is taken from it), else nullptr
   long ld_aux;
@@ -167,10 +169,13 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int n_tiles = WIDE ? p.n_tiles : 1;
-  const int units = (PAIR ? (p.tiles + 1) >> 1 : p.tiles) * n_tiles;
-  auto tile_of = [&](int unit) { return WIDE ? 2 * (unit / n_tiles) + (int)rank : (PAIR ? 2 * unit + (int)rank : unit); };
-  auto nt_of = [&](int unit) { return WIDE ? unit % n_tiles : 0; };
+  const int n_tiles = WIDE ? p.n_tiles : 1, k_slices = WIDE ? p.k_slices : 1;
+  const int units = (PAIR ? (p.tiles + 1) >> 1 : p.tiles) * n_tiles * k_slices;
+  auto tile_of = [&](int unit) { return WIDE ? 2 * (unit / (n_tiles * k_slices)) + (int)rank : (PAIR ? 2 * unit + (int)rank : unit); };
+  auto nt_of = [&](int unit) { return WIDE ? (unit / k_slices) % n_tiles : 0; };
+  auto ks_of = [&](int unit) { return WIDE ? unit % k_slices : 0; };
+  auto kb_lo_of = [&](int unit) { return WIDE ? ks_of(unit) * p.kb_per_slice : 0; };
+  auto kb_hi_of = [&](int unit) { return WIDE ? min(p.k_blocks, (ks_of(unit) + 1) * p.kb_per_slice) : p.k_blocks; };
   constexpr int kNC = NS, kNW = NW;
   static_assert(2 * kNC + 2 * kNW + 9 <= 64, "barrier table");
   extern __shared__ uint8_t smem_raw[];
@@ -254,7 +259,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           }
           __syncwarp();
         }
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb_lo_of(unit), kb_hi = kb_hi_of(unit); kb < kb_hi; ++kb) {
           mbar_wait(conv_empty(s), ph ^ 1);
           if (elect_one()) {
             if (p.diag & 1) { if (leader) mbar_arrive(conv_full(s)); }
@@ -284,7 +289,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       uint32_t ph = 0;
       for (int unit = unit0; unit < units; unit += unit_step) {
         const int wrow0 = nt_of(unit) * BN; // (WIDE: the rows of the B operand of this unit's column tile)
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb_lo_of(unit), kb_hi = kb_hi_of(unit); kb < kb_hi; ++kb) {
           mbar_wait(w_empty(s), ph ^ 1);
           if (elect_one()) {
             if (p.diag & 2) { if (leader) mbar_arrive(w_full(s)); }
@@ -323,14 +328,15 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         // fp32 registers (round to nearest) by the epilogue warps while the next chunk runs in the other buffer.
         int cnt = 0;
         for (int unit = unit0; unit < units; unit += unit_step) {
-          for (int kb0 = 0; kb0 < p.k_blocks; kb0 += p.k_chunk, ++cnt) {
+          const int kb_hi = kb_hi_of(unit);
+          for (int kb0 = kb_lo_of(unit); kb0 < kb_hi; kb0 += p.k_chunk, ++cnt) {
             const int buf = cnt & 1;
             const uint32_t d_acc = tmem_base + (uint32_t)(buf * 2 * BN);
             const long long tt0 = p.dbg ? clock64() : 0;
             mbar_wait(tm_empty(buf), ((cnt >> 1) & 1) ^ 1);
             if (p.dbg) waited_tm += clock64() - tt0;
             tc_fence_after();
-            const int kb1 = min(p.k_blocks, kb0 + p.k_chunk);
+            const int kb1 = min(kb_hi, kb0 + p.k_chunk);
             for (int kb = kb0; kb < kb1; ++kb) {
               const long long t0 = p.dbg ? clock64() : 0;
               mbar_wait(conv_full(cs), cph);
@@ -425,7 +431,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           for (int i = 0; i < BN / 64; ++i)
 #pragma unroll
             for (int j = 0; j < 32; ++j) accr[i][j] = 0.0f;
-          for (int kb0 = 0; kb0 < p.k_blocks; kb0 += p.k_chunk, ++cnt) {
+          for (int kb0 = kb_lo_of(unit), kb_hi = kb_hi_of(unit); kb0 < kb_hi; kb0 += p.k_chunk, ++cnt) {
             const int buf = cnt & 1;
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(tm_full(buf), (cnt >> 1) & 1);
@@ -474,7 +480,7 @@ fwd16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmOut, stage_a, col0, tile * kFM + q * 32);
+              tma_store_3d(&tmOut, stage_a, col0, tile * kFM + q * 32, ks_of(unit));
               tma_store_commit();
             }
           }
@@ -879,14 +885,14 @@ int make_map_2d(CUtensorMap *tm, CUtensorMapDataType dt, const void *ptr, unsign
 // fp16 {dim0 contiguous, dim1, dim2}, strides in bytes for dim1 / dim2, box {box0, box1, box2}
 int make_map_3d_ex(CUtensorMap *tm, const void *ptr, unsigned long long dim0, unsigned long long dim1, unsigned long long dim2,
                    unsigned long long stride1, unsigned long long stride2, unsigned box0, unsigned box1, unsigned box2,
-                   CUtensorMapSwizzle sw) {
+                   CUtensorMapSwizzle sw, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return B200_ERR_CUDA;
   cuuint64_t dims[3] = {dim0, dim1, dim2};
   cuuint64_t strides[2] = {stride1, stride2};
   cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+  const CUresult r = fn(tm, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d fp16) failed (%d): dims %llu x %llu x %llu strides %llu, %llu ptr %p", (int)r, dim0, dim1, dim2,
@@ -1477,9 +1483,13 @@ int wide_input(b200_net *net, int l, const float *in, long batch) {
   if (w.a_ready[l]) return B200_OK;
   const int K = net->dims[l];
   const long Kp = up64(K), Bp = up64(net->cap);
+  // layer 0 on an input the caller holds constant (Wide16::x_src): the split of an earlier evaluation is still there
+  const bool held = l == 0 && w.x_src == in && w.x_rows == batch;
+  if (l == 0 && (!held || w.a[0].halves < (size_t)net->cap * 2 * Kp || w.aT[0].halves < (size_t)(K + 1) * 2 * Bp)) w.x_done = false;
   B200_TRY(wide_buf(net, w.a[l], (size_t)net->cap * 2 * Kp));
   B200_TRY(wide_buf(net, w.aT[l], (size_t)(K + 1) * 2 * Bp));
-  B200_TRY(wide_split(net, in, batch, K, K, w.a[l].p, (int)Kp, w.aT[l].p, up64(batch), 1, w.scal + 8 * l));
+  if (!(held && w.x_done)) B200_TRY(wide_split(net, in, batch, K, K, w.a[l].p, (int)Kp, w.aT[l].p, up64(batch), 1, w.scal + 8 * l));
+  if (held) w.x_done = true;
   w.a_ready[l] = 1;
   return B200_OK;
 }
@@ -1504,9 +1514,10 @@ int wide_delta(b200_net *net, int l, long batch) {
 struct WideGemm {
   const void *A; long rows; const void *B; int ncols; long Kc;
   float *out; long ld_out;
+  int slices = 1; unsigned long long slice_stride = 0; // split-K: slice s of the contraction is stored at out + s * slice_stride
   const float *sa_inv, *sb_inv, *bias, *aux32; long ld_aux; int act, ones_row;
 };
-int wide_gemm(b200_net *net, const WideGemm &g) {
+int wide_gemm(b200_net *net, const WideGemm &g, int *slices_used = nullptr) {
   CUtensorMap tx, twh, twl, tout;
   // A: dims ordered so that the strides ascend {64 halves, 2 Kc / 64 blocks (128 B apart), rows}
   B200_TRY(make_map_3d_ex(&tx, g.A, 64, (unsigned long long)(2 * g.Kc / 64), (unsigned long long)g.rows, 128, (unsigned long long)2 * g.Kc * 2, 64, 1,
@@ -1515,9 +1526,13 @@ int wide_gemm(b200_net *net, const WideGemm &g) {
                        (unsigned long long)2 * g.Kc * 2, kFK, 128, CU_TENSOR_MAP_SWIZZLE_128B));
   B200_TRY(make_map_2d(&twl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (const __half *)g.B + g.Kc, (unsigned long long)g.Kc, (unsigned long long)g.ncols,
                        (unsigned long long)2 * g.Kc * 2, kFK, 128, CU_TENSOR_MAP_SWIZZLE_128B));
-  B200_TRY(make_map_2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, g.out, (unsigned long long)g.ncols, (unsigned long long)g.rows,
-                       (unsigned long long)g.ld_out * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  const int k_blocks = (int)(g.Kc / kFK);
+  const int kb_per_slice = ceil_div(k_blocks, std::max(1, g.slices)), slices = ceil_div(k_blocks, kb_per_slice); // (no empty slice)
+  B200_TRY(make_map_3d_ex(&tout, g.out, (unsigned long long)g.ncols, (unsigned long long)g.rows, (unsigned long long)slices,
+                          (unsigned long long)g.ld_out * 4, (slices > 1 ? g.slice_stride : (unsigned long long)g.rows * g.ld_out) * 4, 32, 32, 1,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
   F16Params p{};
+  p.k_slices = slices; p.kb_per_slice = kb_per_slice;
   p.rows_valid = (int)g.rows; p.cols_valid = g.ncols; p.k_total = (int)g.Kc;
   p.row0 = 0;
   p.k_blocks = (int)(g.Kc / kFK);
@@ -1532,8 +1547,9 @@ int wide_gemm(b200_net *net, const WideGemm &g) {
   p.sa_inv = g.sa_inv; p.sb_inv = g.sb_inv;
   p.aux32 = g.aux32; p.ld_aux = g.ld_aux;
   p.ones_row = g.ones_row;
-  const long units = (long)((p.tiles + 1) / 2) * p.n_tiles;
+  const long units = (long)((p.tiles + 1) / 2) * p.n_tiles * slices;
   const int grid = 2 * (int)std::min<long>(net->ctx->num_sms / 2, units);
+  if (slices_used) *slices_used = slices;
   return launch_fwd16<128, true, EPI_WIDE, 4, true, 4, true>(tx, twh, twl, tout, tout, p, grid, net->ctx->stream);
 }
 
@@ -1542,11 +1558,11 @@ int wide_gemm(b200_net *net, const WideGemm &g) {
 bool wide16_applicable(const b200_net *net, int l, int role, long batch) {
   if (!env().wide16 || net->prec != B200_PREC_TF32X3 || net->m16.on) return false;
   const int K = net->dims[l], N = net->dims[l + 1];
-  if (K < 256 || N < 256 || N % 128 != 0) return false;
+  if (K < 256 || N < 128 || N % 128 != 0) return false;
   // below ~1e9 multiply-adds a GEMM is launch- and latency-bound (S-LBFGS mini-batches on the 256-wide pair network): the two
   // extra launches of an operand split cost more than the tensor time saved (B200_WIDE16_MIN, in multiply-adds)
   if ((double)batch * K * N < (double)env().wide16_min) return false;
-  if (l == 0 && fwd16_shape_ok(net)) return false;
+  if (l == 0 && fwd16_shape_ok(net) && net->xq.valid) return false; // an 8-bit-pixel input: the exact-fp16 kernels of §3.1 take layer 0
   if (role == 1 && (l == 0 || K % 128 != 0 || net->ldd[l - 1] % 4 != 0)) return false; // (dX: the output tile is 128 columns of delta_{l-1})
   return true;
 }
@@ -1556,6 +1572,14 @@ void wide16_begin(b200_net *net) {
   std::fill(w.a_ready.begin(), w.a_ready.end(), 0);
   std::fill(w.w_ready.begin(), w.w_ready.end(), 0);
   std::fill(w.d_ready.begin(), w.d_ready.end(), 0);
+}
+
+// slices the partial buffer of layer l has room for (net_ensure sizes it for the FFMA / generic split-K plans)
+int wide16_dw_slices_cap(const b200_net *net, int l) {
+  const int L = net->nlayers();
+  const size_t per = (size_t)(net->dims[l] + 1) * net->dims[l + 1];
+  const size_t end = (l + 1 < L) ? net->part_off[l + 1] : net->partials_cap;
+  return (int)std::min<size_t>(64, (end - net->part_off[l]) / per);
 }
 
 // A_l = act(A_{l-1} W_l + b_l)
@@ -1636,8 +1660,15 @@ int wide16_dw_layer(b200_net *net, int l, const float *in, long batch) {
   g.out = net->partials + net->part_off[l]; g.ld_out = N;
   g.sa_inv = w.scal + 8 * l + 1; g.sb_inv = w.scal + 8 * l + 5;
   g.act = B200_ACT_LINEAR; g.ones_row = K;
-  B200_TRY(wide_gemm(net, g));
-  net->splits_used[l] = 1;
+  // few output tiles (a 128-wide layer 0: four units): slices of the samples fill the machine, one partial per slice, combined by
+  // finalize_grad_kernel like every other split-K; never more slices than the layer's partials were sized for (net_ensure)
+  const long out_units = (long)((ceil_div(K + 1, kFM) + 1) / 2) * (N / 128);
+  const int want = (int)std::min<long>(std::max<long>(1, (2L * (net->ctx->num_sms / 2)) / out_units), std::max<long>(1, g.Kc / kFK / 8));
+  g.slices = std::max(1, std::min(want, wide16_dw_slices_cap(net, l)));
+  g.slice_stride = (unsigned long long)(K + 1) * N;
+  int used = 1;
+  B200_TRY(wide_gemm(net, g, &used));
+  net->splits_used[l] = used;
   return B200_OK;
 }
 

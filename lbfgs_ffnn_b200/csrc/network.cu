@@ -552,6 +552,16 @@ void net_xq_clear(b200_net *net) {
   net->xq.user = false;
   net->xq.src = nullptr;
   net->xq.rows = 0;
+  net->w16x.x_src = nullptr;
+  net->w16x.x_rows = 0;
+  net->w16x.x_done = false;
+}
+
+// x is not (or cannot be checked to be) 8-bit pixels: remember that the caller holds it constant (b200_net::Wide16::x_src)
+static void net_hold_float_input(b200_net *net, const float *x, long batch) {
+  net->w16x.x_src = batch > 0 ? x : nullptr;
+  net->w16x.x_rows = batch;
+  net->w16x.x_done = false; // (a refresh re-splits: the buffer may hold new data)
 }
 
 int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) {
@@ -562,7 +572,10 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
   // uploaded new data to the same device buffer since the copy was made
   if (!cached) net_xq_clear(net);
   // TMA needs 16-byte row strides on the uint8 copy; float4 reads need an aligned source
-  if (in % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0 || batch <= 0) return B200_OK;
+  if (in % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15u) != 0 || batch <= 0) {
+    net_hold_float_input(net, x, batch);
+    return B200_OK;
+  }
   const size_t bytes = (size_t)batch * in;
   cudaStream_t st = net->ctx->stream;
   const int nb16 = (in + 1 + 63) / 64;
@@ -594,6 +607,7 @@ int net_quantize_input(b200_net *net, const float *x, long batch, bool refresh) 
   } else if (!ok && cached) {
     net_xq_clear(net); // the buffer no longer holds 8-bit pixel data
   }
+  if (!ok) net_hold_float_input(net, x, batch);
   return B200_OK;
 }
 

@@ -116,6 +116,11 @@ struct b200_net {
     float *scal = nullptr;    // device: per layer {S_a, 1/S_a, S_w, 1/S_w, S_d, 1/S_d, -, -}
     float *amax_part = nullptr; // device: per-CTA maxima of the matrix being split
     int amax_n = 0, scal_layers = 0;
+    // an input that net_quantize_input found NOT to be 8-bit pixels: the caller (a solver for the length of its run, or the user
+    // through b200_net_quantize_input) holds x[x_rows] constant, so layer 0's operand split is made once, not per evaluation
+    const float *x_src = nullptr;
+    long x_rows = 0;
+    bool x_done = false;
   } w16x;
 
   double *loss_part = nullptr; // per-CTA partials of sum diff^2

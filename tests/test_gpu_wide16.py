@@ -156,3 +156,57 @@ def test_lbfgs_on_a_wide_net_follows_the_oracle(handle, oracle):
     ref = onet.lbfgs(w, X, T, m=10, max_iters=5, tol=0.0, policy="cuda")
     assert np.allclose(l, ref["loss"], rtol=1e-3), (l, ref["loss"])
     assert launches > 0
+
+
+def _float_problem(oracle, dims, acts, batch):
+    """MNIST-shaped images plus sub-quantum noise: not 8-bit pixels, so the exact-fp16 kernels of layer 0 do not apply"""
+    onet, w, X, T = _problem(oracle, dims, acts, batch)
+    X = (X + np.float32(1e-3) * np.random.RandomState(7).rand(*X.shape).astype(np.float32)).astype(np.float32)
+    return onet, w, X, T
+
+
+@pytest.mark.parametrize("dims,acts", [([784, 128, 10], ["relu", "linear"]), ([784, 128, 64, 10], ["relu", "relu", "linear"])])
+@pytest.mark.parametrize("batch", [33, 3000])
+def test_float_input_takes_the_wide_kernels_for_a_128_wide_layer_0(handle, oracle, dims, acts, batch):
+    """a 128-wide first layer on an input that is not 8-bit pixels: forward as a wide GEMM with one column tile, dW as a split-K wide
+    GEMM (four output units: slices of the samples fill the machine, combined by the deterministic finalize kernel)"""
+    onet, w, X, T = _float_problem(oracle, dims, acts, batch)
+    loss, g, out, pattern, launches = _eval(handle, dims, acts, w, X, T, launches=True)
+    lo, go = onet.loss_grad_masked(w, X, T, pattern)
+    assert abs(loss - lo) <= 5e-6 * abs(lo), (dims, batch, loss, lo)
+    assert rel_l2(g, go) <= 1e-5, (dims, batch, rel_l2(g, go))
+    K, N = dims[0], dims[1]
+    assert rel_l2(g[:K * N], go[:K * N]) <= 1e-5 and rel_l2(g[K * N:(K + 1) * N], go[K * N:(K + 1) * N]) <= 1e-5
+    _, g0, _, _, launches0 = _eval(handle, dims, acts, w, X, T, env={"B200_WIDE16": "0"}, launches=True)
+    assert launches > launches0 and rel_l2(g, g0) <= 1e-5
+
+
+def test_held_float_input_is_split_once(handle, oracle):
+    """b200_net_quantize_input on an input that is not 8-bit pixels: the caller holds it constant, so layer 0's operand split is made by
+    the first evaluation only; an evaluation on other data in between invalidates it"""
+    dims, acts = [784, 128, 10], ["relu", "linear"]
+    onet, w, X, T = _float_problem(oracle, dims, acts, 2000)
+    os.environ["B200_WIDE16_MIN"] = "0"
+    P.api.reload_env()
+    try:
+        net = make_gpu_net(handle, dims, acts, w, precision="tf32x3")
+        dx, dt = upload(X), upload(T)
+        assert net.quantize_input(dx, 2000) is False
+        counts, grads = [], []
+        for _ in range(3):
+            n0 = P.api.launch_count()
+            net.compute_loss_and_grad(dx, dt, 2000)
+            counts.append(P.api.launch_count() - n0)
+            grads.append(net.get_grads().copy())
+        assert counts[1] == counts[2] == counts[0] - 2, counts  # (maximum + split of X: first evaluation only)
+        assert np.array_equal(grads[0], grads[1]) and np.array_equal(grads[0], grads[2])
+        X2 = np.ascontiguousarray(X[::-1])
+        dx2, dt2 = upload(X2), upload(np.ascontiguousarray(T[::-1]))
+        net.compute_loss_and_grad(dx2, dt2, 2000)  # other data through the same buffers
+        n0 = P.api.launch_count()
+        net.compute_loss_and_grad(dx, dt, 2000)
+        assert P.api.launch_count() - n0 == counts[0]  # split again
+        assert np.array_equal(net.get_grads(), grads[0])
+    finally:
+        os.environ.pop("B200_WIDE16_MIN", None)
+        P.api.reload_env()
