@@ -59,6 +59,8 @@ void env_reload() {
   e.dw_bn = num("B200_DW_BN", 0);
   if (const char *s = std::getenv("B200_P2P_SPIN_LIMIT")) e.p2p_spin_limit = std::atol(s);
   if (const char *s = std::getenv("B200_WIDE16_MIN")) e.wide16_min = std::atol(s);
+  if (const char *s = std::getenv("B200_DOTS_BULK")) e.dots_bulk = std::atoi(s);
+  if (const char *s = std::getenv("B200_DOTS_BULK_MIN")) e.dots_bulk_min = std::atol(s);
   g_env = e;
 }
 const EnvFlags &env() {

@@ -1,6 +1,7 @@
 // Kernels of the compact-form L-BFGS direction and the fused line-search vector operations.
 // See lbfgs_kernels.cuh for the algebra and the reference lines each kernel replaces.
 #include "lbfgs_kernels.cuh"
+#include "tc_ptx.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -199,6 +200,287 @@ template <int RPW, bool PAIR>
 __global__ void __launch_bounds__(kDotsThreads) lbfgs_dots_kernel(const DotsArgs a) {
   pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   dots_body<RPW, PAIR>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1b) the same batched GEMV for LONG vectors (BASELINE configs[4]: n = 2·10⁷, m = 20 — the history no longer fits L2 and
+// the pass is HBM-bound). dots_body keeps its loads in registers: at three rows per warp the compiler holds 48 16-byte loads per
+// lane (255 registers, one CTA of 8 warps per SM), and the warps of a CTA load and compute in lockstep between the per-tile
+// barriers — 2.4 TB/s (measured with the ring full: 1 550 µs for 3.7 GB). Here the bytes in flight do not depend on registers:
+// four producer warps (one per scheduler) stream every ring row's 1 KB chunk of a 256-element tile (plus g and, when the pair is
+// formed, x / x_prev / g_prev) into a shared-memory ring with plain bulk async copies (cp.async.bulk, completion counted on an
+// mbarrier); the consumer warps own the same ring rows as in dots_body (row = warp, warp + 8, ...), HS warps per row group
+// with 256 / HS elements of the tile each, and keep g / s_new / y_new of their positions in registers as doubles across their
+// rows. Per-CTA partials in the layout of dots_body, so the solve kernel does not know which of the two ran. Needs 16-byte
+// aligned rows (the `vec` condition of dots_body); the up to three elements past the last multiple of four are added by lane 0
+// of the first warp of every row group from global memory.
+// Measured at n = 2·10⁷, m = 20, ring full (B200_DIAG=1024 prints where the warps of CTA 0 wait): one producer warp next to two
+// busy consumer warps issued a copy per 75 clk — 3 500 clk per 46 KB stage, twice what HBM needs; four producers: the copies
+// alone (B200_DIAG=256) run at 8.0 TB/s.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkTile = 256;                  // floats per row per stage
+constexpr int kBulkSlot = kBulkTile * 4;        // bytes of one row chunk
+constexpr int kBulkProducers = 4;               // producer warps (one per scheduler of the SM)
+constexpr int kBulkMaxStages = 8;
+constexpr int kBulkVecSlots = 4;                // g, x, x_prev, g_prev
+__host__ __device__ constexpr int bulk_threads(int hs) { return kDotsThreads * hs + 32 * kBulkProducers; }
+
+template <int RPW, bool PAIR, int HS>
+__global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(const DotsArgs a, int stages, int stage_slots, int nparts, int diag) {
+  pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
+  constexpr int kCW = kDotsWarps * HS;  // consumer warps
+  constexpr int kPos = 2 / HS;          // 16-byte positions of a tile row per lane
+  constexpr int kE = 4 * kPos;          // elements per lane and tile row
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  __shared__ __align__(8) uint64_t bars[2 * kBulkMaxStages];
+  __shared__ int sh_rows[kMaxSlots];
+  __shared__ int sh_nrows, sh_w, sh_wri;
+  __shared__ double sh_half[HS == 2 ? 2 * RPW * kDotsWarps * kDotsCols : 1];
+  __shared__ double sh_gg[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp % kDotsWarps, wh = warp / kDotsWarps; // consumers: row group, part of the tile
+  const int mp = a.st.h->mp, mod = a.st.h->mod;
+  const bool form = PAIR && a.mode == DOTS_FORM_PAIR;
+  if (tid == 0) {
+    int head = a.st.h->head, count = a.st.h->count;
+    if (a.reset_first) head = count = 0;
+    const int w = head;
+    int nr = 0, wri = -1;
+    for (int p = 0; p < mod; ++p) {
+      int rel = (p - (head - count)) % mod;
+      if (rel < 0) rel += mod;
+      const bool valid = rel < count;
+      if (valid || (PAIR && p == w)) {
+        if (p == w) wri = nr;
+        sh_rows[nr++] = p;
+      }
+    }
+    sh_nrows = nr;
+    sh_w = w;
+    sh_wri = wri;
+    for (int s = 0; s < stages; ++s) {
+      tcx::mbar_init(tcx::smem_u32(&bars[s]), kBulkProducers);            // full: the producers' arrives + the bytes of the copies
+      tcx::mbar_init(tcx::smem_u32(&bars[kBulkMaxStages + s]), kCW);      // empty: one arrive per consumer warp
+    }
+    tcx::fence_mbar_init();
+  }
+  // a short last tile leaves the end of its chunks as they were: zeros or earlier (finite) history values, never uninitialised
+  // shared memory, so masking g / s_new / y_new is enough
+  const int stage_bytes = stage_slots * kBulkSlot;
+  for (int i = tid; i < stages * stage_bytes / 16; i += bulk_threads(HS)) reinterpret_cast<float4 *>(bulk_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  tcx::fence_async_smem();
+  __syncthreads();
+  const int nrows = sh_nrows, w = sh_w, wri = sh_wri;
+  const size_t n4 = a.n & ~(size_t)3;
+  const size_t ntiles = (n4 + kBulkTile - 1) / kBulkTile;
+  const uint32_t smem0 = tcx::smem_u32(bulk_smem);
+
+  double acc[RPW][kDotsCols];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int c = 0; c < kDotsCols; ++c) acc[r][c] = 0.0;
+  double gg = 0.0;
+  long long dbg_wait = 0, dbg_work = 0, dbg_n = 0; // (B200_DIAG 1024: where the warps of CTA 0 wait)
+
+  if (warp >= kCW) { // ---- producers: one copy per lane, the same slot for the whole kernel ----
+    const int nvec = form ? kBulkVecSlots : 1;
+    const int skip = form ? wri : -1; // the row being formed holds last round's pair: not loaded
+    const int c = (warp - kCW) + kBulkProducers * lane;
+    bool active = c < kBulkVecSlots + 2 * nrows;
+    const float *src = nullptr;
+    if (active) {
+      if (c < kBulkVecSlots) {
+        active = c < nvec;
+        src = c == 0 ? a.g : c == 1 ? a.x : c == 2 ? a.x_prev : a.g_prev;
+      } else {
+        const int ri = (c - kBulkVecSlots) >> 1;
+        active = ri != skip && !(diag & 512); // (B200_DIAG 512: timing without the row copies)
+        src = (((c - kBulkVecSlots) & 1) ? a.Y : a.S) + (size_t)sh_rows[ri] * a.ld;
+      }
+    }
+    const uint32_t nact = (uint32_t)__popc(__ballot_sync(0xffffffffu, active));
+    int it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      const long long tw0 = (diag & 1024) ? clock64() : 0;
+      tcx::mbar_wait(tcx::smem_u32(&bars[kBulkMaxStages + s]), ph ^ 1u);
+      if (diag & 1024) { dbg_wait += clock64() - tw0; ++dbg_n; }
+      const size_t base = tile * kBulkTile;
+      const uint32_t bytes = (n4 - base < (size_t)kBulkTile ? (uint32_t)(n4 - base) : (uint32_t)kBulkTile) * 4u;
+      const uint32_t full = tcx::smem_u32(&bars[s]);
+      if (lane == 0) tcx::mbar_expect_tx(full, bytes * nact);
+      __syncwarp();
+      if (active) tcx::bulk_load_1d(smem0 + (uint32_t)(s * stage_bytes + c * kBulkSlot), src + base, bytes, full);
+      if (diag & 1024) { __syncwarp(); dbg_work += clock64() - tw0; }
+    }
+    if ((diag & 1024) && blockIdx.x == 0 && lane == 0)
+      printf("[dots_bulk] producer warp %d: %lld stages, %lld clk waiting for a free stage, %lld clk in all per stage\n", warp, dbg_n, dbg_wait / max(dbg_n, 1LL), dbg_work / max(dbg_n, 1LL));
+  } else { // ---- consumers ----
+    int it = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      const long long tw0 = (diag & 1024) ? clock64() : 0;
+      tcx::mbar_wait(tcx::smem_u32(&bars[s]), ph);
+      if (diag & 1024) { dbg_wait += clock64() - tw0; ++dbg_n; }
+      const float *stg = reinterpret_cast<const float *>(bulk_smem + (size_t)s * stage_bytes);
+      const size_t base = tile * kBulkTile;
+      if (diag & 256) { // (B200_DIAG 256: timing without the consumers' work)
+        __syncwarp();
+        if (lane == 0) tcx::mbar_arrive(tcx::smem_u32(&bars[kBulkMaxStages + s]));
+        continue;
+      }
+      const int valid = n4 - base < (size_t)kBulkTile ? (int)(n4 - base) : kBulkTile;
+      double gd[kE], snd[PAIR ? kE : 1], ynd[PAIR ? kE : 1];
+#pragma unroll
+      for (int h = 0; h < kPos; ++h) {
+        const int e = (HS == 2 ? wh : h) * 128 + lane * 4;
+        const bool in = e < valid;
+        float4 g4 = *reinterpret_cast<const float4 *>(stg + e);
+        if (!in) g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        gd[4 * h + 0] = g4.x; gd[4 * h + 1] = g4.y; gd[4 * h + 2] = g4.z; gd[4 * h + 3] = g4.w;
+        if constexpr (PAIR) {
+          float4 s4, y4;
+          if (form) {
+            const float4 x4 = *reinterpret_cast<const float4 *>(stg + kBulkTile + e);
+            const float4 xp4 = *reinterpret_cast<const float4 *>(stg + 2 * kBulkTile + e);
+            const float4 gp4 = *reinterpret_cast<const float4 *>(stg + 3 * kBulkTile + e);
+            s4 = make_float4(x4.x - xp4.x, x4.y - xp4.y, x4.z - xp4.z, x4.w - xp4.w);
+            y4 = make_float4(g4.x - gp4.x, g4.y - gp4.y, g4.z - gp4.z, g4.w - gp4.w);
+            if (in && wr == (it & (kDotsWarps - 1))) { // the row groups take turns storing the new pair
+              *reinterpret_cast<float4 *>(a.S + (size_t)w * a.ld + base + e) = s4;
+              *reinterpret_cast<float4 *>(a.Y + (size_t)w * a.ld + base + e) = y4;
+            }
+          } else {
+            s4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * wri) * kBulkTile + e);
+            y4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * wri + 1) * kBulkTile + e);
+          }
+          if (!in) s4 = y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          snd[4 * h + 0] = s4.x; snd[4 * h + 1] = s4.y; snd[4 * h + 2] = s4.z; snd[4 * h + 3] = s4.w;
+          ynd[4 * h + 0] = y4.x; ynd[4 * h + 1] = y4.y; ynd[4 * h + 2] = y4.z; ynd[4 * h + 3] = y4.w;
+        }
+      }
+      if (wr == 0) {
+#pragma unroll
+        for (int q = 0; q < kE; ++q) gg = fma(gd[q], gd[q], gg);
+      }
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int ri = wr + r * kDotsWarps;
+        if (ri >= nrows) break;
+        const bool self = form && ri == wri; // the row being formed: the pair is in registers, its slot was not loaded
+        double sd[kE], yd[kE];
+        if (PAIR && self) {
+#pragma unroll
+          for (int q = 0; q < kE; ++q) { sd[q] = snd[PAIR ? q : 0]; yd[q] = ynd[PAIR ? q : 0]; }
+        } else {
+#pragma unroll
+          for (int h = 0; h < kPos; ++h) {
+            const int e = (HS == 2 ? wh : h) * 128 + lane * 4;
+            const float4 s4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * ri) * kBulkTile + e);
+            const float4 y4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * ri + 1) * kBulkTile + e);
+            sd[4 * h + 0] = s4.x; sd[4 * h + 1] = s4.y; sd[4 * h + 2] = s4.z; sd[4 * h + 3] = s4.w;
+            yd[4 * h + 0] = y4.x; yd[4 * h + 1] = y4.y; yd[4 * h + 2] = y4.z; yd[4 * h + 3] = y4.w;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kE; ++q) {
+          acc[r][0] = fma(sd[q], gd[q], acc[r][0]);
+          acc[r][2] = fma(yd[q], gd[q], acc[r][2]);
+          if constexpr (PAIR) {
+            acc[r][1] = fma(sd[q], ynd[q], acc[r][1]);
+            acc[r][3] = fma(yd[q], snd[q], acc[r][3]);
+            acc[r][4] = fma(yd[q], ynd[q], acc[r][4]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tcx::mbar_arrive(tcx::smem_u32(&bars[kBulkMaxStages + s]));
+      if (diag & 1024) dbg_work += clock64() - tw0;
+    }
+    if ((diag & 1024) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kCW - 1))
+      printf("[dots_bulk] consumer warp %d: %lld stages, %lld clk waiting for a full stage, %lld clk in all per stage\n", warp, dbg_n, dbg_wait / max(dbg_n, 1LL), dbg_work / max(dbg_n, 1LL));
+    // the up to three elements past the last multiple of four: lane 0 of the first warp of every row group, from global memory,
+    // in the CTA that would own the next tile (any fixed choice keeps the partials deterministic)
+    if (n4 < a.n && lane == 0 && wh == 0 && blockIdx.x == (unsigned)(ntiles % gridDim.x)) {
+      for (size_t e = n4; e < a.n; ++e) {
+        const float gf = __ldg(a.g + e);
+        float sf = 0.f, yf = 0.f;
+        if constexpr (PAIR) {
+          if (form) {
+            sf = __ldg(a.x + e) - __ldg(a.x_prev + e);
+            yf = gf - __ldg(a.g_prev + e);
+            if (wr == 0) { a.S[(size_t)w * a.ld + e] = sf; a.Y[(size_t)w * a.ld + e] = yf; }
+          } else {
+            sf = __ldg(a.S + (size_t)w * a.ld + e);
+            yf = __ldg(a.Y + (size_t)w * a.ld + e);
+          }
+        }
+        const double g1 = gf, sn1 = sf, yn1 = yf;
+        if (wr == 0) gg = fma(g1, g1, gg);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const int ri = wr + r * kDotsWarps;
+          if (ri >= nrows) break;
+          const bool self = form && ri == wri;
+          const double s1 = self ? sn1 : (double)__ldg(a.S + (size_t)sh_rows[ri] * a.ld + e);
+          const double y1 = self ? yn1 : (double)__ldg(a.Y + (size_t)sh_rows[ri] * a.ld + e);
+          acc[r][0] = fma(s1, g1, acc[r][0]);
+          acc[r][2] = fma(y1, g1, acc[r][2]);
+          if constexpr (PAIR) {
+            acc[r][1] = fma(s1, yn1, acc[r][1]);
+            acc[r][3] = fma(y1, sn1, acc[r][3]);
+            acc[r][4] = fma(y1, yn1, acc[r][4]);
+          }
+        }
+      }
+    }
+  }
+
+  // one reduction per kernel, partials as dots_body writes them (HS == 2: the two parts of the tile combined in a fixed order)
+  const int ncols = kDotsCols * mp + 1;
+  double *out = a.partials + (size_t)blockIdx.x * ncols;
+  for (int c = tid; c < ncols; c += bulk_threads(HS)) out[c] = 0.0;
+  // one CTA per SM is resident (the ring takes the shared memory), so the grid is one wave; the solve kernel sums `nparts` rows
+  // of partials (sized for the register-staged kernel's two CTAs per SM): the rows without a CTA are zeroed here
+  for (int b = blockIdx.x + gridDim.x; b < nparts; b += gridDim.x)
+    for (int c = tid; c < ncols; c += bulk_threads(HS)) a.partials[(size_t)b * ncols + c] = 0.0;
+  if (warp < kCW) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+      for (int c = 0; c < kDotsCols; ++c) {
+        const double v = warp_sum(acc[r][c]);
+        if (HS == 2) { if (lane == 0) sh_half[((wh * RPW + r) * kDotsWarps + wr) * kDotsCols + c] = v; }
+        else acc[r][c] = v;
+      }
+    }
+    gg = warp_sum(gg);
+    if (lane == 0 && wr == 0) sh_gg[wh] = gg;
+  }
+  __syncthreads();
+  if (HS == 2) {
+    if (tid < RPW * kDotsWarps * kDotsCols) {
+      const int c = tid % kDotsCols, wq = tid / kDotsCols, w_ = wq % kDotsWarps, r = wq / kDotsWarps;
+      const int ri = w_ + r * kDotsWarps;
+      if (ri < nrows) out[sh_rows[ri] * kDotsCols + c] = sh_half[tid] + sh_half[RPW * kDotsWarps * kDotsCols + tid];
+    }
+    if (tid == 0) out[kDotsCols * mp] = sh_gg[0] + sh_gg[1];
+  } else if (warp < kCW) {
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int ri = wr + r * kDotsWarps;
+#pragma unroll
+        for (int c = 0; c < kDotsCols; ++c)
+          if (ri < nrows) out[sh_rows[ri] * kDotsCols + c] = acc[r][c];
+      }
+      if (wr == 0) out[kDotsCols * mp] = gg;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -750,6 +1032,56 @@ int dot_blocks(b200_ctx *ctx, size_t n) { return vec_blocks(n, 2 * ctx->num_sms)
 int launch_lbfgs_dots(const DotsArgs &a0, int mp, int nblocks, cudaStream_t st) {
   B200_REQUIRE(mp <= kMaxSlots, "history size above 256 is not supported");
   const bool pair = a0.mode != DOTS_NONE;
+  // long vectors (the history does not fit L2): the bulk-copy form, rows streamed through a shared-memory ring (1b)
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a0.g) | reinterpret_cast<uintptr_t>(a0.S) | reinterpret_cast<uintptr_t>(a0.Y) |
+                         reinterpret_cast<uintptr_t>(a0.x) | reinterpret_cast<uintptr_t>(a0.x_prev) |
+                         reinterpret_cast<uintptr_t>(a0.g_prev)) & 15u) == 0 && a0.ld % 4 == 0;
+  if (env().dots_bulk && aligned && mp <= kRowsPerLaunch && (long)a0.n >= env().dots_bulk_min &&
+      (a0.mode != DOTS_FORM_PAIR || (a0.x && a0.x_prev && a0.g_prev))) {
+    DotsArgs a = a0;
+    a.row_begin = 0;
+    const int stage_slots = kBulkVecSlots + 2 * mp;
+    const int stages = std::min(kBulkMaxStages, (216 * 1024) / (stage_slots * kBulkSlot));
+    const size_t smem = (size_t)stages * stage_slots * kBulkSlot;
+    const int rpw = ceil_div(mp, kDotsWarps);
+    const int hs = env().dots_bulk == 1 ? 1 : 2; // (B200_DOTS_BULK=1: eight consumer warps with two positions per lane; default sixteen)
+    if (stages >= 2 && rpw >= 1 && rpw <= 4) {
+      auto run = [&](auto kern) -> int {
+        static bool attr_set[5][2][3] = {}; // (the instantiations share one pointer type, hence one copy of this lambda)
+        if (!attr_set[rpw][pair][hs]) {
+          B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+          attr_set[rpw][pair][hs] = true;
+        }
+        static int sms = 0;
+        if (!sms) {
+          int dev = 0;
+          B200_CUDA(cudaGetDevice(&dev));
+          B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        B200_CUDA(launch_ex(kern, dim3(std::min(nblocks, sms)), dim3(bulk_threads(hs)), smem, st, 1, a, stages, stage_slots, nblocks, env().diag));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        B200_CUDA(cudaGetLastError());
+        return B200_OK;
+      };
+#define B200_BULK_CASE(R)                                                      \
+  case R:                                                                      \
+    if (hs == 2) {                                                             \
+      if (pair) return run(lbfgs_dots_bulk_kernel<R, true, 2>);                \
+      return run(lbfgs_dots_bulk_kernel<R, false, 2>);                         \
+    }                                                                          \
+    if (pair) return run(lbfgs_dots_bulk_kernel<R, true, 1>);                  \
+    return run(lbfgs_dots_bulk_kernel<R, false, 1>);
+      switch (rpw) {
+        B200_BULK_CASE(1)
+        B200_BULK_CASE(2)
+        B200_BULK_CASE(3)
+        B200_BULK_CASE(4)
+      default:
+        break;
+      }
+#undef B200_BULK_CASE
+    }
+  }
   // the row count is device state (<= mp); launches beyond the live rows exit after the staging loop
   for (int row_begin = 0; row_begin < mp; row_begin += kRowsPerLaunch) {
     DotsArgs a = a0;
@@ -848,6 +1180,17 @@ int launch_lbfgs_direction(b200_ctx *ctx, const DotsArgs &da0, const SolveArgs &
 }
 
 int launch_lbfgs_apply(const ApplyArgs &a, int nblocks, cudaStream_t st) {
+  // a grid-stride kernel: never more CTAs than are resident at once (4 per SM were asked for, 3 fit at 77 registers — the 148 CTAs
+  // of a second wave ran at a third of the occupancy)
+  static int resident = 0;
+  if (!resident) {
+    int dev = 0, sms = 0, per_sm = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbfgs_apply_kernel, 256, 0));
+    resident = std::max(1, per_sm * sms);
+  }
+  nblocks = std::min(nblocks, resident);
   B200_LAUNCH(lbfgs_apply_kernel, nblocks, 256, 0, st, a);
   return B200_OK;
 }
