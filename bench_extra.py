@@ -235,6 +235,11 @@ def run(args, rank, local_rank, world):
                                         "avg_launch_us": t_dir * 1e6, "alg_bytes": dir_bytes, "kernels": dir_keys,
                                         "share_of_step": sum(rep[k][1] for k in dir_keys) / tot_prof,
                                         "ring_full": bool(warmup + steps >= memory),
+                                        # the two passes on their own: history pass (2m rows + g, x, x_prev, g_prev read, the new
+                                        # pair written), output pass (2m rows + g, x read; p, x_prev, x written)
+                                        "passes": {k: {"avg_launch_us": 1e3 * rep[k][1] / rep[k][0], "alg_bytes": b * n_local * 4,
+                                                       "GB/s": b * n_local * 4 / (rep[k][1] / rep[k][0] / 1e3) / 1e9}
+                                                   for k, b in (("lbfgs_dots", 2.0 * memory + 6), ("lbfgs_apply", 2.0 * memory + 5)) if k in rep},
                                         "note": "history ring of k = m pairs streamed twice (Gram / projection pass, output pass); "
                                                 "the bytes assume a full ring (warm-up >= m iterations: ring_full) — with fewer "
                                                 "pairs in the ring the passes move fewer bytes than alg_bytes and the rate is overstated"}

@@ -301,10 +301,9 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
       }
     }
     const uint32_t nact = (uint32_t)__popc(__ballot_sync(0xffffffffu, active));
-    int it = 0;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+    int s = 0;        // stage and its phase as running counters (no division per stage)
+    uint32_t ph = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long tw0 = (diag & 1024) ? clock64() : 0;
       tcx::mbar_wait(tcx::smem_u32(&bars[kBulkMaxStages + s]), ph ^ 1u);
       if (diag & 1024) { dbg_wait += clock64() - tw0; ++dbg_n; }
@@ -315,76 +314,81 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
       __syncwarp();
       if (active) tcx::bulk_load_1d(smem0 + (uint32_t)(s * stage_bytes + c * kBulkSlot), src + base, bytes, full);
       if (diag & 1024) { __syncwarp(); dbg_work += clock64() - tw0; }
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
     if ((diag & 1024) && blockIdx.x == 0 && lane == 0)
       printf("[dots_bulk] producer warp %d: %lld stages, %lld clk waiting for a free stage, %lld clk in all per stage\n", warp, dbg_n, dbg_wait / max(dbg_n, 1LL), dbg_work / max(dbg_n, 1LL));
   } else { // ---- consumers ----
-    int it = 0;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+    // this lane's element offset inside a row chunk, and whether this warp holds the row being formed (its pair goes through the
+    // row's own — never loaded — slots of the stage, so that the row loop below has ONE form)
+    const int e0 = (HS == 2 ? wh : 0) * 128 + lane * 4;
+    const bool owner = form && wri >= 0 && (wri % kDotsWarps) == wr;
+    int s = 0, turn = 0; // stage, its phase, the row group whose turn it is to store the new pair: running counters
+    uint32_t ph = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long tw0 = (diag & 1024) ? clock64() : 0;
       tcx::mbar_wait(tcx::smem_u32(&bars[s]), ph);
       if (diag & 1024) { dbg_wait += clock64() - tw0; ++dbg_n; }
-      const float *stg = reinterpret_cast<const float *>(bulk_smem + (size_t)s * stage_bytes);
+      float *stg = reinterpret_cast<float *>(bulk_smem + (size_t)s * stage_bytes) + e0;
       const size_t base = tile * kBulkTile;
       if (diag & 256) { // (B200_DIAG 256: timing without the consumers' work)
         __syncwarp();
         if (lane == 0) tcx::mbar_arrive(tcx::smem_u32(&bars[kBulkMaxStages + s]));
+        if (++s == stages) { s = 0; ph ^= 1u; }
         continue;
       }
       const int valid = n4 - base < (size_t)kBulkTile ? (int)(n4 - base) : kBulkTile;
       double gd[kE], snd[PAIR ? kE : 1], ynd[PAIR ? kE : 1];
 #pragma unroll
       for (int h = 0; h < kPos; ++h) {
-        const int e = (HS == 2 ? wh : h) * 128 + lane * 4;
-        const bool in = e < valid;
-        float4 g4 = *reinterpret_cast<const float4 *>(stg + e);
-        if (!in) g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        gd[4 * h + 0] = g4.x; gd[4 * h + 1] = g4.y; gd[4 * h + 2] = g4.z; gd[4 * h + 3] = g4.w;
+        float *sp = stg + h * 128;
+        float4 g4 = *reinterpret_cast<const float4 *>(sp);
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), y4 = s4;
         if constexpr (PAIR) {
-          float4 s4, y4;
           if (form) {
-            const float4 x4 = *reinterpret_cast<const float4 *>(stg + kBulkTile + e);
-            const float4 xp4 = *reinterpret_cast<const float4 *>(stg + 2 * kBulkTile + e);
-            const float4 gp4 = *reinterpret_cast<const float4 *>(stg + 3 * kBulkTile + e);
+            const float4 x4 = *reinterpret_cast<const float4 *>(sp + kBulkTile);
+            const float4 xp4 = *reinterpret_cast<const float4 *>(sp + 2 * kBulkTile);
+            const float4 gp4 = *reinterpret_cast<const float4 *>(sp + 3 * kBulkTile);
             s4 = make_float4(x4.x - xp4.x, x4.y - xp4.y, x4.z - xp4.z, x4.w - xp4.w);
             y4 = make_float4(g4.x - gp4.x, g4.y - gp4.y, g4.z - gp4.z, g4.w - gp4.w);
-            if (in && wr == (it & (kDotsWarps - 1))) { // the row groups take turns storing the new pair
-              *reinterpret_cast<float4 *>(a.S + (size_t)w * a.ld + base + e) = s4;
-              *reinterpret_cast<float4 *>(a.Y + (size_t)w * a.ld + base + e) = y4;
-            }
           } else {
-            s4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * wri) * kBulkTile + e);
-            y4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * wri + 1) * kBulkTile + e);
+            s4 = *reinterpret_cast<const float4 *>(sp + (kBulkVecSlots + 2 * wri) * kBulkTile);
+            y4 = *reinterpret_cast<const float4 *>(sp + (kBulkVecSlots + 2 * wri + 1) * kBulkTile);
           }
-          if (!in) s4 = y4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (valid < kBulkTile && e0 + h * 128 >= valid) g4 = s4 = y4 = make_float4(0.f, 0.f, 0.f, 0.f); // (the short last tile only)
+        if constexpr (PAIR) {
+          if (form) {
+            if (wr == turn && e0 + h * 128 < valid) { // the row groups take turns storing the new pair
+              *reinterpret_cast<float4 *>(a.S + (size_t)w * a.ld + base + e0 + h * 128) = s4;
+              *reinterpret_cast<float4 *>(a.Y + (size_t)w * a.ld + base + e0 + h * 128) = y4;
+            }
+            if (owner) {
+              *reinterpret_cast<float4 *>(sp + (kBulkVecSlots + 2 * wri) * kBulkTile) = s4;
+              *reinterpret_cast<float4 *>(sp + (kBulkVecSlots + 2 * wri + 1) * kBulkTile) = y4;
+            }
+          }
           snd[4 * h + 0] = s4.x; snd[4 * h + 1] = s4.y; snd[4 * h + 2] = s4.z; snd[4 * h + 3] = s4.w;
           ynd[4 * h + 0] = y4.x; ynd[4 * h + 1] = y4.y; ynd[4 * h + 2] = y4.z; ynd[4 * h + 3] = y4.w;
         }
+        gd[4 * h + 0] = g4.x; gd[4 * h + 1] = g4.y; gd[4 * h + 2] = g4.z; gd[4 * h + 3] = g4.w;
       }
+      if (owner) __syncwarp(); // (each lane reads back exactly what it wrote; this orders the two for the compiler as well)
       if (wr == 0) {
 #pragma unroll
         for (int q = 0; q < kE; ++q) gg = fma(gd[q], gd[q], gg);
       }
+      const float *rowp = stg + (kBulkVecSlots + 2 * wr) * kBulkTile;
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
-        const int ri = wr + r * kDotsWarps;
-        if (ri >= nrows) break;
-        const bool self = form && ri == wri; // the row being formed: the pair is in registers, its slot was not loaded
+        if (wr + r * kDotsWarps >= nrows) break;
         double sd[kE], yd[kE];
-        if (PAIR && self) {
 #pragma unroll
-          for (int q = 0; q < kE; ++q) { sd[q] = snd[PAIR ? q : 0]; yd[q] = ynd[PAIR ? q : 0]; }
-        } else {
-#pragma unroll
-          for (int h = 0; h < kPos; ++h) {
-            const int e = (HS == 2 ? wh : h) * 128 + lane * 4;
-            const float4 s4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * ri) * kBulkTile + e);
-            const float4 y4 = *reinterpret_cast<const float4 *>(stg + (kBulkVecSlots + 2 * ri + 1) * kBulkTile + e);
-            sd[4 * h + 0] = s4.x; sd[4 * h + 1] = s4.y; sd[4 * h + 2] = s4.z; sd[4 * h + 3] = s4.w;
-            yd[4 * h + 0] = y4.x; yd[4 * h + 1] = y4.y; yd[4 * h + 2] = y4.z; yd[4 * h + 3] = y4.w;
-          }
+        for (int h = 0; h < kPos; ++h) {
+          const float4 s4 = *reinterpret_cast<const float4 *>(rowp + r * (2 * kDotsWarps * kBulkTile) + h * 128);
+          const float4 y4 = *reinterpret_cast<const float4 *>(rowp + r * (2 * kDotsWarps * kBulkTile) + kBulkTile + h * 128);
+          sd[4 * h + 0] = s4.x; sd[4 * h + 1] = s4.y; sd[4 * h + 2] = s4.z; sd[4 * h + 3] = s4.w;
+          yd[4 * h + 0] = y4.x; yd[4 * h + 1] = y4.y; yd[4 * h + 2] = y4.z; yd[4 * h + 3] = y4.w;
         }
 #pragma unroll
         for (int q = 0; q < kE; ++q) {
@@ -400,6 +404,8 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
       __syncwarp();
       if (lane == 0) tcx::mbar_arrive(tcx::smem_u32(&bars[kBulkMaxStages + s]));
       if (diag & 1024) dbg_work += clock64() - tw0;
+      if (++s == stages) { s = 0; ph ^= 1u; }
+      turn = (turn + 1) & (kDotsWarps - 1);
     }
     if ((diag & 1024) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kCW - 1))
       printf("[dots_bulk] consumer warp %d: %lld stages, %lld clk waiting for a full stage, %lld clk in all per stage\n", warp, dbg_n, dbg_wait / max(dbg_n, 1LL), dbg_work / max(dbg_n, 1LL));

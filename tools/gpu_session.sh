@@ -83,4 +83,10 @@ if has memcheck; then
   timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_case.py > $OUT/${TAG}_memcheck.log 2>&1
   echo "memcheck rc=$?"; tail -12 $OUT/${TAG}_memcheck.log
 fi
+if has ncuc5; then  # the direction's two passes at configs[4] size with the ring full (launches 21/22 of each kernel), full metric set
+  CMD="python bench.py --config c5 --samples 8192 --steps 2 --warmup 21 --no-cpu-baseline --no-reference-cuda"
+  timeout 300 $CMD > $OUT/${TAG}_ncuc5_plain.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lbfgs_dots_bulk_kernel|lbfgs_apply_kernel" -s 42 -c 4 -o $OUT/${TAG}_c5dir $CMD > $OUT/${TAG}_ncuc5.log 2>&1
+  echo "ncuc5 rc=$?"; tail -3 $OUT/${TAG}_ncuc5.log
+fi
 echo "session $TAG done"
