@@ -77,7 +77,7 @@ struct EnvFlags {
   int diag = 0;                    // B200_DIAG: timing experiments of the fp16 kernels (parts switched off; results are wrong)
   int tc_mask = 7;                 // B200_TC_MASK: bit0 FWD, bit1 DX, bit2 DW on the tensor cores; bit3 / bit4 see gemm_tc.cu
   int dw_bn = 0;                   // B200_DW_BN: 128 / 256, 0 = by precision mode
-  int dots_bulk = 2;               // B200_DOTS_BULK=0: long history passes on the register-staged dots kernel instead of the bulk-copy ring (1: 8 consumer warps, 2: 16)
+  int dots_bulk = 3;               // B200_DOTS_BULK: history pass of long vectors. 0 register-staged kernel; bulk-copy ring with 1: 8 consumer warps, 2: 16, 3 (default): 16 + the tile's vectors converted once per CTA
   long dots_bulk_min = 1L << 20;   // B200_DOTS_BULK_MIN: shortest vector that takes the bulk-copy dots kernel
   long p2p_spin_limit = 0;         // B200_P2P_SPIN_LIMIT: polls before p2p_reduce_kernel gives up on a peer (0 = default)
 };

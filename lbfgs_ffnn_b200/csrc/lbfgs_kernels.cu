@@ -225,7 +225,7 @@ constexpr int kBulkMaxStages = 8;
 constexpr int kBulkVecSlots = 4;                // g, x, x_prev, g_prev
 __host__ __device__ constexpr int bulk_threads(int hs) { return kDotsThreads * hs + 32 * kBulkProducers; }
 
-template <int RPW, bool PAIR, int HS>
+template <int RPW, bool PAIR, int HS, bool SHARE = false>
 __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(const DotsArgs a, int stages, int stage_slots, int nparts, int diag) {
   pdl_enter(); // programmatic dependent launch: this grid may start while its predecessor drains (common.cuh)
   constexpr int kCW = kDotsWarps * HS;  // consumer warps
@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
   __shared__ int sh_rows[kMaxSlots];
   __shared__ int sh_nrows, sh_w, sh_wri;
   __shared__ double sh_half[HS == 2 ? 2 * RPW * kDotsWarps * kDotsCols : 1];
-  __shared__ double sh_gg[2];
+  __shared__ double sh_gg[kDotsWarps * HS];
+  // SHARE: g / s_new / y_new of the tile being consumed as doubles, converted once per CTA (two buffers, see the consumers)
+  __shared__ __align__(16) double vec_d[SHARE ? 2 * 3 * kBulkTile : 2];
+  static_assert(!SHARE || HS == 2, "the shared conversion is written for sixteen consumer warps");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = warp % kDotsWarps, wh = warp / kDotsWarps; // consumers: row group, part of the tile
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
     // row's own — never loaded — slots of the stage, so that the row loop below has ONE form)
     const int e0 = (HS == 2 ? wh : 0) * 128 + lane * 4;
     const bool owner = form && wri >= 0 && (wri % kDotsWarps) == wr;
-    int s = 0, turn = 0; // stage, its phase, the row group whose turn it is to store the new pair: running counters
+    int s = 0, turn = 0, par = 0; // stage, its phase, the row group whose turn it is to store the new pair, (SHARE) the buffer: running counters
     uint32_t ph = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long tw0 = (diag & 1024) ? clock64() : 0;
@@ -339,6 +342,53 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
       }
       const int valid = n4 - base < (size_t)kBulkTile ? (int)(n4 - base) : kBulkTile;
       double gd[kE], snd[PAIR ? kE : 1], ynd[PAIR ? kE : 1];
+      if constexpr (SHARE) {
+        // One conversion per element and CTA instead of one per element and row group: F2F.F64.F32 runs at 16 lanes per clock and SM
+        // and bounds this kernel at the power-limited clock (576 -> 408 per stage). Thread t < 256 takes g and s_new of element t,
+        // thread 256 + t y_new; the doubles go to a buffer laid out so that a lane reads its four elements with two conflict-free
+        // 16-byte loads per vector. Two buffers: a warp that runs ahead writes the other one, and cannot come back to this one
+        // before every warp has passed the next stage's barrier, i.e. has finished reading it.
+        float *st0 = stg - e0;
+        const int e = tid & (kBulkTile - 1);
+        const bool in = e < valid;
+        const int idx = ((((e >> 7) * 2 + ((e & 3) >> 1)) * 32 + ((e & 127) >> 2)) << 1) + (e & 1);
+        double *vd = vec_d + par * (3 * kBulkTile);
+        const float gf = in ? st0[e] : 0.f;
+        if (tid < kBulkTile) {
+          vd[idx] = gf;
+          gg = fma((double)gf, (double)gf, gg);
+          if constexpr (PAIR) {
+            float sf = form ? st0[kBulkTile + e] - st0[2 * kBulkTile + e] : st0[(kBulkVecSlots + 2 * wri) * kBulkTile + e];
+            if (!in) sf = 0.f;
+            if (form) {
+              if (in) a.S[(size_t)w * a.ld + base + e] = sf;
+              st0[(kBulkVecSlots + 2 * wri) * kBulkTile + e] = sf; // (the formed row's own, never loaded, slot: one form of the row loop)
+            }
+            vd[kBulkTile + idx] = sf;
+          }
+        } else if constexpr (PAIR) {
+          float yf = form ? gf - st0[3 * kBulkTile + e] : st0[(kBulkVecSlots + 2 * wri + 1) * kBulkTile + e];
+          if (!in) yf = 0.f;
+          if (form) {
+            if (in) a.Y[(size_t)w * a.ld + base + e] = yf;
+            st0[(kBulkVecSlots + 2 * wri + 1) * kBulkTile + e] = yf;
+          }
+          vd[2 * kBulkTile + idx] = yf;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kDotsThreads * HS) : "memory");
+        const double2 *v2 = reinterpret_cast<const double2 *>(vd) + (wh * 2) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double2 g2 = v2[j * 32];
+          gd[2 * j] = g2.x; gd[2 * j + 1] = g2.y;
+          if constexpr (PAIR) {
+            const double2 s2 = v2[kBulkTile / 2 + j * 32], y2 = v2[kBulkTile + j * 32];
+            snd[2 * j] = s2.x; snd[2 * j + 1] = s2.y;
+            ynd[2 * j] = y2.x; ynd[2 * j + 1] = y2.y;
+          }
+        }
+        par ^= 1;
+      } else {
 #pragma unroll
       for (int h = 0; h < kPos; ++h) {
         float *sp = stg + h * 128;
@@ -377,6 +427,7 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
       if (wr == 0) {
 #pragma unroll
         for (int q = 0; q < kE; ++q) gg = fma(gd[q], gd[q], gg);
+      }
       }
       const float *rowp = stg + (kBulkVecSlots + 2 * wr) * kBulkTile;
 #pragma unroll
@@ -464,8 +515,8 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
         else acc[r][c] = v;
       }
     }
-    gg = warp_sum(gg);
-    if (lane == 0 && wr == 0) sh_gg[wh] = gg;
+    gg = warp_sum(gg); // (zero in the warps that do not accumulate it)
+    if (lane == 0) sh_gg[warp] = gg;
   }
   __syncthreads();
   if (HS == 2) {
@@ -474,7 +525,11 @@ __global__ void __launch_bounds__(bulk_threads(HS), 1) lbfgs_dots_bulk_kernel(co
       const int ri = w_ + r * kDotsWarps;
       if (ri < nrows) out[sh_rows[ri] * kDotsCols + c] = sh_half[tid] + sh_half[RPW * kDotsWarps * kDotsCols + tid];
     }
-    if (tid == 0) out[kDotsCols * mp] = sh_gg[0] + sh_gg[1];
+    if (tid == 0) {
+      double sgg = 0.0;
+      for (int i = 0; i < kCW; ++i) sgg += sh_gg[i]; // fixed order
+      out[kDotsCols * mp] = sgg;
+    }
   } else if (warp < kCW) {
     if (lane == 0) {
 #pragma unroll
@@ -1047,16 +1102,17 @@ int launch_lbfgs_dots(const DotsArgs &a0, int mp, int nblocks, cudaStream_t st) 
     DotsArgs a = a0;
     a.row_begin = 0;
     const int stage_slots = kBulkVecSlots + 2 * mp;
-    const int stages = std::min(kBulkMaxStages, (216 * 1024) / (stage_slots * kBulkSlot));
+    const int stages = std::min(kBulkMaxStages, (204 * 1024) / (stage_slots * kBulkSlot)); // (+ 13.5 KB static with the shared conversion)
     const size_t smem = (size_t)stages * stage_slots * kBulkSlot;
     const int rpw = ceil_div(mp, kDotsWarps);
     const int hs = env().dots_bulk == 1 ? 1 : 2; // (B200_DOTS_BULK=1: eight consumer warps with two positions per lane; default sixteen)
+    const bool share = env().dots_bulk >= 3;     // (default; B200_DOTS_BULK=2: every row group converts g / s_new / y_new itself)
     if (stages >= 2 && rpw >= 1 && rpw <= 4) {
       auto run = [&](auto kern) -> int {
-        static bool attr_set[5][2][3] = {}; // (the instantiations share one pointer type, hence one copy of this lambda)
-        if (!attr_set[rpw][pair][hs]) {
-          B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-          attr_set[rpw][pair][hs] = true;
+        static bool attr_set[5][2][4] = {}; // (the instantiations share one pointer type, hence one copy of this lambda)
+        if (!attr_set[rpw][pair][hs + share]) {
+          B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+          attr_set[rpw][pair][hs + share] = true;
         }
         static int sms = 0;
         if (!sms) {
@@ -1071,6 +1127,10 @@ int launch_lbfgs_dots(const DotsArgs &a0, int mp, int nblocks, cudaStream_t st) 
       };
 #define B200_BULK_CASE(R)                                                      \
   case R:                                                                      \
+    if (share) {                                                               \
+      if (pair) return run(lbfgs_dots_bulk_kernel<R, true, 2, true>);          \
+      return run(lbfgs_dots_bulk_kernel<R, false, 2, true>);                   \
+    }                                                                          \
     if (hs == 2) {                                                             \
       if (pair) return run(lbfgs_dots_bulk_kernel<R, true, 2>);                \
       return run(lbfgs_dots_bulk_kernel<R, false, 2>);                         \

@@ -42,9 +42,11 @@ class _Env:
         api.reload_env()
 
 
-# the two forms of the bulk kernel (eight consumer warps with two 16-byte positions per lane; sixteen with one) and the register-staged one
+# the forms of the bulk kernel (eight consumer warps with two 16-byte positions per lane; sixteen with one; sixteen with the shared
+# conversion of the tile's vectors) and the register-staged one
 _VARIANTS = (("bulk", dict(B200_DOTS_BULK="1", B200_DOTS_BULK_MIN="0")), ("bulk16", dict(B200_DOTS_BULK="2", B200_DOTS_BULK_MIN="0")),
-             ("staged", dict(B200_DOTS_BULK="0", B200_DOTS_BULK_MIN=None)))
+             ("bulk16s", dict(B200_DOTS_BULK="3", B200_DOTS_BULK_MIN="0")),  # g / s_new / y_new converted once per CTA
+             ("staged", dict(B200_DOTS_BULK="0", B200_DOTS_BULK_MIN=None)))  # (bulk16s is the default form)
 
 
 def _history(rs, k, n):
@@ -74,7 +76,7 @@ def test_bulk_dots_direction_matches_the_oracle(handle, oracle, policy, k, n):
     for name, (p, gdp) in res.items():
         assert rel_l2(p, p_o) <= 1e-6, (name, rel_l2(p, p_o))
         assert abs(gdp - gdp_o) <= 1e-5 * abs(gdp_o), (name, gdp, gdp_o)
-    for name in ("bulk", "bulk16"):
+    for name in ("bulk", "bulk16", "bulk16s"):
         assert rel_l2(res[name][0], res["staged"][0]) <= 1e-6
         assert abs(res[name][1] - res["staged"][1]) <= 1e-9 * abs(gdp_o)
 
@@ -104,7 +106,8 @@ def test_lbfgs_with_the_bulk_dots_kernel_follows_the_staged_one_and_the_oracle(h
     lb, ls = runs["bulk"][0], runs["staged"][0]
     assert len(lb) == len(ls) == len(runs["bulk16"][0]) == iters
     assert np.allclose(lb, ls, rtol=2e-5), np.max(np.abs(lb - ls) / ls)
-    assert np.allclose(runs["bulk16"][0], ls, rtol=2e-5)
+    assert np.allclose(runs["bulk16"][0], ls, rtol=2e-5) and np.allclose(runs["bulk16s"][0], ls, rtol=2e-5)
+    assert len(runs["bulk16s"][0]) == iters
     ref = onet.lbfgs(w, X, T, m=m, max_iters=iters, tol=0.0, policy="cuda")
     # (fp32 and fp64 trajectories part company slowly: 2e-3 over the first ten iterations, 1e-2 over all 25)
     assert np.allclose(lb[:10], ref["loss"][:10], rtol=2e-3) and np.allclose(lb, ref["loss"], rtol=1e-2), (lb, ref["loss"])
