@@ -101,10 +101,21 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
     gdst[j] = s;
     g2 += (double)s * (double)s;
   };
-  // (2) first: the long poles start at once. Uniform per CTA: the class of a group is that of its first element's layer.
-  for (unsigned long long it = blockIdx.x; it < ngroups; it += gridDim.x) {
-    const unsigned long long grp = ngroups - 1 - it; // (from the END: the last layer's elements have the most slices)
-    if (p.L[layer_of(grp * 32)].splits <= kThinSplits) continue;
+  // (2) first: the long poles start at once. Uniform per CTA: the class of a group is that of its first element's layer. Only the
+  // groups of the layers with more than kThinSplits slices are visited: a scan of ALL groups with a layer look-up each (eight warps
+  // per CTA, 626 000 groups at 2·10⁷ elements) was two thirds of this kernel's 0.5 ms at BASELINE configs[4] (ncu source view).
+  // The fat groups of all layers are dealt round-robin over the CTAs as ONE list (a CTA rarely gets two of these long poles).
+  unsigned long long dealt = 0;
+  for (int lf = p.nl - 1; lf >= 0; --lf) { // (from the END: the last layer's elements have the most slices)
+    if (p.L[lf].splits <= kThinSplits) continue;
+    const unsigned long long g_lo = (p.L[lf].off + 31) / 32; // first group whose FIRST element lies in this layer
+    unsigned long long g_hi = (p.L[lf].off + p.L[lf].size + 31) / 32;
+    if (g_hi > ngroups) g_hi = ngroups;
+    if (g_hi <= g_lo) continue;
+    const unsigned long long first = (blockIdx.x + gridDim.x - dealt % gridDim.x) % gridDim.x; // this CTA's first group of the layer
+    dealt += g_hi - g_lo;
+  for (unsigned long long it = first; g_lo + it < g_hi; it += gridDim.x) {
+    const unsigned long long grp = g_hi - 1 - it;
     const unsigned long long j0 = grp * 32 + lane;
     const unsigned long long j = j0 < p.n ? j0 : p.n - 1; // (lanes past the end repeat the last element and are not emitted)
     double acc = 0.0;
@@ -124,6 +135,7 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
     __syncthreads();
     if (warp == 0 && j0 < p.n)
       emit(j, ((sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane])) + ((sh[4][lane] + sh[5][lane]) + (sh[6][lane] + sh[7][lane])));
+  }
   }
   // (1)
   for (unsigned long long grp = (unsigned long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (unsigned long long)gridDim.x * 8) {
