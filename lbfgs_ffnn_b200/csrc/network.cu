@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
   }
   }
   // (1)
-  for (unsigned long long grp = (unsigned long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (unsigned long long)gridDim.x * 8) {
-    if (p.L[layer_of(grp * 32)].splits > kThinSplits) continue; // (warp-uniform)
+  auto do_group = [&](unsigned long long grp) { // (grp is warp-uniform)
+    if (p.L[layer_of(grp * 32)].splits > kThinSplits) return;
     const unsigned long long j0 = grp * 32 + lane;
     const bool live = j0 < p.n;
     const unsigned long long j = live ? j0 : p.n - 1; // (every lane stays in the loop: the warp-level barrier below needs them all)
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
       for (int u = 0; u < 4; ++u) t[u] = ldg_pinned(u < L.splits ? src + (unsigned long long)u * L.stride : p.zero);
       acc = ((double)t[0] + (double)t[1]) + ((double)t[2] + (double)t[3]); // (the tree of the general form: same bits)
       if (live) emit(j, acc);
-      continue;
+      return;
     }
     for (int sp0 = 0; sp0 < L.splits; sp0 += kThinSplits) {
       float t[kThinSplits];
@@ -162,8 +162,40 @@ __global__ void __launch_bounds__(256) finalize_grad_kernel(const FinParams p) {
 #pragma unroll
       for (int u = 0; u < kThinSplits; u += 8) acc = sum8_pinned(acc, t[u], t[u + 1], t[u + 2], t[u + 3], t[u + 4], t[u + 5], t[u + 6], t[u + 7]);
     }
-    if (!live) continue;
-    emit(j, acc);
+    if (live) emit(j, acc);
+  };
+  if (p.n < (1ull << 18)) {
+    for (unsigned long long grp = (unsigned long long)blockIdx.x * 8 + warp; grp < ngroups; grp += (unsigned long long)gridDim.x * 8) do_group(grp);
+  } else {
+    // long gradients (wide layers: 2·10⁷ elements at BASELINE configs[4], one slice per layer): a warp takes FOUR consecutive groups;
+    // when they lie in one layer with at most four slices every load of the four is in flight at once (one group per warp and round
+    // trip is latency-bound at ~1 TB/s). Per-element sums as in do_group: same bits.
+    const unsigned long long nquads = (p.n + 127) / 128;
+    for (unsigned long long quad = (unsigned long long)blockIdx.x * 8 + warp; quad < nquads; quad += (unsigned long long)gridDim.x * 8) {
+      const unsigned long long first = quad * 128, lastj = first + 127 < p.n ? first + 127 : p.n - 1;
+      const int l = layer_of(first);
+      if (l != layer_of(lastj) || p.L[l].splits > 4) { // (warp-uniform)
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g)
+          if (quad * 4 + g < ngroups) do_group(quad * 4 + g);
+        continue;
+      }
+      const FinLayer &L = p.L[l];
+      float t[4][4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const unsigned long long j0 = first + g * 32 + lane, j = j0 < p.n ? j0 : p.n - 1;
+        const float *src = L.part + (j - L.off);
+        t[g][0] = ldg_pinned(src);
+#pragma unroll
+        for (int u = 1; u < 4; ++u) t[g][u] = L.splits > 1 ? ldg_pinned(u < L.splits ? src + (unsigned long long)u * L.stride : p.zero) : 0.0f;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const unsigned long long j0 = first + g * 32 + lane;
+        if (j0 < p.n) emit(j0, ((double)t[g][0] + (double)t[g][1]) + ((double)t[g][2] + (double)t[g][3]));
+      }
+    }
   }
   const double a = block_sum(g2, red);
   const double b = block_sum(w2, red);
