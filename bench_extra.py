@@ -243,6 +243,21 @@ def run(args, rank, local_rank, world):
                                         "note": "history ring of k = m pairs streamed twice (Gram / projection pass, output pass); "
                                                 "the bytes assume a full ring (warm-up >= m iterations: ring_full) — with fewer "
                                                 "pairs in the ring the passes move fewer bytes than alg_bytes and the rate is overstated"}
+            # measured DRAM bytes of the two passes (one `ncu --set full` capture of this workload's direction on one GPU, committed with
+            # the hash of the kernel source it was taken from): reported only while the source still hashes to that and the ring is full
+            roofs["lbfgs_direction"]["traffic"] = None
+            try:
+                import hashlib
+                cap = json.load(open(os.path.join(ROOT, "profiles", "r02_c5_direction_ncu_full_summary.json")))
+                ok = all(hashlib.sha1(open(os.path.join(ROOT, f), "rb").read()).hexdigest()[:12] == h for f, h in cap.get("sources", []))
+                if ok and cap.get("sources") and world == 1 and warmup + steps >= memory:
+                    per = {}
+                    for e in cap["launches"]:
+                        per.setdefault("lbfgs_dots" if "dots" in e["kernel"] else "lbfgs_apply", []).append(e["dram_bytes"])
+                    roofs["lbfgs_direction"]["traffic"] = int(sum(sum(v) / len(v) for v in per.values()))
+                    roofs["lbfgs_direction"]["traffic_source"] = "profiles/r02_c5_direction_ncu_full_summary.json"
+            except Exception:
+                pass
         dom = max(roofs, key=lambda k: roofs[k]["share_of_step"]) if roofs else None
         line.update({"metric": "lbfgs_iters_per_sec", "value": steps / (ms / 1e3), "unit": "iterations/s", "ms_per_step": ms / steps,
                      "scaling": "strong", "gpu_launches": launches,

@@ -30,7 +30,10 @@ for e in out:
         b = e["dram_read"] * sc[e["dram_read_unit"]] + e["dram_write"] * sc[e["dram_write_unit"]]
         e["dram_bytes"] = int(b)
         e["dram_GB_per_s"] = round(b / (e["duration"] * ts[e["duration_unit"]]) / 1e9, 1)
-json.dump(dict(command="ncu --set full --clock-control none --import-source on -k regex:lbfgs_dots_bulk_kernel|lbfgs_apply_kernel -s 42 -c 4 "
+import hashlib
+sha = hashlib.sha1(open(os.path.join(ROOT, "lbfgs_ffnn_b200", "csrc", "lbfgs_kernels.cu"), "rb").read()).hexdigest()[:12]
+json.dump(dict(sources=[["lbfgs_ffnn_b200/csrc/lbfgs_kernels.cu", sha]],  # bench_extra.py reports `traffic` only while this still matches
+               command="ncu --set full --clock-control none --import-source on -k regex:lbfgs_dots_bulk_kernel|lbfgs_apply_kernel -s 42 -c 4 "
                        "python bench.py --config c5 --samples 8192 --steps 2 --warmup 21 --no-cpu-baseline --no-reference-cuda",
                workload="direction of L-BFGS m = 20 on 784-4096-4096-10 (n = 20 037 642), ring full: history pass (dots) and output pass (apply)",
                note="cold-cache, serialised launches under the profiler: rates are the profiler's, the bench line's are CUDA events",
